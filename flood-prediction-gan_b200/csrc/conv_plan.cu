@@ -1,0 +1,626 @@
+// Planners: convolution geometry -> implicit-GEMM descriptors, plus weight packing and the split-K wgrad reduce.
+// Pure host logic except for the small pack / reduce kernels at the bottom.
+#include <string.h>
+
+#include "common.cuh"
+#include "host_util.h"
+
+namespace fpg {
+
+static int pick_cblk(int c) {
+  if (c % 64 == 0) return 64;
+  if (c == 32) return 32;
+  if (c == 16) return 16;
+  return -1;
+}
+
+static int pow2_at_least(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// 5-D TMA view (c, x, plane, y, n) of an activation buffer (interior + halo). stride 2 folds the x parity into
+// dim 0 and the y parity into dim 2 so that a box of consecutive coordinates walks every second pixel.
+static void make_act_view(const fpg_act* a, int stride, int box_c, int tile_w, int tile_h, fpg_tmap* m) {
+  const uint64_t hp = a->h + 2 * a->halo, wp = a->w + 2 * a->halo, cs = a->c_stride;
+  memset(m, 0, sizeof(*m));
+  m->base = a->data;
+  m->rank = 5;
+  m->swizzle_bytes = box_c * 2;
+  if (stride == 1) {
+    m->dims[0] = a->c;
+    m->dims[1] = wp;
+    m->dims[2] = 1;
+    m->dims[3] = hp;
+    m->dims[4] = a->n;
+    m->strides[0] = cs * 2;
+    m->strides[1] = wp * cs * 2;
+    m->strides[2] = wp * cs * 2;
+    m->strides[3] = hp * wp * cs * 2;
+  } else {
+    m->dims[0] = cs + a->c;
+    m->dims[1] = wp / 2;
+    m->dims[2] = 2;
+    m->dims[3] = hp / 2;
+    m->dims[4] = a->n;
+    m->strides[0] = 2 * cs * 2;
+    m->strides[1] = wp * cs * 2;
+    m->strides[2] = 2 * wp * cs * 2;
+    m->strides[3] = hp * wp * cs * 2;
+  }
+  m->box[0] = box_c;
+  m->box[1] = tile_w;
+  m->box[2] = 1;
+  m->box[3] = tile_h;
+  m->box[4] = 1;
+}
+
+// tap (r, s) of a forward conv reading input pixel (o*stride + r - pad) as view coordinates
+static fpg_tap fwd_tap(int r, int s, int stride, int pad, int cs) {
+  fpg_tap t;
+  if (stride == 1) {
+    t.c0 = 0;
+    t.dx = s - pad;
+    t.plane = 0;
+    t.dy = r - pad;
+  } else {
+    const int qx = s - pad, qy = r - pad;
+    t.c0 = pos_mod(qx, 2) * cs;
+    t.dx = floor_div(qx, 2);
+    t.plane = pos_mod(qy, 2);
+    t.dy = floor_div(qy, 2);
+  }
+  return t;
+}
+
+static void out_view_of(const fpg_act* y, int with_halo, fpg_out_view* o) {
+  const int64_t wp = y->w + 2 * y->halo, hp = y->h + 2 * y->halo, cs = y->c_stride;
+  const int64_t org = with_halo ? 0 : (static_cast<int64_t>(y->halo) * wp + y->halo) * cs;
+  o->base = y->fp32 ? static_cast<void*>(static_cast<float*>(y->data) + org)
+                    : static_cast<void*>(static_cast<__nv_bfloat16*>(y->data) + org);
+  o->stride_n = hp * wp * cs;
+  o->stride_y = wp * cs;
+  o->stride_x = cs;
+  o->mul_y = o->mul_x = 1;
+  o->off_y = o->off_x = 0;
+  o->valid_h = with_halo ? static_cast<int>(hp) : y->h;
+  o->valid_w = with_halo ? static_cast<int>(wp) : y->w;
+  o->fp32 = y->fp32;
+}
+
+static void pick_tile(int wo, int* tile_w, int* tile_h, int pixels) {
+  int tw = pow2_at_least(wo < pixels ? wo : pixels);
+  if (tw > pixels) tw = pixels;
+  *tile_w = tw;
+  *tile_h = pixels / tw;
+}
+
+static int pick_block_n(int n_total, int m_tiles, int sms) {
+  int bn = n_total <= 256 ? n_total : 256;
+  while (n_total % bn != 0) bn -= 16;
+  while (m_tiles * (n_total / bn) < sms && bn % 32 == 0 && bn > 32) bn /= 2;
+  return bn;
+}
+
+static int pick_stages(int stage_bytes) {
+  int s = (200 * 1024) / stage_bytes;
+  if (s > 8) s = 8;
+  if (s < 2) s = 2;
+  return s;
+}
+
+// Taps of dgrad parity class (pi, pj) for a forward conv g, in the order used by both the plan and the packing.
+// Returns the number of taps; rs[i] = r*S+s of the forward filter tap, taps[i] = coordinates into dy (stride-1 view).
+static int dgrad_class_taps(const fpg_conv_geom* g, int pi, int pj, int* rs, fpg_tap* taps) {
+  int n = 0;
+  for (int r = 0; r < g->r; ++r) {
+    if (g->stride == 2 && pos_mod(pi + g->pad - r, 2) != 0) continue;
+    for (int s = 0; s < g->s; ++s) {
+      if (g->stride == 2 && pos_mod(pj + g->pad - s, 2) != 0) continue;
+      fpg_tap t;
+      t.c0 = 0;
+      t.plane = 0;
+      if (g->stride == 1) {
+        t.dy = g->pad - r;
+        t.dx = g->pad - s;
+      } else {
+        t.dy = (pi + g->pad - r) / 2;  // exact
+        t.dx = (pj + g->pad - s) / 2;
+      }
+      rs[n] = r * g->s + s;
+      taps[n] = t;
+      ++n;
+    }
+  }
+  return n;
+}
+
+static int padded_taps(int ntaps, int c, int cblk) {
+  const int sub_per_stage = 64 / cblk;
+  const int chunks = c / cblk;
+  int t = ntaps;
+  while ((t * chunks) % sub_per_stage != 0) ++t;
+  return t;
+}
+
+static int plan_fprop(const fpg_act* x, const void* w, const float* bias, int act, const fpg_conv_geom* g,
+                      const fpg_act* y, int sms, fpg_igemm_fprop_desc* d) {
+  FPG_REQUIRE(x && g && y && d, "null argument");
+  FPG_REQUIRE(g->stride == 1 || g->stride == 2, "stride %d", g->stride);
+  FPG_REQUIRE(x->halo == 0 || g->pad == 0, "input halo %d with zero pad %d", x->halo, g->pad);
+  FPG_REQUIRE(x->c == g->c_in && y->c == g->c_out, "channels x %d/%d y %d/%d", x->c, g->c_in, y->c, g->c_out);
+  const int hp = x->h + 2 * x->halo, wp = x->w + 2 * x->halo;
+  const int ho = (hp + 2 * g->pad - g->r) / g->stride + 1, wo = (wp + 2 * g->pad - g->s) / g->stride + 1;
+  FPG_REQUIRE(ho == y->h && wo == y->w && x->n == y->n, "output %dx%d expected %dx%d", y->h, y->w, ho, wo);
+  FPG_REQUIRE(g->stride == 1 || (hp % 2 == 0 && wp % 2 == 0), "stride-2 input must have even extent");
+  const int cblk = pick_cblk(g->c_in);
+  FPG_REQUIRE(cblk > 0 && g->c_out % 16 == 0, "unsupported channels c_in %d c_out %d", g->c_in, g->c_out);
+  memset(d, 0, sizeof(*d));
+  d->cblk = cblk;
+  d->c_per_tap = g->c_in;
+  const int real_taps = g->r * g->s;
+  d->num_taps = padded_taps(real_taps, g->c_in, cblk);
+  FPG_REQUIRE(d->num_taps <= FPG_MAX_TAPS, "too many taps %d", d->num_taps);
+  d->num_sub = d->num_taps * (g->c_in / cblk);
+  for (int r = 0; r < g->r; ++r)
+    for (int s = 0; s < g->s; ++s) d->taps[r * g->s + s] = fwd_tap(r, s, g->stride, g->pad, x->c_stride);
+  for (int t = real_taps; t < d->num_taps; ++t) d->taps[t] = d->taps[0];
+  pick_tile(wo, &d->tile_w, &d->tile_h, 128);
+  d->tiles_x = ceil_div(wo, d->tile_w);
+  d->tiles_y = ceil_div(ho, d->tile_h);
+  d->n_img = x->n;
+  d->block_n = pick_block_n(g->c_out, d->n_img * d->tiles_x * d->tiles_y, sms);
+  d->n_blocks = g->c_out / d->block_n;
+  d->stages = pick_stages(16384 + d->block_n * 128);
+  d->act = act;
+  d->bias = bias;
+  make_act_view(x, g->stride, cblk, d->tile_w, d->tile_h, &d->a);
+  memset(&d->b, 0, sizeof(d->b));
+  d->b.base = const_cast<void*>(w);
+  d->b.rank = 2;
+  d->b.swizzle_bytes = cblk * 2;
+  d->b.dims[0] = static_cast<uint64_t>(d->num_sub) * cblk;
+  d->b.dims[1] = g->c_out;
+  d->b.strides[0] = d->b.dims[0] * 2;
+  d->b.box[0] = cblk;
+  d->b.box[1] = d->block_n;
+  out_view_of(y, 0, &d->out);
+  return 0;
+}
+
+// K extent (elements) of dgrad class q's packed matrix, and its element offset inside the packed buffer
+static void dgrad_class_layout(const fpg_conv_geom* g, int64_t* k_of, int64_t* off_of, int* nclasses) {
+  const int cblk = pick_cblk(g->c_out);
+  const int nc = g->stride == 2 ? 4 : 1;
+  int64_t off = 0;
+  for (int q = 0; q < nc; ++q) {
+    int rs[FPG_MAX_TAPS];
+    fpg_tap taps[FPG_MAX_TAPS];
+    const int nt = dgrad_class_taps(g, q >> 1, q & 1, rs, taps);
+    const int ntp = padded_taps(nt, g->c_out, cblk);
+    k_of[q] = static_cast<int64_t>(ntp) * g->c_out;
+    off_of[q] = off;
+    off += k_of[q] * g->c_in;
+  }
+  *nclasses = nc;
+}
+
+static int plan_dgrad(const fpg_act* dy, const void* wt, const float* bias, int act, const fpg_conv_geom* g,
+                      const fpg_act* dx, int sms, fpg_igemm_fprop_desc* descs, int* n_descs) {
+  FPG_REQUIRE(dy && g && dx && descs && n_descs, "null argument");
+  FPG_REQUIRE(g->stride == 1 || g->stride == 2, "stride %d", g->stride);
+  FPG_REQUIRE(dy->halo == 0, "dy must not have a halo");
+  FPG_REQUIRE(dx->halo == 0 || g->pad == 0, "dx halo %d with zero pad %d", dx->halo, g->pad);
+  FPG_REQUIRE(dy->c == g->c_out && dx->c == g->c_in, "channels dy %d/%d dx %d/%d", dy->c, g->c_out, dx->c, g->c_in);
+  const int hp = dx->h + 2 * dx->halo, wp = dx->w + 2 * dx->halo;
+  const int ho = (hp + 2 * g->pad - g->r) / g->stride + 1, wo = (wp + 2 * g->pad - g->s) / g->stride + 1;
+  FPG_REQUIRE(ho == dy->h && wo == dy->w && dx->n == dy->n, "dy %dx%d expected %dx%d", dy->h, dy->w, ho, wo);
+  FPG_REQUIRE(g->stride == 1 || (hp % 2 == 0 && wp % 2 == 0), "stride-2 dx must have even extent");
+  const int cblk = pick_cblk(g->c_out);
+  FPG_REQUIRE(cblk > 0 && g->c_in % 16 == 0, "unsupported channels c_in %d c_out %d", g->c_in, g->c_out);
+  int64_t k_of[4], off_of[4];
+  int nc = 0;
+  dgrad_class_layout(g, k_of, off_of, &nc);
+  for (int q = 0; q < nc; ++q) {
+    fpg_igemm_fprop_desc* d = &descs[q];
+    memset(d, 0, sizeof(*d));
+    const int pi = q >> 1, pj = q & 1;
+    int rs[FPG_MAX_TAPS];
+    const int nt = dgrad_class_taps(g, pi, pj, rs, d->taps);
+    FPG_REQUIRE(nt > 0, "empty dgrad parity class");
+    d->cblk = cblk;
+    d->c_per_tap = g->c_out;
+    d->num_taps = padded_taps(nt, g->c_out, cblk);
+    FPG_REQUIRE(d->num_taps <= FPG_MAX_TAPS, "too many taps %d", d->num_taps);
+    for (int t = nt; t < d->num_taps; ++t) d->taps[t] = d->taps[0];
+    d->num_sub = d->num_taps * (g->c_out / cblk);
+    const int oh = g->stride == 2 ? hp / 2 : hp, ow = g->stride == 2 ? wp / 2 : wp;  // class output grid
+    pick_tile(ow, &d->tile_w, &d->tile_h, 128);
+    d->tiles_x = ceil_div(ow, d->tile_w);
+    d->tiles_y = ceil_div(oh, d->tile_h);
+    d->n_img = dx->n;
+    d->block_n = pick_block_n(g->c_in, d->n_img * d->tiles_x * d->tiles_y, sms);
+    d->n_blocks = g->c_in / d->block_n;
+    d->stages = pick_stages(16384 + d->block_n * 128);
+    d->act = act;
+    d->bias = bias;
+    make_act_view(dy, 1, cblk, d->tile_w, d->tile_h, &d->a);
+    d->b.base = static_cast<void*>(static_cast<__nv_bfloat16*>(const_cast<void*>(wt)) + off_of[q]);
+    d->b.rank = 2;
+    d->b.swizzle_bytes = cblk * 2;
+    d->b.dims[0] = static_cast<uint64_t>(k_of[q]);
+    d->b.dims[1] = g->c_in;
+    d->b.strides[0] = d->b.dims[0] * 2;
+    d->b.box[0] = cblk;
+    d->b.box[1] = d->block_n;
+    out_view_of(dx, 1, &d->out);
+    if (g->stride == 2) {
+      d->out.mul_y = d->out.mul_x = 2;
+      d->out.off_y = pi;
+      d->out.off_x = pj;
+      d->out.valid_h = oh;
+      d->out.valid_w = ow;
+    }
+  }
+  *n_descs = nc;
+  return 0;
+}
+
+static int largest_divisor_le(int v, int cap) {
+  for (int d = cap; d >= 1; --d)
+    if (v % d == 0) return d;
+  return 1;
+}
+
+static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g, int sms, fpg_igemm_wgrad_desc* d) {
+  FPG_REQUIRE(x && dy && g && d, "null argument");
+  FPG_REQUIRE(g->stride == 1 || g->stride == 2, "stride %d", g->stride);
+  FPG_REQUIRE(dy->halo == 0, "dy must not have a halo");
+  FPG_REQUIRE(x->halo == 0 || g->pad == 0, "input halo %d with zero pad %d", x->halo, g->pad);
+  FPG_REQUIRE(x->c == g->c_in && dy->c == g->c_out, "channels x %d/%d dy %d/%d", x->c, g->c_in, dy->c, g->c_out);
+  const int hp = x->h + 2 * x->halo, wp = x->w + 2 * x->halo;
+  const int ho = (hp + 2 * g->pad - g->r) / g->stride + 1, wo = (wp + 2 * g->pad - g->s) / g->stride + 1;
+  FPG_REQUIRE(ho == dy->h && wo == dy->w && x->n == dy->n, "dy %dx%d expected %dx%d", dy->h, dy->w, ho, wo);
+  FPG_REQUIRE(g->stride == 1 || (hp % 2 == 0 && wp % 2 == 0), "stride-2 input must have even extent");
+  const int ntaps = g->r * g->s;
+  FPG_REQUIRE(ntaps <= FPG_MAX_TAPS, "too many taps");
+  memset(d, 0, sizeof(*d));
+  d->taps_r = g->r;
+  d->taps_s = g->s;
+  pick_tile(wo, &d->tile_w, &d->tile_h, 64);
+  d->kt_x = ceil_div(wo, d->tile_w);
+  d->kt_y = ceil_div(ho, d->tile_h);
+  d->n_img = x->n;
+  fpg_tap null_tap = {0, 0, 0, 0};
+  fpg_tap in_taps[FPG_MAX_TAPS];
+  for (int r = 0; r < g->r; ++r)
+    for (int s = 0; s < g->s; ++s) in_taps[r * g->s + s] = fwd_tap(r, s, g->stride, g->pad, x->c_stride);
+
+  const bool big_out = g->c_out % 64 == 0, big_in = g->c_in % 64 == 0;
+  if (big_out) {
+    // X = dy (rows = output channels)
+    d->x_is_dy = 1;
+    d->x_ca = 64;
+    d->x_atoms = g->c_out % 128 == 0 ? 2 : 1;
+    d->x_groups = g->c_out / (64 * d->x_atoms);
+    d->x_taps_mode = 0;
+    d->x_ntaps = 1;
+    d->x_taps[0] = null_tap;
+    make_act_view(dy, 1, 64, d->tile_w, d->tile_h, &d->x);
+    if (big_in) {
+      d->y_ca = 64;
+      int ya = g->c_in / 64;
+      if (ya > 4) ya = 4;
+      while ((g->c_in / 64) % ya != 0) --ya;
+      d->y_atoms = ya;
+      d->y_groups = g->c_in / (64 * ya);
+      d->y_taps_mode = 0;
+    } else {
+      FPG_REQUIRE(g->c_in == 16 || g->c_in == 32, "unsupported c_in %d", g->c_in);
+      d->y_ca = g->c_in;
+      d->y_atoms = largest_divisor_le(ntaps, 256 / g->c_in);
+      d->y_groups = ntaps / d->y_atoms;
+      d->y_taps_mode = 1;
+    }
+    d->y_ntaps = ntaps;
+    for (int t = 0; t < ntaps; ++t) d->y_taps[t] = in_taps[t];
+    make_act_view(x, g->stride, d->y_ca, d->tile_w, d->tile_h, &d->y);
+  } else {
+    // small c_out: X = input (rows = input channels), Y = dy
+    FPG_REQUIRE(big_in && (g->c_out == 16 || g->c_out == 32), "unsupported wgrad channels c_in %d c_out %d", g->c_in,
+                g->c_out);
+    d->x_is_dy = 0;
+    d->x_ca = 64;
+    d->x_atoms = g->c_in % 128 == 0 ? 2 : 1;
+    d->x_groups = g->c_in / (64 * d->x_atoms);
+    d->x_taps_mode = 0;
+    d->x_ntaps = ntaps;
+    for (int t = 0; t < ntaps; ++t) d->x_taps[t] = in_taps[t];
+    make_act_view(x, g->stride, 64, d->tile_w, d->tile_h, &d->x);
+    d->y_ca = g->c_out;
+    d->y_atoms = 1;
+    d->y_groups = 1;
+    d->y_taps_mode = 0;
+    d->y_ntaps = 1;
+    d->y_taps[0] = null_tap;
+    make_act_view(dy, 1, d->y_ca, d->tile_w, d->tile_h, &d->y);
+  }
+  const int NX = d->x_taps_mode ? d->x_groups : d->x_groups * d->x_ntaps;
+  const int NY = d->y_taps_mode ? d->y_groups : d->y_groups * d->y_ntaps;
+  const int items = NX * NY;
+  const int total_kt = d->n_img * d->kt_x * d->kt_y;
+  int splits = sms / items;
+  if (splits < 1) splits = 1;
+  if (splits > total_kt) splits = total_kt;
+  if (splits > 64) splits = 64;
+  d->splits = splits;
+  const int M = d->x_atoms * d->x_ca, N = d->y_atoms * d->y_ca;
+  d->stages = pick_stages((M + N) * 128);
+  return 0;
+}
+
+static int64_t wgrad_ws_floats(const fpg_igemm_wgrad_desc* d) {
+  const int NX = d->x_taps_mode ? d->x_groups : d->x_groups * d->x_ntaps;
+  const int NY = d->y_taps_mode ? d->y_groups : d->y_groups * d->y_ntaps;
+  return static_cast<int64_t>(d->splits) * NX * NY * (d->x_atoms * d->x_ca) * (d->y_atoms * d->y_ca);
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+struct ReduceArgs {
+  int32_t x_ca, x_atoms, x_groups, x_taps_mode, x_ntaps;
+  int32_t y_ca, y_atoms, y_groups, y_taps_mode, y_ntaps;
+  int32_t splits, x_is_dy;
+  int64_t stride_k, stride_c;
+  int32_t k_valid, c_valid;
+};
+
+// one thread per (item, m, n): sum the split partials and scatter into the parameter-layout gradient
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, ReduceArgs a) {
+  const int M = a.x_atoms * a.x_ca, N = a.y_atoms * a.y_ca;
+  const int NX = a.x_taps_mode ? a.x_groups : a.x_groups * a.x_ntaps;
+  const int NY = a.y_taps_mode ? a.y_groups : a.y_groups * a.y_ntaps;
+  const int64_t items = static_cast<int64_t>(NX) * NY;
+  const int64_t per_split = items * M * N;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= per_split) return;
+  const int n = static_cast<int>(idx % N);
+  const int m = static_cast<int>((idx / N) % M);
+  const int item = static_cast<int>(idx / (static_cast<int64_t>(M) * N));
+  const int xi = item / NY, yi = item % NY;
+  int xtap, xch, ytap, ych;
+  {
+    const int atom = m / a.x_ca, within = m % a.x_ca;
+    if (a.x_taps_mode) {
+      xtap = xi * a.x_atoms + atom;
+      xch = within;
+    } else {
+      xtap = xi / a.x_groups;
+      xch = ((xi % a.x_groups) * a.x_atoms + atom) * a.x_ca + within;
+    }
+  }
+  {
+    const int atom = n / a.y_ca, within = n % a.y_ca;
+    if (a.y_taps_mode) {
+      ytap = yi * a.y_atoms + atom;
+      ych = within;
+    } else {
+      ytap = yi / a.y_groups;
+      ych = ((yi % a.y_groups) * a.y_atoms + atom) * a.y_ca + within;
+    }
+  }
+  int k, c, tap;
+  if (a.x_is_dy) {
+    k = xch;
+    c = ych;
+    tap = ytap;
+    if (ytap >= a.y_ntaps) return;
+  } else {
+    k = ych;
+    c = xch;
+    tap = xtap;
+    if (xtap >= a.x_ntaps) return;
+  }
+  if (k >= a.k_valid || c >= a.c_valid) return;
+  float acc = 0.f;
+  for (int s = 0; s < a.splits; ++s) acc += ws[s * per_split + idx];
+  dw[k * a.stride_k + c * a.stride_c + tap] = acc;
+}
+
+struct PackArgs {
+  int32_t rows, taps, cols;      // dst[rows][taps][cols] bf16
+  int32_t rows_valid, cols_valid;
+  int64_t src_stride_row, src_stride_col;
+  int32_t src_tap[FPG_MAX_TAPS];  // source tap index (r*S+s) or -1 for zero
+};
+
+__global__ void pack_weights_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, PackArgs a) {
+  const int64_t total = static_cast<int64_t>(a.rows) * a.taps * a.cols;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int col = static_cast<int>(i % a.cols);
+    const int t = static_cast<int>((i / a.cols) % a.taps);
+    const int row = static_cast<int>(i / (static_cast<int64_t>(a.cols) * a.taps));
+    float v = 0.f;
+    const int st = a.src_tap[t];
+    if (st >= 0 && row < a.rows_valid && col < a.cols_valid)
+      v = src[row * a.src_stride_row + col * a.src_stride_col + st];
+    dst[i] = __float2bfloat16(v);
+  }
+}
+
+}  // namespace fpg
+
+using namespace fpg;
+
+extern "C" {
+
+int fpg_conv2d_fprop_plan(const fpg_act* x, const void* w_packed, const float* bias, int act, const fpg_conv_geom* g,
+                          const fpg_act* y, int sm_count, fpg_igemm_fprop_desc* out_desc) {
+  return plan_fprop(x, w_packed, bias, act, g, y, sm_count, out_desc);
+}
+
+int fpg_conv2d_fprop(const fpg_act* x, const void* w_packed, const float* bias, int act, const fpg_conv_geom* g,
+                     const fpg_act* y, void* stream) {
+  fpg_igemm_fprop_desc d;
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
+  int rc = plan_fprop(x, w_packed, bias, act, g, y, sms, &d);
+  if (rc) return rc;
+  return fpg_igemm_fprop_launch(&d, stream);
+}
+
+int fpg_conv2d_dgrad_plan(const fpg_act* dy, const void* w_packed_t, const float* bias, int act,
+                          const fpg_conv_geom* g, const fpg_act* dx, int sm_count, fpg_igemm_fprop_desc* out_descs,
+                          int* n_descs) {
+  return plan_dgrad(dy, w_packed_t, bias, act, g, dx, sm_count, out_descs, n_descs);
+}
+
+int fpg_conv2d_dgrad(const fpg_act* dy, const void* w_packed_t, const float* bias, int act, const fpg_conv_geom* g,
+                     const fpg_act* dx, void* stream) {
+  fpg_igemm_fprop_desc d[4];
+  int n = 0;
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
+  int rc = plan_dgrad(dy, w_packed_t, bias, act, g, dx, sms, d, &n);
+  if (rc) return rc;
+  for (int q = 0; q < n; ++q) {
+    rc = fpg_igemm_fprop_launch(&d[q], stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int fpg_conv2d_wgrad_plan(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g, int sm_count,
+                          fpg_igemm_wgrad_desc* out_desc) {
+  return plan_wgrad(x, dy, g, sm_count, out_desc);
+}
+
+int64_t fpg_conv2d_wgrad_ws_bytes(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g, int sm_count) {
+  fpg_igemm_wgrad_desc d;
+  if (plan_wgrad(x, dy, g, sm_count, &d)) return -1;
+  return wgrad_ws_floats(&d) * 4;
+}
+
+int fpg_conv2d_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g, float* dw, int64_t dw_stride_k,
+                     int64_t dw_stride_c, int32_t k_valid, int32_t c_valid, float* ws, void* stream) {
+  fpg_igemm_wgrad_desc d;
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
+  int rc = plan_wgrad(x, dy, g, sms, &d);
+  if (rc) return rc;
+  d.ws = ws;
+  rc = fpg_igemm_wgrad_launch(&d, stream);
+  if (rc) return rc;
+  ReduceArgs a;
+  a.x_ca = d.x_ca;
+  a.x_atoms = d.x_atoms;
+  a.x_groups = d.x_groups;
+  a.x_taps_mode = d.x_taps_mode;
+  a.x_ntaps = d.x_ntaps;
+  a.y_ca = d.y_ca;
+  a.y_atoms = d.y_atoms;
+  a.y_groups = d.y_groups;
+  a.y_taps_mode = d.y_taps_mode;
+  a.y_ntaps = d.y_ntaps;
+  a.splits = d.splits;
+  a.x_is_dy = d.x_is_dy;
+  a.stride_k = dw_stride_k;
+  a.stride_c = dw_stride_c;
+  a.k_valid = k_valid;
+  a.c_valid = c_valid;
+  const int64_t per_split = wgrad_ws_floats(&d) / d.splits;
+  const int threads = 256;
+  const int64_t blocks = (per_split + threads - 1) / threads;
+  wgrad_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(ws, dw, a);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int64_t fpg_packed_weight_bytes(const fpg_conv_geom* g) {
+  const int cblk = pick_cblk(g->c_in);
+  if (cblk < 0) return -1;
+  return static_cast<int64_t>(g->c_out) * padded_taps(g->r * g->s, g->c_in, cblk) * g->c_in * 2;
+}
+
+int64_t fpg_packed_weight_dgrad_bytes(const fpg_conv_geom* g) {
+  if (pick_cblk(g->c_out) < 0) return -1;
+  int64_t k_of[4], off_of[4];
+  int nc = 0;
+  dgrad_class_layout(g, k_of, off_of, &nc);
+  return (off_of[nc - 1] + k_of[nc - 1] * g->c_in) * 2;
+}
+
+int fpg_dgrad_class_info(const fpg_conv_geom* g, int cls, int32_t* src_tap, int32_t* num_taps_padded,
+                         int64_t* elem_offset, int32_t* num_classes) {
+  FPG_REQUIRE(g && src_tap && num_taps_padded && elem_offset && num_classes, "null argument");
+  FPG_REQUIRE(pick_cblk(g->c_out) > 0, "unsupported c_out %d", g->c_out);
+  int64_t k_of[4], off_of[4];
+  int nc = 0;
+  dgrad_class_layout(g, k_of, off_of, &nc);
+  *num_classes = nc;
+  FPG_REQUIRE(cls >= 0 && cls < nc, "class %d of %d", cls, nc);
+  int rs[FPG_MAX_TAPS];
+  fpg_tap taps[FPG_MAX_TAPS];
+  const int nt = dgrad_class_taps(g, cls >> 1, cls & 1, rs, taps);
+  *num_taps_padded = static_cast<int32_t>(k_of[cls] / g->c_out);
+  *elem_offset = off_of[cls];
+  for (int t = 0; t < FPG_MAX_TAPS; ++t) src_tap[t] = t < nt ? rs[t] : -1;
+  return 0;
+}
+
+int fpg_pack_weights(const float* src, int64_t src_stride_k, int64_t src_stride_c, int32_t k_valid, int32_t c_valid,
+                     const fpg_conv_geom* g, void* dst, void* stream) {
+  const int cblk = pick_cblk(g->c_in);
+  FPG_REQUIRE(cblk > 0, "unsupported c_in %d", g->c_in);
+  PackArgs a;
+  a.rows = g->c_out;
+  a.taps = padded_taps(g->r * g->s, g->c_in, cblk);
+  a.cols = g->c_in;
+  a.rows_valid = k_valid;
+  a.cols_valid = c_valid;
+  a.src_stride_row = src_stride_k;
+  a.src_stride_col = src_stride_c;
+  for (int t = 0; t < FPG_MAX_TAPS; ++t) a.src_tap[t] = t < g->r * g->s ? t : -1;
+  const int64_t total = static_cast<int64_t>(a.rows) * a.taps * a.cols;
+  const int threads = 256;
+  int64_t blocks = (total + threads - 1) / threads;
+  if (blocks > 4096) blocks = 4096;
+  pack_weights_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), a);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_pack_weights_dgrad(const float* src, int64_t src_stride_k, int64_t src_stride_c, int32_t k_valid,
+                           int32_t c_valid, const fpg_conv_geom* g, void* dst, void* stream) {
+  const int cblk = pick_cblk(g->c_out);
+  FPG_REQUIRE(cblk > 0, "unsupported c_out %d", g->c_out);
+  int64_t k_of[4], off_of[4];
+  int nc = 0;
+  dgrad_class_layout(g, k_of, off_of, &nc);
+  for (int q = 0; q < nc; ++q) {
+    int rs[FPG_MAX_TAPS];
+    fpg_tap taps[FPG_MAX_TAPS];
+    const int nt = dgrad_class_taps(g, q >> 1, q & 1, rs, taps);
+    PackArgs a;
+    a.rows = g->c_in;  // GEMM N side = forward input channels
+    a.taps = static_cast<int32_t>(k_of[q] / g->c_out);
+    a.cols = g->c_out;
+    a.rows_valid = c_valid;
+    a.cols_valid = k_valid;
+    a.src_stride_row = src_stride_c;
+    a.src_stride_col = src_stride_k;
+    for (int t = 0; t < FPG_MAX_TAPS; ++t) a.src_tap[t] = t < nt ? rs[t] : -1;
+    const int64_t total = static_cast<int64_t>(a.rows) * a.taps * a.cols;
+    const int threads = 256;
+    int64_t blocks = (total + threads - 1) / threads;
+    if (blocks > 4096) blocks = 4096;
+    pack_weights_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, static_cast<__nv_bfloat16*>(dst) + off_of[q], a);
+    FPG_CUDA_CHECK(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // extern "C"

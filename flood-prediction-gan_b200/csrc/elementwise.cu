@@ -1,0 +1,915 @@
+// HBM-bound kernels of the training step: InstanceNorm statistics / apply / backward (with reflect-halo write
+// and fold), attention-content blend forward / backward, loss reductions, Adam, layout packing, flood mask.
+// All activation traffic is NHWC with 128-bit accesses (8 bf16 channels per thread per access).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace fpg {
+
+struct View {
+  void* p;
+  int32_t n, h, w, c, cs, halo;
+  __device__ __forceinline__ int hp() const { return h + 2 * halo; }
+  __device__ __forceinline__ int wp() const { return w + 2 * halo; }
+  // element offset of interior pixel (y, x) of image i, channel 0
+  __device__ __forceinline__ int64_t at(int i, int y, int x) const {
+    return ((static_cast<int64_t>(i) * hp() + (y + halo)) * wp() + (x + halo)) * cs;
+  }
+  // element offset of padded pixel (py, px)
+  __device__ __forceinline__ int64_t at_padded(int i, int py, int px) const {
+    return ((static_cast<int64_t>(i) * hp() + py) * wp() + px) * cs;
+  }
+};
+
+static View view_of(const fpg_act* a) {
+  View v;
+  v.p = a->data;
+  v.n = a->n;
+  v.h = a->h;
+  v.w = a->w;
+  v.c = a->c;
+  v.cs = a->c_stride;
+  v.halo = a->halo;
+  return v;
+}
+
+__device__ __forceinline__ int reflect_idx(int q, int n) { return q < 0 ? -q : (q >= n ? 2 * (n - 1) - q : q); }
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                            pack_bf16x2(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------------------------------------ IN statistics
+// grid (splits, n); block 256. thread t owns channel group (t % G), pixel lane (t / G); G = c / 8.
+// partial[(i*splits + split)*c*2 + ch*2 + {0,1}] = {sum, sum of squares}
+constexpr int kStatThreads = 256;
+
+__global__ void in_stats_partial_kernel(View y, float* __restrict__ partial) {
+  const int G = y.c / 8;
+  const int lanes = kStatThreads / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  const int i = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+  const int hw = y.h * y.w;
+  const int p_begin = static_cast<int>(static_cast<int64_t>(hw) * split / splits);
+  const int p_end = static_cast<int>(static_cast<int64_t>(hw) * (split + 1) / splits);
+  float s[8], ss[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = ss[k] = 0.f;
+  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(y.p);
+  if (pl < lanes) {
+    for (int p = p_begin + pl; p < p_end; p += lanes) {
+      const int py = p / y.w, px = p - py * y.w;
+      float f[8];
+      load8(base + y.at(i, py, px) + g * 8, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        s[k] += f[k];
+        ss[k] += f[k] * f[k];
+      }
+    }
+  }
+  __shared__ float red[kStatThreads][17];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red[threadIdx.x][k] = s[k];
+    red[threadIdx.x][8 + k] = ss[k];
+  }
+  __syncthreads();
+  // thread t < G*16 reduces one (channel group, component) over the pixel lanes in fixed order
+  for (int o = threadIdx.x; o < G * 16; o += kStatThreads) {
+    const int gg = o / 16, comp = o % 16;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[l * G + gg][comp];
+    const int ch = gg * 8 + (comp & 7);
+    partial[((static_cast<int64_t>(i) * splits + split) * y.c + ch) * 2 + (comp >> 3)] = acc;
+  }
+}
+
+// one thread per (image, channel): stats = {mean, rstd}
+__global__ void in_stats_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int n, int c,
+                                         int splits, float inv_hw, float eps) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * c) return;
+  const int i = idx / c, ch = idx % c;
+  float s = 0.f, ss = 0.f;
+  for (int sp = 0; sp < splits; ++sp) {
+    const float* p = partial + ((static_cast<int64_t>(i) * splits + sp) * c + ch) * 2;
+    s += p[0];
+    ss += p[1];
+  }
+  const float mean = s * inv_hw;
+  float var = ss * inv_hw - mean * mean;
+  var = fmaxf(var, 0.f);
+  stats[idx * 2] = mean;
+  stats[idx * 2 + 1] = rsqrtf(var + eps);
+}
+
+// for the backward: red = {mean(g'), mean(g' * zhat)}
+__global__ void in_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ red, int n, int c,
+                                       int splits, float inv_hw) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * c) return;
+  const int i = idx / c, ch = idx % c;
+  float s = 0.f, ss = 0.f;
+  for (int sp = 0; sp < splits; ++sp) {
+    const float* p = partial + ((static_cast<int64_t>(i) * splits + sp) * c + ch) * 2;
+    s += p[0];
+    ss += p[1];
+  }
+  red[idx * 2] = s * inv_hw;
+  red[idx * 2 + 1] = ss * inv_hw;
+}
+
+__device__ __forceinline__ float act_fwd(float v, int act) {
+  return act == FPG_ACT_RELU ? fmaxf(v, 0.f) : (act == FPG_ACT_LEAKY ? (v > 0.f ? v : 0.2f * v) : v);
+}
+__device__ __forceinline__ float act_grad(float pre, int act) {
+  return act == FPG_ACT_RELU ? (pre > 0.f ? 1.f : 0.f) : (act == FPG_ACT_LEAKY ? (pre > 0.f ? 1.f : 0.2f) : 1.f);
+}
+
+// ------------------------------------------------------------------------------------------------ IN apply
+// one thread per (padded output pixel, 8-channel group)
+__global__ void in_apply_kernel(View y, const float* __restrict__ stats, int act, View res, int has_res, View z) {
+  const int G = y.c / 8;
+  const int64_t total = static_cast<int64_t>(z.n) * z.hp() * z.wp() * G;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % G);
+  int64_t r = idx / G;
+  const int px = static_cast<int>(r % z.wp());
+  r /= z.wp();
+  const int py = static_cast<int>(r % z.hp());
+  const int i = static_cast<int>(r / z.hp());
+  const int sy = reflect_idx(py - z.halo, z.h), sx = reflect_idx(px - z.halo, z.w);
+  float f[8];
+  load8(static_cast<const __nv_bfloat16*>(y.p) + y.at(i, sy, sx) + g * 8, f);
+  const float4* st = reinterpret_cast<const float4*>(stats + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
+  float o[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 ms = __ldg(st + k);  // {mean0, rstd0, mean1, rstd1}
+    o[2 * k] = act_fwd((f[2 * k] - ms.x) * ms.y, act);
+    o[2 * k + 1] = act_fwd((f[2 * k + 1] - ms.z) * ms.w, act);
+  }
+  if (has_res) {
+    float rr[8];
+    load8(static_cast<const __nv_bfloat16*>(res.p) + res.at(i, sy, sx) + g * 8, rr);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] += rr[k];
+  }
+  store8(static_cast<__nv_bfloat16*>(z.p) + z.at_padded(i, py, px) + g * 8, o);
+}
+
+// ------------------------------------------------------------------------------------------------ IN backward
+// Folded upstream gradient at interior pixel (y, x): sum of dz over all padded positions that mirror onto it.
+__device__ __forceinline__ void folded_grad(const View& dz, int i, int y, int x, int g, float (&acc)[8]) {
+  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(dz.p);
+  if (dz.halo == 0) {
+    load8(base + dz.at(i, y, x) + g * 8, acc);
+    return;
+  }
+  const int h = dz.halo;
+  int rows[3], cols[3], nr = 0, nc = 0;
+  rows[nr++] = y + h;
+  if (y >= 1 && y <= h) rows[nr++] = h - y;
+  if (y >= dz.h - 1 - h && y <= dz.h - 2) rows[nr++] = 2 * (dz.h - 1) - y + h;
+  cols[nc++] = x + h;
+  if (x >= 1 && x <= h) cols[nc++] = h - x;
+  if (x >= dz.w - 1 - h && x <= dz.w - 2) cols[nc++] = 2 * (dz.w - 1) - x + h;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int a = 0; a < nr; ++a)
+    for (int b = 0; b < nc; ++b) {
+      float f[8];
+      load8(base + dz.at_padded(i, rows[a], cols[b]) + g * 8, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += f[k];
+    }
+}
+
+// pass 1: g = fold(dz) (+ dz2); optionally store g to dres; reduce {sum g', sum g'*zhat} per (image, channel)
+__global__ void in_bwd_reduce_kernel(View dz, View dz2, int has_dz2, View y, const float* __restrict__ stats, int act,
+                                     View dres, int has_dres, float* __restrict__ partial) {
+  const int G = y.c / 8;
+  const int lanes = kStatThreads / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  const int i = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+  const int hw = y.h * y.w;
+  const int p_begin = static_cast<int>(static_cast<int64_t>(hw) * split / splits);
+  const int p_end = static_cast<int>(static_cast<int64_t>(hw) * (split + 1) / splits);
+  float s[8], ss[8], mean[8], rstd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = ss[k] = 0.f;
+  if (pl < lanes) {
+    const float4* st = reinterpret_cast<const float4*>(stats + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 ms = __ldg(st + k);
+      mean[2 * k] = ms.x; rstd[2 * k] = ms.y; mean[2 * k + 1] = ms.z; rstd[2 * k + 1] = ms.w;
+    }
+    for (int p = p_begin + pl; p < p_end; p += lanes) {
+      const int py = p / y.w, px = p - py * y.w;
+      float gr[8], yy[8];
+      folded_grad(dz, i, py, px, g, gr);
+      if (has_dz2) {
+        float e[8];
+        load8(static_cast<const __nv_bfloat16*>(dz2.p) + dz2.at(i, py, px) + g * 8, e);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gr[k] += e[k];
+      }
+      if (has_dres) store8(static_cast<__nv_bfloat16*>(dres.p) + dres.at(i, py, px) + g * 8, gr);
+      load8(static_cast<const __nv_bfloat16*>(y.p) + y.at(i, py, px) + g * 8, yy);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float zh = (yy[k] - mean[k]) * rstd[k];
+        const float gp = gr[k] * act_grad(zh, act);
+        s[k] += gp;
+        ss[k] += gp * zh;
+      }
+    }
+  }
+  __shared__ float red[kStatThreads][17];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red[threadIdx.x][k] = s[k];
+    red[threadIdx.x][8 + k] = ss[k];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < G * 16; o += kStatThreads) {
+    const int gg = o / 16, comp = o % 16;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[l * G + gg][comp];
+    const int ch = gg * 8 + (comp & 7);
+    partial[((static_cast<int64_t>(i) * splits + split) * y.c + ch) * 2 + (comp >> 3)] = acc;
+  }
+}
+
+// pass 2: dy = rstd * (g' - mean(g') - zhat * mean(g' zhat)); g read back from dres when available
+__global__ void in_bwd_apply_kernel(View dz, View dz2, int has_dz2, View gsrc, int has_gsrc, View y,
+                                    const float* __restrict__ stats, const float* __restrict__ red, int act, View dy) {
+  const int G = y.c / 8;
+  const int64_t total = static_cast<int64_t>(y.n) * y.h * y.w * G;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % G);
+  int64_t r = idx / G;
+  const int px = static_cast<int>(r % y.w);
+  r /= y.w;
+  const int py = static_cast<int>(r % y.h);
+  const int i = static_cast<int>(r / y.h);
+  float gr[8], yy[8], o[8];
+  if (has_gsrc) {
+    load8(static_cast<const __nv_bfloat16*>(gsrc.p) + gsrc.at(i, py, px) + g * 8, gr);
+  } else {
+    folded_grad(dz, i, py, px, g, gr);
+    if (has_dz2) {
+      float e[8];
+      load8(static_cast<const __nv_bfloat16*>(dz2.p) + dz2.at(i, py, px) + g * 8, e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gr[k] += e[k];
+    }
+  }
+  load8(static_cast<const __nv_bfloat16*>(y.p) + y.at(i, py, px) + g * 8, yy);
+  const float4* st = reinterpret_cast<const float4*>(stats + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
+  const float4* rd = reinterpret_cast<const float4*>(red + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float4 ms = __ldg(st + k);
+    const float4 mr = __ldg(rd + k);
+    {
+      const float zh = (yy[2 * k] - ms.x) * ms.y;
+      const float gp = gr[2 * k] * act_grad(zh, act);
+      o[2 * k] = ms.y * (gp - mr.x - zh * mr.y);
+    }
+    {
+      const float zh = (yy[2 * k + 1] - ms.z) * ms.w;
+      const float gp = gr[2 * k + 1] * act_grad(zh, act);
+      o[2 * k + 1] = ms.w * (gp - mr.z - zh * mr.w);
+    }
+  }
+  store8(static_cast<__nv_bfloat16*>(dy.p) + dy.at(i, py, px) + g * 8, o);
+}
+
+// dx = fold(dz) * act'(z), z = saved activation output (sign(z) == sign(pre-activation))
+__global__ void act_bwd_kernel(View dz, View z, int act, View dx) {
+  const int G = z.c / 8;
+  const int64_t total = static_cast<int64_t>(z.n) * z.h * z.w * G;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % G);
+  int64_t r = idx / G;
+  const int px = static_cast<int>(r % z.w);
+  r /= z.w;
+  const int py = static_cast<int>(r % z.h);
+  const int i = static_cast<int>(r / z.h);
+  float gr[8], zz[8], o[8];
+  folded_grad(dz, i, py, px, g, gr);
+  load8(static_cast<const __nv_bfloat16*>(z.p) + z.at(i, py, px) + g * 8, zz);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) o[k] = gr[k] * act_grad(zz[k], act);
+  store8(static_cast<__nv_bfloat16*>(dx.p) + dx.at(i, py, px) + g * 8, o);
+}
+
+// c = fold(a) + b
+__global__ void fold_add_kernel(View a, View b, int has_b, View c) {
+  const int G = c.c / 8;
+  const int64_t total = static_cast<int64_t>(c.n) * c.h * c.w * G;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % G);
+  int64_t r = idx / G;
+  const int px = static_cast<int>(r % c.w);
+  r /= c.w;
+  const int py = static_cast<int>(r % c.h);
+  const int i = static_cast<int>(r / c.h);
+  float gr[8];
+  folded_grad(a, i, py, px, g, gr);
+  if (has_b) {
+    float e[8];
+    load8(static_cast<const __nv_bfloat16*>(b.p) + b.at(i, py, px) + g * 8, e);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gr[k] += e[k];
+  }
+  store8(static_cast<__nv_bfloat16*>(c.p) + c.at(i, py, px) + g * 8, gr);
+}
+
+// ------------------------------------------------------------------------------------------------ bias grad
+// db[k] = sum over pixels of dy[.., k]; grid (c/8 groups), block 256: fixed-order tree over pixels
+__global__ void bias_grad_kernel(View dy, float* __restrict__ db, int k_valid) {
+  const int g = blockIdx.x;
+  const int64_t npix = static_cast<int64_t>(dy.n) * dy.h * dy.w;
+  float s[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = 0.f;
+  for (int64_t p = threadIdx.x; p < npix; p += blockDim.x) {
+    const int px = static_cast<int>(p % dy.w);
+    const int64_t r = p / dy.w;
+    const int py = static_cast<int>(r % dy.h);
+    const int i = static_cast<int>(r / dy.h);
+    float f[8];
+    load8(static_cast<const __nv_bfloat16*>(dy.p) + dy.at(i, py, px) + g * 8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] += f[k];
+  }
+  __shared__ float red[256][9];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = s[k];
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (static_cast<int>(threadIdx.x) < off) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[threadIdx.x][k] += red[threadIdx.x + off][k];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 8) {
+    const int ch = g * 8 + threadIdx.x;
+    if (ch < k_valid) db[ch] = red[0][threadIdx.x];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ blend
+// one thread per pixel. content: fp32 NHWC 32 ch (27 valid, tanh applied); logits: fp32 NHWC 16 ch (10 valid)
+__global__ void blend_fwd_kernel(View content, View logits, View input, View out, int out_c0,
+                                 float* __restrict__ out_nchw, float* __restrict__ mask) {
+  const int64_t total = static_cast<int64_t>(content.n) * content.h * content.w;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % content.w);
+  const int64_t r = idx / content.w;
+  const int py = static_cast<int>(r % content.h);
+  const int i = static_cast<int>(r / content.h);
+  float c[28], l[12];
+  const float4* cp = reinterpret_cast<const float4*>(static_cast<const float*>(content.p) + content.at(i, py, px));
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const float4 v = cp[k];
+    c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w;
+  }
+  const float4* lp = reinterpret_cast<const float4*>(static_cast<const float*>(logits.p) + logits.at(i, py, px));
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float4 v = lp[k];
+    l[4 * k] = v.x; l[4 * k + 1] = v.y; l[4 * k + 2] = v.z; l[4 * k + 3] = v.w;
+  }
+  float mx = l[0];
+#pragma unroll
+  for (int k = 1; k < 10; ++k) mx = fmaxf(mx, l[k]);
+  float a[10], sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    a[k] = expf(l[k] - mx);
+    sum += a[k];
+  }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) a[k] *= inv;
+  const __nv_bfloat16* ip = static_cast<const __nv_bfloat16*>(input.p) + input.at(i, py, px);
+  float o[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc += c[3 * k + j] * a[k];
+    acc += __bfloat162float(ip[j]) * a[9];
+    o[j] = acc;
+  }
+  if (out.p != nullptr) {
+    __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out.p) + out.at(i, py, px) + out_c0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) op[j] = __float2bfloat16(o[j]);
+  }
+  const int64_t hw = static_cast<int64_t>(content.h) * content.w;
+  const int64_t pix = static_cast<int64_t>(py) * content.w + px;
+  if (out_nchw != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) out_nchw[(static_cast<int64_t>(i) * 3 + j) * hw + pix] = o[j];
+  }
+  if (mask != nullptr) mask[static_cast<int64_t>(i) * hw + pix] = a[9];
+}
+
+__global__ void blend_bwd_kernel(const float* __restrict__ dout_nchw, View dout_nhwc, int dout_c0, View content,
+                                 View logits, View input, View dcontent, View dlogits, float* __restrict__ dimage_nchw) {
+  const int64_t total = static_cast<int64_t>(content.n) * content.h * content.w;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % content.w);
+  const int64_t r = idx / content.w;
+  const int py = static_cast<int>(r % content.h);
+  const int i = static_cast<int>(r / content.h);
+  const int64_t hw = static_cast<int64_t>(content.h) * content.w;
+  const int64_t pix = static_cast<int64_t>(py) * content.w + px;
+  float gout[3] = {0.f, 0.f, 0.f};
+  if (dout_nchw != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) gout[j] += dout_nchw[(static_cast<int64_t>(i) * 3 + j) * hw + pix];
+  }
+  if (dout_nhwc.p != nullptr) {
+    const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(dout_nhwc.p) + dout_nhwc.at(i, py, px) + dout_c0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) gout[j] += __bfloat162float(gp[j]);
+  }
+  float c[28], l[12];
+  const float4* cp = reinterpret_cast<const float4*>(static_cast<const float*>(content.p) + content.at(i, py, px));
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const float4 v = cp[k];
+    c[4 * k] = v.x; c[4 * k + 1] = v.y; c[4 * k + 2] = v.z; c[4 * k + 3] = v.w;
+  }
+  const float4* lp = reinterpret_cast<const float4*>(static_cast<const float*>(logits.p) + logits.at(i, py, px));
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float4 v = lp[k];
+    l[4 * k] = v.x; l[4 * k + 1] = v.y; l[4 * k + 2] = v.z; l[4 * k + 3] = v.w;
+  }
+  float mx = l[0];
+#pragma unroll
+  for (int k = 1; k < 10; ++k) mx = fmaxf(mx, l[k]);
+  float a[10], sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    a[k] = expf(l[k] - mx);
+    sum += a[k];
+  }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) a[k] *= inv;
+  const __nv_bfloat16* ip = static_cast<const __nv_bfloat16*>(input.p) + input.at(i, py, px);
+  float rgb[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) rgb[j] = __bfloat162float(ip[j]);
+
+  // content gradient (through tanh: c is the tanh output)
+  float dc[32];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float cv = c[3 * k + j];
+      dc[3 * k + j] = gout[j] * a[k] * (1.f - cv * cv);
+    }
+#pragma unroll
+  for (int k = 27; k < 32; ++k) dc[k] = 0.f;
+  __nv_bfloat16* dcp = static_cast<__nv_bfloat16*>(dcontent.p) + dcontent.at(i, py, px);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float f[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) f[m] = dc[8 * k + m];
+    store8(dcp + 8 * k, f);
+  }
+  // attention gradient through the softmax
+  float da[10], dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) acc += gout[j] * c[3 * k + j];
+    da[k] = acc;
+  }
+  da[9] = gout[0] * rgb[0] + gout[1] * rgb[1] + gout[2] * rgb[2];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) dot += a[k] * da[k];
+  float dl[16];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) dl[k] = a[k] * (da[k] - dot);
+#pragma unroll
+  for (int k = 10; k < 16; ++k) dl[k] = 0.f;
+  __nv_bfloat16* dlp = static_cast<__nv_bfloat16*>(dlogits.p) + dlogits.at(i, py, px);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    float f[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) f[m] = dl[8 * k + m];
+    store8(dlp + 8 * k, f);
+  }
+  if (dimage_nchw != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) dimage_nchw[(static_cast<int64_t>(i) * 3 + j) * hw + pix] = gout[j] * a[9];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ losses
+// single CTA: PatchGAN logits are a few thousand elements. logits fp32 NHWC, channel 0 valid.
+__global__ void mse_const_kernel(View logits, float target, float weight, float grad_scale, float* __restrict__ loss,
+                                 View dlogits) {
+  const int64_t count = static_cast<int64_t>(logits.n) * logits.h * logits.w;
+  const float gcoef = dlogits.p != nullptr ? grad_scale * weight * 2.f / static_cast<float>(count) : 0.f;
+  float acc = 0.f;
+  for (int64_t p = threadIdx.x; p < count; p += blockDim.x) {
+    const int px = static_cast<int>(p % logits.w);
+    const int64_t r = p / logits.w;
+    const int py = static_cast<int>(r % logits.h);
+    const int i = static_cast<int>(r / logits.h);
+    const float d = static_cast<const float*>(logits.p)[logits.at(i, py, px)] - target;
+    acc += d * d;
+    if (dlogits.p != nullptr) {
+      __nv_bfloat16* gp = static_cast<__nv_bfloat16*>(dlogits.p) + dlogits.at(i, py, px);
+      float f[8] = {gcoef * d, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      store8(gp, f);
+      for (int k = 8; k < dlogits.c; k += 8) {
+        float zf[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        store8(gp + k, zf);
+      }
+    }
+  }
+  __shared__ float red[1024];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+    if (static_cast<int>(threadIdx.x) < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && loss != nullptr) *loss = weight * red[0] / static_cast<float>(count);
+}
+
+constexpr int kL1Blocks = 296;
+__global__ void l1_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t count,
+                                  float gcoef, float* __restrict__ dpred, int accumulate, float* __restrict__ partial) {
+  float acc = 0.f;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const float d = pred[i] - target[i];
+    acc += fabsf(d);
+    if (dpred != nullptr) {
+      const float gsign = d > 0.f ? gcoef : (d < 0.f ? -gcoef : 0.f);
+      dpred[i] = accumulate ? dpred[i] + gsign : gsign;
+    }
+  }
+  __shared__ float red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (static_cast<int>(threadIdx.x) < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+__global__ void l1_finalize_kernel(const float* __restrict__ partial, int nparts, float scale, float* __restrict__ loss) {
+  __shared__ float red[512];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) acc += partial[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = blockDim.x / 2; off > 0; off >>= 1) {
+    if (static_cast<int>(threadIdx.x) < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = red[0] * scale;
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+// fp32 NCHW -> bf16 NHWC (channels [c0, c0+c_src)), reflect halo; one thread per padded destination pixel
+__global__ void pack_nchw_kernel(const float* __restrict__ src, int c_src, View dst, int c0, int zero_rest) {
+  const int64_t total = static_cast<int64_t>(dst.n) * dst.hp() * dst.wp();
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % dst.wp());
+  const int64_t r = idx / dst.wp();
+  const int py = static_cast<int>(r % dst.hp());
+  const int i = static_cast<int>(r / dst.hp());
+  const int sy = reflect_idx(py - dst.halo, dst.h), sx = reflect_idx(px - dst.halo, dst.w);
+  __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(dst.p) + dst.at_padded(i, py, px);
+  const int64_t hw = static_cast<int64_t>(dst.h) * dst.w;
+  const float* sp = src + static_cast<int64_t>(i) * c_src * hw + static_cast<int64_t>(sy) * dst.w + sx;
+  if (zero_rest) {
+    for (int ch = 0; ch < dst.c; ++ch) {
+      const int sc = ch - c0;
+      dp[ch] = __float2bfloat16((sc >= 0 && sc < c_src) ? sp[sc * hw] : 0.f);
+    }
+  } else {
+    for (int sc = 0; sc < c_src; ++sc) dp[c0 + sc] = __float2bfloat16(sp[sc * hw]);
+  }
+}
+
+// bf16 NHWC (interior, channels [c0, c0+c_dst)) -> fp32 NCHW; one thread per pixel
+__global__ void unpack_nchw_kernel(View src, int c0, float* __restrict__ dst, int c_dst, int accumulate) {
+  const int64_t total = static_cast<int64_t>(src.n) * src.h * src.w;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % src.w);
+  const int64_t r = idx / src.w;
+  const int py = static_cast<int>(r % src.h);
+  const int i = static_cast<int>(r / src.h);
+  const __nv_bfloat16* sp = static_cast<const __nv_bfloat16*>(src.p) + src.at(i, py, px) + c0;
+  const int64_t hw = static_cast<int64_t>(src.h) * src.w;
+  float* dp = dst + static_cast<int64_t>(i) * c_dst * hw + static_cast<int64_t>(py) * src.w + px;
+  for (int ch = 0; ch < c_dst; ++ch) {
+    const float v = __bfloat162float(sp[ch]);
+    dp[ch * hw] = accumulate ? dp[ch * hw] + v : v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ Adam
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t count, float beta1, float beta2, float eps, float step_size,
+                            float bc2_sqrt, float grad_scale) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const float w1 = 1.f - beta1;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const float gr = g[i] * grad_scale;
+    float mi = m[i], vi = v[i];
+    // torch.lerp(m, g, w): w < 0.5 ? m + w*(g-m) : g - (g-m)*(1-w)
+    mi = (w1 < 0.5f) ? mi + w1 * (gr - mi) : gr - (gr - mi) * (1.f - w1);
+    vi = vi * beta2 + (1.f - beta2) * gr * gr;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ flood mask
+__global__ void flood_mask_kernel(const float* __restrict__ logits, float* __restrict__ mask, int64_t count) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    // fp32 sigmoid as ATen computes it, 1 / (1 + exp(-x)), THEN the comparison (model.py:399-400): for
+    // 0 < x <~ 6e-8 the fp32 sigmoid rounds to exactly 0.5 and the mask is 0, so `x > 0` is not equivalent.
+    const float s = 1.0f / (1.0f + expf(-logits[i]));
+    mask[i] = s > 0.5f ? 1.f : 0.f;
+  }
+}
+__global__ void confusion_kernel(const float* __restrict__ pred, const float* __restrict__ truth, int64_t count,
+                                 unsigned long long* __restrict__ counts) {
+  unsigned long long tp = 0, fp = 0, tn = 0, fn = 0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const bool p = pred[i] > 0.5f, t = truth[i] > 0.5f;
+    tp += (p && t);
+    fp += (p && !t);
+    tn += (!p && !t);
+    fn += (!p && t);
+  }
+  // integer counts: atomics are exact and order-independent
+  for (int o = 16; o > 0; o >>= 1) {
+    tp += __shfl_xor_sync(0xffffffffu, tp, o);
+    fp += __shfl_xor_sync(0xffffffffu, fp, o);
+    tn += __shfl_xor_sync(0xffffffffu, tn, o);
+    fn += __shfl_xor_sync(0xffffffffu, fn, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&counts[0], tp);
+    atomicAdd(&counts[1], fp);
+    atomicAdd(&counts[2], tn);
+    atomicAdd(&counts[3], fn);
+  }
+}
+
+static unsigned grid_for(int64_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+
+static int stat_splits(const fpg_act* y, int sms) {
+  // enough CTAs for ~2 waves, at most 64 splits per image, at least ~64 pixels per lane pass
+  int splits = (2 * sms + y->n - 1) / y->n;
+  if (splits > 64) splits = 64;
+  const int hw = y->h * y->w;
+  while (splits > 1 && hw / splits < 256) splits /= 2;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
+}  // namespace fpg
+
+using namespace fpg;
+
+#define FPG_ST(stream) static_cast<cudaStream_t>(stream)
+
+extern "C" {
+
+int64_t fpg_instnorm_scratch_floats(const fpg_act* y) { return static_cast<int64_t>(y->n) * 64 * y->c * 2 + static_cast<int64_t>(y->n) * y->c * 2; }
+
+int fpg_instnorm_stats(const fpg_act* y, float eps, float* stats, float* scratch, void* stream) {
+  FPG_REQUIRE(y && stats && scratch, "null argument");
+  FPG_REQUIRE(y->c % 8 == 0 && kStatThreads % (y->c / 8) == 0, "instnorm channels %d", y->c);
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
+  const int splits = stat_splits(y, sms);
+  in_stats_partial_kernel<<<dim3(splits, y->n), kStatThreads, 0, FPG_ST(stream)>>>(view_of(y), scratch);
+  in_stats_finalize_kernel<<<grid_for(static_cast<int64_t>(y->n) * y->c, 256), 256, 0, FPG_ST(stream)>>>(
+      scratch, stats, y->n, y->c, splits, 1.f / static_cast<float>(y->h * y->w), eps);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_act* residual, const fpg_act* z,
+                       void* stream) {
+  FPG_REQUIRE(y && stats && z, "null argument");
+  FPG_REQUIRE(y->n == z->n && y->h == z->h && y->w == z->w && y->c == z->c && y->c % 8 == 0, "geometry mismatch");
+  FPG_REQUIRE(z->halo < z->h && z->halo < z->w, "halo too large");
+  View rv = residual ? view_of(residual) : view_of(y);
+  const int64_t total = static_cast<int64_t>(z->n) * (z->h + 2 * z->halo) * (z->w + 2 * z->halo) * (y->c / 8);
+  in_apply_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(y), stats, act, rv, residual != nullptr,
+                                                                    view_of(z));
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_instnorm_bwd(const fpg_act* dz, const fpg_act* dz2, const fpg_act* y, const float* stats, int act,
+                     const fpg_act* dy, const fpg_act* dres, float* scratch, void* stream) {
+  FPG_REQUIRE(dz && y && stats && dy && scratch, "null argument");
+  FPG_REQUIRE(y->c % 8 == 0 && kStatThreads % (y->c / 8) == 0, "instnorm channels %d", y->c);
+  FPG_REQUIRE(dz->h == y->h && dz->w == y->w && dz->c == y->c && dy->h == y->h && dy->c == y->c, "geometry mismatch");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
+  const int splits = stat_splits(y, sms);
+  View v2 = dz2 ? view_of(dz2) : view_of(dz);
+  View vr = dres ? view_of(dres) : view_of(dz);
+  float* red = scratch + static_cast<int64_t>(y->n) * 64 * y->c * 2;
+  in_bwd_reduce_kernel<<<dim3(splits, y->n), kStatThreads, 0, FPG_ST(stream)>>>(
+      view_of(dz), v2, dz2 != nullptr, view_of(y), stats, act, vr, dres != nullptr, scratch);
+  in_bwd_finalize_kernel<<<grid_for(static_cast<int64_t>(y->n) * y->c, 256), 256, 0, FPG_ST(stream)>>>(
+      scratch, red, y->n, y->c, splits, 1.f / static_cast<float>(y->h * y->w));
+  const int64_t total = static_cast<int64_t>(y->n) * y->h * y->w * (y->c / 8);
+  in_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(dz), v2, dz2 != nullptr, vr,
+                                                                        dres != nullptr, view_of(y), stats, red, act,
+                                                                        view_of(dy));
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_act_bwd(const fpg_act* dz, const fpg_act* z, int act, const fpg_act* dx, void* stream) {
+  FPG_REQUIRE(dz && z && dx, "null argument");
+  const int64_t total = static_cast<int64_t>(z->n) * z->h * z->w * (z->c / 8);
+  act_bwd_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(dz), view_of(z), act, view_of(dx));
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_halo_fold(const fpg_act* a, const fpg_act* b, const fpg_act* c, void* stream) {
+  FPG_REQUIRE(a && c, "null argument");
+  const int64_t total = static_cast<int64_t>(c->n) * c->h * c->w * (c->c / 8);
+  fold_add_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(a), b ? view_of(b) : view_of(a),
+                                                                    b != nullptr, view_of(c));
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_bias_grad(const fpg_act* dy, float* db, int32_t k_valid, void* stream) {
+  FPG_REQUIRE(dy && db && dy->c % 8 == 0, "bad argument");
+  bias_grad_kernel<<<dy->c / 8, 256, 0, FPG_ST(stream)>>>(view_of(dy), db, k_valid);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_blend_fwd(const fpg_act* content, const fpg_act* logits, const fpg_act* input, const fpg_act* out,
+                  int32_t out_c0, float* out_nchw, float* mask_nhw, void* stream) {
+  FPG_REQUIRE(content && logits && input, "null argument");
+  FPG_REQUIRE(content->c_stride >= 28 && logits->c_stride >= 12 && content->fp32 && logits->fp32,
+              "blend expects fp32 content (>=28 ch) and logits (>=12 ch)");
+  View ov;
+  if (out) {
+    ov = view_of(out);
+  } else {
+    ov = view_of(content);
+    ov.p = nullptr;
+  }
+  const int64_t total = static_cast<int64_t>(content->n) * content->h * content->w;
+  blend_fwd_kernel<<<grid_for(total, 128), 128, 0, FPG_ST(stream)>>>(view_of(content), view_of(logits),
+                                                                     view_of(input), ov, out_c0, out_nchw, mask_nhw);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_blend_bwd(const float* dout_nchw, const fpg_act* dout_nhwc, int32_t dout_c0, const fpg_act* content,
+                  const fpg_act* logits, const fpg_act* input, const fpg_act* dcontent, const fpg_act* dlogits,
+                  float* dimage_nchw, void* stream) {
+  FPG_REQUIRE(content && logits && input && dcontent && dlogits, "null argument");
+  FPG_REQUIRE(dcontent->c_stride >= 32 && dlogits->c_stride >= 16, "gradient buffers too narrow");
+  View gv;
+  if (dout_nhwc) {
+    gv = view_of(dout_nhwc);
+  } else {
+    gv = view_of(content);
+    gv.p = nullptr;
+  }
+  const int64_t total = static_cast<int64_t>(content->n) * content->h * content->w;
+  blend_bwd_kernel<<<grid_for(total, 128), 128, 0, FPG_ST(stream)>>>(dout_nchw, gv, dout_c0, view_of(content),
+                                                                     view_of(logits), view_of(input),
+                                                                     view_of(dcontent), view_of(dlogits), dimage_nchw);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_mse_const_loss(const fpg_act* logits, float target, float weight, float grad_scale, float* loss,
+                       const fpg_act* dlogits, void* stream) {
+  FPG_REQUIRE(logits && logits->fp32, "logits must be fp32");
+  View gv;
+  if (dlogits) {
+    gv = view_of(dlogits);
+  } else {
+    gv = view_of(logits);
+    gv.p = nullptr;
+  }
+  mse_const_kernel<<<1, 1024, 0, FPG_ST(stream)>>>(view_of(logits), target, weight, grad_scale, loss, gv);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_l1_loss(const float* pred, const float* target, int64_t count, float weight, float grad_scale, float* loss,
+                float* dpred, int accumulate, float* scratch, void* stream) {
+  FPG_REQUIRE(pred && target && loss && scratch && count > 0, "bad argument");
+  const float gcoef = grad_scale * weight / static_cast<float>(count);
+  l1_partial_kernel<<<kL1Blocks, 256, 0, FPG_ST(stream)>>>(pred, target, count, gcoef, dpred, accumulate, scratch);
+  l1_finalize_kernel<<<1, 512, 0, FPG_ST(stream)>>>(scratch, kL1Blocks, weight / static_cast<float>(count), loss);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_pack_nchw(const float* src, int32_t c_src, const fpg_act* dst, int32_t c0, int zero_rest, void* stream) {
+  FPG_REQUIRE(src && dst && c0 + c_src <= dst->c_stride, "bad argument");
+  const int64_t total = static_cast<int64_t>(dst->n) * (dst->h + 2 * dst->halo) * (dst->w + 2 * dst->halo);
+  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(src, c_src, view_of(dst), c0, zero_rest);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_unpack_nchw(const fpg_act* src, int32_t c0, float* dst, int32_t c_dst, int accumulate, void* stream) {
+  FPG_REQUIRE(src && dst && c0 + c_dst <= src->c_stride, "bad argument");
+  const int64_t total = static_cast<int64_t>(src->n) * src->h * src->w;
+  unpack_nchw_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(src), c0, dst, c_dst, accumulate);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2,
+                  float eps, int32_t step, float grad_scale, void* stream) {
+  FPG_REQUIRE(p && g && m && v && count > 0 && step >= 1, "bad argument");
+  // bias corrections in double like torch (python floats), then rounded to fp32 scalars
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
+  const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  const float bc2_sqrt = static_cast<float>(sqrt(bc2));
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 2368) blocks = 2368;
+  adam_kernel<<<static_cast<unsigned>(blocks), 256, 0, FPG_ST(stream)>>>(p, g, m, v, count, beta1, beta2, eps,
+                                                                         step_size, bc2_sqrt, grad_scale);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_flood_mask(const float* logits, float* mask, int64_t count, void* stream) {
+  FPG_REQUIRE(logits && mask && count > 0, "bad argument");
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 2368) blocks = 2368;
+  flood_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, FPG_ST(stream)>>>(logits, mask, count);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_confusion_counts(const float* pred, const float* truth, int64_t count, int64_t* counts4, void* stream) {
+  FPG_REQUIRE(pred && truth && counts4 && count > 0, "bad argument");
+  FPG_CUDA_CHECK(cudaMemsetAsync(counts4, 0, 4 * sizeof(int64_t), FPG_ST(stream)));
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  confusion_kernel<<<static_cast<unsigned>(blocks), 256, 0, FPG_ST(stream)>>>(
+      pred, truth, count, reinterpret_cast<unsigned long long*>(counts4));
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

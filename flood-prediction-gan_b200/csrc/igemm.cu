@@ -1,0 +1,524 @@
+// Implicit-GEMM convolution kernels for sm_100a: TMA-gathered operands, tcgen05.mma with TMEM accumulators.
+//
+//  igemm_fprop_kernel : D[pixel, k] = sum_{tap, c} A[pixel + tap, c] * B[k, (tap, c)]      (fprop, dgrad, convT)
+//  igemm_wgrad_kernel : D[m, n]     = sum_{pixel}  X[pixel + xtap, m] * Y[pixel + ytap, n]  (wgrad, split over pixels)
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM owner + MMA issuer (one
+// elected lane), warps 2..5 = epilogue (TMEM -> registers -> global). One CTA per SM (TMEM: all 512 columns).
+#include "common.cuh"
+#include "host_util.h"
+
+namespace fpg {
+
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;  // columns per accumulator stage
+
+struct FpropArgs {
+  int32_t chunks_per_tap;
+  int32_t num_kstages;
+  int32_t block_n;
+  int32_t n_blocks;
+  int32_t n_img, tiles_y, tiles_x;
+  int32_t tile_w_log2;
+  int32_t tile_h, tile_w;
+  int32_t act;
+  int32_t stages;
+  const float* bias;
+  fpg_out_view out;
+  fpg_tap taps[FPG_MAX_TAPS];
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case FPG_ACT_RELU: return fmaxf(v, 0.f);
+    case FPG_ACT_LEAKY: return v > 0.f ? v : 0.2f * v;
+    case FPG_ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+template <int CBLK>
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
+                   const __grid_constant__ FpropArgs args) {
+  constexpr int SUB = 64 / CBLK;                   // TMA sub-loads per 64-wide K stage
+  constexpr uint32_t A_SUB_BYTES = 128u * CBLK * 2u;
+  constexpr uint32_t A_STAGE_BYTES = 128u * 64u * 2u;
+  constexpr uint32_t LAYOUT = swizzle_layout_type(CBLK * 2);
+  constexpr uint32_t SBO = 8u * CBLK * 2u;  // 8 rows of one swizzle atom
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int BN = args.block_n;
+  const uint32_t B_SUB_BYTES = static_cast<uint32_t>(BN) * CBLK * 2u;
+  const uint32_t B_STAGE_BYTES = static_cast<uint32_t>(BN) * 128u;
+  const int STAGES = args.stages;
+
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&amap);
+    tma_prefetch_desc(&bmap);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = args.n_img * args.tiles_y * args.tiles_x * args.n_blocks;
+  const int num_kstages = args.num_kstages;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t stage_bytes = A_STAGE_BYTES + B_STAGE_BYTES;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int nb = tile % args.n_blocks;
+        int r = tile / args.n_blocks;
+        int tx = r % args.tiles_x;
+        r /= args.tiles_x;
+        int ty = r % args.tiles_y;
+        int n = r / args.tiles_y;
+        const int x0 = tx * args.tile_w, y0 = ty * args.tile_h;
+        int sub = 0;
+        for (int ks = 0; ks < num_kstages; ++ks) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], stage_bytes);
+          uint8_t* a_dst = smem_a + stage * A_STAGE_BYTES;
+          uint8_t* b_dst = smem_b + stage * B_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < SUB; ++j, ++sub) {
+            const int tap = sub / args.chunks_per_tap;
+            const int chunk = sub - tap * args.chunks_per_tap;
+            const fpg_tap t = args.taps[tap];
+            tma_load_5d(&amap, &full[stage], a_dst + j * A_SUB_BYTES, t.c0 + chunk * CBLK, x0 + t.dx, t.plane,
+                        y0 + t.dy, n);
+            tma_load_2d(&bmap, &full[stage], b_dst + j * B_SUB_BYTES, sub * CBLK, nb * BN);
+          }
+          if (++stage == static_cast<uint32_t>(STAGES)) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        for (int ks = 0; ks < num_kstages; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < SUB; ++j) {
+#pragma unroll
+            for (int k = 0; k < CBLK / 16; ++k) {
+              const uint64_t ad = make_smem_desc(a_addr + j * A_SUB_BYTES + k * 32, 0, SBO, LAYOUT);
+              const uint64_t bd = make_smem_desc(b_addr + j * B_SUB_BYTES + k * 32, 0, SBO, LAYOUT);
+              umma_bf16(d_tmem, ad, bd, idesc, (ks | j | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == static_cast<uint32_t>(STAGES)) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[as]);  // accumulator complete
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int ry = row >> args.tile_w_log2;
+    const int rx = row & (args.tile_w - 1);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      int nb = tile % args.n_blocks;
+      int r = tile / args.n_blocks;
+      int tx = r % args.tiles_x;
+      r /= args.tiles_x;
+      int ty = r % args.tiles_y;
+      int n = r / args.tiles_y;
+      const int py = ty * args.tile_h + ry, px = tx * args.tile_w + rx;
+      const bool valid = (py < args.out.valid_h) && (px < args.out.valid_w);
+      const int64_t off = static_cast<int64_t>(n) * args.out.stride_n +
+                          static_cast<int64_t>(py * args.out.mul_y + args.out.off_y) * args.out.stride_y +
+                          static_cast<int64_t>(px * args.out.mul_x + args.out.off_x) * args.out.stride_x +
+                          static_cast<int64_t>(nb) * BN;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_addr + c, v);
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+        if (args.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(args.bias + nb * BN + c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = __ldg(bp + i);
+            f[4 * i + 0] += b4.x;
+            f[4 * i + 1] += b4.y;
+            f[4 * i + 2] += b4.z;
+            f[4 * i + 3] += b4.w;
+          }
+        }
+        if (args.act != FPG_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], args.act);
+        }
+        if (valid) {
+          if (args.out.fp32) {
+            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out.base) + off + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out.base) + off + c);
+            dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                pack_bf16x2(f[6], f[7]));
+            dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                                pack_bf16x2(f[14], f[15]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+struct WgradArgs {
+  int32_t x_ca, y_ca, x_atoms, y_atoms;
+  int32_t x_groups, y_groups, x_taps_mode, y_taps_mode, x_ntaps, y_ntaps;
+  int32_t n_img, kt_y, kt_x, tile_h, tile_w;
+  int32_t splits, stages;
+  float* ws;
+  fpg_tap x_taps[FPG_MAX_TAPS];
+  fpg_tap y_taps[FPG_MAX_TAPS];
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap,
+                   const __grid_constant__ WgradArgs args) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int M = args.x_atoms * args.x_ca;
+  const int N = args.y_atoms * args.y_ca;
+  const uint32_t X_ATOM_BYTES = 64u * args.x_ca * 2u;  // 64 pixel rows of one channel atom
+  const uint32_t Y_ATOM_BYTES = 64u * args.y_ca * 2u;
+  const uint32_t X_STAGE_BYTES = X_ATOM_BYTES * args.x_atoms;
+  const uint32_t Y_STAGE_BYTES = Y_ATOM_BYTES * args.y_atoms;
+  const int STAGES = args.stages;
+
+  uint8_t* smem_x = smem;
+  uint8_t* smem_y = smem + STAGES * X_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_y + STAGES * Y_STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&xmap);
+    tma_prefetch_desc(&ymap);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work decomposition: blockIdx.x = (split, xi, yi)
+  const int NX = args.x_taps_mode ? args.x_groups : args.x_groups * args.x_ntaps;
+  const int NY = args.y_taps_mode ? args.y_groups : args.y_groups * args.y_ntaps;
+  const int items = NX * NY;
+  const int item = blockIdx.x % items;
+  const int split = blockIdx.x / items;
+  const int xi = item / NY, yi = item % NY;
+  const int total_kt = args.n_img * args.kt_y * args.kt_x;
+  const int kt_begin = static_cast<int>(static_cast<int64_t>(total_kt) * split / args.splits);
+  const int kt_end = static_cast<int>(static_cast<int64_t>(total_kt) * (split + 1) / args.splits);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // operand tile -> (tap, channel offset) per atom
+      const int xg = args.x_taps_mode ? xi : xi % args.x_groups;
+      const int xt = args.x_taps_mode ? 0 : xi / args.x_groups;
+      const int yg = args.y_taps_mode ? yi : yi % args.y_groups;
+      const int yt = args.y_taps_mode ? 0 : yi / args.y_groups;
+      uint32_t stage = 0, phase = 0;
+      const uint32_t stage_bytes = X_STAGE_BYTES + Y_STAGE_BYTES;
+      for (int kt = kt_begin; kt < kt_end; ++kt) {
+        const int kx = kt % args.kt_x;
+        const int r = kt / args.kt_x;
+        const int ky = r % args.kt_y;
+        const int n = r / args.kt_y;
+        const int x0 = kx * args.tile_w, y0 = ky * args.tile_h;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], stage_bytes);
+        uint8_t* x_dst = smem_x + stage * X_STAGE_BYTES;
+        uint8_t* y_dst = smem_y + stage * Y_STAGE_BYTES;
+        for (int a = 0; a < args.x_atoms; ++a) {
+          int tap, coff;
+          if (args.x_taps_mode) {
+            tap = xg * args.x_atoms + a;
+            if (tap >= args.x_ntaps) tap = 0;
+            coff = 0;
+          } else {
+            tap = xt;
+            coff = (xg * args.x_atoms + a) * args.x_ca;
+          }
+          const fpg_tap t = args.x_taps[tap];
+          tma_load_5d(&xmap, &full[stage], x_dst + a * X_ATOM_BYTES, t.c0 + coff, x0 + t.dx, t.plane, y0 + t.dy, n);
+        }
+        for (int a = 0; a < args.y_atoms; ++a) {
+          int tap, coff;
+          if (args.y_taps_mode) {
+            tap = yg * args.y_atoms + a;
+            if (tap >= args.y_ntaps) tap = 0;
+            coff = 0;
+          } else {
+            tap = yt;
+            coff = (yg * args.y_atoms + a) * args.y_ca;
+          }
+          const fpg_tap t = args.y_taps[tap];
+          tma_load_5d(&ymap, &full[stage], y_dst + a * Y_ATOM_BYTES, t.c0 + coff, x0 + t.dx, t.plane, y0 + t.dy, n);
+        }
+        if (++stage == static_cast<uint32_t>(STAGES)) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(M, N, 1, 1);  // both operands MN-major (pixel rows, channel-contiguous)
+      const uint32_t x_layout = swizzle_layout_type(args.x_ca * 2), y_layout = swizzle_layout_type(args.y_ca * 2);
+      const uint32_t x_sbo = 8u * args.x_ca * 2u, y_sbo = 8u * args.y_ca * 2u;  // 8 pixel rows
+      const uint32_t x_kstep = 16u * args.x_ca * 2u, y_kstep = 16u * args.y_ca * 2u;  // 16 pixel rows per MMA
+      uint32_t stage = 0, phase = 0;
+      bool first = true;
+      for (int kt = kt_begin; kt < kt_end; ++kt) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t x_addr = smem_u32(smem_x + stage * X_STAGE_BYTES);
+        const uint32_t y_addr = smem_u32(smem_y + stage * Y_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t xd = make_smem_desc(x_addr + k * x_kstep, X_ATOM_BYTES, x_sbo, x_layout);
+          const uint64_t yd = make_smem_desc(y_addr + k * y_kstep, Y_ATOM_BYTES, y_sbo, y_layout);
+          umma_bf16(tmem_base, xd, yd, idesc, first ? 0u : 1u);
+          first = false;
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == static_cast<uint32_t>(STAGES)) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    const int q = warp & 3;
+    // M == 128: row = 32q + lane. M == 64: rows 16q..16q+15 live in lanes 0..15 of quarter q.
+    const int row = (M == 128) ? q * 32 + lane : q * 16 + lane;
+    const bool row_valid = (M == 128) || (lane < 16);
+    float* dst = args.ws + (static_cast<int64_t>(split) * items + item) * M * N + static_cast<int64_t>(row) * N;
+    if (kt_end > kt_begin) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int c = 0; c < N; c += 16) {
+      uint32_t v[16];
+      if (kt_end > kt_begin) {
+        tmem_ld16(t_addr + c, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0u;
+      }
+      if (row_valid) {
+        float4* d4 = reinterpret_cast<float4*>(dst + c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                              __uint_as_float(v[4 * i + 3]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+static int log2_exact(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return (1 << l) == v ? l : -1;
+}
+
+}  // namespace fpg
+
+using namespace fpg;
+
+extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* stream) {
+  FPG_REQUIRE(d != nullptr, "null descriptor");
+  FPG_REQUIRE(d->cblk == 16 || d->cblk == 32 || d->cblk == 64, "cblk %d", d->cblk);
+  FPG_REQUIRE(d->block_n >= 16 && d->block_n <= 256 && d->block_n % 16 == 0, "block_n %d", d->block_n);
+  FPG_REQUIRE(d->tile_h * d->tile_w == 128 && log2_exact(d->tile_w) >= 0, "tile %dx%d", d->tile_h, d->tile_w);
+  const int sub_per_stage = 64 / d->cblk;
+  FPG_REQUIRE(d->num_sub > 0 && d->num_sub % sub_per_stage == 0, "num_sub %d", d->num_sub);
+  FPG_REQUIRE(d->c_per_tap % d->cblk == 0, "c_per_tap %d", d->c_per_tap);
+  FPG_REQUIRE(d->num_taps <= FPG_MAX_TAPS && d->num_taps * (d->c_per_tap / d->cblk) == d->num_sub, "taps %d",
+              d->num_taps);
+  FPG_REQUIRE(d->stages >= 2 && d->stages <= 8, "stages %d", d->stages);
+  CUtensorMap amap, bmap;
+  int rc = encode_tmap(&d->a, &amap);
+  if (rc) return rc;
+  rc = encode_tmap(&d->b, &bmap);
+  if (rc) return rc;
+
+  FpropArgs args;
+  args.chunks_per_tap = d->c_per_tap / d->cblk;
+  args.num_kstages = d->num_sub / sub_per_stage;
+  args.block_n = d->block_n;
+  args.n_blocks = d->n_blocks;
+  args.n_img = d->n_img;
+  args.tiles_y = d->tiles_y;
+  args.tiles_x = d->tiles_x;
+  args.tile_w_log2 = log2_exact(d->tile_w);
+  args.tile_h = d->tile_h;
+  args.tile_w = d->tile_w;
+  args.act = d->act;
+  args.stages = d->stages;
+  args.bias = d->bias;
+  args.out = d->out;
+  for (int i = 0; i < FPG_MAX_TAPS; ++i) args.taps[i] = d->taps[i];
+
+  const int total_tiles = d->n_img * d->tiles_y * d->tiles_x * d->n_blocks;
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
+  const int grid = total_tiles < sms ? total_tiles : sms;
+  const size_t smem = static_cast<size_t>(d->stages) * (16384 + d->block_n * 128) + (2 * d->stages + 4) * 8 + 16 + 1024;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define FPG_LAUNCH_FPROP(CB)                                                                                     \
+  do {                                                                                                           \
+    FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_fprop_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                        static_cast<int>(smem)));                                                \
+    igemm_fprop_kernel<CB><<<grid, kThreads, smem, st>>>(amap, bmap, args);                                      \
+  } while (0)
+  if (d->cblk == 64) {
+    FPG_LAUNCH_FPROP(64);
+  } else if (d->cblk == 32) {
+    FPG_LAUNCH_FPROP(32);
+  } else {
+    FPG_LAUNCH_FPROP(16);
+  }
+#undef FPG_LAUNCH_FPROP
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int fpg_igemm_wgrad_launch(const fpg_igemm_wgrad_desc* d, void* stream) {
+  FPG_REQUIRE(d != nullptr, "null descriptor");
+  const int M = d->x_atoms * d->x_ca, N = d->y_atoms * d->y_ca;
+  FPG_REQUIRE(M == 64 || M == 128, "wgrad M %d", M);
+  FPG_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "wgrad N %d", N);
+  FPG_REQUIRE(d->tile_h * d->tile_w == 64, "k tile %dx%d", d->tile_h, d->tile_w);
+  FPG_REQUIRE(d->stages >= 2 && d->stages <= 8 && d->splits >= 1, "stages %d splits %d", d->stages, d->splits);
+  FPG_REQUIRE(d->ws != nullptr, "null workspace");
+  CUtensorMap xmap, ymap;
+  int rc = encode_tmap(&d->x, &xmap);
+  if (rc) return rc;
+  rc = encode_tmap(&d->y, &ymap);
+  if (rc) return rc;
+  WgradArgs args;
+  args.x_ca = d->x_ca;
+  args.y_ca = d->y_ca;
+  args.x_atoms = d->x_atoms;
+  args.y_atoms = d->y_atoms;
+  args.x_groups = d->x_groups;
+  args.y_groups = d->y_groups;
+  args.x_taps_mode = d->x_taps_mode;
+  args.y_taps_mode = d->y_taps_mode;
+  args.x_ntaps = d->x_ntaps;
+  args.y_ntaps = d->y_ntaps;
+  args.n_img = d->n_img;
+  args.kt_y = d->kt_y;
+  args.kt_x = d->kt_x;
+  args.tile_h = d->tile_h;
+  args.tile_w = d->tile_w;
+  args.splits = d->splits;
+  args.stages = d->stages;
+  args.ws = d->ws;
+  for (int i = 0; i < FPG_MAX_TAPS; ++i) {
+    args.x_taps[i] = d->x_taps[i];
+    args.y_taps[i] = d->y_taps[i];
+  }
+  const int NX = d->x_taps_mode ? d->x_groups : d->x_groups * d->x_ntaps;
+  const int NY = d->y_taps_mode ? d->y_groups : d->y_groups * d->y_ntaps;
+  const int grid = NX * NY * d->splits;
+  const size_t smem = static_cast<size_t>(d->stages) * (M + N) * 128 + (2 * d->stages + 2) * 8 + 16 + 1024;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  igemm_wgrad_kernel<<<grid, kThreads, smem, st>>>(xmap, ymap, args);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}

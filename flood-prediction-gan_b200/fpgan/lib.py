@@ -1,0 +1,137 @@
+"""ctypes binding of libfpg_b200.so (C ABI declared in include/fpg.h).
+
+The library is the product's only compute path: there is no CPU fallback. Importing this module only loads the
+shared object (that works without a GPU, so symbol/plan tests can run on CPU); every compute call needs a B200.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "libfpg_b200.so")
+
+FPG_MAX_TAPS = 64
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
+
+
+class Tap(C.Structure):
+    _fields_ = [("c0", C.c_int32), ("dx", C.c_int32), ("plane", C.c_int32), ("dy", C.c_int32)]
+
+
+class TMap(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("rank", C.c_int32), ("swizzle_bytes", C.c_int32),
+                ("dims", C.c_uint64 * 5), ("strides", C.c_uint64 * 4), ("box", C.c_uint32 * 5)]
+
+
+class OutView(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("stride_n", C.c_int64), ("stride_y", C.c_int64), ("stride_x", C.c_int64),
+                ("mul_y", C.c_int32), ("off_y", C.c_int32), ("mul_x", C.c_int32), ("off_x", C.c_int32),
+                ("valid_h", C.c_int32), ("valid_w", C.c_int32), ("fp32", C.c_int32)]
+
+
+class FpropDesc(C.Structure):
+    _fields_ = [("a", TMap), ("b", TMap), ("cblk", C.c_int32), ("c_per_tap", C.c_int32), ("num_taps", C.c_int32),
+                ("num_sub", C.c_int32), ("block_n", C.c_int32), ("n_blocks", C.c_int32), ("n_img", C.c_int32),
+                ("tiles_y", C.c_int32), ("tiles_x", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32),
+                ("act", C.c_int32), ("stages", C.c_int32), ("bias", C.c_void_p), ("out", OutView),
+                ("taps", Tap * FPG_MAX_TAPS)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("x", TMap), ("y", TMap), ("x_ca", C.c_int32), ("y_ca", C.c_int32), ("x_atoms", C.c_int32),
+                ("y_atoms", C.c_int32), ("x_groups", C.c_int32), ("y_groups", C.c_int32),
+                ("x_taps_mode", C.c_int32), ("y_taps_mode", C.c_int32), ("x_ntaps", C.c_int32),
+                ("y_ntaps", C.c_int32), ("n_img", C.c_int32), ("kt_y", C.c_int32), ("kt_x", C.c_int32),
+                ("tile_h", C.c_int32), ("tile_w", C.c_int32), ("splits", C.c_int32), ("stages", C.c_int32),
+                ("x_is_dy", C.c_int32), ("taps_r", C.c_int32), ("taps_s", C.c_int32), ("ws", C.c_void_p),
+                ("x_taps", Tap * FPG_MAX_TAPS), ("y_taps", Tap * FPG_MAX_TAPS)]
+
+
+class Act(C.Structure):
+    """fpg_act: NHWC activation buffer descriptor."""
+    _fields_ = [("data", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+                ("c_stride", C.c_int32), ("halo", C.c_int32), ("fp32", C.c_int32)]
+
+
+class ConvGeom(C.Structure):
+    _fields_ = [("r", C.c_int32), ("s", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
+                ("c_in", C.c_int32), ("c_out", C.c_int32)]
+
+
+_P = C.POINTER
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); kept in one table so the "exports every declared symbol" test can iterate it
+SIGNATURES = {
+    "fpg_abi_version": (C.c_int, []),
+    "fpg_last_error": (C.c_char_p, []),
+    "fpg_sm_count": (C.c_int, []),
+    "fpg_igemm_fprop_launch": (C.c_int, [_P(FpropDesc), _vp]),
+    "fpg_igemm_wgrad_launch": (C.c_int, [_P(WgradDesc), _vp]),
+    "fpg_conv2d_fprop": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), _vp]),
+    "fpg_conv2d_fprop_plan": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), C.c_int, _P(FpropDesc)]),
+    "fpg_conv2d_dgrad": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), _vp]),
+    "fpg_conv2d_dgrad_plan": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), C.c_int, _P(FpropDesc),
+                                        _P(C.c_int)]),
+    "fpg_conv2d_wgrad": (C.c_int, [_P(Act), _P(Act), _P(ConvGeom), _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
+    "fpg_conv2d_wgrad_plan": (C.c_int, [_P(Act), _P(Act), _P(ConvGeom), C.c_int, _P(WgradDesc)]),
+    "fpg_conv2d_wgrad_ws_bytes": (_i64, [_P(Act), _P(Act), _P(ConvGeom), C.c_int]),
+    "fpg_pack_weights": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _P(ConvGeom), _vp, _vp]),
+    "fpg_pack_weights_dgrad": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _P(ConvGeom), _vp, _vp]),
+    "fpg_dgrad_class_info": (C.c_int, [_P(ConvGeom), C.c_int, _P(_i32), _P(_i32), _P(_i64), _P(_i32)]),
+    "fpg_packed_weight_bytes": (_i64, [_P(ConvGeom)]),
+    "fpg_packed_weight_dgrad_bytes": (_i64, [_P(ConvGeom)]),
+    "fpg_bias_grad": (C.c_int, [_P(Act), _vp, _i32, _vp]),
+    "fpg_instnorm_scratch_floats": (_i64, [_P(Act)]),
+    "fpg_instnorm_stats": (C.c_int, [_P(Act), _f32, _vp, _vp, _vp]),
+    "fpg_instnorm_apply": (C.c_int, [_P(Act), _vp, C.c_int, _P(Act), _P(Act), _vp]),
+    "fpg_instnorm_bwd": (C.c_int, [_P(Act), _P(Act), _P(Act), _vp, C.c_int, _P(Act), _P(Act), _vp, _vp]),
+    "fpg_act_bwd": (C.c_int, [_P(Act), _P(Act), C.c_int, _P(Act), _vp]),
+    "fpg_halo_fold": (C.c_int, [_P(Act), _P(Act), _P(Act), _vp]),
+    "fpg_blend_fwd": (C.c_int, [_P(Act), _P(Act), _P(Act), _P(Act), _i32, _vp, _vp, _vp]),
+    "fpg_blend_bwd": (C.c_int, [_vp, _P(Act), _i32, _P(Act), _P(Act), _P(Act), _P(Act), _P(Act), _vp, _vp]),
+    "fpg_mse_const_loss": (C.c_int, [_P(Act), _f32, _f32, _f32, _vp, _P(Act), _vp]),
+    "fpg_l1_loss": (C.c_int, [_vp, _vp, _i64, _f32, _f32, _vp, _vp, C.c_int, _vp, _vp]),
+    "fpg_pack_nchw": (C.c_int, [_vp, _i32, _P(Act), _i32, C.c_int, _vp]),
+    "fpg_unpack_nchw": (C.c_int, [_P(Act), _i32, _vp, _i32, C.c_int, _vp]),
+    "fpg_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
+    "fpg_flood_mask": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "fpg_confusion_counts": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+}
+
+_lib = None
+
+
+class FpgError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libfpg_b200.so (raises if it has not been built: there is no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FpgError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C flood-prediction-gan_b200/csrc`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.fpg_abi_version() != 1:
+        raise FpgError("libfpg_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().fpg_last_error().decode("utf-8", "replace")
+        raise FpgError(f"{what} failed with code {rc}: {msg}")
+
+
+def call(name, *args):
+    """Call a status-returning entry point and raise FpgError on a non-zero status."""
+    rc = getattr(load(), name)(*args)
+    check(rc, name)

@@ -1,0 +1,272 @@
+/*
+ * fpg.h -- C ABI of libfpg_b200.so, the sm_100a kernel library behind the GAN training-step hot path of
+ * Natasha-R/Flood-Prediction-GAN (reference: models/model_architectures.py, models/model.py:598-758).
+ *
+ * The reference has no FFI of its own: every operator below replaces a torch.nn / ATen call site on that path
+ * (cited per function as file:line relative to the reference root). Conventions:
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - activations are NHWC bf16 ("pixel-major": the channel run of one pixel is contiguous), channel counts
+ *     padded to a multiple of 16 with the padding kept at exactly 0;
+ *   - buffers are owned by the caller; kernels borrow them for the launch, allocate nothing, keep no state;
+ *   - `stream` is a cudaStream_t passed as void*; all launches are asynchronous on it;
+ *   - return value: 0 on success, otherwise a cudaError_t / CUresult code or a negative FPG_E* code.
+ *     fpg_last_error() returns a human-readable message for the calling thread. No exceptions cross the ABI.
+ *   - there is no CPU fallback: on a machine without an sm_100 GPU every compute call fails.
+ */
+#ifndef FPG_H_
+#define FPG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPG_ABI_VERSION 1
+#define FPG_MAX_TAPS 64
+
+#define FPG_EINVAL (-22)
+#define FPG_ENOTSUP (-95)
+
+/* activation codes for fused epilogues / elementwise passes */
+#define FPG_ACT_NONE 0
+#define FPG_ACT_RELU 1
+#define FPG_ACT_LEAKY 2 /* LeakyReLU(0.2) */
+#define FPG_ACT_TANH 3
+
+int fpg_abi_version(void);
+const char* fpg_last_error(void);
+/* number of SMs of the current device (148 on B200); <0 on error */
+int fpg_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Generic implicit-GEMM descriptors. The semantic conv entry points below are thin planners that fill these and
+ * launch; the *_plan variants only fill the descriptor (pure host code, usable without a GPU) so that tests can
+ * check the gather geometry against an independent CPU interpreter.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* One filter tap as TMA coordinate offsets into a 5-D view (c, x, plane, y, n) of an NHWC tensor. */
+typedef struct {
+  int32_t c0;    /* offset on dim 0 (channel, or x-parity * channel-stride for stride-2 views) */
+  int32_t dx;    /* offset on dim 1 (x, or x/2) */
+  int32_t plane; /* coordinate on dim 2 (row-parity plane; 0 for stride-1 views) */
+  int32_t dy;    /* offset on dim 3 (y, or y/2) */
+} fpg_tap;
+
+/* A bf16 tensor view for TMA: rank <= 5, dim 0 contiguous. strides[i] is the byte stride of dim i+1. */
+typedef struct {
+  void* base;
+  int32_t rank;
+  int32_t swizzle_bytes; /* 32 / 64 / 128 == box[0] * 2 */
+  uint64_t dims[5];
+  uint64_t strides[4];
+  uint32_t box[5];
+} fpg_tmap;
+
+/* out[n, y*mul_y+off_y, x*mul_x+off_x, k] for tile pixel (n, y, x), element strides */
+typedef struct {
+  void* base;
+  int64_t stride_n, stride_y, stride_x; /* in elements */
+  int32_t mul_y, off_y, mul_x, off_x;
+  int32_t valid_h, valid_w; /* tile pixels with y >= valid_h or x >= valid_w are not stored */
+  int32_t fp32;             /* 0: bf16 output, 1: fp32 output */
+} fpg_out_view;
+
+/* D[pixel, k] = sum_{tap, c} A[pixel + tap, c] * B[k, tap*C + c]  (+bias, activation) */
+typedef struct {
+  fpg_tmap a;      /* gathered operand: box = {cblk, tile_w, 1, tile_h, 1}, tile_w*tile_h == 128 */
+  fpg_tmap b;      /* weight matrix [n_total rows][num_sub*cblk], K-major: box = {cblk, block_n} */
+  int32_t cblk;    /* channels per TMA sub-load: 16 / 32 / 64 */
+  int32_t c_per_tap; /* channels per tap (multiple of cblk) */
+  int32_t num_taps;  /* taps listed in taps[] (incl. zero-weight padding taps) */
+  int32_t num_sub;   /* num_taps * c_per_tap / cblk; multiple of 64/cblk */
+  int32_t block_n;   /* N tile: multiple of 16, <= 256 */
+  int32_t n_blocks;  /* n_total / block_n */
+  int32_t n_img, tiles_y, tiles_x, tile_h, tile_w;
+  int32_t act;
+  int32_t stages;
+  const float* bias; /* [n_total] or NULL */
+  fpg_out_view out;
+  fpg_tap taps[FPG_MAX_TAPS];
+} fpg_igemm_fprop_desc;
+
+/* D_item[m, n] = sum_{pixel} X[pixel + xtap, xc + m] * Y[pixel + ytap, yc + n], split over pixel ranges,
+ * partial tiles written as fp32 to ws[split][item][M][N]. */
+typedef struct {
+  fpg_tmap x, y;          /* box = {ca, tile_w, 1, tile_h, 1}, tile_w*tile_h == 64 */
+  int32_t x_ca, y_ca;     /* atom width in channels: 16 / 32 / 64 */
+  int32_t x_atoms, y_atoms; /* M = x_atoms*x_ca in {64,128}; N = y_atoms*y_ca, multiple of 16 (8 if M==64), <= 256 */
+  int32_t x_groups, y_groups;
+  int32_t x_taps_mode, y_taps_mode; /* 1: atom index enumerates taps; 0: atom index enumerates channel chunks */
+  int32_t x_ntaps, y_ntaps;
+  int32_t n_img, kt_y, kt_x, tile_h, tile_w;
+  int32_t splits, stages;
+  int32_t x_is_dy; /* 1: X operand is the output gradient (rows of D are output channels); 0: X is the input */
+  int32_t taps_r, taps_s; /* filter size, for mapping tap index -> (r, s) when reducing */
+  float* ws;
+  fpg_tap x_taps[FPG_MAX_TAPS];
+  fpg_tap y_taps[FPG_MAX_TAPS];
+} fpg_igemm_wgrad_desc;
+
+int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* stream);
+int fpg_igemm_wgrad_launch(const fpg_igemm_wgrad_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Convolution family (replaces nn.Conv2d / nn.ConvTranspose2d forward and aten::convolution_backward;
+ * model_architectures.py:312-334 (generator), :407-416 (residual blocks), :424-437 (PatchGAN)).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* An NHWC bf16 activation buffer. `halo` pixels of materialised border surround the h x w interior
+ * (reflect halo written by the producer); c_stride >= c is the per-pixel element stride, `data` points at
+ * channel 0 of the first halo pixel. */
+typedef struct {
+  void* data;
+  int32_t n, h, w, c;
+  int32_t c_stride;
+  int32_t halo;
+  int32_t fp32; /* only meaningful for outputs */
+} fpg_act;
+
+typedef struct {
+  int32_t r, s;     /* filter size */
+  int32_t stride;   /* 1 or 2 */
+  int32_t pad;      /* zero padding (TMA out-of-bounds fill); reflect padding is a materialised input halo */
+  int32_t c_in;     /* padded input channels of the packed weight */
+  int32_t c_out;    /* padded output channels of the packed weight */
+} fpg_conv_geom;
+
+/* y = act(conv(x, w) + bias). w_packed: bf16 [c_out][r*s (padded to whole K stages)][c_in], see fpg_pack_weights.
+ * Reads x at interior + halo (x.halo must equal the reflect pad of the layer, or 0).
+ * nn.Conv2d call sites: model_architectures.py:343-345,353,369,414,416,424-437 */
+int fpg_conv2d_fprop(const fpg_act* x, const void* w_packed, const float* bias, int act, const fpg_conv_geom* g,
+                     const fpg_act* y, void* stream);
+int fpg_conv2d_fprop_plan(const fpg_act* x, const void* w_packed, const float* bias, int act,
+                          const fpg_conv_geom* g, const fpg_act* y, int sm_count, fpg_igemm_fprop_desc* out_desc);
+
+/* dx = conv_backward_data(dy, w). g describes the FORWARD conv (y = conv(x)); w_packed_t is the dgrad packing
+ * bf16 [c_in][taps][c_out] produced by fpg_pack_weights_dgrad. stride 1: one launch; stride 2: one launch per
+ * output-parity class (descs[0..3]). dx covers interior + halo of the forward input when dx->halo > 0
+ * (gradient w.r.t. the reflect-padded tensor; the halo fold happens in fpg_instnorm_bwd / fpg_halo_fold).
+ * Also the forward of nn.ConvTranspose2d (model_architectures.py:350-351,367-368) with x := dy.
+ * aten::convolution_backward (input grad): model.py:632,645 */
+int fpg_conv2d_dgrad(const fpg_act* dy, const void* w_packed_t, const float* bias, int act, const fpg_conv_geom* g,
+                     const fpg_act* dx, void* stream);
+int fpg_conv2d_dgrad_plan(const fpg_act* dy, const void* w_packed_t, const float* bias, int act,
+                          const fpg_conv_geom* g, const fpg_act* dx, int sm_count, fpg_igemm_fprop_desc* out_descs,
+                          int* n_descs);
+
+/* dw = conv_backward_weight(x, dy): fp32 gradient written (not accumulated) in the reference parameter layout.
+ *   dw[ko*dw_stride_k + ci*dw_stride_c + (r*S+s)] for ko < k_valid, ci < c_valid.
+ * nn.Conv2d weight [K][C][R][S]: dw_stride_k = C*R*S, dw_stride_c = R*S;
+ * nn.ConvTranspose2d weight [Cin_T][Cout_T][R][S] (call with x := dy_T, dy := x_T): see INTEGRATION.md.
+ * ws: fp32 workspace of at least fpg_conv2d_wgrad_ws_bytes() bytes.
+ * aten::convolution_backward (weight grad): model.py:632,645 */
+int fpg_conv2d_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g, float* dw, int64_t dw_stride_k,
+                     int64_t dw_stride_c, int32_t k_valid, int32_t c_valid, float* ws, void* stream);
+int fpg_conv2d_wgrad_plan(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g, int sm_count,
+                          fpg_igemm_wgrad_desc* out_desc);
+int64_t fpg_conv2d_wgrad_ws_bytes(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g, int sm_count);
+
+/* Weight repack fp32 parameter -> bf16 GEMM operand.
+ * fprop packing:  dst[k][t][c] = src[k*src_stride_k + c*src_stride_c + t]          (t = r*S+s)
+ * dgrad packing:  dst[c][t'][k] with the taps flipped / parity-grouped as fpg_conv2d_dgrad expects.
+ * Rows/taps/channels beyond the valid counts are written as 0. */
+int fpg_pack_weights(const float* src, int64_t src_stride_k, int64_t src_stride_c, int32_t k_valid, int32_t c_valid,
+                     const fpg_conv_geom* g, void* dst, void* stream);
+int fpg_pack_weights_dgrad(const float* src, int64_t src_stride_k, int64_t src_stride_c, int32_t k_valid,
+                           int32_t c_valid, const fpg_conv_geom* g, void* dst, void* stream);
+/* Introspection of the dgrad packing: for parity class `cls` (0 for stride 1; (oy&1)*2+(ox&1) for stride 2) returns
+ * the forward tap index r*S+s of every packed tap (-1 = zero padding tap), the padded tap count, the element offset
+ * of the class matrix [c_in][taps][c_out] inside the packed buffer and the number of classes. */
+int fpg_dgrad_class_info(const fpg_conv_geom* g, int cls, int32_t* src_tap /* [FPG_MAX_TAPS] */,
+                         int32_t* num_taps_padded, int64_t* elem_offset, int32_t* num_classes);
+/* bytes of the packed operands for geometry g */
+int64_t fpg_packed_weight_bytes(const fpg_conv_geom* g);
+int64_t fpg_packed_weight_dgrad_bytes(const fpg_conv_geom* g);
+
+/* db[k] = sum over pixels of dy[.., k]  (bias gradient), k < k_valid */
+int fpg_bias_grad(const fpg_act* dy, float* db, int32_t k_valid, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * InstanceNorm + activation (+ residual, + reflect halo) -- nn.InstanceNorm2d(eps=1e-5, affine=False) followed by
+ * F.relu / nn.LeakyReLU(0.2) / F.pad(reflect): model_architectures.py:313-333,342-352,408-416,430-436.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* scratch floats needed by fpg_instnorm_stats / fpg_instnorm_bwd for activation y */
+int64_t fpg_instnorm_scratch_floats(const fpg_act* y);
+/* stats[(n*C + c)*2 + {0,1}] = {mean, rstd} over the h*w plane of y (biased variance, eps). Deterministic
+ * two-stage reduction through `scratch`. */
+int fpg_instnorm_stats(const fpg_act* y, float eps, float* stats, float* scratch, void* stream);
+/* z = act((y - mean) * rstd) [+ residual]; written to z's interior and, if z->halo > 0, mirrored into its halo.
+ * residual may be NULL; it is read at interior coordinates (its own halo is skipped). */
+int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_act* residual, const fpg_act* z,
+                       void* stream);
+/* Backward of z = act(IN(y)). Upstream gradient g = fold(dz) + dz2, where dz is the gradient w.r.t. z INCLUDING
+ * its halo when dz->halo > 0 (folded back onto the interior: backward of F.pad(reflect)) and dz2 (may be NULL,
+ * halo ignored) is a second gradient branch (residual skip). Writes dy; if dres != NULL also writes g there
+ * (gradient flowing on to the residual input). */
+int fpg_instnorm_bwd(const fpg_act* dz, const fpg_act* dz2, const fpg_act* y, const float* stats, int act,
+                     const fpg_act* dy, const fpg_act* dres, float* scratch, void* stream);
+/* dx = fold(dz) * act'(z) for an activation without normalisation (PatchGAN model.0 LeakyReLU): z is the saved
+ * activation output */
+int fpg_act_bwd(const fpg_act* dz, const fpg_act* z, int act, const fpg_act* dx, void* stream);
+/* c = fold(a) + b  (b may be NULL): backward of F.pad(reflect) plus a gradient accumulation */
+int fpg_halo_fold(const fpg_act* a, const fpg_act* b, const fpg_act* c, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Attention / content blend -- model_architectures.py:353-399.
+ *   content: fp32, tanh already applied, 27 valid channels (9 RGB triplets) in a 32-channel buffer
+ *   logits:  fp32, 10 valid channels in a 16-channel buffer (pre-softmax)
+ *   image:   pre-flood RGB = channels 0..2 of `input` (interior of a possibly haloed buffer)
+ *   out = sum_k content_k * a_k + image * a_10, written as bf16 into `out` channels [out_c0, out_c0+3)
+ *   and as fp32 NCHW into out_nchw (may be NULL); mask_nhw (fp32 [n][h][w], may be NULL) gets a_10.
+ * ---------------------------------------------------------------------------------------------------------- */
+int fpg_blend_fwd(const fpg_act* content, const fpg_act* logits, const fpg_act* input, const fpg_act* out,
+                  int32_t out_c0, float* out_nchw, float* mask_nhw, void* stream);
+/* upstream gradient = dout_nchw (fp32 [n][3][h][w], may be NULL) + dout_nhwc channels [dout_c0, dout_c0+3)
+ * (bf16, may be NULL) -> dcontent (pre-tanh gradient, bf16 32 ch), dlogits (bf16 16 ch) and, if not NULL,
+ * dimage_nchw = gradient w.r.t. the pre-flood RGB (fp32 [n][3][h][w]; needed by the cycle models). */
+int fpg_blend_bwd(const float* dout_nchw, const fpg_act* dout_nhwc, int32_t dout_c0, const fpg_act* content,
+                  const fpg_act* logits, const fpg_act* input, const fpg_act* dcontent, const fpg_act* dlogits,
+                  float* dimage_nchw, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Losses -- nn.MSELoss against torch.full(target) (model.py:626-631,641-642) and nn.L1Loss * weight (model.py:643).
+ * Each writes the scalar loss (mean reduction, times `weight`) to *loss and the gradient of (grad_scale * loss).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* logits: fp32 NHWC buffer with 1 valid channel (PatchGAN output). dlogits: bf16, same geometry (other channels 0) */
+int fpg_mse_const_loss(const fpg_act* logits, float target, float weight, float grad_scale, float* loss,
+                       const fpg_act* dlogits, void* stream);
+/* pred/target: fp32 NCHW [count]; dpred (fp32, may be NULL) = grad_scale * weight * sign(pred-target) / count,
+ * accumulated (+=) if accumulate != 0 */
+int fpg_l1_loss(const float* pred, const float* target, int64_t count, float weight, float grad_scale, float* loss,
+                float* dpred, int accumulate, float* scratch /* >= 512 floats */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Layout / packing helpers around the network boundary (model.py:613-617: .to(device), torch.cat).
+ * ---------------------------------------------------------------------------------------------------------- */
+/* src fp32 NCHW [n][c_src][h][w] -> dst bf16 NHWC channels [c0, c0+c_src) of dst interior, reflect halo filled if
+ * dst->halo > 0. Channels of dst outside the copied range are left untouched unless zero_rest != 0. */
+int fpg_pack_nchw(const float* src, int32_t c_src, const fpg_act* dst, int32_t c0, int zero_rest, void* stream);
+/* src bf16 NHWC channels [c0, c0+c_dst) of the interior -> dst fp32 NCHW; accumulate != 0 adds instead */
+int fpg_unpack_nchw(const fpg_act* src, int32_t c0, float* dst, int32_t c_dst, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Optimiser -- torch.optim.Adam(lr, betas=(0.5, 0.999), eps=1e-8), model.py:119-122, one launch per flat buffer.
+ *   p, g, m, v: fp32 [count]; step is the 1-based step count; grad_scale multiplies g first (1/world_size).
+ * ---------------------------------------------------------------------------------------------------------- */
+int fpg_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2,
+                  float eps, int32_t step, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Flood-mask thresholding -- (sigmoid(logit) > 0.5).float(), model.py:399-400, segmentation_model.py:244-248.
+ * Bit-exact with the fp32 reference expression (sigmoid evaluated in fp32 as 1/(1+exp(-x)), then compared).
+ * ---------------------------------------------------------------------------------------------------------- */
+int fpg_flood_mask(const float* logits, float* mask, int64_t count, void* stream);
+/* confusion counts {tp, fp, tn, fn} of pred vs truth masks (values 0/1), as int64[4] */
+int fpg_confusion_counts(const float* pred, const float* truth, int64_t count, int64_t* counts4, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPG_H_ */

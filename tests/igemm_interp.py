@@ -1,0 +1,138 @@
+"""CPU interpreter of the implicit-GEMM descriptors (test infrastructure, not product code).
+
+Executes exactly the gather semantics the sm_100a kernels implement -- TMA boxes with zero fill outside the tensor
+bounds, tap tables, parity views, output views, split/scatter of wgrad tiles -- with numpy on fake base addresses,
+so that the planners in csrc/conv_plan.cu can be checked against torch.nn.functional on a machine without a GPU.
+"""
+import numpy as np
+
+FAKE_BASE = 0x10000000  # fake "device address" of element 0 of a buffer
+
+
+def _tmap_gather(tm, buf, coords_start, elem_size=2):
+    """Emulate one TMA box load: returns an array shaped box[::-1] (slowest dim first)."""
+    rank = tm.rank
+    dims = [int(tm.dims[i]) for i in range(rank)]
+    strides = [elem_size] + [int(tm.strides[i]) for i in range(rank - 1)]
+    box = [int(tm.box[i]) for i in range(rank)]
+    base_elem = (int(tm.base or 0) - FAKE_BASE) // elem_size
+    assert (int(tm.base or 0) - FAKE_BASE) % 16 == 0, "TMA base must be 16-byte aligned"
+    for s in strides[1:]:
+        assert s % 16 == 0, "TMA strides must be multiples of 16 bytes"
+    assert box[0] * elem_size == tm.swizzle_bytes
+    idx = np.zeros([1] * rank, dtype=np.int64)
+    valid = np.ones([1] * rank, dtype=bool)
+    for d in range(rank):
+        c = coords_start[d] + np.arange(box[d], dtype=np.int64)
+        shape = [1] * rank
+        shape[rank - 1 - d] = box[d]
+        ok = (c >= 0) & (c < dims[d])
+        idx = idx + (np.where(ok, c, 0) * (strides[d] // elem_size)).reshape(shape)
+        valid = valid & ok.reshape(shape)
+    flat = base_elem + idx
+    out = np.where(valid, buf[np.clip(flat, 0, buf.size - 1)], 0.0)
+    assert (flat[valid] < buf.size).all() and (flat[valid] >= 0).all(), "in-bounds coordinates left the buffer"
+    return out
+
+
+def run_fprop(desc, abuf, bbuf, outbuf, bias=None):
+    """Interpret an fpg_igemm_fprop_desc. abuf/bbuf/outbuf are flat float arrays standing for the device buffers."""
+    cblk, bn = desc.cblk, desc.block_n
+    cpt = desc.c_per_tap // cblk
+    sub_per_stage = 64 // cblk
+    assert desc.num_sub % sub_per_stage == 0
+    assert desc.tile_h * desc.tile_w == 128
+    ktot = int(desc.b.dims[0])
+    b_base = (int(desc.b.base or 0) - FAKE_BASE) // 2
+    n_total = desc.n_blocks * bn
+    bmat = bbuf[b_base:b_base + n_total * ktot].reshape(n_total, ktot)
+    o = desc.out
+    o_base = (int(o.base or 0) - FAKE_BASE) // (4 if o.fp32 else 2)
+    for n in range(desc.n_img):
+        for ty in range(desc.tiles_y):
+            for tx in range(desc.tiles_x):
+                x0, y0 = tx * desc.tile_w, ty * desc.tile_h
+                acc = np.zeros((desc.tile_h, desc.tile_w, n_total), dtype=np.float64)
+                for sub in range(desc.num_sub):
+                    tap, chunk = divmod(sub, cpt)
+                    t = desc.taps[tap]
+                    a = _tmap_gather(desc.a, abuf, [t.c0 + chunk * cblk, x0 + t.dx, t.plane, y0 + t.dy, n])
+                    a = a.reshape(desc.tile_h, desc.tile_w, cblk)  # (n=1, y, plane=1, x, c)
+                    acc += a.astype(np.float64) @ bmat[:, sub * cblk:(sub + 1) * cblk].T.astype(np.float64)
+                if bias is not None:
+                    acc += bias[None, None, :n_total]
+                if desc.act == 1:
+                    acc = np.maximum(acc, 0)
+                elif desc.act == 2:
+                    acc = np.where(acc > 0, acc, 0.2 * acc)
+                elif desc.act == 3:
+                    acc = np.tanh(acc)
+                for ry in range(desc.tile_h):
+                    py = y0 + ry
+                    if py >= o.valid_h:
+                        continue
+                    for rx in range(desc.tile_w):
+                        px = x0 + rx
+                        if px >= o.valid_w:
+                            continue
+                        off = (o_base + n * o.stride_n + (py * o.mul_y + o.off_y) * o.stride_y +
+                               (px * o.mul_x + o.off_x) * o.stride_x)
+                        outbuf[off:off + n_total] = acc[ry, rx]
+
+
+def run_wgrad(desc, xbuf, ybuf, dw, stride_k, stride_c, k_valid, c_valid):
+    """Interpret an fpg_igemm_wgrad_desc including the split reduction and the scatter into dw (flat fp array)."""
+    assert desc.tile_h * desc.tile_w == 64
+    M, N = desc.x_atoms * desc.x_ca, desc.y_atoms * desc.y_ca
+    assert M in (64, 128) and N % 16 == 0 and 16 <= N <= 256
+    NX = desc.x_groups if desc.x_taps_mode else desc.x_groups * desc.x_ntaps
+    NY = desc.y_groups if desc.y_taps_mode else desc.y_groups * desc.y_ntaps
+    total_kt = desc.n_img * desc.kt_y * desc.kt_x
+
+    def operand_tile(tm, buf, taps, taps_mode, ntaps, groups, atoms, ca, idx, n, y0, x0):
+        cols = []
+        meta = []
+        for a in range(atoms):
+            if taps_mode:
+                tap = idx * atoms + a
+                dummy = tap >= ntaps
+                if dummy:
+                    tap = 0
+                coff = 0
+            else:
+                tap = idx // groups
+                coff = ((idx % groups) * atoms + a) * ca
+                dummy = False
+            t = taps[tap]
+            tile = _tmap_gather(tm, buf, [t.c0 + coff, x0 + t.dx, t.plane, y0 + t.dy, n]).reshape(64, ca)
+            cols.append(tile)
+            for w in range(ca):
+                meta.append((-1 if dummy else tap, coff + w))
+        return np.concatenate(cols, axis=1), meta
+
+    for xi in range(NX):
+        for yi in range(NY):
+            acc = np.zeros((M, N), dtype=np.float64)
+            xmeta = ymeta = None
+            for kt in range(total_kt):
+                kx = kt % desc.kt_x
+                r = kt // desc.kt_x
+                ky = r % desc.kt_y
+                n = r // desc.kt_y
+                x0, y0 = kx * desc.tile_w, ky * desc.tile_h
+                xt, xmeta = operand_tile(desc.x, xbuf, desc.x_taps, desc.x_taps_mode, desc.x_ntaps, desc.x_groups,
+                                         desc.x_atoms, desc.x_ca, xi, n, y0, x0)
+                yt, ymeta = operand_tile(desc.y, ybuf, desc.y_taps, desc.y_taps_mode, desc.y_ntaps, desc.y_groups,
+                                         desc.y_atoms, desc.y_ca, yi, n, y0, x0)
+                acc += xt.astype(np.float64).T @ yt.astype(np.float64)
+            for m in range(M):
+                xtap, xch = xmeta[m]
+                for nn in range(N):
+                    ytap, ych = ymeta[nn]
+                    if desc.x_is_dy:
+                        k, c, tap = xch, ych, ytap
+                    else:
+                        k, c, tap = ych, xch, xtap
+                    if tap < 0 or k >= k_valid or c >= c_valid:
+                        continue
+                    dw[k * stride_k + c * stride_c + tap] = acc[m, nn]

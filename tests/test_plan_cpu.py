@@ -1,0 +1,222 @@
+"""CPU tests of the conv planners: descriptors produced by libfpg_b200.so (pure host code) are executed by the
+numpy interpreter in igemm_interp.py and compared with torch.nn.functional on the same inputs."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import igemm_interp as interp
+from fpgan import lib as L
+
+SMS = 148
+
+
+def make_act(n, h, w, c, c_stride=None, halo=0, fp32=0, base=interp.FAKE_BASE):
+    a = L.Act()
+    a.data = base
+    a.n, a.h, a.w, a.c = n, h, w, c
+    a.c_stride = c_stride or c
+    a.halo = halo
+    a.fp32 = fp32
+    return a
+
+
+def geom(r, s, stride, pad, c_in, c_out):
+    g = L.ConvGeom()
+    g.r, g.s, g.stride, g.pad, g.c_in, g.c_out = r, s, stride, pad, c_in, c_out
+    return g
+
+
+def nhwc_buffer(x_nchw, c_pad, halo=0, mode="reflect"):
+    """NCHW tensor -> flat NHWC buffer with channel padding and (reflect or zero) halo."""
+    if halo:
+        x_nchw = F.pad(x_nchw, (halo,) * 4, mode) if mode == "reflect" else F.pad(x_nchw, (halo,) * 4)
+    n, c, h, w = x_nchw.shape
+    buf = torch.zeros(n, h, w, c_pad, dtype=torch.float64)
+    buf[..., :c] = x_nchw.permute(0, 2, 3, 1)
+    return buf.reshape(-1).numpy().copy()
+
+
+def pack_fprop(w, c_in_pad, c_out_pad, taps_padded):
+    k, c, r, s = w.shape
+    out = torch.zeros(c_out_pad, taps_padded, c_in_pad, dtype=torch.float64)
+    out[:k, :r * s, :c] = w.reshape(k, c, r * s).permute(0, 2, 1)
+    return out.reshape(-1).numpy().copy()
+
+
+def pack_dgrad(fpglib, w, g):
+    """numpy twin of fpg_pack_weights_dgrad driven by fpg_dgrad_class_info."""
+    k, c, r, s = w.shape
+    src_tap = (C.c_int32 * L.FPG_MAX_TAPS)()
+    ntp, off, ncls = C.c_int32(), C.c_int64(), C.c_int32()
+    total = fpglib.fpg_packed_weight_dgrad_bytes(C.byref(g)) // 2
+    buf = np.zeros(total)
+    L.call("fpg_dgrad_class_info", C.byref(g), 0, src_tap, C.byref(ntp), C.byref(off), C.byref(ncls))
+    wf = w.reshape(k, c, r * s).double().numpy()
+    for cls in range(ncls.value):
+        L.call("fpg_dgrad_class_info", C.byref(g), cls, src_tap, C.byref(ntp), C.byref(off), C.byref(ncls))
+        m = np.zeros((g.c_in, ntp.value, g.c_out))
+        for t in range(ntp.value):
+            if src_tap[t] >= 0:
+                m[:c, t, :k] = wf[:, :, src_tap[t]].T
+        buf[off.value:off.value + m.size] = m.reshape(-1)
+    return buf
+
+
+FPROP_CASES = [
+    # (n, h, w, c_real, c_pad, k_real, k_pad, r, stride, zero_pad, reflect_halo)
+    (1, 16, 16, 9, 16, 64, 64, 7, 1, 0, 3),     # generator stem (model_architectures.py:312)
+    (2, 16, 16, 64, 64, 128, 128, 3, 2, 1, 0),  # downsample (:314)
+    (1, 8, 8, 64, 64, 64, 64, 3, 1, 0, 1),      # residual conv, reflect halo (:407)
+    (1, 12, 12, 64, 64, 27, 32, 7, 1, 0, 3),    # content head (:328)
+    (1, 8, 8, 64, 64, 10, 16, 1, 1, 0, 0),      # attention head (:334)
+    (1, 16, 16, 12, 16, 64, 64, 4, 2, 1, 0),    # PatchGAN model.0 (:424)
+    (1, 9, 9, 64, 64, 128, 128, 4, 1, 1, 0),    # PatchGAN model.8-style 4x4 s1 p1, odd extent (:434)
+    (1, 7, 7, 128, 128, 1, 16, 4, 1, 1, 0),     # PatchGAN model.11 (:437)
+    (1, 6, 6, 27, 32, 64, 64, 3, 1, 1, 0),      # 32-channel input (SW64 path)
+]
+
+
+@pytest.mark.parametrize("case", FPROP_CASES)
+def test_fprop_plan_matches_conv2d(fpglib, case):
+    n, h, w, c, cp, k, kp, r, stride, pad, halo = case
+    torch.manual_seed(0)
+    x = torch.randn(n, c, h, w, dtype=torch.float64)
+    wt = torch.randn(k, c, r, r, dtype=torch.float64)
+    bias = torch.randn(kp, dtype=torch.float64)
+    bias[k:] = 0
+    xin = F.pad(x, (halo,) * 4, "reflect") if halo else x
+    ref = F.conv2d(xin, wt, bias[:k], stride=stride, padding=pad)
+    ho, wo = ref.shape[2:]
+    xa = make_act(n, h, w, cp, halo=halo)
+    ya = make_act(n, ho, wo, kp, halo=1, base=interp.FAKE_BASE)  # output with its own halo: interior is written
+    g = geom(r, r, stride, pad, cp, kp)
+    d = L.FpropDesc()
+    L.call("fpg_conv2d_fprop_plan", C.byref(xa), interp.FAKE_BASE, None, L.ACT_LEAKY, C.byref(g), C.byref(ya), SMS,
+           C.byref(d))
+    assert d.num_sub % (64 // d.cblk) == 0 and d.tile_h * d.tile_w == 128
+    abuf = nhwc_buffer(x, cp, halo)
+    bbuf = pack_fprop(wt, cp, kp, d.num_taps)
+    assert bbuf.size * 2 == fpglib.fpg_packed_weight_bytes(C.byref(g))
+    out = np.full(n * (ho + 2) * (wo + 2) * kp, np.nan)
+    interp.run_fprop(d, abuf, bbuf, out, bias.numpy())
+    out = torch.from_numpy(out).reshape(n, ho + 2, wo + 2, kp)
+    got = out[:, 1:-1, 1:-1, :k].permute(0, 3, 1, 2)
+    torch.testing.assert_close(got, F.leaky_relu(ref, 0.2), rtol=1e-9, atol=1e-9)
+    assert torch.isnan(out[:, 0]).all() and torch.isnan(out[:, :, 0]).all()  # halo untouched
+    assert (out[:, 1:-1, 1:-1, k:] == 0).all()  # padded channels stay exactly zero
+
+
+DGRAD_CASES = [
+    # (n, h, w, c_real, c_pad, k_real, k_pad, r, stride, zero_pad, reflect_halo) of the FORWARD conv
+    (1, 8, 8, 64, 64, 64, 64, 3, 1, 0, 1),      # residual conv: gradient w.r.t. the reflect-padded input
+    (1, 16, 16, 64, 64, 128, 128, 3, 2, 1, 0),  # stride-2 3x3 (== ConvTranspose2d 3x3 s2 p1 op1 forward, :324)
+    (2, 16, 16, 64, 64, 128, 128, 4, 2, 1, 0),  # PatchGAN 4x4 s2
+    (1, 9, 9, 64, 64, 128, 128, 4, 1, 1, 0),    # PatchGAN 4x4 s1 p1
+    (1, 7, 7, 128, 128, 1, 16, 4, 1, 1, 0),     # model.11: 16-channel dy (SW32 path)
+    (1, 12, 12, 64, 64, 27, 32, 7, 1, 0, 3),    # content head: 32-channel dy (SW64 path), halo 3
+    (1, 16, 16, 12, 16, 64, 64, 4, 2, 1, 0),    # model.0: gradient w.r.t. the 16-channel D input
+]
+
+
+@pytest.mark.parametrize("case", DGRAD_CASES)
+def test_dgrad_plan_matches_autograd(fpglib, case):
+    n, h, w, c, cp, k, kp, r, stride, pad, halo = case
+    torch.manual_seed(1)
+    xin = torch.randn(n, c, h + 2 * halo, w + 2 * halo, dtype=torch.float64, requires_grad=True)
+    wt = torch.randn(k, c, r, r, dtype=torch.float64)
+    y = F.conv2d(xin, wt, None, stride=stride, padding=pad)
+    dy = torch.randn_like(y)
+    (ref,) = torch.autograd.grad(y, xin, dy)
+    ho, wo = y.shape[2:]
+    g = geom(r, r, stride, pad, cp, kp)
+    dya = make_act(n, ho, wo, kp)
+    dxa = make_act(n, h, w, cp, halo=halo)
+    descs = (L.FpropDesc * 4)()
+    nd = C.c_int()
+    L.call("fpg_conv2d_dgrad_plan", C.byref(dya), interp.FAKE_BASE, None, L.ACT_NONE, C.byref(g), C.byref(dxa), SMS,
+           descs, C.byref(nd))
+    assert nd.value == (4 if stride == 2 else 1)
+    abuf = nhwc_buffer(dy, kp)
+    bbuf = pack_dgrad(fpglib, wt, g)
+    hp, wp = h + 2 * halo, w + 2 * halo
+    out = np.full(n * hp * wp * cp, np.nan)
+    for q in range(nd.value):
+        interp.run_fprop(descs[q], abuf, bbuf, out)
+    out = torch.from_numpy(out).reshape(n, hp, wp, cp)
+    assert not torch.isnan(out).any()
+    torch.testing.assert_close(out[..., :c].permute(0, 3, 1, 2), ref, rtol=1e-9, atol=1e-9)
+    assert (out[..., c:] == 0).all()
+
+
+def test_conv_transpose_forward_is_dgrad(fpglib):
+    """nn.ConvTranspose2d(k3, s2, p1, op1) forward == fpg_conv2d_dgrad with the weight read as [c_out][c_in][r][s]."""
+    torch.manual_seed(2)
+    n, ci, co, h = 1, 64, 128, 8
+    x = torch.randn(n, ci, h, h, dtype=torch.float64)
+    wt = torch.randn(ci, co, 3, 3, dtype=torch.float64)  # ConvTranspose2d layout [Cin_T][Cout_T][R][S]
+    ref = F.conv_transpose2d(x, wt, None, stride=2, padding=1, output_padding=1)
+    g = geom(3, 3, 2, 1, co, ci)  # equivalent forward conv: c_in = Cout_T, c_out = Cin_T
+    dya = make_act(n, h, h, ci)
+    dxa = make_act(n, 2 * h, 2 * h, co)
+    descs = (L.FpropDesc * 4)()
+    nd = C.c_int()
+    L.call("fpg_conv2d_dgrad_plan", C.byref(dya), interp.FAKE_BASE, None, L.ACT_NONE, C.byref(g), C.byref(dxa), SMS,
+           descs, C.byref(nd))
+    out = np.full(n * 4 * h * h * co, np.nan)
+    for q in range(nd.value):
+        interp.run_fprop(descs[q], nhwc_buffer(x, ci), pack_dgrad(fpglib, wt, g), out)
+    out = torch.from_numpy(out).reshape(n, 2 * h, 2 * h, co).permute(0, 3, 1, 2)
+    torch.testing.assert_close(out, ref, rtol=1e-9, atol=1e-9)
+
+
+WGRAD_CASES = [
+    (1, 8, 8, 64, 64, 128, 128, 3, 1, 0, 1),    # residual conv (reflect halo)
+    (1, 16, 16, 64, 64, 128, 128, 3, 2, 1, 0),  # stride-2 3x3
+    (1, 16, 16, 9, 16, 64, 64, 7, 1, 0, 3),     # stem: 16-channel input, taps-as-atoms
+    (1, 16, 16, 12, 16, 64, 64, 4, 2, 1, 0),    # PatchGAN model.0
+    (1, 12, 12, 64, 64, 27, 32, 7, 1, 0, 3),    # content head: small c_out
+    (1, 8, 8, 64, 64, 10, 16, 1, 1, 0, 0),      # attention head 1x1
+    (1, 7, 7, 128, 128, 1, 16, 4, 1, 1, 0),     # model.11
+    (2, 9, 9, 64, 64, 128, 128, 4, 1, 1, 0),    # 4x4 s1 p1, odd extent
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_wgrad_plan_matches_autograd(fpglib, case):
+    n, h, w, c, cp, k, kp, r, stride, pad, halo = case
+    torch.manual_seed(3)
+    x = torch.randn(n, c, h, w, dtype=torch.float64)
+    xin = F.pad(x, (halo,) * 4, "reflect") if halo else x
+    wt = torch.randn(k, c, r, r, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(xin, wt, None, stride=stride, padding=pad)
+    dy = torch.randn_like(y)
+    (ref,) = torch.autograd.grad(y, wt, dy)
+    ho, wo = y.shape[2:]
+    g = geom(r, r, stride, pad, cp, kp)
+    xa = make_act(n, h, w, cp, halo=halo)
+    dya = make_act(n, ho, wo, kp)
+    d = L.WgradDesc()
+    L.call("fpg_conv2d_wgrad_plan", C.byref(xa), C.byref(dya), C.byref(g), SMS, C.byref(d))
+    assert fpglib.fpg_conv2d_wgrad_ws_bytes(C.byref(xa), C.byref(dya), C.byref(g), SMS) > 0
+    dw = np.full(k * c * r * r, np.nan)
+    xb, yb = nhwc_buffer(x, cp, halo), nhwc_buffer(dy, kp)
+    if d.x_is_dy:
+        interp.run_wgrad(d, yb, xb, dw, c * r * r, r * r, k, c)
+    else:
+        interp.run_wgrad(d, xb, yb, dw, c * r * r, r * r, k, c)
+    assert not np.isnan(dw).any()
+    torch.testing.assert_close(torch.from_numpy(dw).reshape(k, c, r, r), ref, rtol=1e-9, atol=1e-9)
+
+
+def test_library_exports_every_declared_symbol(fpglib):
+    import os
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "fpg.h")).read()
+    declared = set(re.findall(r"\b(fpg_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(fpglib, name), f"{name} declared in include/fpg.h but not exported"
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
