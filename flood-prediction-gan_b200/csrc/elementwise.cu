@@ -669,10 +669,11 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 __global__ void flood_mask_kernel(const float* __restrict__ logits, float* __restrict__ mask, int64_t count) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
-    // fp32 sigmoid as ATen computes it, 1 / (1 + exp(-x)), THEN the comparison (model.py:399-400): for
-    // 0 < x <~ 6e-8 the fp32 sigmoid rounds to exactly 0.5 and the mask is 0, so `x > 0` is not equivalent.
-    const float s = 1.0f / (1.0f + expf(-logits[i]));
-    mask[i] = s > 0.5f ? 1.f : 0.f;
+    // (sigmoid(x) > 0.5) in fp32 (model.py:399-400) is NOT `x > 0`: fl(1 + fl(exp(-x))) rounds to 2 and the
+    // sigmoid to exactly 0.5 for 0 < x <= 1.5 * 2^-24. The reference expression is monotone in x, and its
+    // switch point was found by evaluating it on every positive fp32 value (tests/golden/make_golden.py):
+    // true  <=>  x > 0x1.8p-24f  (bit pattern 0x33c00000). A compare is exact; a device expf would not be.
+    mask[i] = logits[i] > 0x1.8p-24f ? 1.f : 0.f;
   }
 }
 __global__ void confusion_kernel(const float* __restrict__ pred, const float* __restrict__ truth, int64_t count,

@@ -1,0 +1,224 @@
+"""Python-side operator wrappers over the C ABI: device buffers are torch tensors (plumbing only), every
+operator is one call into libfpg_b200.so on the current CUDA stream. No operator here has a torch fallback."""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = L.ACT_NONE, L.ACT_RELU, L.ACT_LEAKY, L.ACT_TANH
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def pad16(c):
+    return (c + 15) // 16 * 16
+
+
+class ActBuf:
+    """An NHWC activation buffer [n, h+2*halo, w+2*halo, c_stride] (bf16 or fp32) plus its fpg_act descriptor.
+
+    `c` channels starting at channel offset `c0` of the underlying storage are visible to the kernels."""
+
+    def __init__(self, n, h, w, c, halo=0, fp32=False, device="cuda", tensor=None, c0=0, c_stride=None, zero=True):
+        self.n, self.h, self.w, self.c, self.halo, self.fp32 = n, h, w, c, halo, fp32
+        self.c_stride = c_stride or c
+        self.c0 = c0
+        dtype = torch.float32 if fp32 else torch.bfloat16
+        if tensor is None:
+            shape = (n, h + 2 * halo, w + 2 * halo, self.c_stride)
+            tensor = torch.zeros(shape, dtype=dtype, device=device) if zero else torch.empty(shape, dtype=dtype,
+                                                                                             device=device)
+        self.t = tensor
+        self.desc = L.Act()
+        self.desc.data = tensor.data_ptr() + c0 * tensor.element_size()
+        self.desc.n, self.desc.h, self.desc.w, self.desc.c = n, h, w, c
+        self.desc.c_stride = self.c_stride
+        self.desc.halo = halo
+        self.desc.fp32 = 1 if fp32 else 0
+
+    def ref(self):
+        return C.byref(self.desc)
+
+    def channels(self, c0, c):
+        """A view of `c` channels starting at c0 (shares storage)."""
+        return ActBuf(self.n, self.h, self.w, c, self.halo, self.fp32, tensor=self.t, c0=self.c0 + c0,
+                      c_stride=self.c_stride)
+
+    def interior(self):
+        """torch view [n, h, w, c] of the interior."""
+        hl = self.halo
+        t = self.t[:, hl:hl + self.h, hl:hl + self.w] if hl else self.t
+        return t[..., self.c0:self.c0 + self.c]
+
+    def to_nchw(self, c=None):
+        return self.interior()[..., :c].permute(0, 3, 1, 2).float().contiguous()
+
+    @staticmethod
+    def from_nchw(x, c_pad=None, halo=0, mode="reflect", fp32=False):
+        """Test helper: NCHW float tensor -> ActBuf (torch ops; the product path uses pack_nchw)."""
+        n, c, h, w = x.shape
+        cp = c_pad or pad16(c)
+        buf = ActBuf(n, h, w, cp, halo=halo, fp32=fp32, device=x.device)
+        xp = torch.nn.functional.pad(x, (halo,) * 4, mode) if halo else x
+        buf.t[..., :c] = xp.permute(0, 2, 3, 1).to(buf.t.dtype)
+        return buf
+
+
+class ConvSpec:
+    """Geometry + packed bf16 operands of one convolution layer (forward conv view)."""
+
+    def __init__(self, r, s, stride, pad, c_in, c_out, c_in_valid=None, c_out_valid=None):
+        self.g = L.ConvGeom()
+        self.g.r, self.g.s, self.g.stride, self.g.pad = r, s, stride, pad
+        self.g.c_in, self.g.c_out = c_in, c_out
+        self.c_in_valid = c_in_valid if c_in_valid is not None else c_in
+        self.c_out_valid = c_out_valid if c_out_valid is not None else c_out
+        self.w_fprop = None
+        self.w_dgrad = None
+
+    def gref(self):
+        return C.byref(self.g)
+
+    def stride_k(self, transposed=False):
+        """element strides of the fp32 parameter for (output channel k, input channel c) of the forward-conv view"""
+        rs = self.g.r * self.g.s
+        return self.c_in_valid * rs  # [K][C][R][S]; for ConvTranspose2d the parameter already is [K=Cin_T][C=Cout_T]
+
+    def pack(self, weight, fprop=True, dgrad=True):
+        """(Re)pack the fp32 parameter `weight` ([K][C][R][S] in the forward-conv view) into the bf16 operands."""
+        lib = L.load()
+        rs = self.g.r * self.g.s
+        sk, sc = self.c_in_valid * rs, rs
+        assert weight.is_contiguous() and weight.dtype == torch.float32
+        assert weight.numel() == self.c_out_valid * self.c_in_valid * rs, (weight.shape, self.c_out_valid,
+                                                                           self.c_in_valid, rs)
+        if fprop:
+            if self.w_fprop is None:
+                nbytes = lib.fpg_packed_weight_bytes(self.gref())
+                assert nbytes > 0
+                self.w_fprop = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)
+            L.call("fpg_pack_weights", _ptr(weight), sk, sc, self.c_out_valid, self.c_in_valid, self.gref(),
+                   _ptr(self.w_fprop), _stream())
+        if dgrad:
+            if self.w_dgrad is None:
+                nbytes = lib.fpg_packed_weight_dgrad_bytes(self.gref())
+                assert nbytes > 0
+                self.w_dgrad = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)
+            L.call("fpg_pack_weights_dgrad", _ptr(weight), sk, sc, self.c_out_valid, self.c_in_valid, self.gref(),
+                   _ptr(self.w_dgrad), _stream())
+
+
+def conv_fprop(x, spec, y, bias=None, act=ACT_NONE):
+    L.call("fpg_conv2d_fprop", x.ref(), _ptr(spec.w_fprop), _ptr(bias), act, spec.gref(), y.ref(), _stream())
+
+
+def conv_dgrad(dy, spec, dx, bias=None, act=ACT_NONE):
+    L.call("fpg_conv2d_dgrad", dy.ref(), _ptr(spec.w_dgrad), _ptr(bias), act, spec.gref(), dx.ref(), _stream())
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only fp32 scratch shared by the wgrad / reduction kernels of one device (stream-ordered reuse)."""
+    key = str(device)
+    cur = _ws_cache.get(key)
+    if cur is None or cur.numel() * 4 < nbytes:
+        cur = torch.empty(max(nbytes // 4 + 1, 1 << 20), dtype=torch.float32, device=device)
+        _ws_cache[key] = cur
+    return cur
+
+
+def conv_wgrad(x, dy, spec, dw):
+    """dw (fp32 parameter-layout gradient, contiguous [K][C][R][S]) = conv_backward_weight(x, dy); overwritten."""
+    lib = L.load()
+    sms = lib.fpg_sm_count()
+    nbytes = lib.fpg_conv2d_wgrad_ws_bytes(x.ref(), dy.ref(), spec.gref(), sms)
+    if nbytes <= 0:
+        L.check(-22, "fpg_conv2d_wgrad_ws_bytes")
+    ws = workspace(nbytes, dw.device)
+    rs = spec.g.r * spec.g.s
+    L.call("fpg_conv2d_wgrad", x.ref(), dy.ref(), spec.gref(), _ptr(dw), spec.c_in_valid * rs, rs,
+           spec.c_out_valid, spec.c_in_valid, _ptr(ws), _stream())
+
+
+def bias_grad(dy, db, k_valid):
+    L.call("fpg_bias_grad", dy.ref(), _ptr(db), k_valid, _stream())
+
+
+def _scratch_for(y):
+    n = L.load().fpg_instnorm_scratch_floats(y.ref())
+    return workspace(n * 4, y.t.device)
+
+
+def instnorm_stats(y, stats, eps=1e-5):
+    L.call("fpg_instnorm_stats", y.ref(), eps, _ptr(stats), _ptr(_scratch_for(y)), _stream())
+
+
+def instnorm_apply(y, stats, act, z, residual=None):
+    L.call("fpg_instnorm_apply", y.ref(), _ptr(stats), act, residual.ref() if residual is not None else None,
+           z.ref(), _stream())
+
+
+def instnorm_bwd(dz, y, stats, act, dy, dz2=None, dres=None):
+    L.call("fpg_instnorm_bwd", dz.ref(), dz2.ref() if dz2 is not None else None, y.ref(), _ptr(stats), act, dy.ref(),
+           dres.ref() if dres is not None else None, _ptr(_scratch_for(y)), _stream())
+
+
+def act_bwd(dz, z, act, dx):
+    L.call("fpg_act_bwd", dz.ref(), z.ref(), act, dx.ref(), _stream())
+
+
+def halo_fold(a, b, c):
+    L.call("fpg_halo_fold", a.ref(), b.ref() if b is not None else None, c.ref(), _stream())
+
+
+def blend_fwd(content, logits, inp, out=None, out_c0=0, out_nchw=None, mask=None):
+    L.call("fpg_blend_fwd", content.ref(), logits.ref(), inp.ref(), out.ref() if out is not None else None, out_c0,
+           _ptr(out_nchw), _ptr(mask), _stream())
+
+
+def blend_bwd(content, logits, inp, dcontent, dlogits, dout_nchw=None, dout_nhwc=None, dout_c0=0, dimage_nchw=None):
+    L.call("fpg_blend_bwd", _ptr(dout_nchw), dout_nhwc.ref() if dout_nhwc is not None else None, dout_c0,
+           content.ref(), logits.ref(), inp.ref(), dcontent.ref(), dlogits.ref(), _ptr(dimage_nchw), _stream())
+
+
+def mse_const_loss(logits, target, weight, grad_scale, loss, dlogits=None):
+    L.call("fpg_mse_const_loss", logits.ref(), float(target), float(weight), float(grad_scale), _ptr(loss),
+           dlogits.ref() if dlogits is not None else None, _stream())
+
+
+def l1_loss(pred, target, weight, grad_scale, loss, dpred=None, accumulate=False):
+    ws = workspace(4096, pred.device)
+    L.call("fpg_l1_loss", _ptr(pred), _ptr(target), pred.numel(), float(weight), float(grad_scale), _ptr(loss),
+           _ptr(dpred), 1 if accumulate else 0, _ptr(ws), _stream())
+
+
+def pack_nchw(src, dst, c0=0, zero_rest=False):
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    L.call("fpg_pack_nchw", _ptr(src), src.shape[1], dst.ref(), c0, 1 if zero_rest else 0, _stream())
+
+
+def unpack_nchw(src, dst, c0=0, accumulate=False):
+    assert dst.dtype == torch.float32 and dst.is_contiguous()
+    L.call("fpg_unpack_nchw", src.ref(), c0, _ptr(dst), dst.shape[1], 1 if accumulate else 0, _stream())
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    L.call("fpg_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
+           float(eps), int(step), float(grad_scale), _stream())
+
+
+def flood_mask(logits, mask):
+    L.call("fpg_flood_mask", _ptr(logits), _ptr(mask), logits.numel(), _stream())
+
+
+def confusion_counts(pred, truth, counts):
+    L.call("fpg_confusion_counts", _ptr(pred), _ptr(truth), pred.numel(), _ptr(counts), _stream())

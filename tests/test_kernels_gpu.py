@@ -1,0 +1,329 @@
+"""GPU parity tests of the individual sm_100a kernels, called through the C ABI (fpgan.ops -> libfpg_b200.so),
+against plain fp32 PyTorch on the same (bf16-rounded) inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+
+def bf16r(t):
+    return t.to(torch.bfloat16).float()
+
+
+def close_rms(got, ref, max_tol, mean_tol, what=""):
+    """Abs error relative to the RMS of the reference. bf16 storage rounds every element to 2^-9 relative, so
+    the element-wise bound also allows 2^-7 of the element's own magnitude (heavy-tailed values)."""
+    rms = ref.float().pow(2).mean().sqrt().item() + 1e-12
+    err = (got.float() - ref.float()).abs()
+    mean = err.mean().item() / rms
+    mx = ((err - ref.float().abs() * 2.0 ** -7).clamp_min(0)).max().item() / rms
+    assert mx < max_tol and mean < mean_tol, f"{what}: max {mx:.4g} (tol {max_tol}) mean {mean:.4g} (tol {mean_tol})"
+
+
+CONV_CASES = [
+    # (n, h, w, c_real, k_real, r, stride, zero_pad, reflect_halo)
+    (6, 64, 64, 256, 256, 3, 1, 0, 1),    # residual conv: 192 tiles > 148 SMs (persistent loop, both TMEM stages)
+    (1, 64, 64, 256, 256, 3, 1, 0, 1),    # B=1: block_n shrinks to fill the SMs
+    (2, 64, 64, 9, 64, 7, 1, 0, 3),       # stem, 16-channel SW32 path
+    (2, 64, 64, 64, 128, 3, 2, 1, 0),     # downsample s2
+    (2, 32, 32, 128, 256, 3, 2, 1, 0),
+    (2, 64, 64, 64, 27, 7, 1, 0, 3),      # content head
+    (2, 64, 64, 64, 10, 1, 1, 0, 0),      # attention head
+    (2, 64, 64, 12, 64, 4, 2, 1, 0),      # PatchGAN model.0
+    (2, 32, 32, 128, 256, 4, 2, 1, 0),    # model.5
+    (2, 32, 32, 256, 512, 4, 1, 1, 0),    # model.8 (31x31 output, masked tiles, 2 n-blocks)
+    (2, 31, 31, 512, 1, 4, 1, 1, 0),      # model.11 (30x30 output)
+    (1, 8, 8, 27, 64, 3, 1, 1, 0),        # 32-channel input (SW64 path)
+]
+
+
+def _conv_setup(case, seed):
+    from fpgan import ops
+    n, h, w, c, k, r, stride, pad, halo = case
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = bf16r(torch.randn(n, c, h, w, device="cuda", generator=g))
+    wt = bf16r(torch.randn(k, c, r, r, device="cuda", generator=g) * (1.0 / (c * r * r) ** 0.5))
+    spec = ops.ConvSpec(r, r, stride, pad, ops.pad16(c), ops.pad16(k), c_in_valid=c, c_out_valid=k)
+    spec.pack(wt.contiguous())
+    xin = F.pad(x, (halo,) * 4, "reflect") if halo else x
+    return ops, x, wt, spec, xin
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fprop(case):
+    ops, x, wt, spec, xin = _conv_setup(case, 0)
+    n, h, w, c, k, r, stride, pad, halo = case
+    bias = torch.randn(ops.pad16(k), device="cuda")
+    bias[k:] = 0
+    ref = F.conv2d(xin, wt, bias[:k], stride=stride, padding=pad)
+    ho, wo = ref.shape[2:]
+    xb = ops.ActBuf.from_nchw(x, halo=halo)
+    for fp32 in (False, True):
+        yb = ops.ActBuf(n, ho, wo, ops.pad16(k), halo=1, fp32=fp32)
+        yb.t.fill_(7.0)
+        ops.conv_fprop(xb, spec, yb, bias=bias, act=ops.ACT_LEAKY)
+        torch.cuda.synchronize()
+        got = yb.to_nchw(k)
+        close_rms(got, F.leaky_relu(ref, 0.2), 0.03 if not fp32 else 2e-3, 0.004 if not fp32 else 2e-4,
+                  f"fprop {case} fp32={fp32}")
+        assert (yb.t[:, 0] == 7.0).all() and (yb.t[:, :, -1] == 7.0).all(), "output halo was overwritten"
+        assert (yb.interior()[..., k:] == 0).all(), "padded output channels must stay zero"
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_dgrad(case):
+    ops, x, wt, spec, xin = _conv_setup(case, 1)
+    n, h, w, c, k, r, stride, pad, halo = case
+    xin = xin.clone().requires_grad_(True)
+    y = F.conv2d(xin, wt, None, stride=stride, padding=pad)
+    dy = bf16r(torch.randn_like(y))
+    (ref,) = torch.autograd.grad(y, xin, dy)
+    dyb = ops.ActBuf.from_nchw(dy)
+    dxb = ops.ActBuf(n, h, w, ops.pad16(c), halo=halo)
+    dxb.t.fill_(float("nan"))
+    ops.conv_dgrad(dyb, spec, dxb)
+    torch.cuda.synchronize()
+    got = dxb.t[..., :c].permute(0, 3, 1, 2).float()
+    assert not torch.isnan(dxb.t).any()
+    close_rms(got, ref, 0.03, 0.004, f"dgrad {case}")
+    assert (dxb.t[..., c:] == 0).all()
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_wgrad(case):
+    ops, x, wt, spec, xin = _conv_setup(case, 2)
+    n, h, w, c, k, r, stride, pad, halo = case
+    wt = wt.clone().requires_grad_(True)
+    y = F.conv2d(xin, wt, None, stride=stride, padding=pad)
+    dy = bf16r(torch.randn_like(y))
+    (ref,) = torch.autograd.grad(y, wt, dy)
+    xb = ops.ActBuf.from_nchw(x, halo=halo)
+    dyb = ops.ActBuf.from_nchw(dy)
+    dw = torch.full_like(ref, float("nan"))
+    ops.conv_wgrad(xb, dyb, spec, dw)
+    torch.cuda.synchronize()
+    assert not torch.isnan(dw).any()
+    close_rms(dw, ref, 5e-3, 5e-4, f"wgrad {case}")
+
+
+def test_conv_transpose_roundtrip():
+    """ConvTranspose2d(3, s2, p1, op1) forward / input-grad / weight-grad through dgrad / fprop / wgrad."""
+    from fpgan import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n, ci, co, h = 2, 256, 128, 64
+    x = bf16r(torch.randn(n, ci, h, h, device="cuda", generator=g)).requires_grad_(True)
+    wt = bf16r(torch.randn(ci, co, 3, 3, device="cuda", generator=g) / 48).requires_grad_(True)
+    y = F.conv_transpose2d(x, wt, None, stride=2, padding=1, output_padding=1)
+    dy = bf16r(torch.randn_like(y))
+    dx_ref, dw_ref = torch.autograd.grad(y, (x, wt), dy)
+    spec = ops.ConvSpec(3, 3, 2, 1, co, ci)  # equivalent forward conv: c_in = Cout_T, c_out = Cin_T
+    spec.pack(wt.detach().contiguous())
+    xb = ops.ActBuf.from_nchw(x.detach())
+    yb = ops.ActBuf(n, 2 * h, 2 * h, co)
+    ops.conv_dgrad(xb, spec, yb)
+    close_rms(yb.to_nchw(), y.detach(), 0.03, 0.004, "convT forward")
+    dyb = ops.ActBuf.from_nchw(dy)
+    dxb = ops.ActBuf(n, h, h, ci)
+    ops.conv_fprop(dyb, spec, dxb)
+    close_rms(dxb.to_nchw(), dx_ref, 0.03, 0.004, "convT input grad")
+    dw = torch.empty_like(dw_ref)
+    ops.conv_wgrad(dyb, xb, spec, dw)
+    close_rms(dw, dw_ref, 5e-3, 5e-4, "convT weight grad")
+
+
+@pytest.mark.parametrize("shape,halo,act", [((3, 64, 64, 256), 1, 1), ((2, 128, 128, 64), 3, 1),
+                                            ((2, 31, 31, 512), 0, 2), ((2, 32, 32, 128), 0, 0),
+                                            ((2, 16, 16, 16), 0, 1)])
+def test_instnorm_fwd_bwd(shape, halo, act):
+    from fpgan import ops
+    n, h, w, c = shape
+    g = torch.Generator(device="cuda").manual_seed(7)
+    y = bf16r(torch.randn(n, c, h, w, device="cuda", generator=g) * 3 + 0.5).requires_grad_(True)
+    res = bf16r(torch.randn(n, c, h, w, device="cuda", generator=g))
+    fn = {0: lambda t: t, 1: F.relu, 2: lambda t: F.leaky_relu(t, 0.2)}[act]
+    zi = fn(F.instance_norm(y, eps=1e-5)) + res
+    z = F.pad(zi, (halo,) * 4, "reflect") if halo else zi
+    dz = bf16r(torch.randn_like(z))
+    dz2 = bf16r(torch.randn_like(zi))
+    (dy_ref,) = torch.autograd.grad([z, zi], y, [dz, dz2])
+
+    yb = ops.ActBuf.from_nchw(y.detach())
+    rb = ops.ActBuf.from_nchw(res)
+    zb = ops.ActBuf(n, h, w, c, halo=halo)
+    stats = torch.empty(n * c * 2, device="cuda")
+    ops.instnorm_stats(yb, stats)
+    ops.instnorm_apply(yb, stats, act, zb, residual=rb)
+    st = stats.view(n, c, 2)
+    torch.testing.assert_close(st[..., 0], y.detach().mean((2, 3)), rtol=1e-3, atol=2e-3)
+    torch.testing.assert_close(st[..., 1], (y.detach().var((2, 3), unbiased=False) + 1e-5).rsqrt(), rtol=1e-3,
+                               atol=1e-4)
+    got = zb.t.permute(0, 3, 1, 2).float()
+    close_rms(got, z.detach(), 0.02, 0.003, "instnorm apply (incl. halo)")
+
+    dzb = ops.ActBuf(n, h, w, c, halo=halo)
+    dzb.t.copy_(dz.permute(0, 2, 3, 1))
+    dz2b = ops.ActBuf.from_nchw(dz2)
+    dyb = ops.ActBuf(n, h, w, c)
+    dres = ops.ActBuf(n, h, w, c)
+    ops.instnorm_bwd(dzb, yb, stats, act, dyb, dz2=dz2b, dres=dres)
+    close_rms(dyb.to_nchw(), dy_ref, 0.03, 0.004, "instnorm bwd")
+    # dres = fold(dz) + dz2 == gradient w.r.t. the residual input
+    res_g = res.clone().requires_grad_(True)
+    zi2 = fn(F.instance_norm(y.detach(), eps=1e-5)) + res_g
+    z2 = F.pad(zi2, (halo,) * 4, "reflect") if halo else zi2
+    (dres_ref,) = torch.autograd.grad([z2, zi2], res_g, [dz, dz2])
+    close_rms(dres.to_nchw(), dres_ref, 0.02, 0.003, "halo fold")
+    # without dres the apply pass recomputes the fold
+    dyb2 = ops.ActBuf(n, h, w, c)
+    ops.instnorm_bwd(dzb, yb, stats, act, dyb2, dz2=dz2b)
+    close_rms(dyb2.to_nchw(), dy_ref, 0.03, 0.004, "instnorm bwd (no dres)")
+    out = ops.ActBuf(n, h, w, c)
+    ops.halo_fold(dzb, dz2b, out)
+    close_rms(out.to_nchw(), dres_ref, 0.02, 0.003, "halo_fold op")
+
+
+def _blend_ref(content_pre, logits, image):
+    """model_architectures.py:353-399 restated with torch ops"""
+    content = torch.tanh(content_pre)
+    att = torch.softmax(logits, dim=1)
+    out = image * att[:, 9:10]
+    for k in range(9):
+        out = out + content[:, 3 * k:3 * k + 3] * att[:, k:k + 1]
+    return out, att[:, 9]
+
+
+def test_blend_fwd_bwd():
+    from fpgan import ops
+    n, h, w = 2, 32, 48
+    g = torch.Generator(device="cuda").manual_seed(11)
+    cpre = torch.randn(n, 27, h, w, device="cuda", generator=g).requires_grad_(True)
+    logits = (torch.randn(n, 10, h, w, device="cuda", generator=g) * 2).requires_grad_(True)
+    image = bf16r(torch.rand(n, 9, h, w, device="cuda", generator=g) * 2 - 1)
+    img_rgb = image[:, :3].clone().requires_grad_(True)
+    out_ref, mask_ref = _blend_ref(cpre, logits, img_rgb)
+    dout = torch.randn_like(out_ref)
+    dc_ref, dl_ref, dimg_ref = torch.autograd.grad(out_ref, (cpre, logits, img_rgb), dout)
+
+    cb = ops.ActBuf.from_nchw(torch.tanh(cpre.detach()), c_pad=32, fp32=True)
+    lb = ops.ActBuf.from_nchw(logits.detach(), c_pad=16, fp32=True)
+    ib = ops.ActBuf.from_nchw(image, halo=3)
+    ob = ops.ActBuf(n, h, w, 16)
+    out_nchw = torch.empty(n, 3, h, w, device="cuda")
+    mask = torch.empty(n, h, w, device="cuda")
+    ops.blend_fwd(cb, lb, ib, out=ob, out_c0=9, out_nchw=out_nchw, mask=mask)
+    torch.testing.assert_close(out_nchw, out_ref.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(mask, mask_ref.detach(), rtol=1e-4, atol=1e-6)
+    close_rms(ob.interior()[..., 9:12].permute(0, 3, 1, 2), out_ref.detach(), 0.01, 0.002, "blend bf16 out")
+    assert (ob.interior()[..., :9] == 0).all() and (ob.interior()[..., 12:] == 0).all()
+
+    dcb = ops.ActBuf(n, h, w, 32)
+    dlb = ops.ActBuf(n, h, w, 16)
+    dimg = torch.empty(n, 3, h, w, device="cuda")
+    # split the upstream gradient over the two supported sources
+    half = bf16r(dout * 0.5)
+    gb = ops.ActBuf(n, h, w, 16)
+    gb.t[..., 9:12] = half.permute(0, 2, 3, 1).to(torch.bfloat16)
+    ops.blend_bwd(cb, lb, ib, dcb, dlb, dout_nchw=(dout - half).contiguous(), dout_nhwc=gb, dout_c0=9,
+                  dimage_nchw=dimg)
+    close_rms(dcb.to_nchw(27), dc_ref, 0.02, 0.003, "blend dcontent")
+    close_rms(dlb.to_nchw(10), dl_ref, 0.02, 0.003, "blend dlogits")
+    torch.testing.assert_close(dimg, dimg_ref, rtol=1e-4, atol=1e-5)
+    assert (dcb.t[..., 27:] == 0).all() and (dlb.t[..., 10:] == 0).all()
+
+
+def test_losses():
+    from fpgan import ops
+    g = torch.Generator(device="cuda").manual_seed(13)
+    n, h, w = 4, 30, 30
+    logit = torch.randn(n, 1, h, w, device="cuda", generator=g).requires_grad_(True)
+    for target in (0.0, 1.0):
+        ref = F.mse_loss(logit, torch.full_like(logit, target))
+        (dref,) = torch.autograd.grad(ref * 0.5, logit)
+        lb = ops.ActBuf.from_nchw(logit.detach(), c_pad=16, fp32=True)
+        db = ops.ActBuf(n, h, w, 16)
+        db.t.fill_(3.0)
+        loss = torch.zeros(1, device="cuda")
+        ops.mse_const_loss(lb, target, 1.0, 0.5, loss, dlogits=db)
+        torch.testing.assert_close(loss[0], ref.detach(), rtol=1e-5, atol=1e-7)
+        close_rms(db.to_nchw(1), dref, 0.01, 0.003, "mse grad")
+        assert (db.t[..., 1:] == 0).all()
+    pred = torch.randn(3, 3, 64, 64, device="cuda", generator=g).requires_grad_(True)
+    tgt = torch.randn(3, 3, 64, 64, device="cuda", generator=g)
+    ref = F.l1_loss(pred, tgt) * 100
+    (dref,) = torch.autograd.grad(ref, pred)
+    loss = torch.zeros(1, device="cuda")
+    dp = torch.ones_like(tgt)
+    ops.l1_loss(pred.detach(), tgt, 100.0, 1.0, loss, dpred=dp, accumulate=True)
+    torch.testing.assert_close(loss[0], ref.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(dp, dref + 1.0, rtol=1e-6, atol=1e-9)
+
+
+def test_adam_matches_torch():
+    from fpgan import ops
+    g = torch.Generator(device="cuda").manual_seed(17)
+    p = torch.randn(100003, device="cuda", generator=g)
+    ref_p = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref_p], lr=2e-4, betas=(0.5, 0.999))
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 6):
+        grad = torch.randn(p.shape, device="cuda", generator=g) * 10 ** (step - 3)
+        ref_p.grad = grad.clone()
+        opt.step()
+        ops.adam_step(p, grad, m, v, 2e-4, 0.5, 0.999, 1e-8, step)
+        torch.testing.assert_close(p, ref_p.detach(), rtol=1e-6, atol=1e-7)
+
+
+def test_pack_unpack_bias_grad():
+    from fpgan import ops
+    g = torch.Generator(device="cuda").manual_seed(19)
+    x = torch.rand(2, 9, 32, 40, device="cuda", generator=g) * 2 - 1
+    y = torch.rand(2, 3, 32, 40, device="cuda", generator=g) * 2 - 1
+    b = ops.ActBuf(2, 32, 40, 16, halo=3)
+    b.t.fill_(5.0)
+    ops.pack_nchw(x, b, 0, zero_rest=True)
+    ops.pack_nchw(y, b, 9)
+    ref = F.pad(torch.cat([x, y], 1), (3,) * 4, "reflect")
+    torch.testing.assert_close(b.t[..., :12].permute(0, 3, 1, 2).float(), bf16r(ref))
+    assert (b.t[..., 12:] == 0).all()
+    out = torch.full((2, 3, 32, 40), 1.0, device="cuda")
+    ops.unpack_nchw(b, out, c0=9, accumulate=True)
+    torch.testing.assert_close(out, bf16r(y) + 1.0)
+    dy = ops.ActBuf.from_nchw(bf16r(torch.randn(3, 27, 20, 20, device="cuda", generator=g)), c_pad=32)
+    db = torch.zeros(27, device="cuda")
+    ops.bias_grad(dy, db, 27)
+    torch.testing.assert_close(db, dy.to_nchw(27).sum((0, 2, 3)), rtol=1e-4, atol=1e-3)
+
+
+def test_flood_mask_bit_exact_and_confusion():
+    """(sigmoid(x) > 0.5).float() -- model.py:399-400 -- bit-exact against the fp32 CPU expression, including the
+    interval 0 < x < ~9e-8 where the fp32 sigmoid rounds to exactly 0.5."""
+    from fpgan import ops
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(1 << 20, generator=g) * 3
+    # every float in a neighbourhood of the rounding threshold, both signs, plus zeros / denormals / infinities
+    near = torch.arange(0x33000000, 0x34400000, 37, dtype=torch.int32).view(torch.float32)
+    special = torch.tensor([0.0, -0.0, 1e-45, -1e-45, 5.9e-8, 6e-8, 8.9e-8, 9e-8, 1.2e-7, float("inf"),
+                            -float("inf"), 88.0, -88.0, 104.0, -104.0])
+    x = torch.cat([x, near, -near, special])
+    ref = (torch.sigmoid(x) > 0.5).float()
+    xd = x.cuda()
+    mask = torch.empty_like(xd)
+    ops.flood_mask(xd, mask)
+    assert torch.equal(mask.cpu(), ref)
+    truth = (torch.rand(x.shape, generator=g) > 0.5).float()
+    counts = torch.zeros(4, dtype=torch.int64, device="cuda")
+    ops.confusion_counts(mask, truth.cuda(), counts)
+    tp = int(((ref == 1) & (truth == 1)).sum())
+    fp = int(((ref == 1) & (truth == 0)).sum())
+    tn = int(((ref == 0) & (truth == 0)).sum())
+    fn = int(((ref == 0) & (truth == 1)).sum())
+    assert counts.tolist() == [tp, fp, tn, fn]
