@@ -1,0 +1,300 @@
+"""Native executors of the generator / discriminator graphs: every layer is a call into libfpg_b200.so.
+
+A network executor owns no parameters: it reads them from the drop-in nn.Module (models/model_architectures.py),
+keeps bf16 GEMM-layout copies (repacked when the fp32 parameters change) and runs
+
+    forward(x)            -> output, tape     (tape = saved activations of this call)
+    backward(tape, grads) -> parameter gradients (+ input gradient)
+
+Layer graphs follow the reference: model_architectures.py:339-400 (attention generators), :95-134 (CycleGAN
+generator), :424-441 (InstanceNorm PatchGAN). Convolution biases that feed an InstanceNorm are mathematical
+no-ops (the norm subtracts the per-plane mean) and are skipped; their gradient is exactly 0.
+"""
+import torch
+
+from . import ops
+from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH, ActBuf, ConvSpec, pad16
+
+
+class ConvLayer:
+    """One convolution in the forward-conv view. For nn.ConvTranspose2d(Cin_T, Cout_T) the equivalent forward conv
+    has c_out = Cin_T, c_in = Cout_T and the parameter [Cin_T][Cout_T][R][S] already is [K][C][R][S]."""
+
+    def __init__(self, name, weight, bias, r, stride, pad, transposed=False, use_bias=False):
+        self.name, self.weight, self.bias = name, weight, bias
+        self.transposed, self.use_bias = transposed, use_bias
+        k, c = weight.shape[0], weight.shape[1]
+        self.k_valid, self.c_valid = k, c
+        self.spec = ConvSpec(r, r, stride, pad, pad16(c), pad16(k), c_in_valid=c, c_out_valid=k)
+        self.bias_pad = None
+        self._version = None
+
+    def repack(self, need_fprop=True, need_dgrad=True):
+        ver = (self.weight._version, self.bias._version if self.bias is not None else 0, self.weight.data_ptr())
+        if ver == self._version:
+            return
+        self._version = ver
+        w = self.weight.detach()
+        if not w.is_contiguous():
+            w = w.contiguous()
+        self.spec.pack(w, fprop=need_fprop, dgrad=need_dgrad)
+        if self.use_bias:
+            n = self.spec.g.c_in if self.transposed else self.spec.g.c_out
+            if self.bias_pad is None:
+                self.bias_pad = torch.zeros(n, dtype=torch.float32, device=w.device)
+            self.bias_pad[:self.bias.numel()].copy_(self.bias.detach())
+
+
+class Grads:
+    """Destination of parameter gradients: name -> fp32 tensor shaped like the parameter (views of a flat buffer)."""
+
+    def __init__(self, named_params, flat=None):
+        self.names = [n for n, _ in named_params]
+        sizes = [p.numel() for _, p in named_params]
+        total = sum(sizes)
+        dev = named_params[0][1].device
+        self.flat = flat if flat is not None else torch.zeros(total, dtype=torch.float32, device=dev)
+        self.views = {}
+        off = 0
+        for (n, p), s in zip(named_params, sizes):
+            self.views[n] = self.flat[off:off + s].view(p.shape)
+            off += s
+
+    def __getitem__(self, name):
+        return self.views[name]
+
+
+def _norm_act(y, act, halo, residual=None):
+    """IN statistics + apply; returns (stats, z)"""
+    stats = torch.empty(y.n * y.c * 2, dtype=torch.float32, device=y.t.device)
+    ops.instnorm_stats(y, stats)
+    z = ActBuf(y.n, y.h, y.w, y.c, halo=halo, zero=False)
+    ops.instnorm_apply(y, stats, act, z, residual=residual)
+    return stats, z
+
+
+class _NetBase:
+    def __init__(self, module):
+        self.module = module
+        self.layers = {}
+        self.grad_ready = None  # optional callback(param_name) fired once a parameter gradient has been produced
+
+    def _add(self, name, conv_module, r, stride, pad, transposed=False, use_bias=False):
+        layer = ConvLayer(name, conv_module.weight, conv_module.bias, r, stride, pad, transposed, use_bias)
+        self.layers[name] = layer
+        return layer
+
+    def repack(self):
+        for layer in self.layers.values():
+            layer.repack()
+
+    def named_params(self):
+        return list(self.module.named_parameters())
+
+    # conv helpers ------------------------------------------------------------------------------
+    def _conv(self, x, name, halo_out=0, fp32=False, act=ACT_NONE):
+        """forward conv (or transposed-conv forward) of layer `name` -> raw output buffer"""
+        L = self.layers[name]
+        g = L.spec.g
+        bias = L.bias_pad if L.use_bias else None
+        if L.transposed:
+            y = ActBuf(x.n, x.h * 2, x.w * 2, g.c_in, halo=halo_out, fp32=fp32, zero=False)
+            ops.conv_dgrad(x, L.spec, y, bias=bias, act=act)
+        else:
+            hp, wp = x.h + 2 * x.halo, x.w + 2 * x.halo
+            ho = (hp + 2 * g.pad - g.r) // g.stride + 1
+            wo = (wp + 2 * g.pad - g.s) // g.stride + 1
+            y = ActBuf(x.n, ho, wo, g.c_out, halo=halo_out, fp32=fp32, zero=False)
+            ops.conv_fprop(x, L.spec, y, bias=bias, act=act)
+        return y
+
+    def _conv_bwd(self, name, x, dy, grads, need_dx, dx_halo=0):
+        """Backward of layer `name`: x = saved layer input, dy = gradient of its raw output.
+        Writes the weight (and used bias) gradient into `grads`; returns dx (incl. halo when dx_halo > 0)."""
+        L = self.layers[name]
+        g = L.spec.g
+        if grads is not None:
+            gw = grads[name + ".weight"]
+            if L.transposed:
+                ops.conv_wgrad(dy, x, L.spec, gw)  # conv view: input role = dy_T (large), output-grad role = x_T
+            else:
+                ops.conv_wgrad(x, dy, L.spec, gw)
+            if L.use_bias:
+                ops.bias_grad(dy, grads[name + ".bias"], L.bias.numel())
+            if self.grad_ready is not None:
+                self.grad_ready(name + ".weight")
+                if L.bias is not None:
+                    self.grad_ready(name + ".bias")  # unused biases (before an InstanceNorm) keep gradient 0
+        if not need_dx:
+            return None
+        if L.transposed:
+            dx = ActBuf(x.n, x.h, x.w, g.c_out, halo=0, zero=False)
+            ops.conv_fprop(dy, L.spec, dx)
+        else:
+            dx = ActBuf(x.n, x.h, x.w, g.c_in, halo=dx_halo, zero=False)
+            ops.conv_dgrad(dy, L.spec, dx)
+        return dx
+
+
+class AttentionGeneratorNet(_NetBase):
+    """PairedAttentionGenerator / AttentionGANGenerator (model_architectures.py:305-400, 163-258)."""
+
+    def __init__(self, module):
+        super().__init__(module)
+        m = module
+        self._add("conv1", m.conv1, 7, 1, 0)
+        self._add("conv2", m.conv2, 3, 2, 1)
+        self._add("conv3", m.conv3, 3, 2, 1)
+        for i, blk in enumerate(m.resnet_blocks):
+            self._add(f"resnet_blocks.{i}.conv1", blk.conv1, 3, 1, 0)
+            self._add(f"resnet_blocks.{i}.conv2", blk.conv2, 3, 1, 0)
+        for br in ("content", "attention"):
+            self._add(f"deconv1_{br}", getattr(m, f"deconv1_{br}"), 3, 2, 1, transposed=True)
+            self._add(f"deconv2_{br}", getattr(m, f"deconv2_{br}"), 3, 2, 1, transposed=True)
+        self._add("deconv3_content", m.deconv3_content, 7, 1, 0, use_bias=True)
+        self._add("deconv3_attention", m.deconv3_attention, 1, 1, 0, use_bias=True)
+        self.n_blocks = len(m.resnet_blocks)
+
+    def forward(self, x, d_input=None, d_c0=0, want_nchw=True):
+        """x: fp32 NCHW [B, C<=16, H, W]. Returns (out_nchw, tape). If d_input (ActBuf [B,H,W,16]) is given the
+        generated image is also written as bf16 into its channels [d_c0, d_c0+3)."""
+        self.repack()
+        B, C, H, W = x.shape
+        t = {}
+        t["xin"] = ActBuf(B, H, W, 16, halo=3, zero=False)
+        ops.pack_nchw(x, t["xin"], 0, zero_rest=True)
+        t["y1"] = self._conv(t["xin"], "conv1")
+        t["s1"], t["z1"] = _norm_act(t["y1"], ACT_RELU, 0)
+        t["y2"] = self._conv(t["z1"], "conv2")
+        t["s2"], t["z2"] = _norm_act(t["y2"], ACT_RELU, 0)
+        t["y3"] = self._conv(t["z2"], "conv3")
+        t["s3"], xcur = _norm_act(t["y3"], ACT_RELU, 1)
+        t["x0"] = xcur
+        for i in range(self.n_blocks):
+            b = f"resnet_blocks.{i}."
+            ya = self._conv(xcur, b + "conv1")
+            sa, za = _norm_act(ya, ACT_RELU, 1)
+            yb = self._conv(za, b + "conv2")
+            last = i == self.n_blocks - 1
+            sb, xnext = _norm_act(yb, ACT_NONE, 0 if last else 1, residual=xcur)
+            t[f"b{i}"] = (ya, sa, za, yb, sb)
+            t[f"x{i + 1}"] = xnext
+            xcur = xnext
+        for br in ("content", "attention"):
+            u1 = self._conv(xcur, f"deconv1_{br}")
+            s1, v1 = _norm_act(u1, ACT_RELU, 0)
+            u2 = self._conv(v1, f"deconv2_{br}")
+            s2, v2 = _norm_act(u2, ACT_RELU, 3 if br == "content" else 0)
+            t[br] = (u1, s1, v1, u2, s2, v2)
+        t["c"] = self._conv(t["content"][5], "deconv3_content", fp32=True, act=ACT_TANH)
+        t["l"] = self._conv(t["attention"][5], "deconv3_attention", fp32=True)
+        out = torch.empty(B, 3, H, W, dtype=torch.float32, device=x.device) if want_nchw else None
+        mask = torch.empty(B, H, W, dtype=torch.float32, device=x.device)
+        ops.blend_fwd(t["c"], t["l"], t["xin"], out=d_input, out_c0=d_c0, out_nchw=out, mask=mask)
+        t["mask"] = mask
+        return out, t
+
+    def backward(self, t, grads, dout_nchw=None, dout_nhwc=None, dout_c0=0, need_dx=False):
+        """Accumulates nothing: writes every parameter gradient of this call into `grads` (overwrite).
+        Returns the fp32 NCHW input gradient [B, 16->C, H, W] if need_dx."""
+        xin = t["xin"]
+        B, H, W = xin.n, xin.h, xin.w
+        dev = xin.t.device
+        dc = ActBuf(B, H, W, 32, zero=False)
+        dl = ActBuf(B, H, W, 16, zero=False)
+        dimg = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev) if need_dx else None
+        ops.blend_bwd(t["c"], t["l"], xin, dc, dl, dout_nchw=dout_nchw, dout_nhwc=dout_nhwc, dout_c0=dout_c0,
+                      dimage_nchw=dimg)
+        gx = []
+        for br, dhead, head in (("content", dc, "deconv3_content"), ("attention", dl, "deconv3_attention")):
+            u1, s1, v1, u2, s2, v2 = t[br]
+            dv2 = self._conv_bwd(head, v2, dhead, grads, True, dx_halo=v2.halo)
+            du2 = ActBuf(u2.n, u2.h, u2.w, u2.c, zero=False)
+            ops.instnorm_bwd(dv2, u2, s2, ACT_RELU, du2)
+            dv1 = self._conv_bwd(f"deconv2_{br}", v1, du2, grads, True)
+            du1 = ActBuf(u1.n, u1.h, u1.w, u1.c, zero=False)
+            ops.instnorm_bwd(dv1, u1, s1, ACT_RELU, du1)
+            gx.append(self._conv_bwd(f"deconv1_{br}", t[f"x{self.n_blocks}"], du1, grads, True))
+        dz, dz2 = gx[0], gx[1]  # gradient w.r.t. x_n interior = sum of the two decoder branches
+        for i in reversed(range(self.n_blocks)):
+            ya, sa, za, yb, sb = t[f"b{i}"]
+            b = f"resnet_blocks.{i}."
+            xi = t[f"x{i}"]
+            gres = ActBuf(yb.n, yb.h, yb.w, yb.c, zero=False)  # total gradient w.r.t. x_{i+1} (skip branch)
+            dyb = ActBuf(yb.n, yb.h, yb.w, yb.c, zero=False)
+            ops.instnorm_bwd(dz, yb, sb, ACT_NONE, dyb, dz2=dz2, dres=gres)
+            dza = self._conv_bwd(b + "conv2", za, dyb, grads, True, dx_halo=1)
+            dya = ActBuf(ya.n, ya.h, ya.w, ya.c, zero=False)
+            ops.instnorm_bwd(dza, ya, sa, ACT_RELU, dya)
+            dz = self._conv_bwd(b + "conv1", xi, dya, grads, True, dx_halo=1)
+            dz2 = gres
+        dy3 = ActBuf(t["y3"].n, t["y3"].h, t["y3"].w, t["y3"].c, zero=False)
+        ops.instnorm_bwd(dz, t["y3"], t["s3"], ACT_RELU, dy3, dz2=dz2)
+        dz2_ = self._conv_bwd("conv3", t["z2"], dy3, grads, True)
+        dy2 = ActBuf(t["y2"].n, t["y2"].h, t["y2"].w, t["y2"].c, zero=False)
+        ops.instnorm_bwd(dz2_, t["y2"], t["s2"], ACT_RELU, dy2)
+        dz1 = self._conv_bwd("conv2", t["z1"], dy2, grads, True)
+        dy1 = ActBuf(t["y1"].n, t["y1"].h, t["y1"].w, t["y1"].c, zero=False)
+        ops.instnorm_bwd(dz1, t["y1"], t["s1"], ACT_RELU, dy1)
+        dxin = self._conv_bwd("conv1", xin, dy1, grads, need_dx, dx_halo=3)
+        if not need_dx:
+            return None
+        folded = ActBuf(B, H, W, 16, zero=False)
+        ops.halo_fold(dxin, None, folded)
+        c_in = self.layers["conv1"].c_valid
+        dx = torch.zeros(B, c_in, H, W, dtype=torch.float32, device=dev)
+        ops.unpack_nchw(folded, dx, 0)
+        dx[:, :3] += dimg
+        return dx
+
+
+class PatchGANNet(_NetBase):
+    """InstanceNorm 70x70 PatchGAN (model_architectures.py:420-441, 136-157, 278-299)."""
+
+    def __init__(self, module):
+        super().__init__(module)
+        seq = module.model
+        self._add("model.0", seq[0], 4, 2, 1, use_bias=True)
+        self._add("model.2", seq[2], 4, 2, 1)
+        self._add("model.5", seq[5], 4, 2, 1)
+        self._add("model.8", seq[8], 4, 1, 1)
+        self._add("model.11", seq[11], 4, 1, 1, use_bias=True)
+
+    def forward_buf(self, din):
+        """din: ActBuf [B, H, W, 16] (D input, channels beyond the real ones zero). Returns (logits ActBuf fp32, tape)."""
+        self.repack()
+        t = {"din": din}
+        t["a1"] = self._conv(din, "model.0", act=ACT_LEAKY)
+        t["y2"] = self._conv(t["a1"], "model.2")
+        t["s2"], t["a2"] = _norm_act(t["y2"], ACT_LEAKY, 0)
+        t["y3"] = self._conv(t["a2"], "model.5")
+        t["s3"], t["a3"] = _norm_act(t["y3"], ACT_LEAKY, 0)
+        t["y4"] = self._conv(t["a3"], "model.8")
+        t["s4"], t["a4"] = _norm_act(t["y4"], ACT_LEAKY, 0)
+        t["logits"] = self._conv(t["a4"], "model.11", fp32=True)
+        return t["logits"], t
+
+    def forward(self, x):
+        """x: fp32 NCHW [B, C<=16, H, W] -> (logits fp32 NCHW [B,1,h,w], tape)"""
+        B, C, H, W = x.shape
+        din = ActBuf(B, H, W, 16, zero=False)
+        ops.pack_nchw(x, din, 0, zero_rest=True)
+        logits, t = self.forward_buf(din)
+        return logits.to_nchw(1), t
+
+    def backward(self, t, dlogits, grads, need_dx):
+        """dlogits: ActBuf bf16 [B,h,w,16] (channel 0 valid). grads may be None (parameters frozen).
+        Returns d(din) ActBuf [B,H,W,16] if need_dx."""
+        da4 = self._conv_bwd("model.11", t["a4"], dlogits, grads, True)
+        dy4 = ActBuf(t["y4"].n, t["y4"].h, t["y4"].w, t["y4"].c, zero=False)
+        ops.instnorm_bwd(da4, t["y4"], t["s4"], ACT_LEAKY, dy4)
+        da3 = self._conv_bwd("model.8", t["a3"], dy4, grads, True)
+        dy3 = ActBuf(t["y3"].n, t["y3"].h, t["y3"].w, t["y3"].c, zero=False)
+        ops.instnorm_bwd(da3, t["y3"], t["s3"], ACT_LEAKY, dy3)
+        da2 = self._conv_bwd("model.5", t["a2"], dy3, grads, True)
+        dy2 = ActBuf(t["y2"].n, t["y2"].h, t["y2"].w, t["y2"].c, zero=False)
+        ops.instnorm_bwd(da2, t["y2"], t["s2"], ACT_LEAKY, dy2)
+        da1 = self._conv_bwd("model.2", t["a1"], dy2, grads, True)
+        dy1 = ActBuf(t["a1"].n, t["a1"].h, t["a1"].w, t["a1"].c, zero=False)
+        ops.act_bwd(da1, t["a1"], ACT_LEAKY, dy1)
+        return self._conv_bwd("model.0", t["din"], dy1, grads, need_dx)

@@ -51,6 +51,11 @@ class ActBuf:
         return ActBuf(self.n, self.h, self.w, c, self.halo, self.fp32, tensor=self.t, c0=self.c0 + c0,
                       c_stride=self.c_stride)
 
+    def batch_slice(self, start, n):
+        """A view of images [start, start+n) (shares storage)."""
+        return ActBuf(n, self.h, self.w, self.c, self.halo, self.fp32, tensor=self.t[start:start + n], c0=self.c0,
+                      c_stride=self.c_stride)
+
     def interior(self):
         """torch view [n, h, w, c] of the interior."""
         hl = self.halo

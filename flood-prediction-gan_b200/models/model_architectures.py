@@ -1,0 +1,182 @@
+"""Drop-in generator / discriminator classes with the reference's names, constructor signatures, sub-module names
+and state_dict layout (reference: models/model_architectures.py), computing through the sm_100a kernel library.
+
+The torch.nn layers instantiated here are PARAMETER CONTAINERS only (same construction order and RNG consumption as
+the reference, so `Model(seed=...)` initialises identical weights and reference checkpoints load unchanged); their
+own forward() is never called. forward() hands the whole network to a native executor (fpgan.networks) wrapped in
+one torch.autograd.Function, so `loss.backward()` / optimisers / requires_grad toggling work as in the reference.
+There is no CPU or eager-PyTorch fallback: inputs must live on a CUDA device.
+"""
+import torch
+from torch import nn
+
+from fpgan import networks, ops
+
+
+def _require_cuda(x, who):
+    if not x.is_cuda:
+        raise RuntimeError(f"{who}: input is on {x.device}; this implementation only runs on a CUDA (sm_100a) device "
+                           "and has no CPU fallback")
+
+
+class _NetFunction(torch.autograd.Function):
+    """One autograd node per network call; parameters are inputs so that autograd routes their gradients."""
+
+    @staticmethod
+    def forward(ctx, owner, x, *params):
+        net = owner._executor()
+        x32 = x.detach().float().contiguous()
+        out, tape = net.forward(x32)
+        ctx.net, ctx.tape, ctx.owner = net, tape, owner
+        ctx.n_params = len(params)
+        ctx.in_channels = x.shape[1]
+        owner._after_forward(tape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        net = ctx.net
+        need_dx = ctx.needs_input_grad[1]
+        need_dw = any(ctx.needs_input_grad[2:])
+        named = net.named_params()
+        grads = networks.Grads(named) if need_dw else None
+        dx = ctx.owner._run_backward(net, ctx.tape, dout.contiguous().float(), grads, need_dx)
+        ctx.tape = None
+        if need_dw:
+            gl = tuple(grads[n] if ctx.needs_input_grad[2 + i] else None for i, (n, _) in enumerate(named))
+        else:
+            gl = (None,) * ctx.n_params
+        return (None, dx) + gl
+
+
+class _NativeModule(nn.Module):
+    _executor_cls = None
+
+    def _executor(self):
+        p = next(self.parameters())
+        key = (p.device, p.data_ptr())
+        if getattr(self, "_exec_key", None) != key:
+            if not p.is_cuda:
+                raise RuntimeError(f"{type(self).__name__}: parameters are on {p.device}; move the module to a CUDA "
+                                   "device (no CPU fallback)")
+            object.__setattr__(self, "_exec", type(self)._executor_cls(self))
+            object.__setattr__(self, "_exec_key", key)
+        return self._exec
+
+    def _after_forward(self, tape):
+        pass
+
+    def forward(self, x):
+        _require_cuda(x, type(self).__name__)
+        params = [p for _, p in self.named_parameters()]
+        return _NetFunction.apply(self, x, *params)
+
+
+# ------------------------------------------------------------------------------------------------ generators
+class _AttentionGeneratorBase(_NativeModule):
+    _executor_cls = networks.AttentionGeneratorNet
+
+    def __init__(self, input_channels, block_cls):
+        super().__init__()
+        self.input_channels = input_channels
+        self.last_attention_mask = None
+        self.conv1 = nn.Conv2d(input_channels, 64, kernel_size=7, stride=1, padding=0)
+        self.conv1_norm = nn.InstanceNorm2d(64)
+        self.conv2 = nn.Conv2d(64, 128, kernel_size=3, stride=2, padding=1)
+        self.conv2_norm = nn.InstanceNorm2d(128)
+        self.conv3 = nn.Conv2d(128, 256, kernel_size=3, stride=2, padding=1)
+        self.conv3_norm = nn.InstanceNorm2d(256)
+        self.resnet_blocks = nn.Sequential(*[block_cls(channel=256, kernel=3, stride=1, padding=1) for _ in range(9)])
+        for branch, out_ch, k in (("content", 27, 7), ("attention", 10, 1)):
+            setattr(self, f"deconv1_{branch}", nn.ConvTranspose2d(256, 128, 3, 2, 1, 1))
+            setattr(self, f"deconv1_norm_{branch}", nn.InstanceNorm2d(128))
+            setattr(self, f"deconv2_{branch}", nn.ConvTranspose2d(128, 64, 3, 2, 1, 1))
+            setattr(self, f"deconv2_norm_{branch}", nn.InstanceNorm2d(64))
+            setattr(self, f"deconv3_{branch}", nn.Conv2d(64, out_ch, k, 1, 0))
+        self.tanh = nn.Tanh()
+        self.softmax = nn.Softmax(dim=1)
+
+    def _after_forward(self, tape):
+        self.last_attention_mask = tape["mask"]  # background attention a_10, [B, H, W] (reference :396)
+
+    def _run_backward(self, net, tape, dout, grads, need_dx):
+        return net.backward(tape, grads, dout_nchw=dout, need_dx=need_dx)
+
+
+class _ResidualBlockParams(nn.Module):
+    """Parameter container of one residual block (reference :402-418 / :260-276); executed by the generator."""
+
+    def __init__(self, channel, kernel, stride, padding):
+        super().__init__()
+        self.padding = padding
+        self.conv1 = nn.Conv2d(channel, channel, kernel, stride, 0)
+        self.conv1_norm = nn.InstanceNorm2d(channel)
+        self.conv2 = nn.Conv2d(channel, channel, kernel, stride, 0)
+        self.conv2_norm = nn.InstanceNorm2d(channel)
+
+    def forward(self, x):
+        raise RuntimeError("residual blocks are executed by the enclosing generator's native executor")
+
+
+class PairedAttentionBlock(_ResidualBlockParams):
+    pass
+
+
+class AttentionGANBlock(_ResidualBlockParams):
+    pass
+
+
+class PairedAttentionGenerator(_AttentionGeneratorBase):
+    def __init__(self, input_channels):
+        super().__init__(input_channels, PairedAttentionBlock)
+
+
+class AttentionGANGenerator(_AttentionGeneratorBase):
+    def __init__(self, input_channels):
+        super().__init__(input_channels, AttentionGANBlock)
+
+
+# ------------------------------------------------------------------------------------------------ discriminators
+class _InstanceNormPatchGAN(_NativeModule):
+    _executor_cls = networks.PatchGANNet
+
+    def __init__(self, in_channels):
+        super().__init__()
+        seq = [nn.Conv2d(in_channels, 64, kernel_size=4, stride=2, padding=1), nn.LeakyReLU(0.2, True)]
+        prev = 64
+        for mult in (2, 4):
+            seq += [nn.Conv2d(prev, 64 * mult, kernel_size=4, stride=2, padding=1, bias=True),
+                    nn.InstanceNorm2d(64 * mult), nn.LeakyReLU(0.2, True)]
+            prev = 64 * mult
+        seq += [nn.Conv2d(prev, 512, kernel_size=4, stride=1, padding=1, bias=True), nn.InstanceNorm2d(512),
+                nn.LeakyReLU(0.2, True)]
+        seq += [nn.Conv2d(512, 1, kernel_size=4, stride=1, padding=1)]
+        self.model = nn.Sequential(*seq)
+
+    def _run_backward(self, net, tape, dout, grads, need_dx):
+        dl = ops.ActBuf.from_nchw(dout, c_pad=16)
+        dd = net.backward(tape, dl, grads, need_dx)
+        if not need_dx:
+            return None
+        c = tape["c_in"]
+        dx = torch.empty(dd.n, c, dd.h, dd.w, dtype=torch.float32, device=dout.device)
+        ops.unpack_nchw(dd, dx, 0)
+        return dx
+
+    def _after_forward(self, tape):
+        tape["c_in"] = self.model[0].weight.shape[1]
+
+
+class PairedAttentionDiscriminator(_InstanceNormPatchGAN):
+    def __init__(self, input_channels):
+        super().__init__(input_channels + 3)
+
+
+class AttentionGANDiscriminator(_InstanceNormPatchGAN):
+    def __init__(self, input_channels):
+        super().__init__(input_channels)
+
+
+class CycleGANDiscriminator(_InstanceNormPatchGAN):
+    def __init__(self, input_channels):
+        super().__init__(input_channels)

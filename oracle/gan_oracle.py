@@ -208,6 +208,7 @@ class Adam:
         self.v = [torch.zeros_like(p) for p in self.params]
         self.t = 0
 
+    @torch.no_grad()
     def step(self, grads):
         self.t += 1
         b1, b2 = self.betas
