@@ -9,6 +9,28 @@ from . import lib as L
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = L.ACT_NONE, L.ACT_RELU, L.ACT_LEAKY, L.ACT_TANH
 
 
+LAUNCHES = 0     # kernels launched through this module (bench.py reports it as gpu_launches)
+PROFILE = None   # when a dict: key -> [(start_event, end_event), ...] around every operator call
+
+
+def _run(key, n_kernels, name, *args):
+    global LAUNCHES
+    LAUNCHES += n_kernels
+    if PROFILE is None:
+        L.call(name, *args)
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    L.call(name, *args)
+    b.record()
+    PROFILE.setdefault(key, []).append((a, b))
+
+
+def _conv_key(kind, n, h, w, spec):
+    g = spec.g
+    return f"{kind} n{n} {h}x{w} c{g.c_in} k{g.c_out} r{g.r} s{g.stride}"
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -109,23 +131,25 @@ class ConvSpec:
                 nbytes = lib.fpg_packed_weight_bytes(self.gref())
                 assert nbytes > 0
                 self.w_fprop = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)
-            L.call("fpg_pack_weights", _ptr(weight), sk, sc, self.c_out_valid, self.c_in_valid, self.gref(),
+            _run("pack_weights", 1, "fpg_pack_weights", _ptr(weight), sk, sc, self.c_out_valid, self.c_in_valid, self.gref(),
                    _ptr(self.w_fprop), _stream())
         if dgrad:
             if self.w_dgrad is None:
                 nbytes = lib.fpg_packed_weight_dgrad_bytes(self.gref())
                 assert nbytes > 0
                 self.w_dgrad = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)
-            L.call("fpg_pack_weights_dgrad", _ptr(weight), sk, sc, self.c_out_valid, self.c_in_valid, self.gref(),
+            _run("pack_weights", 4 if self.g.stride == 2 else 1, "fpg_pack_weights_dgrad", _ptr(weight), sk, sc, self.c_out_valid, self.c_in_valid, self.gref(),
                    _ptr(self.w_dgrad), _stream())
 
 
 def conv_fprop(x, spec, y, bias=None, act=ACT_NONE):
-    L.call("fpg_conv2d_fprop", x.ref(), _ptr(spec.w_fprop), _ptr(bias), act, spec.gref(), y.ref(), _stream())
+    _run(_conv_key("fprop", y.n, y.h, y.w, spec), 1, "fpg_conv2d_fprop", x.ref(), _ptr(spec.w_fprop), _ptr(bias), act,
+         spec.gref(), y.ref(), _stream())
 
 
 def conv_dgrad(dy, spec, dx, bias=None, act=ACT_NONE):
-    L.call("fpg_conv2d_dgrad", dy.ref(), _ptr(spec.w_dgrad), _ptr(bias), act, spec.gref(), dx.ref(), _stream())
+    _run(_conv_key("dgrad", dx.n, dx.h, dx.w, spec), 4 if spec.g.stride == 2 else 1, "fpg_conv2d_dgrad", dy.ref(),
+         _ptr(spec.w_dgrad), _ptr(bias), act, spec.gref(), dx.ref(), _stream())
 
 
 _ws_cache = {}
@@ -150,12 +174,12 @@ def conv_wgrad(x, dy, spec, dw):
         L.check(-22, "fpg_conv2d_wgrad_ws_bytes")
     ws = workspace(nbytes, dw.device)
     rs = spec.g.r * spec.g.s
-    L.call("fpg_conv2d_wgrad", x.ref(), dy.ref(), spec.gref(), _ptr(dw), spec.c_in_valid * rs, rs,
-           spec.c_out_valid, spec.c_in_valid, _ptr(ws), _stream())
+    _run(_conv_key("wgrad", dy.n, dy.h, dy.w, spec), 2, "fpg_conv2d_wgrad", x.ref(), dy.ref(), spec.gref(), _ptr(dw),
+         spec.c_in_valid * rs, rs, spec.c_out_valid, spec.c_in_valid, _ptr(ws), _stream())
 
 
 def bias_grad(dy, db, k_valid):
-    L.call("fpg_bias_grad", dy.ref(), _ptr(db), k_valid, _stream())
+    _run("bias_grad", 1, "fpg_bias_grad", dy.ref(), _ptr(db), k_valid, _stream())
 
 
 def _scratch_for(y):
@@ -164,66 +188,66 @@ def _scratch_for(y):
 
 
 def instnorm_stats(y, stats, eps=1e-5):
-    L.call("fpg_instnorm_stats", y.ref(), eps, _ptr(stats), _ptr(_scratch_for(y)), _stream())
+    _run("instnorm_stats", 2, "fpg_instnorm_stats", y.ref(), eps, _ptr(stats), _ptr(_scratch_for(y)), _stream())
 
 
 def instnorm_apply(y, stats, act, z, residual=None):
-    L.call("fpg_instnorm_apply", y.ref(), _ptr(stats), act, residual.ref() if residual is not None else None,
+    _run("instnorm_apply", 1, "fpg_instnorm_apply", y.ref(), _ptr(stats), act, residual.ref() if residual is not None else None,
            z.ref(), _stream())
 
 
 def instnorm_bwd(dz, y, stats, act, dy, dz2=None, dres=None):
-    L.call("fpg_instnorm_bwd", dz.ref(), dz2.ref() if dz2 is not None else None, y.ref(), _ptr(stats), act, dy.ref(),
+    _run("instnorm_bwd", 3, "fpg_instnorm_bwd", dz.ref(), dz2.ref() if dz2 is not None else None, y.ref(), _ptr(stats), act, dy.ref(),
            dres.ref() if dres is not None else None, _ptr(_scratch_for(y)), _stream())
 
 
 def act_bwd(dz, z, act, dx):
-    L.call("fpg_act_bwd", dz.ref(), z.ref(), act, dx.ref(), _stream())
+    _run("act_bwd", 1, "fpg_act_bwd", dz.ref(), z.ref(), act, dx.ref(), _stream())
 
 
 def halo_fold(a, b, c):
-    L.call("fpg_halo_fold", a.ref(), b.ref() if b is not None else None, c.ref(), _stream())
+    _run("halo_fold", 1, "fpg_halo_fold", a.ref(), b.ref() if b is not None else None, c.ref(), _stream())
 
 
 def blend_fwd(content, logits, inp, out=None, out_c0=0, out_nchw=None, mask=None):
-    L.call("fpg_blend_fwd", content.ref(), logits.ref(), inp.ref(), out.ref() if out is not None else None, out_c0,
+    _run("blend_fwd", 1, "fpg_blend_fwd", content.ref(), logits.ref(), inp.ref(), out.ref() if out is not None else None, out_c0,
            _ptr(out_nchw), _ptr(mask), _stream())
 
 
 def blend_bwd(content, logits, inp, dcontent, dlogits, dout_nchw=None, dout_nhwc=None, dout_c0=0, dimage_nchw=None):
-    L.call("fpg_blend_bwd", _ptr(dout_nchw), dout_nhwc.ref() if dout_nhwc is not None else None, dout_c0,
+    _run("blend_bwd", 1, "fpg_blend_bwd", _ptr(dout_nchw), dout_nhwc.ref() if dout_nhwc is not None else None, dout_c0,
            content.ref(), logits.ref(), inp.ref(), dcontent.ref(), dlogits.ref(), _ptr(dimage_nchw), _stream())
 
 
 def mse_const_loss(logits, target, weight, grad_scale, loss, dlogits=None):
-    L.call("fpg_mse_const_loss", logits.ref(), float(target), float(weight), float(grad_scale), _ptr(loss),
+    _run("mse_const_loss", 1, "fpg_mse_const_loss", logits.ref(), float(target), float(weight), float(grad_scale), _ptr(loss),
            dlogits.ref() if dlogits is not None else None, _stream())
 
 
 def l1_loss(pred, target, weight, grad_scale, loss, dpred=None, accumulate=False):
     ws = workspace(4096, pred.device)
-    L.call("fpg_l1_loss", _ptr(pred), _ptr(target), pred.numel(), float(weight), float(grad_scale), _ptr(loss),
+    _run("l1_loss", 2, "fpg_l1_loss", _ptr(pred), _ptr(target), pred.numel(), float(weight), float(grad_scale), _ptr(loss),
            _ptr(dpred), 1 if accumulate else 0, _ptr(ws), _stream())
 
 
 def pack_nchw(src, dst, c0=0, zero_rest=False):
     assert src.dtype == torch.float32 and src.is_contiguous()
-    L.call("fpg_pack_nchw", _ptr(src), src.shape[1], dst.ref(), c0, 1 if zero_rest else 0, _stream())
+    _run("pack_nchw", 1, "fpg_pack_nchw", _ptr(src), src.shape[1], dst.ref(), c0, 1 if zero_rest else 0, _stream())
 
 
 def unpack_nchw(src, dst, c0=0, accumulate=False):
     assert dst.dtype == torch.float32 and dst.is_contiguous()
-    L.call("fpg_unpack_nchw", src.ref(), c0, _ptr(dst), dst.shape[1], 1 if accumulate else 0, _stream())
+    _run("unpack_nchw", 1, "fpg_unpack_nchw", src.ref(), c0, _ptr(dst), dst.shape[1], 1 if accumulate else 0, _stream())
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
-    L.call("fpg_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
+    _run("adam_step", 1, "fpg_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
            float(eps), int(step), float(grad_scale), _stream())
 
 
 def flood_mask(logits, mask):
-    L.call("fpg_flood_mask", _ptr(logits), _ptr(mask), logits.numel(), _stream())
+    _run("flood_mask", 1, "fpg_flood_mask", _ptr(logits), _ptr(mask), logits.numel(), _stream())
 
 
 def confusion_counts(pred, truth, counts):
-    L.call("fpg_confusion_counts", _ptr(pred), _ptr(truth), pred.numel(), _ptr(counts), _stream())
+    _run("confusion_counts", 1, "fpg_confusion_counts", _ptr(pred), _ptr(truth), pred.numel(), _ptr(counts), _stream())
