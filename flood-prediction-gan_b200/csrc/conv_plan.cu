@@ -89,11 +89,21 @@ static void out_view_of(const fpg_act* y, int with_halo, fpg_out_view* o) {
   o->fp32 = y->fp32;
 }
 
-static void pick_tile(int wo, int* tile_w, int* tile_h, int pixels) {
-  int tw = pow2_at_least(wo < pixels ? wo : pixels);
-  if (tw > pixels) tw = pixels;
-  *tile_w = tw;
-  *tile_h = pixels / tw;
+// Pixel tile (tile_w x tile_h == pixels, tile_w a power of two) covering a ho x wo grid with the fewest tiles;
+// ties go to the widest tile (longest contiguous runs per TMA box row).
+static void pick_tile(int ho, int wo, int* tile_w, int* tile_h, int pixels) {
+  int best_tw = pixels, best_tiles = -1;
+  for (int tw = pixels; tw >= 1; tw >>= 1) {
+    const int th = pixels / tw;
+    if (th > 256) break;  // TMA box dimension limit
+    const int tiles = ceil_div(wo, tw) * ceil_div(ho, th);
+    if (best_tiles < 0 || tiles < best_tiles) {
+      best_tiles = tiles;
+      best_tw = tw;
+    }
+  }
+  *tile_w = best_tw;
+  *tile_h = pixels / best_tw;
 }
 
 static int pick_block_n(int n_total, int m_tiles, int sms) {
@@ -166,7 +176,7 @@ static int plan_fprop(const fpg_act* x, const void* w, const float* bias, int ac
   for (int r = 0; r < g->r; ++r)
     for (int s = 0; s < g->s; ++s) d->taps[r * g->s + s] = fwd_tap(r, s, g->stride, g->pad, x->c_stride);
   for (int t = real_taps; t < d->num_taps; ++t) d->taps[t] = d->taps[0];
-  pick_tile(wo, &d->tile_w, &d->tile_h, 128);
+  pick_tile(ho, wo, &d->tile_w, &d->tile_h, 128);
   d->tiles_x = ceil_div(wo, d->tile_w);
   d->tiles_y = ceil_div(ho, d->tile_h);
   d->n_img = x->n;
@@ -236,7 +246,7 @@ static int plan_dgrad(const fpg_act* dy, const void* wt, const float* bias, int 
     for (int t = nt; t < d->num_taps; ++t) d->taps[t] = d->taps[0];
     d->num_sub = d->num_taps * (g->c_out / cblk);
     const int oh = g->stride == 2 ? hp / 2 : hp, ow = g->stride == 2 ? wp / 2 : wp;  // class output grid
-    pick_tile(ow, &d->tile_w, &d->tile_h, 128);
+    pick_tile(oh, ow, &d->tile_w, &d->tile_h, 128);
     d->tiles_x = ceil_div(ow, d->tile_w);
     d->tiles_y = ceil_div(oh, d->tile_h);
     d->n_img = dx->n;
@@ -288,7 +298,7 @@ static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* 
   memset(d, 0, sizeof(*d));
   d->taps_r = g->r;
   d->taps_s = g->s;
-  pick_tile(wo, &d->tile_w, &d->tile_h, 64);
+  pick_tile(ho, wo, &d->tile_w, &d->tile_h, 64);
   d->kt_x = ceil_div(wo, d->tile_w);
   d->kt_y = ceil_div(ho, d->tile_h);
   d->n_img = x->n;
@@ -301,6 +311,7 @@ static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* 
   if (big_out) {
     // X = dy (rows = output channels)
     d->x_is_dy = 1;
+    d->tap_on_x = 0;
     d->x_ca = 64;
     d->x_atoms = g->c_out % 128 == 0 ? 2 : 1;
     d->x_groups = g->c_out / (64 * d->x_atoms);
@@ -335,15 +346,37 @@ static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* 
     d->x_atoms = g->c_in % 128 == 0 ? 2 : 1;
     d->x_groups = g->c_in / (64 * d->x_atoms);
     d->x_taps_mode = 0;
-    d->x_ntaps = ntaps;
-    for (int t = 0; t < ntaps; ++t) d->x_taps[t] = in_taps[t];
-    make_act_view(x, g->stride, 64, d->tile_w, d->tile_h, &d->x);
     d->y_ca = g->c_out;
-    d->y_atoms = 1;
-    d->y_groups = 1;
-    d->y_taps_mode = 0;
-    d->y_ntaps = 1;
-    d->y_taps[0] = null_tap;
+    if (g->stride == 1 && ntaps > 1) {
+      // Shift dy instead of x: dW[k, (r,s), c] = sum_p x[p, c] * dy[p - (r,s) + pad, k] over INPUT pixels p. Several
+      // taps of dy become atoms of one wide N tile, so each x tile is loaded once per filter row instead of once per
+      // tap (the tap-per-item form is L2-bandwidth bound: every item streams the whole input again).
+      d->tap_on_x = 0;
+      d->x_ntaps = 1;
+      d->x_taps[0] = null_tap;
+      pick_tile(hp, wp, &d->tile_w, &d->tile_h, 64);
+      d->kt_x = ceil_div(wp, d->tile_w);
+      d->kt_y = ceil_div(hp, d->tile_h);
+      d->y_atoms = largest_divisor_le(ntaps, 256 / g->c_out);
+      d->y_groups = ntaps / d->y_atoms;
+      d->y_taps_mode = 1;
+      d->y_ntaps = ntaps;
+      for (int r = 0; r < g->r; ++r)
+        for (int s = 0; s < g->s; ++s) {
+          fpg_tap t = {0, -(s - g->pad), 0, -(r - g->pad)};
+          d->y_taps[r * g->s + s] = t;
+        }
+    } else {
+      d->tap_on_x = 1;
+      d->x_ntaps = ntaps;
+      for (int t = 0; t < ntaps; ++t) d->x_taps[t] = in_taps[t];
+      d->y_atoms = 1;
+      d->y_groups = 1;
+      d->y_taps_mode = 0;
+      d->y_ntaps = 1;
+      d->y_taps[0] = null_tap;
+    }
+    make_act_view(x, g->stride, 64, d->tile_w, d->tile_h, &d->x);
     make_act_view(dy, 1, d->y_ca, d->tile_w, d->tile_h, &d->y);
   }
   const int NX = d->x_taps_mode ? d->x_groups : d->x_groups * d->x_ntaps;
@@ -370,7 +403,7 @@ static int64_t wgrad_ws_floats(const fpg_igemm_wgrad_desc* d) {
 struct ReduceArgs {
   int32_t x_ca, x_atoms, x_groups, x_taps_mode, x_ntaps;
   int32_t y_ca, y_atoms, y_groups, y_taps_mode, y_ntaps;
-  int32_t splits, x_is_dy;
+  int32_t splits, x_is_dy, tap_on_x;
   int64_t stride_k, stride_c;
   int32_t k_valid, c_valid;
 };
@@ -409,18 +442,9 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
       ych = ((yi % a.y_groups) * a.y_atoms + atom) * a.y_ca + within;
     }
   }
-  int k, c, tap;
-  if (a.x_is_dy) {
-    k = xch;
-    c = ych;
-    tap = ytap;
-    if (ytap >= a.y_ntaps) return;
-  } else {
-    k = ych;
-    c = xch;
-    tap = xtap;
-    if (xtap >= a.x_ntaps) return;
-  }
+  const int k = a.x_is_dy ? xch : ych, c = a.x_is_dy ? ych : xch;
+  const int tap = a.tap_on_x ? xtap : ytap;
+  if (tap >= (a.tap_on_x ? a.x_ntaps : a.y_ntaps)) return;
   if (k >= a.k_valid || c >= a.c_valid) return;
   float acc = 0.f;
   for (int s = 0; s < a.splits; ++s) acc += ws[s * per_split + idx];
@@ -525,6 +549,7 @@ int fpg_conv2d_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g
   a.y_ntaps = d.y_ntaps;
   a.splits = d.splits;
   a.x_is_dy = d.x_is_dy;
+  a.tap_on_x = d.tap_on_x;
   a.stride_k = dw_stride_k;
   a.stride_c = dw_stride_c;
   a.k_valid = k_valid;

@@ -47,10 +47,44 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
 
 // ------------------------------------------------------------------------------------------------ IN statistics
 // grid (splits, n); block 256. thread t owns channel group (t % G), pixel lane (t / G); G = c / 8.
-// partial[(i*splits + split)*c*2 + ch*2 + {0,1}] = {sum, sum of squares}
+// partial[(i*splits + split)*c*2 + ch*2 + {0,1}] = {sum, sum of squares}. The last CTA of an image to finish
+// (ticket counter, reset to 0 on exit) sums the partials in split order -> deterministic, no second launch.
 constexpr int kStatThreads = 256;
 
-__global__ void in_stats_partial_kernel(View y, float* __restrict__ partial) {
+__device__ __forceinline__ bool last_cta_of_image(int* counter, int total) {
+  __shared__ int ticket;
+  __threadfence();  // publish this CTA's partial sums
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(counter, 1);
+  __syncthreads();
+  if (ticket != total - 1) return false;
+  __threadfence();  // acquire the other CTAs' partial sums
+  return true;
+}
+
+// block-level fixed-order reduction of per-thread {s[8], ss[8]} over the pixel lanes -> partial[(i, split)]
+__device__ __forceinline__ void block_reduce_to_partial(const float (&s)[8], const float (&ss)[8], int G, int lanes,
+                                                        float* __restrict__ partial, int i, int split, int splits,
+                                                        int c) {
+  __shared__ float red[kStatThreads][17];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red[threadIdx.x][k] = s[k];
+    red[threadIdx.x][8 + k] = ss[k];
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < G * 16; o += kStatThreads) {
+    const int gg = o / 16, comp = o % 16;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[l * G + gg][comp];
+    const int ch = gg * 8 + (comp & 7);
+    partial[((static_cast<int64_t>(i) * splits + split) * c + ch) * 2 + (comp >> 3)] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kStatThreads)
+in_stats_kernel(View y, float* __restrict__ partial, float* __restrict__ stats, int* __restrict__ counters,
+                float inv_hw, float eps) {
   const int G = y.c / 8;
   const int lanes = kStatThreads / G;
   const int g = threadIdx.x % G, pl = threadIdx.x / G;
@@ -62,68 +96,48 @@ __global__ void in_stats_partial_kernel(View y, float* __restrict__ partial) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) s[k] = ss[k] = 0.f;
   const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(y.p);
-  if (pl < lanes) {
-    for (int p = p_begin + pl; p < p_end; p += lanes) {
-      const int py = p / y.w, px = p - py * y.w;
-      float f[8];
-      load8(base + y.at(i, py, px) + g * 8, f);
+  int p = p_begin + pl;
+  for (; p + 3 * lanes < p_end; p += 4 * lanes) {  // four independent 16-byte loads in flight
+    float f[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = p + u * lanes;
+      const int py = q / y.w, px = q - py * y.w;
+      load8(base + y.at(i, py, px) + g * 8, f[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        s[k] += f[k];
-        ss[k] += f[k] * f[k];
+        s[k] += f[u][k];
+        ss[k] += f[u][k] * f[u][k];
       }
+  }
+  for (; p < p_end; p += lanes) {
+    const int py = p / y.w, px = p - py * y.w;
+    float f[8];
+    load8(base + y.at(i, py, px) + g * 8, f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s[k] += f[k];
+      ss[k] += f[k] * f[k];
     }
   }
-  __shared__ float red[kStatThreads][17];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    red[threadIdx.x][k] = s[k];
-    red[threadIdx.x][8 + k] = ss[k];
+  block_reduce_to_partial(s, ss, G, lanes, partial, i, split, splits, y.c);
+  if (!last_cta_of_image(&counters[i], splits)) return;
+  for (int ch = threadIdx.x; ch < y.c; ch += kStatThreads) {
+    float a = 0.f, b = 0.f;
+    for (int sp = 0; sp < splits; ++sp) {
+      const float* q = partial + ((static_cast<int64_t>(i) * splits + sp) * y.c + ch) * 2;
+      a += q[0];
+      b += q[1];
+    }
+    const float mean = a * inv_hw;
+    const float var = fmaxf(b * inv_hw - mean * mean, 0.f);
+    stats[(static_cast<int64_t>(i) * y.c + ch) * 2] = mean;
+    stats[(static_cast<int64_t>(i) * y.c + ch) * 2 + 1] = rsqrtf(var + eps);
   }
-  __syncthreads();
-  // thread t < G*16 reduces one (channel group, component) over the pixel lanes in fixed order
-  for (int o = threadIdx.x; o < G * 16; o += kStatThreads) {
-    const int gg = o / 16, comp = o % 16;
-    float acc = 0.f;
-    for (int l = 0; l < lanes; ++l) acc += red[l * G + gg][comp];
-    const int ch = gg * 8 + (comp & 7);
-    partial[((static_cast<int64_t>(i) * splits + split) * y.c + ch) * 2 + (comp >> 3)] = acc;
-  }
-}
-
-// one thread per (image, channel): stats = {mean, rstd}
-__global__ void in_stats_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int n, int c,
-                                         int splits, float inv_hw, float eps) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * c) return;
-  const int i = idx / c, ch = idx % c;
-  float s = 0.f, ss = 0.f;
-  for (int sp = 0; sp < splits; ++sp) {
-    const float* p = partial + ((static_cast<int64_t>(i) * splits + sp) * c + ch) * 2;
-    s += p[0];
-    ss += p[1];
-  }
-  const float mean = s * inv_hw;
-  float var = ss * inv_hw - mean * mean;
-  var = fmaxf(var, 0.f);
-  stats[idx * 2] = mean;
-  stats[idx * 2 + 1] = rsqrtf(var + eps);
-}
-
-// for the backward: red = {mean(g'), mean(g' * zhat)}
-__global__ void in_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ red, int n, int c,
-                                       int splits, float inv_hw) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * c) return;
-  const int i = idx / c, ch = idx % c;
-  float s = 0.f, ss = 0.f;
-  for (int sp = 0; sp < splits; ++sp) {
-    const float* p = partial + ((static_cast<int64_t>(i) * splits + sp) * c + ch) * 2;
-    s += p[0];
-    ss += p[1];
-  }
-  red[idx * 2] = s * inv_hw;
-  red[idx * 2 + 1] = ss * inv_hw;
+  if (threadIdx.x == 0) counters[i] = 0;
 }
 
 __device__ __forceinline__ float act_fwd(float v, int act) {
@@ -134,47 +148,61 @@ __device__ __forceinline__ float act_grad(float pre, int act) {
 }
 
 // ------------------------------------------------------------------------------------------------ IN apply
-// one thread per (padded output pixel, 8-channel group)
-__global__ void in_apply_kernel(View y, const float* __restrict__ stats, int act, View res, int has_res, View z) {
+// grid (chunks, n). Thread t owns channel group (t % G) for its whole life -- the 8 {mean, rstd} pairs are loaded
+// once into registers (reloading them per pixel made L1 the bottleneck: 9x more L1 than DRAM sectors) -- and walks
+// the padded output pixels chunk_begin + (t / G) + k * lanes. A warp covers contiguous 512 B of one or more pixels.
+constexpr int kApplyPixelsPerLane = 16;
+
+__global__ void __launch_bounds__(256, 4)
+in_apply_kernel(View y, const float* __restrict__ stats, int act, View res, int has_res, View z) {
   const int G = y.c / 8;
-  const int64_t total = static_cast<int64_t>(z.n) * z.hp() * z.wp() * G;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int g = static_cast<int>(idx % G);
-  int64_t r = idx / G;
-  const int px = static_cast<int>(r % z.wp());
-  r /= z.wp();
-  const int py = static_cast<int>(r % z.hp());
-  const int i = static_cast<int>(r / z.hp());
-  const int sy = reflect_idx(py - z.halo, z.h), sx = reflect_idx(px - z.halo, z.w);
-  float f[8];
-  load8(static_cast<const __nv_bfloat16*>(y.p) + y.at(i, sy, sx) + g * 8, f);
-  const float4* st = reinterpret_cast<const float4*>(stats + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
-  float o[8];
+  const int lanes = 256 / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  const int i = blockIdx.y;
+  const int wp = z.wp();
+  const int npix = z.hp() * wp;
+  const int chunk = lanes * kApplyPixelsPerLane;
+  const int p_end = min(npix, (static_cast<int>(blockIdx.x) + 1) * chunk);
+  float mean[8], rstd[8];
+  {
+    const float4* st = reinterpret_cast<const float4*>(stats + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float4 ms = __ldg(st + k);  // {mean0, rstd0, mean1, rstd1}
-    o[2 * k] = act_fwd((f[2 * k] - ms.x) * ms.y, act);
-    o[2 * k + 1] = act_fwd((f[2 * k + 1] - ms.z) * ms.w, act);
+    for (int k = 0; k < 4; ++k) {
+      const float4 ms = __ldg(st + k);
+      mean[2 * k] = ms.x; rstd[2 * k] = ms.y; mean[2 * k + 1] = ms.z; rstd[2 * k + 1] = ms.w;
+    }
   }
-  if (has_res) {
-    float rr[8];
-    load8(static_cast<const __nv_bfloat16*>(res.p) + res.at(i, sy, sx) + g * 8, rr);
+  const __nv_bfloat16* yb = static_cast<const __nv_bfloat16*>(y.p) + g * 8;
+  const __nv_bfloat16* rb = static_cast<const __nv_bfloat16*>(res.p) + g * 8;
+  __nv_bfloat16* zb = static_cast<__nv_bfloat16*>(z.p) + g * 8;
+#pragma unroll 2
+  for (int p = blockIdx.x * chunk + pl; p < p_end; p += lanes) {
+    const int py = p / wp, px = p - py * wp;
+    const int sy = reflect_idx(py - z.halo, z.h), sx = reflect_idx(px - z.halo, z.w);
+    float f[8], o[8];
+    load8(yb + y.at(i, sy, sx), f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] += rr[k];
+    for (int k = 0; k < 8; ++k) o[k] = act_fwd((f[k] - mean[k]) * rstd[k], act);
+    if (has_res) {
+      float rr[8];
+      load8(rb + res.at(i, sy, sx), rr);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] += rr[k];
+    }
+    store8(zb + z.at_padded(i, py, px), o);
   }
-  store8(static_cast<__nv_bfloat16*>(z.p) + z.at_padded(i, py, px) + g * 8, o);
 }
 
 // ------------------------------------------------------------------------------------------------ IN backward
 // Folded upstream gradient at interior pixel (y, x): sum of dz over all padded positions that mirror onto it.
 __device__ __forceinline__ void folded_grad(const View& dz, int i, int y, int x, int g, float (&acc)[8]) {
   const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(dz.p);
-  if (dz.halo == 0) {
+  const int h = dz.halo;
+  // interior fast path: no mirrored position lands here
+  if (h == 0 || (y > h && y < dz.h - 1 - h && x > h && x < dz.w - 1 - h)) {
     load8(base + dz.at(i, y, x) + g * 8, acc);
     return;
   }
-  const int h = dz.halo;
   int rows[3], cols[3], nr = 0, nc = 0;
   rows[nr++] = y + h;
   if (y >= 1 && y <= h) rows[nr++] = h - y;
@@ -193,9 +221,12 @@ __device__ __forceinline__ void folded_grad(const View& dz, int i, int y, int x,
     }
 }
 
-// pass 1: g = fold(dz) (+ dz2); optionally store g to dres; reduce {sum g', sum g'*zhat} per (image, channel)
-__global__ void in_bwd_reduce_kernel(View dz, View dz2, int has_dz2, View y, const float* __restrict__ stats, int act,
-                                     View dres, int has_dres, float* __restrict__ partial) {
+// pass 1: g = fold(dz) (+ dz2); optionally store g to dres; reduce {sum g', sum g'*zhat} per (image, channel);
+// the last CTA of the image turns the partials into red = {mean(g'), mean(g' zhat)}
+__global__ void __launch_bounds__(kStatThreads, 3)
+in_bwd_reduce_kernel(View dz, View dz2, int has_dz2, View y, const float* __restrict__ stats, int act, View dres,
+                     int has_dres, float* __restrict__ partial, float* __restrict__ red_out,
+                     int* __restrict__ counters, float inv_hw) {
   const int G = y.c / 8;
   const int lanes = kStatThreads / G;
   const int g = threadIdx.x % G, pl = threadIdx.x / G;
@@ -206,16 +237,79 @@ __global__ void in_bwd_reduce_kernel(View dz, View dz2, int has_dz2, View y, con
   float s[8], ss[8], mean[8], rstd[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s[k] = ss[k] = 0.f;
-  if (pl < lanes) {
+  {
     const float4* st = reinterpret_cast<const float4*>(stats + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float4 ms = __ldg(st + k);
       mean[2 * k] = ms.x; rstd[2 * k] = ms.y; mean[2 * k + 1] = ms.z; rstd[2 * k + 1] = ms.w;
     }
-    for (int p = p_begin + pl; p < p_end; p += lanes) {
-      const int py = p / y.w, px = p - py * y.w;
-      float gr[8], yy[8];
+  }
+  for (int p = p_begin + pl; p < p_end; p += lanes) {
+    const int py = p / y.w, px = p - py * y.w;
+    float gr[8], yy[8];
+    folded_grad(dz, i, py, px, g, gr);
+    load8(static_cast<const __nv_bfloat16*>(y.p) + y.at(i, py, px) + g * 8, yy);
+    if (has_dz2) {
+      float e[8];
+      load8(static_cast<const __nv_bfloat16*>(dz2.p) + dz2.at(i, py, px) + g * 8, e);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) gr[k] += e[k];
+    }
+    if (has_dres) store8(static_cast<__nv_bfloat16*>(dres.p) + dres.at(i, py, px) + g * 8, gr);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float zh = (yy[k] - mean[k]) * rstd[k];
+      const float gp = gr[k] * act_grad(zh, act);
+      s[k] += gp;
+      ss[k] += gp * zh;
+    }
+  }
+  block_reduce_to_partial(s, ss, G, lanes, partial, i, split, splits, y.c);
+  if (!last_cta_of_image(&counters[i], splits)) return;
+  for (int ch = threadIdx.x; ch < y.c; ch += kStatThreads) {
+    float a = 0.f, b = 0.f;
+    for (int sp = 0; sp < splits; ++sp) {
+      const float* q = partial + ((static_cast<int64_t>(i) * splits + sp) * y.c + ch) * 2;
+      a += q[0];
+      b += q[1];
+    }
+    red_out[(static_cast<int64_t>(i) * y.c + ch) * 2] = a * inv_hw;
+    red_out[(static_cast<int64_t>(i) * y.c + ch) * 2 + 1] = b * inv_hw;
+  }
+  if (threadIdx.x == 0) counters[i] = 0;
+}
+
+// pass 2: dy = rstd * (g' - mean(g') - zhat * mean(g' zhat)); g read back from dres when available.
+// Same thread layout as in_apply_kernel (per-thread channel group, statistics in registers).
+__global__ void __launch_bounds__(256, 3)
+in_bwd_apply_kernel(View dz, View dz2, int has_dz2, View gsrc, int has_gsrc, View y, const float* __restrict__ stats,
+                    const float* __restrict__ red, int act, View dy) {
+  const int G = y.c / 8;
+  const int lanes = 256 / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  const int i = blockIdx.y;
+  const int npix = y.h * y.w;
+  const int chunk = lanes * kApplyPixelsPerLane;
+  const int p_end = min(npix, (static_cast<int>(blockIdx.x) + 1) * chunk);
+  float mean[8], rstd[8], m1[8], m2[8];
+  {
+    const float4* st = reinterpret_cast<const float4*>(stats + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
+    const float4* rd = reinterpret_cast<const float4*>(red + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 ms = __ldg(st + k);
+      const float4 mr = __ldg(rd + k);
+      mean[2 * k] = ms.x; rstd[2 * k] = ms.y; mean[2 * k + 1] = ms.z; rstd[2 * k + 1] = ms.w;
+      m1[2 * k] = mr.x; m2[2 * k] = mr.y; m1[2 * k + 1] = mr.z; m2[2 * k + 1] = mr.w;
+    }
+  }
+  for (int p = blockIdx.x * chunk + pl; p < p_end; p += lanes) {
+    const int py = p / y.w, px = p - py * y.w;
+    float gr[8], yy[8], o[8];
+    if (has_gsrc) {
+      load8(static_cast<const __nv_bfloat16*>(gsrc.p) + gsrc.at(i, py, px) + g * 8, gr);
+    } else {
       folded_grad(dz, i, py, px, g, gr);
       if (has_dz2) {
         float e[8];
@@ -223,77 +317,16 @@ __global__ void in_bwd_reduce_kernel(View dz, View dz2, int has_dz2, View y, con
 #pragma unroll
         for (int k = 0; k < 8; ++k) gr[k] += e[k];
       }
-      if (has_dres) store8(static_cast<__nv_bfloat16*>(dres.p) + dres.at(i, py, px) + g * 8, gr);
-      load8(static_cast<const __nv_bfloat16*>(y.p) + y.at(i, py, px) + g * 8, yy);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float zh = (yy[k] - mean[k]) * rstd[k];
-        const float gp = gr[k] * act_grad(zh, act);
-        s[k] += gp;
-        ss[k] += gp * zh;
-      }
     }
-  }
-  __shared__ float red[kStatThreads][17];
+    load8(static_cast<const __nv_bfloat16*>(y.p) + y.at(i, py, px) + g * 8, yy);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    red[threadIdx.x][k] = s[k];
-    red[threadIdx.x][8 + k] = ss[k];
-  }
-  __syncthreads();
-  for (int o = threadIdx.x; o < G * 16; o += kStatThreads) {
-    const int gg = o / 16, comp = o % 16;
-    float acc = 0.f;
-    for (int l = 0; l < lanes; ++l) acc += red[l * G + gg][comp];
-    const int ch = gg * 8 + (comp & 7);
-    partial[((static_cast<int64_t>(i) * splits + split) * y.c + ch) * 2 + (comp >> 3)] = acc;
-  }
-}
-
-// pass 2: dy = rstd * (g' - mean(g') - zhat * mean(g' zhat)); g read back from dres when available
-__global__ void in_bwd_apply_kernel(View dz, View dz2, int has_dz2, View gsrc, int has_gsrc, View y,
-                                    const float* __restrict__ stats, const float* __restrict__ red, int act, View dy) {
-  const int G = y.c / 8;
-  const int64_t total = static_cast<int64_t>(y.n) * y.h * y.w * G;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int g = static_cast<int>(idx % G);
-  int64_t r = idx / G;
-  const int px = static_cast<int>(r % y.w);
-  r /= y.w;
-  const int py = static_cast<int>(r % y.h);
-  const int i = static_cast<int>(r / y.h);
-  float gr[8], yy[8], o[8];
-  if (has_gsrc) {
-    load8(static_cast<const __nv_bfloat16*>(gsrc.p) + gsrc.at(i, py, px) + g * 8, gr);
-  } else {
-    folded_grad(dz, i, py, px, g, gr);
-    if (has_dz2) {
-      float e[8];
-      load8(static_cast<const __nv_bfloat16*>(dz2.p) + dz2.at(i, py, px) + g * 8, e);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) gr[k] += e[k];
+    for (int k = 0; k < 8; ++k) {
+      const float zh = (yy[k] - mean[k]) * rstd[k];
+      const float gp = gr[k] * act_grad(zh, act);
+      o[k] = rstd[k] * (gp - m1[k] - zh * m2[k]);
     }
+    store8(static_cast<__nv_bfloat16*>(dy.p) + dy.at(i, py, px) + g * 8, o);
   }
-  load8(static_cast<const __nv_bfloat16*>(y.p) + y.at(i, py, px) + g * 8, yy);
-  const float4* st = reinterpret_cast<const float4*>(stats + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
-  const float4* rd = reinterpret_cast<const float4*>(red + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const float4 ms = __ldg(st + k);
-    const float4 mr = __ldg(rd + k);
-    {
-      const float zh = (yy[2 * k] - ms.x) * ms.y;
-      const float gp = gr[2 * k] * act_grad(zh, act);
-      o[2 * k] = ms.y * (gp - mr.x - zh * mr.y);
-    }
-    {
-      const float zh = (yy[2 * k + 1] - ms.z) * ms.w;
-      const float gp = gr[2 * k + 1] * act_grad(zh, act);
-      o[2 * k + 1] = ms.w * (gp - mr.z - zh * mr.w);
-    }
-  }
-  store8(static_cast<__nv_bfloat16*>(dy.p) + dy.at(i, py, px) + g * 8, o);
 }
 
 // dx = fold(dz) * act'(z), z = saved activation output (sign(z) == sign(pre-activation))
@@ -340,38 +373,48 @@ __global__ void fold_add_kernel(View a, View b, int has_b, View c) {
 }
 
 // ------------------------------------------------------------------------------------------------ bias grad
-// db[k] = sum over pixels of dy[.., k]; grid (c/8 groups), block 256: fixed-order tree over pixels
-__global__ void bias_grad_kernel(View dy, float* __restrict__ db, int k_valid) {
-  const int g = blockIdx.x;
+// db[k] = sum over pixels of dy[.., k]. Stage 1: grid of pixel ranges, thread = (channel group, pixel lane), fixed-order
+// block reduction -> partial[block][c]. Stage 2: one thread per channel sums the partials in block order.
+constexpr int kBiasBlocks = 592;
+__global__ void bias_grad_partial_kernel(View dy, float* __restrict__ partial) {
+  const int G = dy.c / 8;
+  const int lanes = kStatThreads / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
   const int64_t npix = static_cast<int64_t>(dy.n) * dy.h * dy.w;
+  const int64_t p_begin = npix * blockIdx.x / gridDim.x, p_end = npix * (blockIdx.x + 1) / gridDim.x;
   float s[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s[k] = 0.f;
-  for (int64_t p = threadIdx.x; p < npix; p += blockDim.x) {
-    const int px = static_cast<int>(p % dy.w);
-    const int64_t r = p / dy.w;
-    const int py = static_cast<int>(r % dy.h);
-    const int i = static_cast<int>(r / dy.h);
-    float f[8];
-    load8(static_cast<const __nv_bfloat16*>(dy.p) + dy.at(i, py, px) + g * 8, f);
+  if (pl < lanes) {
+    for (int64_t p = p_begin + pl; p < p_end; p += lanes) {
+      const int px = static_cast<int>(p % dy.w);
+      const int64_t r = p / dy.w;
+      const int py = static_cast<int>(r % dy.h);
+      const int i = static_cast<int>(r / dy.h);
+      float f[8];
+      load8(static_cast<const __nv_bfloat16*>(dy.p) + dy.at(i, py, px) + g * 8, f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s[k] += f[k];
+      for (int k = 0; k < 8; ++k) s[k] += f[k];
+    }
   }
-  __shared__ float red[256][9];
+  __shared__ float red[kStatThreads][9];
 #pragma unroll
   for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = s[k];
   __syncthreads();
-  for (int off = 128; off > 0; off >>= 1) {
-    if (static_cast<int>(threadIdx.x) < off) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) red[threadIdx.x][k] += red[threadIdx.x + off][k];
-    }
-    __syncthreads();
+  for (int o = threadIdx.x; o < G * 8; o += kStatThreads) {
+    const int gg = o / 8, comp = o % 8;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[l * G + gg][comp];
+    partial[static_cast<int64_t>(blockIdx.x) * dy.c + gg * 8 + comp] = acc;
   }
-  if (threadIdx.x < 8) {
-    const int ch = g * 8 + threadIdx.x;
-    if (ch < k_valid) db[ch] = red[0][threadIdx.x];
-  }
+}
+__global__ void bias_grad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ db, int c, int k_valid,
+                                          int nblocks) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= k_valid) return;
+  float acc = 0.f;
+  for (int b = 0; b < nblocks; ++b) acc += partial[static_cast<int64_t>(b) * c + ch];
+  db[ch] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------ blend
@@ -705,11 +748,12 @@ __global__ void confusion_kernel(const float* __restrict__ pred, const float* __
 static unsigned grid_for(int64_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
 
 static int stat_splits(const fpg_act* y, int sms) {
-  // enough CTAs for ~2 waves, at most 64 splits per image, at least ~64 pixels per lane pass
-  int splits = (2 * sms + y->n - 1) / y->n;
+  // ~8 resident CTAs per SM (the loops are latency-bound: parallelism hides it), at most 64 splits per image
+  // (scratch bound), at least 64 pixels per split
+  int splits = (8 * sms + y->n - 1) / y->n;
   if (splits > 64) splits = 64;
   const int hw = y->h * y->w;
-  while (splits > 1 && hw / splits < 256) splits /= 2;
+  while (splits > 1 && hw / splits < 64) splits /= 2;
   if (splits < 1) splits = 1;
   return splits;
 }
@@ -724,15 +768,14 @@ extern "C" {
 
 int64_t fpg_instnorm_scratch_floats(const fpg_act* y) { return static_cast<int64_t>(y->n) * 64 * y->c * 2 + static_cast<int64_t>(y->n) * y->c * 2; }
 
-int fpg_instnorm_stats(const fpg_act* y, float eps, float* stats, float* scratch, void* stream) {
-  FPG_REQUIRE(y && stats && scratch, "null argument");
+int fpg_instnorm_stats(const fpg_act* y, float eps, float* stats, float* scratch, int32_t* counters, void* stream) {
+  FPG_REQUIRE(y && stats && scratch && counters, "null argument");
   FPG_REQUIRE(y->c % 8 == 0 && kStatThreads % (y->c / 8) == 0, "instnorm channels %d", y->c);
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
   const int splits = stat_splits(y, sms);
-  in_stats_partial_kernel<<<dim3(splits, y->n), kStatThreads, 0, FPG_ST(stream)>>>(view_of(y), scratch);
-  in_stats_finalize_kernel<<<grid_for(static_cast<int64_t>(y->n) * y->c, 256), 256, 0, FPG_ST(stream)>>>(
-      scratch, stats, y->n, y->c, splits, 1.f / static_cast<float>(y->h * y->w), eps);
+  in_stats_kernel<<<dim3(splits, y->n), kStatThreads, 0, FPG_ST(stream)>>>(
+      view_of(y), scratch, stats, counters, 1.f / static_cast<float>(y->h * y->w), eps);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -743,16 +786,18 @@ int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_
   FPG_REQUIRE(y->n == z->n && y->h == z->h && y->w == z->w && y->c == z->c && y->c % 8 == 0, "geometry mismatch");
   FPG_REQUIRE(z->halo < z->h && z->halo < z->w, "halo too large");
   View rv = residual ? view_of(residual) : view_of(y);
-  const int64_t total = static_cast<int64_t>(z->n) * (z->h + 2 * z->halo) * (z->w + 2 * z->halo) * (y->c / 8);
-  in_apply_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(y), stats, act, rv, residual != nullptr,
-                                                                    view_of(z));
+  FPG_REQUIRE(256 % (y->c / 8) == 0, "instnorm channels %d", y->c);
+  const int64_t npix = static_cast<int64_t>(z->h + 2 * z->halo) * (z->w + 2 * z->halo);
+  const int chunk = (256 / (y->c / 8)) * kApplyPixelsPerLane;
+  in_apply_kernel<<<dim3(grid_for(npix, chunk), y->n), 256, 0, FPG_ST(stream)>>>(
+      view_of(y), stats, act, rv, residual != nullptr, view_of(z));
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int fpg_instnorm_bwd(const fpg_act* dz, const fpg_act* dz2, const fpg_act* y, const float* stats, int act,
-                     const fpg_act* dy, const fpg_act* dres, float* scratch, void* stream) {
-  FPG_REQUIRE(dz && y && stats && dy && scratch, "null argument");
+                     const fpg_act* dy, const fpg_act* dres, float* scratch, int32_t* counters, void* stream) {
+  FPG_REQUIRE(dz && y && stats && dy && scratch && counters, "null argument");
   FPG_REQUIRE(y->c % 8 == 0 && kStatThreads % (y->c / 8) == 0, "instnorm channels %d", y->c);
   FPG_REQUIRE(dz->h == y->h && dz->w == y->w && dz->c == y->c && dy->h == y->h && dy->c == y->c, "geometry mismatch");
   const int sms = sm_count_cached();
@@ -762,13 +807,11 @@ int fpg_instnorm_bwd(const fpg_act* dz, const fpg_act* dz2, const fpg_act* y, co
   View vr = dres ? view_of(dres) : view_of(dz);
   float* red = scratch + static_cast<int64_t>(y->n) * 64 * y->c * 2;
   in_bwd_reduce_kernel<<<dim3(splits, y->n), kStatThreads, 0, FPG_ST(stream)>>>(
-      view_of(dz), v2, dz2 != nullptr, view_of(y), stats, act, vr, dres != nullptr, scratch);
-  in_bwd_finalize_kernel<<<grid_for(static_cast<int64_t>(y->n) * y->c, 256), 256, 0, FPG_ST(stream)>>>(
-      scratch, red, y->n, y->c, splits, 1.f / static_cast<float>(y->h * y->w));
-  const int64_t total = static_cast<int64_t>(y->n) * y->h * y->w * (y->c / 8);
-  in_bwd_apply_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(dz), v2, dz2 != nullptr, vr,
-                                                                        dres != nullptr, view_of(y), stats, red, act,
-                                                                        view_of(dy));
+      view_of(dz), v2, dz2 != nullptr, view_of(y), stats, act, vr, dres != nullptr, scratch, red, counters,
+      1.f / static_cast<float>(y->h * y->w));
+  const int chunk = (256 / (y->c / 8)) * kApplyPixelsPerLane;
+  in_bwd_apply_kernel<<<dim3(grid_for(static_cast<int64_t>(y->h) * y->w, chunk), y->n), 256, 0, FPG_ST(stream)>>>(
+      view_of(dz), v2, dz2 != nullptr, vr, dres != nullptr, view_of(y), stats, red, act, view_of(dy));
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -790,9 +833,13 @@ int fpg_halo_fold(const fpg_act* a, const fpg_act* b, const fpg_act* c, void* st
   return 0;
 }
 
-int fpg_bias_grad(const fpg_act* dy, float* db, int32_t k_valid, void* stream) {
-  FPG_REQUIRE(dy && db && dy->c % 8 == 0, "bad argument");
-  bias_grad_kernel<<<dy->c / 8, 256, 0, FPG_ST(stream)>>>(view_of(dy), db, k_valid);
+int fpg_bias_grad(const fpg_act* dy, float* db, int32_t k_valid, float* scratch, void* stream) {
+  FPG_REQUIRE(dy && db && scratch && dy->c % 8 == 0 && kStatThreads % (dy->c / 8) == 0, "bad argument");
+  const int64_t npix = static_cast<int64_t>(dy->n) * dy->h * dy->w;
+  int blocks = kBiasBlocks;
+  if (npix / blocks < 64) blocks = static_cast<int>(npix / 64 > 0 ? npix / 64 : 1);
+  bias_grad_partial_kernel<<<blocks, kStatThreads, 0, FPG_ST(stream)>>>(view_of(dy), scratch);
+  bias_grad_finalize_kernel<<<(k_valid + 127) / 128, 128, 0, FPG_ST(stream)>>>(scratch, db, dy->c, k_valid, blocks);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -42,7 +42,7 @@ class WgradDesc(C.Structure):
                 ("x_taps_mode", C.c_int32), ("y_taps_mode", C.c_int32), ("x_ntaps", C.c_int32),
                 ("y_ntaps", C.c_int32), ("n_img", C.c_int32), ("kt_y", C.c_int32), ("kt_x", C.c_int32),
                 ("tile_h", C.c_int32), ("tile_w", C.c_int32), ("splits", C.c_int32), ("stages", C.c_int32),
-                ("x_is_dy", C.c_int32), ("taps_r", C.c_int32), ("taps_s", C.c_int32), ("ws", C.c_void_p),
+                ("x_is_dy", C.c_int32), ("tap_on_x", C.c_int32), ("taps_r", C.c_int32), ("taps_s", C.c_int32), ("ws", C.c_void_p),
                 ("x_taps", Tap * FPG_MAX_TAPS), ("y_taps", Tap * FPG_MAX_TAPS)]
 
 
@@ -80,11 +80,11 @@ SIGNATURES = {
     "fpg_dgrad_class_info": (C.c_int, [_P(ConvGeom), C.c_int, _P(_i32), _P(_i32), _P(_i64), _P(_i32)]),
     "fpg_packed_weight_bytes": (_i64, [_P(ConvGeom)]),
     "fpg_packed_weight_dgrad_bytes": (_i64, [_P(ConvGeom)]),
-    "fpg_bias_grad": (C.c_int, [_P(Act), _vp, _i32, _vp]),
+    "fpg_bias_grad": (C.c_int, [_P(Act), _vp, _i32, _vp, _vp]),
     "fpg_instnorm_scratch_floats": (_i64, [_P(Act)]),
-    "fpg_instnorm_stats": (C.c_int, [_P(Act), _f32, _vp, _vp, _vp]),
+    "fpg_instnorm_stats": (C.c_int, [_P(Act), _f32, _vp, _vp, _vp, _vp]),
     "fpg_instnorm_apply": (C.c_int, [_P(Act), _vp, C.c_int, _P(Act), _P(Act), _vp]),
-    "fpg_instnorm_bwd": (C.c_int, [_P(Act), _P(Act), _P(Act), _vp, C.c_int, _P(Act), _P(Act), _vp, _vp]),
+    "fpg_instnorm_bwd": (C.c_int, [_P(Act), _P(Act), _P(Act), _vp, C.c_int, _P(Act), _P(Act), _vp, _vp, _vp]),
     "fpg_act_bwd": (C.c_int, [_P(Act), _P(Act), C.c_int, _P(Act), _vp]),
     "fpg_halo_fold": (C.c_int, [_P(Act), _P(Act), _P(Act), _vp]),
     "fpg_blend_fwd": (C.c_int, [_P(Act), _P(Act), _P(Act), _P(Act), _i32, _vp, _vp, _vp]),

@@ -179,7 +179,8 @@ def conv_wgrad(x, dy, spec, dw):
 
 
 def bias_grad(dy, db, k_valid):
-    _run("bias_grad", 1, "fpg_bias_grad", dy.ref(), _ptr(db), k_valid, _stream())
+    ws = workspace(592 * dy.c * 4, db.device)
+    _run("bias_grad", 2, "fpg_bias_grad", dy.ref(), _ptr(db), k_valid, _ptr(ws), _stream())
 
 
 def _scratch_for(y):
@@ -187,8 +188,20 @@ def _scratch_for(y):
     return workspace(n * 4, y.t.device)
 
 
+_counter_cache = {}
+
+
+def _counters(device):
+    """zero-initialised int32 ticket counters (kernels leave them zero)"""
+    key = str(device)
+    if key not in _counter_cache:
+        _counter_cache[key] = torch.zeros(4096, dtype=torch.int32, device=device)
+    return _counter_cache[key]
+
+
 def instnorm_stats(y, stats, eps=1e-5):
-    _run("instnorm_stats", 2, "fpg_instnorm_stats", y.ref(), eps, _ptr(stats), _ptr(_scratch_for(y)), _stream())
+    _run("instnorm_stats", 1, "fpg_instnorm_stats", y.ref(), eps, _ptr(stats), _ptr(_scratch_for(y)),
+         _ptr(_counters(y.t.device)), _stream())
 
 
 def instnorm_apply(y, stats, act, z, residual=None):
@@ -197,8 +210,9 @@ def instnorm_apply(y, stats, act, z, residual=None):
 
 
 def instnorm_bwd(dz, y, stats, act, dy, dz2=None, dres=None):
-    _run("instnorm_bwd", 3, "fpg_instnorm_bwd", dz.ref(), dz2.ref() if dz2 is not None else None, y.ref(), _ptr(stats), act, dy.ref(),
-           dres.ref() if dres is not None else None, _ptr(_scratch_for(y)), _stream())
+    _run("instnorm_bwd", 2, "fpg_instnorm_bwd", dz.ref(), dz2.ref() if dz2 is not None else None, y.ref(), _ptr(stats),
+         act, dy.ref(), dres.ref() if dres is not None else None, _ptr(_scratch_for(y)), _ptr(_counters(y.t.device)),
+         _stream())
 
 
 def act_bwd(dz, z, act, dx):

@@ -102,6 +102,7 @@ typedef struct {
   int32_t n_img, kt_y, kt_x, tile_h, tile_w;
   int32_t splits, stages;
   int32_t x_is_dy; /* 1: X operand is the output gradient (rows of D are output channels); 0: X is the input */
+  int32_t tap_on_x; /* 1: the filter taps are enumerated by the X operand, 0: by the Y operand */
   int32_t taps_r, taps_s; /* filter size, for mapping tap index -> (r, s) when reducing */
   float* ws;
   fpg_tap x_taps[FPG_MAX_TAPS];
@@ -184,8 +185,8 @@ int fpg_dgrad_class_info(const fpg_conv_geom* g, int cls, int32_t* src_tap /* [F
 int64_t fpg_packed_weight_bytes(const fpg_conv_geom* g);
 int64_t fpg_packed_weight_dgrad_bytes(const fpg_conv_geom* g);
 
-/* db[k] = sum over pixels of dy[.., k]  (bias gradient), k < k_valid */
-int fpg_bias_grad(const fpg_act* dy, float* db, int32_t k_valid, void* stream);
+/* db[k] = sum over pixels of dy[.., k]  (bias gradient), k < k_valid; scratch: >= 592 * dy->c floats */
+int fpg_bias_grad(const fpg_act* dy, float* db, int32_t k_valid, float* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * InstanceNorm + activation (+ residual, + reflect halo) -- nn.InstanceNorm2d(eps=1e-5, affine=False) followed by
@@ -195,8 +196,9 @@ int fpg_bias_grad(const fpg_act* dy, float* db, int32_t k_valid, void* stream);
 /* scratch floats needed by fpg_instnorm_stats / fpg_instnorm_bwd for activation y */
 int64_t fpg_instnorm_scratch_floats(const fpg_act* y);
 /* stats[(n*C + c)*2 + {0,1}] = {mean, rstd} over the h*w plane of y (biased variance, eps). Deterministic
- * two-stage reduction through `scratch`. */
-int fpg_instnorm_stats(const fpg_act* y, float eps, float* stats, float* scratch, void* stream);
+ * two-stage reduction through `scratch`; `counters`: int32[n] that is zero on entry and left zero (ticket counters
+ * of the last-CTA-finalizes scheme; shared by all instnorm calls of one stream). */
+int fpg_instnorm_stats(const fpg_act* y, float eps, float* stats, float* scratch, int32_t* counters, void* stream);
 /* z = act((y - mean) * rstd) [+ residual]; written to z's interior and, if z->halo > 0, mirrored into its halo.
  * residual may be NULL; it is read at interior coordinates (its own halo is skipped). */
 int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_act* residual, const fpg_act* z,
@@ -206,7 +208,7 @@ int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_
  * halo ignored) is a second gradient branch (residual skip). Writes dy; if dres != NULL also writes g there
  * (gradient flowing on to the residual input). */
 int fpg_instnorm_bwd(const fpg_act* dz, const fpg_act* dz2, const fpg_act* y, const float* stats, int act,
-                     const fpg_act* dy, const fpg_act* dres, float* scratch, void* stream);
+                     const fpg_act* dy, const fpg_act* dres, float* scratch, int32_t* counters, void* stream);
 /* dx = fold(dz) * act'(z) for an activation without normalisation (PatchGAN model.0 LeakyReLU): z is the saved
  * activation output */
 int fpg_act_bwd(const fpg_act* dz, const fpg_act* z, int act, const fpg_act* dx, void* stream);

@@ -129,10 +129,8 @@ def run_wgrad(desc, xbuf, ybuf, dw, stride_k, stride_c, k_valid, c_valid):
                 xtap, xch = xmeta[m]
                 for nn in range(N):
                     ytap, ych = ymeta[nn]
-                    if desc.x_is_dy:
-                        k, c, tap = xch, ych, ytap
-                    else:
-                        k, c, tap = ych, xch, xtap
+                    k, c = (xch, ych) if desc.x_is_dy else (ych, xch)
+                    tap = xtap if desc.tap_on_x else ytap
                     if tap < 0 or k >= k_valid or c >= c_valid:
                         continue
                     dw[k * stride_k + c * stride_c + tap] = acc[m, nn]
