@@ -38,26 +38,47 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
-
-    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks / throttle reasons (NVML, every 20 ms) while the timed region runs."""
 
     def __init__(self, index):
         self.index, self.samples, self.stop = index, [], threading.Event()
         self.thread = threading.Thread(target=self._run, daemon=True)
+        self.max_mhz = None
 
     def _run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                    "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                    "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            while not self.stop.is_set():
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.samples.append((mhz, [n for n, b in bits.items() if mask & b]))
+                self.stop.wait(0.02)
+        except Exception:
+            self._run_smi()
+
+    def _run_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout
                 f = [v.strip() for v in out.strip().split(",")]
-                if len(f) >= 6:
-                    self.samples.append(f)
+                if len(f) >= 6 and f[0].isdigit():
+                    self.max_mhz = int(f[1])
+                    self.samples.append((int(f[0]), [n for i, n in enumerate(names)
+                                                     if f[2 + i].lower().startswith("active")]))
             except Exception:
                 pass
-            self.stop.wait(0.2)
+            self.stop.wait(0.1)
 
     def __enter__(self):
         self.thread.start()
@@ -69,12 +90,11 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]),
-                "reasons": reasons, "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = sorted({r for s in self.samples for r in s[1]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.samples)}
 
 
 def cpu_reference_tiles_per_s(steps, warmup, batch=1):
@@ -127,6 +147,7 @@ def run_native(args):
         raise SystemExit("bench.py: no CUDA device (this implementation has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("FPG_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B, steps, warmup = args.batch, args.steps, args.warmup
@@ -240,7 +261,7 @@ def run_native(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])

@@ -1,0 +1,83 @@
+"""World-size-2 `gloo` tests (CPU) of the host-side data-parallel logic: batch sharding of the synthetic loader,
+parameter flattening and the bucketed gradient all-reduce driven by grad-ready callbacks (fpgan/trainer.py).
+The kernels themselves need a GPU; everything tested here is plain torch.distributed plumbing."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from torch import nn
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+class _TinyNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = nn.Conv2d(4, 8, 3)
+        self.b = nn.Conv2d(8, 8, 3)
+        self.c = nn.ConvTranspose2d(8, 4, 3)
+
+
+def _worker(rank, world, port, results):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from fpgan.trainer import FlatParams, _BucketReducer
+        from models.data import SyntheticLoader
+        torch.manual_seed(0)
+        net = _TinyNet()
+        ref_state = {k: v.clone() for k, v in net.state_dict().items()}
+        fp = FlatParams(net)
+        # flattening keeps values, names and state_dict semantics
+        for k, v in net.state_dict().items():
+            assert torch.equal(v, ref_state[k])
+        assert fp.flat.numel() == sum(p.numel() for p in net.parameters())
+        fp.flat.mul_(2.0)  # parameters are views of the flat buffer
+        assert torch.equal(net.a.weight, ref_state["a.weight"] * 2)
+
+        red = _BucketReducer(fp, bucket_bytes=1024)  # tiny buckets -> several of them
+        assert len(red.bounds) > 1 and red.bounds[0][0] == 0 and red.bounds[-1][1] == fp.flat.numel()
+        for (s0, e0), (s1, e1) in zip(red.bounds[:-1], red.bounds[1:]):
+            assert e0 == s1
+        fp.grads.flat.copy_(torch.arange(fp.flat.numel(), dtype=torch.float32) * (rank + 1))
+        red.start()
+        for name, _ in reversed(fp.named):  # backward order; "c.bias" style names are signalled like the executor
+            red.ready(name)
+        red.finish()
+        want = torch.arange(fp.flat.numel(), dtype=torch.float32) * sum(r + 1 for r in range(world))
+        assert torch.equal(fp.grads.flat, want), "bucketed all-reduce must equal the sum over ranks"
+        # a parameter whose gradient is never signalled (bias before an InstanceNorm) is still reduced by finish()
+        fp.grads.flat.fill_(float(rank + 1))
+        red.start()
+        for name, _ in fp.named:
+            if not name.endswith(".bias"):
+                red.ready(name)
+        red.finish()
+        assert torch.all(fp.grads.flat == sum(r + 1 for r in range(world)))
+
+        # loader sharding: the ranks' shards tile the single-process global batch
+        full = next(iter(SyntheticLoader(steps=1, batch=4, channels=9, size=8, pin=False)))
+        mine = next(iter(SyntheticLoader(steps=1, batch=2, channels=9, size=8, rank=rank, world_size=world, pin=False)))
+        assert torch.equal(mine[0], full[0][2 * rank:2 * rank + 2]) and torch.equal(mine[1], full[1][2 * rank:2 * rank + 2])
+        results[rank] = "ok"
+    except Exception as e:  # noqa: BLE001
+        results[rank] = f"{type(e).__name__}: {e}"
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_and_sharding_world2():
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)
+    assert dict(results) == {0: "ok", 1: "ok"}, dict(results)
