@@ -672,7 +672,7 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int c_src, View 
 }
 
 // bf16 NHWC (interior, channels [c0, c0+c_dst)) -> fp32 NCHW; one thread per pixel
-__global__ void unpack_nchw_kernel(View src, int c0, float* __restrict__ dst, int c_dst, int accumulate) {
+__global__ void unpack_nchw_kernel(View src, int src_fp32, int c0, float* __restrict__ dst, int c_dst, int accumulate) {
   const int64_t total = static_cast<int64_t>(src.n) * src.h * src.w;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -680,12 +680,42 @@ __global__ void unpack_nchw_kernel(View src, int c0, float* __restrict__ dst, in
   const int64_t r = idx / src.w;
   const int py = static_cast<int>(r % src.h);
   const int i = static_cast<int>(r / src.h);
-  const __nv_bfloat16* sp = static_cast<const __nv_bfloat16*>(src.p) + src.at(i, py, px) + c0;
+  const int64_t soff = src.at(i, py, px) + c0;
   const int64_t hw = static_cast<int64_t>(src.h) * src.w;
   float* dp = dst + static_cast<int64_t>(i) * c_dst * hw + static_cast<int64_t>(py) * src.w + px;
   for (int ch = 0; ch < c_dst; ++ch) {
-    const float v = __bfloat162float(sp[ch]);
+    const float v = src_fp32 ? static_cast<const float*>(src.p)[soff + ch]
+                             : __bfloat162float(static_cast<const __nv_bfloat16*>(src.p)[soff + ch]);
     dp[ch * hw] = accumulate ? dp[ch * hw] + v : v;
+  }
+}
+
+// dpre[n,y,x,c] = dout[n,c,y,x] * (1 - out[n,y,x,c]^2) for c < c_valid (out = tanh output, fp32 NHWC), 0 elsewhere;
+// one thread per pixel, 16-channel bf16 destination (CycleGAN generator head, model_architectures.py:115-116)
+__global__ void tanh_bwd_pack_kernel(const float* __restrict__ dout, View out, int c_valid, View dpre) {
+  const int64_t total = static_cast<int64_t>(out.n) * out.h * out.w;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % out.w);
+  const int64_t r = idx / out.w;
+  const int py = static_cast<int>(r % out.h);
+  const int i = static_cast<int>(r / out.h);
+  const int64_t hw = static_cast<int64_t>(out.h) * out.w;
+  const float* op = static_cast<const float*>(out.p) + out.at(i, py, px);
+  const float* gp = dout + static_cast<int64_t>(i) * c_valid * hw + static_cast<int64_t>(py) * out.w + px;
+  __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(dpre.p) + dpre.at(i, py, px);
+  for (int c8 = 0; c8 < dpre.c; c8 += 8) {
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = c8 + k;
+      f[k] = 0.f;
+      if (ch < c_valid) {
+        const float o = op[ch];
+        f[k] = gp[ch * hw] * (1.f - o * o);
+      }
+    }
+    store8(dp + c8, f);
   }
 }
 
@@ -919,7 +949,17 @@ int fpg_pack_nchw(const float* src, int32_t c_src, const fpg_act* dst, int32_t c
 int fpg_unpack_nchw(const fpg_act* src, int32_t c0, float* dst, int32_t c_dst, int accumulate, void* stream) {
   FPG_REQUIRE(src && dst && c0 + c_dst <= src->c_stride, "bad argument");
   const int64_t total = static_cast<int64_t>(src->n) * src->h * src->w;
-  unpack_nchw_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(src), c0, dst, c_dst, accumulate);
+  unpack_nchw_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(src), src->fp32, c0, dst, c_dst,
+                                                                       accumulate);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_tanh_bwd_pack(const float* dout_nchw, const fpg_act* out, int32_t c_valid, const fpg_act* dpre, void* stream) {
+  FPG_REQUIRE(dout_nchw && out && dpre && out->fp32 && dpre->c % 8 == 0 && c_valid <= out->c_stride, "bad argument");
+  const int64_t total = static_cast<int64_t>(out->n) * out->h * out->w;
+  tanh_bwd_pack_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(dout_nchw, view_of(out), c_valid,
+                                                                         view_of(dpre));
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -136,7 +136,98 @@ class _NetBase:
         return dx
 
 
-class AttentionGeneratorNet(_NetBase):
+class _ResnetGeneratorNet(_NetBase):
+    """Shared trunk of the ResNet generators: reflect-pad 7x7 stem, two stride-2 convs, 9 residual blocks
+    (model_architectures.py:342-346 + :412-418, :95-105 + :122-134), and the two-stage transposed-conv decoder."""
+
+    # names of the trunk layers in the module's state_dict: overridden per architecture
+    STEM = ("conv1", "conv2", "conv3")
+
+    def _block_names(self, i):
+        raise NotImplementedError
+
+    def _trunk_forward(self, x, t):
+        B, C, H, W = x.shape
+        c1, c2, c3 = self.STEM
+        t["xin"] = ActBuf(B, H, W, 16, halo=3, zero=False)
+        ops.pack_nchw(x, t["xin"], 0, zero_rest=True)
+        t["y1"] = self._conv(t["xin"], c1)
+        t["s1"], t["z1"] = _norm_act(t["y1"], ACT_RELU, 0)
+        t["y2"] = self._conv(t["z1"], c2)
+        t["s2"], t["z2"] = _norm_act(t["y2"], ACT_RELU, 0)
+        t["y3"] = self._conv(t["z2"], c3)
+        t["s3"], xcur = _norm_act(t["y3"], ACT_RELU, 1)
+        t["x0"] = xcur
+        for i in range(self.n_blocks):
+            n1, n2 = self._block_names(i)
+            ya = self._conv(xcur, n1)
+            sa, za = _norm_act(ya, ACT_RELU, 1)
+            yb = self._conv(za, n2)
+            last = i == self.n_blocks - 1
+            sb, xnext = _norm_act(yb, ACT_NONE, 0 if last else 1, residual=xcur)
+            t[f"b{i}"] = (ya, sa, za, yb, sb)
+            t[f"x{i + 1}"] = xnext
+            xcur = xnext
+        return xcur
+
+    def _decoder_forward(self, x, up1, up2, halo_out):
+        u1 = self._conv(x, up1)
+        s1, v1 = _norm_act(u1, ACT_RELU, 0)
+        u2 = self._conv(v1, up2)
+        s2, v2 = _norm_act(u2, ACT_RELU, halo_out)
+        return (u1, s1, v1, u2, s2, v2)
+
+    def _decoder_backward(self, saved, x_top, dv2, up1, up2, grads):
+        """dv2: gradient w.r.t. the decoder output v2 (incl. halo). Returns the gradient w.r.t. the trunk output."""
+        u1, s1, v1, u2, s2, v2 = saved
+        du2 = ActBuf(u2.n, u2.h, u2.w, u2.c, zero=False)
+        ops.instnorm_bwd(dv2, u2, s2, ACT_RELU, du2)
+        dv1 = self._conv_bwd(up2, v1, du2, grads, True)
+        du1 = ActBuf(u1.n, u1.h, u1.w, u1.c, zero=False)
+        ops.instnorm_bwd(dv1, u1, s1, ACT_RELU, du1)
+        return self._conv_bwd(up1, x_top, du1, grads, True)
+
+    def _trunk_backward(self, t, dz, dz2, grads, need_dx):
+        """dz (+ dz2): gradient w.r.t. the trunk output x_n (interior). Returns d(xin) incl. halo if need_dx."""
+        c1, c2, c3 = self.STEM
+        for i in reversed(range(self.n_blocks)):
+            ya, sa, za, yb, sb = t[f"b{i}"]
+            n1, n2 = self._block_names(i)
+            xi = t[f"x{i}"]
+            gres = None
+            if dz2 is not None or dz.halo:
+                gres = ActBuf(yb.n, yb.h, yb.w, yb.c, zero=False)  # total gradient w.r.t. x_{i+1} (skip branch)
+            dyb = ActBuf(yb.n, yb.h, yb.w, yb.c, zero=False)
+            ops.instnorm_bwd(dz, yb, sb, ACT_NONE, dyb, dz2=dz2, dres=gres)
+            skip = gres if gres is not None else dz
+            dza = self._conv_bwd(n2, za, dyb, grads, True, dx_halo=1)
+            dya = ActBuf(ya.n, ya.h, ya.w, ya.c, zero=False)
+            ops.instnorm_bwd(dza, ya, sa, ACT_RELU, dya)
+            dz = self._conv_bwd(n1, xi, dya, grads, True, dx_halo=1)
+            dz2 = skip
+        dy3 = ActBuf(t["y3"].n, t["y3"].h, t["y3"].w, t["y3"].c, zero=False)
+        ops.instnorm_bwd(dz, t["y3"], t["s3"], ACT_RELU, dy3, dz2=dz2)
+        dz2_ = self._conv_bwd(c3, t["z2"], dy3, grads, True)
+        dy2 = ActBuf(t["y2"].n, t["y2"].h, t["y2"].w, t["y2"].c, zero=False)
+        ops.instnorm_bwd(dz2_, t["y2"], t["s2"], ACT_RELU, dy2)
+        dz1 = self._conv_bwd(c2, t["z1"], dy2, grads, True)
+        dy1 = ActBuf(t["y1"].n, t["y1"].h, t["y1"].w, t["y1"].c, zero=False)
+        ops.instnorm_bwd(dz1, t["y1"], t["s1"], ACT_RELU, dy1)
+        return self._conv_bwd(c1, t["xin"], dy1, grads, need_dx, dx_halo=3)
+
+    def _input_grad_nchw(self, t, dxin, extra_rgb=None):
+        xin = t["xin"]
+        folded = ActBuf(xin.n, xin.h, xin.w, 16, zero=False)
+        ops.halo_fold(dxin, None, folded)
+        c_in = self.layers[self.STEM[0]].c_valid
+        dx = torch.zeros(xin.n, c_in, xin.h, xin.w, dtype=torch.float32, device=xin.t.device)
+        ops.unpack_nchw(folded, dx, 0)
+        if extra_rgb is not None:
+            dx[:, :3] += extra_rgb
+        return dx
+
+
+class AttentionGeneratorNet(_ResnetGeneratorNet):
     """PairedAttentionGenerator / AttentionGANGenerator (model_architectures.py:305-400, 163-258)."""
 
     def __init__(self, module):
@@ -155,37 +246,18 @@ class AttentionGeneratorNet(_NetBase):
         self._add("deconv3_attention", m.deconv3_attention, 1, 1, 0, use_bias=True)
         self.n_blocks = len(m.resnet_blocks)
 
+    def _block_names(self, i):
+        return f"resnet_blocks.{i}.conv1", f"resnet_blocks.{i}.conv2"
+
     def forward(self, x, d_input=None, d_c0=0, want_nchw=True):
         """x: fp32 NCHW [B, C<=16, H, W]. Returns (out_nchw, tape). If d_input (ActBuf [B,H,W,16]) is given the
         generated image is also written as bf16 into its channels [d_c0, d_c0+3)."""
         self.repack()
         B, C, H, W = x.shape
         t = {}
-        t["xin"] = ActBuf(B, H, W, 16, halo=3, zero=False)
-        ops.pack_nchw(x, t["xin"], 0, zero_rest=True)
-        t["y1"] = self._conv(t["xin"], "conv1")
-        t["s1"], t["z1"] = _norm_act(t["y1"], ACT_RELU, 0)
-        t["y2"] = self._conv(t["z1"], "conv2")
-        t["s2"], t["z2"] = _norm_act(t["y2"], ACT_RELU, 0)
-        t["y3"] = self._conv(t["z2"], "conv3")
-        t["s3"], xcur = _norm_act(t["y3"], ACT_RELU, 1)
-        t["x0"] = xcur
-        for i in range(self.n_blocks):
-            b = f"resnet_blocks.{i}."
-            ya = self._conv(xcur, b + "conv1")
-            sa, za = _norm_act(ya, ACT_RELU, 1)
-            yb = self._conv(za, b + "conv2")
-            last = i == self.n_blocks - 1
-            sb, xnext = _norm_act(yb, ACT_NONE, 0 if last else 1, residual=xcur)
-            t[f"b{i}"] = (ya, sa, za, yb, sb)
-            t[f"x{i + 1}"] = xnext
-            xcur = xnext
-        for br in ("content", "attention"):
-            u1 = self._conv(xcur, f"deconv1_{br}")
-            s1, v1 = _norm_act(u1, ACT_RELU, 0)
-            u2 = self._conv(v1, f"deconv2_{br}")
-            s2, v2 = _norm_act(u2, ACT_RELU, 3 if br == "content" else 0)
-            t[br] = (u1, s1, v1, u2, s2, v2)
+        xtop = self._trunk_forward(x, t)
+        t["content"] = self._decoder_forward(xtop, "deconv1_content", "deconv2_content", 3)
+        t["attention"] = self._decoder_forward(xtop, "deconv1_attention", "deconv2_attention", 0)
         t["c"] = self._conv(t["content"][5], "deconv3_content", fp32=True, act=ACT_TANH)
         t["l"] = self._conv(t["attention"][5], "deconv3_attention", fp32=True)
         out = torch.empty(B, 3, H, W, dtype=torch.float32, device=x.device) if want_nchw else None
@@ -195,57 +267,68 @@ class AttentionGeneratorNet(_NetBase):
         return out, t
 
     def backward(self, t, grads, dout_nchw=None, dout_nhwc=None, dout_c0=0, need_dx=False):
-        """Accumulates nothing: writes every parameter gradient of this call into `grads` (overwrite).
-        Returns the fp32 NCHW input gradient [B, 16->C, H, W] if need_dx."""
+        """Writes every parameter gradient of this call into `grads` (overwrite, no accumulation).
+        Returns the fp32 NCHW input gradient if need_dx."""
         xin = t["xin"]
         B, H, W = xin.n, xin.h, xin.w
-        dev = xin.t.device
         dc = ActBuf(B, H, W, 32, zero=False)
         dl = ActBuf(B, H, W, 16, zero=False)
-        dimg = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev) if need_dx else None
+        dimg = torch.empty(B, 3, H, W, dtype=torch.float32, device=xin.t.device) if need_dx else None
         ops.blend_bwd(t["c"], t["l"], xin, dc, dl, dout_nchw=dout_nchw, dout_nhwc=dout_nhwc, dout_c0=dout_c0,
                       dimage_nchw=dimg)
+        xtop = t[f"x{self.n_blocks}"]
         gx = []
         for br, dhead, head in (("content", dc, "deconv3_content"), ("attention", dl, "deconv3_attention")):
-            u1, s1, v1, u2, s2, v2 = t[br]
+            v2 = t[br][5]
             dv2 = self._conv_bwd(head, v2, dhead, grads, True, dx_halo=v2.halo)
-            du2 = ActBuf(u2.n, u2.h, u2.w, u2.c, zero=False)
-            ops.instnorm_bwd(dv2, u2, s2, ACT_RELU, du2)
-            dv1 = self._conv_bwd(f"deconv2_{br}", v1, du2, grads, True)
-            du1 = ActBuf(u1.n, u1.h, u1.w, u1.c, zero=False)
-            ops.instnorm_bwd(dv1, u1, s1, ACT_RELU, du1)
-            gx.append(self._conv_bwd(f"deconv1_{br}", t[f"x{self.n_blocks}"], du1, grads, True))
-        dz, dz2 = gx[0], gx[1]  # gradient w.r.t. x_n interior = sum of the two decoder branches
-        for i in reversed(range(self.n_blocks)):
-            ya, sa, za, yb, sb = t[f"b{i}"]
-            b = f"resnet_blocks.{i}."
-            xi = t[f"x{i}"]
-            gres = ActBuf(yb.n, yb.h, yb.w, yb.c, zero=False)  # total gradient w.r.t. x_{i+1} (skip branch)
-            dyb = ActBuf(yb.n, yb.h, yb.w, yb.c, zero=False)
-            ops.instnorm_bwd(dz, yb, sb, ACT_NONE, dyb, dz2=dz2, dres=gres)
-            dza = self._conv_bwd(b + "conv2", za, dyb, grads, True, dx_halo=1)
-            dya = ActBuf(ya.n, ya.h, ya.w, ya.c, zero=False)
-            ops.instnorm_bwd(dza, ya, sa, ACT_RELU, dya)
-            dz = self._conv_bwd(b + "conv1", xi, dya, grads, True, dx_halo=1)
-            dz2 = gres
-        dy3 = ActBuf(t["y3"].n, t["y3"].h, t["y3"].w, t["y3"].c, zero=False)
-        ops.instnorm_bwd(dz, t["y3"], t["s3"], ACT_RELU, dy3, dz2=dz2)
-        dz2_ = self._conv_bwd("conv3", t["z2"], dy3, grads, True)
-        dy2 = ActBuf(t["y2"].n, t["y2"].h, t["y2"].w, t["y2"].c, zero=False)
-        ops.instnorm_bwd(dz2_, t["y2"], t["s2"], ACT_RELU, dy2)
-        dz1 = self._conv_bwd("conv2", t["z1"], dy2, grads, True)
-        dy1 = ActBuf(t["y1"].n, t["y1"].h, t["y1"].w, t["y1"].c, zero=False)
-        ops.instnorm_bwd(dz1, t["y1"], t["s1"], ACT_RELU, dy1)
-        dxin = self._conv_bwd("conv1", xin, dy1, grads, need_dx, dx_halo=3)
-        if not need_dx:
-            return None
-        folded = ActBuf(B, H, W, 16, zero=False)
-        ops.halo_fold(dxin, None, folded)
-        c_in = self.layers["conv1"].c_valid
-        dx = torch.zeros(B, c_in, H, W, dtype=torch.float32, device=dev)
-        ops.unpack_nchw(folded, dx, 0)
-        dx[:, :3] += dimg
-        return dx
+            gx.append(self._decoder_backward(t[br], xtop, dv2, f"deconv1_{br}", f"deconv2_{br}", grads))
+        dxin = self._trunk_backward(t, gx[0], gx[1], grads, need_dx)  # x_n gradient = sum of both decoder branches
+        return self._input_grad_nchw(t, dxin, dimg) if need_dx else None
+
+
+class CycleGANGeneratorNet(_ResnetGeneratorNet):
+    """CycleGANGenerator (model_architectures.py:91-134): same trunk, one decoder, 7x7 -> 3 + tanh head."""
+
+    STEM = ("model.1", "model.4", "model.7")
+
+    def __init__(self, module):
+        super().__init__(module)
+        seq = module.model
+        self._add("model.1", seq[1], 7, 1, 0)
+        self._add("model.4", seq[4], 3, 2, 1)
+        self._add("model.7", seq[7], 3, 2, 1)
+        self.n_blocks = 9
+        for i in range(9):
+            blk = seq[10 + i].conv_block
+            self._add(f"model.{10 + i}.conv_block.1", blk[1], 3, 1, 0)
+            self._add(f"model.{10 + i}.conv_block.5", blk[5], 3, 1, 0)
+        self._add("model.19", seq[19], 3, 2, 1, transposed=True)
+        self._add("model.22", seq[22], 3, 2, 1, transposed=True)
+        self._add("model.26", seq[26], 7, 1, 0, use_bias=True)
+
+    def _block_names(self, i):
+        return f"model.{10 + i}.conv_block.1", f"model.{10 + i}.conv_block.5"
+
+    def forward(self, x):
+        self.repack()
+        B, C, H, W = x.shape
+        t = {}
+        xtop = self._trunk_forward(x, t)
+        t["dec"] = self._decoder_forward(xtop, "model.19", "model.22", 3)
+        t["o"] = self._conv(t["dec"][5], "model.26", fp32=True, act=ACT_TANH)  # fp32 NHWC, 3 of 16 channels valid
+        out = torch.empty(B, 3, H, W, dtype=torch.float32, device=x.device)
+        ops.unpack_nchw(t["o"], out, 0)
+        return out, t
+
+    def backward(self, t, grads, dout_nchw, need_dx=False):
+        o = t["o"]
+        dpre = ActBuf(o.n, o.h, o.w, 16, zero=False)
+        ops.tanh_bwd_pack(dout_nchw, o, dpre)
+        v2 = t["dec"][5]
+        dv2 = self._conv_bwd("model.26", v2, dpre, grads, True, dx_halo=3)
+        gtop = self._decoder_backward(t["dec"], t[f"x{self.n_blocks}"], dv2, "model.19", "model.22", grads)
+        dxin = self._trunk_backward(t, gtop, None, grads, need_dx)
+        return self._input_grad_nchw(t, dxin) if need_dx else None
 
 
 class PatchGANNet(_NetBase):

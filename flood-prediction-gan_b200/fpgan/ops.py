@@ -254,6 +254,11 @@ def unpack_nchw(src, dst, c0=0, accumulate=False):
     _run("unpack_nchw", 1, "fpg_unpack_nchw", src.ref(), c0, _ptr(dst), dst.shape[1], 1 if accumulate else 0, _stream())
 
 
+def tanh_bwd_pack(dout_nchw, out, dpre, c_valid=3):
+    assert dout_nchw.dtype == torch.float32 and dout_nchw.is_contiguous()
+    _run("tanh_bwd_pack", 1, "fpg_tanh_bwd_pack", _ptr(dout_nchw), out.ref(), c_valid, dpre.ref(), _stream())
+
+
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
     _run("adam_step", 1, "fpg_adam_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(lr), float(beta1), float(beta2),
            float(eps), int(step), float(grad_scale), _stream())

@@ -136,6 +136,42 @@ class AttentionGANGenerator(_AttentionGeneratorBase):
         super().__init__(input_channels, AttentionGANBlock)
 
 
+class CycleGANBlock(nn.Module):
+    """Parameter container of one CycleGAN residual block (reference :122-134); executed by the generator."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.conv_block = nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(dim, dim, kernel_size=3, padding=0, bias=True),
+                                        nn.InstanceNorm2d(dim), nn.ReLU(True), nn.ReflectionPad2d(1),
+                                        nn.Conv2d(dim, dim, kernel_size=3, padding=0, bias=True),
+                                        nn.InstanceNorm2d(dim))
+
+    def forward(self, x):
+        raise RuntimeError("residual blocks are executed by the enclosing generator's native executor")
+
+
+class CycleGANGenerator(_NativeModule):
+    """reference :91-120; `model` keeps the reference's Sequential indices (state_dict keys model.1, model.4, ...)."""
+    _executor_cls = networks.CycleGANGeneratorNet
+
+    def __init__(self, input_channels):
+        super().__init__()
+        seq = [nn.ReflectionPad2d(3), nn.Conv2d(input_channels, 64, kernel_size=7, padding=0, bias=True),
+               nn.InstanceNorm2d(64), nn.ReLU(True)]
+        for mult in (1, 2):
+            seq += [nn.Conv2d(64 * mult, 128 * mult, kernel_size=3, stride=2, padding=1, bias=True),
+                    nn.InstanceNorm2d(128 * mult), nn.ReLU(True)]
+        seq += [CycleGANBlock(dim=256) for _ in range(9)]
+        for mult in (4, 2):
+            seq += [nn.ConvTranspose2d(64 * mult, 32 * mult, kernel_size=3, stride=2, padding=1, output_padding=1,
+                                       bias=True), nn.InstanceNorm2d(32 * mult), nn.ReLU(True)]
+        seq += [nn.ReflectionPad2d(3), nn.Conv2d(64, 3, kernel_size=7, padding=0), nn.Tanh()]
+        self.model = nn.Sequential(*seq)
+
+    def _run_backward(self, net, tape, dout, grads, need_dx):
+        return net.backward(tape, grads, dout, need_dx=need_dx)
+
+
 # ------------------------------------------------------------------------------------------------ discriminators
 class _InstanceNormPatchGAN(_NativeModule):
     _executor_cls = networks.PatchGANNet

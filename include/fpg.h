@@ -250,7 +250,11 @@ int fpg_l1_loss(const float* pred, const float* target, int64_t count, float wei
 /* src fp32 NCHW [n][c_src][h][w] -> dst bf16 NHWC channels [c0, c0+c_src) of dst interior, reflect halo filled if
  * dst->halo > 0. Channels of dst outside the copied range are left untouched unless zero_rest != 0. */
 int fpg_pack_nchw(const float* src, int32_t c_src, const fpg_act* dst, int32_t c0, int zero_rest, void* stream);
-/* src bf16 NHWC channels [c0, c0+c_dst) of the interior -> dst fp32 NCHW; accumulate != 0 adds instead */
+/* Backward through a fused tanh head (CycleGAN generator, model_architectures.py:115-116): dpre (bf16 NHWC) =
+ * dout (fp32 NCHW [n][c_valid][h][w]) * (1 - out^2), out = the fp32 NHWC tanh output; channels >= c_valid are 0. */
+int fpg_tanh_bwd_pack(const float* dout_nchw, const fpg_act* out, int32_t c_valid, const fpg_act* dpre, void* stream);
+/* src (bf16 or fp32 per src->fp32) NHWC channels [c0, c0+c_dst) of the interior -> dst fp32 NCHW; accumulate != 0
+ * adds instead */
 int fpg_unpack_nchw(const fpg_act* src, int32_t c0, float* dst, int32_t c_dst, int accumulate, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
