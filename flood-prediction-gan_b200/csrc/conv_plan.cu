@@ -1,5 +1,6 @@
 // Planners: convolution geometry -> implicit-GEMM descriptors, plus weight packing and the split-K wgrad reduce.
 // Pure host logic except for the small pack / reduce kernels at the bottom.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -113,6 +114,40 @@ static int pick_block_n(int n_total, int m_tiles, int sms) {
   return bn;
 }
 
+// Chooses the 128-pixel CTA tile shape and block_n of the fprop-type kernel. (A 256-pixel single-CTA tile -- two MMAs
+// sharing one B tile -- was measured slower on B200: its accumulators fill TMEM, so the epilogue is exposed; the 2-CTA
+// kernel is how operand traffic is cut instead, see maybe_pair.)
+static void choose_fprop_tile(int ho, int wo, int n_img, int n_total, int cblk, int sms, int* tile_w, int* tile_h,
+                              int* block_n) {
+  int tw1, th1;
+  pick_tile(ho, wo, &tw1, &th1, 128);
+  const int t1 = n_img * ceil_div(wo, tw1) * ceil_div(ho, th1);
+  const int bn1 = pick_block_n(n_total, t1, sms);
+  *tile_w = tw1;
+  *tile_h = th1;
+  *block_n = bn1;
+}
+
+// 2-CTA (cta_group::2) variant of a planned fprop-type launch: pair tiles of 2*tile_h x tile_w pixels, each CTA loads
+// half of the weight tile. Chosen when there is enough work for the 74 clusters and the layer is wide enough to be
+// bound by operand delivery.
+static void maybe_pair(fpg_igemm_fprop_desc* d, int grid_h, int sms) {
+  d->cta_pair = 0;
+  if (getenv("FPG_DISABLE_2CTA") != nullptr) return;
+  if (d->cblk != 64 || d->block_n < 128 || d->block_n % 32 != 0 || d->tile_h * d->tile_w != 128) return;
+  const int single = d->n_img * d->tiles_x * d->tiles_y * d->n_blocks;
+  const int pair_rows = ceil_div(grid_h, 2 * d->tile_h);
+  const int pairs = d->n_img * d->tiles_x * pair_rows * d->n_blocks;
+  const double cost_single = static_cast<double>(ceil_div(single, sms));
+  const double cost_pair = static_cast<double>(ceil_div(pairs, sms / 2)) * 0.88;  // measured pair/single tile time
+  if (cost_pair >= cost_single) return;
+  d->cta_pair = 1;
+  d->tiles_y = pair_rows;
+  d->b.box[1] = d->block_n / 2;
+  int s2 = (200 * 1024) / (16384 + d->block_n * 64);
+  d->stages = s2 > 8 ? 8 : s2;
+}
+
 static int pick_stages(int stage_bytes) {
   int s = (200 * 1024) / stage_bytes;
   if (s > 8) s = 8;
@@ -176,13 +211,12 @@ static int plan_fprop(const fpg_act* x, const void* w, const float* bias, int ac
   for (int r = 0; r < g->r; ++r)
     for (int s = 0; s < g->s; ++s) d->taps[r * g->s + s] = fwd_tap(r, s, g->stride, g->pad, x->c_stride);
   for (int t = real_taps; t < d->num_taps; ++t) d->taps[t] = d->taps[0];
-  pick_tile(ho, wo, &d->tile_w, &d->tile_h, 128);
+  choose_fprop_tile(ho, wo, x->n, g->c_out, cblk, sms, &d->tile_w, &d->tile_h, &d->block_n);
   d->tiles_x = ceil_div(wo, d->tile_w);
   d->tiles_y = ceil_div(ho, d->tile_h);
   d->n_img = x->n;
-  d->block_n = pick_block_n(g->c_out, d->n_img * d->tiles_x * d->tiles_y, sms);
   d->n_blocks = g->c_out / d->block_n;
-  d->stages = pick_stages(16384 + d->block_n * 128);
+  d->stages = pick_stages(d->tile_w * d->tile_h * 128 + d->block_n * 128);
   d->act = act;
   d->bias = bias;
   make_act_view(x, g->stride, cblk, d->tile_w, d->tile_h, &d->a);
@@ -196,6 +230,7 @@ static int plan_fprop(const fpg_act* x, const void* w, const float* bias, int ac
   d->b.box[0] = cblk;
   d->b.box[1] = d->block_n;
   out_view_of(y, 0, &d->out);
+  maybe_pair(d, ho, sms);
   return 0;
 }
 
@@ -246,13 +281,12 @@ static int plan_dgrad(const fpg_act* dy, const void* wt, const float* bias, int 
     for (int t = nt; t < d->num_taps; ++t) d->taps[t] = d->taps[0];
     d->num_sub = d->num_taps * (g->c_out / cblk);
     const int oh = g->stride == 2 ? hp / 2 : hp, ow = g->stride == 2 ? wp / 2 : wp;  // class output grid
-    pick_tile(oh, ow, &d->tile_w, &d->tile_h, 128);
+    choose_fprop_tile(oh, ow, dx->n, g->c_in, cblk, sms, &d->tile_w, &d->tile_h, &d->block_n);
     d->tiles_x = ceil_div(ow, d->tile_w);
     d->tiles_y = ceil_div(oh, d->tile_h);
     d->n_img = dx->n;
-    d->block_n = pick_block_n(g->c_in, d->n_img * d->tiles_x * d->tiles_y, sms);
     d->n_blocks = g->c_in / d->block_n;
-    d->stages = pick_stages(16384 + d->block_n * 128);
+    d->stages = pick_stages(d->tile_w * d->tile_h * 128 + d->block_n * 128);
     d->act = act;
     d->bias = bias;
     make_act_view(dy, 1, cblk, d->tile_w, d->tile_h, &d->a);
@@ -272,6 +306,7 @@ static int plan_dgrad(const fpg_act* dy, const void* wt, const float* bias, int 
       d->out.valid_h = oh;
       d->out.valid_w = ow;
     }
+    maybe_pair(d, oh, sms);
   }
   *n_descs = nc;
   return 0;
@@ -313,7 +348,7 @@ static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* 
     d->x_is_dy = 1;
     d->tap_on_x = 0;
     d->x_ca = 64;
-    d->x_atoms = g->c_out % 128 == 0 ? 2 : 1;
+    d->x_atoms = g->c_out % 256 == 0 && big_in ? 4 : (g->c_out % 128 == 0 ? 2 : 1);
     d->x_groups = g->c_out / (64 * d->x_atoms);
     d->x_taps_mode = 0;
     d->x_ntaps = 1;

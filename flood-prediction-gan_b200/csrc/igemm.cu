@@ -12,7 +12,6 @@ namespace fpg {
 
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;  // columns per accumulator stage
 
 struct FpropArgs {
   int32_t chunks_per_tap;
@@ -22,6 +21,8 @@ struct FpropArgs {
   int32_t n_img, tiles_y, tiles_x;
   int32_t tile_w_log2;
   int32_t tile_h, tile_w;
+  int32_t m_sub;       // 128-pixel sub-tiles per CTA tile (1 or 2): each K step issues m_sub MMAs sharing one B tile
+  int32_t acc_stages;  // accumulator stages in TMEM: 2 if 2 * m_sub * block_n <= 512 else 1
   int32_t act;
   int32_t stages;
   const float* bias;
@@ -43,8 +44,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
                    const __grid_constant__ FpropArgs args) {
   constexpr int SUB = 64 / CBLK;                   // TMA sub-loads per 64-wide K stage
-  constexpr uint32_t A_SUB_BYTES = 128u * CBLK * 2u;
-  constexpr uint32_t A_STAGE_BYTES = 128u * 64u * 2u;
   constexpr uint32_t LAYOUT = swizzle_layout_type(CBLK * 2);
   constexpr uint32_t SBO = 8u * CBLK * 2u;  // 8 rows of one swizzle atom
 
@@ -52,9 +51,15 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int BN = args.block_n;
+  constexpr int MS = 1;  // 256-pixel single-CTA tiles (two MMAs per B tile) measured slower: epilogue exposed
+  constexpr uint32_t A_SUB_BYTES = static_cast<uint32_t>(MS) * 128u * CBLK * 2u;  // one TMA box: MS*128 pixel rows
+  constexpr uint32_t A_HALF_BYTES = 128u * CBLK * 2u;                             // rows of one 128-pixel sub-tile
+  constexpr uint32_t A_STAGE_BYTES = static_cast<uint32_t>(MS) * 128u * 64u * 2u;
   const uint32_t B_SUB_BYTES = static_cast<uint32_t>(BN) * CBLK * 2u;
   const uint32_t B_STAGE_BYTES = static_cast<uint32_t>(BN) * 128u;
   const int STAGES = args.stages;
+  const uint32_t ACC_COLS = static_cast<uint32_t>(MS * BN);  // TMEM columns of one accumulator stage
+  const uint32_t ACC_STAGES = static_cast<uint32_t>(args.acc_stages);
 
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
@@ -132,10 +137,10 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
       const uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        const uint32_t as = it % ACC_STAGES, aph = (it / ACC_STAGES) & 1;
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * kAccStride;
+        const uint32_t d_tmem = tmem_base + as * ACC_COLS;
         for (int ks = 0; ks < num_kstages; ++ks) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
@@ -145,9 +150,12 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
           for (int j = 0; j < SUB; ++j) {
 #pragma unroll
             for (int k = 0; k < CBLK / 16; ++k) {
-              const uint64_t ad = make_smem_desc(a_addr + j * A_SUB_BYTES + k * 32, 0, SBO, LAYOUT);
               const uint64_t bd = make_smem_desc(b_addr + j * B_SUB_BYTES + k * 32, 0, SBO, LAYOUT);
-              umma_bf16(d_tmem, ad, bd, idesc, (ks | j | k) != 0 ? 1u : 0u);
+              for (int ms = 0; ms < MS; ++ms) {
+                const uint64_t ad =
+                    make_smem_desc(a_addr + j * A_SUB_BYTES + ms * A_HALF_BYTES + k * 32, 0, SBO, LAYOUT);
+                umma_bf16(d_tmem + ms * BN, ad, bd, idesc, (ks | j | k) != 0 ? 1u : 0u);
+              }
             }
           }
           umma_commit(&empty[stage]);  // frees the smem slot once these MMAs have read it
@@ -162,11 +170,219 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it % ACC_STAGES, aph = (it / ACC_STAGES) & 1;
+      int nb = tile % args.n_blocks;
+      int r = tile / args.n_blocks;
+      int tx = r % args.tiles_x;
+      r /= args.tiles_x;
+      int ty = r % args.tiles_y;
+      int n = r / args.tiles_y;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      for (int ms = 0; ms < MS; ++ms) {
+        const int row = ms * 128 + q * 32 + lane;
+        const int ry = row >> args.tile_w_log2;
+        const int rx = row & (args.tile_w - 1);
+        const int py = ty * args.tile_h + ry, px = tx * args.tile_w + rx;
+        const bool valid = (py < args.out.valid_h) && (px < args.out.valid_w);
+        const int64_t off = static_cast<int64_t>(n) * args.out.stride_n +
+                            static_cast<int64_t>(py * args.out.mul_y + args.out.off_y) * args.out.stride_y +
+                            static_cast<int64_t>(px * args.out.mul_x + args.out.off_x) * args.out.stride_x +
+                            static_cast<int64_t>(nb) * BN;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC_COLS + ms * BN;
+        for (int c = 0; c < BN; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_addr + c, v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (args.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(args.bias + nb * BN + c);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = __ldg(bp + i);
+              f[4 * i + 0] += b4.x;
+              f[4 * i + 1] += b4.y;
+              f[4 * i + 2] += b4.z;
+              f[4 * i + 3] += b4.w;
+            }
+          }
+          if (args.act != FPG_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], args.act);
+          }
+          if (valid) {
+            if (args.out.fp32) {
+              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out.base) + off + c);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out.base) + off + c);
+              dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                  pack_bf16x2(f[6], f[7]));
+              dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                                  pack_bf16x2(f[14], f[15]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ 2-CTA fprop
+// Same implicit GEMM on a CTA PAIR (cluster of 2 = one TPC): tcgen05.mma.cta_group::2 with M = 256 pixels (128 per
+// CTA) and N = block_n. Each CTA TMA-loads its own 128 pixel rows of A and only HALF of the weight tile (block_n / 2
+// rows); the tensor cores read the other half from the peer's shared memory. Per CTA and K stage that is 16 KB + 16 KB
+// instead of 16 KB + 32 KB: the 1-CTA kernel is bound by L2->SM operand delivery (~45 B/clk/SM), not by the MMA.
+// Protocol (leader = cluster rank 0): both producers credit the LEADER's full barrier; the leader's elected thread
+// issues the MMAs and multicasts the commit to both CTAs' empty / tmem-full barriers; both epilogues drain their own
+// TMEM lanes and arrive on the leader's tmem-empty barrier.
+template <int CBLK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+igemm_fprop2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
+                    const __grid_constant__ FpropArgs args) {
+  constexpr int SUB = 64 / CBLK;
+  constexpr uint32_t A_SUB_BYTES = 128u * CBLK * 2u;
+  constexpr uint32_t A_STAGE_BYTES = 128u * 64u * 2u;
+  constexpr uint32_t LAYOUT = swizzle_layout_type(CBLK * 2);
+  constexpr uint32_t SBO = 8u * CBLK * 2u;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int BN = args.block_n;
+  const int BH = BN / 2;  // weight rows held by each CTA
+  const uint32_t B_SUB_BYTES = static_cast<uint32_t>(BH) * CBLK * 2u;
+  const uint32_t B_STAGE_BYTES = static_cast<uint32_t>(BH) * 128u;
+  const int STAGES = args.stages;
+
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 2);   // leader's copy is used: its own arrive.expect_tx + the peer's remote arrive
+      mbar_init(&empty[i], 1);  // one multicast commit per use
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 256);  // leader's copy is used: 128 epilogue threads of each CTA
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&amap);
+    tma_prefetch_desc(&bmap);
+  }
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = args.n_img * args.tiles_y * args.tiles_x * args.n_blocks;  // pair tiles
+  const int num_kstages = args.num_kstages;
+  const int first_tile = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      const uint32_t stage_bytes = 2u * (A_STAGE_BYTES + B_STAGE_BYTES);
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        int nb = tile % args.n_blocks;
+        int r = tile / args.n_blocks;
+        int tx = r % args.tiles_x;
+        r /= args.tiles_x;
+        int ty = r % args.tiles_y;
+        int n = r / args.tiles_y;
+        const int x0 = tx * args.tile_w, y0 = (ty * 2 + static_cast<int>(rank)) * args.tile_h;
+        int sub = 0;
+        for (int ks = 0; ks < num_kstages; ++ks) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          if (leader) {
+            mbar_arrive_expect_tx(&full[stage], stage_bytes);
+          } else {
+            mbar_arrive_cluster(&full[stage], 0);
+          }
+          uint8_t* a_dst = smem_a + stage * A_STAGE_BYTES;
+          uint8_t* b_dst = smem_b + stage * B_STAGE_BYTES;
+#pragma unroll
+          for (int j = 0; j < SUB; ++j, ++sub) {
+            const int tap = sub / args.chunks_per_tap;
+            const int chunk = sub - tap * args.chunks_per_tap;
+            const fpg_tap t = args.taps[tap];
+            tma_load_5d_2sm(&amap, &full[stage], a_dst + j * A_SUB_BYTES, t.c0 + chunk * CBLK, x0 + t.dx, t.plane,
+                            y0 + t.dy, n);
+            tma_load_2d_2sm(&bmap, &full[stage], b_dst + j * B_SUB_BYTES, sub * CBLK,
+                            nb * BN + static_cast<int>(rank) * BH);
+          }
+          if (++stage == static_cast<uint32_t>(STAGES)) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(256, BN, 0, 0);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        for (int ks = 0; ks < num_kstages; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int j = 0; j < SUB; ++j) {
+#pragma unroll
+            for (int k = 0; k < CBLK / 16; ++k) {
+              const uint64_t ad = make_smem_desc(a_addr + j * A_SUB_BYTES + k * 32, 0, SBO, LAYOUT);
+              const uint64_t bd = make_smem_desc(b_addr + j * B_SUB_BYTES + k * 32, 0, SBO, LAYOUT);
+              umma_bf16_2cta(d_tmem, ad, bd, idesc, (ks | j | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit_2cta(&empty[stage], 3);  // both CTAs' slots are free once these MMAs have read them
+          if (++stage == static_cast<uint32_t>(STAGES)) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2cta(&tfull[as], 3);  // accumulators complete in both CTAs
+      }
+    }
+  } else {
+    const int q = warp & 3;
     const int row = q * 32 + lane;
     const int ry = row >> args.tile_w_log2;
     const int rx = row & (args.tile_w - 1);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       const uint32_t as = it & 1, aph = (it >> 1) & 1;
       int nb = tile % args.n_blocks;
       int r = tile / args.n_blocks;
@@ -174,7 +390,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
       r /= args.tiles_x;
       int ty = r % args.tiles_y;
       int n = r / args.tiles_y;
-      const int py = ty * args.tile_h + ry, px = tx * args.tile_w + rx;
+      const int py = (ty * 2 + static_cast<int>(rank)) * args.tile_h + ry, px = tx * args.tile_w + rx;
       const bool valid = (py < args.out.valid_h) && (px < args.out.valid_w);
       const int64_t off = static_cast<int64_t>(n) * args.out.stride_n +
                           static_cast<int64_t>(py * args.out.mul_y + args.out.off_y) * args.out.stride_y +
@@ -182,7 +398,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                           static_cast<int64_t>(nb) * BN;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * kAccStride;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
       for (int c = 0; c < BN; c += 16) {
         uint32_t v[16];
         tmem_ld16(t_addr + c, v);
@@ -220,13 +436,13 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      mbar_arrive_cluster(&tempty[as], 0);
     }
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad
@@ -346,7 +562,11 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(M, N, 1, 1);  // both operands MN-major (pixel rows, channel-contiguous)
+      // both operands MN-major (pixel rows, channel-contiguous). M == 256 is issued as two M=128 MMAs that share the Y
+      // tile (accumulators at columns [0,N) and [N,2N)): 1/3 less operand traffic per FLOP than two M=128 CTAs.
+      const int MI = M > 128 ? 128 : M;
+      const int msub = M / MI;
+      const uint32_t idesc = make_idesc_bf16(MI, N, 1, 1);
       const uint32_t x_layout = swizzle_layout_type(args.x_ca * 2), y_layout = swizzle_layout_type(args.y_ca * 2);
       const uint32_t x_sbo = 8u * args.x_ca * 2u, y_sbo = 8u * args.y_ca * 2u;  // 8 pixel rows
       const uint32_t x_kstep = 16u * args.x_ca * 2u, y_kstep = 16u * args.y_ca * 2u;  // 16 pixel rows per MMA
@@ -359,9 +579,12 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
         const uint32_t y_addr = smem_u32(smem_y + stage * Y_STAGE_BYTES);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t xd = make_smem_desc(x_addr + k * x_kstep, X_ATOM_BYTES, x_sbo, x_layout);
           const uint64_t yd = make_smem_desc(y_addr + k * y_kstep, Y_ATOM_BYTES, y_sbo, y_layout);
-          umma_bf16(tmem_base, xd, yd, idesc, first ? 0u : 1u);
+          for (int ms = 0; ms < msub; ++ms) {
+            const uint64_t xd = make_smem_desc(x_addr + ms * 2 * X_ATOM_BYTES + k * x_kstep, X_ATOM_BYTES, x_sbo,
+                                               x_layout);
+            umma_bf16(tmem_base + ms * N, xd, yd, idesc, first ? 0u : 1u);
+          }
           first = false;
         }
         umma_commit(&empty[stage]);
@@ -374,30 +597,33 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     }
   } else {
     const int q = warp & 3;
-    // M == 128: row = 32q + lane. M == 64: rows 16q..16q+15 live in lanes 0..15 of quarter q.
-    const int row = (M == 128) ? q * 32 + lane : q * 16 + lane;
-    const bool row_valid = (M == 128) || (lane < 16);
-    float* dst = args.ws + (static_cast<int64_t>(split) * items + item) * M * N + static_cast<int64_t>(row) * N;
+    // M >= 128: row = 32q + lane (+128 for the second sub-tile). M == 64: rows 16q..16q+15 are lanes 0..15 of quarter q
+    const int msub = M > 128 ? 2 : 1;
+    const bool row_valid = (M >= 128) || (lane < 16);
     if (kt_end > kt_begin) {
       mbar_wait(tfull, 0);
       tc_fence_after();
     }
-    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int c = 0; c < N; c += 16) {
-      uint32_t v[16];
-      if (kt_end > kt_begin) {
-        tmem_ld16(t_addr + c, v);
-        tmem_ld_wait();
-      } else {
+    for (int ms = 0; ms < msub; ++ms) {
+      const int row = (M >= 128) ? ms * 128 + q * 32 + lane : q * 16 + lane;
+      float* dst = args.ws + (static_cast<int64_t>(split) * items + item) * M * N + static_cast<int64_t>(row) * N;
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ms * N;
+      for (int c = 0; c < N; c += 16) {
+        uint32_t v[16];
+        if (kt_end > kt_begin) {
+          tmem_ld16(t_addr + c, v);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = 0u;
-      }
-      if (row_valid) {
-        float4* d4 = reinterpret_cast<float4*>(dst + c);
+          for (int i = 0; i < 16; ++i) v[i] = 0u;
+        }
+        if (row_valid) {
+          float4* d4 = reinterpret_cast<float4*>(dst + c);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                              __uint_as_float(v[4 * i + 3]));
+          for (int i = 0; i < 4; ++i)
+            d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+        }
       }
     }
   }
@@ -421,7 +647,10 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
   FPG_REQUIRE(d != nullptr, "null descriptor");
   FPG_REQUIRE(d->cblk == 16 || d->cblk == 32 || d->cblk == 64, "cblk %d", d->cblk);
   FPG_REQUIRE(d->block_n >= 16 && d->block_n <= 256 && d->block_n % 16 == 0, "block_n %d", d->block_n);
-  FPG_REQUIRE(d->tile_h * d->tile_w == 128 && log2_exact(d->tile_w) >= 0, "tile %dx%d", d->tile_h, d->tile_w);
+  const int m_sub = d->tile_h * d->tile_w / 128;
+  FPG_REQUIRE(m_sub == 1 && d->tile_h * d->tile_w == 128 * m_sub && log2_exact(d->tile_w) >= 0,
+              "tile %dx%d", d->tile_h, d->tile_w);
+  FPG_REQUIRE(m_sub * d->block_n <= 512, "accumulator does not fit TMEM");
   const int sub_per_stage = 64 / d->cblk;
   FPG_REQUIRE(d->num_sub > 0 && d->num_sub % sub_per_stage == 0, "num_sub %d", d->num_sub);
   FPG_REQUIRE(d->c_per_tap % d->cblk == 0, "c_per_tap %d", d->c_per_tap);
@@ -445,6 +674,8 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
   args.tile_w_log2 = log2_exact(d->tile_w);
   args.tile_h = d->tile_h;
   args.tile_w = d->tile_w;
+  args.m_sub = m_sub;
+  args.acc_stages = (2 * m_sub * d->block_n <= 512) ? 2 : 1;
   args.act = d->act;
   args.stages = d->stages;
   args.bias = d->bias;
@@ -454,9 +685,29 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
   const int total_tiles = d->n_img * d->tiles_y * d->tiles_x * d->n_blocks;
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
-  const int grid = total_tiles < sms ? total_tiles : sms;
-  const size_t smem = static_cast<size_t>(d->stages) * (16384 + d->block_n * 128) + (2 * d->stages + 4) * 8 + 16 + 1024;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d->cta_pair) {
+    FPG_REQUIRE(m_sub == 1 && d->block_n % 32 == 0 && d->cblk >= 32, "cta_pair needs 128-pixel tiles, block_n % 32");
+    const int clusters = total_tiles < sms / 2 ? total_tiles : sms / 2;
+    const size_t smem2 =
+        static_cast<size_t>(d->stages) * (16384 + d->block_n * 64) + (2 * d->stages + 4) * 8 + 16 + 1024;
+    FPG_REQUIRE(smem2 <= 227 * 1024, "shared memory %zu", smem2);
+    if (d->cblk == 64) {
+      FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_fprop2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem2)));
+      igemm_fprop2_kernel<64><<<2 * clusters, kThreads, smem2, st>>>(amap, bmap, args);
+    } else {
+      FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_fprop2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem2)));
+      igemm_fprop2_kernel<32><<<2 * clusters, kThreads, smem2, st>>>(amap, bmap, args);
+    }
+    FPG_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
+  const int grid = total_tiles < sms ? total_tiles : sms;
+  const size_t smem =
+      static_cast<size_t>(d->stages) * (16384 * m_sub + d->block_n * 128) + (2 * d->stages + 4) * 8 + 16 + 1024;
+  FPG_REQUIRE(smem <= 227 * 1024, "shared memory %zu", smem);
 #define FPG_LAUNCH_FPROP(CB)                                                                                     \
   do {                                                                                                           \
     FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_fprop_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
@@ -478,7 +729,7 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
 extern "C" int fpg_igemm_wgrad_launch(const fpg_igemm_wgrad_desc* d, void* stream) {
   FPG_REQUIRE(d != nullptr, "null descriptor");
   const int M = d->x_atoms * d->x_ca, N = d->y_atoms * d->y_ca;
-  FPG_REQUIRE(M == 64 || M == 128, "wgrad M %d", M);
+  FPG_REQUIRE(M == 64 || M == 128 || (M == 256 && d->x_ca == 64 && N <= 256), "wgrad M %d", M);
   FPG_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "wgrad N %d", N);
   FPG_REQUIRE(d->tile_h * d->tile_w == 64, "k tile %dx%d", d->tile_h, d->tile_w);
   FPG_REQUIRE(d->stages >= 2 && d->stages <= 8 && d->splits >= 1, "stages %d splits %d", d->stages, d->splits);

@@ -32,7 +32,7 @@ class FpropDesc(C.Structure):
     _fields_ = [("a", TMap), ("b", TMap), ("cblk", C.c_int32), ("c_per_tap", C.c_int32), ("num_taps", C.c_int32),
                 ("num_sub", C.c_int32), ("block_n", C.c_int32), ("n_blocks", C.c_int32), ("n_img", C.c_int32),
                 ("tiles_y", C.c_int32), ("tiles_x", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32),
-                ("act", C.c_int32), ("stages", C.c_int32), ("bias", C.c_void_p), ("out", OutView),
+                ("act", C.c_int32), ("stages", C.c_int32), ("cta_pair", C.c_int32), ("bias", C.c_void_p), ("out", OutView),
                 ("taps", Tap * FPG_MAX_TAPS)]
 
 

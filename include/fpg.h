@@ -74,7 +74,7 @@ typedef struct {
 
 /* D[pixel, k] = sum_{tap, c} A[pixel + tap, c] * B[k, tap*C + c]  (+bias, activation) */
 typedef struct {
-  fpg_tmap a;      /* gathered operand: box = {cblk, tile_w, 1, tile_h, 1}, tile_w*tile_h == 128 */
+  fpg_tmap a;      /* gathered operand: box = {cblk, tile_w, 1, tile_h, 1}, tile_w*tile_h == 128 or 256 */
   fpg_tmap b;      /* weight matrix [n_total rows][num_sub*cblk], K-major: box = {cblk, block_n} */
   int32_t cblk;    /* channels per TMA sub-load: 16 / 32 / 64 */
   int32_t c_per_tap; /* channels per tap (multiple of cblk) */
@@ -85,6 +85,9 @@ typedef struct {
   int32_t n_img, tiles_y, tiles_x, tile_h, tile_w;
   int32_t act;
   int32_t stages;
+  int32_t cta_pair;  /* 1: 2-CTA kernel (tcgen05 cta_group::2): a tile is 2*tile_h x tile_w pixels, the CTA of cluster
+                        rank r takes rows [r*tile_h, (r+1)*tile_h) and loads weight rows [r*block_n/2, ...): b.box[1] ==
+                        block_n / 2; tiles_y counts pair tiles */
   const float* bias; /* [n_total] or NULL */
   fpg_out_view out;
   fpg_tap taps[FPG_MAX_TAPS];
@@ -95,7 +98,7 @@ typedef struct {
 typedef struct {
   fpg_tmap x, y;          /* box = {ca, tile_w, 1, tile_h, 1}, tile_w*tile_h == 64 */
   int32_t x_ca, y_ca;     /* atom width in channels: 16 / 32 / 64 */
-  int32_t x_atoms, y_atoms; /* M = x_atoms*x_ca in {64,128}; N = y_atoms*y_ca, multiple of 16 (8 if M==64), <= 256 */
+  int32_t x_atoms, y_atoms; /* M = x_atoms*x_ca in {64,128,256}; N = y_atoms*y_ca, multiple of 16, <= 256 */
   int32_t x_groups, y_groups;
   int32_t x_taps_mode, y_taps_mode; /* 1: atom index enumerates taps; 0: atom index enumerates channel chunks */
   int32_t x_ntaps, y_ntaps;

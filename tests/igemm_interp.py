@@ -41,15 +41,20 @@ def run_fprop(desc, abuf, bbuf, outbuf, bias=None):
     cpt = desc.c_per_tap // cblk
     sub_per_stage = 64 // cblk
     assert desc.num_sub % sub_per_stage == 0
-    assert desc.tile_h * desc.tile_w == 128
+    assert desc.tile_h * desc.tile_w in (128, 256)
     ktot = int(desc.b.dims[0])
     b_base = (int(desc.b.base or 0) - FAKE_BASE) // 2
     n_total = desc.n_blocks * bn
     bmat = bbuf[b_base:b_base + n_total * ktot].reshape(n_total, ktot)
     o = desc.out
     o_base = (int(o.base or 0) - FAKE_BASE) // (4 if o.fp32 else 2)
+    pair = 2 if desc.cta_pair else 1
+    if desc.cta_pair:  # each CTA of the pair loads half of the weight rows of an n-block
+        assert int(desc.b.box[1]) * 2 == bn and desc.tile_h * desc.tile_w == 128
+    else:
+        assert int(desc.b.box[1]) == bn
     for n in range(desc.n_img):
-        for ty in range(desc.tiles_y):
+        for ty in range(desc.tiles_y * pair):  # pair tiles: rank r of the cluster takes row-tile 2*ty + r
             for tx in range(desc.tiles_x):
                 x0, y0 = tx * desc.tile_w, ty * desc.tile_h
                 acc = np.zeros((desc.tile_h, desc.tile_w, n_total), dtype=np.float64)
@@ -84,7 +89,7 @@ def run_wgrad(desc, xbuf, ybuf, dw, stride_k, stride_c, k_valid, c_valid):
     """Interpret an fpg_igemm_wgrad_desc including the split reduction and the scatter into dw (flat fp array)."""
     assert desc.tile_h * desc.tile_w == 64
     M, N = desc.x_atoms * desc.x_ca, desc.y_atoms * desc.y_ca
-    assert M in (64, 128) and N % 16 == 0 and 16 <= N <= 256
+    assert M in (64, 128, 256) and N % 16 == 0 and 16 <= N <= 256 and (M < 256 or 2 * N <= 512)
     NX = desc.x_groups if desc.x_taps_mode else desc.x_groups * desc.x_ntaps
     NY = desc.y_groups if desc.y_taps_mode else desc.y_groups * desc.y_ntaps
     total_kt = desc.n_img * desc.kt_y * desc.kt_x

@@ -96,7 +96,7 @@ def test_fprop_plan_matches_conv2d(fpglib, case):
     d = L.FpropDesc()
     L.call("fpg_conv2d_fprop_plan", C.byref(xa), interp.FAKE_BASE, None, L.ACT_LEAKY, C.byref(g), C.byref(ya), SMS,
            C.byref(d))
-    assert d.num_sub % (64 // d.cblk) == 0 and d.tile_h * d.tile_w == 128
+    assert d.num_sub % (64 // d.cblk) == 0 and d.tile_h * d.tile_w in (128, 256)
     abuf = nhwc_buffer(x, cp, halo)
     bbuf = pack_fprop(wt, cp, kp, d.num_taps)
     assert bbuf.size * 2 == fpglib.fpg_packed_weight_bytes(C.byref(g))
@@ -181,6 +181,7 @@ WGRAD_CASES = [
     (1, 8, 8, 64, 64, 10, 16, 1, 1, 0, 0),      # attention head 1x1
     (1, 7, 7, 128, 128, 1, 16, 4, 1, 1, 0),     # model.11
     (2, 9, 9, 64, 64, 128, 128, 4, 1, 1, 0),    # 4x4 s1 p1, odd extent
+    (1, 8, 8, 64, 64, 256, 256, 3, 1, 0, 1),    # c_out 256: M = 256 tile (two MMAs sharing the input tile)
 ]
 
 
@@ -220,3 +221,50 @@ def test_library_exports_every_declared_symbol(fpglib):
     for name in sorted(declared):
         assert hasattr(fpglib, name), f"{name} declared in include/fpg.h but not exported"
     assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+
+
+@pytest.mark.parametrize("kind", ["fprop", "dgrad_s1_halo", "dgrad_s2"])
+def test_cta_pair_plans(fpglib, kind):
+    """2-CTA (cta_group::2) descriptors: pair tiles, half weight boxes, odd number of row tiles (masked dummy half).
+    A small sm_count makes the planner choose pairing on shapes the interpreter can afford."""
+    torch.manual_seed(4)
+    sms = 2
+    if kind == "fprop":
+        n, h, w, c, k, r, stride, pad, halo = 1, 24, 16, 64, 128, 3, 1, 0, 1   # 24 rows -> 3 row tiles of 8: odd
+        x = torch.randn(n, c, h, w, dtype=torch.float64)
+        wt = torch.randn(k, c, r, r, dtype=torch.float64)
+        xin = F.pad(x, (halo,) * 4, "reflect")
+        ref = F.conv2d(xin, wt, None, stride=stride, padding=pad)
+        xa, ya, g = make_act(n, h, w, c, halo=halo), make_act(n, h, w, k), geom(r, r, stride, pad, c, k)
+        d = L.FpropDesc()
+        L.call("fpg_conv2d_fprop_plan", C.byref(xa), interp.FAKE_BASE, None, L.ACT_NONE, C.byref(g), C.byref(ya), sms,
+               C.byref(d))
+        assert d.cta_pair == 1 and int(d.b.box[1]) * 2 == d.block_n
+        out = np.full(n * h * w * k, np.nan)
+        interp.run_fprop(d, nhwc_buffer(x, c, halo), pack_fprop(wt, c, k, d.num_taps), out)
+        got = torch.from_numpy(out).reshape(n, h, w, k).permute(0, 3, 1, 2)
+        torch.testing.assert_close(got, ref, rtol=1e-9, atol=1e-9)
+        return
+    if kind == "dgrad_s1_halo":
+        n, h, w, c, k, r, stride, pad, halo = 1, 22, 14, 128, 64, 3, 1, 0, 1
+    else:
+        n, h, w, c, k, r, stride, pad, halo = 1, 32, 32, 128, 64, 4, 2, 1, 0
+    xin = torch.randn(n, c, h + 2 * halo, w + 2 * halo, dtype=torch.float64, requires_grad=True)
+    wt = torch.randn(k, c, r, r, dtype=torch.float64)
+    y = F.conv2d(xin, wt, None, stride=stride, padding=pad)
+    dy = torch.randn_like(y)
+    (ref,) = torch.autograd.grad(y, xin, dy)
+    g = geom(r, r, stride, pad, c, k)
+    dya, dxa = make_act(n, y.shape[2], y.shape[3], k), make_act(n, h, w, c, halo=halo)
+    descs = (L.FpropDesc * 4)()
+    nd = C.c_int()
+    L.call("fpg_conv2d_dgrad_plan", C.byref(dya), interp.FAKE_BASE, None, L.ACT_NONE, C.byref(g), C.byref(dxa), sms,
+           descs, C.byref(nd))
+    assert all(descs[q].cta_pair == 1 for q in range(nd.value))
+    hp, wp = h + 2 * halo, w + 2 * halo
+    out = np.full(n * hp * wp * c, np.nan)
+    for q in range(nd.value):
+        interp.run_fprop(descs[q], nhwc_buffer(dy, k), pack_dgrad(fpglib, wt, g), out)
+    out = torch.from_numpy(out).reshape(n, hp, wp, c)
+    assert not torch.isnan(out).any()
+    torch.testing.assert_close(out.permute(0, 3, 1, 2), ref, rtol=1e-9, atol=1e-9)
