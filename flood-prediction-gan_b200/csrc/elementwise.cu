@@ -19,6 +19,29 @@ struct View {
   __device__ __forceinline__ int64_t at_padded(int i, int py, int px) const {
     return ((static_cast<int64_t>(i) * hp() + py) * wp() + px) * cs;
   }
+  // 32-bit variants for the streaming kernels (launchers guarantee < 2^31 elements): 3 IMADs instead of 64-bit math
+  __device__ __forceinline__ uint32_t at32(int i, int y, int x) const {
+    return ((static_cast<uint32_t>(i) * hp() + (y + halo)) * wp() + (x + halo)) * cs;
+  }
+  __device__ __forceinline__ uint32_t at_padded32(int i, int py, int px) const {
+    return ((static_cast<uint32_t>(i) * hp() + py) * wp() + px) * cs;
+  }
+};
+
+// (row, col) of a linear pixel index advanced by a constant step without divisions
+struct PixIter {
+  int y, x;
+  __device__ __forceinline__ void init(int p, int w) {
+    y = p / w;
+    x = p - y * w;
+  }
+  __device__ __forceinline__ void advance(int step, int w) {
+    x += step;
+    while (x >= w) {
+      x -= w;
+      ++y;
+    }
+  }
 };
 
 static View view_of(const fpg_act* a) {
@@ -95,42 +118,56 @@ in_stats_kernel(View y, float* __restrict__ partial, float* __restrict__ stats, 
   float s[8], ss[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) s[k] = ss[k] = 0.f;
-  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(y.p);
-  int p = p_begin + pl;
-  for (; p + 3 * lanes < p_end; p += 4 * lanes) {  // four independent 16-byte loads in flight
-    float f[4][8];
+  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(y.p) + g * 8;
+  if (y.halo == 0) {
+    // halo-free tensors (raw conv outputs) are flat [n][h*w][cs]: one pointer, constant stride, no index math
+    const __nv_bfloat16* ptr = base + (static_cast<uint32_t>(i) * hw + p_begin + pl) * static_cast<uint32_t>(y.cs);
+    const uint32_t stride = static_cast<uint32_t>(lanes) * y.cs;
+    int p = p_begin + pl;
+    for (; p + 3 * lanes < p_end; p += 4 * lanes, ptr += 4 * stride) {  // four independent 16-byte loads in flight
+      float f[4][8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int q = p + u * lanes;
-      const int py = q / y.w, px = q - py * y.w;
-      load8(base + y.at(i, py, px) + g * 8, f[u]);
+      for (int u = 0; u < 4; ++u) load8(ptr + u * stride, f[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s[k] += f[u][k];
+          ss[k] += f[u][k] * f[u][k];
+        }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (; p < p_end; p += lanes, ptr += stride) {
+      float f[8];
+      load8(ptr, f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        s[k] += f[u][k];
-        ss[k] += f[u][k] * f[u][k];
+        s[k] += f[k];
+        ss[k] += f[k] * f[k];
       }
-  }
-  for (; p < p_end; p += lanes) {
-    const int py = p / y.w, px = p - py * y.w;
-    float f[8];
-    load8(base + y.at(i, py, px) + g * 8, f);
+    }
+  } else {
+    PixIter it;
+    it.init(p_begin + pl, y.w);
+    for (int p = p_begin + pl; p < p_end; p += lanes, it.advance(lanes, y.w)) {
+      float f[8];
+      load8(base + y.at32(i, it.y, it.x), f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      s[k] += f[k];
-      ss[k] += f[k] * f[k];
+      for (int k = 0; k < 8; ++k) {
+        s[k] += f[k];
+        ss[k] += f[k] * f[k];
+      }
     }
   }
   block_reduce_to_partial(s, ss, G, lanes, partial, i, split, splits, y.c);
   if (!last_cta_of_image(&counters[i], splits)) return;
   for (int ch = threadIdx.x; ch < y.c; ch += kStatThreads) {
     float a = 0.f, b = 0.f;
-    for (int sp = 0; sp < splits; ++sp) {
-      const float* q = partial + ((static_cast<int64_t>(i) * splits + sp) * y.c + ch) * 2;
-      a += q[0];
-      b += q[1];
+    const float2* q = reinterpret_cast<const float2*>(partial + (static_cast<int64_t>(i) * splits * y.c + ch) * 2);
+#pragma unroll 16
+    for (int sp = 0; sp < splits; ++sp) {  // fixed order; unrolled so that 16 loads are in flight
+      const float2 v = __ldcg(q + static_cast<int64_t>(sp) * y.c);
+      a += v.x;
+      b += v.y;
     }
     const float mean = a * inv_hw;
     const float var = fmaxf(b * inv_hw - mean * mean, 0.f);
@@ -175,21 +212,22 @@ in_apply_kernel(View y, const float* __restrict__ stats, int act, View res, int 
   const __nv_bfloat16* yb = static_cast<const __nv_bfloat16*>(y.p) + g * 8;
   const __nv_bfloat16* rb = static_cast<const __nv_bfloat16*>(res.p) + g * 8;
   __nv_bfloat16* zb = static_cast<__nv_bfloat16*>(z.p) + g * 8;
+  PixIter it;
+  it.init(blockIdx.x * chunk + pl, wp);
 #pragma unroll 2
-  for (int p = blockIdx.x * chunk + pl; p < p_end; p += lanes) {
-    const int py = p / wp, px = p - py * wp;
-    const int sy = reflect_idx(py - z.halo, z.h), sx = reflect_idx(px - z.halo, z.w);
+  for (int p = blockIdx.x * chunk + pl; p < p_end; p += lanes, it.advance(lanes, wp)) {
+    const int sy = reflect_idx(it.y - z.halo, z.h), sx = reflect_idx(it.x - z.halo, z.w);
     float f[8], o[8];
-    load8(yb + y.at(i, sy, sx), f);
+    load8(yb + y.at32(i, sy, sx), f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = act_fwd((f[k] - mean[k]) * rstd[k], act);
     if (has_res) {
       float rr[8];
-      load8(rb + res.at(i, sy, sx), rr);
+      load8(rb + res.at32(i, sy, sx), rr);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] += rr[k];
     }
-    store8(zb + z.at_padded(i, py, px), o);
+    store8(zb + z.at_padded32(i, it.y, it.x), o);
   }
 }
 
@@ -200,7 +238,7 @@ __device__ __forceinline__ void folded_grad(const View& dz, int i, int y, int x,
   const int h = dz.halo;
   // interior fast path: no mirrored position lands here
   if (h == 0 || (y > h && y < dz.h - 1 - h && x > h && x < dz.w - 1 - h)) {
-    load8(base + dz.at(i, y, x) + g * 8, acc);
+    load8(base + dz.at32(i, y, x) + g * 8, acc);
     return;
   }
   int rows[3], cols[3], nr = 0, nc = 0;
@@ -215,7 +253,7 @@ __device__ __forceinline__ void folded_grad(const View& dz, int i, int y, int x,
   for (int a = 0; a < nr; ++a)
     for (int b = 0; b < nc; ++b) {
       float f[8];
-      load8(base + dz.at_padded(i, rows[a], cols[b]) + g * 8, f);
+      load8(base + dz.at_padded32(i, rows[a], cols[b]) + g * 8, f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] += f[k];
     }
@@ -245,18 +283,21 @@ in_bwd_reduce_kernel(View dz, View dz2, int has_dz2, View y, const float* __rest
       mean[2 * k] = ms.x; rstd[2 * k] = ms.y; mean[2 * k + 1] = ms.z; rstd[2 * k + 1] = ms.w;
     }
   }
-  for (int p = p_begin + pl; p < p_end; p += lanes) {
-    const int py = p / y.w, px = p - py * y.w;
+  PixIter it;
+  it.init(p_begin + pl, y.w);
+#pragma unroll 2
+  for (int p = p_begin + pl; p < p_end; p += lanes, it.advance(lanes, y.w)) {
+    const int py = it.y, px = it.x;
     float gr[8], yy[8];
     folded_grad(dz, i, py, px, g, gr);
-    load8(static_cast<const __nv_bfloat16*>(y.p) + y.at(i, py, px) + g * 8, yy);
+    load8(static_cast<const __nv_bfloat16*>(y.p) + y.at32(i, py, px) + g * 8, yy);
     if (has_dz2) {
       float e[8];
-      load8(static_cast<const __nv_bfloat16*>(dz2.p) + dz2.at(i, py, px) + g * 8, e);
+      load8(static_cast<const __nv_bfloat16*>(dz2.p) + dz2.at32(i, py, px) + g * 8, e);
 #pragma unroll
       for (int k = 0; k < 8; ++k) gr[k] += e[k];
     }
-    if (has_dres) store8(static_cast<__nv_bfloat16*>(dres.p) + dres.at(i, py, px) + g * 8, gr);
+    if (has_dres) store8(static_cast<__nv_bfloat16*>(dres.p) + dres.at32(i, py, px) + g * 8, gr);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float zh = (yy[k] - mean[k]) * rstd[k];
@@ -269,10 +310,12 @@ in_bwd_reduce_kernel(View dz, View dz2, int has_dz2, View y, const float* __rest
   if (!last_cta_of_image(&counters[i], splits)) return;
   for (int ch = threadIdx.x; ch < y.c; ch += kStatThreads) {
     float a = 0.f, b = 0.f;
-    for (int sp = 0; sp < splits; ++sp) {
-      const float* q = partial + ((static_cast<int64_t>(i) * splits + sp) * y.c + ch) * 2;
-      a += q[0];
-      b += q[1];
+    const float2* q = reinterpret_cast<const float2*>(partial + (static_cast<int64_t>(i) * splits * y.c + ch) * 2);
+#pragma unroll 16
+    for (int sp = 0; sp < splits; ++sp) {  // fixed order; unrolled so that 16 loads are in flight
+      const float2 v = __ldcg(q + static_cast<int64_t>(sp) * y.c);
+      a += v.x;
+      b += v.y;
     }
     red_out[(static_cast<int64_t>(i) * y.c + ch) * 2] = a * inv_hw;
     red_out[(static_cast<int64_t>(i) * y.c + ch) * 2 + 1] = b * inv_hw;
@@ -304,28 +347,31 @@ in_bwd_apply_kernel(View dz, View dz2, int has_dz2, View gsrc, int has_gsrc, Vie
       m1[2 * k] = mr.x; m2[2 * k] = mr.y; m1[2 * k + 1] = mr.z; m2[2 * k + 1] = mr.w;
     }
   }
-  for (int p = blockIdx.x * chunk + pl; p < p_end; p += lanes) {
-    const int py = p / y.w, px = p - py * y.w;
+  PixIter it;
+  it.init(blockIdx.x * chunk + pl, y.w);
+#pragma unroll 2
+  for (int p = blockIdx.x * chunk + pl; p < p_end; p += lanes, it.advance(lanes, y.w)) {
+    const int py = it.y, px = it.x;
     float gr[8], yy[8], o[8];
     if (has_gsrc) {
-      load8(static_cast<const __nv_bfloat16*>(gsrc.p) + gsrc.at(i, py, px) + g * 8, gr);
+      load8(static_cast<const __nv_bfloat16*>(gsrc.p) + gsrc.at32(i, py, px) + g * 8, gr);
     } else {
       folded_grad(dz, i, py, px, g, gr);
       if (has_dz2) {
         float e[8];
-        load8(static_cast<const __nv_bfloat16*>(dz2.p) + dz2.at(i, py, px) + g * 8, e);
+        load8(static_cast<const __nv_bfloat16*>(dz2.p) + dz2.at32(i, py, px) + g * 8, e);
 #pragma unroll
         for (int k = 0; k < 8; ++k) gr[k] += e[k];
       }
     }
-    load8(static_cast<const __nv_bfloat16*>(y.p) + y.at(i, py, px) + g * 8, yy);
+    load8(static_cast<const __nv_bfloat16*>(y.p) + y.at32(i, py, px) + g * 8, yy);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float zh = (yy[k] - mean[k]) * rstd[k];
       const float gp = gr[k] * act_grad(zh, act);
       o[k] = rstd[k] * (gp - m1[k] - zh * m2[k]);
     }
-    store8(static_cast<__nv_bfloat16*>(dy.p) + dy.at(i, py, px) + g * 8, o);
+    store8(static_cast<__nv_bfloat16*>(dy.p) + dy.at32(i, py, px) + g * 8, o);
   }
 }
 
