@@ -312,6 +312,92 @@ static int plan_dgrad(const fpg_act* dy, const void* wt, const float* bias, int 
   return 0;
 }
 
+// Row-stationary plan (igemm_rows.cu). Returns 0 when planned, 1 when the path does not apply.
+static int plan_rows(const fpg_act* a, const void* w, const float* bias, int act, const fpg_conv_geom* g,
+                     const fpg_act* out, int dgrad, int sms, fpg_igemm_rows_desc* d) {
+  FPG_REQUIRE(a && g && out && d, "null argument");
+  if (getenv("FPG_DISABLE_ROWS") != nullptr) return 1;
+  if (g->stride != 1 || g->r * g->s <= 1 || g->r * g->s > FPG_MAX_TAPS) return 1;
+  const int ca = dgrad ? g->c_out : g->c_in;     // channels of the gathered operand
+  const int n_total = dgrad ? g->c_in : g->c_out;  // channels produced
+  if (!(ca == 16 || ca == 32 || ca == 64) || n_total > 128 || n_total % 16 != 0) return 1;
+  FPG_REQUIRE(a->c == ca && out->c == n_total, "channels a %d/%d out %d/%d", a->c, ca, out->c, n_total);
+  int oh, ow;  // output grid
+  if (!dgrad) {
+    FPG_REQUIRE(a->halo == 0 || g->pad == 0, "input halo %d with zero pad %d", a->halo, g->pad);
+    const int hp = a->h + 2 * a->halo, wp = a->w + 2 * a->halo;
+    oh = hp + 2 * g->pad - g->r + 1;
+    ow = wp + 2 * g->pad - g->s + 1;
+    FPG_REQUIRE(oh == out->h && ow == out->w && a->n == out->n, "output %dx%d expected %dx%d", out->h, out->w, oh, ow);
+  } else {
+    FPG_REQUIRE(a->halo == 0, "dy must not have a halo");
+    FPG_REQUIRE(out->halo == 0 || g->pad == 0, "dx halo %d with zero pad %d", out->halo, g->pad);
+    oh = out->h + 2 * out->halo;
+    ow = out->w + 2 * out->halo;
+    FPG_REQUIRE(oh + 2 * g->pad - g->r + 1 == a->h && ow + 2 * g->pad - g->s + 1 == a->w && a->n == out->n,
+                "dy %dx%d does not match dx", a->h, a->w);
+  }
+  if (ow < 96) return 1;
+  memset(d, 0, sizeof(*d));
+  d->cblk = ca;
+  d->block_n = n_total;
+  d->rows = g->r;
+  d->cols = g->s;
+  int th = 256 / n_total;
+  if (th > 4) th = 4;
+  const int64_t tap_bytes = static_cast<int64_t>(n_total) * ca * 2;
+  const int64_t b_row = tap_bytes * g->s;
+  const int64_t a_slot = ((static_cast<int64_t>(128 + g->s - 1) * ca * 2) + 1023) & ~static_cast<int64_t>(1023);
+  const int64_t budget = 210 * 1024;
+  if (b_row * g->r + 3 * a_slot <= budget) {
+    d->b_stages = g->r;  // the whole filter stays in shared memory
+  } else {
+    while (th > 1 && b_row * (th + 1) + 3 * a_slot > budget) --th;
+    if (b_row * (th + 1) + 3 * a_slot > budget) return 1;
+    d->b_stages = th + 1;
+  }
+  d->tile_rows = th;
+  int64_t as = (budget - b_row * d->b_stages) / a_slot;
+  d->a_stages = as > 8 ? 8 : static_cast<int>(as);
+  const int real_taps = g->r * g->s;
+  if (!dgrad) {
+    d->dy0 = -g->pad;
+    d->dx0 = -g->pad;
+    for (int i = 0; i < g->r; ++i)
+      for (int j = 0; j < g->s; ++j) d->tap_of[i * g->s + j] = static_cast<int16_t>(i * g->s + j);
+    d->b.dims[0] = static_cast<uint64_t>(padded_taps(real_taps, ca, ca)) * ca;
+    d->b.base = const_cast<void*>(w);
+    out_view_of(out, 0, &d->out);
+  } else {
+    // dx[p] = sum_{r,s} dy[p + pad - (r,s)] * w[r,s]: ascending offsets run through the filter backwards
+    d->dy0 = g->pad - (g->r - 1);
+    d->dx0 = g->pad - (g->s - 1);
+    for (int i = 0; i < g->r; ++i)
+      for (int j = 0; j < g->s; ++j)
+        d->tap_of[i * g->s + j] = static_cast<int16_t>((g->r - 1 - i) * g->s + (g->s - 1 - j));
+    int64_t k_of[4], off_of[4];
+    int nc = 0;
+    dgrad_class_layout(g, k_of, off_of, &nc);
+    d->b.dims[0] = static_cast<uint64_t>(k_of[0]);
+    d->b.base = const_cast<void*>(w);
+    out_view_of(out, 1, &d->out);
+  }
+  d->b.rank = 2;
+  d->b.swizzle_bytes = ca * 2;
+  d->b.dims[1] = n_total;
+  d->b.strides[0] = d->b.dims[0] * 2;
+  d->b.box[0] = ca;
+  d->b.box[1] = n_total;
+  make_act_view(a, 1, ca, 128 + g->s - 1, 1, &d->a);
+  d->n_img = a->n;
+  d->tiles_x = ceil_div(ow, 128);
+  d->tiles_y = ceil_div(oh, th);
+  d->act = act;
+  d->bias = bias;
+  (void)sms;
+  return 0;
+}
+
 static int largest_divisor_le(int v, int cap) {
   for (int d = cap; d >= 1; --d)
     if (v % d == 0) return d;
@@ -524,7 +610,11 @@ int fpg_conv2d_fprop(const fpg_act* x, const void* w_packed, const float* bias, 
   fpg_igemm_fprop_desc d;
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
-  int rc = plan_fprop(x, w_packed, bias, act, g, y, sms, &d);
+  fpg_igemm_rows_desc rd;
+  int rc = plan_rows(x, w_packed, bias, act, g, y, 0, sms, &rd);
+  if (rc == 0) return fpg_igemm_rows_launch(&rd, stream);
+  if (rc != 1) return rc;
+  rc = plan_fprop(x, w_packed, bias, act, g, y, sms, &d);
   if (rc) return rc;
   return fpg_igemm_fprop_launch(&d, stream);
 }
@@ -541,13 +631,22 @@ int fpg_conv2d_dgrad(const fpg_act* dy, const void* w_packed_t, const float* bia
   int n = 0;
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
-  int rc = plan_dgrad(dy, w_packed_t, bias, act, g, dx, sms, d, &n);
+  fpg_igemm_rows_desc rd;
+  int rc = plan_rows(dy, w_packed_t, bias, act, g, dx, 1, sms, &rd);
+  if (rc == 0) return fpg_igemm_rows_launch(&rd, stream);
+  if (rc != 1) return rc;
+  rc = plan_dgrad(dy, w_packed_t, bias, act, g, dx, sms, d, &n);
   if (rc) return rc;
   for (int q = 0; q < n; ++q) {
     rc = fpg_igemm_fprop_launch(&d[q], stream);
     if (rc) return rc;
   }
   return 0;
+}
+
+int fpg_conv2d_rows_plan(const fpg_act* a, const void* w_packed, const float* bias, int act, const fpg_conv_geom* g,
+                         const fpg_act* out, int dgrad, int sm_count, fpg_igemm_rows_desc* out_desc) {
+  return plan_rows(a, w_packed, bias, act, g, out, dgrad, sm_count, out_desc);
 }
 
 int fpg_conv2d_wgrad_plan(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g, int sm_count,

@@ -36,6 +36,14 @@ class FpropDesc(C.Structure):
                 ("taps", Tap * FPG_MAX_TAPS)]
 
 
+class RowsDesc(C.Structure):
+    _fields_ = [("a", TMap), ("b", TMap), ("cblk", C.c_int32), ("block_n", C.c_int32), ("rows", C.c_int32),
+                ("cols", C.c_int32), ("dy0", C.c_int32), ("dx0", C.c_int32), ("tile_rows", C.c_int32),
+                ("n_img", C.c_int32), ("tiles_y", C.c_int32), ("tiles_x", C.c_int32), ("act", C.c_int32),
+                ("a_stages", C.c_int32), ("b_stages", C.c_int32), ("bias", C.c_void_p), ("out", OutView),
+                ("tap_of", C.c_int16 * FPG_MAX_TAPS)]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [("x", TMap), ("y", TMap), ("x_ca", C.c_int32), ("y_ca", C.c_int32), ("x_atoms", C.c_int32),
                 ("y_atoms", C.c_int32), ("x_groups", C.c_int32), ("y_groups", C.c_int32),
@@ -67,6 +75,9 @@ SIGNATURES = {
     "fpg_sm_count": (C.c_int, []),
     "fpg_igemm_fprop_launch": (C.c_int, [_P(FpropDesc), _vp]),
     "fpg_igemm_wgrad_launch": (C.c_int, [_P(WgradDesc), _vp]),
+    "fpg_igemm_rows_launch": (C.c_int, [_P(RowsDesc), _vp]),
+    "fpg_conv2d_rows_plan": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), C.c_int, C.c_int,
+                                       _P(RowsDesc)]),
     "fpg_conv2d_fprop": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), _vp]),
     "fpg_conv2d_fprop_plan": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), C.c_int, _P(FpropDesc)]),
     "fpg_conv2d_dgrad": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), _vp]),

@@ -112,8 +112,32 @@ typedef struct {
   fpg_tap y_taps[FPG_MAX_TAPS];
 } fpg_igemm_wgrad_desc;
 
+/* Row-stationary implicit GEMM for stride-1 R x S filters on wide images (7x7 stem / heads): a CTA tile is
+ * tile_rows output rows x 128 pixels with one TMEM accumulator per output row. Every input row of the halo patch is
+ * loaded ONCE as a (128 + S - 1)-pixel TMA box and feeds up to tile_rows x S MMAs whose shared-memory descriptors start
+ * at shifted pixel rows of that box (the 128B/64B/32B swizzles are functions of the address, so any pixel-row start is
+ * legal); every filter row of B is loaded once per tile and reused by all accumulators.
+ *   D[(y, x), k] = sum_{i < rows, j < cols, c} A[y + dy0 + i, x + dx0 + j, c] * B[k, tap_of[i*cols + j]*cblk + c]  */
+typedef struct {
+  fpg_tmap a;          /* 5-D stride-1 activation view, box = {cblk, 128 + cols - 1, 1, 1, 1} */
+  fpg_tmap b;          /* weight matrix [block_n rows][num_taps_padded * cblk], K-major: box = {cblk, block_n} */
+  int32_t cblk;        /* channels per tap == channels of A: 16 / 32 / 64 */
+  int32_t block_n;     /* N: multiple of 16, <= 128 */
+  int32_t rows, cols;  /* distinct row / column offsets of the filter (R, S) */
+  int32_t dy0, dx0;    /* smallest row / column offset */
+  int32_t tile_rows;   /* accumulators per tile: 2 * tile_rows * block_n <= 512 */
+  int32_t n_img, tiles_y, tiles_x;
+  int32_t act;
+  int32_t a_stages;    /* ring of input-row slots */
+  int32_t b_stages;    /* ring of filter-row slots; == rows: the whole filter stays resident for the CTA's lifetime */
+  const float* bias;
+  fpg_out_view out;
+  int16_t tap_of[FPG_MAX_TAPS]; /* packed tap index of grid position (i, j) */
+} fpg_igemm_rows_desc;
+
 int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* stream);
 int fpg_igemm_wgrad_launch(const fpg_igemm_wgrad_desc* d, void* stream);
+int fpg_igemm_rows_launch(const fpg_igemm_rows_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Convolution family (replaces nn.Conv2d / nn.ConvTranspose2d forward and aten::convolution_backward;
@@ -158,6 +182,14 @@ int fpg_conv2d_dgrad(const fpg_act* dy, const void* w_packed_t, const float* bia
 int fpg_conv2d_dgrad_plan(const fpg_act* dy, const void* w_packed_t, const float* bias, int act,
                           const fpg_conv_geom* g, const fpg_act* dx, int sm_count, fpg_igemm_fprop_desc* out_descs,
                           int* n_descs);
+
+/* Row-stationary plan of the same operation as fpg_conv2d_fprop (dgrad == 0: a = x, out = y) or fpg_conv2d_dgrad
+ * (dgrad != 0: a = dy, out = dx, w_packed = the dgrad packing). Returns 0 and fills *out_desc when that path applies
+ * (stride 1, filter larger than 1x1, one channel chunk of 16/32/64 on the gathered side, at most 128 channels on the
+ * produced side, at least 96 output columns), 1 when it does not (fpg_conv2d_fprop / _dgrad then use the tiled
+ * kernel), another code on invalid arguments. fpg_conv2d_fprop and fpg_conv2d_dgrad call this first. */
+int fpg_conv2d_rows_plan(const fpg_act* a, const void* w_packed, const float* bias, int act, const fpg_conv_geom* g,
+                         const fpg_act* out, int dgrad, int sm_count, fpg_igemm_rows_desc* out_desc);
 
 /* dw = conv_backward_weight(x, dy): fp32 gradient written (not accumulated) in the reference parameter layout.
  *   dw[ko*dw_stride_k + ci*dw_stride_c + (r*S+s)] for ko < k_valid, ci < c_valid.

@@ -85,6 +85,57 @@ def run_fprop(desc, abuf, bbuf, outbuf, bias=None):
                         outbuf[off:off + n_total] = acc[ry, rx]
 
 
+def run_rows(desc, abuf, bbuf, outbuf, bias=None):
+    """Interpret an fpg_igemm_rows_desc (row-stationary kernel): one (128 + cols - 1)-pixel box per input row of the
+    patch; accumulator `a` of a tile uses input row j as filter row j - a and the column taps as shifted windows of
+    that box."""
+    cblk, bn = desc.cblk, desc.block_n
+    R, S, TH = desc.rows, desc.cols, desc.tile_rows
+    assert 2 * TH * bn <= 512 and int(desc.a.box[1]) == 128 + S - 1 and int(desc.a.box[0]) == cblk
+    assert int(desc.b.box[0]) == cblk and int(desc.b.box[1]) == bn
+    assert desc.b_stages == R or desc.b_stages >= TH + 1
+    smem = (desc.a_stages * (((128 + S - 1) * cblk * 2 + 1023) // 1024 * 1024) + desc.b_stages * S * bn * cblk * 2)
+    assert smem <= 220 * 1024, smem
+    ktot = int(desc.b.dims[0])
+    b_base = (int(desc.b.base or 0) - FAKE_BASE) // 2
+    bmat = bbuf[b_base:b_base + bn * ktot].reshape(bn, ktot)
+    o = desc.out
+    o_base = (int(o.base or 0) - FAKE_BASE) // (4 if o.fp32 else 2)
+    for n in range(desc.n_img):
+        for ty in range(desc.tiles_y):
+            for tx in range(desc.tiles_x):
+                x0, y0 = tx * 128 + desc.dx0, ty * TH + desc.dy0
+                acc = np.zeros((TH, 128, bn), dtype=np.float64)
+                for j in range(TH + R - 1):
+                    row = _tmap_gather(desc.a, abuf, [0, x0, 0, y0 + j, n]).reshape(128 + S - 1, cblk)
+                    for a in range(TH):
+                        r = j - a
+                        if r < 0 or r >= R:
+                            continue
+                        for s in range(S):
+                            t = desc.tap_of[r * S + s]
+                            acc[a] += row[s:s + 128].astype(np.float64) @ bmat[:, t * cblk:(t + 1) * cblk].T
+                if bias is not None:
+                    acc += bias[None, None, :bn]
+                if desc.act == 1:
+                    acc = np.maximum(acc, 0)
+                elif desc.act == 2:
+                    acc = np.where(acc > 0, acc, 0.2 * acc)
+                elif desc.act == 3:
+                    acc = np.tanh(acc)
+                for a in range(TH):
+                    py = ty * TH + a
+                    if py >= o.valid_h:
+                        continue
+                    for rx in range(128):
+                        px = tx * 128 + rx
+                        if px >= o.valid_w:
+                            continue
+                        off = (o_base + n * o.stride_n + (py * o.mul_y + o.off_y) * o.stride_y +
+                               (px * o.mul_x + o.off_x) * o.stride_x)
+                        outbuf[off:off + bn] = acc[a, rx]
+
+
 def run_wgrad(desc, xbuf, ybuf, dw, stride_k, stride_c, k_valid, c_valid):
     """Interpret an fpg_igemm_wgrad_desc including the split reduction and the scatter into dw (flat fp array)."""
     assert desc.tile_h * desc.tile_w == 64

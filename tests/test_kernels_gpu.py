@@ -43,6 +43,11 @@ CONV_CASES = [
     (2, 32, 32, 256, 512, 4, 1, 1, 0),    # model.8 (31x31 output, masked tiles, 2 n-blocks)
     (2, 31, 31, 512, 1, 4, 1, 1, 0),      # model.11 (30x30 output)
     (1, 8, 8, 27, 64, 3, 1, 1, 0),        # 32-channel input (SW64 path)
+    # wide images: the 7x7 layers run on the row-stationary kernel (igemm_rows.cu), fprop and dgrad
+    (3, 42, 256, 9, 64, 7, 1, 0, 3),      # stem at full width: resident filter; 3*2*11 = 66 tiles
+    (2, 130, 256, 64, 27, 7, 1, 0, 3),    # content head: filter-row ring, 132 tiles, ragged last row tile
+    (1, 20, 200, 27, 64, 3, 1, 1, 0),     # zero-padded 3x3 on a ragged width (two column tiles, SW64)
+    (19, 64, 128, 64, 27, 7, 1, 0, 3),    # 304 tiles > 148 SMs: persistent loop over both accumulator stages
 ]
 
 

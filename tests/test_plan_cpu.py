@@ -268,3 +268,72 @@ def test_cta_pair_plans(fpglib, kind):
     out = torch.from_numpy(out).reshape(n, hp, wp, c)
     assert not torch.isnan(out).any()
     torch.testing.assert_close(out.permute(0, 3, 1, 2), ref, rtol=1e-9, atol=1e-9)
+
+
+ROWS_CASES = [
+    # (kind, n, h, w, c_real, c_pad, k_real, k_pad, r, zero_pad, reflect_halo) of the FORWARD conv (stride 1)
+    ("fprop", 1, 6, 100, 9, 16, 64, 64, 7, 0, 3),     # generator stem on a wide image: resident filter, SW32
+    ("fprop", 2, 5, 130, 64, 64, 27, 32, 7, 0, 3),    # content head: two column tiles, filter-row ring
+    ("fprop", 1, 9, 128, 27, 32, 64, 64, 3, 1, 0),    # zero padding: negative offsets / TMA zero fill, SW64
+    ("dgrad", 1, 6, 96, 64, 64, 27, 32, 7, 0, 3),     # content head data gradient incl. halo (dy has 32 channels)
+    ("dgrad", 1, 7, 100, 9, 16, 64, 64, 7, 0, 3),     # stem data gradient (cycle models): N = 16
+    ("dgrad", 1, 10, 120, 64, 64, 32, 32, 3, 1, 0),   # zero-padded 3x3
+]
+
+
+@pytest.mark.parametrize("case", ROWS_CASES)
+def test_rows_plan_matches_torch(fpglib, case):
+    """Row-stationary descriptors (igemm_rows.cu) interpreted on the CPU against conv2d / its input gradient."""
+    kind, n, h, w, c, cp, k, kp, r, pad, halo = case
+    torch.manual_seed(5)
+    xin = torch.randn(n, c, h + 2 * halo, w + 2 * halo, dtype=torch.float64, requires_grad=True)
+    wt = torch.randn(k, c, r, r, dtype=torch.float64)
+    bias = torch.randn(kp, dtype=torch.float64)
+    bias[k:] = 0
+    y = F.conv2d(xin, wt, None, stride=1, padding=pad)
+    ho, wo = y.shape[2:]
+    g = geom(r, r, 1, pad, cp, kp)
+    d = L.RowsDesc()
+    if kind == "fprop":
+        xa, ya = make_act(n, h, w, cp, halo=halo), make_act(n, ho, wo, kp, halo=1)
+        rc = fpglib.fpg_conv2d_rows_plan(C.byref(xa), interp.FAKE_BASE, None, L.ACT_LEAKY, C.byref(g), C.byref(ya), 0,
+                                         SMS, C.byref(d))
+        assert rc == 0
+        abuf = torch.zeros(n, h + 2 * halo, w + 2 * halo, cp, dtype=torch.float64)
+        abuf[..., :c] = xin.detach().permute(0, 2, 3, 1)
+        bbuf = pack_fprop(wt, cp, kp, int(d.b.dims[0]) // cp)
+        assert bbuf.size * 2 == fpglib.fpg_packed_weight_bytes(C.byref(g))
+        out = np.full(n * (ho + 2) * (wo + 2) * kp, np.nan)
+        interp.run_rows(d, abuf.reshape(-1).numpy(), bbuf, out, bias.numpy())
+        out = torch.from_numpy(out).reshape(n, ho + 2, wo + 2, kp)
+        ref = F.leaky_relu(y.detach() + bias[:k].view(1, -1, 1, 1), 0.2)
+        torch.testing.assert_close(out[:, 1:-1, 1:-1, :k].permute(0, 3, 1, 2), ref, rtol=1e-9, atol=1e-9)
+        assert torch.isnan(out[:, 0]).all() and torch.isnan(out[:, :, 0]).all()
+        assert (out[:, 1:-1, 1:-1, k:] == 0).all()
+    else:
+        dy = torch.randn_like(y)
+        (ref,) = torch.autograd.grad(y, xin, dy)
+        dya, dxa = make_act(n, ho, wo, kp), make_act(n, h, w, cp, halo=halo)
+        rc = fpglib.fpg_conv2d_rows_plan(C.byref(dya), interp.FAKE_BASE, None, L.ACT_NONE, C.byref(g), C.byref(dxa), 1,
+                                         SMS, C.byref(d))
+        assert rc == 0
+        hp, wp = h + 2 * halo, w + 2 * halo
+        out = np.full(n * hp * wp * cp, np.nan)
+        interp.run_rows(d, nhwc_buffer(dy, kp), pack_dgrad(fpglib, wt, g), out)
+        out = torch.from_numpy(out).reshape(n, hp, wp, cp)
+        assert not torch.isnan(out).any()
+        torch.testing.assert_close(out[..., :c].permute(0, 3, 1, 2), ref, rtol=1e-9, atol=1e-9)
+        assert (out[..., c:] == 0).all()
+
+
+def test_rows_plan_declines_other_shapes(fpglib):
+    """Narrow images, strided, 1x1 and wide-channel convolutions stay on the tiled kernel (return code 1)."""
+    d = L.RowsDesc()
+    for (h, w, cp, kp, r, stride, pad, halo) in [(64, 64, 64, 64, 3, 1, 0, 1), (256, 256, 16, 64, 4, 2, 1, 0),
+                                                 (256, 256, 64, 16, 1, 1, 0, 0), (128, 128, 128, 64, 3, 1, 1, 0)]:
+        g = geom(r, r, stride, pad, cp, kp)
+        hp, wp = h + 2 * halo, w + 2 * halo
+        ho, wo = (hp + 2 * pad - r) // stride + 1, (wp + 2 * pad - r) // stride + 1
+        xa, ya = make_act(1, h, w, cp, halo=halo), make_act(1, ho, wo, kp)
+        assert fpglib.fpg_conv2d_rows_plan(C.byref(xa), interp.FAKE_BASE, None, 0, C.byref(g), C.byref(ya), 0, SMS,
+                                           C.byref(d)) == 1
