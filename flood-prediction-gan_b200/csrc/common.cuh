@@ -94,6 +94,14 @@ __device__ __forceinline__ void tma_load_5d(const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (TMA engine, no tensor map): dst/src 16-byte aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

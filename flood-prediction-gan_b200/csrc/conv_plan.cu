@@ -348,13 +348,15 @@ static int plan_rows(const fpg_act* a, const void* w, const float* bias, int act
   const int64_t tap_bytes = static_cast<int64_t>(n_total) * ca * 2;
   const int64_t b_row = tap_bytes * g->s;
   const int64_t a_slot = ((static_cast<int64_t>(128 + g->s - 1) * ca * 2) + 1023) & ~static_cast<int64_t>(1023);
-  const int64_t budget = 210 * 1024;
+  const int64_t budget = 222 * 1024;  // of the 227 KB a CTA may use (barriers + 1 KB alignment slack come on top)
   if (b_row * g->r + 3 * a_slot <= budget) {
     d->b_stages = g->r;  // the whole filter stays in shared memory
   } else {
+    // a filter row is released th - 1 steps after its first use: th + 1 slots prefetch ONE row ahead, which does not
+    // cover the L2 latency of a 28 KB row inside one ~0.7 us step; th + 2 does
     while (th > 1 && b_row * (th + 1) + 3 * a_slot > budget) --th;
     if (b_row * (th + 1) + 3 * a_slot > budget) return 1;
-    d->b_stages = th + 1;
+    d->b_stages = b_row * (th + 2) + 3 * a_slot <= budget ? th + 2 : th + 1;
   }
   d->tile_rows = th;
   int64_t as = (budget - b_row * d->b_stages) / a_slot;
@@ -594,6 +596,40 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, __nv_bfloat16
   }
 }
 
+// One launch for every packed operand of a network: block b works on elements [2048 * block_first[b], +2048) of job
+// block_job[b]. Jobs with dst_fp32 != 0 copy an fp32 vector (bias) into a zero-padded fp32 buffer.
+constexpr int kPackChunk = 2048;
+__global__ void __launch_bounds__(256)
+pack_batched_kernel(const fpg_pack_job* __restrict__ jobs, const int32_t* __restrict__ block_job,
+                    const int32_t* __restrict__ block_first) {
+  __shared__ fpg_pack_job job;
+  {
+    const int32_t* src = reinterpret_cast<const int32_t*>(jobs + block_job[blockIdx.x]);
+    int32_t* dst = reinterpret_cast<int32_t*>(&job);
+    for (int i = threadIdx.x; i < static_cast<int>(sizeof(fpg_pack_job) / 4); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int64_t total = static_cast<int64_t>(job.rows) * job.taps * job.cols;
+  const int64_t begin = static_cast<int64_t>(block_first[blockIdx.x]) * kPackChunk;
+#pragma unroll
+  for (int u = 0; u < kPackChunk / 256; ++u) {
+    const int64_t i = begin + u * 256 + threadIdx.x;
+    if (i >= total) break;
+    const int col = static_cast<int>(i % job.cols);
+    const int t = static_cast<int>((i / job.cols) % job.taps);
+    const int row = static_cast<int>(i / (static_cast<int64_t>(job.cols) * job.taps));
+    float v = 0.f;
+    const int st = job.src_tap[t];
+    if (st >= 0 && row < job.rows_valid && col < job.cols_valid)
+      v = job.src[row * job.src_stride_row + col * job.src_stride_col + st];
+    if (job.dst_fp32) {
+      static_cast<float*>(job.dst)[i] = v;
+    } else {
+      static_cast<__nv_bfloat16*>(job.dst)[i] = __float2bfloat16(v);
+    }
+  }
+}
+
 }  // namespace fpg
 
 using namespace fpg;
@@ -779,6 +815,85 @@ int fpg_pack_weights_dgrad(const float* src, int64_t src_stride_k, int64_t src_s
         src, static_cast<__nv_bfloat16*>(dst) + off_of[q], a);
     FPG_CUDA_CHECK(cudaGetLastError());
   }
+  return 0;
+}
+
+int fpg_pack_jobs(const float* src, int64_t src_stride_k, int64_t src_stride_c, int32_t k_valid, int32_t c_valid,
+                  const fpg_conv_geom* g, void* dst_fprop, void* dst_dgrad, fpg_pack_job* jobs, int32_t* n_jobs) {
+  FPG_REQUIRE(src && g && jobs && n_jobs, "null argument");
+  int n = 0;
+  if (dst_fprop != nullptr) {
+    const int cblk = pick_cblk(g->c_in);
+    FPG_REQUIRE(cblk > 0, "unsupported c_in %d", g->c_in);
+    fpg_pack_job* j = &jobs[n++];
+    memset(j, 0, sizeof(*j));
+    j->src = src;
+    j->dst = dst_fprop;
+    j->rows = g->c_out;
+    j->taps = padded_taps(g->r * g->s, g->c_in, cblk);
+    j->cols = g->c_in;
+    j->rows_valid = k_valid;
+    j->cols_valid = c_valid;
+    j->src_stride_row = src_stride_k;
+    j->src_stride_col = src_stride_c;
+    for (int t = 0; t < FPG_MAX_TAPS; ++t) j->src_tap[t] = static_cast<int8_t>(t < g->r * g->s ? t : -1);
+  }
+  if (dst_dgrad != nullptr) {
+    const int cblk = pick_cblk(g->c_out);
+    FPG_REQUIRE(cblk > 0, "unsupported c_out %d", g->c_out);
+    int64_t k_of[4], off_of[4];
+    int nc = 0;
+    dgrad_class_layout(g, k_of, off_of, &nc);
+    for (int q = 0; q < nc; ++q) {
+      int rs[FPG_MAX_TAPS];
+      fpg_tap taps[FPG_MAX_TAPS];
+      const int nt = dgrad_class_taps(g, q >> 1, q & 1, rs, taps);
+      fpg_pack_job* j = &jobs[n++];
+      memset(j, 0, sizeof(*j));
+      j->src = src;
+      j->dst = static_cast<__nv_bfloat16*>(dst_dgrad) + off_of[q];
+      j->rows = g->c_in;
+      j->taps = static_cast<int32_t>(k_of[q] / g->c_out);
+      j->cols = g->c_out;
+      j->rows_valid = c_valid;
+      j->cols_valid = k_valid;
+      j->src_stride_row = src_stride_c;
+      j->src_stride_col = src_stride_k;
+      for (int t = 0; t < FPG_MAX_TAPS; ++t) j->src_tap[t] = static_cast<int8_t>(t < nt ? rs[t] : -1);
+    }
+  }
+  *n_jobs = n;
+  return 0;
+}
+
+int fpg_pack_job_copy_f32(const float* src, int32_t count_valid, float* dst, int32_t count_padded, fpg_pack_job* job) {
+  FPG_REQUIRE(src && dst && job && count_valid <= count_padded, "bad argument");
+  memset(job, 0, sizeof(*job));
+  job->src = src;
+  job->dst = dst;
+  job->rows = 1;
+  job->taps = 1;
+  job->cols = count_padded;
+  job->rows_valid = 1;
+  job->cols_valid = count_valid;
+  job->src_stride_row = 0;
+  job->src_stride_col = 1;
+  job->dst_fp32 = 1;
+  for (int t = 0; t < FPG_MAX_TAPS; ++t) job->src_tap[t] = static_cast<int8_t>(t == 0 ? 0 : -1);
+  return 0;
+}
+
+int32_t fpg_pack_job_blocks(const fpg_pack_job* job) {
+  const int64_t total = static_cast<int64_t>(job->rows) * job->taps * job->cols;
+  return static_cast<int32_t>((total + kPackChunk - 1) / kPackChunk);
+}
+
+int fpg_pack_weights_batched(const fpg_pack_job* jobs_dev, const int32_t* block_job_dev, const int32_t* block_first_dev,
+                             int32_t n_blocks, void* stream) {
+  FPG_REQUIRE(jobs_dev && block_job_dev && block_first_dev && n_blocks > 0, "bad argument");
+  pack_batched_kernel<<<n_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(jobs_dev, block_job_dev,
+                                                                               block_first_dev);
+  FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 

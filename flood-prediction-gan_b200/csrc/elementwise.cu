@@ -1,6 +1,8 @@
 // HBM-bound kernels of the training step: InstanceNorm statistics / apply / backward (with reflect-halo write
 // and fold), attention-content blend forward / backward, loss reductions, Adam, layout packing, flood mask.
 // All activation traffic is NHWC with 128-bit accesses (8 bf16 channels per thread per access).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -67,6 +69,12 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
                                             pack_bf16x2(f[6], f[7]));
 }
+
+__device__ __forceinline__ void cvt8(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 ld16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
 
 // ------------------------------------------------------------------------------------------------ IN statistics
 // grid (splits, n); block 256. thread t owns channel group (t % G), pixel lane (t / G); G = c / 8.
@@ -177,6 +185,117 @@ in_stats_kernel(View y, float* __restrict__ partial, float* __restrict__ stats, 
   if (threadIdx.x == 0) counters[i] = 0;
 }
 
+// ------------------------------------------------------------------------------------------------ bulk-copy ring
+// The streaming kernels below move their inputs with 1-D bulk copies (TMA engine) into a shared-memory ring: one
+// producer warp keeps kRingStages x 16 KB per input tensor in flight per CTA, independent of how many warps are
+// resident -- plain 128-bit loads left these kernels latency bound at ~2 TB/s (ncu: long_scoreboard). 8 consumer
+// warps read the stages from shared memory. A stage holds SP = 16 KB / (2 * c) pixels = 4 pixels per consumer thread.
+constexpr int kRingThreads = 288;  // 8 consumer warps + 1 producer warp
+constexpr int kRingStages = 5;
+constexpr int kRingStageBytes = 16384;
+
+__global__ void __launch_bounds__(kRingThreads, 2)
+in_stats_ring_kernel(View y, float* __restrict__ partial, float* __restrict__ stats, int* __restrict__ counters,
+                     float inv_hw, float eps) {
+  extern __shared__ uint8_t ring_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ring_raw) + 127) & ~uintptr_t(127));
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + kRingStages * kRingStageBytes);
+  uint64_t* empty = full + kRingStages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = y.c / 8;
+  const int lanes = kStatThreads / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  const int i = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+  const int hw = y.h * y.w;
+  const int p_begin = static_cast<int>(static_cast<int64_t>(hw) * split / splits);
+  const int p_end = static_cast<int>(static_cast<int64_t>(hw) * (split + 1) / splits);
+  const int pix_bytes = y.cs * 2;
+  const int SP = kRingStageBytes / pix_bytes;
+  const int nchunks = (p_end - p_begin + SP - 1) / SP;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRingStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  float s[8], ss[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = ss[k] = 0.f;
+  if (warp == 8) {
+    if (lane == 0) {
+      const uint8_t* src = static_cast<const uint8_t*>(y.p) + (static_cast<int64_t>(i) * hw + p_begin) * pix_bytes;
+      for (int k = 0; k < nchunks; ++k) {
+        const int st = k % kRingStages, ph = (k / kRingStages) & 1;
+        mbar_wait(&empty[st], ph ^ 1);
+        const int npx = min(SP, p_end - p_begin - k * SP);
+        const uint32_t bytes = static_cast<uint32_t>(npx) * pix_bytes;
+        mbar_arrive_expect_tx(&full[st], bytes);
+        bulk_load(ring + st * kRingStageBytes, src + static_cast<int64_t>(k) * kRingStageBytes, bytes, &full[st]);
+      }
+    }
+  } else {
+    for (int k = 0; k < nchunks; ++k) {
+      const int st = k % kRingStages, ph = (k / kRingStages) & 1;
+      const int npx = min(SP, p_end - p_begin - k * SP);
+      mbar_wait(&full[st], ph);
+      const uint8_t* sp = ring + st * kRingStageBytes + g * 16;
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int px = pl + u * lanes;
+        v[u] = px < npx ? *reinterpret_cast<const uint4*>(sp + px * pix_bytes) : make_uint4(0, 0, 0, 0);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        cvt8(v[u], f);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
+          s[k2] += f[k2];
+          ss[k2] += f[k2] * f[k2];
+        }
+      }
+    }
+  }
+  // block-level fixed-order reduction (consumer threads only), then the last CTA of the image finalises
+  __shared__ float red[kStatThreads][17];
+  if (threadIdx.x < kStatThreads) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[threadIdx.x][k] = s[k];
+      red[threadIdx.x][8 + k] = ss[k];
+    }
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < G * 16; o += kRingThreads) {
+    const int gg = o / 16, comp = o % 16;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[l * G + gg][comp];
+    const int ch = gg * 8 + (comp & 7);
+    partial[((static_cast<int64_t>(i) * splits + split) * y.c + ch) * 2 + (comp >> 3)] = acc;
+  }
+  if (!last_cta_of_image(&counters[i], splits)) return;
+  for (int ch = threadIdx.x; ch < y.c; ch += kRingThreads) {
+    float a = 0.f, b = 0.f;
+    const float2* q = reinterpret_cast<const float2*>(partial + (static_cast<int64_t>(i) * splits * y.c + ch) * 2);
+#pragma unroll 16
+    for (int sp = 0; sp < splits; ++sp) {
+      const float2 v = __ldcg(q + static_cast<int64_t>(sp) * y.c);
+      a += v.x;
+      b += v.y;
+    }
+    const float mean = a * inv_hw;
+    const float var = fmaxf(b * inv_hw - mean * mean, 0.f);
+    stats[(static_cast<int64_t>(i) * y.c + ch) * 2] = mean;
+    stats[(static_cast<int64_t>(i) * y.c + ch) * 2 + 1] = rsqrtf(var + eps);
+  }
+  if (threadIdx.x == 0) counters[i] = 0;
+}
+
 __device__ __forceinline__ float act_fwd(float v, int act) {
   return act == FPG_ACT_RELU ? fmaxf(v, 0.f) : (act == FPG_ACT_LEAKY ? (v > 0.f ? v : 0.2f * v) : v);
 }
@@ -188,17 +307,17 @@ __device__ __forceinline__ float act_grad(float pre, int act) {
 // grid (chunks, n). Thread t owns channel group (t % G) for its whole life -- the 8 {mean, rstd} pairs are loaded
 // once into registers (reloading them per pixel made L1 the bottleneck: 9x more L1 than DRAM sectors) -- and walks
 // the padded output pixels chunk_begin + (t / G) + k * lanes. A warp covers contiguous 512 B of one or more pixels.
-constexpr int kApplyPixelsPerLane = 16;
+// The grid is sized to ONE wave of resident CTAs (a 1.15-wave grid costs two waves): ppl pixels per pixel lane.
 
 __global__ void __launch_bounds__(256, 4)
-in_apply_kernel(View y, const float* __restrict__ stats, int act, View res, int has_res, View z) {
+in_apply_kernel(View y, const float* __restrict__ stats, int act, View res, int has_res, View z, int ppl) {
   const int G = y.c / 8;
   const int lanes = 256 / G;
   const int g = threadIdx.x % G, pl = threadIdx.x / G;
   const int i = blockIdx.y;
   const int wp = z.wp();
   const int npix = z.hp() * wp;
-  const int chunk = lanes * kApplyPixelsPerLane;
+  const int chunk = lanes * ppl;
   const int p_end = min(npix, (static_cast<int>(blockIdx.x) + 1) * chunk);
   float mean[8], rstd[8];
   {
@@ -327,13 +446,13 @@ in_bwd_reduce_kernel(View dz, View dz2, int has_dz2, View y, const float* __rest
 // Same thread layout as in_apply_kernel (per-thread channel group, statistics in registers).
 __global__ void __launch_bounds__(256, 3)
 in_bwd_apply_kernel(View dz, View dz2, int has_dz2, View gsrc, int has_gsrc, View y, const float* __restrict__ stats,
-                    const float* __restrict__ red, int act, View dy) {
+                    const float* __restrict__ red, int act, View dy, int ppl) {
   const int G = y.c / 8;
   const int lanes = 256 / G;
   const int g = threadIdx.x % G, pl = threadIdx.x / G;
   const int i = blockIdx.y;
   const int npix = y.h * y.w;
-  const int chunk = lanes * kApplyPixelsPerLane;
+  const int chunk = lanes * ppl;
   const int p_end = min(npix, (static_cast<int>(blockIdx.x) + 1) * chunk);
   float mean[8], rstd[8], m1[8], m2[8];
   {
@@ -372,6 +491,301 @@ in_bwd_apply_kernel(View dz, View dz2, int has_dz2, View gsrc, int has_gsrc, Vie
       o[k] = rstd[k] * (gp - m1[k] - zh * m2[k]);
     }
     store8(static_cast<__nv_bfloat16*>(dy.p) + dy.at32(i, py, px) + g * 8, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fused IN backward
+// Both passes in ONE cooperative launch: the CTAs of an image meet at a rendezvous between the reduction and the
+// apply pass, so the second pass re-reads y and g from L2 instead of HBM and one launch + one drain disappear.
+// Images are processed `imgs_per_round` at a time (working set of a round sized to stay L2-resident), ctas_per_img
+// CTAs per image; all CTAs are co-resident (grid <= occupancy x SMs, cooperative launch), which makes the spin legal.
+// sync[i] = arrival counter of image i, sync[kSyncFlags + i] = release flag; both zero on entry and on exit.
+constexpr int kSyncFlags = 2048;
+constexpr int kU = 4;  // pixels per batch of hoisted loads
+
+__global__ void __launch_bounds__(kStatThreads, 2)
+in_bwd_fused_kernel(View dz, View dz2, int has_dz2, View y, const float* __restrict__ stats, int act, View dres,
+                    int has_dres, View dy, float* __restrict__ partial, float* __restrict__ red_out,
+                    int* __restrict__ sync, float inv_hw, int imgs_per_round, int ctas_per_img) {
+  const int G = y.c / 8;
+  const int lanes = kStatThreads / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  const int local = blockIdx.x / ctas_per_img, split = blockIdx.x % ctas_per_img;
+  const int hw = y.h * y.w;
+  const int p_begin = static_cast<int>(static_cast<int64_t>(hw) * split / ctas_per_img);
+  const int p_end = static_cast<int>(static_cast<int64_t>(hw) * (split + 1) / ctas_per_img);
+  __shared__ int s_last;
+  __shared__ float4 s_fin[kStatThreads];
+
+  for (int base = 0; base < y.n; base += imgs_per_round) {
+    const int i = base + local;
+    if (i >= y.n) break;  // uniform per CTA; no CTA of a missing image takes part in a rendezvous
+    float s[8], ss[8], mean[8], rstd[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = ss[k] = 0.f;
+    {
+      const float4* st = reinterpret_cast<const float4*>(stats + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 ms = __ldg(st + k);
+        mean[2 * k] = ms.x; rstd[2 * k] = ms.y; mean[2 * k + 1] = ms.z; rstd[2 * k + 1] = ms.w;
+      }
+    }
+    // ---- pass 1: g = fold(dz) (+ dz2) [-> dres]; partial sums of g' and g' * zhat.
+    // y, dz2, dres and dy are halo-free with one channel stride (checked by the launcher): pixel p of image i sits at
+    // (i * hw + p) * cs. Batches of kU pixels: when none of them touches the mirror band of dz (the common case) all
+    // 2-3 x kU 128-bit loads are issued before any arithmetic -- one pixel's loads in flight leave the loop latency
+    // bound at ~2 TB/s.
+    const uint32_t cs = static_cast<uint32_t>(y.cs);
+    const uint32_t img_off = static_cast<uint32_t>(i) * static_cast<uint32_t>(hw) * cs + g * 8;
+    const __nv_bfloat16* dzb = static_cast<const __nv_bfloat16*>(dz.p) + g * 8;
+    const __nv_bfloat16* yb = static_cast<const __nv_bfloat16*>(y.p) + img_off;
+    const __nv_bfloat16* d2b = static_cast<const __nv_bfloat16*>(dz2.p) + img_off;
+    __nv_bfloat16* drb = static_cast<__nv_bfloat16*>(dres.p) + img_off;
+    __nv_bfloat16* dyb = static_cast<__nv_bfloat16*>(dy.p) + img_off;
+    const int hl = dz.halo;
+    {
+      PixIter it;
+      it.init(p_begin + pl, y.w);
+      int p = p_begin + pl;
+      for (; p + (kU - 1) * lanes < p_end; p += kU * lanes) {
+        uint32_t odz[kU];
+        bool fast = true;
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          odz[u] = dz.at32(i, it.y, it.x);
+          fast = fast && (hl == 0 || (it.y > hl && it.y < dz.h - 1 - hl && it.x > hl && it.x < dz.w - 1 - hl));
+          it.advance(lanes, y.w);
+        }
+        if (fast) {
+          uint4 rg[kU], ry[kU], r2[kU];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            rg[u] = ld16(dzb + odz[u]);
+            ry[u] = ld16(yb + (p + u * lanes) * cs);
+            if (has_dz2) r2[u] = ld16(d2b + (p + u * lanes) * cs);
+          }
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            float gr[8], yy[8];
+            cvt8(rg[u], gr);
+            cvt8(ry[u], yy);
+            if (has_dz2) {
+              float e[8];
+              cvt8(r2[u], e);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) gr[k] += e[k];
+            }
+            if (has_dres) store8(drb + (p + u * lanes) * cs, gr);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float zh = (yy[k] - mean[k]) * rstd[k];
+              const float gp = gr[k] * act_grad(zh, act);
+              s[k] += gp;
+              ss[k] += gp * zh;
+            }
+          }
+        } else {
+          PixIter jt;
+          jt.init(p, y.w);
+          for (int u = 0; u < kU; ++u, jt.advance(lanes, y.w)) {
+            float gr[8], yy[8];
+            folded_grad(dz, i, jt.y, jt.x, g, gr);
+            load8(yb + (p + u * lanes) * cs, yy);
+            if (has_dz2) {
+              float e[8];
+              load8(d2b + (p + u * lanes) * cs, e);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) gr[k] += e[k];
+            }
+            if (has_dres) store8(drb + (p + u * lanes) * cs, gr);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float zh = (yy[k] - mean[k]) * rstd[k];
+              const float gp = gr[k] * act_grad(zh, act);
+              s[k] += gp;
+              ss[k] += gp * zh;
+            }
+          }
+        }
+      }
+      for (; p < p_end; p += lanes, it.advance(lanes, y.w)) {
+        float gr[8], yy[8];
+        folded_grad(dz, i, it.y, it.x, g, gr);
+        load8(yb + p * cs, yy);
+        if (has_dz2) {
+          float e[8];
+          load8(d2b + p * cs, e);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) gr[k] += e[k];
+        }
+        if (has_dres) store8(drb + p * cs, gr);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float zh = (yy[k] - mean[k]) * rstd[k];
+          const float gp = gr[k] * act_grad(zh, act);
+          s[k] += gp;
+          ss[k] += gp * zh;
+        }
+      }
+    }
+    block_reduce_to_partial(s, ss, G, lanes, partial, local, split, ctas_per_img, y.c);
+    // ---- rendezvous of the image's CTAs; the last one to arrive reduces the partials in a fixed order
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(&sync[i], 1) == ctas_per_img - 1;
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const int F4 = y.c / 2;                 // float4 per partial row (2 * c floats)
+      const int P = kStatThreads / F4;        // rows summed in parallel
+      const int col = threadIdx.x % F4, par = threadIdx.x / F4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (par < P) {
+        const float4* rows = reinterpret_cast<const float4*>(partial) +
+                             static_cast<int64_t>(local) * ctas_per_img * F4 + col;
+#pragma unroll 8
+        for (int sp = par; sp < ctas_per_img; sp += P) {
+          const float4 v = __ldcg(rows + static_cast<int64_t>(sp) * F4);
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+      s_fin[threadIdx.x] = acc;
+      __syncthreads();
+      if (threadIdx.x < F4) {
+        float4 t = s_fin[threadIdx.x];
+        for (int q = 1; q < P; ++q) {
+          const float4 v = s_fin[q * F4 + threadIdx.x];
+          t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+        }
+        reinterpret_cast<float4*>(red_out)[static_cast<int64_t>(i) * F4 + threadIdx.x] =
+            make_float4(t.x * inv_hw, t.y * inv_hw, t.z * inv_hw, t.w * inv_hw);
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) atomicExch(&sync[kSyncFlags + i], 1);
+    } else {
+      if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        while (atomicAdd(&sync[kSyncFlags + i], 0) == 0) {
+          __nanosleep(64);
+          if (clock64() - t0 > 4000000000LL) {
+            printf("fpg: instnorm rendezvous timed out (block %d image %d)\n", blockIdx.x, i);
+            __trap();
+          }
+        }
+      }
+      __syncthreads();
+    }
+    __threadfence();
+    if (threadIdx.x == 0) {  // the last CTA to leave resets the counters for the next launch
+      if (atomicAdd(&sync[i], 1) == 2 * ctas_per_img - 1) {
+        sync[kSyncFlags + i] = 0;
+        __threadfence();
+        sync[i] = 0;
+      }
+    }
+    // ---- pass 2: dy = rstd * (g' - mean(g') - zhat * mean(g' zhat)) over the same pixels (L2-resident re-read)
+    float m1[8], m2[8];
+    {
+      const float4* rd = reinterpret_cast<const float4*>(red_out + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float4 mr = __ldcg(rd + k);
+        m1[2 * k] = mr.x; m2[2 * k] = mr.y; m1[2 * k + 1] = mr.z; m2[2 * k + 1] = mr.w;
+      }
+    }
+    {
+      PixIter it;
+      it.init(p_begin + pl, y.w);
+      int p = p_begin + pl;
+      const bool need_dz = !has_dres;
+      for (; p + (kU - 1) * lanes < p_end; p += kU * lanes) {
+        uint32_t odz[kU];
+        bool fast = true;
+        if (need_dz) {
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            odz[u] = dz.at32(i, it.y, it.x);
+            fast = fast && (hl == 0 || (it.y > hl && it.y < dz.h - 1 - hl && it.x > hl && it.x < dz.w - 1 - hl));
+            it.advance(lanes, y.w);
+          }
+        }
+        if (fast) {
+          uint4 rg[kU], ry[kU], r2[kU];
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            rg[u] = need_dz ? ld16(dzb + odz[u]) : ld16(drb + (p + u * lanes) * cs);
+            ry[u] = ld16(yb + (p + u * lanes) * cs);
+            if (need_dz && has_dz2) r2[u] = ld16(d2b + (p + u * lanes) * cs);
+          }
+#pragma unroll
+          for (int u = 0; u < kU; ++u) {
+            float gr[8], yy[8], o[8];
+            cvt8(rg[u], gr);
+            cvt8(ry[u], yy);
+            if (need_dz && has_dz2) {
+              float e[8];
+              cvt8(r2[u], e);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) gr[k] += e[k];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float zh = (yy[k] - mean[k]) * rstd[k];
+              const float gp = gr[k] * act_grad(zh, act);
+              o[k] = rstd[k] * (gp - m1[k] - zh * m2[k]);
+            }
+            store8(dyb + (p + u * lanes) * cs, o);
+          }
+        } else {
+          PixIter jt;
+          jt.init(p, y.w);
+          for (int u = 0; u < kU; ++u, jt.advance(lanes, y.w)) {
+            float gr[8], yy[8], o[8];
+            folded_grad(dz, i, jt.y, jt.x, g, gr);
+            if (has_dz2) {
+              float e[8];
+              load8(d2b + (p + u * lanes) * cs, e);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) gr[k] += e[k];
+            }
+            load8(yb + (p + u * lanes) * cs, yy);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float zh = (yy[k] - mean[k]) * rstd[k];
+              const float gp = gr[k] * act_grad(zh, act);
+              o[k] = rstd[k] * (gp - m1[k] - zh * m2[k]);
+            }
+            store8(dyb + (p + u * lanes) * cs, o);
+          }
+        }
+      }
+      if (!need_dz) it.init(p, y.w);
+      for (; p < p_end; p += lanes, it.advance(lanes, y.w)) {
+        float gr[8], yy[8], o[8];
+        if (has_dres) {
+          load8(drb + p * cs, gr);
+        } else {
+          folded_grad(dz, i, it.y, it.x, g, gr);
+          if (has_dz2) {
+            float e[8];
+            load8(d2b + p * cs, e);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gr[k] += e[k];
+          }
+        }
+        load8(yb + p * cs, yy);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float zh = (yy[k] - mean[k]) * rstd[k];
+          const float gp = gr[k] * act_grad(zh, act);
+          o[k] = rstd[k] * (gp - m1[k] - zh * m2[k]);
+        }
+        store8(dyb + p * cs, o);
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -454,13 +868,15 @@ __global__ void bias_grad_partial_kernel(View dy, float* __restrict__ partial) {
     partial[static_cast<int64_t>(blockIdx.x) * dy.c + gg * 8 + comp] = acc;
   }
 }
+// one warp per channel: lanes stride over the partials, fixed shuffle tree -> deterministic
 __global__ void bias_grad_finalize_kernel(const float* __restrict__ partial, float* __restrict__ db, int c, int k_valid,
                                           int nblocks) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (ch >= k_valid) return;
   float acc = 0.f;
-  for (int b = 0; b < nblocks; ++b) acc += partial[static_cast<int64_t>(b) * c + ch];
-  db[ch] = acc;
+  for (int b = threadIdx.x & 31; b < nblocks; b += 32) acc += partial[static_cast<int64_t>(b) * c + ch];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) db[ch] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------ blend
@@ -707,7 +1123,19 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int c_src, View 
   __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(dst.p) + dst.at_padded(i, py, px);
   const int64_t hw = static_cast<int64_t>(dst.h) * dst.w;
   const float* sp = src + static_cast<int64_t>(i) * c_src * hw + static_cast<int64_t>(sy) * dst.w + sx;
-  if (zero_rest) {
+  if (zero_rest && dst.c == 16) {
+    // the whole 16-channel pixel is assembled in registers and written with two 128-bit stores
+    float f[16];
+#pragma unroll
+    for (int ch = 0; ch < 16; ++ch) {
+      const int sc = ch - c0;
+      f[ch] = (sc >= 0 && sc < c_src) ? __ldg(sp + sc * hw) : 0.f;
+    }
+    uint4* d4 = reinterpret_cast<uint4*>(dp);
+    d4[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    d4[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                       pack_bf16x2(f[14], f[15]));
+  } else if (zero_rest) {
     for (int ch = 0; ch < dst.c; ++ch) {
       const int sc = ch - c0;
       dp[ch] = __float2bfloat16((sc >= 0 && sc < c_src) ? sp[sc * hw] : 0.f);
@@ -821,12 +1249,35 @@ __global__ void confusion_kernel(const float* __restrict__ pred, const float* __
   }
 }
 
+// CTAs of `kernel` that are resident at once on the whole device (occupancy x SM count), cached per kernel
+template <typename K>
+static int resident_ctas(K kernel, int threads) {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 1;
+  }
+  const int sms = sm_count_cached();
+  cached = per_sm * (sms > 0 ? sms : 1);
+  return cached;
+}
+
+// pixels per pixel lane such that n images x ceil(npix / (lanes * ppl)) CTAs fit one wave of `slots` CTAs
+static int pixels_per_lane(int64_t npix, int lanes, int n, int slots) {
+  int per_image = slots / n;
+  if (per_image < 1) per_image = 1;
+  int64_t ppl = (npix + static_cast<int64_t>(per_image) * lanes - 1) / (static_cast<int64_t>(per_image) * lanes);
+  if (ppl < 4) ppl = 4;
+  return static_cast<int>(ppl);
+}
+
 static unsigned grid_for(int64_t total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
 
-static int stat_splits(const fpg_act* y, int sms) {
-  // ~8 resident CTAs per SM (the loops are latency-bound: parallelism hides it), at most 64 splits per image
-  // (scratch bound), at least 64 pixels per split
-  int splits = (8 * sms + y->n - 1) / y->n;
+static int stat_splits(const fpg_act* y, int slots) {
+  // one wave of resident CTAs, at most 64 splits per image (scratch bound), at least 64 pixels per split
+  int splits = slots / y->n;
   if (splits > 64) splits = 64;
   const int hw = y->h * y->w;
   while (splits > 1 && hw / splits < 64) splits /= 2;
@@ -842,14 +1293,31 @@ using namespace fpg;
 
 extern "C" {
 
-int64_t fpg_instnorm_scratch_floats(const fpg_act* y) { return static_cast<int64_t>(y->n) * 64 * y->c * 2 + static_cast<int64_t>(y->n) * y->c * 2; }
+int64_t fpg_instnorm_scratch_floats(const fpg_act* y) {
+  return static_cast<int64_t>(y->n > 16 ? y->n * 64 : 1024) * y->c * 2 + static_cast<int64_t>(y->n) * y->c * 2;
+}
 
 int fpg_instnorm_stats(const fpg_act* y, float eps, float* stats, float* scratch, int32_t* counters, void* stream) {
   FPG_REQUIRE(y && stats && scratch && counters, "null argument");
   FPG_REQUIRE(y->c % 8 == 0 && kStatThreads % (y->c / 8) == 0, "instnorm channels %d", y->c);
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
-  const int splits = stat_splits(y, sms);
+  static const bool no_ring = getenv("FPG_NO_RING") != nullptr;
+  if (!no_ring && y->halo == 0 && y->c == y->c_stride && kRingStageBytes % (y->c_stride * 2) == 0) {
+    const size_t smem = kRingStages * kRingStageBytes + 2 * kRingStages * 8 + 128;
+    static bool attr_set = false;
+    if (!attr_set) {
+      FPG_CUDA_CHECK(cudaFuncSetAttribute(in_stats_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+      attr_set = true;
+    }
+    const int splits = stat_splits(y, 2 * sms);
+    in_stats_ring_kernel<<<dim3(splits, y->n), kRingThreads, smem, FPG_ST(stream)>>>(
+        view_of(y), scratch, stats, counters, 1.f / static_cast<float>(y->h * y->w), eps);
+    FPG_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
+  const int splits = stat_splits(y, resident_ctas(in_stats_kernel, kStatThreads));
   in_stats_kernel<<<dim3(splits, y->n), kStatThreads, 0, FPG_ST(stream)>>>(
       view_of(y), scratch, stats, counters, 1.f / static_cast<float>(y->h * y->w), eps);
   FPG_CUDA_CHECK(cudaGetLastError());
@@ -864,9 +1332,10 @@ int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_
   View rv = residual ? view_of(residual) : view_of(y);
   FPG_REQUIRE(256 % (y->c / 8) == 0, "instnorm channels %d", y->c);
   const int64_t npix = static_cast<int64_t>(z->h + 2 * z->halo) * (z->w + 2 * z->halo);
-  const int chunk = (256 / (y->c / 8)) * kApplyPixelsPerLane;
-  in_apply_kernel<<<dim3(grid_for(npix, chunk), y->n), 256, 0, FPG_ST(stream)>>>(
-      view_of(y), stats, act, rv, residual != nullptr, view_of(z));
+  const int lanes = 256 / (y->c / 8);
+  const int ppl = pixels_per_lane(npix, lanes, y->n, resident_ctas(in_apply_kernel, 256));
+  in_apply_kernel<<<dim3(grid_for(npix, lanes * ppl), y->n), 256, 0, FPG_ST(stream)>>>(
+      view_of(y), stats, act, rv, residual != nullptr, view_of(z), ppl);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -876,18 +1345,54 @@ int fpg_instnorm_bwd(const fpg_act* dz, const fpg_act* dz2, const fpg_act* y, co
   FPG_REQUIRE(dz && y && stats && dy && scratch && counters, "null argument");
   FPG_REQUIRE(y->c % 8 == 0 && kStatThreads % (y->c / 8) == 0, "instnorm channels %d", y->c);
   FPG_REQUIRE(dz->h == y->h && dz->w == y->w && dz->c == y->c && dy->h == y->h && dy->c == y->c, "geometry mismatch");
+  FPG_REQUIRE(y->n <= kSyncFlags, "batch %d", y->n);
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
-  const int splits = stat_splits(y, sms);
   View v2 = dz2 ? view_of(dz2) : view_of(dz);
   View vr = dres ? view_of(dres) : view_of(dz);
-  float* red = scratch + static_cast<int64_t>(y->n) * 64 * y->c * 2;
+  float* red = scratch + static_cast<int64_t>(y->n > 16 ? y->n * 64 : 1024) * y->c * 2;
+  const float inv_hw = 1.f / static_cast<float>(y->h * y->w);
+  static const bool split_launch = getenv("FPG_IN_BWD_FUSED") == nullptr;  // measured: the rendezvous costs what the L2 re-read saves
+  // the fused kernel addresses y, dz2, dres and dy as flat halo-free [n][h*w][c_stride] tensors
+  const bool flat = y->halo == 0 && dy->halo == 0 && dy->c_stride == y->c_stride && dy->w == y->w &&
+                    (!dz2 || (dz2->halo == 0 && dz2->c_stride == y->c_stride)) &&
+                    (!dres || (dres->halo == 0 && dres->c_stride == y->c_stride)) &&
+                    static_cast<int64_t>(y->n) * y->h * y->w * y->c_stride < (1ll << 31);
+  if (!split_launch && flat) {
+    // one cooperative launch: rounds of imgs_per_round images whose working set (~64 MB) stays in L2
+    const int slots = resident_ctas(in_bwd_fused_kernel, kStatThreads) < 1024
+                          ? resident_ctas(in_bwd_fused_kernel, kStatThreads) : 1024;
+    const int64_t hw = static_cast<int64_t>(y->h) * y->w;
+    const int64_t img_bytes = hw * y->c * 2 * (2 + (dz2 != nullptr) + (dres != nullptr));
+    int ipr = static_cast<int>((64ll << 20) / img_bytes);
+    if (ipr < 1) ipr = 1;
+    if (ipr > y->n) ipr = y->n;
+    if (ipr > slots) ipr = slots;
+    const int rounds = (y->n + ipr - 1) / ipr;
+    ipr = (y->n + rounds - 1) / rounds;
+    int cpi = slots / ipr;
+    if (cpi > hw / 64) cpi = static_cast<int>(hw / 64 > 0 ? hw / 64 : 1);
+    View a_dz = view_of(dz), a_y = view_of(y), a_dy = view_of(dy);
+    int has2 = dz2 != nullptr, hasr = dres != nullptr, a_act = act, a_ipr = ipr, a_cpi = cpi;
+    float a_inv = inv_hw;
+    float* a_partial = scratch;
+    float* a_red = red;
+    int* a_sync = counters;
+    const float* a_stats = stats;
+    void* params[] = {&a_dz, &v2, &has2, &a_y, &a_stats, &a_act, &vr, &hasr, &a_dy, &a_partial, &a_red, &a_sync,
+                      &a_inv, &a_ipr, &a_cpi};
+    FPG_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(in_bwd_fused_kernel), dim3(ipr * cpi),
+                                               dim3(kStatThreads), params, 0, FPG_ST(stream)));
+    return 0;
+  }
+  const int splits = stat_splits(y, resident_ctas(in_bwd_reduce_kernel, kStatThreads));
   in_bwd_reduce_kernel<<<dim3(splits, y->n), kStatThreads, 0, FPG_ST(stream)>>>(
-      view_of(dz), v2, dz2 != nullptr, view_of(y), stats, act, vr, dres != nullptr, scratch, red, counters,
-      1.f / static_cast<float>(y->h * y->w));
-  const int chunk = (256 / (y->c / 8)) * kApplyPixelsPerLane;
-  in_bwd_apply_kernel<<<dim3(grid_for(static_cast<int64_t>(y->h) * y->w, chunk), y->n), 256, 0, FPG_ST(stream)>>>(
-      view_of(dz), v2, dz2 != nullptr, vr, dres != nullptr, view_of(y), stats, red, act, view_of(dy));
+      view_of(dz), v2, dz2 != nullptr, view_of(y), stats, act, vr, dres != nullptr, scratch, red, counters, inv_hw);
+  const int lanes = 256 / (y->c / 8);
+  const int64_t npix = static_cast<int64_t>(y->h) * y->w;
+  const int ppl = pixels_per_lane(npix, lanes, y->n, resident_ctas(in_bwd_apply_kernel, 256));
+  in_bwd_apply_kernel<<<dim3(grid_for(npix, lanes * ppl), y->n), 256, 0, FPG_ST(stream)>>>(
+      view_of(dz), v2, dz2 != nullptr, vr, dres != nullptr, view_of(y), stats, red, act, view_of(dy), ppl);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -915,7 +1420,7 @@ int fpg_bias_grad(const fpg_act* dy, float* db, int32_t k_valid, float* scratch,
   int blocks = kBiasBlocks;
   if (npix / blocks < 64) blocks = static_cast<int>(npix / 64 > 0 ? npix / 64 : 1);
   bias_grad_partial_kernel<<<blocks, kStatThreads, 0, FPG_ST(stream)>>>(view_of(dy), scratch);
-  bias_grad_finalize_kernel<<<(k_valid + 127) / 128, 128, 0, FPG_ST(stream)>>>(scratch, db, dy->c, k_valid, blocks);
+  bias_grad_finalize_kernel<<<(k_valid + 7) / 8, 256, 0, FPG_ST(stream)>>>(scratch, db, dy->c, k_valid, blocks);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

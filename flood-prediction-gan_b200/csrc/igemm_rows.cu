@@ -9,7 +9,13 @@
 //     shared-memory rows addressed through descriptors that start s pixel rows later (the swizzle is a function of the
 //     shared-memory address, so a descriptor may start at any pixel row of a TMA-written box: tools/exp/desc_shift.cu);
 //   * every filter row of B (S taps x N x CBLK) is loaded once per tile and used by all TH accumulators; if the whole
-//     filter fits next to the A ring it is loaded once per CTA.
+//     filter fits next to the A ring it is loaded once per CTA;
+//   * a shared-memory-operand tcgen05.mma of K = 16 costs max(N/2, 32 + N/4) cycles (tools/exp/mma_rate.cu: the
+//     128 x 16 A slice and the N x 16 B slice are read at 128 B/clk), so N = 32 or 64 MMAs run at 40 / 67 % of the
+//     tensor peak. The accumulators that share an A window (input row j, column tap s) are therefore STACKED along N:
+//     they sit at consecutive TMEM columns, and filter rows r = j - a are kept at consecutive (descending-r) slots of
+//     a per-column-tap ring, so ONE MMA with N = (#accumulators) x block_n serves all of them (two where the ring
+//     wraps). A tile starts with one MMA against an all-zero B that clears every accumulator; all others accumulate.
 // Warp roles as in igemm.cu: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue.
 #include "common.cuh"
 #include "host_util.h"
@@ -53,12 +59,14 @@ igemm_rows_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
   const int BN = args.block_n;
   const int R = args.rows, S = args.cols, TH = args.tile_rows;
   const int ASTG = args.a_stages, BSTG = args.b_stages;
-  const uint32_t B_SLOT_BYTES = args.b_tap_bytes * static_cast<uint32_t>(S);
+  const uint32_t B_SLOT_BYTES = args.b_tap_bytes * static_cast<uint32_t>(S);     // one filter row (all column taps)
+  const uint32_t B_COL_BYTES = args.b_tap_bytes * static_cast<uint32_t>(BSTG);  // ring of one column tap
   const uint32_t ACC_COLS = static_cast<uint32_t>(TH * BN);
 
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + ASTG * args.a_slot_bytes;
-  uint64_t* full_a = reinterpret_cast<uint64_t*>(smem_b + BSTG * B_SLOT_BYTES);
+  uint8_t* smem_z = smem_b + BSTG * B_SLOT_BYTES;  // 1 KB of zeros: B operand that clears the accumulators
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(smem_z + 1024);
   uint64_t* empty_a = full_a + ASTG;
   uint64_t* full_b = empty_a + ASTG;
   uint64_t* empty_b = full_b + BSTG;
@@ -88,6 +96,8 @@ igemm_rows_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
     tma_prefetch_desc(&amap);
     tma_prefetch_desc(&bmap);
   }
+  for (int i = threadIdx.x; i < 256; i += kRowsThreads) reinterpret_cast<uint32_t*>(smem_z)[i] = 0u;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy zeros visible to the tensor core
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -112,9 +122,10 @@ igemm_rows_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
           if (j < R && (first || !args.b_resident)) {
             mbar_wait(&empty_b[bs], bph ^ 1);
             mbar_arrive_expect_tx(&full_b[bs], B_SLOT_BYTES);
-            uint8_t* dst = smem_b + bs * B_SLOT_BYTES;
+            // filter rows sit in DESCENDING order inside each column tap's ring: data slot = BSTG - 1 - ring index
+            uint8_t* dst = smem_b + (BSTG - 1 - bs) * args.b_tap_bytes;
             for (int s = 0; s < S; ++s)
-              tma_load_2d(&bmap, &full_b[bs], dst + s * args.b_tap_bytes, args.tap_of[j * S + s] * CBLK, 0);
+              tma_load_2d(&bmap, &full_b[bs], dst + s * B_COL_BYTES, args.tap_of[j * S + s] * CBLK, 0);
             if (++bs == static_cast<uint32_t>(BSTG)) {
               bs = 0;
               bph ^= 1;
@@ -134,8 +145,10 @@ igemm_rows_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      const uint32_t idesc1 = make_idesc_bf16(128, BN, 0, 0);  // N field scaled up for stacked accumulators
       const uint64_t desc_hi = make_smem_desc(0, 0, SBO, LAYOUT);  // everything but the start address
+      const uint64_t zdesc = make_smem_desc(smem_u32(smem_z), 0, 0, LAYOUT);
+      const uint32_t b_lo = (smem_u32(smem_b) >> 4) & 0x3FFFu;
       uint32_t as = 0, aph = 0, it = 0;
       uint32_t bcount = 0;  // filter rows consumed before this tile (ring position of filter row 0)
       bool first = true;
@@ -152,20 +165,43 @@ igemm_rows_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
           }
           tc_fence_after();
           const uint32_t a_lo = (smem_u32(smem_a + as * args.a_slot_bytes) >> 4) & 0x3FFFu;
-          const int a_hi = j < TH - 1 ? j : TH - 1;       // accumulators that use this input row: r = j - a in [0, R)
-          const int a_lo_i = j - (R - 1) > 0 ? j - (R - 1) : 0;
-          for (int a = a_lo_i; a <= a_hi; ++a) {
-            const int r = j - a;
-            const uint32_t bslot = args.b_resident ? static_cast<uint32_t>(r) : (bcount + r) % BSTG;
-            const uint32_t b_lo = (smem_u32(smem_b + bslot * B_SLOT_BYTES) >> 4) & 0x3FFFu;
-            const uint32_t d_acc = d_tmem + a * BN;
+          if (j == 0) {
+            // zero all TH accumulators with one MMA against the all-zero B region (8 aliased rows: SBO = 0), so that
+            // every other MMA of the tile accumulates and the stacked issue loop below has no special cases
+            umma_bf16(d_tmem, desc_hi | static_cast<uint64_t>(a_lo), zdesc,
+                      idesc1 + (static_cast<uint32_t>((TH - 1) * BN >> 3) << 17), 0u);
+          }
+          // accumulators using this input row: a in [a0, a1], filter row r = j - a. Stacked along N in order of a,
+          // i.e. descending r == ascending data slots starting at the slot of r = j - a0; a second MMA covers the
+          // part of the stack that wraps around the ring.
+          const int a1 = j < TH - 1 ? j : TH - 1;
+          const int a0 = j - (R - 1) > 0 ? j - (R - 1) : 0;
+          const int n_acc = a1 - a0 + 1;
+          const uint32_t ring0 = args.b_resident ? static_cast<uint32_t>(j - a0) : (bcount + (j - a0)) % BSTG;
+          const uint32_t slot0 = BSTG - 1 - ring0;
+          const int seg1 = n_acc < static_cast<int>(BSTG - slot0) ? n_acc : static_cast<int>(BSTG - slot0);
+          const int seg2 = n_acc - seg1;
+          const uint32_t d1 = d_tmem + a0 * BN, d2 = d_tmem + (a0 + seg1) * BN;
+          const uint32_t id1 = idesc1 + (static_cast<uint32_t>((seg1 - 1) * BN >> 3) << 17);
+          const uint32_t id2 = idesc1 + (static_cast<uint32_t>((seg2 > 0 ? seg2 - 1 : 0) * BN >> 3) << 17);
+          const uint32_t b_off1 = b_lo + ((slot0 * args.b_tap_bytes) >> 4);
+          const uint32_t b_col16 = B_COL_BYTES >> 4;
+          if (seg2 == 0) {
             for (int s = 0; s < S; ++s) {
-              const uint32_t a_s = a_lo + ((s * PIX_BYTES) >> 4);
-              const uint32_t b_s = b_lo + ((s * args.b_tap_bytes) >> 4);
+              const uint32_t a_s = a_lo + s * (PIX_BYTES >> 4), b_s = b_off1 + s * b_col16;
+#pragma unroll
+              for (int k = 0; k < CBLK / 16; ++k)
+                umma_bf16(d1, desc_hi | static_cast<uint64_t>(a_s + 2 * k), desc_hi | static_cast<uint64_t>(b_s + 2 * k),
+                          id1, 1u);
+            }
+          } else {
+            for (int s = 0; s < S; ++s) {
+              const uint32_t a_s = a_lo + s * (PIX_BYTES >> 4), b_s = b_off1 + s * b_col16, b_w = b_lo + s * b_col16;
 #pragma unroll
               for (int k = 0; k < CBLK / 16; ++k) {
-                umma_bf16(d_acc, desc_hi | static_cast<uint64_t>(a_s + 2 * k), desc_hi | static_cast<uint64_t>(b_s + 2 * k),
-                          idesc, (r | s | k) != 0 ? 1u : 0u);
+                const uint64_t ad = desc_hi | static_cast<uint64_t>(a_s + 2 * k);
+                umma_bf16(d1, ad, desc_hi | static_cast<uint64_t>(b_s + 2 * k), id1, 1u);
+                umma_bf16(d2, ad, desc_hi | static_cast<uint64_t>(b_w + 2 * k), id2, 1u);
               }
             }
           }
@@ -294,7 +330,7 @@ extern "C" int fpg_igemm_rows_launch(const fpg_igemm_rows_desc* d, void* stream)
 
   const size_t smem = static_cast<size_t>(d->a_stages) * args.a_slot_bytes +
                       static_cast<size_t>(d->b_stages) * d->cols * args.b_tap_bytes +
-                      (2 * d->a_stages + 2 * d->b_stages + 4) * 8 + 16 + 1024;
+                      1024 + (2 * d->a_stages + 2 * d->b_stages + 4) * 8 + 16 + 1024;
   FPG_REQUIRE(smem <= 227 * 1024, "shared memory %zu", smem);
   const int total_tiles = d->n_img * d->tiles_y * d->tiles_x;
   const int sms = sm_count_cached();

@@ -44,6 +44,12 @@ class RowsDesc(C.Structure):
                 ("tap_of", C.c_int16 * FPG_MAX_TAPS)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int32), ("taps", C.c_int32),
+                ("cols", C.c_int32), ("rows_valid", C.c_int32), ("cols_valid", C.c_int32), ("dst_fp32", C.c_int32),
+                ("src_stride_row", C.c_int64), ("src_stride_col", C.c_int64), ("src_tap", C.c_int8 * FPG_MAX_TAPS)]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [("x", TMap), ("y", TMap), ("x_ca", C.c_int32), ("y_ca", C.c_int32), ("x_atoms", C.c_int32),
                 ("y_atoms", C.c_int32), ("x_groups", C.c_int32), ("y_groups", C.c_int32),
@@ -88,6 +94,10 @@ SIGNATURES = {
     "fpg_conv2d_wgrad_ws_bytes": (_i64, [_P(Act), _P(Act), _P(ConvGeom), C.c_int]),
     "fpg_pack_weights": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _P(ConvGeom), _vp, _vp]),
     "fpg_pack_weights_dgrad": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _P(ConvGeom), _vp, _vp]),
+    "fpg_pack_jobs": (C.c_int, [_vp, _i64, _i64, _i32, _i32, _P(ConvGeom), _vp, _vp, _P(PackJob), _P(_i32)]),
+    "fpg_pack_job_copy_f32": (C.c_int, [_vp, _i32, _vp, _i32, _P(PackJob)]),
+    "fpg_pack_job_blocks": (_i32, [_P(PackJob)]),
+    "fpg_pack_weights_batched": (C.c_int, [_vp, _vp, _vp, _i32, _vp]),
     "fpg_dgrad_class_info": (C.c_int, [_P(ConvGeom), C.c_int, _P(_i32), _P(_i32), _P(_i64), _P(_i32)]),
     "fpg_packed_weight_bytes": (_i64, [_P(ConvGeom)]),
     "fpg_packed_weight_dgrad_bytes": (_i64, [_P(ConvGeom)]),

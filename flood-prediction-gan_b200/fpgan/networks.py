@@ -10,8 +10,11 @@ Layer graphs follow the reference: model_architectures.py:339-400 (attention gen
 generator), :424-441 (InstanceNorm PatchGAN). Convolution biases that feed an InstanceNorm are mathematical
 no-ops (the norm subtracts the per-plane mean) and are skipped; their gradient is exactly 0.
 """
+import ctypes as C
+
 import torch
 
+from . import lib as L
 from . import ops
 from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU, ACT_TANH, ActBuf, ConvSpec, pad16
 
@@ -27,22 +30,59 @@ class ConvLayer:
         self.k_valid, self.c_valid = k, c
         self.spec = ConvSpec(r, r, stride, pad, pad16(c), pad16(k), c_in_valid=c, c_out_valid=k)
         self.bias_pad = None
-        self._version = None
 
-    def repack(self, need_fprop=True, need_dgrad=True):
-        ver = (self.weight._version, self.bias._version if self.bias is not None else 0, self.weight.data_ptr())
-        if ver == self._version:
-            return
-        self._version = ver
-        w = self.weight.detach()
-        if not w.is_contiguous():
-            w = w.contiguous()
-        self.spec.pack(w, fprop=need_fprop, dgrad=need_dgrad)
-        if self.use_bias:
-            n = self.spec.g.c_in if self.transposed else self.spec.g.c_out
-            if self.bias_pad is None:
-                self.bias_pad = torch.zeros(n, dtype=torch.float32, device=w.device)
-            self.bias_pad[:self.bias.numel()].copy_(self.bias.detach())
+    def version(self):
+        return (self.weight._version, self.weight.data_ptr(),
+                self.bias._version if self.use_bias else 0, self.bias.data_ptr() if self.use_bias else 0)
+
+
+class _PackTable:
+    """Device-resident job table of fpg_pack_weights_batched for one network: every packed bf16 operand (fprop and
+    dgrad layouts) and zero-padded bias vector is rebuilt from the fp32 parameters by ONE launch."""
+
+    def __init__(self, layers):
+        lib = L.load()
+        jobs = []
+        for layer in layers:
+            w = layer.weight.detach()
+            assert w.is_contiguous() and w.dtype == torch.float32 and w.is_cuda
+            sp = layer.spec
+            sp.alloc(w.device)
+            rs = sp.g.r * sp.g.s
+            buf = (L.PackJob * 5)()
+            n = C.c_int32()
+            L.call("fpg_pack_jobs", C.c_void_p(w.data_ptr()), sp.c_in_valid * rs, rs, sp.c_out_valid, sp.c_in_valid,
+                   sp.gref(), C.c_void_p(sp.w_fprop.data_ptr()), C.c_void_p(sp.w_dgrad.data_ptr()), buf, C.byref(n))
+            jobs.extend(_copy_job(buf[i]) for i in range(n.value))
+            if layer.use_bias:
+                npad = sp.g.c_in if layer.transposed else sp.g.c_out
+                if layer.bias_pad is None:
+                    layer.bias_pad = torch.zeros(npad, dtype=torch.float32, device=w.device)
+                job = L.PackJob()
+                L.call("fpg_pack_job_copy_f32", C.c_void_p(layer.bias.data_ptr()), layer.bias.numel(),
+                       C.c_void_p(layer.bias_pad.data_ptr()), npad, C.byref(job))
+                jobs.append(job)
+        arr = (L.PackJob * len(jobs))(*jobs)
+        block_job, block_first = [], []
+        for j, job in enumerate(jobs):
+            nb = lib.fpg_pack_job_blocks(C.byref(job))
+            block_job.extend([j] * nb)
+            block_first.extend(range(nb))
+        dev = layers[0].weight.device
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.jobs = raw.to(dev)
+        self.block_job = torch.tensor(block_job, dtype=torch.int32, device=dev)
+        self.block_first = torch.tensor(block_first, dtype=torch.int32, device=dev)
+        self.n_blocks = len(block_job)
+
+    def run(self):
+        ops.pack_weights_batched(self.jobs, self.block_job, self.block_first, self.n_blocks)
+
+
+def _copy_job(job):
+    out = L.PackJob()
+    C.memmove(C.byref(out), C.byref(job), C.sizeof(L.PackJob))
+    return out
 
 
 class Grads:
@@ -77,6 +117,9 @@ class _NetBase:
     def __init__(self, module):
         self.module = module
         self.layers = {}
+        self._pack = None
+        self._pack_ptrs = None
+        self._pack_ver = None
         self.grad_ready = None  # optional callback(param_name) fired once a parameter gradient has been produced
 
     def _add(self, name, conv_module, r, stride, pad, transposed=False, use_bias=False):
@@ -84,9 +127,17 @@ class _NetBase:
         self.layers[name] = layer
         return layer
 
-    def repack(self):
-        for layer in self.layers.values():
-            layer.repack()
+    def repack(self, force=False):
+        """Rebuild the bf16 GEMM operands if any fp32 parameter changed since the last call (one launch)."""
+        ver = tuple(layer.version() for layer in self.layers.values())
+        ptrs = tuple(v[1::2] for v in ver)
+        if self._pack is None or ptrs != self._pack_ptrs:
+            self._pack = _PackTable(list(self.layers.values()))  # parameters were re-homed (.cuda(), FlatParams)
+            self._pack_ptrs = ptrs
+        elif ver == self._pack_ver and not force:
+            return
+        self._pack_ver = ver
+        self._pack.run()
 
     def named_params(self):
         return list(self.module.named_parameters())

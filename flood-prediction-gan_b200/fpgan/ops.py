@@ -118,6 +118,18 @@ class ConvSpec:
         rs = self.g.r * self.g.s
         return self.c_in_valid * rs  # [K][C][R][S]; for ConvTranspose2d the parameter already is [K=Cin_T][C=Cout_T]
 
+    def alloc(self, device):
+        """Allocate the packed bf16 operands (fprop and dgrad layouts)."""
+        lib = L.load()
+        if self.w_fprop is None:
+            nbytes = lib.fpg_packed_weight_bytes(self.gref())
+            assert nbytes > 0
+            self.w_fprop = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=device)
+        if self.w_dgrad is None:
+            nbytes = lib.fpg_packed_weight_dgrad_bytes(self.gref())
+            assert nbytes > 0
+            self.w_dgrad = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=device)
+
     def pack(self, weight, fprop=True, dgrad=True):
         """(Re)pack the fp32 parameter `weight` ([K][C][R][S] in the forward-conv view) into the bf16 operands."""
         lib = L.load()
@@ -140,6 +152,11 @@ class ConvSpec:
                 self.w_dgrad = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)
             _run("pack_weights", 4 if self.g.stride == 2 else 1, "fpg_pack_weights_dgrad", _ptr(weight), sk, sc, self.c_out_valid, self.c_in_valid, self.gref(),
                    _ptr(self.w_dgrad), _stream())
+
+
+def pack_weights_batched(jobs, block_job, block_first, n_blocks):
+    _run("pack_weights", 1, "fpg_pack_weights_batched", _ptr(jobs), _ptr(block_job), _ptr(block_first), n_blocks,
+         _stream())
 
 
 def conv_fprop(x, spec, y, bias=None, act=ACT_NONE):

@@ -108,9 +108,7 @@ class PairedTrainer:
         self.launches = 0
 
     def _force_repack(self, net):
-        for layer in net.layers.values():
-            layer._version = None
-        net.repack()
+        net.repack(force=True)
 
     def step(self, input_stack, output_image, lr_g=0.0002, lr_d=0.0002):
         """input_stack [B,C,H,W], output_image [B,3,H,W]: fp32 CUDA tensors. Returns the generated image (fp32 NCHW).

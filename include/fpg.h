@@ -211,6 +211,27 @@ int fpg_pack_weights(const float* src, int64_t src_stride_k, int64_t src_stride_
                      const fpg_conv_geom* g, void* dst, void* stream);
 int fpg_pack_weights_dgrad(const float* src, int64_t src_stride_k, int64_t src_stride_c, int32_t k_valid,
                            int32_t c_valid, const fpg_conv_geom* g, void* dst, void* stream);
+/* Batched repack: every packed operand (and padded bias vector) of a network in ONE launch after the optimiser
+ * step. The job table is built once on the host with fpg_pack_jobs (up to 5 jobs per layer: the fprop operand and one
+ * dgrad operand per parity class; pass NULL for an operand that is not needed) / fpg_pack_job_copy_f32, copied to the
+ * device together with a block table: block b packs elements [2048*block_first[b], +2048) of job block_job[b];
+ * fpg_pack_job_blocks(job) blocks cover a job. */
+typedef struct {
+  const float* src;
+  void* dst;
+  int32_t rows, taps, cols; /* dst[rows][taps][cols] */
+  int32_t rows_valid, cols_valid;
+  int32_t dst_fp32;         /* 0: bf16 destination, 1: fp32 destination (bias vectors) */
+  int64_t src_stride_row, src_stride_col;
+  int8_t src_tap[FPG_MAX_TAPS]; /* source tap r*S+s of every destination tap, -1 = zero */
+} fpg_pack_job;
+int fpg_pack_jobs(const float* src, int64_t src_stride_k, int64_t src_stride_c, int32_t k_valid, int32_t c_valid,
+                  const fpg_conv_geom* g, void* dst_fprop, void* dst_dgrad, fpg_pack_job* jobs /* >= 5 */,
+                  int32_t* n_jobs);
+int fpg_pack_job_copy_f32(const float* src, int32_t count_valid, float* dst, int32_t count_padded, fpg_pack_job* job);
+int32_t fpg_pack_job_blocks(const fpg_pack_job* job);
+int fpg_pack_weights_batched(const fpg_pack_job* jobs_dev, const int32_t* block_job_dev, const int32_t* block_first_dev,
+                             int32_t n_blocks, void* stream);
 /* Introspection of the dgrad packing: for parity class `cls` (0 for stride 1; (oy&1)*2+(ox&1) for stride 2) returns
  * the forward tap index r*S+s of every packed tap (-1 = zero padding tap), the padded tap count, the element offset
  * of the class matrix [c_in][taps][c_out] inside the packed buffer and the number of classes. */
@@ -231,8 +252,8 @@ int fpg_bias_grad(const fpg_act* dy, float* db, int32_t k_valid, float* scratch,
 /* scratch floats needed by fpg_instnorm_stats / fpg_instnorm_bwd for activation y */
 int64_t fpg_instnorm_scratch_floats(const fpg_act* y);
 /* stats[(n*C + c)*2 + {0,1}] = {mean, rstd} over the h*w plane of y (biased variance, eps). Deterministic
- * two-stage reduction through `scratch`; `counters`: int32[n] that is zero on entry and left zero (ticket counters
- * of the last-CTA-finalizes scheme; shared by all instnorm calls of one stream). */
+ * two-stage reduction through `scratch`; `counters`: int32[4096] that is zero on entry and left zero (arrival counters
+ * and release flags of the per-image rendezvous; shared by all instnorm calls of one stream; n <= 2048). */
 int fpg_instnorm_stats(const fpg_act* y, float eps, float* stats, float* scratch, int32_t* counters, void* stream);
 /* z = act((y - mean) * rstd) [+ residual]; written to z's interior and, if z->halo > 0, mirrored into its halo.
  * residual may be NULL; it is read at interior coordinates (its own halo is skipped). */

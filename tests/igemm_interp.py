@@ -95,7 +95,7 @@ def run_rows(desc, abuf, bbuf, outbuf, bias=None):
     assert int(desc.b.box[0]) == cblk and int(desc.b.box[1]) == bn
     assert desc.b_stages == R or desc.b_stages >= TH + 1
     smem = (desc.a_stages * (((128 + S - 1) * cblk * 2 + 1023) // 1024 * 1024) + desc.b_stages * S * bn * cblk * 2)
-    assert smem <= 220 * 1024, smem
+    assert smem <= 224 * 1024, smem
     ktot = int(desc.b.dims[0])
     b_base = (int(desc.b.base or 0) - FAKE_BASE) // 2
     bmat = bbuf[b_base:b_base + bn * ktot].reshape(bn, ktot)
