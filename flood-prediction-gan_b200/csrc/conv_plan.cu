@@ -406,6 +406,9 @@ static int largest_divisor_le(int v, int cap) {
   return 1;
 }
 
+// width efficiency of 64 x 1 k tiles on a row of `w` pixels: shifted operands need one-row tiles
+static bool rows_of_64_ok(int w) { return 10 * w >= 7 * 64 * ceil_div(w, 64); }  // >= 70 % of the tile pixels used
+
 static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g, int sms, fpg_igemm_wgrad_desc* d) {
   FPG_REQUIRE(x && dy && g && d, "null argument");
   FPG_REQUIRE(g->stride == 1 || g->stride == 2, "stride %d", g->stride);
@@ -421,7 +424,12 @@ static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* 
   memset(d, 0, sizeof(*d));
   d->taps_r = g->r;
   d->taps_s = g->s;
+  d->y_shifts = 1;
   pick_tile(ho, wo, &d->tile_w, &d->tile_h, 64);
+  if (getenv("FPG_EXP_WGRAD_ROW_TILES") != nullptr) {  // experiment: one-row k tiles without shifted operands
+    d->tile_w = 64;
+    d->tile_h = 1;
+  }
   d->kt_x = ceil_div(wo, d->tile_w);
   d->kt_y = ceil_div(ho, d->tile_h);
   d->n_img = x->n;
@@ -429,9 +437,122 @@ static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* 
   fpg_tap in_taps[FPG_MAX_TAPS];
   for (int r = 0; r < g->r; ++r)
     for (int s = 0; s < g->s; ++s) in_taps[r * g->s + s] = fwd_tap(r, s, g->stride, g->pad, x->c_stride);
+  const bool shift_ok = getenv("FPG_DISABLE_WGRAD_SHIFT") == nullptr && g->stride == 1 && g->s >= 2;
+  int x_extra = 0, y_extra = 0;  // additional pixels of the X / Y boxes (shifted operands)
 
   const bool big_out = g->c_out % 64 == 0, big_in = g->c_in % 64 == 0;
-  if (big_out) {
+  // measured on B200: not faster than the M = 256 / N = 256 plan below (N = 128 MMAs read 8 KB of operands per 64
+  // cycles, which together with the TMA writes saturates the 128 B/clk of shared memory): opt-in for experiments
+  const bool wide_shift = shift_ok && getenv("FPG_WGRAD_SHIFT_WIDE") != nullptr;
+  if (big_out && big_in && wide_shift && g->c_out % 128 == 0 && g->c_in % 128 == 0 && g->s * 128 <= 512 &&
+      wo % 64 == 0) {
+    // Wide layers on 64-pixel rows (residual 3x3 convs): M = 128 output channels, N = 128 input channels, the S column
+    // taps of a filter row are S MMA groups reading ONE (64 + S - 1)-pixel input box at shifted pixel rows.
+    d->x_is_dy = 1;
+    d->x_ca = 64;
+    d->x_atoms = 2;
+    d->x_groups = g->c_out / 128;
+    d->x_taps_mode = 0;
+    d->x_ntaps = 1;
+    d->x_taps[0] = null_tap;
+    d->y_ca = 64;
+    d->y_atoms = 2;
+    d->y_groups = g->c_in / 128;
+    d->y_taps_mode = 0;
+    d->y_ntaps = g->r;
+    d->y_shifts = g->s;
+    for (int r = 0; r < g->r; ++r) {
+      d->y_taps[r] = in_taps[r * g->s];
+      d->y_tap_rs[r] = static_cast<int16_t>(r * g->s);
+    }
+    d->tile_w = 64;
+    d->tile_h = 1;
+    d->kt_x = wo / 64;
+    d->kt_y = ho;
+    y_extra = g->s - 1;
+    make_act_view(dy, 1, 64, 64, 1, &d->x);
+    make_act_view(x, 1, 64, 64 + y_extra, 1, &d->y);
+  } else if (big_out && !big_in && shift_ok && g->c_out == 64 && g->s * g->c_in <= 256 && rows_of_64_ok(wo)) {
+    // Few input channels (generator stem): M = 128 = dy at output rows o - 1 and o (two filter rows per item),
+    // N = S x c_in = the S column taps as pixel-shift atoms of one input box. Output rows run from -1 so that the
+    // second atom sees every row of dy.
+    FPG_REQUIRE(g->c_in == 16 || g->c_in == 32, "unsupported c_in %d", g->c_in);
+    d->x_is_dy = 1;
+    d->x_ca = 64;
+    d->x_atoms = 2;
+    d->x_groups = 1;
+    d->x_taps_mode = 1;
+    d->x_ntaps = 2;
+    fpg_tap up = {0, 0, 0, -1};
+    d->x_taps[0] = up;        // dy[o - 1 + ...]: pairs with input row (o - 1) + r_y  -> filter row r_y
+    d->x_taps[1] = null_tap;  // dy[o]:            pairs with input row (o - 1) + r_y  -> filter row r_y - 1
+    d->x_tap_rs[0] = 0;
+    d->x_tap_rs[1] = static_cast<int16_t>(-g->s);
+    d->y_ca = g->c_in;
+    d->y_atoms = g->s;
+    d->y_shift_atoms = 1;
+    d->y_taps_mode = 1;
+    d->y_groups = (g->r + 1) / 2;
+    d->y_ntaps = d->y_groups * g->s;
+    d->y_sets = 512 / (g->s * g->c_in) < d->y_groups ? 512 / (g->s * g->c_in) : d->y_groups;  // filter-row pairs per CTA
+    if (d->y_sets > 4) d->y_sets = 4;
+    for (int q = 0; q < d->y_groups; ++q) {
+      const int ry = 2 * q + 1;  // may equal R for odd R: that half is dropped by the tap-id check
+      for (int a = 0; a < g->s; ++a) {
+        fpg_tap t = fwd_tap(ry, a, 1, g->pad, x->c_stride);
+        t.dy -= 1;
+        d->y_taps[q * g->s + a] = t;
+        d->y_tap_rs[q * g->s + a] = static_cast<int16_t>(ry * g->s + a);
+      }
+    }
+    d->tile_w = 64;
+    d->tile_h = 1;
+    d->kt_x = ceil_div(wo, 64);
+    d->kt_y = ho + 1;
+    y_extra = g->s - 1;
+    make_act_view(dy, 1, 64, 64, 1, &d->x);
+    make_act_view(x, 1, d->y_ca, 64 + y_extra, 1, &d->y);
+  } else if (!big_out && big_in && shift_ok && g->c_in == 64 && g->s * g->c_out <= 256 && rows_of_64_ok(wp)) {
+    // Few output channels (content / tanh heads): dW[k,c,r,s] = sum_p x[p,c] * dy[p - (r,s) + pad, k] over INPUT
+    // pixels p. M = 128 = x at input rows p and p + 1 (filter rows r_y and r_y + 1), N = S x c_out = the S column taps
+    // as pixel-shift atoms of one dy box. Input rows run from -1 (see above).
+    FPG_REQUIRE(g->c_out == 16 || g->c_out == 32, "unsupported c_out %d", g->c_out);
+    d->x_is_dy = 0;
+    d->x_ca = 64;
+    d->x_atoms = 2;
+    d->x_groups = 1;
+    d->x_taps_mode = 1;
+    d->x_ntaps = 2;
+    fpg_tap up = {0, 0, 0, -1};
+    d->x_taps[0] = up;
+    d->x_taps[1] = null_tap;
+    d->x_tap_rs[0] = 0;
+    d->x_tap_rs[1] = static_cast<int16_t>(g->s);
+    d->y_ca = g->c_out;
+    d->y_atoms = g->s;
+    d->y_shift_atoms = 1;
+    d->y_taps_mode = 1;
+    d->y_groups = (g->r + 1) / 2;
+    d->y_ntaps = d->y_groups * g->s;
+    d->y_sets = 512 / (g->s * g->c_out) < d->y_groups ? 512 / (g->s * g->c_out) : d->y_groups;
+    if (d->y_sets > 4) d->y_sets = 4;
+    for (int q = 0; q < d->y_groups; ++q) {
+      const int ry = 2 * q;
+      for (int a = 0; a < g->s; ++a) {
+        // atom a reads dy a pixels further right: column tap s = S - 1 - a
+        fpg_tap t = {0, g->pad - (g->s - 1) + a, 0, -(ry - g->pad) - 1};
+        d->y_taps[q * g->s + a] = t;
+        d->y_tap_rs[q * g->s + a] = static_cast<int16_t>(ry * g->s + (g->s - 1 - a));
+      }
+    }
+    d->tile_w = 64;
+    d->tile_h = 1;
+    d->kt_x = ceil_div(wp, 64);
+    d->kt_y = hp + 1;
+    y_extra = g->s - 1;
+    make_act_view(x, 1, 64, 64, 1, &d->x);
+    make_act_view(dy, 1, d->y_ca, 64 + y_extra, 1, &d->y);
+  } else if (big_out) {
     // X = dy (rows = output channels)
     d->x_is_dy = 1;
     d->tap_on_x = 0;
@@ -458,7 +579,10 @@ static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* 
       d->y_taps_mode = 1;
     }
     d->y_ntaps = ntaps;
-    for (int t = 0; t < ntaps; ++t) d->y_taps[t] = in_taps[t];
+    for (int t = 0; t < ntaps; ++t) {
+      d->y_taps[t] = in_taps[t];
+      d->y_tap_rs[t] = static_cast<int16_t>(t);
+    }
     make_act_view(x, g->stride, d->y_ca, d->tile_w, d->tile_h, &d->y);
   } else {
     // small c_out: X = input (rows = input channels), Y = dy
@@ -488,11 +612,15 @@ static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* 
         for (int s = 0; s < g->s; ++s) {
           fpg_tap t = {0, -(s - g->pad), 0, -(r - g->pad)};
           d->y_taps[r * g->s + s] = t;
+          d->y_tap_rs[r * g->s + s] = static_cast<int16_t>(r * g->s + s);
         }
     } else {
       d->tap_on_x = 1;
       d->x_ntaps = ntaps;
-      for (int t = 0; t < ntaps; ++t) d->x_taps[t] = in_taps[t];
+      for (int t = 0; t < ntaps; ++t) {
+        d->x_taps[t] = in_taps[t];
+        d->x_tap_rs[t] = static_cast<int16_t>(t);
+      }
       d->y_atoms = 1;
       d->y_groups = 1;
       d->y_taps_mode = 0;
@@ -502,47 +630,64 @@ static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* 
     make_act_view(x, g->stride, 64, d->tile_w, d->tile_h, &d->x);
     make_act_view(dy, 1, d->y_ca, d->tile_w, d->tile_h, &d->y);
   }
+  (void)x_extra;
+  if (d->y_sets < 1) d->y_sets = 1;
   const int NX = d->x_taps_mode ? d->x_groups : d->x_groups * d->x_ntaps;
-  const int NY = d->y_taps_mode ? d->y_groups : d->y_groups * d->y_ntaps;
+  const int sets = d->y_sets;
+  const int NY = d->y_taps_mode ? (d->y_groups + sets - 1) / sets : d->y_groups * d->y_ntaps;
   const int items = NX * NY;
   const int total_kt = d->n_img * d->kt_x * d->kt_y;
   int splits = sms / items;
   if (splits < 1) splits = 1;
   if (splits > total_kt) splits = total_kt;
-  if (splits > 64) splits = 64;
+  if (splits > 160) splits = 160;
   d->splits = splits;
-  const int M = d->x_atoms * d->x_ca, N = d->y_atoms * d->y_ca;
-  d->stages = pick_stages((M + N) * 128);
+  const int M = d->x_atoms * d->x_ca;
+  const int x_stage = d->x_shift_atoms ? ((64 + d->x_atoms - 1) * d->x_ca * 2 + 1023) / 1024 * 1024 : M * 128;
+  const int y_px = 64 + (d->y_shift_atoms ? d->y_atoms - 1 : 0) + (d->y_shifts - 1);
+  const int y_stage = ((y_px * d->y_ca * 2 + 1023) / 1024 * 1024) * (d->y_shift_atoms ? d->y_sets : d->y_atoms);
+  d->stages = pick_stages(x_stage + y_stage);
   return 0;
+}
+
+static int wgrad_items_y(const fpg_igemm_wgrad_desc* d) {
+  const int sets = d->y_sets > 1 ? d->y_sets : 1;
+  return d->y_taps_mode ? (d->y_groups + sets - 1) / sets : d->y_groups * d->y_ntaps;
 }
 
 static int64_t wgrad_ws_floats(const fpg_igemm_wgrad_desc* d) {
   const int NX = d->x_taps_mode ? d->x_groups : d->x_groups * d->x_ntaps;
-  const int NY = d->y_taps_mode ? d->y_groups : d->y_groups * d->y_ntaps;
-  return static_cast<int64_t>(d->splits) * NX * NY * (d->x_atoms * d->x_ca) * (d->y_atoms * d->y_ca);
+  const int NY = wgrad_items_y(d);
+  return static_cast<int64_t>(d->splits) * NX * NY * (d->x_atoms * d->x_ca) * (d->y_atoms * d->y_ca) *
+         (d->y_shifts > 1 ? d->y_shifts : 1) * (d->y_sets > 1 ? d->y_sets : 1);
 }
 
 // ------------------------------------------------------------------------------------------------ kernels
 struct ReduceArgs {
   int32_t x_ca, x_atoms, x_groups, x_taps_mode, x_ntaps;
   int32_t y_ca, y_atoms, y_groups, y_taps_mode, y_ntaps;
-  int32_t splits, x_is_dy, tap_on_x;
+  int32_t splits, x_is_dy, y_shifts, y_sets, taps_total;
   int64_t stride_k, stride_c;
   int32_t k_valid, c_valid;
+  int16_t x_tap_rs[FPG_MAX_TAPS];
+  int16_t y_tap_rs[FPG_MAX_TAPS];
 };
 
-// one thread per (item, m, n): sum the split partials and scatter into the parameter-layout gradient
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, ReduceArgs a) {
+// one thread per (item, m, shift group, n): sum the split partials and scatter into the parameter-layout gradient
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, const ReduceArgs a) {
   const int M = a.x_atoms * a.x_ca, N = a.y_atoms * a.y_ca;
+  const int NT = a.y_shifts * a.y_sets * N;
   const int NX = a.x_taps_mode ? a.x_groups : a.x_groups * a.x_ntaps;
-  const int NY = a.y_taps_mode ? a.y_groups : a.y_groups * a.y_ntaps;
+  const int NY = a.y_taps_mode ? (a.y_groups + a.y_sets - 1) / a.y_sets : a.y_groups * a.y_ntaps;
   const int64_t items = static_cast<int64_t>(NX) * NY;
-  const int64_t per_split = items * M * N;
+  const int64_t per_split = items * M * NT;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= per_split) return;
-  const int n = static_cast<int>(idx % N);
-  const int m = static_cast<int>((idx / N) % M);
-  const int item = static_cast<int>(idx / (static_cast<int64_t>(M) * N));
+  const int nt = static_cast<int>(idx % NT);
+  const int grp = nt / N, n = nt % N;  // MMA group: pixel shift (y_shifts) or tap set (y_sets)
+  const int shift = a.y_sets > 1 ? 0 : grp;
+  const int m = static_cast<int>((idx / NT) % M);
+  const int item = static_cast<int>(idx / (static_cast<int64_t>(M) * NT));
   const int xi = item / NY, yi = item % NY;
   int xtap, xch, ytap, ych;
   {
@@ -558,16 +703,17 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
   {
     const int atom = n / a.y_ca, within = n % a.y_ca;
     if (a.y_taps_mode) {
-      ytap = yi * a.y_atoms + atom;
+      ytap = (yi * a.y_sets + (a.y_sets > 1 ? grp : 0)) * a.y_atoms + atom;
       ych = within;
     } else {
       ytap = yi / a.y_groups;
       ych = ((yi % a.y_groups) * a.y_atoms + atom) * a.y_ca + within;
     }
   }
+  if (xtap >= a.x_ntaps || ytap >= a.y_ntaps) return;  // dummy atoms of a ragged last group
   const int k = a.x_is_dy ? xch : ych, c = a.x_is_dy ? ych : xch;
-  const int tap = a.tap_on_x ? xtap : ytap;
-  if (tap >= (a.tap_on_x ? a.x_ntaps : a.y_ntaps)) return;
+  const int tap = a.x_tap_rs[xtap] + a.y_tap_rs[ytap] + shift;
+  if (tap < 0 || tap >= a.taps_total) return;
   if (k >= a.k_valid || c >= a.c_valid) return;
   float acc = 0.f;
   for (int s = 0; s < a.splits; ++s) acc += ws[s * per_split + idx];
@@ -719,11 +865,17 @@ int fpg_conv2d_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g
   a.y_ntaps = d.y_ntaps;
   a.splits = d.splits;
   a.x_is_dy = d.x_is_dy;
-  a.tap_on_x = d.tap_on_x;
+  a.y_shifts = d.y_shifts > 1 ? d.y_shifts : 1;
+  a.y_sets = d.y_sets > 1 ? d.y_sets : 1;
+  a.taps_total = d.taps_r * d.taps_s;
   a.stride_k = dw_stride_k;
   a.stride_c = dw_stride_c;
   a.k_valid = k_valid;
   a.c_valid = c_valid;
+  for (int i = 0; i < FPG_MAX_TAPS; ++i) {
+    a.x_tap_rs[i] = d.x_tap_rs[i];
+    a.y_tap_rs[i] = d.y_tap_rs[i];
+  }
   const int64_t per_split = wgrad_ws_floats(&d) / d.splits;
   const int threads = 256;
   const int64_t blocks = (per_split + threads - 1) / threads;

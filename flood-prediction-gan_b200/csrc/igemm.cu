@@ -109,20 +109,27 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
         int ty = r % args.tiles_y;
         int n = r / args.tiles_y;
         const int x0 = tx * args.tile_w, y0 = ty * args.tile_h;
-        int sub = 0;
+        // the issue time of this thread is on the critical path of the pipeline: no divisions, the tap entry is
+        // re-read only when the tap changes
+        int tap = 0, ccol = 0, kcol = 0;
+        fpg_tap t = args.taps[0];
+        const int c_per_tap = args.chunks_per_tap * CBLK;
         for (int ks = 0; ks < num_kstages; ++ks) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full[stage], stage_bytes);
           uint8_t* a_dst = smem_a + stage * A_STAGE_BYTES;
           uint8_t* b_dst = smem_b + stage * B_STAGE_BYTES;
 #pragma unroll
-          for (int j = 0; j < SUB; ++j, ++sub) {
-            const int tap = sub / args.chunks_per_tap;
-            const int chunk = sub - tap * args.chunks_per_tap;
-            const fpg_tap t = args.taps[tap];
-            tma_load_5d(&amap, &full[stage], a_dst + j * A_SUB_BYTES, t.c0 + chunk * CBLK, x0 + t.dx, t.plane,
-                        y0 + t.dy, n);
-            tma_load_2d(&bmap, &full[stage], b_dst + j * B_SUB_BYTES, sub * CBLK, nb * BN);
+          for (int j = 0; j < SUB; ++j) {
+            tma_load_5d(&amap, &full[stage], a_dst + j * A_SUB_BYTES, t.c0 + ccol, x0 + t.dx, t.plane, y0 + t.dy, n);
+            tma_load_2d(&bmap, &full[stage], b_dst + j * B_SUB_BYTES, kcol, nb * BN);
+            kcol += CBLK;
+            ccol += CBLK;
+            if (ccol == c_per_tap) {
+              ccol = 0;
+              ++tap;
+              t = args.taps[tap & (FPG_MAX_TAPS - 1)];
+            }
           }
           if (++stage == static_cast<uint32_t>(STAGES)) {
             stage = 0;
@@ -317,7 +324,10 @@ igemm_fprop2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
         int ty = r % args.tiles_y;
         int n = r / args.tiles_y;
         const int x0 = tx * args.tile_w, y0 = (ty * 2 + static_cast<int>(rank)) * args.tile_h;
-        int sub = 0;
+        int tap = 0, ccol = 0, kcol = 0;
+        fpg_tap t = args.taps[0];
+        const int c_per_tap = args.chunks_per_tap * CBLK;
+        const int b_row = nb * BN + static_cast<int>(rank) * BH;
         for (int ks = 0; ks < num_kstages; ++ks) {
           mbar_wait(&empty[stage], phase ^ 1);
           if (leader) {
@@ -328,14 +338,17 @@ igemm_fprop2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
           uint8_t* a_dst = smem_a + stage * A_STAGE_BYTES;
           uint8_t* b_dst = smem_b + stage * B_STAGE_BYTES;
 #pragma unroll
-          for (int j = 0; j < SUB; ++j, ++sub) {
-            const int tap = sub / args.chunks_per_tap;
-            const int chunk = sub - tap * args.chunks_per_tap;
-            const fpg_tap t = args.taps[tap];
-            tma_load_5d_2sm(&amap, &full[stage], a_dst + j * A_SUB_BYTES, t.c0 + chunk * CBLK, x0 + t.dx, t.plane,
-                            y0 + t.dy, n);
-            tma_load_2d_2sm(&bmap, &full[stage], b_dst + j * B_SUB_BYTES, sub * CBLK,
-                            nb * BN + static_cast<int>(rank) * BH);
+          for (int j = 0; j < SUB; ++j) {
+            tma_load_5d_2sm(&amap, &full[stage], a_dst + j * A_SUB_BYTES, t.c0 + ccol, x0 + t.dx, t.plane, y0 + t.dy,
+                            n);
+            tma_load_2d_2sm(&bmap, &full[stage], b_dst + j * B_SUB_BYTES, kcol, b_row);
+            kcol += CBLK;
+            ccol += CBLK;
+            if (ccol == c_per_tap) {
+              ccol = 0;
+              ++tap;
+              t = args.taps[tap & (FPG_MAX_TAPS - 1)];
+            }
           }
           if (++stage == static_cast<uint32_t>(STAGES)) {
             stage = 0;
@@ -451,10 +464,55 @@ struct WgradArgs {
   int32_t x_groups, y_groups, x_taps_mode, y_taps_mode, x_ntaps, y_ntaps;
   int32_t n_img, kt_y, kt_x, tile_h, tile_w;
   int32_t splits, stages;
+  int32_t x_shift_atoms, y_shift_atoms, y_shifts, y_sets;
+  uint32_t x_box_bytes, y_box_bytes;    // bytes one TMA box delivers
+  uint32_t x_atom_stride, y_atom_stride;  // shared-memory pitch between separately loaded boxes (1 KB multiple)
+  uint32_t x_stage_bytes, y_stage_bytes;
   float* ws;
   fpg_tap x_taps[FPG_MAX_TAPS];
   fpg_tap y_taps[FPG_MAX_TAPS];
 };
+
+// Loop-invariant pieces of the MMA descriptors of one wgrad CTA. A single thread issues every MMA and the tensor pipe
+// idles whenever that thread needs more cycles per MMA than the MMA takes (ncu: 41 % tensor-active with ~15 uniform
+// instructions per N = 128 MMA), so the per-stage issue routine is fully unrolled per (shift groups, M halves).
+struct WgradIssue {
+  uint32_t tmem;
+  uint64_t x_hi, y_hi;                 // descriptors without the start-address field
+  uint32_t x_k16, y_k16, x_h16, y_g16;  // 16-byte units: K step (16 pixel rows), second M half, MMA group stride
+  uint32_t n, idesc;
+  uint64_t* full;
+  uint64_t* empty;
+  uint32_t x_base, y_base, x_stage, y_stage, stages;
+};
+
+template <int YS, int MSUB>
+__device__ __forceinline__ void wgrad_mma_loop(const WgradIssue& is, int n_kt) {
+  uint32_t stage = 0, phase = 0, acc = 0;
+  for (int kt = 0; kt < n_kt; ++kt) {
+    mbar_wait(&is.full[stage], phase);
+    tc_fence_after();
+    const uint32_t x_lo = ((is.x_base + stage * is.x_stage) >> 4) & 0x3FFFu;
+    const uint32_t y_lo = ((is.y_base + stage * is.y_stage) >> 4) & 0x3FFFu;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t xd0 = is.x_hi | static_cast<uint64_t>(x_lo + k * is.x_k16);
+      const uint64_t xd1 = is.x_hi | static_cast<uint64_t>(x_lo + is.x_h16 + k * is.x_k16);
+#pragma unroll
+      for (int g = 0; g < YS; ++g) {
+        const uint64_t yd = is.y_hi | static_cast<uint64_t>(y_lo + k * is.y_k16 + g * is.y_g16);
+        umma_bf16(is.tmem + (g * MSUB) * is.n, xd0, yd, is.idesc, k == 0 ? acc : 1u);
+        if (MSUB == 2) umma_bf16(is.tmem + (g * MSUB + 1) * is.n, xd1, yd, is.idesc, k == 0 ? acc : 1u);
+      }
+    }
+    acc = 1u;
+    umma_commit(&is.empty[stage]);
+    if (++stage == is.stages) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap,
@@ -462,12 +520,12 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
+  __shared__ int4 boxtab[32];  // producer thread only: TMA coordinates of the X boxes [0,16) and Y boxes [16,32)
   const int M = args.x_atoms * args.x_ca;
   const int N = args.y_atoms * args.y_ca;
-  const uint32_t X_ATOM_BYTES = 64u * args.x_ca * 2u;  // 64 pixel rows of one channel atom
-  const uint32_t Y_ATOM_BYTES = 64u * args.y_ca * 2u;
-  const uint32_t X_STAGE_BYTES = X_ATOM_BYTES * args.x_atoms;
-  const uint32_t Y_STAGE_BYTES = Y_ATOM_BYTES * args.y_atoms;
+  const int YS = args.y_shifts * args.y_sets;  // MMA groups per stage, each with its own accumulator columns
+  const uint32_t X_STAGE_BYTES = args.x_stage_bytes;
+  const uint32_t Y_STAGE_BYTES = args.y_stage_bytes;
   const int STAGES = args.stages;
 
   uint8_t* smem_x = smem;
@@ -500,7 +558,7 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
 
   // work decomposition: blockIdx.x = (split, xi, yi)
   const int NX = args.x_taps_mode ? args.x_groups : args.x_groups * args.x_ntaps;
-  const int NY = args.y_taps_mode ? args.y_groups : args.y_groups * args.y_ntaps;
+  const int NY = args.y_taps_mode ? (args.y_groups + args.y_sets - 1) / args.y_sets : args.y_groups * args.y_ntaps;
   const int items = NX * NY;
   const int item = blockIdx.x % items;
   const int split = blockIdx.x / items;
@@ -511,87 +569,124 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
 
   if (warp == 0) {
     if (elect_one()) {
-      // operand tile -> (tap, channel offset) per atom
+      // operand tile -> (tap, channel offset) per separately loaded box
       const int xg = args.x_taps_mode ? xi : xi % args.x_groups;
       const int xt = args.x_taps_mode ? 0 : xi / args.x_groups;
       const int yg = args.y_taps_mode ? yi : yi % args.y_groups;
       const int yt = args.y_taps_mode ? 0 : yi / args.y_groups;
+      const int x_boxes = args.x_shift_atoms ? 1 : args.x_atoms;
+      const int y_boxes = args.y_shift_atoms ? args.y_sets : args.y_atoms;
+      // per-box TMA coordinates (channel, dx, plane, dy) are loop invariant: with three 64 KB stages the producer's
+      // issue time is on the critical path (slot period = issue + L2 latency + MMA), so they are tabulated once
+      // (shared memory, up to 16 boxes per operand), nothing but the tile origin is computed per stage and the k-tile
+      // counter is advanced without divisions
+      for (int a = 0; a < x_boxes; ++a) {
+        int tap = 0, coff = 0;
+        if (args.x_taps_mode) {
+          tap = xg * args.x_atoms + a;
+          if (tap >= args.x_ntaps) tap = 0;
+        } else {
+          tap = xt;
+          coff = (xg * args.x_atoms + a) * args.x_ca;
+        }
+        const fpg_tap t = args.x_taps[tap];
+        boxtab[a] = make_int4(t.c0 + coff, t.dx, t.plane, t.dy);
+      }
+      for (int a = 0; a < y_boxes; ++a) {
+        int tap = 0, coff = 0;
+        if (args.y_shift_atoms) {  // box a = tap group yg * y_sets + a (its first tap; the others are pixel shifts)
+          tap = (yg * args.y_sets + a) * args.y_atoms;
+          if (tap >= args.y_ntaps) tap = 0;
+        } else if (args.y_taps_mode) {
+          tap = yg * args.y_atoms + a;
+          if (tap >= args.y_ntaps) tap = 0;
+        } else {
+          tap = yt;
+          coff = (yg * args.y_atoms + a) * args.y_ca;
+        }
+        const fpg_tap t = args.y_taps[tap];
+        boxtab[16 + a] = make_int4(t.c0 + coff, t.dx, t.plane, t.dy);
+      }
       uint32_t stage = 0, phase = 0;
-      const uint32_t stage_bytes = X_STAGE_BYTES + Y_STAGE_BYTES;
+      const uint32_t stage_bytes = x_boxes * args.x_box_bytes + y_boxes * args.y_box_bytes;
+      int kx = kt_begin % args.kt_x;
+      int ky = (kt_begin / args.kt_x) % args.kt_y;
+      int n = kt_begin / (args.kt_x * args.kt_y);
       for (int kt = kt_begin; kt < kt_end; ++kt) {
-        const int kx = kt % args.kt_x;
-        const int r = kt / args.kt_x;
-        const int ky = r % args.kt_y;
-        const int n = r / args.kt_y;
         const int x0 = kx * args.tile_w, y0 = ky * args.tile_h;
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full[stage], stage_bytes);
         uint8_t* x_dst = smem_x + stage * X_STAGE_BYTES;
         uint8_t* y_dst = smem_y + stage * Y_STAGE_BYTES;
-        for (int a = 0; a < args.x_atoms; ++a) {
-          int tap, coff;
-          if (args.x_taps_mode) {
-            tap = xg * args.x_atoms + a;
-            if (tap >= args.x_ntaps) tap = 0;
-            coff = 0;
-          } else {
-            tap = xt;
-            coff = (xg * args.x_atoms + a) * args.x_ca;
-          }
-          const fpg_tap t = args.x_taps[tap];
-          tma_load_5d(&xmap, &full[stage], x_dst + a * X_ATOM_BYTES, t.c0 + coff, x0 + t.dx, t.plane, y0 + t.dy, n);
+        for (int a = 0; a < x_boxes; ++a) {
+          const int4 b = boxtab[a];
+          tma_load_5d(&xmap, &full[stage], x_dst + a * args.x_atom_stride, b.x, x0 + b.y, b.z, y0 + b.w, n);
         }
-        for (int a = 0; a < args.y_atoms; ++a) {
-          int tap, coff;
-          if (args.y_taps_mode) {
-            tap = yg * args.y_atoms + a;
-            if (tap >= args.y_ntaps) tap = 0;
-            coff = 0;
-          } else {
-            tap = yt;
-            coff = (yg * args.y_atoms + a) * args.y_ca;
-          }
-          const fpg_tap t = args.y_taps[tap];
-          tma_load_5d(&ymap, &full[stage], y_dst + a * Y_ATOM_BYTES, t.c0 + coff, x0 + t.dx, t.plane, y0 + t.dy, n);
+        for (int a = 0; a < y_boxes; ++a) {
+          const int4 b = boxtab[16 + a];
+          tma_load_5d(&ymap, &full[stage], y_dst + a * args.y_atom_stride, b.x, x0 + b.y, b.z, y0 + b.w, n);
         }
         if (++stage == static_cast<uint32_t>(STAGES)) {
           stage = 0;
           phase ^= 1;
+        }
+        if (++kx == args.kt_x) {
+          kx = 0;
+          if (++ky == args.kt_y) {
+            ky = 0;
+            ++n;
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       // both operands MN-major (pixel rows, channel-contiguous). M == 256 is issued as two M=128 MMAs that share the Y
-      // tile (accumulators at columns [0,N) and [N,2N)): 1/3 less operand traffic per FLOP than two M=128 CTAs.
+      // tile; y_shifts > 1 issues one MMA group per pixel shift of the Y tile. Accumulator (shift g, half ms) lives
+      // at TMEM columns (g * msub + ms) * N.
       const int MI = M > 128 ? 128 : M;
       const int msub = M / MI;
       const uint32_t idesc = make_idesc_bf16(MI, N, 1, 1);
       const uint32_t x_layout = swizzle_layout_type(args.x_ca * 2), y_layout = swizzle_layout_type(args.y_ca * 2);
       const uint32_t x_sbo = 8u * args.x_ca * 2u, y_sbo = 8u * args.y_ca * 2u;  // 8 pixel rows
       const uint32_t x_kstep = 16u * args.x_ca * 2u, y_kstep = 16u * args.y_ca * 2u;  // 16 pixel rows per MMA
-      uint32_t stage = 0, phase = 0;
-      bool first = true;
-      for (int kt = kt_begin; kt < kt_end; ++kt) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t x_addr = smem_u32(smem_x + stage * X_STAGE_BYTES);
-        const uint32_t y_addr = smem_u32(smem_y + stage * Y_STAGE_BYTES);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t yd = make_smem_desc(y_addr + k * y_kstep, Y_ATOM_BYTES, y_sbo, y_layout);
-          for (int ms = 0; ms < msub; ++ms) {
-            const uint64_t xd = make_smem_desc(x_addr + ms * 2 * X_ATOM_BYTES + k * x_kstep, X_ATOM_BYTES, x_sbo,
-                                               x_layout);
-            umma_bf16(tmem_base + ms * N, xd, yd, idesc, first ? 0u : 1u);
-          }
-          first = false;
-        }
-        umma_commit(&empty[stage]);
-        if (++stage == static_cast<uint32_t>(STAGES)) {
-          stage = 0;
-          phase ^= 1;
-        }
+      // atom stride seen by the tensor core: one pixel row for shift atoms, the box pitch otherwise
+      const uint32_t x_lbo = args.x_shift_atoms ? args.x_ca * 2u : args.x_atom_stride;
+      const uint32_t y_lbo = args.y_shift_atoms ? args.y_ca * 2u : args.y_atom_stride;
+      const uint32_t x_half = args.x_shift_atoms ? 0u : 2u * args.x_atom_stride;  // second M = 128 half (4 channel atoms)
+      // descriptors = constant high part | (start address >> 4): the issue loop only adds precomputed 16-byte offsets
+      // (a single thread issues every MMA; ~25 ALU instructions per MMA made the N = 128 plan issue bound)
+      const uint64_t x_hi = make_smem_desc(0, x_lbo, x_sbo, x_layout);
+      const uint64_t y_hi = make_smem_desc(0, y_lbo, y_sbo, y_layout);
+      // MMA group stride: the next box (tap sets) or one pixel row (shift groups)
+      const uint32_t x_k16 = x_kstep >> 4, y_k16 = y_kstep >> 4, x_h16 = x_half >> 4,
+                     y_g16 = (args.y_sets > 1 ? args.y_atom_stride : args.y_ca * 2u) >> 4;
+      WgradIssue is;
+      is.tmem = tmem_base;
+      is.x_hi = x_hi;
+      is.y_hi = y_hi;
+      is.x_k16 = x_k16;
+      is.y_k16 = y_k16;
+      is.x_h16 = x_h16;
+      is.y_g16 = y_g16;
+      is.n = static_cast<uint32_t>(N);
+      is.idesc = idesc;
+      is.full = full;
+      is.empty = empty;
+      is.x_base = smem_u32(smem_x);
+      is.y_base = smem_u32(smem_y);
+      is.x_stage = X_STAGE_BYTES;
+      is.y_stage = Y_STAGE_BYTES;
+      is.stages = static_cast<uint32_t>(STAGES);
+      const int n_kt = kt_end - kt_begin;
+      switch ((YS - 1) * 2 + (msub - 1)) {  // (MMA groups, M halves) -> fully unrolled main loop
+        case 0: wgrad_mma_loop<1, 1>(is, n_kt); break;
+        case 1: wgrad_mma_loop<1, 2>(is, n_kt); break;
+        case 2: wgrad_mma_loop<2, 1>(is, n_kt); break;
+        case 3: wgrad_mma_loop<2, 2>(is, n_kt); break;
+        case 4: wgrad_mma_loop<3, 1>(is, n_kt); break;
+        case 6: wgrad_mma_loop<4, 1>(is, n_kt); break;
+        default: __trap();  // never planned: the accumulators would not fit TMEM
       }
       umma_commit(tfull);
     }
@@ -600,29 +695,32 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     // M >= 128: row = 32q + lane (+128 for the second sub-tile). M == 64: rows 16q..16q+15 are lanes 0..15 of quarter q
     const int msub = M > 128 ? 2 : 1;
     const bool row_valid = (M >= 128) || (lane < 16);
+    const int NT = YS * N;  // workspace row length
     if (kt_end > kt_begin) {
       mbar_wait(tfull, 0);
       tc_fence_after();
     }
     for (int ms = 0; ms < msub; ++ms) {
       const int row = (M >= 128) ? ms * 128 + q * 32 + lane : q * 16 + lane;
-      float* dst = args.ws + (static_cast<int64_t>(split) * items + item) * M * N + static_cast<int64_t>(row) * N;
-      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ms * N;
-      for (int c = 0; c < N; c += 16) {
-        uint32_t v[16];
-        if (kt_end > kt_begin) {
-          tmem_ld16(t_addr + c, v);
-          tmem_ld_wait();
-        } else {
+      float* dst = args.ws + (static_cast<int64_t>(split) * items + item) * M * NT + static_cast<int64_t>(row) * NT;
+      for (int g = 0; g < YS; ++g) {
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (g * msub + ms) * N;
+        for (int c = 0; c < N; c += 16) {
+          uint32_t v[16];
+          if (kt_end > kt_begin) {
+            tmem_ld16(t_addr + c, v);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = 0u;
-        }
-        if (row_valid) {
-          float4* d4 = reinterpret_cast<float4*>(dst + c);
+            for (int i = 0; i < 16; ++i) v[i] = 0u;
+          }
+          if (row_valid) {
+            float4* d4 = reinterpret_cast<float4*>(dst + g * N + c);
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+            for (int i = 0; i < 4; ++i)
+              d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                  __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+          }
         }
       }
     }
@@ -729,9 +827,16 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
 extern "C" int fpg_igemm_wgrad_launch(const fpg_igemm_wgrad_desc* d, void* stream) {
   FPG_REQUIRE(d != nullptr, "null descriptor");
   const int M = d->x_atoms * d->x_ca, N = d->y_atoms * d->y_ca;
-  FPG_REQUIRE(M == 64 || M == 128 || (M == 256 && d->x_ca == 64 && N <= 256), "wgrad M %d", M);
+  const int ysh = d->y_shifts > 1 ? d->y_shifts : 1, ysets = d->y_sets > 1 ? d->y_sets : 1;
+  const int ys = ysh * ysets;
+  FPG_REQUIRE(M == 64 || M == 128 || (M == 256 && d->x_ca == 64 && !d->x_shift_atoms), "wgrad M %d", M);
   FPG_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0, "wgrad N %d", N);
+  FPG_REQUIRE((M > 128 ? 2 : 1) * ys * N <= 512, "accumulators do not fit TMEM");
   FPG_REQUIRE(d->tile_h * d->tile_w == 64, "k tile %dx%d", d->tile_h, d->tile_w);
+  const bool shifted = d->x_shift_atoms || d->y_shift_atoms || ys > 1;
+  FPG_REQUIRE(!shifted || d->tile_h == 1, "shifted operands need one-row k tiles");
+  FPG_REQUIRE(!(d->y_shift_atoms && ysh > 1) && (ysets == 1 || d->y_shift_atoms),
+              "y_shift_atoms excludes y_shifts; y_sets needs y_shift_atoms");
   FPG_REQUIRE(d->stages >= 2 && d->stages <= 8 && d->splits >= 1, "stages %d splits %d", d->stages, d->splits);
   FPG_REQUIRE(d->ws != nullptr, "null workspace");
   CUtensorMap xmap, ymap;
@@ -757,15 +862,32 @@ extern "C" int fpg_igemm_wgrad_launch(const fpg_igemm_wgrad_desc* d, void* strea
   args.tile_w = d->tile_w;
   args.splits = d->splits;
   args.stages = d->stages;
+  args.x_shift_atoms = d->x_shift_atoms ? 1 : 0;
+  args.y_shift_atoms = d->y_shift_atoms ? 1 : 0;
+  args.y_shifts = ysh;
+  args.y_sets = ysets;
+  // box extents in pixels: 64 (+ shift range)
+  const uint32_t x_px = 64u + (d->x_shift_atoms ? d->x_atoms - 1 : 0);
+  const uint32_t y_px = 64u + (d->y_shift_atoms ? d->y_atoms - 1 : 0) + (ysh - 1);
+  FPG_REQUIRE(d->x.box[1] * d->x.box[3] == x_px && d->y.box[1] * d->y.box[3] == y_px, "box extents %u %u",
+              d->x.box[1], d->y.box[1]);
+  args.x_box_bytes = x_px * d->x_ca * 2u;
+  args.y_box_bytes = y_px * d->y_ca * 2u;
+  args.x_atom_stride = (args.x_box_bytes + 1023u) & ~1023u;
+  args.y_atom_stride = (args.y_box_bytes + 1023u) & ~1023u;
+  args.x_stage_bytes = args.x_atom_stride * (d->x_shift_atoms ? 1 : d->x_atoms);
+  args.y_stage_bytes = args.y_atom_stride * (d->y_shift_atoms ? ysets : d->y_atoms);
   args.ws = d->ws;
   for (int i = 0; i < FPG_MAX_TAPS; ++i) {
     args.x_taps[i] = d->x_taps[i];
     args.y_taps[i] = d->y_taps[i];
   }
   const int NX = d->x_taps_mode ? d->x_groups : d->x_groups * d->x_ntaps;
-  const int NY = d->y_taps_mode ? d->y_groups : d->y_groups * d->y_ntaps;
+  const int NY = d->y_taps_mode ? (d->y_groups + ysets - 1) / ysets : d->y_groups * d->y_ntaps;
   const int grid = NX * NY * d->splits;
-  const size_t smem = static_cast<size_t>(d->stages) * (M + N) * 128 + (2 * d->stages + 2) * 8 + 16 + 1024;
+  const size_t smem = static_cast<size_t>(d->stages) * (args.x_stage_bytes + args.y_stage_bytes) +
+                      (2 * d->stages + 2) * 8 + 16 + 1024;
+  FPG_REQUIRE(smem <= 227 * 1024, "shared memory %zu", smem);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));

@@ -94,9 +94,18 @@ typedef struct {
 } fpg_igemm_fprop_desc;
 
 /* D_item[m, n] = sum_{pixel} X[pixel + xtap, xc + m] * Y[pixel + ytap, yc + n], split over pixel ranges,
- * partial tiles written as fp32 to ws[split][item][M][N]. */
+ * partial tiles written as fp32 to ws[split][item][M][y_shifts * N].
+ * Shifted operands (tile_h == 1): because shared-memory descriptors may start at any pixel row of a TMA-written box,
+ * several filter taps that differ by whole pixels in x can be served by ONE box of tile_w + (taps - 1) pixels:
+ *   x_shift_atoms / y_shift_atoms = 1: the atoms of the tile are the pixel shifts 0 .. atoms-1 of one box (one MMA,
+ *       descriptor atom stride = one pixel row); the tap tables must list dx(first) + a for atom a;
+ *   y_shifts = g > 1: g MMA groups per Y tile, group j reads the Y tile j pixels later and accumulates into its own
+ *       columns [j*N, (j+1)*N): one box per channel atom instead of g;
+ *   y_sets = g > 1 (with y_shift_atoms): g shift-atom boxes per stage, i.e. an item covers the g consecutive tap
+ *       groups yi*g .. yi*g + g-1 of the Y table, each with its own accumulator columns: the X tile is loaded once
+ *       for all of them (the X stream otherwise repeats per tap group and saturates L2 -> SM bandwidth). */
 typedef struct {
-  fpg_tmap x, y;          /* box = {ca, tile_w, 1, tile_h, 1}, tile_w*tile_h == 64 */
+  fpg_tmap x, y;          /* box = {ca, tile_w (+ shift extent), 1, tile_h, 1}, tile_w*tile_h == 64 */
   int32_t x_ca, y_ca;     /* atom width in channels: 16 / 32 / 64 */
   int32_t x_atoms, y_atoms; /* M = x_atoms*x_ca in {64,128,256}; N = y_atoms*y_ca, multiple of 16, <= 256 */
   int32_t x_groups, y_groups;
@@ -105,11 +114,15 @@ typedef struct {
   int32_t n_img, kt_y, kt_x, tile_h, tile_w;
   int32_t splits, stages;
   int32_t x_is_dy; /* 1: X operand is the output gradient (rows of D are output channels); 0: X is the input */
-  int32_t tap_on_x; /* 1: the filter taps are enumerated by the X operand, 0: by the Y operand */
-  int32_t taps_r, taps_s; /* filter size, for mapping tap index -> (r, s) when reducing */
+  int32_t tap_on_x; /* informational: 1 if the filter taps are enumerated by the X operand only */
+  int32_t taps_r, taps_s; /* filter size: tap ids >= taps_r*taps_s (or < 0) are padding and are dropped */
+  int32_t x_shift_atoms, y_shift_atoms, y_shifts, y_sets;
   float* ws;
   fpg_tap x_taps[FPG_MAX_TAPS];
   fpg_tap y_taps[FPG_MAX_TAPS];
+  /* filter tap id r*S+s of element (m, n) = x_tap_rs[x tap index] + y_tap_rs[y tap index] + shift group */
+  int16_t x_tap_rs[FPG_MAX_TAPS];
+  int16_t y_tap_rs[FPG_MAX_TAPS];
 } fpg_igemm_wgrad_desc;
 
 /* Row-stationary implicit GEMM for stride-1 R x S filters on wide images (7x7 stem / heads): a CTA tile is

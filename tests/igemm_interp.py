@@ -137,18 +137,29 @@ def run_rows(desc, abuf, bbuf, outbuf, bias=None):
 
 
 def run_wgrad(desc, xbuf, ybuf, dw, stride_k, stride_c, k_valid, c_valid):
-    """Interpret an fpg_igemm_wgrad_desc including the split reduction and the scatter into dw (flat fp array)."""
+    """Interpret an fpg_igemm_wgrad_desc including shifted operands (shift atoms / shift groups), the split
+    reduction and the scatter into dw (flat fp array)."""
     assert desc.tile_h * desc.tile_w == 64
     M, N = desc.x_atoms * desc.x_ca, desc.y_atoms * desc.y_ca
-    assert M in (64, 128, 256) and N % 16 == 0 and 16 <= N <= 256 and (M < 256 or 2 * N <= 512)
+    YSH, SETS = max(desc.y_shifts, 1), max(desc.y_sets, 1)
+    YS = YSH * SETS  # MMA groups per stage, each with its own accumulator columns
+    assert M in (64, 128, 256) and N % 16 == 0 and 16 <= N <= 256 and (2 if M > 128 else 1) * YS * N <= 512
+    if desc.x_shift_atoms or desc.y_shift_atoms or YS > 1:
+        assert desc.tile_h == 1
+    assert not (desc.y_shift_atoms and YSH > 1) and not (desc.x_shift_atoms and M > 128)
+    assert SETS == 1 or desc.y_shift_atoms
     NX = desc.x_groups if desc.x_taps_mode else desc.x_groups * desc.x_ntaps
-    NY = desc.y_groups if desc.y_taps_mode else desc.y_groups * desc.y_ntaps
+    NY = -(-desc.y_groups // SETS) if desc.y_taps_mode else desc.y_groups * desc.y_ntaps
     total_kt = desc.n_img * desc.kt_y * desc.kt_x
+    taps_total = desc.taps_r * desc.taps_s
 
-    def operand_tile(tm, buf, taps, taps_mode, ntaps, groups, atoms, ca, idx, n, y0, x0):
-        cols = []
+    def operand_tile(tm, buf, taps, taps_mode, ntaps, groups, atoms, ca, shift_atoms, shifts, idx, n, y0, x0):
+        """returns [shift group] -> (64 x atoms*ca matrix), and per-column (tap index or -1, channel)"""
+        extent = 64 + (atoms - 1 if shift_atoms else 0) + (shifts - 1)
+        assert int(tm.box[1]) * int(tm.box[3]) == extent and int(tm.box[0]) == ca
         meta = []
-        for a in range(atoms):
+        boxes = []
+        for a in range(1 if shift_atoms else atoms):
             if taps_mode:
                 tap = idx * atoms + a
                 dummy = tap >= ntaps
@@ -158,17 +169,32 @@ def run_wgrad(desc, xbuf, ybuf, dw, stride_k, stride_c, k_valid, c_valid):
             else:
                 tap = idx // groups
                 coff = ((idx % groups) * atoms + a) * ca
-                dummy = False
             t = taps[tap]
-            tile = _tmap_gather(tm, buf, [t.c0 + coff, x0 + t.dx, t.plane, y0 + t.dy, n]).reshape(64, ca)
-            cols.append(tile)
+            boxes.append(_tmap_gather(tm, buf, [t.c0 + coff, x0 + t.dx, t.plane, y0 + t.dy, n]).reshape(extent, ca))
+        for a in range(atoms):
+            if taps_mode:
+                tap = idx * atoms + a
+                coff = 0
+            else:
+                tap = idx // groups
+                coff = ((idx % groups) * atoms + a) * ca
+            if shift_atoms:
+                base = taps[idx * atoms]
+                assert taps[tap].dx == base.dx + a and taps[tap].dy == base.dy and taps[tap].c0 == base.c0
             for w in range(ca):
-                meta.append((-1 if dummy else tap, coff + w))
-        return np.concatenate(cols, axis=1), meta
+                meta.append((tap if tap < ntaps else -1, coff + w))
+        mats = []
+        for g in range(shifts):
+            if shift_atoms:
+                cols = [boxes[0][a:a + 64] for a in range(atoms)]
+            else:
+                cols = [b[g:g + 64] for b in boxes]
+            mats.append(np.concatenate(cols, axis=1))
+        return mats, meta
 
     for xi in range(NX):
         for yi in range(NY):
-            acc = np.zeros((M, N), dtype=np.float64)
+            acc = np.zeros((YS, M, N), dtype=np.float64)
             xmeta = ymeta = None
             for kt in range(total_kt):
                 kx = kt % desc.kt_x
@@ -177,16 +203,30 @@ def run_wgrad(desc, xbuf, ybuf, dw, stride_k, stride_c, k_valid, c_valid):
                 n = r // desc.kt_y
                 x0, y0 = kx * desc.tile_w, ky * desc.tile_h
                 xt, xmeta = operand_tile(desc.x, xbuf, desc.x_taps, desc.x_taps_mode, desc.x_ntaps, desc.x_groups,
-                                         desc.x_atoms, desc.x_ca, xi, n, y0, x0)
-                yt, ymeta = operand_tile(desc.y, ybuf, desc.y_taps, desc.y_taps_mode, desc.y_ntaps, desc.y_groups,
-                                         desc.y_atoms, desc.y_ca, yi, n, y0, x0)
-                acc += xt.astype(np.float64).T @ yt.astype(np.float64)
-            for m in range(M):
-                xtap, xch = xmeta[m]
-                for nn in range(N):
-                    ytap, ych = ymeta[nn]
-                    k, c = (xch, ych) if desc.x_is_dy else (ych, xch)
-                    tap = xtap if desc.tap_on_x else ytap
-                    if tap < 0 or k >= k_valid or c >= c_valid:
-                        continue
-                    dw[k * stride_k + c * stride_c + tap] = acc[m, nn]
+                                         desc.x_atoms, desc.x_ca, desc.x_shift_atoms, 1, xi, n, y0, x0)
+                if SETS > 1:  # one shift-atom box per tap group yi*SETS + j
+                    yt, ymeta = [], []
+                    for j in range(SETS):
+                        m_, meta_ = operand_tile(desc.y, ybuf, desc.y_taps, 1, desc.y_ntaps, desc.y_groups,
+                                                 desc.y_atoms, desc.y_ca, 1, 1, yi * SETS + j, n, y0, x0)
+                        yt.append(m_[0])
+                        ymeta.append(meta_)
+                else:
+                    yt, meta_ = operand_tile(desc.y, ybuf, desc.y_taps, desc.y_taps_mode, desc.y_ntaps,
+                                             desc.y_groups, desc.y_atoms, desc.y_ca, desc.y_shift_atoms, YSH, yi, n,
+                                             y0, x0)
+                    ymeta = [meta_] * YSH
+                for g in range(YS):
+                    acc[g] += xt[0].astype(np.float64).T @ yt[g].astype(np.float64)
+            for g in range(YS):
+                for m in range(M):
+                    xtap, xch = xmeta[m]
+                    for nn in range(N):
+                        ytap, ych = ymeta[g][nn]
+                        if xtap < 0 or ytap < 0:
+                            continue
+                        k, c = (xch, ych) if desc.x_is_dy else (ych, xch)
+                        tap = desc.x_tap_rs[xtap] + desc.y_tap_rs[ytap] + (g if SETS == 1 else 0)
+                        if tap < 0 or tap >= taps_total or k >= k_valid or c >= c_valid:
+                            continue
+                        dw[k * stride_k + c * stride_c + tap] = acc[g, m, nn]

@@ -182,12 +182,19 @@ WGRAD_CASES = [
     (1, 7, 7, 128, 128, 1, 16, 4, 1, 1, 0),     # model.11
     (2, 9, 9, 64, 64, 128, 128, 4, 1, 1, 0),    # 4x4 s1 p1, odd extent
     (1, 8, 8, 64, 64, 256, 256, 3, 1, 0, 1),    # c_out 256: M = 256 tile (two MMAs sharing the input tile)
+    # shifted operands (64-pixel rows): column taps read from ONE box at shifted pixel rows
+    (1, 3, 64, 128, 128, 256, 256, 3, 1, 0, 1),  # residual conv: S shift groups, M = N = 128, 2x2 channel groups
+    (2, 4, 64, 9, 16, 64, 64, 7, 1, 0, 3),       # stem: dy row pairs x 7 shift atoms of the 16-channel input
+    (1, 5, 58, 64, 64, 27, 32, 7, 1, 0, 3),      # content head: input row pairs x 7 shift atoms of dy (wp = 64)
+    (1, 4, 130, 64, 64, 3, 16, 7, 1, 0, 3),      # tanh head (3 -> 16 channels), ragged row of 136 pixels
+    (1, 6, 64, 27, 32, 64, 64, 3, 1, 1, 0),      # zero-padded 3x3 on 32 input channels: shift atoms with pad
 ]
 
 
 @pytest.mark.parametrize("case", WGRAD_CASES)
-def test_wgrad_plan_matches_autograd(fpglib, case):
+def test_wgrad_plan_matches_autograd(fpglib, case, monkeypatch):
     n, h, w, c, cp, k, kp, r, stride, pad, halo = case
+    monkeypatch.setenv("FPG_WGRAD_SHIFT_WIDE", "1")  # also cover the opt-in shift-group plan of the wide layers
     torch.manual_seed(3)
     x = torch.randn(n, c, h, w, dtype=torch.float64)
     xin = F.pad(x, (halo,) * 4, "reflect") if halo else x
@@ -202,6 +209,8 @@ def test_wgrad_plan_matches_autograd(fpglib, case):
     d = L.WgradDesc()
     L.call("fpg_conv2d_wgrad_plan", C.byref(xa), C.byref(dya), C.byref(g), SMS, C.byref(d))
     assert fpglib.fpg_conv2d_wgrad_ws_bytes(C.byref(xa), C.byref(dya), C.byref(g), SMS) > 0
+    if w >= 58 and stride == 1 and r > 1:
+        assert d.y_shift_atoms or d.y_shifts > 1, "wide stride-1 layers must plan shifted operands"
     dw = np.full(k * c * r * r, np.nan)
     xb, yb = nhwc_buffer(x, cp, halo), nhwc_buffer(dy, kp)
     if d.x_is_dy:

@@ -9,7 +9,7 @@
 using namespace fpg;
 
 __global__ void __launch_bounds__(128, 1)
-rate_kernel(int M, int N, int mn_major, int iters, int a_step, int n_acc, int n_warps, int swz, long long* out) {
+rate_kernel(int M, int N, int mn_major, int iters, int a_step, int n_acc, int n_warps, int swz, int b_shift, int b_lbo, long long* out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* done = reinterpret_cast<uint64_t*>(smem + 160 * 1024);
@@ -32,7 +32,7 @@ rate_kernel(int M, int N, int mn_major, int iters, int a_step, int n_acc, int n_
     const uint32_t a0 = smem_u32(smem), b0 = smem_u32(smem + 96 * 1024);
     const uint32_t lt = swizzle_layout_type(swz);
     const uint64_t ad0 = mn_major ? make_smem_desc(a0, 64 * swz, 8 * swz, lt) : make_smem_desc(a0, 0, 8 * swz, lt);
-    const uint64_t bd0 = mn_major ? make_smem_desc(b0, 64 * swz, 8 * swz, lt) : make_smem_desc(b0, 0, 8 * swz, lt);
+    const uint64_t bd0 = mn_major ? make_smem_desc(b0 + b_shift * swz, b_lbo, 8 * swz, lt) : make_smem_desc(b0 + b_shift * swz, 0, 8 * swz, lt);
     const uint32_t astep16 = a_step >> 4;
     const long long t0 = clock64();
     for (int i = 0; i < iters / n_warps; i += 16) {
@@ -57,20 +57,20 @@ int main() {
   cudaMalloc(&dout, 8);
   cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 162 * 1024 + 1024);
   const int iters = 8192;
-  for (int swz : {128, 64, 32})
-    for (int n_warps : {1, 2}) {
-      const int a_step = 0, mn = 0, M = 128, n_acc = 1;
-      printf("K-major M=128 swizzle=%3d issuing warps=%d :", swz, n_warps);
-      for (int N : {16, 32, 64, 128, 256}) {
-        if (n_warps * N > 512) continue;
-        rate_kernel<<<148, 128, 162 * 1024 + 1024>>>(M, N, mn, iters, a_step, n_acc, n_warps, swz, dout);
-        cudaError_t e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { printf(" [%s]\n", cudaGetErrorString(e)); return 1; }
-        long long cyc;
-        cudaMemcpy(&cyc, dout, 8, cudaMemcpyDeviceToHost);
-        printf("  N=%3d %6.1f", N, static_cast<double>(cyc) / iters);
+  for (int mn : {1, 0})
+    for (int b_lbo : {8192, 9216, 128})
+      for (int b_shift : {0, 1, 2, 8}) {
+        const int a_step = 0, M = 128, n_acc = 1, swz = 128, n_warps = 1;
+        printf("%s M=128 swizzle=128 B start +%d rows, B atom stride %5d :", mn ? "MN-major" : "K-major ", b_shift, b_lbo);
+        for (int N : {64, 128, 256}) {
+          rate_kernel<<<148, 128, 162 * 1024 + 1024>>>(M, N, mn, iters, a_step, n_acc, n_warps, swz, b_shift, b_lbo, dout);
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) { printf(" [%s]\n", cudaGetErrorString(e)); return 1; }
+          long long cyc;
+          cudaMemcpy(&cyc, dout, 8, cudaMemcpyDeviceToHost);
+          printf("  N=%3d %6.1f", N, static_cast<double>(cyc) / iters);
+        }
+        printf("  clk/MMA\n");
       }
-      printf("  clk/MMA (all warps together)\n");
-    }
   return 0;
 }
