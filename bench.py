@@ -29,6 +29,19 @@ GFLOP_PER_TILE = 397.31           # algorit
 RES_CONV_GFLOP_PER_TILE = 4.8318  # one residual 3x3 conv, 256->256 @ 64x64: 2 * 4096 * 256 * 2304
 
 
+def ncu_traffic_bytes(report="r01_res_fprop.ncu-rep"):
+    """DRAM bytes (read + write) per launch of the dominant kernel from the committed ncu --set full summary
+    (profiles/r01_ncu_kernels_v6.csv, produced by tools/profile_kernels.sh + tools/summarize_ncu.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_kernels_v6.csv")
+    if not os.path.exists(path):
+        return None
+    import csv
+    for row in csv.DictReader(open(path)):
+        if row["report"] == report:
+            return int((float(row["dram_read_MB"]) + float(row["dram_write_MB"])) * 1e6)
+    return None
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -222,9 +235,9 @@ def run_native(args):
     if res_ms:
         avg = sum(res_ms) / len(res_ms)
         achieved = RES_CONV_GFLOP_PER_TILE * B / avg  # GFLOP / ms == TFLOP/s
-        roofline = {"bound": "tensor", "kernel": "igemm_fprop_kernel<64> (residual 3x3 conv 256->256 @64x64)",
+        roofline = {"bound": "tensor", "kernel": "igemm_fprop2_kernel<64> (2-CTA tcgen05, residual 3x3 conv 256->256 @64x64)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "traffic": None, "peak_source": peak_src + ", sustained bf16", "launches_timed": len(res_ms),
+                    "traffic": ncu_traffic_bytes(), "peak_source": peak_src + ", sustained bf16", "launches_timed": len(res_ms),
                     "avg_ms": avg}
     conv_ms = sum(sum(v) for k, v in prof.items() if k.split()[0] in ("fprop", "dgrad", "wgrad")) / 2
     all_ms = sum(sum(v) for v in prof.values()) / 2

@@ -104,6 +104,93 @@ def patchgan_plan(in_channels, batch_norm):
     return p
 
 
+# Pix2Pix U-Net (model_architectures.py:9-63). Blocks from the outside in: (outer_nc, inner_nc, kind)
+PIX2PIX_BLOCKS = [(3, 64, "outermost"), (64, 128, "middle"), (128, 256, "middle"), (256, 512, "middle"),
+                  (512, 512, "dropout"), (512, 512, "dropout"), (512, 512, "dropout"), (512, 512, "innermost")]
+
+
+def pix2pix_block_prefix(level):
+    """state_dict prefix of block `level` (0 = outermost): the sub-block is child 1 of the outermost Sequential and
+    child 3 of every other one (model_architectures.py:41,53-55)."""
+    prefix = "model.model."
+    for lv in range(level):
+        prefix += ("1." if lv == 0 else "3.") + "model."
+    return prefix
+
+
+def pix2pix_layer_names(level):
+    """(downconv, downnorm, upconv, upnorm) state_dict names of block `level` (None where the layer does not exist)."""
+    pre = pix2pix_block_prefix(level)
+    kind = PIX2PIX_BLOCKS[level][2]
+    if kind == "outermost":
+        return pre + "0", None, pre + "3", None           # [downconv, sub, uprelu, upconv, tanh]
+    if kind == "innermost":
+        return pre + "1", None, pre + "3", pre + "4"      # [downrelu, downconv, uprelu, upconv, upnorm]
+    return pre + "1", pre + "2", pre + "5", pre + "6"     # [downrelu, downconv, downnorm, sub, uprelu, upconv, upnorm, (dropout)]
+
+
+def _bn_entries(params, name, c):
+    params[name + ".weight"] = _normal((c,), 1.0)
+    params[name + ".bias"] = torch.zeros(c)
+    params[name + ".running_mean"] = torch.zeros(c)
+    params[name + ".running_var"] = torch.ones(c)
+    params[name + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+
+def init_pix2pix_generator(input_channels):
+    """Pix2PixGenerator.__init__ (model_architectures.py:13-19) builds the blocks from the INSIDE out, each drawing
+    downconv then upconv (:32,41,46,51); `.apply(initialise_weights)` (model.py:103) then visits the Sequential children
+    in registration order: down layers on the way in, up layers on the way out."""
+    shapes = {}
+    for level in reversed(range(8)):
+        outer, inner, kind = PIX2PIX_BLOCKS[level]
+        in_nc = input_channels if kind == "outermost" else outer
+        down = (inner, in_nc, 4, 4)
+        up = (inner if kind == "innermost" else inner * 2, outer, 4, 4)  # ConvTranspose2d weight [Cin][Cout][4][4]
+        shapes[level] = (down, up)
+        torch.empty(down).uniform_(-1, 1)
+        torch.empty(up).uniform_(-1, 1)
+        if kind == "outermost":
+            torch.empty(outer).uniform_(-1, 1)  # the only layer with a bias (:41)
+    draws = {}
+
+    def visit(level):  # nn.Module.apply order
+        outer, inner, kind = PIX2PIX_BLOCKS[level]
+        dn, dnorm, un, unorm = pix2pix_layer_names(level)
+        draws[dn + ".weight"] = _normal(shapes[level][0])
+        if dnorm:
+            _bn_entries(draws, dnorm, inner)
+        if kind != "innermost":
+            visit(level + 1)
+        draws[un + ".weight"] = _normal(shapes[level][1])
+        if kind == "outermost":
+            draws[un + ".bias"] = torch.zeros(outer)
+        if unorm:
+            _bn_entries(draws, unorm, outer)
+
+    visit(0)
+    params = OrderedDict()
+
+    def order(level):  # state_dict order: registration order, depth first
+        outer, inner, kind = PIX2PIX_BLOCKS[level]
+        dn, dnorm, un, unorm = pix2pix_layer_names(level)
+        keys = [dn + ".weight"]
+        if dnorm:
+            keys += [dnorm + s for s in (".weight", ".bias", ".running_mean", ".running_var", ".num_batches_tracked")]
+        for k in keys:
+            params[k] = draws[k]
+        if kind != "innermost":
+            order(level + 1)
+        keys = [un + ".weight"] + ([un + ".bias"] if kind == "outermost" else [])
+        if unorm:
+            keys += [unorm + s for s in (".weight", ".bias", ".running_mean", ".running_var", ".num_batches_tracked")]
+        for k in keys:
+            params[k] = draws[k]
+
+    order(0)
+    return params
+
+
 def init_model(model, topography="all", seed=47, training=True):
     """Model.__init__ wiring (model.py:78-104): seed once, then generator(s) and discriminator(s) in this order."""
     n = TOPOGRAPHY_CHANNELS[topography]
@@ -120,8 +207,12 @@ def init_model(model, topography="all", seed=47, training=True):
         if training:
             nets["pre_discriminator"] = _init_from_plan(patchgan_plan(n, False))
             nets["post_discriminator"] = _init_from_plan(patchgan_plan(n, False))
+    elif model == "pix2pix":
+        nets["generator"] = init_pix2pix_generator(n)
+        if training:
+            nets["discriminator"] = _init_from_plan(patchgan_plan(n + 3, True))
     else:
-        raise NotImplementedError("oracle covers pairedattention, attentiongan, cyclegan (Pix2Pix: see pix2pix_oracle)")
+        raise NotImplementedError(model)
     return nets
 
 
@@ -192,8 +283,60 @@ def patchgan_forward(p, x):
     return F.conv2d(x, p["model.11.weight"], p["model.11.bias"], stride=1, padding=1)
 
 
+def _bn(p, name, x):
+    """nn.BatchNorm2d in training mode: batch statistics, running statistics updated in place (momentum 0.1)."""
+    p[name + ".num_batches_tracked"] += 1
+    return F.batch_norm(x, p[name + ".running_mean"], p[name + ".running_var"], p[name + ".weight"], p[name + ".bias"],
+                        training=True, momentum=0.1, eps=1e-5)
+
+
+def pix2pix_generator_forward(p, x, masks=None):
+    """Pix2PixGenerator (model_architectures.py:9-63) in training mode. The LeakyReLU / ReLU layers are IN PLACE
+    (:33-34): downrelu overwrites the block input that torch.cat((x, model(x))) (:63) then reads, and uprelu
+    overwrites the concatenated output of the sub-block, so a block returns cat(lrelu(x), up(...)) and the up
+    convolution sees relu(cat(lrelu(e), d)) = cat(relu(e), relu(d)).
+    masks: optional dropout masks (values 0 or 2) for the three dropout blocks in execution order (levels 6, 5, 4);
+    None draws them with F.dropout from the global RNG as the reference does."""
+    enc = []  # e_k: output of block k's downconv (+ downnorm)
+    t = x
+    for level in range(8):
+        dn, dnorm, _, _ = pix2pix_layer_names(level)
+        if level > 0:
+            t = F.leaky_relu(t, 0.2)
+        t = F.conv2d(t, p[dn + ".weight"], None, stride=2, padding=1)
+        if dnorm:
+            t = _bn(p, dnorm, t)
+        enc.append(t)
+    mi = 0
+    d = None
+    for level in reversed(range(8)):
+        _, _, un, unorm = pix2pix_layer_names(level)
+        kind = PIX2PIX_BLOCKS[level][2]
+        src = F.relu(enc[level]) if kind == "innermost" else torch.cat((F.relu(enc[level]), F.relu(d)), 1)
+        d = F.conv_transpose2d(src, p[un + ".weight"], p.get(un + ".bias"), stride=2, padding=1)
+        if unorm:
+            d = _bn(p, unorm, d)
+        if kind == "dropout":
+            if masks is None:
+                d = F.dropout(d, 0.5, training=True)
+            else:
+                d = d * masks[mi]
+                mi += 1
+    return torch.tanh(d)
+
+
+def patchgan_bn_forward(p, x):
+    """Pix2PixDiscriminator (model_architectures.py:65-85): BatchNorm PatchGAN, no bias on the normalised convs"""
+    x = F.leaky_relu(F.conv2d(x, p["model.0.weight"], p["model.0.bias"], stride=2, padding=1), 0.2)
+    x = F.leaky_relu(_bn(p, "model.3", F.conv2d(x, p["model.2.weight"], None, stride=2, padding=1)), 0.2)
+    x = F.leaky_relu(_bn(p, "model.6", F.conv2d(x, p["model.5.weight"], None, stride=2, padding=1)), 0.2)
+    x = F.leaky_relu(_bn(p, "model.9", F.conv2d(x, p["model.8.weight"], None, stride=1, padding=1)), 0.2)
+    return F.conv2d(x, p["model.11.weight"], p["model.11.bias"], stride=1, padding=1)
+
+
 GENERATOR_FORWARD = {"pairedattention": attention_generator_forward, "attentiongan": attention_generator_forward,
-                     "cyclegan": cyclegan_generator_forward}
+                     "cyclegan": cyclegan_generator_forward, "pix2pix": pix2pix_generator_forward}
+DISCRIMINATOR_FORWARD = {"pix2pix": patchgan_bn_forward}
 
 
 # ---------------------------------------------------------------------------------------------- optimiser
@@ -228,7 +371,8 @@ def lambda_rule(epoch, num_epochs):
 
 
 def _float_params(p):
-    return [v for v in p.values() if v.is_floating_point() and v.dim() > 0]
+    """trainable tensors: everything but the BatchNorm buffers (running statistics, batch counter)"""
+    return [v for k, v in p.items() if v.is_floating_point() and v.dim() > 0 and ".running_" not in k]
 
 
 def _req(p, flag):
@@ -238,11 +382,13 @@ def _req(p, flag):
 
 # ---------------------------------------------------------------------------------------------- paired step
 class PairedTrainer:
-    """Model.train_paired inner loop (model.py:611-651) for the InstanceNorm models (PairedAttention)."""
+    """Model.train_paired inner loop (model.py:611-651): PairedAttention (InstanceNorm) and Pix2Pix (BatchNorm in
+    training mode + dropout from the global torch RNG, seeded per epoch at model.py:609)."""
 
     def __init__(self, nets, model="pairedattention"):
         self.G, self.D = nets["generator"], nets["discriminator"]
         self.g_forward = GENERATOR_FORWARD[model]
+        self.d_forward = DISCRIMINATOR_FORWARD.get(model, patchgan_forward)
         self.opt_d = Adam(_float_params(self.D))  # model.py:121
         self.opt_g = Adam(_float_params(self.G))  # model.py:122
 
@@ -253,15 +399,15 @@ class PairedTrainer:
         concat_real = torch.cat((input_stack, output_image), 1)                      # :616
         concat_synth = torch.cat((input_stack, synthetic), 1)                        # :617
         _req(D, True)                                                                # :620-622
-        pred_s = patchgan_forward(D, concat_synth.detach())                          # :624
+        pred_s = self.d_forward(D, concat_synth.detach())                          # :624
         loss_d_synth = F.mse_loss(pred_s, torch.full(pred_s.shape, 0.0))             # :626-627
-        pred_r = patchgan_forward(D, concat_real)                                    # :628
+        pred_r = self.d_forward(D, concat_real)                                    # :628
         loss_d_real = F.mse_loss(pred_r, torch.full(pred_s.shape, 1.0))              # :629-630
         loss_d = (loss_d_synth + loss_d_real) * 0.5                                  # :631
         dparams = _float_params(D)
         self.opt_d.step(torch.autograd.grad(loss_d, dparams))                        # :632-633
         _req(D, False)                                                               # :636-638
-        pred_s = patchgan_forward(D, concat_synth)                                   # :640 (updated D)
+        pred_s = self.d_forward(D, concat_synth)                                   # :640 (updated D)
         loss_g_adv = F.mse_loss(pred_s, torch.full(pred_s.shape, 1.0))               # :641-642
         loss_l1 = F.l1_loss(synthetic, output_image) * 100                           # :643
         gparams = _float_params(G)

@@ -64,8 +64,8 @@ def param_digest(module):
             for k, v in module.state_dict().items() if v.is_floating_point()}
 
 
-def run_paired(ref_model, size, batch, steps):
-    M = ref_model.Model(model="pairedattention", dataset_subset="usa", dataset_dem="same", data_path="/tmp/none",
+def run_paired(ref_model, size, batch, steps, model="pairedattention"):
+    M = ref_model.Model(model=model, dataset_subset="usa", dataset_dem="same", data_path="/tmp/none",
                         num_epochs=200, topography="all", resize=512, crop=4, training_model=True, seed=47)
     init = {"generator": param_digest(M.generator), "discriminator": param_digest(M.discriminator)}
     per_step = []
@@ -80,12 +80,14 @@ def run_paired(ref_model, size, batch, steps):
         per_step.append([float(M.all_losses[k][-1]) for k in
                          ("all_losses_discriminator_real", "all_losses_discriminator_synthetic",
                           "all_losses_generator_synthetic", "all_l1_losses_generator_synthetic")])
-    x = data[0][0]
-    with torch.no_grad():
-        out = M.generator(x)
-    return {"size": size, "batch": batch, "losses": per_step, "init": init,
-            "final_generator_output": sample(out), "final_mask": sample(M.generator.last_attention_mask),
-            "final": {"generator": param_digest(M.generator), "discriminator": param_digest(M.discriminator)}}
+    res = {"size": size, "batch": batch, "losses": per_step, "init": init, "epoch_seed": M.num_epochs,
+           "final": {"generator": param_digest(M.generator), "discriminator": param_digest(M.discriminator)}}
+    if model == "pairedattention":
+        with torch.no_grad():
+            out = M.generator(data[0][0])
+        res["final_generator_output"] = sample(out)
+        res["final_mask"] = sample(M.generator.last_attention_mask)
+    return res
 
 
 def run_cycle(ref_model, name, size, batch, steps, identity):
@@ -136,6 +138,9 @@ def main():
     out = {"torch": torch.__version__, "note": "outputs of the unmodified reference, CPU fp32"}
     out["pairedattention_64"] = run_paired(ref_model, 64, 2, 3)
     out["pairedattention_256"] = run_paired(ref_model, 256, 1, 2)
+    # Pix2Pix: BatchNorm in training mode + dropout drawn from the global RNG that train_paired seeds with the epoch
+    # number (model.py:609; every step here is its own "epoch" 200). 256x256 is the smallest input of the 8-level U-Net
+    out["pix2pix_256"] = run_paired(ref_model, 256, 1, 2, model="pix2pix")
     out["cyclegan_64"] = run_cycle(ref_model, "cyclegan", 64, 1, 2, False)
     out["attentiongan_64_identity"] = run_cycle(ref_model, "attentiongan", 64, 1, 2, True)
     out["flood_mask"] = flood_mask_facts()

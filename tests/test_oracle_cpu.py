@@ -111,3 +111,26 @@ def test_oracle_forward_matches_live_reference_modules():
     xd = torch.rand(1, 12, 64, 64)
     with torch.no_grad():
         torch.testing.assert_close(O.patchgan_forward(p, xd), d(xd), rtol=1e-5, atol=1e-6)
+
+
+def test_pix2pix_oracle_matches_reference_golden():
+    """Pix2Pix (BASELINE.json configs[0]): 8-level U-Net with BatchNorm in training mode, in-place activations feeding
+    the skip connections and dropout from the torch RNG seeded per epoch (model.py:609)."""
+    gold = GOLD["pix2pix_256"]
+    torch.set_num_threads(8)
+    nets = O.init_model("pix2pix", "all", seed=47)
+    assert len(nets["generator"]) == 82
+    assert_digest(digest(nets["generator"]), gold["init"]["generator"], 1e-12, "G init")
+    assert_digest(digest(nets["discriminator"]), gold["init"]["discriminator"], 1e-12, "D init")
+    tr = O.PairedTrainer(nets, "pix2pix")
+    for step in range(len(gold["losses"])):
+        x, y = O.synthetic_batch(step, gold["batch"], 9, gold["size"])
+        torch.manual_seed(gold["epoch_seed"])
+        out = tr.step(x, y)
+        got = [out[k] for k in ("losses_discriminator_real", "losses_discriminator_synthetic",
+                                "losses_generator_synthetic", "l1_losses_generator_synthetic")]
+        for g, w in zip(got, gold["losses"][step]):
+            assert abs(g - w) <= 2e-4 * abs(w) + 1e-5, f"pix2pix step {step}: {got} vs {gold['losses'][step]}"
+    # parameters AND BatchNorm running statistics after the two steps
+    assert_digest(digest(nets["generator"]), gold["final"]["generator"], 2e-3, "G final")
+    assert_digest(digest(nets["discriminator"]), gold["final"]["discriminator"], 2e-3, "D final")
