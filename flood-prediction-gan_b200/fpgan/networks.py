@@ -432,3 +432,200 @@ class PatchGANNet(_NetBase):
         dy1 = ActBuf(t["a1"].n, t["a1"].h, t["a1"].w, t["a1"].c, zero=False)
         ops.act_bwd(da1, t["a1"], ACT_LEAKY, dy1)
         return self._conv_bwd("model.0", t["din"], dy1, grads, need_dx)
+
+
+# ------------------------------------------------------------------------------------------------ Pix2Pix
+class _BatchNormMixin:
+    """BatchNorm2d in training mode for the executors below: batch statistics + running-statistics side effects."""
+
+    def _bn_forward(self, y, bn, act1, z1, act2=ACT_NONE, z2=None, mask=None):
+        stats = torch.empty(y.c * 2, dtype=torch.float32, device=y.t.device)
+        ops.batch_stats(y, stats, bn.eps)
+        if bn.track_running_stats and bn.training:
+            ops.batchnorm_running_update(stats, y.n * y.h * y.w, bn.running_mean, bn.running_var, bn.eps,
+                                         bn.momentum)
+            bn.num_batches_tracked += 1
+        ops.batchnorm_apply(y, stats, bn.weight.detach(), bn.bias.detach(), act1, z1, act2, z2, mask=mask)
+        return stats
+
+    def _bn_backward(self, name, bn, dz1, act1, y, stats, grads, dz2=None, act2=ACT_NONE, mask=None):
+        dy = ActBuf(y.n, y.h, y.w, y.c, zero=False)
+        dg = grads[name + ".weight"] if grads is not None else None
+        db = grads[name + ".bias"] if grads is not None else None
+        ops.batchnorm_bwd(dz1, act1, y, stats, bn.weight.detach(), bn.bias.detach(), dy, dgamma=dg, dbeta=db, dz2=dz2,
+                          act2=act2, mask=mask)
+        if grads is not None and self.grad_ready is not None:
+            self.grad_ready(name + ".weight")
+            self.grad_ready(name + ".bias")
+        return dy
+
+
+class Pix2PixGeneratorNet(_NetBase, _BatchNormMixin):
+    """Pix2PixGenerator (model_architectures.py:9-63): 8-level U-Net of 4x4 stride-2 (transposed) convolutions,
+    BatchNorm2d with batch statistics, dropout in three blocks. The reference's in-place activations make a block
+    return cat(lrelu(x), up(...)) and hand relu(cat(...)) to the up-convolution (see oracle.pix2pix_generator_forward);
+    here every encoder activation e_k is written twice -- lrelu(e_k) for the next down-convolution and relu(e_k)
+    straight into the first half of level k's concatenation buffer -- and relu(d_{k+1}) into its second half."""
+
+    # (outer_nc, inner_nc, kind) from the outside in
+    BLOCKS = [(3, 64, "outermost"), (64, 128, "middle"), (128, 256, "middle"), (256, 512, "middle"),
+              (512, 512, "dropout"), (512, 512, "dropout"), (512, 512, "dropout"), (512, 512, "innermost")]
+
+    def __init__(self, module):
+        super().__init__(module)
+        self.levels = []
+        blk, prefix = module.model, "model.model."
+        for level, (outer, inner, kind) in enumerate(self.BLOCKS):
+            seq = blk.model
+            if kind == "outermost":
+                idx = dict(down=0, sub=1, up=3)
+            elif kind == "innermost":
+                idx = dict(down=1, up=3, upnorm=4)
+            else:
+                idx = dict(down=1, downnorm=2, sub=3, up=5, upnorm=6)
+            lv = {"kind": kind, "outer": outer, "inner": inner,
+                  "down": prefix + str(idx["down"]), "up": prefix + str(idx["up"]),
+                  "downnorm": prefix + str(idx["downnorm"]) if "downnorm" in idx else None,
+                  "upnorm": prefix + str(idx["upnorm"]) if "upnorm" in idx else None,
+                  "downnorm_m": seq[idx["downnorm"]] if "downnorm" in idx else None,
+                  "upnorm_m": seq[idx["upnorm"]] if "upnorm" in idx else None}
+            self._add(lv["down"], seq[idx["down"]], 4, 2, 1)
+            self._add(lv["up"], seq[idx["up"]], 4, 2, 1, transposed=True, use_bias=(kind == "outermost"))
+            self.levels.append(lv)
+            if "sub" in idx:
+                prefix += str(idx["sub"]) + ".model."
+                blk = seq[idx["sub"]]
+        self.dropout_seed = 0
+        self.dropout_masks = None  # test hook: list of three uint8 masks [pixels][c] in execution order
+
+    def forward(self, x):
+        self.repack()
+        B, C, H, W = x.shape
+        if H % 256 or W % 256:
+            raise RuntimeError("Pix2PixGenerator: the 8-level U-Net needs inputs that are multiples of 256 pixels")
+        t = {"x": x}
+        xin = ActBuf(B, H, W, 16, zero=False)
+        ops.pack_nchw(x, xin, 0, zero_rest=True)
+        t["xin"] = xin
+        cats = []  # cats[k]: input of level k's up-convolution = [relu(e_k) | relu(d_{k+1})]
+        cur = xin
+        for k, lv in enumerate(self.levels):
+            h, w, c = cur.h // 2, cur.w // 2, lv["inner"]
+            if lv["kind"] == "innermost":
+                r7 = self._conv(cur, lv["down"], act=ACT_RELU)  # only consumer: relu(e_7) -> up-convolution
+                t["r7"] = r7
+                cats.append(r7)
+                break
+            cat = ActBuf(B, h, w, 2 * c, zero=False)
+            cats.append(cat)
+            if lv["kind"] == "outermost":
+                a = self._conv(cur, lv["down"], act=ACT_LEAKY)  # a_0 = lrelu(e_0); relu(e_0) = relu(a_0)
+                ops.batchnorm_apply(a, None, None, None, ACT_RELU, cat.channels(0, c))
+                t["y0"] = a
+            else:
+                y = self._conv(cur, lv["down"])
+                a = ActBuf(B, h, w, c, zero=False)
+                t[f"s{k}"] = self._bn_forward(y, lv["downnorm_m"], ACT_LEAKY, a, ACT_RELU, cat.channels(0, c))
+                t[f"y{k}"] = y
+            t[f"a{k}"] = a
+            cur = a
+        t["cats"] = cats
+        masks = []
+        for k in range(7, 0, -1):  # up path: level k writes relu(d_k) into the second half of cats[k - 1]
+            lv = self.levels[k]
+            u = self._conv(cats[k], lv["up"])
+            mask = None
+            if lv["kind"] == "dropout":
+                if self.dropout_masks is not None:
+                    mask = self.dropout_masks[len(masks)]
+                else:
+                    mask = torch.empty(u.n * u.h * u.w * u.c, dtype=torch.uint8, device=x.device)
+                    self.dropout_seed += 1
+                    ops.dropout_mask(mask, torch.initial_seed() * 1000003 + self.dropout_seed)
+                masks.append(mask)
+            c = lv["outer"]
+            t[f"us{k}"] = self._bn_forward(u, lv["upnorm_m"], ACT_RELU, cats[k - 1].channels(c, c), mask=mask)
+            t[f"u{k}"] = u
+            t[f"m{k}"] = mask
+        t["o"] = self._conv(cats[0], self.levels[0]["up"], fp32=True, act=ACT_TANH)
+        out = torch.empty(B, 3, H, W, dtype=torch.float32, device=x.device)
+        ops.unpack_nchw(t["o"], out, 0)
+        return out, t
+
+    def backward(self, t, grads, dout_nchw, need_dx=False):
+        cats = t["cats"]
+        o = t["o"]
+        dpre = ActBuf(o.n, o.h, o.w, 16, zero=False)
+        ops.tanh_bwd_pack(dout_nchw, o, dpre)
+        dcat = self._conv_bwd(self.levels[0]["up"], cats[0], dpre, grads, True)  # [.., 2 * 64]
+        for k in range(1, 8):  # down the up path: gradient w.r.t. relu(d_k) is the second half of dcat_{k-1}
+            lv = self.levels[k]
+            c = lv["outer"]
+            du = self._bn_backward(lv["upnorm"], lv["upnorm_m"], dcat.channels(c, c), ACT_RELU, t[f"u{k}"],
+                                   t[f"us{k}"], grads, mask=t[f"m{k}"])
+            dcat_next = self._conv_bwd(lv["up"], cats[k], du, grads, True)
+            t[f"dcat{k - 1}"] = dcat
+            dcat = dcat_next
+        # innermost: dcat is the gradient w.r.t. r7 = relu(e_7)
+        lv = self.levels[7]
+        de = ActBuf(dcat.n, dcat.h, dcat.w, dcat.c, zero=False)
+        ops.act_bwd(dcat, t["r7"], ACT_RELU, de)
+        da = self._conv_bwd(lv["down"], t["a6"], de, grads, True)
+        for k in range(6, 0, -1):  # e_k has two consumers: lrelu -> down conv (da), relu -> skip (first half of dcat_k)
+            lv = self.levels[k]
+            c = lv["inner"]
+            dy = self._bn_backward(lv["downnorm"], lv["downnorm_m"], da, ACT_LEAKY, t[f"y{k}"], t[f"s{k}"], grads,
+                                   dz2=t[f"dcat{k}"].channels(0, c), act2=ACT_RELU)
+            da = self._conv_bwd(lv["down"], t[f"a{k - 1}"], dy, grads, True)
+        lv = self.levels[0]
+        de0 = ActBuf(da.n, da.h, da.w, da.c, zero=False)
+        ops.batchnorm_bwd(da, ACT_LEAKY, t["y0"], None, None, None, de0, dz2=t["dcat0"].channels(0, lv["inner"]),
+                          act2=ACT_RELU)
+        dxin = self._conv_bwd(lv["down"], t["xin"], de0, grads, need_dx)
+        if not need_dx:
+            return None
+        c_in = self.layers[lv["down"]].c_valid
+        dx = torch.zeros(dxin.n, c_in, dxin.h, dxin.w, dtype=torch.float32, device=dxin.t.device)
+        ops.unpack_nchw(dxin, dx, 0)
+        return dx
+
+
+class PatchGANBatchNormNet(_NetBase, _BatchNormMixin):
+    """Pix2PixDiscriminator (model_architectures.py:65-85): 70x70 PatchGAN with BatchNorm2d (batch statistics) and
+    no bias on the normalised convolutions."""
+
+    def __init__(self, module):
+        super().__init__(module)
+        seq = module.model
+        self._add("model.0", seq[0], 4, 2, 1, use_bias=True)
+        self._add("model.2", seq[2], 4, 2, 1)
+        self._add("model.5", seq[5], 4, 2, 1)
+        self._add("model.8", seq[8], 4, 1, 1)
+        self._add("model.11", seq[11], 4, 1, 1, use_bias=True)
+        self.norms = {"model.3": seq[3], "model.6": seq[6], "model.9": seq[9]}
+
+    def forward(self, x):
+        self.repack()
+        B, C, H, W = x.shape
+        din = ActBuf(B, H, W, 16, zero=False)
+        ops.pack_nchw(x, din, 0, zero_rest=True)
+        t = {"din": din}
+        t["a1"] = self._conv(din, "model.0", act=ACT_LEAKY)
+        cur = t["a1"]
+        for i, (conv, norm) in enumerate((("model.2", "model.3"), ("model.5", "model.6"), ("model.8", "model.9")), 2):
+            y = self._conv(cur, conv)
+            a = ActBuf(y.n, y.h, y.w, y.c, zero=False)
+            t[f"s{i}"] = self._bn_forward(y, self.norms[norm], ACT_LEAKY, a)
+            t[f"y{i}"], t[f"a{i}"] = y, a
+            cur = a
+        t["logits"] = self._conv(cur, "model.11", fp32=True)
+        return t["logits"].to_nchw(1), t
+
+    def backward(self, t, dlogits, grads, need_dx):
+        d = self._conv_bwd("model.11", t["a4"], dlogits, grads, True)
+        for i, (conv, norm) in zip((4, 3, 2), (("model.8", "model.9"), ("model.5", "model.6"), ("model.2", "model.3"))):
+            dy = self._bn_backward(norm, self.norms[norm], d, ACT_LEAKY, t[f"y{i}"], t[f"s{i}"], grads)
+            d = self._conv_bwd(conv, t[f"a{i - 1}"], dy, grads, True)
+        dy1 = ActBuf(t["a1"].n, t["a1"].h, t["a1"].w, t["a1"].c, zero=False)
+        ops.act_bwd(d, t["a1"], ACT_LEAKY, dy1)
+        return self._conv_bwd("model.0", t["din"], dy1, grads, need_dx)

@@ -232,6 +232,36 @@ def instnorm_bwd(dz, y, stats, act, dy, dz2=None, dres=None):
          _stream())
 
 
+def batch_stats(y, stats, eps=1e-5):
+    """Per-channel {mean, rstd} over the whole batch: InstanceNorm statistics of the batch viewed as one image."""
+    flat = ActBuf(1, y.n * y.h, y.w, y.c, tensor=y.t, c0=y.c0, c_stride=y.c_stride)
+    instnorm_stats(flat, stats, eps)
+
+
+def batchnorm_apply(y, stats, gamma, beta, act1, z1, act2=ACT_NONE, z2=None, mask=None, mask_scale=2.0):
+    _run("batchnorm_apply", 1, "fpg_batchnorm_apply", y.ref(), _ptr(stats), _ptr(gamma), _ptr(beta), _ptr(mask),
+         float(mask_scale), act1, z1.ref(), act2, z2.ref() if z2 is not None else None, _stream())
+
+
+def batchnorm_bwd(dz1, act1, y, stats, gamma, beta, dy, dgamma=None, dbeta=None, dz2=None, act2=ACT_NONE, mask=None,
+                  mask_scale=2.0, accumulate=False):
+    n = L.load().fpg_batchnorm_scratch_floats(y.ref())
+    ws = workspace(n * 4, y.t.device)
+    _run("batchnorm_bwd", 3, "fpg_batchnorm_bwd", dz1.ref(), act1, dz2.ref() if dz2 is not None else None, act2,
+         _ptr(mask), float(mask_scale), y.ref(), _ptr(stats), _ptr(gamma), _ptr(beta), dy.ref(), _ptr(dgamma),
+         _ptr(dbeta), 1 if accumulate else 0, _ptr(ws), _stream())
+
+
+def batchnorm_running_update(stats, count, running_mean, running_var, eps=1e-5, momentum=0.1):
+    _run("batchnorm_running", 1, "fpg_batchnorm_running_update", _ptr(stats), running_mean.numel(), int(count),
+         float(eps), float(momentum), _ptr(running_mean), _ptr(running_var), _stream())
+
+
+def dropout_mask(mask, seed, keep=0.5):
+    _run("dropout_mask", 1, "fpg_dropout_mask", _ptr(mask), mask.numel(), C.c_uint64(int(seed) & (2 ** 64 - 1)),
+         float(keep), _stream())
+
+
 def act_bwd(dz, z, act, dx):
     _run("act_bwd", 1, "fpg_act_bwd", dz.ref(), z.ref(), act, dx.ref(), _stream())
 

@@ -261,9 +261,10 @@ class Model:
         return self._native
 
     def train_paired(self):
-        """Paired training (reference :598-658). PairedAttention runs the fused native step."""
+        """Paired training (reference :598-658). PairedAttention runs the fused native step; Pix2Pix (BatchNorm with
+        batch statistics, dropout) steps through the drop-in modules' autograd path."""
         if self.model != "pairedattention":
-            raise NotImplementedError(f"train_paired for {PRETTY[self.model]} is not available in this build yet")
+            return self._train_paired_modules()
         tr = self._ensure_native_paired()
         for epoch in range(self.starting_epoch, self.num_epochs + 1):
             t0 = time.time()
@@ -282,6 +283,48 @@ class Model:
                 if len(pending) >= self.log_interval:
                     self._flush_losses(pending, losses)
             self._flush_losses(pending, losses)
+            self.scheduler_discriminator.step()
+            self.scheduler_generator.step()
+            self.save_results(epoch=epoch, losses=losses, epoch_start_time=t0)
+
+    def _train_paired_modules(self):
+        """The reference loop (model.py:598-658) over the drop-in modules: every network call is one autograd node
+        executing native kernels; losses and Adam are the reference's torch objects."""
+        dev = self.device
+        G, D = self.generator, self.discriminator
+
+        def lsgan(pred, target):
+            return self.loss_func(pred, torch.full(pred.shape, target, dtype=torch.float32, device=dev))
+
+        for epoch in range(self.starting_epoch, self.num_epochs + 1):
+            t0 = time.time()
+            losses = self.initialise_loss_storage(overall=False)
+            D.train()
+            G.train()
+            torch.manual_seed(epoch)
+            for input_stack, output_image, _ in self.train_loader:
+                x = input_stack.to(dev).float()
+                y = output_image.to(dev).float()
+                synthetic = G(x)
+                concat_real = torch.cat((x, y), 1)
+                concat_synth = torch.cat((x, synthetic), 1)
+                for p in D.parameters():
+                    p.requires_grad = True
+                self.optimizer_discriminator.zero_grad()
+                d_syn = lsgan(D(concat_synth.detach()), 0.0)
+                d_real = lsgan(D(concat_real), 1.0)
+                ((d_syn + d_real) * 0.5).backward()
+                self.optimizer_discriminator.step()
+                for p in D.parameters():
+                    p.requires_grad = False
+                self.optimizer_generator.zero_grad()
+                g_adv = lsgan(D(concat_synth), 1.0)
+                g_l1 = self.l1_loss(synthetic, y) * 100
+                (g_adv + g_l1).backward()
+                self.optimizer_generator.step()
+                vals = torch.stack([d_real.detach(), d_syn.detach(), g_adv.detach(), g_l1.detach()]).tolist()
+                for k, v in zip(native_trainer.PairedTrainer.LOSS_KEYS, vals):
+                    losses[k].append(v)
             self.scheduler_discriminator.step()
             self.scheduler_generator.step()
             self.save_results(epoch=epoch, losses=losses, epoch_start_time=t0)

@@ -216,3 +216,80 @@ class AttentionGANDiscriminator(_InstanceNormPatchGAN):
 class CycleGANDiscriminator(_InstanceNormPatchGAN):
     def __init__(self, input_channels):
         super().__init__(input_channels)
+
+
+# ------------------------------------------------------------------------------------------------ Pix2Pix
+class Pix2PixBlock(nn.Module):
+    """Parameter container of one U-Net block with the reference's Sequential layout (reference :25-63), so that the
+    nested state_dict keys (model.model.1.model.3...) and the construction / initialisation order are identical."""
+
+    def __init__(self, outer_nc, inner_nc, input_nc, submodule, outermost, innermost, use_dropout):
+        super().__init__()
+        self.outermost = outermost
+        if input_nc is None:
+            input_nc = outer_nc
+        downconv = nn.Conv2d(input_nc, inner_nc, kernel_size=4, stride=2, padding=1, bias=False)
+        downrelu, uprelu = nn.LeakyReLU(0.2, True), nn.ReLU(True)
+        downnorm, upnorm = nn.BatchNorm2d(inner_nc), nn.BatchNorm2d(outer_nc)
+        if outermost:
+            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1)
+            model = [downconv, submodule, uprelu, upconv, nn.Tanh()]
+        elif innermost:
+            upconv = nn.ConvTranspose2d(inner_nc, outer_nc, kernel_size=4, stride=2, padding=1, bias=False)
+            model = [downrelu, downconv, uprelu, upconv, upnorm]
+        else:
+            upconv = nn.ConvTranspose2d(inner_nc * 2, outer_nc, kernel_size=4, stride=2, padding=1, bias=False)
+            model = [downrelu, downconv, downnorm, submodule, uprelu, upconv, upnorm]
+            if use_dropout:
+                model.append(nn.Dropout(0.5))
+        self.model = nn.Sequential(*model)
+
+    def forward(self, x):
+        raise RuntimeError("U-Net blocks are executed by the enclosing generator's native executor")
+
+
+class Pix2PixGenerator(_NativeModule):
+    """reference :9-23. Always computes in training mode (batch statistics, dropout), as the reference does -- it
+    never calls .eval()."""
+    _executor_cls = networks.Pix2PixGeneratorNet
+
+    def __init__(self, input_channels):
+        super().__init__()
+        block = Pix2PixBlock(512, 512, None, None, False, True, False)
+        for _ in range(3):
+            block = Pix2PixBlock(512, 512, None, block, False, False, True)
+        block = Pix2PixBlock(256, 512, None, block, False, False, False)
+        block = Pix2PixBlock(128, 256, None, block, False, False, False)
+        block = Pix2PixBlock(64, 128, None, block, False, False, False)
+        self.model = Pix2PixBlock(3, 64, input_channels, block, True, False, False)
+
+    def _run_backward(self, net, tape, dout, grads, need_dx):
+        return net.backward(tape, grads, dout, need_dx=need_dx)
+
+
+class Pix2PixDiscriminator(_NativeModule):
+    """reference :65-85: BatchNorm PatchGAN on cat(input stack, image)."""
+    _executor_cls = networks.PatchGANBatchNormNet
+
+    def __init__(self, input_channels):
+        super().__init__()
+        seq = [nn.Conv2d(input_channels + 3, 64, kernel_size=4, stride=2, padding=1), nn.LeakyReLU(0.2, True)]
+        prev = 64
+        for mult in (2, 4):
+            seq += [nn.Conv2d(prev, 64 * mult, kernel_size=4, stride=2, padding=1, bias=False),
+                    nn.BatchNorm2d(64 * mult), nn.LeakyReLU(0.2, True)]
+            prev = 64 * mult
+        seq += [nn.Conv2d(prev, 512, kernel_size=4, stride=1, padding=1, bias=False), nn.BatchNorm2d(512),
+                nn.LeakyReLU(0.2, True)]
+        seq += [nn.Conv2d(512, 1, kernel_size=4, stride=1, padding=1)]
+        self.model = nn.Sequential(*seq)
+
+    def _run_backward(self, net, tape, dout, grads, need_dx):
+        dl = ops.ActBuf.from_nchw(dout, c_pad=16)
+        dd = net.backward(tape, dl, grads, need_dx)
+        if not need_dx:
+            return None
+        c = self.model[0].weight.shape[1]
+        dx = torch.empty(dd.n, c, dd.h, dd.w, dtype=torch.float32, device=dout.device)
+        ops.unpack_nchw(dd, dx, 0)
+        return dx

@@ -285,6 +285,33 @@ int fpg_act_bwd(const fpg_act* dz, const fpg_act* z, int act, const fpg_act* dx,
 int fpg_halo_fold(const fpg_act* a, const fpg_act* b, const fpg_act* c, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * BatchNorm2d in training mode + dropout -- the Pix2Pix U-Net and its BatchNorm PatchGAN
+ * (model_architectures.py:9-85; nn.BatchNorm2d(eps=1e-5, momentum=0.1, affine), nn.Dropout(0.5)).
+ * Batch statistics: fpg_instnorm_stats on the batch viewed as ONE image (n = 1, h = N*H) gives stats[c] = {mean, rstd}.
+ * All tensors halo-free NHWC bf16; destinations / gradients may be channel slices (c_stride > c) of the U-Net's
+ * concatenation buffers. In-place activations of the reference (:33-34,:63) give an encoder activation two
+ * consumers, lrelu(e) (next down-conv) and relu(e) (skip connection): hence two outputs / two upstream gradients.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* v = gamma * (y - mean) * rstd + beta (stats == NULL: v = y); v *= mask ? mask_scale : 0 (mask == NULL: none;
+ * mask: uint8 [n*h*w][c]); z1 = act1(v); z2 = act2(v) if z2 != NULL */
+int fpg_batchnorm_apply(const fpg_act* y, const float* stats, const float* gamma, const float* beta,
+                        const uint8_t* mask, float mask_scale, int act1, const fpg_act* z1, int act2,
+                        const fpg_act* z2, void* stream);
+/* Backward of the above. Upstream g = (dz1 * act1'(v) + dz2 * act2'(v)) * mask (dz2 may be NULL).
+ * stats != NULL: dy = gamma * rstd * (g - mean(g) - zhat * mean(g * zhat)), dbeta = sum g, dgamma = sum g * zhat
+ * (written, or added if accumulate != 0; either may be NULL). stats == NULL: dy = g (y supplies the sign of v).
+ * scratch: >= fpg_batchnorm_scratch_floats(y) floats. */
+int fpg_batchnorm_bwd(const fpg_act* dz1, int act1, const fpg_act* dz2, int act2, const uint8_t* mask,
+                      float mask_scale, const fpg_act* y, const float* stats, const float* gamma, const float* beta,
+                      const fpg_act* dy, float* dgamma, float* dbeta, int accumulate, float* scratch, void* stream);
+int64_t fpg_batchnorm_scratch_floats(const fpg_act* y);
+/* running_mean = (1-m) running_mean + m mean; running_var = (1-m) running_var + m var * count/(count-1) */
+int fpg_batchnorm_running_update(const float* stats, int32_t c, int64_t count, float eps, float momentum,
+                                 float* running_mean, float* running_var, void* stream);
+/* mask[i] = 1 with probability keep (counter-based hash of seed and i: reproducible), else 0 */
+int fpg_dropout_mask(uint8_t* mask, int64_t count, uint64_t seed, float keep, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Attention / content blend -- model_architectures.py:353-399.
  *   content: fp32, tanh already applied, 27 valid channels (9 RGB triplets) in a 32-channel buffer
  *   logits:  fp32, 10 valid channels in a 16-channel buffer (pre-softmax)

@@ -332,3 +332,63 @@ def test_flood_mask_bit_exact_and_confusion():
     tn = int(((ref == 0) & (truth == 0)).sum())
     fn = int(((ref == 0) & (truth == 1)).sum())
     assert counts.tolist() == [tp, fp, tn, fn]
+
+
+@pytest.mark.parametrize("shape,use_mask,two", [((2, 16, 16, 64), False, True), ((1, 2, 2, 512), True, False),
+                                               ((3, 8, 8, 128), True, True), ((2, 31, 31, 256), False, False)])
+def test_batchnorm_fwd_bwd(shape, use_mask, two):
+    """BatchNorm2d (batch statistics, affine, running statistics) + dropout mask + up to two activated outputs
+    (lrelu for the next down-convolution, relu for the skip connection) against torch autograd."""
+    from fpgan import ops
+    n, h, w, c = shape
+    g = torch.Generator(device="cuda").manual_seed(11)
+    y = bf16r(torch.randn(n, c, h, w, device="cuda", generator=g) * 2 + 0.3).requires_grad_(True)
+    gamma = (1 + 0.2 * torch.randn(c, device="cuda", generator=g)).requires_grad_(True)
+    beta = (0.1 * torch.randn(c, device="cuda", generator=g)).requires_grad_(True)
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    v = F.batch_norm(y, rm_ref, rv_ref, gamma, beta, training=True, momentum=0.1, eps=1e-5)
+    keep = (torch.rand(n, c, h, w, device="cuda", generator=g) < 0.5) if use_mask else None
+    if use_mask:
+        v = v * keep * 2.0
+    z1, z2 = F.leaky_relu(v, 0.2), F.relu(v)
+    dz1, dz2 = bf16r(torch.randn_like(z1)), bf16r(torch.randn_like(z2))
+    outs, gouts = ([z1, z2], [dz1, dz2]) if two else ([z1], [dz1])
+    dy_ref, dg_ref, db_ref = torch.autograd.grad(outs, (y, gamma, beta), gouts)
+
+    yb = ops.ActBuf.from_nchw(y.detach())
+    stats = torch.empty(c * 2, device="cuda")
+    ops.batch_stats(yb, stats)
+    ops.batchnorm_running_update(stats, n * h * w, rm, rv)
+    torch.testing.assert_close(rm, rm_ref, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(rv, rv_ref, rtol=1e-3, atol=1e-4)
+    mask = keep.permute(0, 2, 3, 1).contiguous().to(torch.uint8).reshape(-1) if use_mask else None
+    wide = ops.ActBuf(n, h, w, 2 * c)  # the second output lands in a channel slice of a wider buffer
+    z1b = ops.ActBuf(n, h, w, c)
+    ops.batchnorm_apply(yb, stats, gamma.detach(), beta.detach(), ops.ACT_LEAKY, z1b, ops.ACT_RELU,
+                        wide.channels(c, c) if two else None, mask=mask)
+    close_rms(z1b.to_nchw(), z1.detach(), 0.03, 0.004, "bn apply lrelu")
+    if two:
+        close_rms(wide.t[..., c:].permute(0, 3, 1, 2).float(), z2.detach(), 0.03, 0.004, "bn apply relu slice")
+        assert (wide.t[..., :c] == 0).all()
+    dyb = ops.ActBuf(n, h, w, c)
+    dg, db = torch.empty(c, device="cuda"), torch.empty(c, device="cuda")
+    gw = ops.ActBuf(n, h, w, 2 * c)
+    gw.t[..., :c] = dz2.permute(0, 2, 3, 1)
+    ops.batchnorm_bwd(ops.ActBuf.from_nchw(dz1), ops.ACT_LEAKY, yb, stats, gamma.detach(), beta.detach(), dyb, dg, db,
+                      dz2=gw.channels(0, c) if two else None, act2=ops.ACT_RELU, mask=mask)
+    close_rms(dyb.to_nchw(), dy_ref, 0.05, 0.006, "bn bwd dy")
+    close_rms(dg, dg_ref, 0.02, 0.005, "bn bwd dgamma")
+    close_rms(db, db_ref, 0.02, 0.005, "bn bwd dbeta")
+
+
+def test_dropout_mask_is_reproducible_and_fair():
+    from fpgan import ops
+    m1 = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    m2 = torch.empty_like(m1)
+    ops.dropout_mask(m1, 1234)
+    ops.dropout_mask(m2, 1234)
+    assert (m1 == m2).all() and set(m1.unique().tolist()) == {0, 1}
+    assert abs(m1.float().mean().item() - 0.5) < 5e-3
+    ops.dropout_mask(m2, 1235)
+    assert (m1 != m2).float().mean().item() > 0.4

@@ -286,3 +286,132 @@ def test_paired_100_steps_tracked_against_oracle():
           " | oracle " + ", ".join(f"{v:.4f}" for v in ref_mean.tolist()))
     for k, a, b in zip(keys, free_mean.tolist(), ref_mean.tolist()):
         assert abs(a - b) <= 0.05 * abs(b) + 1e-3, f"free-running mean of {k}: {a} vs oracle {b}"
+
+
+# ------------------------------------------------------------------------------------------------ Pix2Pix
+def _pix2pix_pair(seed=47):
+    from oracle import gan_oracle as O
+    from models import model_architectures as A
+    nets = O.init_model("pix2pix", "all", seed=seed)
+    G, D = A.Pix2PixGenerator(9), A.Pix2PixDiscriminator(9)
+    G.load_state_dict(nets["generator"])
+    D.load_state_dict(nets["discriminator"])
+    return O, nets, G.cuda(), D.cuda()
+
+
+def _dropout_masks(batch, seed):
+    """keep masks of the three dropout blocks in execution order (levels 6, 5, 4: 4x4, 8x8, 16x16 at 256x256)"""
+    g = torch.Generator().manual_seed(seed)
+    keeps = [torch.rand(batch, 512, s, s, generator=g) < 0.5 for s in (4, 8, 16)]
+    oracle = [k.float() * 2.0 for k in keeps]
+    native = [k.permute(0, 2, 3, 1).contiguous().to(torch.uint8).reshape(-1).cuda() for k in keeps]
+    return oracle, native
+
+
+def test_pix2pix_constructors_match_reference_init():
+    import json
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))["pix2pix_256"]
+    from models import model_architectures as A
+    from models.model import Model
+    torch.manual_seed(47)
+    G = A.Pix2PixGenerator(9).apply(Model.initialise_weights)
+    D = A.Pix2PixDiscriminator(9).apply(Model.initialise_weights)
+    for net, key in ((G, "generator"), (D, "discriminator")):
+        sd = net.state_dict()
+        assert set(k for k, v in sd.items() if v.is_floating_point()) == set(gold["init"][key])
+        for k, want in gold["init"][key].items():
+            assert abs(sd[k].double().sum().item() - want["sum"]) <= 1e-9 * max(1.0, abs(want["sum"])), k
+
+
+def test_pix2pix_forward_and_step_match_oracle():
+    """BASELINE.json configs[0]: Pix2Pix U-Net + BatchNorm PatchGAN, batch 1, 256x256, topography=all -- forward
+    tensors, BatchNorm running statistics and the losses of a full train_paired step (module / autograd path)
+    against the oracle with identical dropout masks."""
+    O, nets, G, D = _pix2pix_pair()
+    x, y = O.synthetic_batch(0, 1, 9, 256)
+    om, nm = _dropout_masks(1, 5)
+    G._executor().dropout_masks = nm
+    ref_nets = {k: {n: v.clone() for n, v in p.items()} for k, p in nets.items()}
+    with torch.no_grad():
+        ref_out = O.pix2pix_generator_forward(ref_nets["generator"], x, masks=om)
+        ref_logits = O.patchgan_bn_forward(ref_nets["discriminator"], torch.cat((x, y), 1))
+        out = G(x.cuda())
+        logits = D(torch.cat((x, y), 1).cuda())
+    e_out, e_log = rel_rms(out, ref_out), rel_rms(logits, ref_logits)
+    print(f"[parity] pix2pix generator rel-rms {e_out:.4f}, BatchNorm PatchGAN logits rel-rms {e_log:.4f}")
+    assert e_out < 6e-2 and e_log < OUT_TOL
+    for net, ref in ((G, ref_nets["generator"]), (D, ref_nets["discriminator"])):
+        sd = net.state_dict()
+        for k in ref:
+            if "running_" in k:
+                assert rel_rms(sd[k], ref[k]) < 2e-2, k
+            if "num_batches" in k:
+                assert int(sd[k]) == int(ref[k]) == 1
+
+    # one full training step through the module path (losses + updated parameters)
+    O, nets, G, D = _pix2pix_pair()
+    G._executor().dropout_masks = nm
+    tr = O.PairedTrainer(nets, "pix2pix")
+    tr.g_forward = lambda p, inp: O.pix2pix_generator_forward(p, inp, masks=om)
+    ref = tr.step(x, y)
+    opt_d = torch.optim.Adam(D.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    opt_g = torch.optim.Adam(G.parameters(), lr=2e-4, betas=(0.5, 0.999))
+    xc, yc = x.cuda(), y.cuda()
+    mse = torch.nn.MSELoss()
+    syn = G(xc)
+    d_syn_in, d_real_in = torch.cat((xc, syn), 1), torch.cat((xc, yc), 1)
+    opt_d.zero_grad()
+    p_s = D(d_syn_in.detach())
+    l_syn = mse(p_s, torch.zeros_like(p_s))
+    p_r = D(d_real_in)
+    l_real = mse(p_r, torch.ones_like(p_r))
+    ((l_syn + l_real) * 0.5).backward()
+    opt_d.step()
+    for p in D.parameters():
+        p.requires_grad = False
+    opt_g.zero_grad()
+    p_g = D(d_syn_in)
+    l_adv = mse(p_g, torch.ones_like(p_g))
+    l_l1 = torch.nn.functional.l1_loss(syn, yc) * 100
+    (l_adv + l_l1).backward()
+    opt_g.step()
+    got = {"losses_discriminator_real": l_real.item(), "losses_discriminator_synthetic": l_syn.item(),
+           "losses_generator_synthetic": l_adv.item(), "l1_losses_generator_synthetic": l_l1.item()}
+    print("[parity] pix2pix step losses", got, "oracle", {k: ref[k] for k in got})
+    for k in got:
+        assert abs(got[k] - ref[k]) <= 3e-2 * abs(ref[k]) + 1e-3, (k, got[k], ref[k])
+    # Adam's first step moves every weight by ~lr regardless of the gradient scale: compare the update DIRECTION
+    agree = []
+    for (n_, p), q in zip(G.named_parameters(), [v for k, v in tr.G.items() if ".running_" not in k
+                                                  and v.is_floating_point() and v.dim() > 0]):
+        init = O.init_model("pix2pix", "all", seed=47)["generator"][n_]
+        d_nat, d_ref = (p.detach().cpu() - init).flatten(), (q.detach() - init).flatten()
+        agree.append(((d_nat * d_ref) > 0).float().mean().item())
+    print(f"[parity] pix2pix Adam update sign agreement: min {min(agree):.3f} mean {sum(agree) / len(agree):.3f}")
+    assert sum(agree) / len(agree) > 0.8
+
+
+def test_model_api_pix2pix_train_paired_and_checkpoint(tmp_path):
+    """`--model=Pix2Pix` through the public API: Model(...).train_paired() on synthetic 256x256 batches, losses stay
+    in the reference's range (golden first-step losses of the unmodified reference; dropout masks differ: the
+    reference draws them from the CPU RNG), BatchNorm buffers land in the checkpoint."""
+    import json
+    from models import model as M
+    from models.data import SyntheticLoader
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))["pix2pix_256"]
+    m = M.Model(model="Pix2Pix", topography="all", num_epochs=200, seed=47, data_path=str(tmp_path),
+                save_model_interval=200)
+    m.train_loader = list(SyntheticLoader(steps=2, batch=1, size=256))
+    m.starting_epoch = m.num_epochs
+    m.train_paired()
+    got = [m.all_losses[k][-1] for k in ("all_losses_discriminator_real", "all_losses_discriminator_synthetic",
+                                         "all_losses_generator_synthetic", "all_l1_losses_generator_synthetic")]
+    want = [sum(s[i] for s in gold["losses"]) / len(gold["losses"]) for i in range(4)]
+    print("[parity] Pix2Pix epoch-mean losses", got, "reference (other dropout masks)", want)
+    for g, w in zip(got, want):
+        assert abs(g - w) <= 0.1 * abs(w), (got, want)
+    files = list((tmp_path / "models").glob("Pix2Pix_*.pth.tar"))
+    assert len(files) == 1
+    ck = torch.load(files[0], weights_only=False)
+    assert len(ck["generator"]) == 82 and int(ck["generator"]["model.model.1.model.2.num_batches_tracked"]) == 2
+    assert int(ck["discriminator"]["model.3.num_batches_tracked"]) == 6  # three discriminator calls per step
