@@ -22,6 +22,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
+_RESULT_OUT = sys.stdout
 TILE = 256
 CHANNELS = 9
 BATCH_PER_GPU = 16
@@ -143,7 +144,7 @@ def run_reference(args):
             "cpu_baseline": {"value": tps, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tps, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 def run_native(args):
@@ -266,12 +267,17 @@ def run_native(args):
             line["cpu_baseline"] = {"value": cpu_tps, "unit": "tiles/s", "cores": cores, "kind": "port",
                                     "sample": "oracle port of train_paired, fp32, 8 timed batch-1 steps (256x256) "
                                               "after 1 warm-up"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that print to file descriptor 1 (NCCL prints its version there)
+    # are diverted to stderr for the whole run and the result is written to the saved descriptor
+    global _RESULT_OUT
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
