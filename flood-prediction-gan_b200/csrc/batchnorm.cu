@@ -222,6 +222,32 @@ __global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t count, u
   }
 }
 
+// 2x2 max pooling, stride 2 (nn.MaxPool2d(2), model_architectures.py:556): one thread per (output pixel, 8 channels)
+__global__ void __launch_bounds__(256)
+maxpool2_kernel(BView x, BView y) {
+  const int G = y.c / 8;
+  const int64_t total = static_cast<int64_t>(y.n) * y.h * y.w * G;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const int g = static_cast<int>(idx % G);
+    int64_t r = idx / G;
+    const int ox = static_cast<int>(r % y.w);
+    r /= y.w;
+    const int oy = static_cast<int>(r % y.h);
+    const int n = static_cast<int>(r / y.h);
+    const int64_t in0 = (static_cast<int64_t>(n) * x.h + 2 * oy) * x.w + 2 * ox;
+    float a[8], b[8], c[8], d[8], o[8];
+    const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x.p) + g * 8;
+    bn_load8(xp + x.at(in0), a);
+    bn_load8(xp + x.at(in0 + 1), b);
+    bn_load8(xp + x.at(in0 + x.w), c);
+    bn_load8(xp + x.at(in0 + x.w + 1), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = fmaxf(fmaxf(a[k], b[k]), fmaxf(c[k], d[k]));
+    bn_store8(static_cast<__nv_bfloat16*>(y.p) + y.at((static_cast<int64_t>(n) * y.h + oy) * y.w + ox) + g * 8, o);
+  }
+}
+
 static bool bn_geometry_ok(const fpg_act* a) {
   return a != nullptr && a->halo == 0 && a->c % 8 == 0 && a->c >= 8 && 256 % (a->c / 8) == 0 && !a->fp32;
 }
@@ -292,6 +318,17 @@ int fpg_batchnorm_running_update(const float* stats, int32_t c, int64_t count, f
   const float unbias = count > 1 ? static_cast<float>(count) / static_cast<float>(count - 1) : 1.f;
   bn_running_kernel<<<(c + 127) / 128, 128, 0, FPG_ST(stream)>>>(stats, eps, momentum, unbias, c, running_mean,
                                                                  running_var);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_maxpool2(const fpg_act* x, const fpg_act* y, void* stream) {
+  FPG_REQUIRE(x && y && x->halo == 0 && y->halo == 0 && !x->fp32 && !y->fp32 && x->c == y->c && x->c % 8 == 0 &&
+                  x->n == y->n && x->h == 2 * y->h && x->w == 2 * y->w, "maxpool geometry");
+  const int64_t total = static_cast<int64_t>(y->n) * y->h * y->w * (y->c / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 4736) blocks = 4736;
+  maxpool2_kernel<<<static_cast<unsigned>(blocks), 256, 0, FPG_ST(stream)>>>(bview_of(x), bview_of(y));
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

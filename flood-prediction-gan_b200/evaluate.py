@@ -38,8 +38,8 @@ if __name__ == "__main__":
     if args.plot_losses or args.plot_sample_images or args.plot_single_image or args.plot_image_set:
         raise NotImplementedError("plotting is outside the accelerated hot path (DESIGN.md section 8)")
     if args.calculate_metrics:
-        raise NotImplementedError("PSNR/SSIM/MS-SSIM/LPIPS need torchmetrics (un-vendored, absent); the flood-mask "
-                                  "threshold and confusion counts are available as fpgan.ops.flood_mask / "
-                                  "confusion_counts")
+        # flood metrics natively (U-Net inference, bit-exact masks, confusion counts); the torchmetrics image-quality
+        # columns are NaN (un-vendored dependency)
+        evaluate_model.calculate_metrics(use_test_data=args.use_test_data, seg_model_path=args.segmentation_model_path)
     print(f"loaded {evaluate_model.prettify_model_name()} (epoch {evaluate_model.current_epoch - 1}); "
           f"generator on {evaluate_model.device}")

@@ -114,6 +114,7 @@ SIGNATURES = {
                                     _vp, _vp, C.c_int, _vp, _vp]),
     "fpg_batchnorm_scratch_floats": (_i64, [_P(Act)]),
     "fpg_batchnorm_running_update": (C.c_int, [_vp, _i32, _i64, _f32, _f32, _vp, _vp, _vp]),
+    "fpg_maxpool2": (C.c_int, [_P(Act), _P(Act), _vp]),
     "fpg_dropout_mask": (C.c_int, [_vp, _i64, C.c_uint64, _f32, _vp]),
     "fpg_act_bwd": (C.c_int, [_P(Act), _P(Act), C.c_int, _P(Act), _vp]),
     "fpg_halo_fold": (C.c_int, [_P(Act), _P(Act), _P(Act), _vp]),

@@ -629,3 +629,70 @@ class PatchGANBatchNormNet(_NetBase, _BatchNormMixin):
         dy1 = ActBuf(t["a1"].n, t["a1"].h, t["a1"].w, t["a1"].c, zero=False)
         ops.act_bwd(d, t["a1"], ACT_LEAKY, dy1)
         return self._conv_bwd("model.0", t["din"], dy1, grads, need_dx)
+
+
+# ------------------------------------------------------------------------------------------------ segmentation U-Net
+class UNetNet(_NetBase, _BatchNormMixin):
+    """UNet(bilinear=False) forward (model_architectures.py:508-586) as used by calculate_metrics (model.py:380-400):
+    3x3 zero-padded convolutions without bias + BatchNorm2d in TRAINING mode (the reference never calls .eval()) + ReLU,
+    2x2 max pooling, 2x2 stride-2 transposed convolutions, channel concatenation, 1x1 head. Inference only."""
+
+    def __init__(self, module):
+        super().__init__(module)
+        self.doubles = {}
+
+        def double(prefix, seq):
+            self._add(prefix + ".0", seq[0], 3, 1, 1)
+            self._add(prefix + ".3", seq[3], 3, 1, 1)
+            self.doubles[prefix] = (seq[1], seq[4])
+
+        double("inc.double_conv", module.inc.double_conv)
+        for i in range(1, 5):
+            double(f"down{i}.maxpool_conv.1.double_conv", getattr(module, f"down{i}").maxpool_conv[1].double_conv)
+        for i in range(1, 5):
+            up = getattr(module, f"up{i}")
+            self._add(f"up{i}.up", up.up, 2, 2, 0, transposed=True, use_bias=True)
+            double(f"up{i}.conv.double_conv", up.conv.double_conv)
+        self._add("outc.conv", module.outc.conv, 1, 1, 0, use_bias=True)
+
+    def repack(self, force=False):
+        # inference only: the dgrad layouts of the plain convolutions are never used, but the batched packer fills both
+        super().repack(force)
+
+    def _double(self, prefix, x, out=None):
+        """conv-BN-ReLU twice; the second result may be written into `out` (a channel slice of a concatenation
+        buffer)"""
+        bn1, bn2 = self.doubles[prefix]
+        y = self._conv(x, prefix + ".0")
+        a = ActBuf(y.n, y.h, y.w, y.c, zero=False)
+        self._bn_forward(y, bn1, ACT_RELU, a)
+        y2 = self._conv(a, prefix + ".3")
+        z = out if out is not None else ActBuf(y2.n, y2.h, y2.w, y2.c, zero=False)
+        self._bn_forward(y2, bn2, ACT_RELU, z)
+        return z
+
+    def forward(self, x):
+        """x: fp32 NCHW [B, 3, H, W] with H, W multiples of 16 -> (logits fp32 NCHW [B, 1, H, W], tape)"""
+        self.repack()
+        B, C, H, W = x.shape
+        if H % 16 or W % 16:
+            raise RuntimeError("UNet: input extent must be a multiple of 16")
+        xin = ActBuf(B, H, W, 16, zero=False)
+        ops.pack_nchw(x, xin, 0, zero_rest=True)
+        widths = (64, 128, 256, 512, 1024)
+        # cats[i]: input of up-level i's DoubleConv = [skip x_{i} | upsampled]; the encoder writes its output straight
+        # into the first half
+        cats = [ActBuf(B, H >> i, W >> i, 2 * widths[i], zero=False) for i in range(4)]
+        cur = self._double("inc.double_conv", xin, out=cats[0].channels(0, 64))
+        for i in range(1, 5):
+            pooled = ActBuf(B, cur.h // 2, cur.w // 2, cur.c, zero=False)
+            ops.maxpool2(cur, pooled)
+            out = cats[i].channels(0, widths[i]) if i < 4 else None
+            cur = self._double(f"down{i}.maxpool_conv.1.double_conv", pooled, out=out)
+        for i in range(1, 5):
+            lvl = 4 - i
+            L = self.layers[f"up{i}.up"]
+            ops.conv_dgrad(cur, L.spec, cats[lvl].channels(widths[lvl], widths[lvl]), bias=L.bias_pad)
+            cur = self._double(f"up{i}.conv.double_conv", cats[lvl])
+        logits = self._conv(cur, "outc.conv", fp32=True)
+        return logits.to_nchw(1), {"logits": logits}

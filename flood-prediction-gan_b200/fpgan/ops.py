@@ -257,6 +257,10 @@ def batchnorm_running_update(stats, count, running_mean, running_var, eps=1e-5, 
          float(eps), float(momentum), _ptr(running_mean), _ptr(running_var), _stream())
 
 
+def maxpool2(x, y):
+    _run("maxpool2", 1, "fpg_maxpool2", x.ref(), y.ref(), _stream())
+
+
 def dropout_mask(mask, seed, keep=0.5):
     _run("dropout_mask", 1, "fpg_dropout_mask", _ptr(mask), mask.numel(), C.c_uint64(int(seed) & (2 ** 64 - 1)),
          float(keep), _stream())

@@ -239,6 +239,71 @@ class Model:
             print(f"Saving {self.prettify_model_name()} model to {path}")
             torch.save(saved, path)
 
+
+    # ------------------------------------------------------------------------------------------ evaluation
+    @staticmethod
+    def binary_metrics_from_counts(tp, fp, tn, fn):
+        """torchmetrics Binary{Accuracy,F1Score,Precision,Recall} and MeanSquaredError of two {0,1} masks restated from
+        the integer confusion counts (reference call sites model.py:372-378, 409-418; torchmetrics divides safely:
+        0 when a denominator is 0). The *_No_Flood metrics are the same formulas on the inverted masks abs(mask - 1)
+        (model.py:415-416), i.e. with tp<->tn and fp<->fn exchanged."""
+        def div(a, b):
+            return float(a) / float(b) if b else 0.0
+        n = tp + fp + tn + fn
+        return {"MSE": div(fp + fn, n), "Accuracy": div(tp + tn, n),
+                "F1_Flood": div(2 * tp, 2 * tp + fp + fn), "Precision_Flood": div(tp, tp + fp),
+                "Recall_Flood": div(tp, tp + fn),
+                "F1_No_Flood": div(2 * tn, 2 * tn + fn + fp), "Precision_No_Flood": div(tn, tn + fn),
+                "Recall_No_Flood": div(tn, tn + fp)}
+
+    def load_segmentation_model(self, seg_model_path=None):
+        """SegmentationModel(train=False).model (segmentation_model.py:55-61): U-Net initialised like the reference
+        and, if a checkpoint is given, loaded from its "model" entry. Never switched to eval mode (the reference
+        does not)."""
+        net = model_architectures.UNet().apply(self.initialise_weights).to(self.device)
+        if seg_model_path:
+            saved = torch.load(seg_model_path, map_location=self.device, weights_only=False)
+            net.load_state_dict(saved["model"])
+        return net
+
+    def calculate_metrics(self, use_test_data=False, seg_model_path=None, loader=None):
+        """Flood-segmentation metrics of calculate_metrics (reference model.py:363-422): generator inference,
+        segmentation of the generated and the ground-truth tile, bit-exact (sigmoid > 0.5) masks, confusion counts
+        accumulated over the whole split on the device. PSNR / SSIM / MS-SSIM / LPIPS need torchmetrics (un-vendored,
+        absent: parity unpinnable) and are reported as NaN. Returns the metrics dict (and writes the reference's CSV
+        when data_path is set)."""
+        seg_model = self.load_segmentation_model(seg_model_path)
+        generator = self.pre_to_post_generator if self.model_is_cycle else self.generator
+        if loader is None:
+            loader = self.test_loader if use_test_data else self.val_loader
+        totals = torch.zeros(4, dtype=torch.int64, device=self.device)
+        times = []
+        n_in = TOPOGRAPHY_CHANNELS[self.topography]
+        for input_stack, ground_truth, _ in loader:
+            x = input_stack[:, :n_in].to(self.device).float().contiguous()
+            truth = ground_truth.to(self.device).float()
+            torch.cuda.synchronize()
+            t0 = time.time()
+            torch.manual_seed(47)
+            with torch.no_grad():
+                generated = generator(x)
+            torch.cuda.synchronize()
+            times.append(time.time() - t0)
+            _, _, counts = model_architectures.flood_masks_and_counts(seg_model, generated, truth)
+            totals += counts
+        tp, fp, tn, fn = (int(v) for v in totals.tolist())
+        results = {"PSNR": float("nan"), "SSIM": float("nan"), "MS-SSIM": float("nan"), "LPIPS": float("nan")}
+        results.update(self.binary_metrics_from_counts(tp, fp, tn, fn))
+        results["Inference"] = float(np.mean(times)) if times else float("nan")
+        if self.verbose:
+            print(results)
+        if self.data_path and os.path.isdir(str(self.data_path)):
+            path = self.create_path("metric")
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            with open(path, "w") as f:
+                f.write(",".join(results.keys()) + "\n" + ",".join(str(v) for v in results.values()) + "\n")
+        return results
+
     # ------------------------------------------------------------------------------------------ training
     def _world(self):
         if dist.is_available() and dist.is_initialized():

@@ -293,3 +293,85 @@ class Pix2PixDiscriminator(_NativeModule):
         dx = torch.empty(dd.n, c, dd.h, dd.w, dtype=torch.float32, device=dout.device)
         ops.unpack_nchw(dd, dx, 0)
         return dx
+
+
+# ------------------------------------------------------------------------------------------------ segmentation U-Net
+class DoubleConv(nn.Module):
+    """parameter container (reference :541-552)"""
+
+    def __init__(self, in_channels, out_channels, mid_channels=None):
+        super().__init__()
+        mid_channels = mid_channels or out_channels
+        self.double_conv = nn.Sequential(
+            nn.Conv2d(in_channels, mid_channels, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(mid_channels),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(mid_channels, out_channels, kernel_size=3, padding=1, bias=False), nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True))
+
+
+class Down(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), DoubleConv(in_channels, out_channels))
+
+
+class Up(nn.Module):
+    def __init__(self, in_channels, out_channels, bilinear=False):
+        super().__init__()
+        if bilinear:
+            raise NotImplementedError("the reference instantiates UNet(bilinear=False) only")
+        self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
+        self.conv = DoubleConv(in_channels, out_channels)
+
+
+class OutConv(nn.Module):
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
+
+
+class UNet(nn.Module):
+    """Segmentation U-Net of calculate_metrics (reference :508-586), inference through the native executor. Like the
+    reference it always runs BatchNorm with batch statistics (no .eval() anywhere in the reference)."""
+
+    def __init__(self, n_channels=3, n_classes=1, bilinear=False):
+        super().__init__()
+        self.n_channels, self.n_classes, self.bilinear = n_channels, n_classes, bilinear
+        self.inc = DoubleConv(n_channels, 64)
+        self.down1, self.down2 = Down(64, 128), Down(128, 256)
+        self.down3, self.down4 = Down(256, 512), Down(512, 1024)
+        self.up1, self.up2 = Up(1024, 512), Up(512, 256)
+        self.up3, self.up4 = Up(256, 128), Up(128, 64)
+        self.outc = OutConv(64, n_classes)
+
+    def _executor(self):
+        p = next(self.parameters())
+        key = (p.device, p.data_ptr())
+        if getattr(self, "_exec_key", None) != key:
+            if not p.is_cuda:
+                raise RuntimeError("UNet: parameters must be on a CUDA device (no CPU fallback)")
+            object.__setattr__(self, "_exec", networks.UNetNet(self))
+            object.__setattr__(self, "_exec_key", key)
+        return self._exec
+
+    @torch.no_grad()
+    def forward(self, x):
+        _require_cuda(x, "UNet")
+        out, _ = self._executor().forward(x.detach().float().contiguous())
+        return out
+
+
+def flood_masks_and_counts(seg_model, generated, ground_truth):
+    """model.py:397-418: rescale both images to [0, 1], segment, threshold with the bit-exact (sigmoid > 0.5) kernel,
+    count TP / FP / TN / FN on the device. Returns (output_mask, true_mask, counts int64[4])."""
+    gt = torch.clamp((ground_truth + 1) * 0.5, min=0, max=1)
+    gen = torch.clamp((generated + 1) * 0.5, min=0, max=1)
+    masks = []
+    for img in (gen, gt):
+        logits = seg_model(img).contiguous()
+        m = torch.empty_like(logits)
+        ops.flood_mask(logits, m)
+        masks.append(m)
+    counts = torch.zeros(4, dtype=torch.int64, device=generated.device)
+    ops.confusion_counts(masks[0].reshape(-1), masks[1].reshape(-1), counts)
+    return masks[0], masks[1], counts

@@ -308,6 +308,8 @@ int64_t fpg_batchnorm_scratch_floats(const fpg_act* y);
 /* running_mean = (1-m) running_mean + m mean; running_var = (1-m) running_var + m var * count/(count-1) */
 int fpg_batchnorm_running_update(const float* stats, int32_t c, int64_t count, float eps, float momentum,
                                  float* running_mean, float* running_var, void* stream);
+/* y = max over 2x2 windows, stride 2 (nn.MaxPool2d(2) of the segmentation U-Net, model_architectures.py:556) */
+int fpg_maxpool2(const fpg_act* x, const fpg_act* y, void* stream);
 /* mask[i] = 1 with probability keep (counter-based hash of seed and i: reproducible), else 0 */
 int fpg_dropout_mask(uint8_t* mask, int64_t count, uint64_t seed, float keep, void* stream);
 

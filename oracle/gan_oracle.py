@@ -511,6 +511,57 @@ class CycleTrainer:
         return out
 
 
+# ---------------------------------------------------------------------------------------------- segmentation U-Net
+def unet_plan(n_channels=3, n_classes=1):
+    """UNet(bilinear=False): model_architectures.py:508-586 (construction order == registration order == apply order)"""
+    p = []
+
+    def double(prefix, cin, cout):
+        p.extend([(prefix + ".0", (cout, cin, 3, 3), False, "conv"), (prefix + ".1", (cout,), False, "bn"),
+                  (prefix + ".3", (cout, cout, 3, 3), False, "conv"), (prefix + ".4", (cout,), False, "bn")])
+
+    double("inc.double_conv", n_channels, 64)
+    for i, (cin, cout) in enumerate(((64, 128), (128, 256), (256, 512), (512, 1024)), 1):
+        double(f"down{i}.maxpool_conv.1.double_conv", cin, cout)
+    for i, (cin, cout) in enumerate(((1024, 512), (512, 256), (256, 128), (128, 64)), 1):
+        p.append((f"up{i}.up", (cin, cin // 2, 2, 2), True, "convT"))
+        double(f"up{i}.conv.double_conv", cin, cout)
+    p.append(("outc.conv", (n_classes, 64, 1, 1), True, "conv"))
+    return p
+
+
+def init_unet(seed=None):
+    """SegmentationModel.__init__ (segmentation_model.py:55): UNet().apply(initialise_weights)"""
+    if seed is not None:
+        torch.manual_seed(seed)
+    return _init_from_plan(unet_plan())
+
+
+def unet_forward(p, x):
+    """UNet.forward in TRAINING mode -- the reference never calls .eval() on the segmentation model
+    (segmentation_model.py:55-61, model.py:380-400), so BatchNorm uses batch statistics and updates its buffers."""
+    def double(prefix, t):
+        t = F.relu(_bn(p, prefix + ".1", F.conv2d(t, p[prefix + ".0.weight"], None, padding=1)))
+        return F.relu(_bn(p, prefix + ".4", F.conv2d(t, p[prefix + ".3.weight"], None, padding=1)))
+
+    xs = [double("inc.double_conv", x)]
+    for i in range(1, 5):
+        xs.append(double(f"down{i}.maxpool_conv.1.double_conv", F.max_pool2d(xs[-1], 2)))
+    t = xs[4]
+    for i in range(1, 5):
+        up = F.conv_transpose2d(t, p[f"up{i}.up.weight"], p[f"up{i}.up.bias"], stride=2)
+        skip = xs[4 - i]
+        t = double(f"up{i}.conv.double_conv", torch.cat((skip, up), 1))  # sizes match for inputs divisible by 16
+    return F.conv2d(t, p["outc.conv.weight"], p["outc.conv.bias"])
+
+
+def segmentation_masks(p, generated, ground_truth):
+    """model.py:397-400: both images rescaled from [-1, 1] to [0, 1], segmented, thresholded"""
+    gt = torch.clamp((ground_truth + 1) * 0.5, min=0, max=1)
+    gen = torch.clamp((generated + 1) * 0.5, min=0, max=1)
+    return flood_mask(unet_forward(p, gen)), flood_mask(unet_forward(p, gt))
+
+
 # ---------------------------------------------------------------------------------------------- integer work
 def flood_mask(logits):
     """(sigmoid(x) > 0.5).float(): model.py:399-400, segmentation_model.py:244-248 (fp32, CPU)"""

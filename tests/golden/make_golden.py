@@ -112,6 +112,46 @@ def run_cycle(ref_model, name, size, batch, steps, identity):
             "final_generator_output": sample(out)}
 
 
+def run_unet(size, batch):
+    """The segmentation U-Net exactly as calculate_metrics uses it (model.py:380-400): constructed and initialised like
+    SegmentationModel.__init__ (segmentation_model.py:55), never switched to eval mode, applied to the generated and the
+    ground-truth image rescaled to [0, 1]; masks by (sigmoid > 0.5)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_arch", os.path.join(REF, "models", "model_architectures.py"))
+    arch = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(arch)
+
+    def init(m):  # segmentation_model.py:73-84
+        name = m.__class__.__name__
+        if hasattr(m, "weight") and (name.find("Conv") != -1 or name.find("Linear") != -1):
+            torch.nn.init.normal_(m.weight.data, 0.0, 0.02)
+            if hasattr(m, "bias") and m.bias is not None:
+                torch.nn.init.constant_(m.bias.data, 0.0)
+        elif name.find("BatchNorm2d") != -1:
+            torch.nn.init.normal_(m.weight.data, 1.0, 0.02)
+            torch.nn.init.constant_(m.bias.data, 0.0)
+
+    torch.manual_seed(47)
+    net = arch.UNet().apply(init)
+    init_digest = param_digest(net)
+    g = torch.Generator().manual_seed(2000)
+    generated = torch.rand(batch, 3, size, size, generator=g) * 2 - 1
+    truth = torch.rand(batch, 3, size, size, generator=g) * 2 - 1
+    with torch.no_grad():
+        gt = torch.clamp((truth + 1) * 0.5, min=0, max=1)
+        gen = torch.clamp((generated + 1) * 0.5, min=0, max=1)
+        logits_gen = net(gen)
+        out_mask = (torch.sigmoid(logits_gen) > 0.5).float()
+        logits_gt = net(gt)
+        true_mask = (torch.sigmoid(logits_gt) > 0.5).float()
+    p, t = out_mask.flatten() > 0.5, true_mask.flatten() > 0.5
+    counts = [int((p & t).sum()), int((p & ~t).sum()), int((~p & ~t).sum()), int((~p & t).sum())]
+    return {"size": size, "batch": batch, "init": init_digest, "logits_generated": sample(logits_gen),
+            "logits_truth": sample(logits_gt), "mask_generated_sum": float(out_mask.sum()),
+            "mask_truth_sum": float(true_mask.sum()), "confusion_tp_fp_tn_fn": counts,
+            "final": param_digest(net)}
+
+
 def flood_mask_facts():
     """Exhaustive scan of (sigmoid(x) > 0.5) over every positive fp32 value: the expression is a step function."""
     first_true = last_false = None
@@ -143,6 +183,7 @@ def main():
     out["pix2pix_256"] = run_paired(ref_model, 256, 1, 2, model="pix2pix")
     out["cyclegan_64"] = run_cycle(ref_model, "cyclegan", 64, 1, 2, False)
     out["attentiongan_64_identity"] = run_cycle(ref_model, "attentiongan", 64, 1, 2, True)
+    out["unet_64"] = run_unet(64, 4)
     out["flood_mask"] = flood_mask_facts()
     with open(os.path.join(HERE, "reference_vectors.json"), "w") as f:
         json.dump(out, f, indent=1)

@@ -81,3 +81,22 @@ def test_bucketed_allreduce_and_sharding_world2():
     results = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), results), nprocs=world, join=True)
     assert dict(results) == {0: "ok", 1: "ok"}, dict(results)
+
+
+def test_binary_metrics_from_counts_match_definitions():
+    """torchmetrics Binary* restated from integer confusion counts (reference model.py:409-418)."""
+    import importlib
+    M = importlib.import_module("models.model")  # conftest.py puts the package directory on sys.path
+    torch.manual_seed(0)
+    pred, truth = (torch.rand(5000) > 0.6).float(), (torch.rand(5000) > 0.5).float()
+    p, t = pred > 0.5, truth > 0.5
+    tp, fp, tn, fn = int((p & t).sum()), int((p & ~t).sum()), int((~p & ~t).sum()), int((~p & t).sum())
+    m = M.Model.binary_metrics_from_counts(tp, fp, tn, fn)
+    assert abs(m["MSE"] - torch.mean((pred - truth) ** 2).item()) < 1e-7
+    assert abs(m["Accuracy"] - (pred == truth).float().mean().item()) < 1e-7
+    prec, rec = tp / (tp + fp), tp / (tp + fn)
+    assert abs(m["F1_Flood"] - 2 * prec * rec / (prec + rec)) < 1e-12
+    inv_p, inv_t = torch.abs(pred - 1) > 0.5, torch.abs(truth - 1) > 0.5
+    assert abs(m["Precision_No_Flood"] - int((inv_p & inv_t).sum()) / int(inv_p.sum())) < 1e-12
+    assert abs(m["Recall_No_Flood"] - int((inv_p & inv_t).sum()) / int(inv_t.sum())) < 1e-12
+    assert M.Model.binary_metrics_from_counts(0, 0, 10, 0)["Precision_Flood"] == 0.0  # safe division

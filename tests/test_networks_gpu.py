@@ -415,3 +415,58 @@ def test_model_api_pix2pix_train_paired_and_checkpoint(tmp_path):
     ck = torch.load(files[0], weights_only=False)
     assert len(ck["generator"]) == 82 and int(ck["generator"]["model.model.1.model.2.num_batches_tracked"]) == 2
     assert int(ck["discriminator"]["model.3.num_batches_tracked"]) == 6  # three discriminator calls per step
+
+
+# ------------------------------------------------------------------------------------------------ segmentation U-Net
+def test_unet_inference_masks_and_counts():
+    """BASELINE.json configs[4] at test size: the segmentation U-Net of calculate_metrics (model.py:380-418) on a
+    generated / ground-truth pair. Logits against the oracle within the bf16 bound; the integer work -- the
+    (sigmoid > 0.5) threshold and the TP/FP/TN/FN counts -- bit-exact against the reference expressions evaluated on
+    the same logits."""
+    from oracle import gan_oracle as O
+    from models import model_architectures as A
+    p = O.init_unet(47)
+    # make the head decisive: with N(0, 0.02) weights the logits sit within bf16 noise of the threshold
+    p["outc.conv.weight"] = p["outc.conv.weight"] * 40
+    net = A.UNet()
+    net.load_state_dict(p)
+    net = net.cuda()
+    g = torch.Generator().manual_seed(2000)
+    gen = torch.rand(4, 3, 64, 64, generator=g) * 2 - 1
+    truth = torch.rand(4, 3, 64, 64, generator=g) * 2 - 1
+    ref = {k: v.clone() for k, v in p.items()}
+    with torch.no_grad():
+        ref_logits = O.unet_forward(ref, torch.clamp((gen + 1) * 0.5, min=0, max=1))
+    logits = net(torch.clamp((gen.cuda() + 1) * 0.5, min=0, max=1))
+    err = rel_rms(logits - logits.mean(), ref_logits - ref_logits.mean())
+    print(f"[parity] U-Net logits rel-rms {err:.4f} (spread {ref_logits.std().item():.3f})")
+    assert err < 5e-2
+    sd = net.state_dict()
+    assert int(sd["inc.double_conv.1.num_batches_tracked"]) == 1
+    assert rel_rms(sd["down4.maxpool_conv.1.double_conv.4.running_var"],
+                   ref["down4.maxpool_conv.1.double_conv.4.running_var"]) < 3e-2
+    # away from the threshold the masks agree with the oracle's
+    mo, mt, counts = A.flood_masks_and_counts(net, gen.cuda(), truth.cuda())
+    safe = ref_logits.abs() > 6 * (logits.cpu() - ref_logits).abs().max()
+    assert safe.float().mean() > 0.3
+    assert torch.equal(mo.cpu()[safe], O.flood_mask(ref_logits)[safe])
+    # bit-exact integer work on the native logits (second forward pass: BatchNorm buffers moved, logits unchanged
+    # because batch statistics are used)
+    lg = net(torch.clamp((gen.cuda() + 1) * 0.5, min=0, max=1))
+    lt = net(torch.clamp((truth.cuda() + 1) * 0.5, min=0, max=1))
+    assert torch.equal(mo, (torch.sigmoid(lg) > 0.5).float()) and torch.equal(mt, (torch.sigmoid(lt) > 0.5).float())
+    assert counts.tolist() == O.confusion_counts(mo.flatten().cpu(), mt.flatten().cpu())
+
+
+def test_model_calculate_metrics_flood_columns():
+    """evaluate.py --calculate_metrics path (model.py:363-422): generator inference, segmentation of generated and
+    ground-truth tiles, bit-exact masks, confusion counts over the split, torchmetrics-equivalent flood metrics."""
+    from models import model as M
+    from models.data import SyntheticLoader
+    m = M.Model(model="PairedAttention", topography="all", num_epochs=1, seed=47, training_model=False)
+    res = m.calculate_metrics(loader=list(SyntheticLoader(steps=2, batch=2, size=64)))
+    for k in ("MSE", "Accuracy", "F1_Flood", "Precision_Flood", "Recall_Flood", "F1_No_Flood", "Precision_No_Flood",
+              "Recall_No_Flood", "Inference"):
+        assert 0.0 <= res[k] <= 1.0 or k == "Inference", (k, res[k])
+    assert abs(res["MSE"] + res["Accuracy"] - 1.0) < 1e-12  # both are functions of the same integer counts
+    assert res["PSNR"] != res["PSNR"]  # NaN: torchmetrics image-quality metrics are out of scope

@@ -134,3 +134,26 @@ def test_pix2pix_oracle_matches_reference_golden():
     # parameters AND BatchNorm running statistics after the two steps
     assert_digest(digest(nets["generator"]), gold["final"]["generator"], 2e-3, "G final")
     assert_digest(digest(nets["discriminator"]), gold["final"]["discriminator"], 2e-3, "D final")
+
+
+def test_unet_oracle_matches_reference_golden():
+    """Segmentation U-Net as used by calculate_metrics (model.py:380-418, BASELINE.json configs[4]): same initial
+    weights, logits, BatchNorm buffer side effects, and -- integer work -- identical flood masks and confusion counts."""
+    gold = GOLD["unet_64"]
+    torch.set_num_threads(8)
+    p = O.init_unet(47)
+    assert_digest(digest(p), gold["init"], 1e-12, "U-Net init")
+    g = torch.Generator().manual_seed(2000)
+    gen = torch.rand(gold["batch"], 3, gold["size"], gold["size"], generator=g) * 2 - 1
+    truth = torch.rand(gold["batch"], 3, gold["size"], gold["size"], generator=g) * 2 - 1
+    with torch.no_grad():
+        lg = O.unet_forward(p, torch.clamp((gen + 1) * 0.5, min=0, max=1))
+        lt = O.unet_forward(p, torch.clamp((truth + 1) * 0.5, min=0, max=1))
+    torch.testing.assert_close(sample(lg), torch.tensor(gold["logits_generated"]["samples"], dtype=torch.float64),
+                               rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(sample(lt), torch.tensor(gold["logits_truth"]["samples"], dtype=torch.float64),
+                               rtol=1e-4, atol=1e-6)
+    mo, mt = O.flood_mask(lg), O.flood_mask(lt)
+    assert float(mo.sum()) == gold["mask_generated_sum"] and float(mt.sum()) == gold["mask_truth_sum"]
+    assert O.confusion_counts(mo.flatten(), mt.flatten()) == gold["confusion_tp_fp_tn_fn"]
+    assert_digest(digest(p), gold["final"], 1e-5, "U-Net buffers after two forward passes")
