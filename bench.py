@@ -269,6 +269,9 @@ def run_native(args):
                                               "after 1 warm-up"}
         print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
+        tr.release_graphs()  # captured NCCL work must be gone before the communicator is torn down
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

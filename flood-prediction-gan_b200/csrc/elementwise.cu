@@ -1212,6 +1212,36 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Device-side step counter and bias corrections (CUDA-graph friendly: nothing step-dependent in the launch arguments).
+// state = {int32 step, float lr, float step_size, float bc2_sqrt}; one thread advances it before the update kernel.
+__global__ void adam_prepare_kernel(int32_t* __restrict__ state, float beta1, float beta2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int step = ++state[0];
+  float* f = reinterpret_cast<float*>(state);
+  const double bc1 = 1.0 - pow(static_cast<double>(beta1), static_cast<double>(step));
+  const double bc2 = 1.0 - pow(static_cast<double>(beta2), static_cast<double>(step));
+  f[2] = static_cast<float>(static_cast<double>(f[1]) / bc1);
+  f[3] = static_cast<float>(sqrt(bc2));
+}
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t count, float beta1, float beta2, float eps,
+                                const int32_t* __restrict__ state, float grad_scale) {
+  const float step_size = reinterpret_cast<const float*>(state)[2];
+  const float bc2_sqrt = reinterpret_cast<const float*>(state)[3];
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const float w1 = 1.f - beta1;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const float gr = g[i] * grad_scale;
+    float mi = m[i], vi = v[i];
+    mi = (w1 < 0.5f) ? mi + w1 * (gr - mi) : gr - (gr - mi) * (1.f - w1);
+    vi = vi * beta2 + (1.f - beta2) * gr * gr;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ flood mask
 __global__ void flood_mask_kernel(const float* __restrict__ logits, float* __restrict__ mask, int64_t count) {
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -1527,6 +1557,18 @@ int fpg_adam_step(float* p, const float* g, float* m, float* v, int64_t count, f
   if (blocks > 2368) blocks = 2368;
   adam_kernel<<<static_cast<unsigned>(blocks), 256, 0, FPG_ST(stream)>>>(p, g, m, v, count, beta1, beta2, eps,
                                                                          step_size, bc2_sqrt, grad_scale);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t count, float beta1, float beta2, float eps,
+                      int32_t* state, float grad_scale, void* stream) {
+  FPG_REQUIRE(p && g && m && v && state && count > 0, "bad argument");
+  adam_prepare_kernel<<<1, 32, 0, FPG_ST(stream)>>>(state, beta1, beta2);
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 2368) blocks = 2368;
+  adam_dev_kernel<<<static_cast<unsigned>(blocks), 256, 0, FPG_ST(stream)>>>(p, g, m, v, count, beta1, beta2, eps, state,
+                                                                             grad_scale);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

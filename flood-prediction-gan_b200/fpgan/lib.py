@@ -126,6 +126,7 @@ SIGNATURES = {
     "fpg_unpack_nchw": (C.c_int, [_P(Act), _i32, _vp, _i32, C.c_int, _vp]),
     "fpg_tanh_bwd_pack": (C.c_int, [_vp, _P(Act), _i32, _P(Act), _vp]),
     "fpg_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
+    "fpg_adam_step_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp, _f32, _vp]),
     "fpg_flood_mask": (C.c_int, [_vp, _vp, _i64, _vp]),
     "fpg_confusion_counts": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
 }

@@ -315,6 +315,12 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, step, grad_scale=1.0):
            float(eps), int(step), float(grad_scale), _stream())
 
 
+def adam_step_dev(p, g, m, v, state, beta1, beta2, eps, grad_scale=1.0):
+    """state: int32[4] device tensor {step, lr bits, -, -}"""
+    _run("adam_step", 2, "fpg_adam_step_dev", _ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), float(beta1), float(beta2),
+         float(eps), _ptr(state), float(grad_scale), _stream())
+
+
 def flood_mask(logits, mask):
     _run("flood_mask", 1, "fpg_flood_mask", _ptr(logits), _ptr(mask), logits.numel(), _stream())
 

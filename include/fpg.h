@@ -362,6 +362,12 @@ int fpg_unpack_nchw(const fpg_act* src, int32_t c0, float* dst, int32_t c_dst, i
 int fpg_adam_step(float* p, const float* g, float* m, float* v, int64_t count, float lr, float beta1, float beta2,
                   float eps, int32_t step, float grad_scale, void* stream);
 
+/* Same update with the step count, learning rate and bias corrections in DEVICE memory, so that the launch
+ * arguments never change and the whole training step can be replayed as a CUDA graph.
+ *   state: int32[4] = {step (incremented by this call), lr as float bits, scratch, scratch}. */
+int fpg_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t count, float beta1, float beta2, float eps,
+                      int32_t* state, float grad_scale, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Flood-mask thresholding -- (sigmoid(logit) > 0.5).float(), model.py:399-400, segmentation_model.py:244-248.
  * Bit-exact with the fp32 reference expression (sigmoid evaluated in fp32 as 1/(1+exp(-x)), then compared).
