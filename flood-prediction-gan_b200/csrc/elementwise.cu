@@ -789,6 +789,376 @@ in_bwd_fused_kernel(View dz, View dz2, int has_dz2, View y, const float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------------------------ streamed IN passes
+// Bulk-copy-ring versions of the InstanceNorm apply / backward passes (see the ring note above in_stats_ring_kernel):
+// ncu showed the register-load versions latency bound (long_scoreboard 10-15 stalls per issue, 2-3 TB/s). A CTA streams
+// a range of CHUNKS of one image; a chunk is a run of <= SP = 16 KB / pixel-bytes pixels inside one image row, so it is
+// contiguous in every operand whether or not that operand carries a halo. NT operands are fetched per chunk.
+struct RingTensor {
+  const uint8_t* base;  // channel 0 of interior pixel (0, 0) of image 0
+  int64_t img_bytes;    // between images
+  int32_t row_bytes;    // between rows (padded width x pixel bytes)
+};
+
+static RingTensor ring_tensor(const fpg_act* a) {
+  RingTensor t;
+  const int64_t wp = a->w + 2 * a->halo, hp = a->h + 2 * a->halo, pb = static_cast<int64_t>(a->c_stride) * 2;
+  t.base = static_cast<const uint8_t*>(a->data) + (static_cast<int64_t>(a->halo) * wp + a->halo) * pb;
+  t.img_bytes = hp * wp * pb;
+  t.row_bytes = static_cast<int32_t>(wp * pb);
+  return t;
+}
+
+struct RingGeom {
+  int32_t h, w, c, pix_bytes, sp, segs;  // sp pixels per chunk, segs chunks per row
+  int32_t stages, ctas_per_img;
+};
+
+// Runs the ring for chunks [c_begin, c_end) of image i. body(ptrs, row, x0, npx) is called by the 256 consumer threads
+// with ptrs[t] = shared-memory address of operand t's chunk; every consumer warp must call it (it may not return early).
+template <int NT, typename Body>
+__device__ __forceinline__ void ring_run(const RingTensor (&ts)[NT], const bool (&on)[NT], const RingGeom& gm, int i,
+                                         int c_begin, int c_end, uint8_t* ring, uint64_t* full, uint64_t* empty,
+                                         Body body) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int stage_bytes = NT * kRingStageBytes;
+  if (warp == 8) {
+    if (lane == 0) {
+      int n_on = 0;
+#pragma unroll
+      for (int t = 0; t < NT; ++t) n_on += on[t] ? 1 : 0;
+      int st = 0, ph = 0;
+      int row = c_begin / gm.segs, seg = c_begin - row * gm.segs;
+      for (int k = c_begin; k < c_end; ++k) {
+        const int x0 = seg * gm.sp;
+        const int npx = min(gm.sp, gm.w - x0);
+        const uint32_t bytes = static_cast<uint32_t>(npx) * gm.pix_bytes;
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&full[st], bytes * n_on);
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          if (on[t])
+            bulk_load(ring + st * stage_bytes + t * kRingStageBytes,
+                      ts[t].base + i * ts[t].img_bytes + static_cast<int64_t>(row) * ts[t].row_bytes +
+                          static_cast<int64_t>(x0) * gm.pix_bytes,
+                      bytes, &full[st]);
+        if (++st == gm.stages) {
+          st = 0;
+          ph ^= 1;
+        }
+        if (++seg == gm.segs) {
+          seg = 0;
+          ++row;
+        }
+      }
+    }
+  } else {
+    int st = 0, ph = 0;
+    int row = c_begin / gm.segs, seg = c_begin - row * gm.segs;
+    for (int k = c_begin; k < c_end; ++k) {
+      const int x0 = seg * gm.sp;
+      const int npx = min(gm.sp, gm.w - x0);
+      mbar_wait(&full[st], ph);
+      const uint8_t* ptrs[NT];
+#pragma unroll
+      for (int t = 0; t < NT; ++t) ptrs[t] = ring + st * stage_bytes + t * kRingStageBytes;
+      body(ptrs, row, x0, npx);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+      if (++st == gm.stages) {
+        st = 0;
+        ph ^= 1;
+      }
+      if (++seg == gm.segs) {
+        seg = 0;
+        ++row;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void ring_setup(uint8_t* raw, int stages, int nt, uint8_t*& ring, uint64_t*& full,
+                                           uint64_t*& empty) {
+  ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 127) & ~uintptr_t(127));
+  full = reinterpret_cast<uint64_t*>(ring + stages * nt * kRingStageBytes);
+  empty = full + stages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 8);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+}
+
+// contributions of the mirrored halo positions of dz to interior pixel (y, x) (the direct position is streamed)
+__device__ __forceinline__ void fold_extra(const View& dz, int i, int y, int x, int g, float (&acc)[8]) {
+  const int h = dz.halo;
+  if (h == 0 || (y > h && y < dz.h - 1 - h && x > h && x < dz.w - 1 - h)) return;
+  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(dz.p);
+  int rows[3], cols[3], nr = 0, nc = 0;
+  rows[nr++] = y + h;
+  if (y >= 1 && y <= h) rows[nr++] = h - y;
+  if (y >= dz.h - 1 - h && y <= dz.h - 2) rows[nr++] = 2 * (dz.h - 1) - y + h;
+  cols[nc++] = x + h;
+  if (x >= 1 && x <= h) cols[nc++] = h - x;
+  if (x >= dz.w - 1 - h && x <= dz.w - 2) cols[nc++] = 2 * (dz.w - 1) - x + h;
+  for (int a = 0; a < nr; ++a)
+    for (int b = 0; b < nc; ++b) {
+      if (a == 0 && b == 0) continue;
+      float f[8];
+      load8(base + dz.at_padded32(i, rows[a], cols[b]) + g * 8, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += f[k];
+    }
+}
+
+// dz.interior += the halo positions that mirror onto it (backward of F.pad(reflect)), IN PLACE, band pixels only. Run
+// once before the two streamed passes so that neither has to chase mirrored positions through global memory in the
+// middle of its shared-memory pipeline (that stalled the consumer warps ~1 us per chunk: every 64-pixel row has band
+// pixels).
+__global__ void halo_fold_inplace_kernel(View dz) {
+  const int G = dz.c / 8;
+  const int64_t total = static_cast<int64_t>(dz.n) * dz.h * dz.w * G;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int g = static_cast<int>(idx % G);
+  int64_t r = idx / G;
+  const int x = static_cast<int>(r % dz.w);
+  r /= dz.w;
+  const int y = static_cast<int>(r % dz.h);
+  const int i = static_cast<int>(r / dz.h);
+  const int h = dz.halo;
+  if (y > h && y < dz.h - 1 - h && x > h && x < dz.w - 1 - h) return;
+  float acc[8];
+  __nv_bfloat16* p = static_cast<__nv_bfloat16*>(dz.p) + dz.at32(i, y, x) + g * 8;
+  load8(p, acc);
+  fold_extra(dz, i, y, x, g, acc);
+  store8(p, acc);
+}
+
+// pass 1 of the backward: operands {dz (fold), y, dz2}; optional dres = g; partial sums -> last CTA finalises
+__global__ void __launch_bounds__(kRingThreads, 1)
+in_bwd_reduce_ring_kernel(View dz, View dz2, int has_dz2, View y, const float* __restrict__ stats, int act, View dres,
+                          int has_dres, float* __restrict__ partial, float* __restrict__ red_out,
+                          int* __restrict__ counters, float inv_hw, const RingTensor t_dz, const RingTensor t_y,
+                          const RingTensor t_dz2, const RingGeom gm, int folded) {
+  extern __shared__ uint8_t ring_raw[];
+  uint8_t* ring;
+  uint64_t *full, *empty;
+  ring_setup(ring_raw, gm.stages, 3, ring, full, empty);
+  const int G = y.c / 8;
+  const int lanes = kStatThreads / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  const int i = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+  const int chunks = gm.h * gm.segs;
+  const int c_begin = static_cast<int>(static_cast<int64_t>(chunks) * split / splits);
+  const int c_end = static_cast<int>(static_cast<int64_t>(chunks) * (split + 1) / splits);
+  float s[8], ss[8], mean[8], rstd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s[k] = ss[k] = mean[k] = rstd[k] = 0.f;
+  if (threadIdx.x < kStatThreads) {
+    const float4* st = reinterpret_cast<const float4*>(stats + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 ms = __ldg(st + k);
+      mean[2 * k] = ms.x; rstd[2 * k] = ms.y; mean[2 * k + 1] = ms.z; rstd[2 * k + 1] = ms.w;
+    }
+  }
+  const RingTensor ts[3] = {t_dz, t_y, t_dz2};
+  const bool on[3] = {true, true, has_dz2 != 0};
+  ring_run<3>(ts, on, gm, i, c_begin, c_end, ring, full, empty,
+              [&](const uint8_t* const (&ptrs)[3], int row, int x0, int npx) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int px = pl + u * lanes;
+                  if (px < npx) {
+                    const int off = px * gm.pix_bytes + g * 16;
+                    float gr[8], yy[8];
+                    cvt8(*reinterpret_cast<const uint4*>(ptrs[0] + off), gr);
+                    cvt8(*reinterpret_cast<const uint4*>(ptrs[1] + off), yy);
+                    if (!folded) fold_extra(dz, i, row, x0 + px, g, gr);
+                    if (has_dz2) {
+                      float e[8];
+                      cvt8(*reinterpret_cast<const uint4*>(ptrs[2] + off), e);
+#pragma unroll
+                      for (int k = 0; k < 8; ++k) gr[k] += e[k];
+                    }
+                    if (has_dres)
+                      store8(static_cast<__nv_bfloat16*>(dres.p) + dres.at32(i, row, x0 + px) + g * 8, gr);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                      const float zh = (yy[k] - mean[k]) * rstd[k];
+                      const float gp = gr[k] * act_grad(zh, act);
+                      s[k] += gp;
+                      ss[k] += gp * zh;
+                    }
+                  }
+                }
+              });
+  __shared__ float red[kStatThreads][17];
+  if (threadIdx.x < kStatThreads) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[threadIdx.x][k] = s[k];
+      red[threadIdx.x][8 + k] = ss[k];
+    }
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < G * 16; o += kRingThreads) {
+    const int gg = o / 16, comp = o % 16;
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[l * G + gg][comp];
+    partial[((static_cast<int64_t>(i) * splits + split) * y.c + gg * 8 + (comp & 7)) * 2 + (comp >> 3)] = acc;
+  }
+  if (!last_cta_of_image(&counters[i], splits)) return;
+  for (int ch = threadIdx.x; ch < y.c; ch += kRingThreads) {
+    float a = 0.f, b = 0.f;
+    const float2* q = reinterpret_cast<const float2*>(partial + (static_cast<int64_t>(i) * splits * y.c + ch) * 2);
+#pragma unroll 16
+    for (int sp = 0; sp < splits; ++sp) {
+      const float2 v = __ldcg(q + static_cast<int64_t>(sp) * y.c);
+      a += v.x;
+      b += v.y;
+    }
+    red_out[(static_cast<int64_t>(i) * y.c + ch) * 2] = a * inv_hw;
+    red_out[(static_cast<int64_t>(i) * y.c + ch) * 2 + 1] = b * inv_hw;
+  }
+  if (threadIdx.x == 0) counters[i] = 0;
+}
+
+// pass 2 of the backward: operands {g source (dres, or dz with fold), y, dz2}
+__global__ void __launch_bounds__(kRingThreads, 1)
+in_bwd_apply_ring_kernel(View dz, View dz2, int has_dz2, int has_gsrc, View y, const float* __restrict__ stats,
+                         const float* __restrict__ red, int act, View dy, const RingTensor t_g, const RingTensor t_y,
+                         const RingTensor t_dz2, const RingGeom gm, int folded) {
+  extern __shared__ uint8_t ring_raw[];
+  uint8_t* ring;
+  uint64_t *full, *empty;
+  ring_setup(ring_raw, gm.stages, 3, ring, full, empty);
+  const int G = y.c / 8;
+  const int lanes = kStatThreads / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  const int i = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+  const int chunks = gm.h * gm.segs;
+  const int c_begin = static_cast<int>(static_cast<int64_t>(chunks) * split / splits);
+  const int c_end = static_cast<int>(static_cast<int64_t>(chunks) * (split + 1) / splits);
+  float mean[8], rstd[8], m1[8], m2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mean[k] = rstd[k] = m1[k] = m2[k] = 0.f;
+  if (threadIdx.x < kStatThreads) {
+    const float4* st = reinterpret_cast<const float4*>(stats + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
+    const float4* rd = reinterpret_cast<const float4*>(red + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 ms = __ldg(st + k);
+      const float4 mr = __ldg(rd + k);
+      mean[2 * k] = ms.x; rstd[2 * k] = ms.y; mean[2 * k + 1] = ms.z; rstd[2 * k + 1] = ms.w;
+      m1[2 * k] = mr.x; m2[2 * k] = mr.y; m1[2 * k + 1] = mr.z; m2[2 * k + 1] = mr.w;
+    }
+  }
+  const bool use_dz2 = has_dz2 != 0 && has_gsrc == 0;
+  const RingTensor ts[3] = {t_g, t_y, t_dz2};
+  const bool on[3] = {true, true, use_dz2};
+  ring_run<3>(ts, on, gm, i, c_begin, c_end, ring, full, empty,
+              [&](const uint8_t* const (&ptrs)[3], int row, int x0, int npx) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int px = pl + u * lanes;
+                  if (px < npx) {
+                    const int off = px * gm.pix_bytes + g * 16;
+                    float gr[8], yy[8], o[8];
+                    cvt8(*reinterpret_cast<const uint4*>(ptrs[0] + off), gr);
+                    cvt8(*reinterpret_cast<const uint4*>(ptrs[1] + off), yy);
+                    if (!has_gsrc) {
+                      if (!folded) fold_extra(dz, i, row, x0 + px, g, gr);
+                      if (use_dz2) {
+                        float e[8];
+                        cvt8(*reinterpret_cast<const uint4*>(ptrs[2] + off), e);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) gr[k] += e[k];
+                      }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                      const float zh = (yy[k] - mean[k]) * rstd[k];
+                      const float gp = gr[k] * act_grad(zh, act);
+                      o[k] = rstd[k] * (gp - m1[k] - zh * m2[k]);
+                    }
+                    store8(static_cast<__nv_bfloat16*>(dy.p) + dy.at32(i, row, x0 + px) + g * 8, o);
+                  }
+                }
+              });
+}
+
+// forward apply: operands {y, residual}; z = act((y - mean) * rstd) (+ residual), scattered to every padded position
+// of z that mirrors the pixel (reflect halo)
+__global__ void __launch_bounds__(kRingThreads, 2)
+in_apply_ring_kernel(View y, const float* __restrict__ stats, int act, int has_res, View z, const RingTensor t_y,
+                     const RingTensor t_res, const RingGeom gm) {
+  extern __shared__ uint8_t ring_raw[];
+  uint8_t* ring;
+  uint64_t *full, *empty;
+  ring_setup(ring_raw, gm.stages, 2, ring, full, empty);
+  const int G = y.c / 8;
+  const int lanes = kStatThreads / G;
+  const int g = threadIdx.x % G, pl = threadIdx.x / G;
+  const int i = blockIdx.y, split = blockIdx.x, splits = gridDim.x;
+  const int chunks = gm.h * gm.segs;
+  const int c_begin = static_cast<int>(static_cast<int64_t>(chunks) * split / splits);
+  const int c_end = static_cast<int>(static_cast<int64_t>(chunks) * (split + 1) / splits);
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) mean[k] = rstd[k] = 0.f;
+  if (threadIdx.x < kStatThreads) {
+    const float4* st = reinterpret_cast<const float4*>(stats + (static_cast<int64_t>(i) * y.c + g * 8) * 2);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float4 ms = __ldg(st + k);
+      mean[2 * k] = ms.x; rstd[2 * k] = ms.y; mean[2 * k + 1] = ms.z; rstd[2 * k + 1] = ms.w;
+    }
+  }
+  const RingTensor ts[2] = {t_y, t_res};
+  const bool on[2] = {true, has_res != 0};
+  const int hl = z.halo;
+  __nv_bfloat16* zb = static_cast<__nv_bfloat16*>(z.p) + g * 8;
+  ring_run<2>(ts, on, gm, i, c_begin, c_end, ring, full, empty,
+              [&](const uint8_t* const (&ptrs)[2], int row, int x0, int npx) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int px = pl + u * lanes;
+                  if (px < npx) {
+                    const int off = px * gm.pix_bytes + g * 16;
+                    const int x = x0 + px;
+                    float f[8], o[8];
+                    cvt8(*reinterpret_cast<const uint4*>(ptrs[0] + off), f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) o[k] = act_fwd((f[k] - mean[k]) * rstd[k], act);
+                    if (has_res) {
+                      float rr[8];
+                      cvt8(*reinterpret_cast<const uint4*>(ptrs[1] + off), rr);
+#pragma unroll
+                      for (int k = 0; k < 8; ++k) o[k] += rr[k];
+                    }
+                    store8(zb + z.at32(i, row, x), o);
+                    if (hl > 0 && !(row > hl && row < z.h - 1 - hl && x > hl && x < z.w - 1 - hl)) {
+                      int rows[3], cols[3], nr = 0, nc = 0;  // padded positions mirroring onto (row, x)
+                      rows[nr++] = row + hl;
+                      if (row >= 1 && row <= hl) rows[nr++] = hl - row;
+                      if (row >= z.h - 1 - hl && row <= z.h - 2) rows[nr++] = 2 * (z.h - 1) - row + hl;
+                      cols[nc++] = x + hl;
+                      if (x >= 1 && x <= hl) cols[nc++] = hl - x;
+                      if (x >= z.w - 1 - hl && x <= z.w - 2) cols[nc++] = 2 * (z.w - 1) - x + hl;
+                      for (int a = 0; a < nr; ++a)
+                        for (int b = 0; b < nc; ++b)
+                          if (a | b) store8(zb + z.at_padded32(i, rows[a], cols[b]), o);
+                    }
+                  }
+                }
+              });
+}
+
 // dx = fold(dz) * act'(z), z = saved activation output (sign(z) == sign(pre-activation))
 __global__ void act_bwd_kernel(View dz, View z, int act, View dx) {
   const int G = z.c / 8;
@@ -1315,6 +1685,34 @@ static int stat_splits(const fpg_act* y, int slots) {
   return splits;
 }
 
+
+// ring-path eligibility of an operand set: dense channels, 16 KB chunks hold whole pixels, 32-bit offsets
+static bool ring_ok(const fpg_act* a) {
+  return a->c == a->c_stride && a->c % 8 == 0 && kStatThreads % (a->c / 8) == 0 &&
+         kRingStageBytes % (a->c_stride * 2) == 0 && !a->fp32 &&
+         static_cast<int64_t>(a->n) * (a->h + 2 * a->halo) * (a->w + 2 * a->halo) * a->c_stride < (1ll << 31);
+}
+
+static RingGeom ring_geom(const fpg_act* y, int stages, int slots) {
+  RingGeom g;
+  g.h = y->h;
+  g.w = y->w;
+  g.c = y->c;
+  g.pix_bytes = y->c_stride * 2;
+  g.sp = kRingStageBytes / g.pix_bytes;
+  g.segs = (y->w + g.sp - 1) / g.sp;
+  g.stages = stages;
+  int per = slots / y->n;
+  if (per < 1) per = 1;
+  const int chunks = g.h * g.segs;
+  if (per > chunks) per = chunks;
+  if (per > 64) per = 64;  // scratch layout of the two-stage reductions
+  g.ctas_per_img = per;
+  return g;
+}
+
+static size_t ring_smem(int stages, int nt) { return static_cast<size_t>(stages) * nt * kRingStageBytes + 2 * stages * 8 + 128; }
+
 }  // namespace fpg
 
 using namespace fpg;
@@ -1361,6 +1759,24 @@ int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_
   FPG_REQUIRE(z->halo < z->h && z->halo < z->w, "halo too large");
   View rv = residual ? view_of(residual) : view_of(y);
   FPG_REQUIRE(256 % (y->c / 8) == 0, "instnorm channels %d", y->c);
+  static const bool no_ring = getenv("FPG_NO_RING") != nullptr;
+  const int sms = sm_count_cached();
+  if (!no_ring && sms > 0 && ring_ok(y) && ring_ok(z) && (!residual || (ring_ok(residual) && residual->c == y->c))) {
+    const int stages = 3;
+    const size_t smem = ring_smem(stages, 2);
+    static bool attr_set = false;
+    if (!attr_set) {
+      FPG_CUDA_CHECK(cudaFuncSetAttribute(in_apply_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+      attr_set = true;
+    }
+    const RingGeom gm = ring_geom(y, stages, 2 * sms);
+    in_apply_ring_kernel<<<dim3(gm.ctas_per_img, y->n), kRingThreads, smem, FPG_ST(stream)>>>(
+        view_of(y), stats, act, residual != nullptr, view_of(z), ring_tensor(y),
+        residual ? ring_tensor(residual) : ring_tensor(y), gm);
+    FPG_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   const int64_t npix = static_cast<int64_t>(z->h + 2 * z->halo) * (z->w + 2 * z->halo);
   const int lanes = 256 / (y->c / 8);
   const int ppl = pixels_per_lane(npix, lanes, y->n, resident_ctas(in_apply_kernel, 256));
@@ -1413,6 +1829,34 @@ int fpg_instnorm_bwd(const fpg_act* dz, const fpg_act* dz2, const fpg_act* y, co
                       &a_inv, &a_ipr, &a_cpi};
     FPG_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(in_bwd_fused_kernel), dim3(ipr * cpi),
                                                dim3(kStatThreads), params, 0, FPG_ST(stream)));
+    return 0;
+  }
+  static const bool no_ring = getenv("FPG_NO_RING") != nullptr;
+  if (!no_ring && ring_ok(y) && ring_ok(dz) && ring_ok(dy) && dz->c == y->c && (!dz2 || (ring_ok(dz2) && dz2->c == y->c)) &&
+      (!dres || (ring_ok(dres) && dres->c == y->c))) {
+    const int stages = 4;
+    const size_t smem = ring_smem(stages, 3);
+    static bool attr_set = false;
+    if (!attr_set) {
+      FPG_CUDA_CHECK(cudaFuncSetAttribute(in_bwd_reduce_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+      FPG_CUDA_CHECK(cudaFuncSetAttribute(in_bwd_apply_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(smem)));
+      attr_set = true;
+    }
+    const RingGeom gm = ring_geom(y, stages, sms);
+    const RingTensor t_dz = ring_tensor(dz), t_y = ring_tensor(y), t_dz2 = dz2 ? ring_tensor(dz2) : ring_tensor(y);
+    if (dz->halo > 0) {  // fold the mirror band of dz in place first (dz is consumed by this call)
+      const int64_t total = static_cast<int64_t>(dz->n) * dz->h * dz->w * (dz->c / 8);
+      halo_fold_inplace_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(dz));
+    }
+    in_bwd_reduce_ring_kernel<<<dim3(gm.ctas_per_img, y->n), kRingThreads, smem, FPG_ST(stream)>>>(
+        view_of(dz), v2, dz2 != nullptr, view_of(y), stats, act, vr, dres != nullptr, scratch, red, counters, inv_hw,
+        t_dz, t_y, t_dz2, gm, 1);
+    in_bwd_apply_ring_kernel<<<dim3(gm.ctas_per_img, y->n), kRingThreads, smem, FPG_ST(stream)>>>(
+        view_of(dz), v2, dz2 != nullptr, dres != nullptr, view_of(y), stats, red, act, view_of(dy),
+        dres ? ring_tensor(dres) : t_dz, t_y, t_dz2, gm, 1);
+    FPG_CUDA_CHECK(cudaGetLastError());
     return 0;
   }
   const int splits = stat_splits(y, resident_ctas(in_bwd_reduce_kernel, kStatThreads));

@@ -342,9 +342,11 @@ class Model:
             pending = []
             for x, y in self._prefetch_to_device(self.train_loader):
                 tr.step(x, y, lr_g=lr_g, lr_d=lr_d)
-                pending.append(tr.loss_buf.clone())  # stays on the device; no host sync per step
-                if len(pending) >= self.log_interval:
-                    self._flush_losses(pending, losses)
+                pending.append(tr.loss_buf.clone())  # stays on the device
+                # losses are read back one step late: the device->host read of step i's losses is issued after step
+                # i+1 has been enqueued, so the GPU never waits for the host between steps
+                if len(pending) > self.log_interval:
+                    self._flush_losses(pending, losses, keep_last=1)
             self._flush_losses(pending, losses)
             self.scheduler_discriminator.step()
             self.scheduler_generator.step()
@@ -424,10 +426,12 @@ class Model:
             self.scheduler_generator.step()
             self.save_results(epoch=epoch, losses=losses, epoch_start_time=t0)
 
-    def _flush_losses(self, pending, losses):
-        if not pending:
+    def _flush_losses(self, pending, losses, keep_last=0):
+        ready = pending[:len(pending) - keep_last]
+        if not ready:
             return
-        vals = torch.stack(pending)
+        del pending[:len(ready)]
+        vals = torch.stack(ready)
         if self._world() > 1:
             dist.all_reduce(vals)
             vals /= self._world()
@@ -435,7 +439,6 @@ class Model:
         for row in vals:
             for k, v in zip(native_trainer.PairedTrainer.LOSS_KEYS, row):
                 losses[k].append(v)
-        pending.clear()
 
     def train_cycle(self):
         """Cycle training (reference :660-758) through the drop-in modules' autograd path."""

@@ -275,7 +275,8 @@ int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_
 /* Backward of z = act(IN(y)). Upstream gradient g = fold(dz) + dz2, where dz is the gradient w.r.t. z INCLUDING
  * its halo when dz->halo > 0 (folded back onto the interior: backward of F.pad(reflect)) and dz2 (may be NULL,
  * halo ignored) is a second gradient branch (residual skip). Writes dy; if dres != NULL also writes g there
- * (gradient flowing on to the residual input). */
+ * (gradient flowing on to the residual input). dz is CONSUMED: when dz->halo > 0 the mirror band of its interior may
+ * be updated in place with the folded halo contributions. */
 int fpg_instnorm_bwd(const fpg_act* dz, const fpg_act* dz2, const fpg_act* y, const float* stats, int act,
                      const fpg_act* dy, const fpg_act* dres, float* scratch, int32_t* counters, void* stream);
 /* dx = fold(dz) * act'(z) for an activation without normalisation (PatchGAN model.0 LeakyReLU): z is the saved

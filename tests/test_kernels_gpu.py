@@ -174,8 +174,12 @@ def test_instnorm_fwd_bwd(shape, halo, act):
     got = zb.t.permute(0, 3, 1, 2).float()
     close_rms(got, z.detach(), 0.02, 0.003, "instnorm apply (incl. halo)")
 
-    dzb = ops.ActBuf(n, h, w, c, halo=halo)
-    dzb.t.copy_(dz.permute(0, 2, 3, 1))
+    def fresh_dz():  # fpg_instnorm_bwd consumes dz (folds its mirror band in place)
+        b = ops.ActBuf(n, h, w, c, halo=halo)
+        b.t.copy_(dz.permute(0, 2, 3, 1))
+        return b
+
+    dzb = fresh_dz()
     dz2b = ops.ActBuf.from_nchw(dz2)
     dyb = ops.ActBuf(n, h, w, c)
     dres = ops.ActBuf(n, h, w, c)
@@ -189,10 +193,10 @@ def test_instnorm_fwd_bwd(shape, halo, act):
     close_rms(dres.to_nchw(), dres_ref, 0.02, 0.003, "halo fold")
     # without dres the apply pass recomputes the fold
     dyb2 = ops.ActBuf(n, h, w, c)
-    ops.instnorm_bwd(dzb, yb, stats, act, dyb2, dz2=dz2b)
+    ops.instnorm_bwd(fresh_dz(), yb, stats, act, dyb2, dz2=dz2b)
     close_rms(dyb2.to_nchw(), dy_ref, 0.03, 0.004, "instnorm bwd (no dres)")
     out = ops.ActBuf(n, h, w, c)
-    ops.halo_fold(dzb, dz2b, out)
+    ops.halo_fold(fresh_dz(), dz2b, out)
     close_rms(out.to_nchw(), dres_ref, 0.02, 0.003, "halo_fold op")
 
 
