@@ -306,6 +306,36 @@ static int plan_dgrad(const fpg_act* dy, const void* wt, const float* bias, int 
       d->out.valid_h = oh;
       d->out.valid_w = ow;
     }
+    // An extent just above a multiple of 64 (66 = 64 + reflect halo) quantises badly into one tile shape (16 x 8
+    // tiles cover 80 x 72 of it): cover x < 64k with 64 x 2 tiles and the few edge columns with tall narrow tiles.
+    const int rem = ow % 64;
+    if (g->stride == 1 && ow > 64 && rem > 0 && rem <= 8 && getenv("FPG_DISABLE_TILE_REGIONS") == nullptr) {
+      const int tw1 = pow2_at_least(rem), th1 = 128 / tw1;
+      const int t0 = (ow / 64) * ceil_div(oh, 2), t1 = ceil_div(oh, th1);
+      const int single = d->tiles_x * d->tiles_y;
+      const int nb_single = d->n_blocks;
+      const int bn2 = pick_block_n(g->c_in, dx->n * (t0 + t1), sms);
+      const int waves_single = ceil_div(dx->n * single * nb_single, sms);
+      const int waves_two = ceil_div(dx->n * (t0 + t1) * (g->c_in / bn2), sms);
+      if (waves_two * bn2 < waves_single * d->block_n) {  // compare in units of (waves x N columns per tile)
+        d->tile_w = 64;
+        d->tile_h = 2;
+        d->tiles_x = ow / 64;
+        d->tiles_y = ceil_div(oh, 2);
+        d->block_n = bn2;
+        d->n_blocks = g->c_in / bn2;
+        d->b.box[1] = bn2;
+        d->stages = pick_stages(128 * 128 + bn2 * 128);
+        make_act_view(dy, 1, cblk, 64, 2, &d->a);
+        make_act_view(dy, 1, cblk, tw1, th1, &d->a1);
+        d->tile_w1 = tw1;
+        d->tile_h1 = th1;
+        d->tiles_x1 = 1;
+        d->tiles_y1 = t1;
+        d->x_org1 = (ow / 64) * 64;
+        continue;  // regions are not combined with CTA pairs
+      }
+    }
     maybe_pair(d, oh, sms);
   }
   *n_descs = nc;

@@ -21,6 +21,9 @@ struct FpropArgs {
   int32_t n_img, tiles_y, tiles_x;
   int32_t tile_w_log2;
   int32_t tile_h, tile_w;
+  // optional second tile region (edge columns x >= x_org1 with their own tile shape and tensor map): tiles
+  // [r0_tiles, r0_tiles + r1_tiles) of the persistent loop
+  int32_t r0_tiles, tiles_y1, tiles_x1, tile_h1, tile_w1, tile_w1_log2, x_org1;
   int32_t m_sub;       // 128-pixel sub-tiles per CTA tile (1 or 2): each K step issues m_sub MMAs sharing one B tile
   int32_t acc_stages;  // accumulator stages in TMEM: 2 if 2 * m_sub * block_n <= 512 else 1
   int32_t act;
@@ -42,7 +45,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 template <int CBLK>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
-                   const __grid_constant__ FpropArgs args) {
+                   const __grid_constant__ CUtensorMap amap1, const __grid_constant__ FpropArgs args) {
   constexpr int SUB = 64 / CBLK;                   // TMA sub-loads per 64-wide K stage
   constexpr uint32_t LAYOUT = swizzle_layout_type(CBLK * 2);
   constexpr uint32_t SBO = 8u * CBLK * 2u;  // 8 rows of one swizzle atom
@@ -93,7 +96,8 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = args.n_img * args.tiles_y * args.tiles_x * args.n_blocks;
+  const int r1_tiles = args.n_img * args.tiles_y1 * args.tiles_x1 * args.n_blocks;
+  const int total_tiles = args.r0_tiles + r1_tiles;
   const int num_kstages = args.num_kstages;
 
   if (warp == 0) {
@@ -102,17 +106,22 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
       uint32_t stage = 0, phase = 0;
       const uint32_t stage_bytes = A_STAGE_BYTES + B_STAGE_BYTES;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int nb = tile % args.n_blocks;
-        int r = tile / args.n_blocks;
-        int tx = r % args.tiles_x;
-        r /= args.tiles_x;
-        int ty = r % args.tiles_y;
-        int n = r / args.tiles_y;
-        const int x0 = tx * args.tile_w, y0 = ty * args.tile_h;
+        const bool r1 = tile >= args.r0_tiles;
+        const int t = r1 ? tile - args.r0_tiles : tile;
+        const int ntx = r1 ? args.tiles_x1 : args.tiles_x, nty = r1 ? args.tiles_y1 : args.tiles_y;
+        const CUtensorMap* am = r1 ? &amap1 : &amap;
+        int nb = t % args.n_blocks;
+        int r = t / args.n_blocks;
+        int tx = r % ntx;
+        r /= ntx;
+        int ty = r % nty;
+        int n = r / nty;
+        const int x0 = r1 ? args.x_org1 + tx * args.tile_w1 : tx * args.tile_w;
+        const int y0 = ty * (r1 ? args.tile_h1 : args.tile_h);
         // the issue time of this thread is on the critical path of the pipeline: no divisions, the tap entry is
         // re-read only when the tap changes
         int tap = 0, ccol = 0, kcol = 0;
-        fpg_tap t = args.taps[0];
+        fpg_tap tp = args.taps[0];
         const int c_per_tap = args.chunks_per_tap * CBLK;
         for (int ks = 0; ks < num_kstages; ++ks) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -121,14 +130,14 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
           uint8_t* b_dst = smem_b + stage * B_STAGE_BYTES;
 #pragma unroll
           for (int j = 0; j < SUB; ++j) {
-            tma_load_5d(&amap, &full[stage], a_dst + j * A_SUB_BYTES, t.c0 + ccol, x0 + t.dx, t.plane, y0 + t.dy, n);
+            tma_load_5d(am, &full[stage], a_dst + j * A_SUB_BYTES, tp.c0 + ccol, x0 + tp.dx, tp.plane, y0 + tp.dy, n);
             tma_load_2d(&bmap, &full[stage], b_dst + j * B_SUB_BYTES, kcol, nb * BN);
             kcol += CBLK;
             ccol += CBLK;
             if (ccol == c_per_tap) {
               ccol = 0;
               ++tap;
-              t = args.taps[tap & (FPG_MAX_TAPS - 1)];
+              tp = args.taps[tap & (FPG_MAX_TAPS - 1)];
             }
           }
           if (++stage == static_cast<uint32_t>(STAGES)) {
@@ -180,19 +189,24 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it % ACC_STAGES, aph = (it / ACC_STAGES) & 1;
-      int nb = tile % args.n_blocks;
-      int r = tile / args.n_blocks;
-      int tx = r % args.tiles_x;
-      r /= args.tiles_x;
-      int ty = r % args.tiles_y;
-      int n = r / args.tiles_y;
+      const bool r1 = tile >= args.r0_tiles;
+      const int t = r1 ? tile - args.r0_tiles : tile;
+      const int ntx = r1 ? args.tiles_x1 : args.tiles_x, nty = r1 ? args.tiles_y1 : args.tiles_y;
+      const int tw = r1 ? args.tile_w1 : args.tile_w, th = r1 ? args.tile_h1 : args.tile_h;
+      const int twl = r1 ? args.tile_w1_log2 : args.tile_w_log2;
+      int nb = t % args.n_blocks;
+      int r = t / args.n_blocks;
+      int tx = r % ntx;
+      r /= ntx;
+      int ty = r % nty;
+      int n = r / nty;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       for (int ms = 0; ms < MS; ++ms) {
         const int row = ms * 128 + q * 32 + lane;
-        const int ry = row >> args.tile_w_log2;
-        const int rx = row & (args.tile_w - 1);
-        const int py = ty * args.tile_h + ry, px = tx * args.tile_w + rx;
+        const int ry = row >> twl;
+        const int rx = row & (tw - 1);
+        const int py = ty * th + ry, px = (r1 ? args.x_org1 : 0) + tx * tw + rx;
         const bool valid = (py < args.out.valid_h) && (px < args.out.valid_w);
         const int64_t off = static_cast<int64_t>(n) * args.out.stride_n +
                             static_cast<int64_t>(py * args.out.mul_y + args.out.off_y) * args.out.stride_y +
@@ -772,6 +786,20 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
   args.tile_w_log2 = log2_exact(d->tile_w);
   args.tile_h = d->tile_h;
   args.tile_w = d->tile_w;
+  args.r0_tiles = d->n_img * d->tiles_y * d->tiles_x * d->n_blocks;
+  const bool two_regions = d->tiles_x1 > 0 && d->tiles_y1 > 0;
+  args.tiles_y1 = two_regions ? d->tiles_y1 : 0;
+  args.tiles_x1 = two_regions ? d->tiles_x1 : 0;
+  args.tile_h1 = two_regions ? d->tile_h1 : 1;
+  args.tile_w1 = two_regions ? d->tile_w1 : 1;
+  args.tile_w1_log2 = two_regions ? log2_exact(d->tile_w1) : 0;
+  args.x_org1 = two_regions ? d->x_org1 : 0;
+  CUtensorMap amap1 = amap;
+  if (two_regions) {
+    FPG_REQUIRE(!d->cta_pair && d->tile_h1 * d->tile_w1 == 128 && log2_exact(d->tile_w1) >= 0, "second tile region");
+    rc = encode_tmap(&d->a1, &amap1);
+    if (rc) return rc;
+  }
   args.m_sub = m_sub;
   args.acc_stages = (2 * m_sub * d->block_n <= 512) ? 2 : 1;
   args.act = d->act;
@@ -780,7 +808,8 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
   args.out = d->out;
   for (int i = 0; i < FPG_MAX_TAPS; ++i) args.taps[i] = d->taps[i];
 
-  const int total_tiles = d->n_img * d->tiles_y * d->tiles_x * d->n_blocks;
+  const int total_tiles = d->n_img * d->tiles_y * d->tiles_x * d->n_blocks +
+                          (two_regions ? d->n_img * d->tiles_y1 * d->tiles_x1 * d->n_blocks : 0);
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -810,7 +839,7 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
   do {                                                                                                           \
     FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_fprop_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                         static_cast<int>(smem)));                                                \
-    igemm_fprop_kernel<CB><<<grid, kThreads, smem, st>>>(amap, bmap, args);                                      \
+    igemm_fprop_kernel<CB><<<grid, kThreads, smem, st>>>(amap, bmap, amap1, args);                                      \
   } while (0)
   if (d->cblk == 64) {
     FPG_LAUNCH_FPROP(64);

@@ -33,7 +33,8 @@ class FpropDesc(C.Structure):
                 ("num_sub", C.c_int32), ("block_n", C.c_int32), ("n_blocks", C.c_int32), ("n_img", C.c_int32),
                 ("tiles_y", C.c_int32), ("tiles_x", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32),
                 ("act", C.c_int32), ("stages", C.c_int32), ("cta_pair", C.c_int32), ("bias", C.c_void_p), ("out", OutView),
-                ("taps", Tap * FPG_MAX_TAPS)]
+                ("taps", Tap * FPG_MAX_TAPS), ("a1", TMap), ("tiles_y1", C.c_int32), ("tiles_x1", C.c_int32),
+                ("tile_h1", C.c_int32), ("tile_w1", C.c_int32), ("x_org1", C.c_int32)]
 
 
 class RowsDesc(C.Structure):

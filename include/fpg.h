@@ -91,6 +91,12 @@ typedef struct {
   const float* bias; /* [n_total] or NULL */
   fpg_out_view out;
   fpg_tap taps[FPG_MAX_TAPS];
+  /* Optional second tile region (tiles_x1 > 0): the columns x >= x_org1 are covered by tiles of tile_w1 x tile_h1
+   * pixels gathered through `a1` (same view, different box), so that an extent just above a multiple of 64 (66 = a
+   * 64-pixel row with its reflect halo) does not force a tile shape that wastes a third of every tile; region 0 then
+   * covers x < x_org1 only (tiles_x * tile_w == x_org1). Not combined with cta_pair. */
+  fpg_tmap a1;
+  int32_t tiles_y1, tiles_x1, tile_h1, tile_w1, x_org1;
 } fpg_igemm_fprop_desc;
 
 /* D_item[m, n] = sum_{pixel} X[pixel + xtap, xc + m] * Y[pixel + ytap, yc + n], split over pixel ranges,

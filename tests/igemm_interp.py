@@ -53,16 +53,21 @@ def run_fprop(desc, abuf, bbuf, outbuf, bias=None):
         assert int(desc.b.box[1]) * 2 == bn and desc.tile_h * desc.tile_w == 128
     else:
         assert int(desc.b.box[1]) == bn
+    regions = [(desc.a, desc.tiles_y * pair, desc.tiles_x, desc.tile_h, desc.tile_w, 0)]
+    if desc.tiles_x1 > 0:  # second tile region: edge columns with their own tile shape
+        assert not desc.cta_pair and desc.tile_h1 * desc.tile_w1 == 128 and desc.tiles_x * desc.tile_w == desc.x_org1
+        regions.append((desc.a1, desc.tiles_y1, desc.tiles_x1, desc.tile_h1, desc.tile_w1, desc.x_org1))
     for n in range(desc.n_img):
-        for ty in range(desc.tiles_y * pair):  # pair tiles: rank r of the cluster takes row-tile 2*ty + r
-            for tx in range(desc.tiles_x):
-                x0, y0 = tx * desc.tile_w, ty * desc.tile_h
-                acc = np.zeros((desc.tile_h, desc.tile_w, n_total), dtype=np.float64)
+      for (amap, n_ty, n_tx, tile_h, tile_w, x_org) in regions:
+        for ty in range(n_ty):  # pair tiles: rank r of the cluster takes row-tile 2*ty + r
+            for tx in range(n_tx):
+                x0, y0 = x_org + tx * tile_w, ty * tile_h
+                acc = np.zeros((tile_h, tile_w, n_total), dtype=np.float64)
                 for sub in range(desc.num_sub):
                     tap, chunk = divmod(sub, cpt)
                     t = desc.taps[tap]
-                    a = _tmap_gather(desc.a, abuf, [t.c0 + chunk * cblk, x0 + t.dx, t.plane, y0 + t.dy, n])
-                    a = a.reshape(desc.tile_h, desc.tile_w, cblk)  # (n=1, y, plane=1, x, c)
+                    a = _tmap_gather(amap, abuf, [t.c0 + chunk * cblk, x0 + t.dx, t.plane, y0 + t.dy, n])
+                    a = a.reshape(tile_h, tile_w, cblk)  # (n=1, y, plane=1, x, c)
                     acc += a.astype(np.float64) @ bmat[:, sub * cblk:(sub + 1) * cblk].T.astype(np.float64)
                 if bias is not None:
                     acc += bias[None, None, :n_total]
@@ -72,11 +77,11 @@ def run_fprop(desc, abuf, bbuf, outbuf, bias=None):
                     acc = np.where(acc > 0, acc, 0.2 * acc)
                 elif desc.act == 3:
                     acc = np.tanh(acc)
-                for ry in range(desc.tile_h):
+                for ry in range(tile_h):
                     py = y0 + ry
                     if py >= o.valid_h:
                         continue
-                    for rx in range(desc.tile_w):
+                    for rx in range(tile_w):
                         px = x0 + rx
                         if px >= o.valid_w:
                             continue

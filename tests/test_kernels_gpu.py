@@ -48,6 +48,7 @@ CONV_CASES = [
     (2, 130, 256, 64, 27, 7, 1, 0, 3),    # content head: filter-row ring, 132 tiles, ragged last row tile
     (1, 20, 200, 27, 64, 3, 1, 1, 0),     # zero-padded 3x3 on a ragged width (two column tiles, SW64)
     (19, 64, 128, 64, 27, 7, 1, 0, 3),    # 304 tiles > 148 SMs: persistent loop over both accumulator stages
+    (16, 64, 64, 256, 256, 3, 1, 0, 1),   # B=16 residual conv: dgrad over the 66x66 haloed grid uses two tile regions
 ]
 
 

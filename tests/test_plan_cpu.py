@@ -118,6 +118,7 @@ DGRAD_CASES = [
     (1, 7, 7, 128, 128, 1, 16, 4, 1, 1, 0),     # model.11: 16-channel dy (SW32 path)
     (1, 12, 12, 64, 64, 27, 32, 7, 1, 0, 3),    # content head: 32-channel dy (SW64 path), halo 3
     (1, 16, 16, 12, 16, 64, 64, 4, 2, 1, 0),    # model.0: gradient w.r.t. the 16-channel D input
+    (16, 64, 64, 64, 64, 64, 64, 3, 1, 0, 1),   # 66x66 haloed gradient: two tile regions (64x2 tiles + edge columns)
 ]
 
 
@@ -139,6 +140,8 @@ def test_dgrad_plan_matches_autograd(fpglib, case):
     L.call("fpg_conv2d_dgrad_plan", C.byref(dya), interp.FAKE_BASE, None, L.ACT_NONE, C.byref(g), C.byref(dxa), SMS,
            descs, C.byref(nd))
     assert nd.value == (4 if stride == 2 else 1)
+    if h == 64:
+        assert descs[0].tiles_x1 == 1 and descs[0].x_org1 == 64 and descs[0].tile_w == 64, "expected two tile regions"
     abuf = nhwc_buffer(dy, kp)
     bbuf = pack_dgrad(fpglib, wt, g)
     hp, wp = h + 2 * halo, w + 2 * halo
