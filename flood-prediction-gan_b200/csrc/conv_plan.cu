@@ -806,6 +806,67 @@ pack_batched_kernel(const fpg_pack_job* __restrict__ jobs, const int32_t* __rest
   }
 }
 
+// stats[(i*c + ch)*2] = {mean, rstd} of image i from the epilogue partials [i][rows][c][2] (fixed summation order).
+// block = 64 channels x 4 row groups
+__global__ void __launch_bounds__(256)
+stats_finalize_kernel(const float* __restrict__ partial, int rows, int c, float inv_count, float eps,
+                      float* __restrict__ stats) {
+  const int i = blockIdx.x;
+  const int ch = blockIdx.y * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
+  __shared__ float2 red[4][64];
+  float a = 0.f, b = 0.f;
+  if (ch < c) {
+    const float2* p = reinterpret_cast<const float2*>(partial) + static_cast<int64_t>(i) * rows * c + ch;
+#pragma unroll 8
+    for (int r = part; r < rows; r += 4) {
+      const float2 v = __ldcg(p + static_cast<int64_t>(r) * c);
+      a += v.x;
+      b += v.y;
+    }
+  }
+  red[part][threadIdx.x & 63] = make_float2(a, b);
+  __syncthreads();
+  if (part == 0 && ch < c) {
+    for (int q = 1; q < 4; ++q) {
+      a += red[q][threadIdx.x].x;
+      b += red[q][threadIdx.x].y;
+    }
+    const float mean = a * inv_count;
+    const float var = fmaxf(b * inv_count - mean * mean, 0.f);
+    stats[(static_cast<int64_t>(i) * c + ch) * 2] = mean;
+    stats[(static_cast<int64_t>(i) * c + ch) * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
+// partial rows [n][rows][c][2] -> [n][ceil(rows / 256)][c][2] (fixed order): keeps the final reduction short when a
+// batch-statistics layer has 10^5 partial rows
+__global__ void __launch_bounds__(256)
+stats_rows_reduce_kernel(const float* __restrict__ in, int rows, int c, float* __restrict__ out, int out_rows) {
+  const int i = blockIdx.x, grp = blockIdx.y;
+  const int ch = blockIdx.z * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
+  __shared__ float2 red[4][64];
+  float a = 0.f, b = 0.f;
+  if (ch < c) {
+    const float2* p = reinterpret_cast<const float2*>(in) + static_cast<int64_t>(i) * rows * c + ch;
+    const int r_end = min(rows, (grp + 1) * 256);
+#pragma unroll 8
+    for (int r = grp * 256 + part; r < r_end; r += 4) {
+      const float2 v = __ldcg(p + static_cast<int64_t>(r) * c);
+      a += v.x;
+      b += v.y;
+    }
+  }
+  red[part][threadIdx.x & 63] = make_float2(a, b);
+  __syncthreads();
+  if (part == 0 && ch < c) {
+    for (int q = 1; q < 4; ++q) {
+      a += red[q][threadIdx.x].x;
+      b += red[q][threadIdx.x].y;
+    }
+    reinterpret_cast<float2*>(out)[(static_cast<int64_t>(i) * out_rows + grp) * c + ch] = make_float2(a, b);
+  }
+}
+
 }  // namespace fpg
 
 using namespace fpg;
@@ -859,6 +920,90 @@ int fpg_conv2d_dgrad(const fpg_act* dy, const void* w_packed_t, const float* bia
 int fpg_conv2d_rows_plan(const fpg_act* a, const void* w_packed, const float* bias, int act, const fpg_conv_geom* g,
                          const fpg_act* out, int dgrad, int sm_count, fpg_igemm_rows_desc* out_desc) {
   return plan_rows(a, w_packed, bias, act, g, out, dgrad, sm_count, out_desc);
+}
+
+static int stats_rows_of(const fpg_igemm_fprop_desc* d) {
+  return (d->tiles_y * d->tiles_x * (d->cta_pair ? 2 : 1) + d->tiles_y1 * d->tiles_x1) * 4;
+}
+
+// rows per image of the epilogue statistics that fpg_conv2d_fprop_stats / _dgrad_stats produce for this layer
+// (0: the layer runs on a kernel without that epilogue and the caller uses fpg_instnorm_stats instead)
+int32_t fpg_conv_stats_rows(const fpg_act* a, const fpg_conv_geom* g, const fpg_act* out, int dgrad) {
+  const int sms = sm_count_cached() > 0 ? sm_count_cached() : 148;
+  fpg_igemm_rows_desc rd;
+  if (plan_rows(a, nullptr, nullptr, 0, g, out, dgrad, sms, &rd) == 0) return 0;
+  fpg_igemm_fprop_desc d[4];
+  int n = 1;
+  if (dgrad) {
+    if (plan_dgrad(a, nullptr, nullptr, 0, g, out, sms, d, &n)) return -1;
+  } else {
+    if (plan_fprop(a, nullptr, nullptr, 0, g, out, sms, &d[0])) return -1;
+  }
+  int rows = 0;
+  for (int q = 0; q < n; ++q) rows += stats_rows_of(&d[q]);
+  return rows;
+}
+
+int fpg_conv2d_fprop_stats(const fpg_act* x, const void* w_packed, const float* bias, int act, const fpg_conv_geom* g,
+                           const fpg_act* y, float* stat_partial, void* stream) {
+  FPG_REQUIRE(stat_partial != nullptr, "null statistics buffer");
+  fpg_igemm_fprop_desc d;
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
+  fpg_igemm_rows_desc rd;
+  FPG_REQUIRE(plan_rows(x, w_packed, bias, act, g, y, 0, sms, &rd) == 1, "layer runs on the row-stationary kernel");
+  int rc = plan_fprop(x, w_packed, bias, act, g, y, sms, &d);
+  if (rc) return rc;
+  d.stat_partial = stat_partial;
+  d.stat_rows_per_img = stats_rows_of(&d);
+  d.stat_row0 = 0;
+  return fpg_igemm_fprop_launch(&d, stream);
+}
+
+int fpg_conv2d_dgrad_stats(const fpg_act* dy, const void* w_packed_t, const float* bias, int act,
+                           const fpg_conv_geom* g, const fpg_act* dx, float* stat_partial, void* stream) {
+  FPG_REQUIRE(stat_partial != nullptr, "null statistics buffer");
+  fpg_igemm_fprop_desc d[4];
+  int n = 0;
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
+  fpg_igemm_rows_desc rd;
+  FPG_REQUIRE(plan_rows(dy, w_packed_t, bias, act, g, dx, 1, sms, &rd) == 1, "layer runs on the row-stationary kernel");
+  int rc = plan_dgrad(dy, w_packed_t, bias, act, g, dx, sms, d, &n);
+  if (rc) return rc;
+  int rows = 0;
+  for (int q = 0; q < n; ++q) rows += stats_rows_of(&d[q]);
+  int row0 = 0;
+  for (int q = 0; q < n; ++q) {
+    d[q].stat_partial = stat_partial;
+    d[q].stat_rows_per_img = rows;
+    d[q].stat_row0 = row0;
+    row0 += stats_rows_of(&d[q]);
+    rc = fpg_igemm_fprop_launch(&d[q], stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int fpg_instnorm_stats_finalize(const float* stat_partial, int32_t rows_per_img, int32_t n, int32_t c,
+                                int64_t count_per_img, float eps, float* stats, void* stream) {
+  FPG_REQUIRE(stat_partial && stats && rows_per_img > 0 && n > 0 && c > 0 && count_per_img > 0, "bad argument");
+  const float* cur = stat_partial;
+  int rows = rows_per_img;
+  // long row lists are first folded 256:1 into the tail of the buffer (the caller sizes it for that)
+  float* spare = const_cast<float*>(stat_partial) + static_cast<int64_t>(n) * rows_per_img * c * 2;
+  while (rows > 512) {
+    const int out_rows = (rows + 255) / 256;
+    stats_rows_reduce_kernel<<<dim3(n, out_rows, (c + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        cur, rows, c, spare, out_rows);
+    cur = spare;
+    spare += static_cast<int64_t>(n) * out_rows * c * 2;
+    rows = out_rows;
+  }
+  stats_finalize_kernel<<<dim3(n, (c + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      cur, rows, c, 1.f / static_cast<float>(count_per_img), eps, stats);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
 }
 
 int fpg_conv2d_wgrad_plan(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g, int sm_count,

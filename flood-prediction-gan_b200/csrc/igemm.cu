@@ -13,6 +13,16 @@ namespace fpg {
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
 
+// InstanceNorm / BatchNorm statistics from the epilogue: per (tile row-quarter, column) partial {sum, sum of squares} of
+// the bf16-rounded values that are stored (a later tiny kernel reduces the rows of an image in a fixed order). Saves
+// the separate pass that re-reads the whole activation.
+struct StatOut {
+  float* partial;        // [n_img][rows_per_img][c_total][2]; nullptr = off
+  int32_t rows_per_img;  // partial rows of one image over all launches that contribute to it
+  int32_t row0;          // first row of this launch inside an image
+  int32_t c_total;
+};
+
 struct FpropArgs {
   int32_t chunks_per_tap;
   int32_t num_kstages;
@@ -30,8 +40,43 @@ struct FpropArgs {
   int32_t stages;
   const float* bias;
   fpg_out_view out;
+  StatOut stat;
   fpg_tap taps[FPG_MAX_TAPS];
 };
+
+// Column sums over the 32 rows of a warp for 16 consecutive columns held per lane: a butterfly that halves the
+// columns kept at every step (16 -> 8 -> 4 -> 2 -> 1 per lane, 15 + 1 shuffles instead of 80). Afterwards lane l holds
+// the 32-row sum of column 8*b4 + 4*b3 + 2*b2 + b1 (b_k = bit k of l); lanes l and l^1 hold the same column.
+__device__ __forceinline__ float warp_colsum16(float (&a)[16], int lane) {
+#pragma unroll
+  for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+    const bool hi = (lane & bit) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float keep = hi ? a[j + half] : a[j];
+      const float send = hi ? a[j] : a[j + half];
+      a[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
+}
+
+__device__ __forceinline__ void stat_accumulate(const StatOut& so, const float (&f)[16], bool valid, int lane,
+                                                int64_t prow, int col0) {
+  float a[16], b[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float r = valid ? __bfloat162float(__float2bfloat16(f[i])) : 0.f;
+    a[i] = r;
+    b[i] = r * r;
+  }
+  const float sa = warp_colsum16(a, lane);
+  const float sb = warp_colsum16(b, lane);
+  if ((lane & 1) == 0) {
+    const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    reinterpret_cast<float2*>(so.partial)[prow * so.c_total + col0 + col] = make_float2(sa, sb);
+  }
+}
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
@@ -213,6 +258,9 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                             static_cast<int64_t>(px * args.out.mul_x + args.out.off_x) * args.out.stride_x +
                             static_cast<int64_t>(nb) * BN;
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * ACC_COLS + ms * BN;
+        // statistics row of this warp: image-major, then (region, tile row, tile column, warp quarter)
+        const int64_t prow = static_cast<int64_t>(n) * args.stat.rows_per_img + args.stat.row0 +
+                             ((r1 ? args.tiles_y * args.tiles_x : 0) + ty * ntx + tx) * 4 + q;
         for (int c = 0; c < BN; c += 16) {
           uint32_t v[16];
           tmem_ld16(t_addr + c, v);
@@ -235,6 +283,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], args.act);
           }
+          if (args.stat.partial != nullptr) stat_accumulate(args.stat, f, valid, lane, prow, nb * BN + c);
           if (valid) {
             if (args.out.fp32) {
               float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out.base) + off + c);
@@ -426,6 +475,8 @@ igemm_fprop2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
+      const int64_t prow = static_cast<int64_t>(n) * args.stat.rows_per_img + args.stat.row0 +
+                           ((ty * 2 + static_cast<int>(rank)) * args.tiles_x + tx) * 4 + q;
       for (int c = 0; c < BN; c += 16) {
         uint32_t v[16];
         tmem_ld16(t_addr + c, v);
@@ -448,6 +499,7 @@ igemm_fprop2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], args.act);
         }
+        if (args.stat.partial != nullptr) stat_accumulate(args.stat, f, valid, lane, prow, nb * BN + c);
         if (valid) {
           if (args.out.fp32) {
             float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out.base) + off + c);
@@ -806,6 +858,10 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
   args.stages = d->stages;
   args.bias = d->bias;
   args.out = d->out;
+  args.stat.partial = d->stat_partial;
+  args.stat.rows_per_img = d->stat_rows_per_img;
+  args.stat.row0 = d->stat_row0;
+  args.stat.c_total = d->block_n * d->n_blocks;
   for (int i = 0; i < FPG_MAX_TAPS; ++i) args.taps[i] = d->taps[i];
 
   const int total_tiles = d->n_img * d->tiles_y * d->tiles_x * d->n_blocks +

@@ -34,7 +34,8 @@ class FpropDesc(C.Structure):
                 ("tiles_y", C.c_int32), ("tiles_x", C.c_int32), ("tile_h", C.c_int32), ("tile_w", C.c_int32),
                 ("act", C.c_int32), ("stages", C.c_int32), ("cta_pair", C.c_int32), ("bias", C.c_void_p), ("out", OutView),
                 ("taps", Tap * FPG_MAX_TAPS), ("a1", TMap), ("tiles_y1", C.c_int32), ("tiles_x1", C.c_int32),
-                ("tile_h1", C.c_int32), ("tile_w1", C.c_int32), ("x_org1", C.c_int32)]
+                ("tile_h1", C.c_int32), ("tile_w1", C.c_int32), ("x_org1", C.c_int32), ("stat_partial", C.c_void_p),
+                ("stat_rows_per_img", C.c_int32), ("stat_row0", C.c_int32)]
 
 
 class RowsDesc(C.Structure):
@@ -93,6 +94,10 @@ SIGNATURES = {
     "fpg_conv2d_dgrad": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), _vp]),
     "fpg_conv2d_dgrad_plan": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), C.c_int, _P(FpropDesc),
                                         _P(C.c_int)]),
+    "fpg_conv_stats_rows": (_i32, [_P(Act), _P(ConvGeom), _P(Act), C.c_int]),
+    "fpg_conv2d_fprop_stats": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), _vp, _vp]),
+    "fpg_conv2d_dgrad_stats": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), _vp, _vp]),
+    "fpg_instnorm_stats_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _f32, _vp, _vp]),
     "fpg_conv2d_wgrad": (C.c_int, [_P(Act), _P(Act), _P(ConvGeom), _vp, _i64, _i64, _i32, _i32, _vp, _vp]),
     "fpg_conv2d_wgrad_plan": (C.c_int, [_P(Act), _P(Act), _P(ConvGeom), C.c_int, _P(WgradDesc)]),
     "fpg_conv2d_wgrad_ws_bytes": (_i64, [_P(Act), _P(Act), _P(ConvGeom), C.c_int]),

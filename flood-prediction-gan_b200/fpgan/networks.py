@@ -159,6 +159,36 @@ class _NetBase:
             ops.conv_fprop(x, L.spec, y, bias=bias, act=act)
         return y
 
+    def _conv_stats(self, x, name, batch=False, eps=1e-5):
+        """Raw forward conv of a normalised layer plus its {mean, rstd}: from the conv epilogue where the kernel has
+        that epilogue (no separate pass over the activation), else from the statistics kernel."""
+        L = self.layers[name]
+        g = L.spec.g
+        if L.transposed:
+            y = ActBuf(x.n, x.h * 2, x.w * 2, g.c_in, zero=False)
+        else:
+            hp, wp = x.h + 2 * x.halo, x.w + 2 * x.halo
+            y = ActBuf(x.n, (hp + 2 * g.pad - g.r) // g.stride + 1, (wp + 2 * g.pad - g.s) // g.stride + 1, g.c_out,
+                       zero=False)
+        stats = torch.empty((1 if batch else y.n) * y.c * 2, dtype=torch.float32, device=y.t.device)
+        if not ops.conv_with_stats(x, L.spec, y, stats, transposed=L.transposed, eps=eps, batch=batch):
+            if L.transposed:
+                ops.conv_dgrad(x, L.spec, y)
+            else:
+                ops.conv_fprop(x, L.spec, y)
+            if batch:
+                ops.batch_stats(y, stats, eps)
+            else:
+                ops.instnorm_stats(y, stats, eps)
+        return y, stats
+
+    def _conv_in(self, x, name, act, halo, residual=None):
+        """conv -> InstanceNorm -> activation (+ residual, + reflect halo); returns (y, stats, z)"""
+        y, stats = self._conv_stats(x, name)
+        z = ActBuf(y.n, y.h, y.w, y.c, halo=halo, zero=False)
+        ops.instnorm_apply(y, stats, act, z, residual=residual)
+        return y, stats, z
+
     def _conv_bwd(self, name, x, dy, grads, need_dx, dx_halo=0):
         """Backward of layer `name`: x = saved layer input, dy = gradient of its raw output.
         Writes the weight (and used bias) gradient into `grads`; returns dx (incl. halo when dx_halo > 0)."""
@@ -202,30 +232,23 @@ class _ResnetGeneratorNet(_NetBase):
         c1, c2, c3 = self.STEM
         t["xin"] = ActBuf(B, H, W, 16, halo=3, zero=False)
         ops.pack_nchw(x, t["xin"], 0, zero_rest=True)
-        t["y1"] = self._conv(t["xin"], c1)
-        t["s1"], t["z1"] = _norm_act(t["y1"], ACT_RELU, 0)
-        t["y2"] = self._conv(t["z1"], c2)
-        t["s2"], t["z2"] = _norm_act(t["y2"], ACT_RELU, 0)
-        t["y3"] = self._conv(t["z2"], c3)
-        t["s3"], xcur = _norm_act(t["y3"], ACT_RELU, 1)
+        t["y1"], t["s1"], t["z1"] = self._conv_in(t["xin"], c1, ACT_RELU, 0)
+        t["y2"], t["s2"], t["z2"] = self._conv_in(t["z1"], c2, ACT_RELU, 0)
+        t["y3"], t["s3"], xcur = self._conv_in(t["z2"], c3, ACT_RELU, 1)
         t["x0"] = xcur
         for i in range(self.n_blocks):
             n1, n2 = self._block_names(i)
-            ya = self._conv(xcur, n1)
-            sa, za = _norm_act(ya, ACT_RELU, 1)
-            yb = self._conv(za, n2)
+            ya, sa, za = self._conv_in(xcur, n1, ACT_RELU, 1)
             last = i == self.n_blocks - 1
-            sb, xnext = _norm_act(yb, ACT_NONE, 0 if last else 1, residual=xcur)
+            yb, sb, xnext = self._conv_in(za, n2, ACT_NONE, 0 if last else 1, residual=xcur)
             t[f"b{i}"] = (ya, sa, za, yb, sb)
             t[f"x{i + 1}"] = xnext
             xcur = xnext
         return xcur
 
     def _decoder_forward(self, x, up1, up2, halo_out):
-        u1 = self._conv(x, up1)
-        s1, v1 = _norm_act(u1, ACT_RELU, 0)
-        u2 = self._conv(v1, up2)
-        s2, v2 = _norm_act(u2, ACT_RELU, halo_out)
+        u1, s1, v1 = self._conv_in(x, up1, ACT_RELU, 0)
+        u2, s2, v2 = self._conv_in(v1, up2, ACT_RELU, halo_out)
         return (u1, s1, v1, u2, s2, v2)
 
     def _decoder_backward(self, saved, x_top, dv2, up1, up2, grads):
@@ -399,12 +422,9 @@ class PatchGANNet(_NetBase):
         self.repack()
         t = {"din": din}
         t["a1"] = self._conv(din, "model.0", act=ACT_LEAKY)
-        t["y2"] = self._conv(t["a1"], "model.2")
-        t["s2"], t["a2"] = _norm_act(t["y2"], ACT_LEAKY, 0)
-        t["y3"] = self._conv(t["a2"], "model.5")
-        t["s3"], t["a3"] = _norm_act(t["y3"], ACT_LEAKY, 0)
-        t["y4"] = self._conv(t["a3"], "model.8")
-        t["s4"], t["a4"] = _norm_act(t["y4"], ACT_LEAKY, 0)
+        t["y2"], t["s2"], t["a2"] = self._conv_in(t["a1"], "model.2", ACT_LEAKY, 0)
+        t["y3"], t["s3"], t["a3"] = self._conv_in(t["a2"], "model.5", ACT_LEAKY, 0)
+        t["y4"], t["s4"], t["a4"] = self._conv_in(t["a3"], "model.8", ACT_LEAKY, 0)
         t["logits"] = self._conv(t["a4"], "model.11", fp32=True)
         return t["logits"], t
 
@@ -438,9 +458,10 @@ class PatchGANNet(_NetBase):
 class _BatchNormMixin:
     """BatchNorm2d in training mode for the executors below: batch statistics + running-statistics side effects."""
 
-    def _bn_forward(self, y, bn, act1, z1, act2=ACT_NONE, z2=None, mask=None):
-        stats = torch.empty(y.c * 2, dtype=torch.float32, device=y.t.device)
-        ops.batch_stats(y, stats, bn.eps)
+    def _bn_forward(self, y, bn, act1, z1, act2=ACT_NONE, z2=None, mask=None, stats=None):
+        if stats is None:
+            stats = torch.empty(y.c * 2, dtype=torch.float32, device=y.t.device)
+            ops.batch_stats(y, stats, bn.eps)
         if bn.track_running_stats and bn.training:
             ops.batchnorm_running_update(stats, y.n * y.h * y.w, bn.running_mean, bn.running_var, bn.eps,
                                          bn.momentum)
@@ -663,12 +684,12 @@ class UNetNet(_NetBase, _BatchNormMixin):
         """conv-BN-ReLU twice; the second result may be written into `out` (a channel slice of a concatenation
         buffer)"""
         bn1, bn2 = self.doubles[prefix]
-        y = self._conv(x, prefix + ".0")
+        y, st = self._conv_stats(x, prefix + ".0", batch=True, eps=bn1.eps)
         a = ActBuf(y.n, y.h, y.w, y.c, zero=False)
-        self._bn_forward(y, bn1, ACT_RELU, a)
-        y2 = self._conv(a, prefix + ".3")
+        self._bn_forward(y, bn1, ACT_RELU, a, stats=st)
+        y2, st2 = self._conv_stats(a, prefix + ".3", batch=True, eps=bn2.eps)
         z = out if out is not None else ActBuf(y2.n, y2.h, y2.w, y2.c, zero=False)
-        self._bn_forward(y2, bn2, ACT_RELU, z)
+        self._bn_forward(y2, bn2, ACT_RELU, z, stats=st2)
         return z
 
     def forward(self, x):

@@ -169,6 +169,40 @@ def conv_dgrad(dy, spec, dx, bias=None, act=ACT_NONE):
          _ptr(spec.w_dgrad), _ptr(bias), act, spec.gref(), dx.ref(), _stream())
 
 
+_stat_ws = {}
+
+
+def _stat_workspace(nfloats, device):
+    """partials of the epilogue statistics (own buffer: the generic workspace is in use by other kernels)"""
+    key = str(device)
+    cur = _stat_ws.get(key)
+    if cur is None or cur.numel() < nfloats:
+        cur = torch.empty(max(nfloats, 1 << 22), dtype=torch.float32, device=device)
+        _stat_ws[key] = cur
+    return cur
+
+
+def conv_with_stats(x, spec, y, stats, transposed=False, eps=1e-5, batch=False):
+    """y = conv(x) (or the transposed-conv forward) and stats = per-(image, channel) {mean, rstd} of y computed from
+    the conv epilogue; `batch`: statistics over the whole batch (BatchNorm). Returns False if this layer's kernel has no
+    statistics epilogue (the caller then runs instnorm_stats)."""
+    lib = L.load()
+    rows = lib.fpg_conv_stats_rows(x.ref(), spec.gref(), y.ref(), 1 if transposed else 0)
+    if rows <= 0:
+        return False
+    ws = _stat_workspace(int(1.02 * y.n * rows * y.c * 2) + 4096, y.t.device)
+    if transposed:
+        _run(_conv_key("dgrad", y.n, y.h, y.w, spec), 4 if spec.g.stride == 2 else 1, "fpg_conv2d_dgrad_stats", x.ref(),
+             _ptr(spec.w_dgrad), None, ACT_NONE, spec.gref(), y.ref(), _ptr(ws), _stream())
+    else:
+        _run(_conv_key("fprop", y.n, y.h, y.w, spec), 1, "fpg_conv2d_fprop_stats", x.ref(), _ptr(spec.w_fprop), None,
+             ACT_NONE, spec.gref(), y.ref(), _ptr(ws), _stream())
+    n, per = (1, y.n * rows) if batch else (y.n, rows)
+    _run("instnorm_stats", 1, "fpg_instnorm_stats_finalize", _ptr(ws), per, n, y.c,
+         (y.n if batch else 1) * y.h * y.w, eps, _ptr(stats), _stream())
+    return True
+
+
 _ws_cache = {}
 
 

@@ -97,6 +97,12 @@ typedef struct {
    * covers x < x_org1 only (tiles_x * tile_w == x_org1). Not combined with cta_pair. */
   fpg_tmap a1;
   int32_t tiles_y1, tiles_x1, tile_h1, tile_w1, x_org1;
+  /* Optional normalisation statistics from the epilogue (stat_partial != NULL): every epilogue warp writes the
+   * {sum, sum of squares} over its 32 pixel rows of the bf16-rounded stored values of every column to
+   * stat_partial[image][stat_row0 + local row][column][2]; local row = (tile index inside the image) * 4 + warp.
+   * fpg_conv_stats_rows() gives the rows one launch contributes per image. */
+  float* stat_partial;
+  int32_t stat_rows_per_img, stat_row0;
 } fpg_igemm_fprop_desc;
 
 /* D_item[m, n] = sum_{pixel} X[pixel + xtap, xc + m] * Y[pixel + ytap, yc + n], split over pixel ranges,
@@ -209,6 +215,20 @@ int fpg_conv2d_dgrad_plan(const fpg_act* dy, const void* w_packed_t, const float
  * kernel), another code on invalid arguments. fpg_conv2d_fprop and fpg_conv2d_dgrad call this first. */
 int fpg_conv2d_rows_plan(const fpg_act* a, const void* w_packed, const float* bias, int act, const fpg_conv_geom* g,
                          const fpg_act* out, int dgrad, int sm_count, fpg_igemm_rows_desc* out_desc);
+
+/* Convolution + normalisation statistics in one pass: as fpg_conv2d_fprop / fpg_conv2d_dgrad, and the epilogue also
+ * writes per-warp partial column sums of the stored output to stat_partial (>= 1.02 * n * rows * c_out_padded * 2
+ * + 4096 floats: the tail is scratch of the finalisation; rows = fpg_conv_stats_rows(); 0 rows: this layer runs on the
+ * row-stationary kernel, use fpg_instnorm_stats).
+ * fpg_instnorm_stats_finalize reduces them to stats[(n*c + ch)*2] = {mean, rstd} (n = 1 and count = N*H*W: BatchNorm).
+ * Replaces the separate statistics pass of nn.InstanceNorm2d / nn.BatchNorm2d (model_architectures.py:313-333). */
+int32_t fpg_conv_stats_rows(const fpg_act* a, const fpg_conv_geom* g, const fpg_act* out, int dgrad);
+int fpg_conv2d_fprop_stats(const fpg_act* x, const void* w_packed, const float* bias, int act, const fpg_conv_geom* g,
+                           const fpg_act* y, float* stat_partial, void* stream);
+int fpg_conv2d_dgrad_stats(const fpg_act* dy, const void* w_packed_t, const float* bias, int act,
+                           const fpg_conv_geom* g, const fpg_act* dx, float* stat_partial, void* stream);
+int fpg_instnorm_stats_finalize(const float* stat_partial, int32_t rows_per_img, int32_t n, int32_t c,
+                                int64_t count_per_img, float eps, float* stats, void* stream);
 
 /* dw = conv_backward_weight(x, dy): fp32 gradient written (not accumulated) in the reference parameter layout.
  *   dw[ko*dw_stride_k + ci*dw_stride_c + (r*S+s)] for ko < k_valid, ci < c_valid.

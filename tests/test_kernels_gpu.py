@@ -397,3 +397,48 @@ def test_dropout_mask_is_reproducible_and_fair():
     assert abs(m1.float().mean().item() - 0.5) < 5e-3
     ops.dropout_mask(m2, 1235)
     assert (m1 != m2).float().mean().item() > 0.4
+
+
+@pytest.mark.parametrize("case", [
+    # (n, h, w, c, k, r, stride, pad, halo, transposed)
+    (16, 64, 64, 256, 256, 3, 1, 0, 1, False),   # residual conv on the 2-CTA kernel
+    (2, 64, 64, 64, 128, 3, 2, 1, 0, False),     # stride-2 down conv, 1-CTA kernel
+    (3, 31, 31, 256, 512, 4, 1, 1, 0, False),    # PatchGAN model.8: ragged tiles, two n-blocks
+    (2, 32, 32, 256, 128, 3, 2, 1, 0, True),     # transposed conv: four parity-class launches share the partials
+])
+def test_conv_with_epilogue_statistics(case):
+    """{mean, rstd} per (image, channel) from the conv epilogue (no separate pass) vs torch on the stored output;
+    also in batch mode (BatchNorm statistics)."""
+    from fpgan import ops
+    n, h, w, c, k, r, stride, pad, halo, transposed = case
+    g = torch.Generator(device="cuda").manual_seed(21)
+    if transposed:
+        x = bf16r(torch.randn(n, c, h, w, device="cuda", generator=g))
+        wt = bf16r(torch.randn(c, k, r, r, device="cuda", generator=g) / (c * r * r) ** 0.5 * 2)
+        spec = ops.ConvSpec(r, r, stride, pad, ops.pad16(k), ops.pad16(c), c_in_valid=k, c_out_valid=c)
+        spec.pack(wt.contiguous())
+        xb = ops.ActBuf.from_nchw(x)
+        yb = ops.ActBuf(n, 2 * h, 2 * w, ops.pad16(k))
+    else:
+        x = bf16r(torch.randn(n, c, h, w, device="cuda", generator=g) + 0.2)
+        wt = bf16r(torch.randn(k, c, r, r, device="cuda", generator=g) / (c * r * r) ** 0.5)
+        spec = ops.ConvSpec(r, r, stride, pad, ops.pad16(c), ops.pad16(k), c_in_valid=c, c_out_valid=k)
+        spec.pack(wt.contiguous())
+        xb = ops.ActBuf.from_nchw(x, halo=halo)
+        hp, wp = h + 2 * halo, w + 2 * halo
+        yb = ops.ActBuf(n, (hp + 2 * pad - r) // stride + 1, (wp + 2 * pad - r) // stride + 1, ops.pad16(k))
+    for batch in (False, True):
+        stats = torch.zeros((1 if batch else n) * yb.c * 2, device="cuda")
+        assert ops.conv_with_stats(xb, spec, yb, stats, transposed=transposed, batch=batch)
+        y = yb.t.float()  # the stored (bf16-rounded) output [n, h, w, c]
+        dims = (0, 1, 2) if batch else (1, 2)
+        mean, var = y.mean(dims), y.var(dims, unbiased=False)
+        st = stats.view(-1, yb.c, 2)
+        torch.testing.assert_close(st[..., 0].reshape(mean.shape), mean, rtol=1e-3, atol=2e-4)
+        torch.testing.assert_close(st[..., 1].reshape(var.shape), (var + 1e-5).rsqrt(), rtol=1e-3, atol=1e-3)
+    ref = ops.ActBuf(yb.n, yb.h, yb.w, yb.c)
+    if transposed:
+        ops.conv_dgrad(xb, spec, ref)
+    else:
+        ops.conv_fprop(xb, spec, ref)
+    assert torch.equal(ref.t, yb.t), "the statistics epilogue must not change the convolution output"
