@@ -593,7 +593,14 @@ static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* 
     d->x_ntaps = 1;
     d->x_taps[0] = null_tap;
     make_act_view(dy, 1, 64, d->tile_w, d->tile_h, &d->x);
-    if (big_in) {
+    if (big_in && g->c_in == 64 && ntaps > 1 && getenv("FPG_DISABLE_WGRAD_TAP_ATOMS") == nullptr) {
+      // one 64-channel atom of input: a tap per item would stream dy once per tap for an N = 64 MMA (110 B/clk of
+      // operand traffic per SM, 54-cycle MMAs). Up to four taps become atoms of one N <= 256 tile instead.
+      d->y_ca = 64;
+      d->y_atoms = largest_divisor_le(ntaps, 4);
+      d->y_groups = ntaps / d->y_atoms;
+      d->y_taps_mode = 1;
+    } else if (big_in) {
       d->y_ca = 64;
       int ya = g->c_in / 64;
       if (ya > 4) ya = 4;

@@ -918,19 +918,30 @@ __device__ __forceinline__ void fold_extra(const View& dz, int i, int y, int x, 
 // once before the two streamed passes so that neither has to chase mirrored positions through global memory in the
 // middle of its shared-memory pipeline (that stalled the consumer warps ~1 us per chunk: every 64-pixel row has band
 // pixels).
-__global__ void halo_fold_inplace_kernel(View dz) {
+__global__ void halo_fold_inplace_kernel(View dz, int band_px) {
+  // threads enumerate the BAND pixels only (~6 % of the image): first the 2h band rows in full, then the 2h band
+  // columns of the remaining rows
   const int G = dz.c / 8;
-  const int64_t total = static_cast<int64_t>(dz.n) * dz.h * dz.w * G;
+  const int64_t total = static_cast<int64_t>(dz.n) * band_px * G;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int g = static_cast<int>(idx % G);
   int64_t r = idx / G;
-  const int x = static_cast<int>(r % dz.w);
-  r /= dz.w;
-  const int y = static_cast<int>(r % dz.h);
-  const int i = static_cast<int>(r / dz.h);
+  const int b = static_cast<int>(r % band_px);
+  const int i = static_cast<int>(r / band_px);
   const int h = dz.halo;
-  if (y > h && y < dz.h - 1 - h && x > h && x < dz.w - 1 - h) return;
+  int y, x;
+  if (b < 2 * h * dz.w) {  // band rows 1..h and H-1-h..H-2
+    const int br = b / dz.w;
+    x = b - br * dz.w;
+    y = br < h ? 1 + br : dz.h - 1 - h + (br - h);
+  } else {  // remaining rows, band columns 1..h and W-1-h..W-2
+    const int rest = b - 2 * h * dz.w;
+    const int rr = rest / (2 * h), bc = rest - rr * (2 * h);
+    // rows that are not band rows: 0, h+1 .. H-2-h, H-1
+    y = rr == 0 ? 0 : (rr <= dz.h - 2 - 2 * h ? h + rr : dz.h - 1);
+    x = bc < h ? 1 + bc : dz.w - 1 - h + (bc - h);
+  }
   float acc[8];
   __nv_bfloat16* p = static_cast<__nv_bfloat16*>(dz.p) + dz.at32(i, y, x) + g * 8;
   load8(p, acc);
@@ -1847,8 +1858,10 @@ int fpg_instnorm_bwd(const fpg_act* dz, const fpg_act* dz2, const fpg_act* y, co
     const RingGeom gm = ring_geom(y, stages, sms);
     const RingTensor t_dz = ring_tensor(dz), t_y = ring_tensor(y), t_dz2 = dz2 ? ring_tensor(dz2) : ring_tensor(y);
     if (dz->halo > 0) {  // fold the mirror band of dz in place first (dz is consumed by this call)
-      const int64_t total = static_cast<int64_t>(dz->n) * dz->h * dz->w * (dz->c / 8);
-      halo_fold_inplace_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(dz));
+      // band pixels: 2h full rows + 2h columns of the other H - 2h rows
+      const int band_px = 2 * dz->halo * dz->w + 2 * dz->halo * (dz->h - 2 * dz->halo);
+      const int64_t total = static_cast<int64_t>(dz->n) * band_px * (dz->c / 8);
+      halo_fold_inplace_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(dz), band_px);
     }
     in_bwd_reduce_ring_kernel<<<dim3(gm.ctas_per_img, y->n), kRingThreads, smem, FPG_ST(stream)>>>(
         view_of(dz), v2, dz2 != nullptr, view_of(y), stats, act, vr, dres != nullptr, scratch, red, counters, inv_hw,
