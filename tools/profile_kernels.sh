@@ -20,8 +20,8 @@ $NCU -k regex:igemm -s 17 -c 1 -o gpurun_out/r01_head_wgrad python tools/micro_c
 $NCU -k regex:igemm -s 3 -c 1 -o gpurun_out/r01_stem_fprop python tools/micro_conv.py $STEM fprop wgrad > /dev/null 2>&1
 $NCU -k regex:igemm -s 10 -c 1 -o gpurun_out/r01_stem_wgrad python tools/micro_conv.py $STEM fprop wgrad > /dev/null 2>&1
 # InstanceNorm kernels on the residual-trunk shape: micro_in runs 10 repetitions of stats, apply, bwd(dz2+dres), bwd
-$NCU -k regex:"in_stats|in_apply_kernel" -s 3 -c 1 -o gpurun_out/r01_in_stats python tools/micro_in.py > /dev/null 2>&1
-$NCU -k regex:"in_apply_kernel" -s 3 -c 1 -o gpurun_out/r01_in_apply python tools/micro_in.py > /dev/null 2>&1
+$NCU -k regex:"in_stats" -s 3 -c 1 -o gpurun_out/r01_in_stats python tools/micro_in.py > /dev/null 2>&1
+$NCU -k regex:"in_apply" -s 3 -c 1 -o gpurun_out/r01_in_apply python tools/micro_in.py > /dev/null 2>&1
 $NCU -k regex:"in_bwd_reduce" -s 3 -c 1 -o gpurun_out/r01_in_bwd_reduce python tools/micro_in.py > /dev/null 2>&1
 $NCU -k regex:"in_bwd_apply" -s 3 -c 1 -o gpurun_out/r01_in_bwd_apply python tools/micro_in.py > /dev/null 2>&1
 ls -la gpurun_out/r01_*.ncu-rep
