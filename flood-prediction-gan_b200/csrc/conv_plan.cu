@@ -582,6 +582,29 @@ static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* 
     y_extra = g->s - 1;
     make_act_view(x, 1, 64, 64, 1, &d->x);
     make_act_view(dy, 1, d->y_ca, 64 + y_extra, 1, &d->y);
+  } else if (big_out && big_in && g->c_out == 256 && g->c_in == 256 && ntaps >= 2 && sms >= 2 * ((ntaps + 1) / 2) &&
+             getenv("FPG_DISABLE_WGRAD_PAIR") == nullptr) {
+    // 256 x 256-channel layers (residual convs): CTA pairs, an item = two taps (igemm_wgrad2_kernel)
+    d->cta_pair = 1;
+    d->x_is_dy = 1;
+    d->x_ca = 64;
+    d->x_atoms = 4;
+    d->x_groups = 1;
+    d->x_taps_mode = 0;
+    d->x_ntaps = 1;
+    d->x_taps[0] = null_tap;
+    d->y_ca = 64;
+    d->y_atoms = 4;
+    d->y_groups = 1;
+    d->y_taps_mode = 0;
+    d->y_sets = 2;
+    d->y_ntaps = ntaps;
+    for (int t = 0; t < ntaps; ++t) {
+      d->y_taps[t] = in_taps[t];
+      d->y_tap_rs[t] = static_cast<int16_t>(t);
+    }
+    make_act_view(dy, 1, 64, d->tile_w, d->tile_h, &d->x);
+    make_act_view(x, g->stride, 64, d->tile_w, d->tile_h, &d->y);
   } else if (big_out) {
     // X = dy (rows = output channels)
     d->x_is_dy = 1;
@@ -679,6 +702,33 @@ static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* 
   if (splits > total_kt) splits = total_kt;
   if (splits > 160) splits = 160;
   d->splits = splits;
+  if (d->cta_pair) {
+    // (ntaps / 2) tap pairs of `splits` clusters each + (odd tap count) the last tap alone with `last_splits` clusters.
+    // Measured per k-tile: 1100 clk for a tap pair (8 MMAs of 128 clk), ~650 clk for the single tap (load bound), so
+    // the split counts minimise the longer of the two cluster kinds over the sms / 2 co-resident clusters.
+    const int clusters = sms / 2, pairs = ntaps / 2;
+    int best_sp = 1, best_last = 1;
+    int64_t best_cost = INT64_MAX;
+    for (int sp = 1; sp <= clusters && sp <= total_kt; ++sp) {
+      int last = (ntaps & 1) ? clusters - pairs * sp : 0;
+      if ((ntaps & 1) && last < 1) break;
+      if (pairs * sp > clusters) break;
+      if (last > total_kt) last = total_kt;
+      if (last > sp) last = sp;  // workspace slots are [splits][items]
+      const int64_t c2 = static_cast<int64_t>(ceil_div(total_kt, sp)) * 1100;
+      const int64_t c1 = (ntaps & 1) ? static_cast<int64_t>(ceil_div(total_kt, last)) * 650 : 0;
+      const int64_t cost = c2 > c1 ? c2 : c1;
+      if (cost < best_cost) {
+        best_cost = cost;
+        best_sp = sp;
+        best_last = last;
+      }
+    }
+    d->splits = best_sp;
+    d->last_splits = (ntaps & 1) ? best_last : 0;
+    d->stages = 4;
+    return 0;
+  }
   const int M = d->x_atoms * d->x_ca;
   const int x_stage = d->x_shift_atoms ? ((64 + d->x_atoms - 1) * d->x_ca * 2 + 1023) / 1024 * 1024 : M * 128;
   const int y_px = 64 + (d->y_shift_atoms ? d->y_atoms - 1 : 0) + (d->y_shifts - 1);
@@ -693,6 +743,7 @@ static int wgrad_items_y(const fpg_igemm_wgrad_desc* d) {
 }
 
 static int64_t wgrad_ws_floats(const fpg_igemm_wgrad_desc* d) {
+  if (d->cta_pair) return static_cast<int64_t>(d->splits) * ((d->y_ntaps + 1) / 2) * 256 * 512;
   const int NX = d->x_taps_mode ? d->x_groups : d->x_groups * d->x_ntaps;
   const int NY = wgrad_items_y(d);
   return static_cast<int64_t>(d->splits) * NX * NY * (d->x_atoms * d->x_ca) * (d->y_atoms * d->y_ca) *
@@ -703,28 +754,35 @@ static int64_t wgrad_ws_floats(const fpg_igemm_wgrad_desc* d) {
 struct ReduceArgs {
   int32_t x_ca, x_atoms, x_groups, x_taps_mode, x_ntaps;
   int32_t y_ca, y_atoms, y_groups, y_taps_mode, y_ntaps;
-  int32_t splits, x_is_dy, y_shifts, y_sets, taps_total;
+  int32_t splits, x_is_dy, y_shifts, y_sets, taps_total, pair, last_splits;
   int64_t stride_k, stride_c;
   int32_t k_valid, c_valid;
   int16_t x_tap_rs[FPG_MAX_TAPS];
   int16_t y_tap_rs[FPG_MAX_TAPS];
 };
 
-// one thread per (item, m, shift group, n): sum the split partials and scatter into the parameter-layout gradient
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, const ReduceArgs a) {
+// One thread per 4 consecutive workspace floats (same item, row, tap; 4 consecutive channels of the Y operand): sums the
+// split partials with 16-byte loads in a fixed order and scatters into the parameter-layout gradient.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, const ReduceArgs a) {
   const int M = a.x_atoms * a.x_ca, N = a.y_atoms * a.y_ca;
   const int NT = a.y_shifts * a.y_sets * N;
   const int NX = a.x_taps_mode ? a.x_groups : a.x_groups * a.x_ntaps;
-  const int NY = a.y_taps_mode ? (a.y_groups + a.y_sets - 1) / a.y_sets : a.y_groups * a.y_ntaps;
-  const int64_t items = static_cast<int64_t>(NX) * NY;
-  const int64_t per_split = items * M * NT;
-  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= per_split) return;
-  const int nt = static_cast<int>(idx % NT);
+  const int NY = a.pair ? (a.y_ntaps + 1) / 2
+                        : (a.y_taps_mode ? (a.y_groups + a.y_sets - 1) / a.y_sets : a.y_groups * a.y_ntaps);
+  const int per_split4 = NX * NY * M * (NT >> 2);  // float4 per split (a few million at most)
+  const int idx4 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx4 >= per_split4) return;
+  // accumulator-native workspace order of an item: [row block of RB rows][16-column chunk][4][RB][4] floats
+  const int item4 = M * (NT >> 2);
+  const int item = idx4 / item4;
+  const int rem = idx4 - item * item4;
+  const int RB = M >= 128 ? 32 : 16;
+  const int lane = rem % RB, i4 = (rem / RB) & 3, blk = rem / (RB * 4);
+  const int nt = (blk % (NT >> 4)) * 16 + i4 * 4;
+  const int m = (blk / (NT >> 4)) * RB + lane;
   const int grp = nt / N, n = nt % N;  // MMA group: pixel shift (y_shifts) or tap set (y_sets)
-  const int shift = a.y_sets > 1 ? 0 : grp;
-  const int m = static_cast<int>((idx / NT) % M);
-  const int item = static_cast<int>(idx / (static_cast<int64_t>(M) * NT));
+  const int shift = a.y_sets > 1 ? 0 : grp;  // tap sets carry their taps in the table, shift groups add to the id
   const int xi = item / NY, yi = item % NY;
   int xtap, xch, ytap, ych;
   {
@@ -738,23 +796,40 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restr
     }
   }
   {
-    const int atom = n / a.y_ca, within = n % a.y_ca;
+    const int atom = n / a.y_ca, within = n % a.y_ca;  // the 4 floats share the atom (y_ca >= 16)
     if (a.y_taps_mode) {
       ytap = (yi * a.y_sets + (a.y_sets > 1 ? grp : 0)) * a.y_atoms + atom;
       ych = within;
+    } else if (a.pair) {  // item = tap pair, group = tap inside the pair, atoms = channel chunks
+      ytap = yi * 2 + grp;
+      ych = atom * a.y_ca + within;
     } else {
       ytap = yi / a.y_groups;
       ych = ((yi % a.y_groups) * a.y_atoms + atom) * a.y_ca + within;
     }
   }
   if (xtap >= a.x_ntaps || ytap >= a.y_ntaps) return;  // dummy atoms of a ragged last group
-  const int k = a.x_is_dy ? xch : ych, c = a.x_is_dy ? ych : xch;
   const int tap = a.x_tap_rs[xtap] + a.y_tap_rs[ytap] + shift;
   if (tap < 0 || tap >= a.taps_total) return;
-  if (k >= a.k_valid || c >= a.c_valid) return;
-  float acc = 0.f;
-  for (int s = 0; s < a.splits; ++s) acc += ws[s * per_split + idx];
-  dw[k * a.stride_k + c * a.stride_c + tap] = acc;
+  const int x_valid = a.x_is_dy ? a.k_valid : a.c_valid, y_valid = a.x_is_dy ? a.c_valid : a.k_valid;
+  if (xch >= x_valid || ych >= y_valid) return;
+  const float4* p = reinterpret_cast<const float4*>(ws) + idx4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int splits = (a.pair && (a.y_ntaps & 1) && yi == NY - 1) ? a.last_splits : a.splits;
+#pragma unroll 8
+  for (int s = 0; s < splits; ++s) {  // loads batched by the unroll, summation order fixed
+    const float4 v = __ldcg(p + static_cast<int64_t>(s) * per_split4);
+    acc.x += v.x;
+    acc.y += v.y;
+    acc.z += v.z;
+    acc.w += v.w;
+  }
+  const int64_t x_stride = a.x_is_dy ? a.stride_k : a.stride_c, y_stride = a.x_is_dy ? a.stride_c : a.stride_k;
+  float* out = dw + xch * x_stride + ych * y_stride + tap;
+  const float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    if (ych + e < y_valid) out[e * y_stride] = r[e];
 }
 
 struct PackArgs {
@@ -1049,6 +1124,8 @@ int fpg_conv2d_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g
   a.x_is_dy = d.x_is_dy;
   a.y_shifts = d.y_shifts > 1 ? d.y_shifts : 1;
   a.y_sets = d.y_sets > 1 ? d.y_sets : 1;
+  a.pair = d.cta_pair ? 1 : 0;
+  a.last_splits = d.last_splits;
   a.taps_total = d.taps_r * d.taps_s;
   a.stride_k = dw_stride_k;
   a.stride_c = dw_stride_c;
@@ -1058,9 +1135,9 @@ int fpg_conv2d_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g
     a.x_tap_rs[i] = d.x_tap_rs[i];
     a.y_tap_rs[i] = d.y_tap_rs[i];
   }
-  const int64_t per_split = wgrad_ws_floats(&d) / d.splits;
+  const int64_t per_split4 = wgrad_ws_floats(&d) / d.splits / 4;
   const int threads = 256;
-  const int64_t blocks = (per_split + threads - 1) / threads;
+  const int64_t blocks = (per_split4 + threads - 1) / threads;
   wgrad_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(ws, dw, a);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;

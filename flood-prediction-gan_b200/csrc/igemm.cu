@@ -13,6 +13,29 @@ namespace fpg {
 constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
 
+// Phase stamps of the wgrad kernels (diagnostic build: make EXTRA=-DFPG_WGRAD_TRACE): cycles from kernel entry to the
+// end of setup, the accumulators complete, and the partials stored; printed for a few CTAs.
+#ifdef FPG_WGRAD_TRACE
+#define FPG_TRACE_DECL __shared__ long long trace_t[5];
+#define FPG_TRACE_MARK(i)                                                           \
+  if (threadIdx.x == 64) {                                                          \
+    trace_t[i] = clock64();                                                         \
+    if (i == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_t[4]));      \
+  }
+#define FPG_TRACE_PRINT(name)                                                                                       \
+  if (threadIdx.x == 64) {                                                                                          \
+    long long t_end;                                                                                                \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));                                                       \
+    printf(name " cta %d: setup %lld  mainloop %lld  epilogue %lld clk  start %lld end %lld ns\n",                  \
+           static_cast<int>(blockIdx.x), trace_t[1] - trace_t[0], trace_t[2] - trace_t[1], trace_t[3] - trace_t[2], \
+           trace_t[4] % 100000000ll, t_end % 100000000ll);                                                          \
+  }
+#else
+#define FPG_TRACE_DECL
+#define FPG_TRACE_MARK(i)
+#define FPG_TRACE_PRINT(name)
+#endif
+
 // InstanceNorm / BatchNorm statistics from the epilogue: per (tile row-quarter, column) partial {sum, sum of squares} of
 // the bf16-rounded values that are stored (a later tiny kernel reduces the rows of an image in a fixed order). Saves
 // the separate pass that re-reads the whole activation.
@@ -603,6 +626,8 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  FPG_TRACE_DECL
+  FPG_TRACE_MARK(0)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -621,6 +646,7 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  FPG_TRACE_MARK(1)
 
   // work decomposition: blockIdx.x = (split, xi, yi)
   const int NX = args.x_taps_mode ? args.x_groups : args.x_groups * args.x_ntaps;
@@ -766,9 +792,14 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
       mbar_wait(tfull, 0);
       tc_fence_after();
     }
+    FPG_TRACE_MARK(2)
+    // Workspace layout (decoded by wgrad_reduce_kernel): an item is [row block of RB rows][16-column chunk][4][RB][4]
+    // floats, so one store instruction of a warp writes RB x 16 contiguous bytes (row-major rows of NT floats made
+    // every lane hit its own 128-byte line: 8x the L2 write requests for the same bytes).
+    const int RB = (M >= 128) ? 32 : 16;
+    float* item_ws = args.ws + (static_cast<int64_t>(split) * items + item) * M * NT;
     for (int ms = 0; ms < msub; ++ms) {
-      const int row = (M >= 128) ? ms * 128 + q * 32 + lane : q * 16 + lane;
-      float* dst = args.ws + (static_cast<int64_t>(split) * items + item) * M * NT + static_cast<int64_t>(row) * NT;
+      const int rowblk = (M >= 128) ? ms * 4 + q : q;
       for (int g = 0; g < YS; ++g) {
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (g * msub + ms) * N;
         for (int c = 0; c < N; c += 16) {
@@ -781,20 +812,204 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             for (int i = 0; i < 16; ++i) v[i] = 0u;
           }
           if (row_valid) {
-            float4* d4 = reinterpret_cast<float4*>(dst + g * N + c);
+            float4* d4 = reinterpret_cast<float4*>(item_ws + (static_cast<int64_t>(rowblk) * (NT >> 4) + ((g * N + c) >> 4)) * (RB * 16)) + lane;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              d4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
-                                  __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+              d4[i * RB] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                       __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
           }
         }
       }
     }
+    FPG_TRACE_MARK(3)
+    FPG_TRACE_PRINT("wgrad")
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ 2-CTA wgrad
+// Weight gradient of the wide layers (c_out = 256, c_in = 256: the residual 3x3 convs) on a CTA PAIR with
+// tcgen05.mma.cta_group::2. Pair tile: D[256 output channels, 2 taps x 256 input channels]. CTA r loads only ITS half of
+// both operands -- dy channels [128 r, +128) (the M rows it owns) and input channels [128 r, +128) of both taps (its
+// half of every N = 256 MMA) -- so a stage is 48 KB per SM for 8 MMAs of 128 cycles: 47 B/clk of L2->SM traffic
+// instead of 62 (the 1-CTA M = 256 / N = 256 plan is L2-bound at 0.67 tensor-active) and 8 KB of shared-memory operand
+// reads per MMA instead of 12. Each CTA's TMEM holds its 128 rows x (2 x 256) fp32 columns: all 512 columns, one use.
+// Barrier protocol as in igemm_fprop2_kernel (leader = cluster rank 0 issues, commits are multicast to both CTAs).
+struct Wgrad2Args {
+  int32_t n_img, kt_y, kt_x, tile_h, tile_w;
+  int32_t splits, last_splits, stages, ntaps, items;
+  float* ws;
+  fpg_tap y_taps[FPG_MAX_TAPS];
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+igemm_wgrad2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap ymap,
+                    const __grid_constant__ Wgrad2Args args) {
+  constexpr uint32_t ATOM = 8192;              // 64 pixel rows x 64 channels bf16
+  constexpr uint32_t X_STAGE = 2 * ATOM;       // this CTA's 128 dy channels
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // clusters [0, pairs * splits): (tap pair, split); with an odd tap count the last tap is an item of its own with
+  // last_splits splits. Its stage holds one tap (32 KB instead of 48), so the same ring memory gives it 1.5x the stages:
+  // a single-tap k-tile is only 4 MMAs (512 clk) and needs the deeper look-ahead to cover the L2 latency.
+  const int cluster = blockIdx.x >> 1;
+  const int pairs = args.ntaps >> 1;
+  const bool single = cluster >= pairs * args.splits;
+  const int nt = single ? 1 : 2;  // taps of this item
+  const uint32_t Y_STAGE = static_cast<uint32_t>(nt) * 2u * ATOM;
+  const int STAGES = single ? args.stages * 3 / 2 : args.stages;
+  uint8_t* smem_x = smem;
+  uint8_t* smem_y = smem + STAGES * X_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + args.stages * (X_STAGE + 4 * ATOM));
+  uint64_t* empty = full + 8;
+  uint64_t* tfull = empty + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  FPG_TRACE_DECL
+  FPG_TRACE_MARK(0)
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 2);   // leader's copy: its own arrive.expect_tx + the peer's remote arrive
+      mbar_init(&empty[i], 1);  // one multicast commit per use
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&xmap);
+    tma_prefetch_desc(&ymap);
+  }
+  cluster_sync_all();
+  if (warp == 1) tmem_alloc_2cta(tmem_slot, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  FPG_TRACE_MARK(1)
+
+  const int item = single ? pairs : cluster % pairs;
+  const int split = single ? cluster - pairs * args.splits : cluster / pairs;
+  const int my_splits = single ? args.last_splits : args.splits;
+  const int total_kt = args.n_img * args.kt_y * args.kt_x;
+  const int kt_begin = static_cast<int>(static_cast<int64_t>(total_kt) * split / my_splits);
+  const int kt_end = static_cast<int>(static_cast<int64_t>(total_kt) * (split + 1) / my_splits);
+
+  if (warp == 0) {
+    if (elect_one()) {
+      fpg_tap tp[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) tp[j] = args.y_taps[item * 2 + j < args.ntaps ? item * 2 + j : 0];
+      const uint32_t stage_tx = 2u * (X_STAGE + Y_STAGE);  // both CTAs' bytes
+      const int c0 = static_cast<int>(rank) * 128;
+      uint32_t stage = 0, phase = 0;
+      int kx = kt_begin % args.kt_x;
+      int ky = (kt_begin / args.kt_x) % args.kt_y;
+      int n = kt_begin / (args.kt_x * args.kt_y);
+      for (int kt = kt_begin; kt < kt_end; ++kt) {
+        const int x0 = kx * args.tile_w, y0 = ky * args.tile_h;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (leader) {
+          mbar_arrive_expect_tx(&full[stage], stage_tx);
+        } else {
+          mbar_arrive_cluster(&full[stage], 0);
+        }
+        uint8_t* x_dst = smem_x + stage * X_STAGE;
+        uint8_t* y_dst = smem_y + stage * Y_STAGE;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) tma_load_5d_2sm(&xmap, &full[stage], x_dst + a * ATOM, c0 + a * 64, x0, 0, y0, n);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (j < nt) {
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+              tma_load_5d_2sm(&ymap, &full[stage], y_dst + (j * 2 + a) * ATOM, tp[j].c0 + c0 + a * 64, x0 + tp[j].dx,
+                              tp[j].plane, y0 + tp[j].dy, n);
+          }
+        if (++stage == static_cast<uint32_t>(STAGES)) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++kx == args.kt_x) {
+          kx = 0;
+          if (++ky == args.kt_y) {
+            ky = 0;
+            ++n;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(256, 256, 1, 1);
+      const uint64_t hi = make_smem_desc(0, ATOM, 1024, 2);  // MN-major, 128B swizzle, atom stride 8 KB, 8-row groups
+      uint32_t stage = 0, phase = 0, acc = 0;
+      for (int kt = kt_begin; kt < kt_end; ++kt) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t x_lo = (smem_u32(smem_x + stage * X_STAGE) >> 4) & 0x3FFFu;
+        const uint32_t y_lo = (smem_u32(smem_y + stage * Y_STAGE) >> 4) & 0x3FFFu;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t xd = hi | static_cast<uint64_t>(x_lo + k * 128);  // 16 pixel rows = 2 KB = 128 x 16 B
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            if (j < nt) {
+              const uint64_t yd = hi | static_cast<uint64_t>(y_lo + j * (2 * ATOM >> 4) + k * 128);
+              umma_bf16_2cta(tmem_base + j * 256, xd, yd, idesc, k == 0 ? acc : 1u);
+            }
+          }
+        }
+        acc = 1u;
+        umma_commit_2cta(&empty[stage], 3);
+        if (++stage == static_cast<uint32_t>(STAGES)) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit_2cta(tfull, 3);
+    }
+  } else {
+    // each CTA drains its own 128 rows (output channels 128 r + ...) x 512 columns = (tap j, input channel)
+    const int q = warp & 3;
+    if (kt_end > kt_begin) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+    }
+    FPG_TRACE_MARK(2)
+    // workspace layout as in igemm_wgrad_kernel: [row block of 32][16-column chunk][4][32 lanes][4] floats
+    const int rowblk = static_cast<int>(rank) * 4 + q;
+    float* item_ws = args.ws + (static_cast<int64_t>(split) * args.items + item) * 256 * 512;
+    const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int c = 0; c < nt * 256; c += 16) {
+      uint32_t v[16];
+      if (kt_end > kt_begin) {
+        tmem_ld16(t_addr + c, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = 0u;
+      }
+      float4* d4 = reinterpret_cast<float4*>(item_ws + (static_cast<int64_t>(rowblk) * 32 + (c >> 4)) * 512) + lane;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        d4[i * 32] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                 __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+    }
+    FPG_TRACE_MARK(3)
+    FPG_TRACE_PRINT("wgrad2")
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, kTmemCols);
 }
 
 static int log2_exact(int v) {
@@ -909,8 +1124,45 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
   return 0;
 }
 
+static int launch_wgrad_pair(const fpg_igemm_wgrad_desc* d, void* stream) {
+  FPG_REQUIRE(d->x_ca == 64 && d->y_ca == 64 && d->x_atoms == 4 && d->y_atoms == 4 && d->x_groups == 1 &&
+                  d->y_groups == 1 && d->y_sets == 2 && !d->x_taps_mode && !d->y_taps_mode && d->x_is_dy &&
+                  !d->x_shift_atoms && !d->y_shift_atoms && d->y_shifts <= 1,
+              "cta_pair wgrad: 256 x 256 channels, two taps per item");
+  FPG_REQUIRE(d->tile_h * d->tile_w == 64 && d->ws != nullptr && d->splits >= 1 && d->stages >= 2 && d->stages <= 4 &&
+                  (!(d->y_ntaps & 1) || (d->last_splits >= 1 && d->last_splits <= d->splits)),
+              "cta_pair wgrad geometry");
+  CUtensorMap xmap, ymap;
+  int rc = encode_tmap(&d->x, &xmap);
+  if (rc) return rc;
+  rc = encode_tmap(&d->y, &ymap);
+  if (rc) return rc;
+  Wgrad2Args args;
+  args.n_img = d->n_img;
+  args.kt_y = d->kt_y;
+  args.kt_x = d->kt_x;
+  args.tile_h = d->tile_h;
+  args.tile_w = d->tile_w;
+  args.splits = d->splits;
+  args.last_splits = d->last_splits;
+  args.stages = d->stages;
+  args.ntaps = d->y_ntaps;
+  args.items = (d->y_ntaps + 1) / 2;
+  const int clusters = (d->y_ntaps / 2) * d->splits + (d->y_ntaps & 1) * args.last_splits;
+  args.ws = d->ws;
+  for (int i = 0; i < FPG_MAX_TAPS; ++i) args.y_taps[i] = d->y_taps[i];
+  const size_t smem = static_cast<size_t>(d->stages) * 6 * 8192 + (2 * 8 + 2) * 8 + 16 + 1024;
+  FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  igemm_wgrad2_kernel<<<2 * clusters, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(xmap, ymap,
+                                                                                                       args);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int fpg_igemm_wgrad_launch(const fpg_igemm_wgrad_desc* d, void* stream) {
   FPG_REQUIRE(d != nullptr, "null descriptor");
+  if (d->cta_pair) return launch_wgrad_pair(d, stream);
   const int M = d->x_atoms * d->x_ca, N = d->y_atoms * d->y_ca;
   const int ysh = d->y_shifts > 1 ? d->y_shifts : 1, ysets = d->y_sets > 1 ? d->y_sets : 1;
   const int ys = ysh * ysets;

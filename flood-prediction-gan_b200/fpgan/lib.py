@@ -60,7 +60,7 @@ class WgradDesc(C.Structure):
                 ("tile_h", C.c_int32), ("tile_w", C.c_int32), ("splits", C.c_int32), ("stages", C.c_int32),
                 ("x_is_dy", C.c_int32), ("tap_on_x", C.c_int32), ("taps_r", C.c_int32), ("taps_s", C.c_int32),
                 ("x_shift_atoms", C.c_int32), ("y_shift_atoms", C.c_int32), ("y_shifts", C.c_int32), ("y_sets", C.c_int32),
-                ("ws", C.c_void_p),
+                ("cta_pair", C.c_int32), ("last_splits", C.c_int32), ("ws", C.c_void_p),
                 ("x_taps", Tap * FPG_MAX_TAPS), ("y_taps", Tap * FPG_MAX_TAPS),
                 ("x_tap_rs", C.c_int16 * FPG_MAX_TAPS), ("y_tap_rs", C.c_int16 * FPG_MAX_TAPS)]
 

@@ -129,6 +129,9 @@ typedef struct {
   int32_t tap_on_x; /* informational: 1 if the filter taps are enumerated by the X operand only */
   int32_t taps_r, taps_s; /* filter size: tap ids >= taps_r*taps_s (or < 0) are padding and are dropped */
   int32_t x_shift_atoms, y_shift_atoms, y_shifts, y_sets;
+  int32_t cta_pair; /* 1: 2-CTA kernel for 256 x 256-channel layers: an item is a pair of taps (y_sets == 2, the sets
+                       enumerate taps, the 4 atoms channels), CTA r of the pair loads its half of both operands */
+  int32_t last_splits; /* cta_pair with an odd tap count: k-range splits of the last, single-tap item (<= splits) */
   float* ws;
   fpg_tap x_taps[FPG_MAX_TAPS];
   fpg_tap y_taps[FPG_MAX_TAPS];

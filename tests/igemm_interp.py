@@ -145,6 +145,8 @@ def run_wgrad(desc, xbuf, ybuf, dw, stride_k, stride_c, k_valid, c_valid):
     """Interpret an fpg_igemm_wgrad_desc including shifted operands (shift atoms / shift groups), the split
     reduction and the scatter into dw (flat fp array)."""
     assert desc.tile_h * desc.tile_w == 64
+    if desc.cta_pair:
+        return _run_wgrad_pair(desc, xbuf, ybuf, dw, stride_k, stride_c, k_valid, c_valid)
     M, N = desc.x_atoms * desc.x_ca, desc.y_atoms * desc.y_ca
     YSH, SETS = max(desc.y_shifts, 1), max(desc.y_sets, 1)
     YS = YSH * SETS  # MMA groups per stage, each with its own accumulator columns
@@ -235,3 +237,37 @@ def run_wgrad(desc, xbuf, ybuf, dw, stride_k, stride_c, k_valid, c_valid):
                         if tap < 0 or tap >= taps_total or k >= k_valid or c >= c_valid:
                             continue
                         dw[k * stride_k + c * stride_c + tap] = acc[g, m, nn]
+
+
+def _run_wgrad_pair(desc, xbuf, ybuf, dw, stride_k, stride_c, k_valid, c_valid):
+    """2-CTA wgrad (igemm_wgrad2_kernel): an item is a pair of taps; CTA r of the pair loads dy channels
+    [128 r, +128) and input channels [128 r, +128) of both taps; D[256, 2 x 256]."""
+    assert desc.x_is_dy and desc.x_ca == 64 and desc.y_ca == 64 and desc.x_atoms == 4 and desc.y_atoms == 4
+    assert desc.y_sets == 2 and not desc.x_taps_mode and not desc.y_taps_mode and desc.stages <= 4
+    assert int(desc.x.box[0]) == 64 and int(desc.x.box[1]) * int(desc.x.box[3]) == 64
+    total_kt = desc.n_img * desc.kt_y * desc.kt_x
+    for item in range((desc.y_ntaps + 1) // 2):
+        acc = np.zeros((2, 256, 256), dtype=np.float64)
+        for kt in range(total_kt):
+            kx = kt % desc.kt_x
+            r = kt // desc.kt_x
+            ky = r % desc.kt_y
+            n = r // desc.kt_y
+            x0, y0 = kx * desc.tile_w, ky * desc.tile_h
+            xt = np.concatenate([_tmap_gather(desc.x, xbuf, [rank * 128 + a * 64, x0, 0, y0, n]).reshape(64, 64)
+                                 for rank in range(2) for a in range(2)], axis=1)
+            for j in range(2):
+                tap = item * 2 + j
+                t = desc.y_taps[tap if tap < desc.y_ntaps else 0]
+                yt = np.concatenate([_tmap_gather(desc.y, ybuf, [t.c0 + rank * 128 + a * 64, x0 + t.dx, t.plane,
+                                                                 y0 + t.dy, n]).reshape(64, 64)
+                                     for rank in range(2) for a in range(2)], axis=1)
+                acc[j] += xt.astype(np.float64).T @ yt.astype(np.float64)
+        for j in range(2):
+            tap = item * 2 + j
+            if tap >= desc.y_ntaps:
+                continue
+            tid = desc.y_tap_rs[tap]
+            for k in range(min(256, k_valid)):
+                for c in range(min(256, c_valid)):
+                    dw[k * stride_k + c * stride_c + tid] = acc[j, k, c]

@@ -194,10 +194,28 @@ WGRAD_CASES = [
 ]
 
 
+@pytest.mark.parametrize("case", [(2, 16, 16, 256, 256, 256, 256, 3, 1, 0, 1),  # residual conv of the 256x256 step
+                                  (1, 8, 8, 256, 256, 256, 256, 2, 1, 0, 0)])    # even tap count
+def test_wgrad_pair_plan_matches_autograd(fpglib, case, monkeypatch):
+    """256 x 256-channel layers plan the CTA-pair kernel (an item = two taps, D[256, 2 x 256])."""
+    monkeypatch.delenv("FPG_WGRAD_SHIFT_WIDE", raising=False)
+    d = _check_wgrad_plan(fpglib, case)
+    assert d.cta_pair == 1 and d.y_sets == 2 and d.stages <= 4
+    monkeypatch.setenv("FPG_DISABLE_WGRAD_PAIR", "1")
+    assert _check_wgrad_plan(fpglib, case, run=False).cta_pair == 0
+
+
 @pytest.mark.parametrize("case", WGRAD_CASES)
 def test_wgrad_plan_matches_autograd(fpglib, case, monkeypatch):
-    n, h, w, c, cp, k, kp, r, stride, pad, halo = case
     monkeypatch.setenv("FPG_WGRAD_SHIFT_WIDE", "1")  # also cover the opt-in shift-group plan of the wide layers
+    n, h, w, c, cp, k, kp, r, stride, pad, halo = case
+    d = _check_wgrad_plan(fpglib, case)
+    if w >= 58 and stride == 1 and r > 1:
+        assert d.y_shift_atoms or d.y_shifts > 1, "wide stride-1 layers must plan shifted operands"
+
+
+def _check_wgrad_plan(fpglib, case, run=True):
+    n, h, w, c, cp, k, kp, r, stride, pad, halo = case
     torch.manual_seed(3)
     x = torch.randn(n, c, h, w, dtype=torch.float64)
     xin = F.pad(x, (halo,) * 4, "reflect") if halo else x
@@ -212,8 +230,8 @@ def test_wgrad_plan_matches_autograd(fpglib, case, monkeypatch):
     d = L.WgradDesc()
     L.call("fpg_conv2d_wgrad_plan", C.byref(xa), C.byref(dya), C.byref(g), SMS, C.byref(d))
     assert fpglib.fpg_conv2d_wgrad_ws_bytes(C.byref(xa), C.byref(dya), C.byref(g), SMS) > 0
-    if w >= 58 and stride == 1 and r > 1:
-        assert d.y_shift_atoms or d.y_shifts > 1, "wide stride-1 layers must plan shifted operands"
+    if not run:
+        return d
     dw = np.full(k * c * r * r, np.nan)
     xb, yb = nhwc_buffer(x, cp, halo), nhwc_buffer(dy, kp)
     if d.x_is_dy:
@@ -222,6 +240,7 @@ def test_wgrad_plan_matches_autograd(fpglib, case, monkeypatch):
         interp.run_wgrad(d, xb, yb, dw, c * r * r, r * r, k, c)
     assert not np.isnan(dw).any()
     torch.testing.assert_close(torch.from_numpy(dw).reshape(k, c, r, r), ref, rtol=1e-9, atol=1e-9)
+    return d
 
 
 def test_library_exports_every_declared_symbol(fpglib):
