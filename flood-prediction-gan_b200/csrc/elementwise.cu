@@ -816,20 +816,26 @@ struct RingGeom {
 
 // Runs the ring for chunks [c_begin, c_end) of image i. body(ptrs, row, x0, npx) is called by the 256 consumer threads
 // with ptrs[t] = shared-memory address of operand t's chunk; every consumer warp must call it (it may not return early).
+// reverse: walk the chunks from c_end - 1 down to c_begin. The second pass of a two-pass operator reads what the first
+// pass touched LAST first, while it is still in the 126 MB L2 (a forward re-scan of a >100 MB footprint evicts every line
+// just before it is needed).
 template <int NT, typename Body>
 __device__ __forceinline__ void ring_run(const RingTensor (&ts)[NT], const bool (&on)[NT], const RingGeom& gm, int i,
                                          int c_begin, int c_end, uint8_t* ring, uint64_t* full, uint64_t* empty,
-                                         Body body) {
+                                         Body body, bool reverse = false) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int stage_bytes = NT * kRingStageBytes;
+  const int k0 = reverse ? c_end - 1 : c_begin;
+  const int row0 = k0 / gm.segs, seg0 = k0 - row0 * gm.segs;
+  const int n_chunks = c_end - c_begin;
   if (warp == 8) {
     if (lane == 0) {
       int n_on = 0;
 #pragma unroll
       for (int t = 0; t < NT; ++t) n_on += on[t] ? 1 : 0;
       int st = 0, ph = 0;
-      int row = c_begin / gm.segs, seg = c_begin - row * gm.segs;
-      for (int k = c_begin; k < c_end; ++k) {
+      int row = row0, seg = seg0;
+      for (int k = 0; k < n_chunks; ++k) {
         const int x0 = seg * gm.sp;
         const int npx = min(gm.sp, gm.w - x0);
         const uint32_t bytes = static_cast<uint32_t>(npx) * gm.pix_bytes;
@@ -846,7 +852,12 @@ __device__ __forceinline__ void ring_run(const RingTensor (&ts)[NT], const bool 
           st = 0;
           ph ^= 1;
         }
-        if (++seg == gm.segs) {
+        if (reverse) {
+          if (--seg < 0) {
+            seg = gm.segs - 1;
+            --row;
+          }
+        } else if (++seg == gm.segs) {
           seg = 0;
           ++row;
         }
@@ -854,8 +865,8 @@ __device__ __forceinline__ void ring_run(const RingTensor (&ts)[NT], const bool 
     }
   } else {
     int st = 0, ph = 0;
-    int row = c_begin / gm.segs, seg = c_begin - row * gm.segs;
-    for (int k = c_begin; k < c_end; ++k) {
+    int row = row0, seg = seg0;
+    for (int k = 0; k < n_chunks; ++k) {
       const int x0 = seg * gm.sp;
       const int npx = min(gm.sp, gm.w - x0);
       mbar_wait(&full[st], ph);
@@ -869,7 +880,12 @@ __device__ __forceinline__ void ring_run(const RingTensor (&ts)[NT], const bool 
         st = 0;
         ph ^= 1;
       }
-      if (++seg == gm.segs) {
+      if (reverse) {
+        if (--seg < 0) {
+          seg = gm.segs - 1;
+          --row;
+        }
+      } else if (++seg == gm.segs) {
         seg = 0;
         ++row;
       }
@@ -1100,7 +1116,8 @@ in_bwd_apply_ring_kernel(View dz, View dz2, int has_dz2, int has_gsrc, View y, c
                     store8(static_cast<__nv_bfloat16*>(dy.p) + dy.at32(i, row, x0 + px) + g * 8, o);
                   }
                 }
-              });
+              },
+              /*reverse=*/true);
 }
 
 // forward apply: operands {y, residual}; z = act((y - mean) * rstd) (+ residual), scattered to every padded position
