@@ -11,6 +11,7 @@ generator), :424-441 (InstanceNorm PatchGAN). Convolution biases that feed an In
 no-ops (the norm subtracts the per-plane mean) and are skipped; their gradient is exactly 0.
 """
 import ctypes as C
+import functools
 
 import torch
 
@@ -114,6 +115,18 @@ def _norm_act(y, act, halo, residual=None):
 
 
 class _NetBase:
+    def __init_subclass__(cls, **kw):
+        super().__init_subclass__(**kw)
+        fn = cls.__dict__.get("backward")
+        if fn is not None:  # every backward() joins the weight-gradient stream before it returns
+            @functools.wraps(fn)
+            def backward(self, *a, **k):
+                try:
+                    return fn(self, *a, **k)
+                finally:
+                    ops.wgrad_join()
+            cls.backward = backward
+
     def __init__(self, module):
         self.module = module
         self.layers = {}
@@ -196,16 +209,17 @@ class _NetBase:
         g = L.spec.g
         if grads is not None:
             gw = grads[name + ".weight"]
-            if L.transposed:
-                ops.conv_wgrad(dy, x, L.spec, gw)  # conv view: input role = dy_T (large), output-grad role = x_T
-            else:
-                ops.conv_wgrad(x, dy, L.spec, gw)
-            if L.use_bias:
-                ops.bias_grad(dy, grads[name + ".bias"], L.bias.numel())
-            if self.grad_ready is not None:
-                self.grad_ready(name + ".weight")
-                if L.bias is not None:
-                    self.grad_ready(name + ".bias")  # unused biases (before an InstanceNorm) keep gradient 0
+            with ops.wgrad_side(x, dy):  # second stream, joined at the end of backward()
+                if L.transposed:
+                    ops.conv_wgrad(dy, x, L.spec, gw)  # conv view: input role = dy_T (large), output-grad role = x_T
+                else:
+                    ops.conv_wgrad(x, dy, L.spec, gw)
+                if L.use_bias:
+                    ops.bias_grad(dy, grads[name + ".bias"], L.bias.numel())
+                if self.grad_ready is not None:  # collectives are ordered after the stream they are launched from
+                    self.grad_ready(name + ".weight")
+                    if L.bias is not None:
+                        self.grad_ready(name + ".bias")  # unused biases (before an InstanceNorm) keep gradient 0
         if not need_dx:
             return None
         if L.transposed:

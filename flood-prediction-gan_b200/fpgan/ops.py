@@ -1,6 +1,8 @@
 """Python-side operator wrappers over the C ABI: device buffers are torch tensors (plumbing only), every
 operator is one call into libfpg_b200.so on the current CUDA stream. No operator here has a torch fallback."""
+import contextlib
 import ctypes as C
+import os
 
 import torch
 
@@ -207,13 +209,60 @@ _ws_cache = {}
 
 
 def workspace(nbytes, device):
-    """Grow-only fp32 scratch shared by the wgrad / reduction kernels of one device (stream-ordered reuse)."""
-    key = str(device)
+    """Grow-only fp32 scratch shared by the wgrad / reduction kernels of one device and stream (stream-ordered reuse)."""
+    key = (str(device), torch.cuda.current_stream().cuda_stream)
     cur = _ws_cache.get(key)
     if cur is None or cur.numel() * 4 < nbytes:
         cur = torch.empty(max(nbytes // 4 + 1, 1 << 20), dtype=torch.float32, device=device)
         _ws_cache[key] = cur
     return cur
+
+
+class _WgradSide:
+    """The weight-gradient kernels of a backward pass run on a second stream: they depend only on the layer's saved
+    input and its output gradient, not on the dgrad -> InstanceNorm-backward chain, so their CTAs fill the SMs that the
+    chain's kernels leave idle (the 64x64 convs run 3.46 waves of tiles: 80 SMs idle through the fourth).
+    `with wgrad_side(x, dy):` switches to the side stream after making it wait for the producing stream and keeps the
+    operands alive until `wgrad_join()`, which every executor's backward() calls before it returns.
+    Opt-in (FPG_WGRAD_STREAM=1): measured on the B=16 PairedAttention step it is no gain (10.04 ms against 9.96 ms on
+    one stream) -- every kernel here is a one-CTA-per-SM persistent grid, so two streams only trade places."""
+
+    def __init__(self):
+        self.streams, self.keep, self.dirty = {}, [], False
+        self.enabled = os.environ.get("FPG_WGRAD_STREAM", "0") == "1"
+
+    def stream(self, device):
+        st = self.streams.get(str(device))
+        if st is None:
+            st = self.streams[str(device)] = torch.cuda.Stream(device=device)
+        return st
+
+
+_SIDE = _WgradSide()
+
+
+@contextlib.contextmanager
+def wgrad_side(*operands):
+    if not _SIDE.enabled or PROFILE is not None:
+        yield
+        return
+    main = torch.cuda.current_stream()
+    side = _SIDE.stream(operands[0].t.device)
+    side.wait_stream(main)
+    _SIDE.keep.append(operands)
+    _SIDE.dirty = True
+    with torch.cuda.stream(side):
+        yield
+
+
+def wgrad_join():
+    """the current stream waits for the weight-gradient stream; the operands it kept alive are released"""
+    if not _SIDE.dirty:
+        return
+    main = torch.cuda.current_stream()
+    main.wait_stream(_SIDE.stream(main.device))
+    _SIDE.keep.clear()
+    _SIDE.dirty = False
 
 
 def conv_wgrad(x, dy, spec, dw):
