@@ -122,6 +122,9 @@ SIGNATURES = {
     "fpg_batchnorm_running_update": (C.c_int, [_vp, _i32, _i64, _f32, _f32, _vp, _vp, _vp]),
     "fpg_maxpool2": (C.c_int, [_P(Act), _P(Act), _vp]),
     "fpg_dropout_mask": (C.c_int, [_vp, _i64, C.c_uint64, _f32, _vp]),
+    "fpg_resize_aa_scratch_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32]),
+    "fpg_resize_bicubic_aa": (C.c_int, [_vp, _i32, _i32, _i32, _P(_i32), _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "fpg_tile_gather": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _f32, _f32, _vp, _vp]),
     "fpg_act_bwd": (C.c_int, [_P(Act), _P(Act), C.c_int, _P(Act), _vp]),
     "fpg_halo_fold": (C.c_int, [_P(Act), _P(Act), _P(Act), _vp]),
     "fpg_blend_fwd": (C.c_int, [_P(Act), _P(Act), _P(Act), _P(Act), _i32, _vp, _vp, _vp]),

@@ -410,3 +410,31 @@ def flood_mask(logits, mask):
 
 def confusion_counts(pred, truth, counts):
     _run("confusion_counts", 1, "fpg_confusion_counts", _ptr(pred), _ptr(truth), pred.numel(), _ptr(counts), _stream())
+
+
+# ---------------------------------------------------------------------------------------------- input pipeline
+def resize_bicubic_aa(src_hwc, channel_map, out_h, out_w, flip_w=False, out=None):
+    """src_hwc: decoded stack [H, W, C] fp32 on the device. Returns [len(channel_map), out_h, out_w] fp32: the selected
+    channels, optionally mirrored left-right, resized like torchvision Resize(BICUBIC, antialias=True)."""
+    assert src_hwc.is_cuda and src_hwc.dtype == torch.float32 and src_hwc.is_contiguous() and src_hwc.dim() == 3
+    h, w, c = src_hwc.shape
+    n = len(channel_map)
+    if out is None:
+        out = torch.empty(n, out_h, out_w, dtype=torch.float32, device=src_hwc.device)
+    nbytes = L.load().fpg_resize_aa_scratch_bytes(h, w, out_h, out_w, n)
+    if nbytes <= 0:
+        L.check(-22, "fpg_resize_aa_scratch_bytes")
+    ws = workspace(nbytes + 256, src_hwc.device)
+    base = (ws.data_ptr() + 255) & ~255
+    cmap = (C.c_int32 * n)(*channel_map)
+    _run("resize_bicubic_aa", 3, "fpg_resize_bicubic_aa", _ptr(src_hwc), h, w, c, cmap, n, 1 if flip_w else 0, out_h,
+         out_w, _ptr(out), C.c_void_p(base), _stream())
+    return out
+
+
+def tile_gather(image_ptrs, crop_index, channels, height, width, divisions, out, mean=0.5, std=0.5):
+    """image_ptrs: int64 device tensor of B pointers to resident [channels, height, width] fp32 images; crop_index:
+    int32 device tensor [B]; out: [B, channels, height // divisions, width // divisions] fp32."""
+    _run("tile_gather", 1, "fpg_tile_gather", _ptr(image_ptrs), channels, height, width, _ptr(crop_index),
+         image_ptrs.numel(), divisions, mean, std, _ptr(out), _stream())
+    return out

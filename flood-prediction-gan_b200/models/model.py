@@ -45,7 +45,7 @@ class Model:
     def __init__(self, model="Pix2Pix", dataset_subset="all", dataset_dem="best", data_path=None, num_epochs=1,
                  topography="all", resize=256, crop=None, save_model_interval=0, save_images_interval=0,
                  verbose=False, load_pretrained_model=False, pretrained_model_path=None, add_identity_loss=False,
-                 training_model=True, seed=47, log_interval=50):
+                 training_model=True, seed=47, log_interval=50, batch_size=1):
         self.device = _device()
         if verbose:
             print(f"\nSetting up the {self.prettify_model_name(model)} model...")
@@ -117,8 +117,11 @@ class Model:
         self.current_epoch = self.starting_epoch
         self._native = None
 
+        # device-resident loaders (models/data.py); batch_size is an extension, the reference's loaders use 1
+        rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
         self.train_loader, self.val_loader, self.test_loader = data.create_flood_dataset(
-            self.dataset_subset, self.dataset_dem, self.data_path, self.topography, self.resize, self.crop)
+            self.dataset_subset, self.dataset_dem, self.data_path, self.topography, self.resize, self.crop,
+            batch_size=batch_size, rank=rank, world_size=world)
         if self.verbose and self.training_model:
             self.print_training_setup()
 

@@ -344,6 +344,27 @@ int fpg_maxpool2(const fpg_act* x, const fpg_act* y, void* stream);
 int fpg_dropout_mask(uint8_t* mask, int64_t count, uint64_t seed, float keep, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Input pipeline -- models/utils.py:19-67 (apply_transformations), models/data.py:57-78 (FloodDataset.__getitem__).
+ *   fpg_resize_bicubic_aa: src_hwc = one decoded TIFF stack [in_h][in_w][in_c] fp32 (the layout tifffile.imread
+ *     returns); keeps the `channels` (<= 16) input channels listed in channel_map (HOST array; the `topography`
+ *     selection, utils.py:30-39), mirrors the columns when flip_w != 0 (np.fliplr, data.py:63-65), resamples with
+ *     torchvision's Resize(BICUBIC, antialias=True) algorithm (utils.py:41-43; horizontal pass, then vertical, fp32)
+ *     and writes dst_chw [channels][out_h][out_w] fp32. An axis whose size does not change is copied.
+ *     scratch: fpg_resize_aa_scratch_bytes() bytes of device memory (256-byte aligned).
+ *   fpg_tile_gather: images = DEVICE array of `batch` pointers to resident resized images [channels][height][width]
+ *     fp32; sample b is window crop_index[b] (row-major, DEVICE int32 array) of a divisions x divisions grid of
+ *     images[b] (utils.py:45-56), normalised as (v - mean) / stdv (utils.py:58-61);
+ *     dst [batch][channels][height/divisions][width/divisions] fp32.
+ * ---------------------------------------------------------------------------------------------------------- */
+int64_t fpg_resize_aa_scratch_bytes(int32_t in_h, int32_t in_w, int32_t out_h, int32_t out_w, int32_t channels);
+int fpg_resize_bicubic_aa(const float* src_hwc, int32_t in_h, int32_t in_w, int32_t in_c, const int32_t* channel_map,
+                          int32_t channels, int32_t flip_w, int32_t out_h, int32_t out_w, float* dst_chw,
+                          void* scratch, void* stream);
+int fpg_tile_gather(const float* const* images, int32_t channels, int32_t height, int32_t width,
+                    const int32_t* crop_index, int32_t batch, int32_t divisions, float mean, float stdv, float* dst,
+                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Attention / content blend -- model_architectures.py:353-399.
  *   content: fp32, tanh already applied, 27 valid channels (9 RGB triplets) in a 32-channel buffer
  *   logits:  fp32, 10 valid channels in a 16-channel buffer (pre-softmax)

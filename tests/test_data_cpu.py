@@ -1,0 +1,121 @@
+"""Input pipeline, CPU side: the numpy oracle of apply_transformations against the golden
+vectors produced by the reference's own code (tests/golden/make_golden_data.py), the dataset-split logic against the
+reference's lists on the fixture metadata, and the loader order against torch's DataLoader(shuffle=True)."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "flood-prediction-gan_b200"))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+from oracle import data_oracle as DO  # noqa: E402
+from models import data  # noqa: E402
+import make_golden_data as G  # noqa: E402  (only its seeded synthetic-image helper is used; the reference is not imported)
+
+VECTORS = json.load(open(os.path.join(HERE, "golden", "data_vectors.json")))
+FIXTURE = os.path.join(HERE, "golden", "dataset_split_fixture.csv")
+TOL = 2e-6  # float32 resampling: the restatement agrees with ATen to 1-4 ulp of values in [-1, 1]
+
+
+def check_digest(got, ref):
+    assert list(got.shape) == ref["shape"]
+    f = torch.from_numpy(np.ascontiguousarray(got)).double().reshape(-1)
+    idx = torch.linspace(0, f.numel() - 1, len(ref["samples"])).long()
+    assert (f[idx] - torch.tensor(ref["samples"], dtype=torch.float64)).abs().max().item() <= TOL
+    assert abs(f.sum().item() - ref["sum"]) <= TOL * f.numel() ** 0.5 * 4
+    assert abs(f.abs().sum().item() - ref["abs_sum"]) <= TOL * f.numel() ** 0.5 * 4
+
+
+@pytest.mark.parametrize("case", VECTORS["transforms"], ids=lambda c: f"seed{c['seed']}")
+def test_oracle_matches_reference_transformations(case):
+    x, y = G.decoded_pair(case["seed"], case["h"], case["w"])
+    a, b = DO.apply_transformations(x, y, case["topography"], case["resize"], case["crop"], case["crop_index"],
+                                    case["flipped"])
+    check_digest(a, case["input"])
+    check_digest(b, case["output"])
+
+
+def test_resampling_weights_properties():
+    for n_in, n_out in ((1024, 512), (96, 40), (40, 64), (7, 3)):
+        table = DO.aa_weights(n_in, n_out)
+        assert len(table) == n_out
+        for lo, n, w in table:
+            assert 0 <= lo and lo + n <= n_in and n >= 1
+            assert abs(float(w.sum()) - 1.0) < 1e-6  # a constant image stays constant
+    img = np.full((2, 12, 20), 0.25, dtype=np.float32)
+    assert np.allclose(DO.resize_bicubic_aa(img, 6), 0.25, atol=1e-6)
+    assert DO.resize_output_size(48, 80, 32) == (32, 53) and DO.resize_output_size(80, 48, 32) == (53, 32)
+    assert data.resize_output_size(48, 80, 32) == (32, 53) and data.resize_output_size(64, 64, None) == (64, 64)
+
+
+@pytest.mark.parametrize("rec", VECTORS["splits"], ids=lambda r: f"{r['subset']}-{r['dem']}-{r['crop']}")
+def test_dataset_split_matches_reference(rec):
+    got = data.determine_flood_dataset(rec["subset"], rec["dem"], rec["crop"], metadata_csv=FIXTURE)
+    for split in ("train", "validation", "test"):
+        items = [tuple(int(v) if isinstance(v, (int, np.integer)) else v for v in it) for it in got[split]]
+        assert len(items) == rec[split]["n"]
+        assert [list(it) for it in items[:3]] == rec[split]["head"]
+        assert hashlib.sha1(repr(items).encode()).hexdigest() == rec[split]["sha1"]
+
+
+def test_dataset_split_rejects_unknown_names():
+    with pytest.raises(NotImplementedError):
+        data.determine_flood_dataset("atlantis", "best", None, metadata_csv=FIXTURE)
+    with pytest.raises(NotImplementedError):
+        data.determine_flood_dataset("usa", "worst", None, metadata_csv=FIXTURE)
+
+
+class _Indices(torch.utils.data.Dataset):
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return i
+
+
+@pytest.mark.parametrize("n,batch", [(10, 4), (37, 1), (64, 16)])
+def test_loader_order_is_torch_dataloader_order(n, batch):
+    """same global seed -> the same sample order as DataLoader(shuffle=True) (data.py:28-32), epoch after epoch"""
+    torch.manual_seed(47)
+    ref_loader = torch.utils.data.DataLoader(_Indices(n), batch_size=batch, shuffle=True, num_workers=0)
+    ref = [[b.tolist() for b in ref_loader] for _ in range(2)]
+    torch.manual_seed(47)
+    mine = data.DeviceLoader(_Indices(n), batch_size=batch, shuffle=True)
+    for epoch in range(2):
+        order = mine.order()
+        got = [order[s:s + batch] for s in range(0, n, batch)]
+        assert got == ref[epoch]
+    assert len(mine) == len(ref_loader)
+
+
+def test_sharded_loader_partitions_the_global_batch():
+    n, batch, world = 23, 3, 2
+
+    class Rec(_Indices):
+        def gather(self, idx):
+            return list(idx)
+
+    per_rank = []
+    for rank in range(world):
+        torch.manual_seed(5)
+        per_rank.append(list(data.DeviceLoader(Rec(n), batch, rank=rank, world_size=world)))
+    torch.manual_seed(5)
+    single = list(data.DeviceLoader(Rec(n), batch * world))
+    merged = [a + (b if i < len(per_rank[1]) else []) for i, (a, b) in
+              enumerate(zip(per_rank[0], per_rank[1] + [[]] * len(per_rank[0])))]
+    assert merged == single
+
+
+def test_create_flood_dataset_without_data_returns_empty_loaders():
+    assert data.create_flood_dataset("all", "best", None, "all", 256, None) == ([], [], [])
