@@ -122,6 +122,11 @@ SIGNATURES = {
     "fpg_batchnorm_running_update": (C.c_int, [_vp, _i32, _i64, _f32, _f32, _vp, _vp, _vp]),
     "fpg_maxpool2": (C.c_int, [_P(Act), _P(Act), _vp]),
     "fpg_dropout_mask": (C.c_int, [_vp, _i64, C.c_uint64, _f32, _vp]),
+    "fpg_ssim_scratch_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "fpg_ssim_stats": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
+    "fpg_avgpool2_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "fpg_sq_err_scratch_bytes": (_i64, []),
+    "fpg_sq_err_sum": (C.c_int, [_vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp]),
     "fpg_resize_aa_scratch_bytes": (_i64, [_i32, _i32, _i32, _i32, _i32]),
     "fpg_resize_bicubic_aa": (C.c_int, [_vp, _i32, _i32, _i32, _P(_i32), _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "fpg_tile_gather": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _f32, _f32, _vp, _vp]),

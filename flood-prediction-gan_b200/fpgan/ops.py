@@ -438,3 +438,36 @@ def tile_gather(image_ptrs, crop_index, channels, height, width, divisions, out,
     _run("tile_gather", 1, "fpg_tile_gather", _ptr(image_ptrs), channels, height, width, _ptr(crop_index),
          image_ptrs.numel(), divisions, mean, std, _ptr(out), _stream())
     return out
+
+
+# ---------------------------------------------------------------------------------------------- image-quality metrics
+def ssim_stats(pred, target, data_range=1.0, k1=0.01, k2=0.03, sigma=1.5):
+    """pred, target: [B, C, H, W] fp32 CUDA. Returns [B, 2] = per-image (mean SSIM, mean contrast sensitivity)."""
+    assert pred.shape == target.shape and pred.is_cuda and pred.dtype == torch.float32
+    pred, target = pred.contiguous(), target.contiguous()
+    b, c, h, w = pred.shape
+    nbytes = L.load().fpg_ssim_scratch_bytes(b, c, h, w)
+    if nbytes <= 0:
+        L.check(-22, "fpg_ssim_scratch_bytes")
+    ws = workspace(nbytes, pred.device)
+    out = torch.empty(b, 2, dtype=torch.float32, device=pred.device)
+    _run("ssim_stats", 2, "fpg_ssim_stats", _ptr(pred), _ptr(target), b, c, h, w, data_range, k1, k2, sigma, _ptr(out),
+         _ptr(ws), _stream())
+    return out
+
+
+def avgpool2_f32(x):
+    b, c, h, w = x.shape
+    y = torch.empty(b, c, h // 2, w // 2, dtype=torch.float32, device=x.device)
+    _run("avgpool2_f32", 1, "fpg_avgpool2_f32", _ptr(x.contiguous()), _ptr(y), b * c, h, w, _stream())
+    return y
+
+
+def sq_err_sum(a, b, clamp=(0.0, 1.0)):
+    """sum (clamp(a) - clamp(b))^2 as a float64 device scalar (fixed summation order)"""
+    a, b = a.contiguous(), b.contiguous()
+    ws = workspace(L.load().fpg_sq_err_scratch_bytes(), a.device)
+    out = torch.empty(1, dtype=torch.float64, device=a.device)
+    _run("sq_err_sum", 2, "fpg_sq_err_sum", _ptr(a), _ptr(b), a.numel(), clamp[0], clamp[1], _ptr(out), _ptr(ws),
+         _stream())
+    return out

@@ -20,7 +20,7 @@ from torch import nn
 from torch.optim import lr_scheduler
 
 from fpgan import trainer as native_trainer
-from models import data, model_architectures
+from models import data, metrics, model_architectures
 
 MODEL_TABLE = {
     # name: (generator, discriminator, cycle training?, attention generator?)
@@ -272,15 +272,20 @@ class Model:
     def calculate_metrics(self, use_test_data=False, seg_model_path=None, loader=None):
         """Flood-segmentation metrics of calculate_metrics (reference model.py:363-422): generator inference,
         segmentation of the generated and the ground-truth tile, bit-exact (sigmoid > 0.5) masks, confusion counts
-        accumulated over the whole split on the device. PSNR / SSIM / MS-SSIM / LPIPS need torchmetrics (un-vendored,
-        absent: parity unpinnable) and are reported as NaN. Returns the metrics dict (and writes the reference's CSV
-        when data_path is set)."""
+        accumulated over the whole split on the device; PSNR / SSIM / MS-SSIM per batch from models/metrics.py (the
+        published torchmetrics algorithm; that dependency is absent, parity unpinned), averaged over batches as the
+        reference does with np.mean; LPIPS is NaN. Returns the metrics dict (and writes the reference's CSV when
+        data_path is set)."""
         seg_model = self.load_segmentation_model(seg_model_path)
         generator = self.pre_to_post_generator if self.model_is_cycle else self.generator
         if loader is None:
             loader = self.test_loader if use_test_data else self.val_loader
         totals = torch.zeros(4, dtype=torch.int64, device=self.device)
         times = []
+        quality = {"PSNR": metrics.PeakSignalNoiseRatio(data_range=(0, 1)),                       # :367-369
+                   "SSIM": metrics.StructuralSimilarityIndexMeasure(data_range=(0, 1)),
+                   "MS-SSIM": metrics.MultiScaleStructuralSimilarityIndexMeasure(data_range=(0, 1))}
+        per_batch = {k: [] for k in quality}
         n_in = TOPOGRAPHY_CHANNELS[self.topography]
         for input_stack, ground_truth, _ in loader:
             x = input_stack[:, :n_in].to(self.device).float().contiguous()
@@ -294,8 +299,16 @@ class Model:
             times.append(time.time() - t0)
             _, _, counts = model_architectures.flood_masks_and_counts(seg_model, generated, truth)
             totals += counts
+            g01 = torch.clamp((generated + 1) * 0.5, min=0, max=1)                                # :397-398
+            t01 = torch.clamp((truth + 1) * 0.5, min=0, max=1)
+            for name, metric in quality.items():                                                    # :404-406
+                if name == "MS-SSIM" and not metrics.ms_ssim_size_ok(*g01.shape[-2:]):
+                    continue  # torchmetrics raises for tiles this small; the column stays NaN
+                per_batch[name].append(metric(g01, t01))
+                metric.reset()
         tp, fp, tn, fn = (int(v) for v in totals.tolist())
-        results = {"PSNR": float("nan"), "SSIM": float("nan"), "MS-SSIM": float("nan"), "LPIPS": float("nan")}
+        results = {k: (float(torch.stack(v).mean().item()) if v else float("nan")) for k, v in per_batch.items()}
+        results["LPIPS"] = float("nan")  # needs pretrained AlexNet weights (download): not provided
         results.update(self.binary_metrics_from_counts(tp, fp, tn, fn))
         results["Inference"] = float(np.mean(times)) if times else float("nan")
         if self.verbose:

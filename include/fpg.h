@@ -365,6 +365,24 @@ int fpg_tile_gather(const float* const* images, int32_t channels, int32_t height
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Image-quality metrics of calculate_metrics -- models/model.py:367-371, 404-406 (torchmetrics 1.2.0, un-vendored:
+ * PeakSignalNoiseRatio / StructuralSimilarityIndexMeasure / MultiScaleStructuralSimilarityIndexMeasure with
+ * data_range=(0, 1)). Images are fp32 NCHW on the device.
+ *   fpg_ssim_stats: out[img] = {mean SSIM, mean contrast sensitivity} over the image's C*(H-10)*(W-10) window
+ *     positions (gaussian 11x11 window of `sigma`, constants (k1*data_range)^2 and (k2*data_range)^2, 5-pixel border
+ *     cropped as torchmetrics does). scratch: fpg_ssim_scratch_bytes() bytes.
+ *   fpg_avgpool2_f32: y[planes][h/2][w/2] = F.avg_pool2d(x, (2, 2)) -- the link between MS-SSIM scales.
+ *   fpg_sq_err_sum: out[0] (double) = sum (clamp(a) - clamp(b))^2, fixed summation order -- the PSNR numerator.
+ * ---------------------------------------------------------------------------------------------------------- */
+int64_t fpg_ssim_scratch_bytes(int32_t n, int32_t c, int32_t h, int32_t w);
+int fpg_ssim_stats(const float* pred, const float* target, int32_t n, int32_t c, int32_t h, int32_t w,
+                   float data_range, float k1, float k2, float sigma, float* out, void* scratch, void* stream);
+int fpg_avgpool2_f32(const float* x, float* y, int32_t planes, int32_t h, int32_t w, void* stream);
+int64_t fpg_sq_err_scratch_bytes(void);
+int fpg_sq_err_sum(const float* a, const float* b, int64_t count, float clamp_lo, float clamp_hi, double* out,
+                   void* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * Attention / content blend -- model_architectures.py:353-399.
  *   content: fp32, tanh already applied, 27 valid channels (9 RGB triplets) in a 32-channel buffer
  *   logits:  fp32, 10 valid channels in a 16-channel buffer (pre-softmax)

@@ -469,4 +469,5 @@ def test_model_calculate_metrics_flood_columns():
               "Recall_No_Flood", "Inference"):
         assert 0.0 <= res[k] <= 1.0 or k == "Inference", (k, res[k])
     assert abs(res["MSE"] + res["Accuracy"] - 1.0) < 1e-12  # both are functions of the same integer counts
-    assert res["PSNR"] != res["PSNR"]  # NaN: torchmetrics image-quality metrics are out of scope
+    assert 0.0 < res["PSNR"] < 60.0 and -1.0 <= res["SSIM"] <= 1.0  # image-quality columns (models/metrics.py)
+    assert res["MS-SSIM"] != res["MS-SSIM"] and res["LPIPS"] != res["LPIPS"]  # 64-pixel tiles are below MS-SSIM's 160
