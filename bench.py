@@ -32,8 +32,8 @@ RES_CONV_GFLOP_PER_TILE = 4.8318  # one residual 3x3 conv, 256->256 @ 64x64: 2 *
 
 def ncu_traffic_bytes(report="r01_res_fprop.ncu-rep"):
     """DRAM bytes (read + write) per launch of the dominant kernel from the committed ncu --set full summary
-    (profiles/r01_ncu_kernels_v8.csv, produced by tools/profile_kernels.sh + tools/summarize_ncu.py); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_kernels_v8.csv")
+    (profiles/r01_ncu_kernels_v9.csv, produced by tools/profile_kernels.sh + tools/summarize_ncu.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_kernels_v9.csv")
     if not os.path.exists(path):
         return None
     import csv

@@ -891,7 +891,7 @@ pack_batched_kernel(const fpg_pack_job* __restrict__ jobs, const int32_t* __rest
 // stats[(i*c + ch)*2] = {mean, rstd} of image i from the epilogue partials [i][rows][c][2] (fixed summation order).
 // block = 64 channels x 4 row groups
 __global__ void __launch_bounds__(256)
-stats_finalize_kernel(const float* __restrict__ partial, int rows, int c, float inv_count, float eps,
+stats_finalize_kernel(const float* __restrict__ partial, int rows, int c, float inv_count, float eps, int sums_only,
                       float* __restrict__ stats) {
   const int i = blockIdx.x;
   const int ch = blockIdx.y * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
@@ -916,7 +916,8 @@ stats_finalize_kernel(const float* __restrict__ partial, int rows, int c, float 
     const float mean = a * inv_count;
     const float var = fmaxf(b * inv_count - mean * mean, 0.f);
     stats[(static_cast<int64_t>(i) * c + ch) * 2] = mean;
-    stats[(static_cast<int64_t>(i) * c + ch) * 2 + 1] = rsqrtf(var + eps);
+    // sums_only: the two plane means themselves (InstanceNorm backward: mean g', mean g' * zhat)
+    stats[(static_cast<int64_t>(i) * c + ch) * 2 + 1] = sums_only ? b * inv_count : rsqrtf(var + eps);
   }
 }
 
@@ -1067,9 +1068,45 @@ int fpg_conv2d_dgrad_stats(const fpg_act* dy, const void* w_packed_t, const floa
   return 0;
 }
 
-int fpg_instnorm_stats_finalize(const float* stat_partial, int32_t rows_per_img, int32_t n, int32_t c,
-                                int64_t count_per_img, float eps, float* stats, void* stream) {
-  FPG_REQUIRE(stat_partial && stats && rows_per_img > 0 && n > 0 && c > 0 && count_per_img > 0, "bad argument");
+int fpg_conv2d_dgrad_inbwd(const fpg_act* dy, const void* w_packed_t, const fpg_conv_geom* g, const fpg_act* dx,
+                           const fpg_act* y, const float* stats, int act, const fpg_act* add, float* stat_partial,
+                           int32_t* rows_per_img, void* stream) {
+  FPG_REQUIRE(dy && w_packed_t && g && dx && y && stats && stat_partial && rows_per_img, "null argument");
+  FPG_REQUIRE(!y->fp32 && y->halo == 0 && y->c == y->c_stride && y->h == dx->h && y->w == dx->w && y->c == dx->c &&
+                  y->n == dx->n && y->c % 16 == 0,
+              "y must be the halo-free bf16 pre-norm tensor of the activation whose gradient is produced");
+  if (add != nullptr)
+    FPG_REQUIRE(!add->fp32 && add->c == add->c_stride && add->h == dx->h && add->w == dx->w && add->c == dx->c &&
+                    add->n == dx->n,
+                "add must match the interior of dx");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
+  if (g->stride != 1) return 1;
+  fpg_igemm_rows_desc rd;
+  if (plan_rows(dy, w_packed_t, nullptr, FPG_ACT_NONE, g, dx, 1, sms, &rd) != 1) return 1;  // row-stationary layer
+  fpg_igemm_fprop_desc d[4];
+  int n = 0;
+  int rc = plan_dgrad(dy, w_packed_t, nullptr, FPG_ACT_NONE, g, dx, sms, d, &n);
+  if (rc) return rc;
+  if (n != 1 || d[0].cta_pair || d[0].block_n * d[0].n_blocks != y->c) return 1;
+  d[0].stat_partial = stat_partial;
+  d[0].stat_rows_per_img = stats_rows_of(&d[0]);
+  d[0].stat_row0 = 0;
+  d[0].inbwd_y = y->data;
+  d[0].inbwd_stats = stats;
+  d[0].inbwd_add = add ? add->data : nullptr;
+  d[0].inbwd_h = y->h;
+  d[0].inbwd_w = y->w;
+  d[0].inbwd_c = y->c;
+  d[0].inbwd_halo = dx->halo;
+  d[0].inbwd_add_halo = add ? add->halo : 0;
+  d[0].inbwd_act = act;
+  *rows_per_img = d[0].stat_rows_per_img;
+  return fpg_igemm_fprop_launch(&d[0], stream);
+}
+
+static int reduce_stat_rows(const float* stat_partial, int32_t rows_per_img, int32_t n, int32_t c, float inv_count,
+                            float eps, int sums_only, float* out, void* stream) {
   const float* cur = stat_partial;
   int rows = rows_per_img;
   // long row lists are first folded 256:1 into the tail of the buffer (the caller sizes it for that)
@@ -1082,10 +1119,22 @@ int fpg_instnorm_stats_finalize(const float* stat_partial, int32_t rows_per_img,
     spare += static_cast<int64_t>(n) * out_rows * c * 2;
     rows = out_rows;
   }
-  stats_finalize_kernel<<<dim3(n, (c + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      cur, rows, c, 1.f / static_cast<float>(count_per_img), eps, stats);
+  stats_finalize_kernel<<<dim3(n, (c + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(cur, rows, c, inv_count,
+                                                                                               eps, sums_only, out);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+int fpg_instnorm_bwd_sums_finalize(const float* stat_partial, int32_t rows_per_img, int32_t n, int32_t c,
+                                   int64_t count_per_img, float* red, void* stream) {
+  FPG_REQUIRE(stat_partial && red && rows_per_img > 0 && n > 0 && c > 0 && count_per_img > 0, "bad argument");
+  return reduce_stat_rows(stat_partial, rows_per_img, n, c, 1.f / static_cast<float>(count_per_img), 0.f, 1, red, stream);
+}
+
+int fpg_instnorm_stats_finalize(const float* stat_partial, int32_t rows_per_img, int32_t n, int32_t c,
+                                int64_t count_per_img, float eps, float* stats, void* stream) {
+  FPG_REQUIRE(stat_partial && stats && rows_per_img > 0 && n > 0 && c > 0 && count_per_img > 0, "bad argument");
+  return reduce_stat_rows(stat_partial, rows_per_img, n, c, 1.f / static_cast<float>(count_per_img), eps, 0, stats, stream);
 }
 
 int fpg_conv2d_wgrad_plan(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g, int sm_count,

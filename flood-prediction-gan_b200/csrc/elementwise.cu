@@ -1901,6 +1901,34 @@ int fpg_instnorm_bwd(const fpg_act* dz, const fpg_act* dz2, const fpg_act* y, co
   return 0;
 }
 
+int fpg_instnorm_bwd_apply(const fpg_act* dz, const fpg_act* y, const float* stats, const float* red, int act,
+                           const fpg_act* dy, void* stream) {
+  FPG_REQUIRE(dz && y && stats && red && dy, "null argument");
+  FPG_REQUIRE(dz->h == y->h && dz->w == y->w && dz->c == y->c && dy->h == y->h && dy->c == y->c, "geometry mismatch");
+  FPG_REQUIRE(ring_ok(y) && ring_ok(dz) && ring_ok(dy), "tensors must suit the bulk-copy ring (see fpg_instnorm_bwd)");
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
+  const int stages = 4;
+  const size_t smem = ring_smem(stages, 3);
+  static bool attr_set = false;
+  if (!attr_set) {
+    FPG_CUDA_CHECK(cudaFuncSetAttribute(in_bwd_apply_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(smem)));
+    attr_set = true;
+  }
+  const RingGeom gm = ring_geom(y, stages, sms);
+  const RingTensor t_dz = ring_tensor(dz), t_y = ring_tensor(y);
+  if (dz->halo > 0) {
+    const int band_px = 2 * dz->halo * dz->w + 2 * dz->halo * (dz->h - 2 * dz->halo);
+    const int64_t total = static_cast<int64_t>(dz->n) * band_px * (dz->c / 8);
+    halo_fold_inplace_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(dz), band_px);
+  }
+  in_bwd_apply_ring_kernel<<<dim3(gm.ctas_per_img, y->n), kRingThreads, smem, FPG_ST(stream)>>>(
+      view_of(dz), view_of(dz), 0, 0, view_of(y), stats, red, act, view_of(dy), t_dz, t_y, t_y, gm, 1);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int fpg_act_bwd(const fpg_act* dz, const fpg_act* z, int act, const fpg_act* dx, void* stream) {
   FPG_REQUIRE(dz && z && dx, "null argument");
   const int64_t total = static_cast<int64_t>(z->n) * z->h * z->w * (z->c / 8);

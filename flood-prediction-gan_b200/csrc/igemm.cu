@@ -46,6 +46,14 @@ struct StatOut {
   int32_t c_total;
 };
 
+// InstanceNorm-backward statistics from a dgrad epilogue (fpg_igemm_fprop_desc.inbwd_*): y == nullptr = off
+struct InBwdStat {
+  const __nv_bfloat16* y;    // [n][h][w][c] forward pre-norm output
+  const float* stats;        // [n][c][2] mean, rstd
+  const __nv_bfloat16* add;  // optional [n][h + 2 add_halo][w + 2 add_halo][c]: added to the interior outputs
+  int32_t h, w, c, halo, add_halo, act;
+};
+
 struct FpropArgs {
   int32_t chunks_per_tap;
   int32_t num_kstages;
@@ -64,6 +72,7 @@ struct FpropArgs {
   const float* bias;
   fpg_out_view out;
   StatOut stat;
+  InBwdStat inbwd;
   fpg_tap taps[FPG_MAX_TAPS];
 };
 
@@ -92,6 +101,48 @@ __device__ __forceinline__ void stat_accumulate(const StatOut& so, const float (
     const float r = valid ? __bfloat162float(__float2bfloat16(f[i])) : 0.f;
     a[i] = r;
     b[i] = r * r;
+  }
+  const float sa = warp_colsum16(a, lane);
+  const float sb = warp_colsum16(b, lane);
+  if ((lane & 1) == 0) {
+    const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    reinterpret_cast<float2*>(so.partial)[prow * so.c_total + col0 + col] = make_float2(sa, sb);
+  }
+}
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// InstanceNorm-backward variant of stat_accumulate: f = the 16 values about to be stored for this thread's pixel,
+// yreg = the forward pre-norm output (16 bf16) at the interior pixel it mirrors, st = {mean, rstd} of the channels.
+// Column sums over the warp's 32 rows of g' = round_bf16(f) * act'(zhat) and g' * zhat.
+__device__ __forceinline__ void inbwd_accumulate(const StatOut& so, const float (&f)[16], const uint4 (&yreg)[2],
+                                                 const float* st, int act, bool valid, int lane, int64_t prow,
+                                                 int col0) {
+  float a[16], b[16];
+  float yv[16];
+  unpack_bf16x8(yreg[0], yv);
+  unpack_bf16x8(yreg[1], yv + 8);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 ms = __ldg(reinterpret_cast<const float4*>(st) + i);  // {mean, rstd} of channels 2i, 2i + 1
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = 2 * i + h;
+      const float mean = h ? ms.z : ms.x, rstd = h ? ms.w : ms.y;
+      const float zh = valid ? (yv[k] - mean) * rstd : 0.f;
+      const float r = valid ? __bfloat162float(__float2bfloat16(f[k])) : 0.f;
+      const float slope = act == FPG_ACT_RELU ? (zh > 0.f ? 1.f : 0.f)
+                                              : (act == FPG_ACT_LEAKY ? (zh > 0.f ? 1.f : 0.2f) : 1.f);
+      a[k] = r * slope;
+      b[k] = a[k] * zh;
+    }
   }
   const float sa = warp_colsum16(a, lane);
   const float sb = warp_colsum16(b, lane);
@@ -284,13 +335,40 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
         // statistics row of this warp: image-major, then (region, tile row, tile column, warp quarter)
         const int64_t prow = static_cast<int64_t>(n) * args.stat.rows_per_img + args.stat.row0 +
                              ((r1 ? args.tiles_y * args.tiles_x : 0) + ty * ntx + tx) * 4 + q;
-        for (int c = 0; c < BN; c += 16) {
+        // InstanceNorm-backward statistics: the interior pixel this (padded) output pixel mirrors, and the pixel of
+        // the skip-connection gradient added to interior outputs
+        const __nv_bfloat16* y_px = nullptr;
+        const __nv_bfloat16* add_px = nullptr;
+        const float* st_img = nullptr;
+        if (args.inbwd.y != nullptr) {
+          const InBwdStat& ib = args.inbwd;
+          int iy = py - ib.halo, ix = px - ib.halo;
+          const bool interior = iy >= 0 && iy < ib.h && ix >= 0 && ix < ib.w;
+          iy = iy < 0 ? -iy : (iy >= ib.h ? 2 * (ib.h - 1) - iy : iy);
+          ix = ix < 0 ? -ix : (ix >= ib.w ? 2 * (ib.w - 1) - ix : ix);
+          if (valid) {
+            y_px = ib.y + ((static_cast<int64_t>(n) * ib.h + iy) * ib.w + ix) * ib.c + nb * BN;
+            if (ib.add != nullptr && interior)
+              add_px = ib.add + ((static_cast<int64_t>(n) * (ib.h + 2 * ib.add_halo) + iy + ib.add_halo) *
+                                     (ib.w + 2 * ib.add_halo) + ix + ib.add_halo) * ib.c + nb * BN;
+          }
+          st_img = ib.stats + (static_cast<int64_t>(n) * ib.c + nb * BN) * 2;
+        }
+        // one 16-column chunk: accumulator -> (+ skip gradient) -> bias / activation -> statistics -> store
+        auto chunk = [&](int c, const uint4 (&yreg)[2], const uint4 (&areg)[2]) {
           uint32_t v[16];
           tmem_ld16(t_addr + c, v);
           tmem_ld_wait();
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (add_px != nullptr) {
+            float e[16];
+            unpack_bf16x8(areg[0], e);
+            unpack_bf16x8(areg[1], e + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += e[i];
+          }
           if (args.bias != nullptr) {
             const float4* bp = reinterpret_cast<const float4*>(args.bias + nb * BN + c);
 #pragma unroll
@@ -306,7 +384,12 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], args.act);
           }
-          if (args.stat.partial != nullptr) stat_accumulate(args.stat, f, valid, lane, prow, nb * BN + c);
+          if (args.stat.partial != nullptr) {
+            if (st_img != nullptr)
+              inbwd_accumulate(args.stat, f, yreg, st_img + 2 * c, args.inbwd.act, valid, lane, prow, nb * BN + c);
+            else
+              stat_accumulate(args.stat, f, valid, lane, prow, nb * BN + c);
+          }
           if (valid) {
             if (args.out.fp32) {
               float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out.base) + off + c);
@@ -318,6 +401,35 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                                   pack_bf16x2(f[6], f[7]));
               dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
                                   pack_bf16x2(f[14], f[15]));
+            }
+          }
+        };
+        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+        if (st_img == nullptr) {
+          const uint4 none[2] = {zero4, zero4};
+          for (int c = 0; c < BN; c += 16) chunk(c, none, none);
+        } else {
+          // the y (and skip-gradient) reads are global loads with ~1 us latency: two register buffers, each reloaded
+          // for the chunk after next as soon as it has been consumed
+          uint4 y0[2] = {zero4, zero4}, y1[2] = {zero4, zero4}, a0[2] = {zero4, zero4}, a1[2] = {zero4, zero4};
+          auto fetch = [&](int c, uint4 (&yreg)[2], uint4 (&areg)[2]) {
+            if (y_px != nullptr) {
+              yreg[0] = __ldg(reinterpret_cast<const uint4*>(y_px + c));
+              yreg[1] = __ldg(reinterpret_cast<const uint4*>(y_px + c) + 1);
+            }
+            if (add_px != nullptr) {
+              areg[0] = __ldg(reinterpret_cast<const uint4*>(add_px + c));
+              areg[1] = __ldg(reinterpret_cast<const uint4*>(add_px + c) + 1);
+            }
+          };
+          fetch(0, y0, a0);
+          if (BN > 16) fetch(16, y1, a1);
+          for (int c = 0; c < BN; c += 32) {
+            chunk(c, y0, a0);
+            if (c + 32 < BN) fetch(c + 32, y0, a0);
+            if (c + 16 < BN) {
+              chunk(c + 16, y1, a1);
+              if (c + 48 < BN) fetch(c + 48, y1, a1);
             }
           }
         }
@@ -1076,6 +1188,19 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
   args.stat.partial = d->stat_partial;
   args.stat.rows_per_img = d->stat_rows_per_img;
   args.stat.row0 = d->stat_row0;
+  args.inbwd.y = static_cast<const __nv_bfloat16*>(d->inbwd_y);
+  args.inbwd.stats = d->inbwd_stats;
+  args.inbwd.add = static_cast<const __nv_bfloat16*>(d->inbwd_add);
+  args.inbwd.h = d->inbwd_h;
+  args.inbwd.w = d->inbwd_w;
+  args.inbwd.c = d->inbwd_c;
+  args.inbwd.halo = d->inbwd_halo;
+  args.inbwd.add_halo = d->inbwd_add_halo;
+  args.inbwd.act = d->inbwd_act;
+  if (d->inbwd_y != nullptr)
+    FPG_REQUIRE(!d->cta_pair && d->stat_partial != nullptr && d->inbwd_stats != nullptr && !d->out.fp32 &&
+                    d->inbwd_c == d->block_n * d->n_blocks && d->out.mul_y == 1 && d->out.mul_x == 1,
+                "InstanceNorm-backward statistics: 1-CTA stride-1 bf16 launch with the statistics buffer");
   args.stat.c_total = d->block_n * d->n_blocks;
   for (int i = 0; i < FPG_MAX_TAPS; ++i) args.taps[i] = d->taps[i];
 

@@ -202,9 +202,12 @@ class _NetBase:
         ops.instnorm_apply(y, stats, act, z, residual=residual)
         return y, stats, z
 
-    def _conv_bwd(self, name, x, dy, grads, need_dx, dx_halo=0):
+    def _conv_bwd(self, name, x, dy, grads, need_dx, dx_halo=0, in_bwd=None):
         """Backward of layer `name`: x = saved layer input, dy = gradient of its raw output.
-        Writes the weight (and used bias) gradient into `grads`; returns dx (incl. halo when dx_halo > 0)."""
+        Writes the weight (and used bias) gradient into `grads`; returns dx (incl. halo when dx_halo > 0).
+        in_bwd = (y, stats, act, add): x is act(IN(y)) -- the data-gradient kernel then also produces the plane means
+        of that InstanceNorm's backward (and merges the skip gradient `add` into dx's interior); returns (dx, red),
+        red = None when the layer has no such epilogue (dx is then the plain gradient, `add` NOT merged)."""
         L = self.layers[name]
         g = L.spec.g
         if grads is not None:
@@ -227,7 +230,14 @@ class _NetBase:
             ops.conv_fprop(dy, L.spec, dx)
         else:
             dx = ActBuf(x.n, x.h, x.w, g.c_in, halo=dx_halo, zero=False)
+            if in_bwd is not None:  # fuse the reduction pass of the producing InstanceNorm's backward (ops.py)
+                y_prev, stats_prev, act_prev, add = in_bwd
+                red = ops.conv_dgrad_inbwd(dy, L.spec, dx, y_prev, stats_prev, act_prev, add)
+                if red is not None:
+                    return dx, red
             ops.conv_dgrad(dy, L.spec, dx)
+            if in_bwd is not None:
+                return dx, None
         return dx
 
 
@@ -278,23 +288,39 @@ class _ResnetGeneratorNet(_NetBase):
     def _trunk_backward(self, t, dz, dz2, grads, need_dx):
         """dz (+ dz2): gradient w.r.t. the trunk output x_n (interior). Returns d(xin) incl. halo if need_dx."""
         c1, c2, c3 = self.STEM
+        # `red` is not None: dz already holds the merged gradient fold^-1(dz) + dz2 w.r.t. x_{i+1} and `red` the plane
+        # means of the InstanceNorm backward that consumes it -- both produced by the previous data-gradient kernel
+        red = None
         for i in reversed(range(self.n_blocks)):
             ya, sa, za, yb, sb = t[f"b{i}"]
             n1, n2 = self._block_names(i)
             xi = t[f"x{i}"]
-            gres = None
-            if dz2 is not None or dz.halo:
-                gres = ActBuf(yb.n, yb.h, yb.w, yb.c, zero=False)  # total gradient w.r.t. x_{i+1} (skip branch)
             dyb = ActBuf(yb.n, yb.h, yb.w, yb.c, zero=False)
-            ops.instnorm_bwd(dz, yb, sb, ACT_NONE, dyb, dz2=dz2, dres=gres)
-            skip = gres if gres is not None else dz
-            dza = self._conv_bwd(n2, za, dyb, grads, True, dx_halo=1)
+            if red is not None:
+                ops.instnorm_bwd_apply(dz, yb, sb, red, ACT_NONE, dyb)
+                skip = dz  # folded in place: its interior is the total gradient w.r.t. x_{i+1}
+            else:
+                gres = None
+                if dz2 is not None or dz.halo:
+                    gres = ActBuf(yb.n, yb.h, yb.w, yb.c, zero=False)  # total gradient w.r.t. x_{i+1} (skip branch)
+                ops.instnorm_bwd(dz, yb, sb, ACT_NONE, dyb, dz2=dz2, dres=gres)
+                skip = gres if gres is not None else dz
+            dza, red_a = self._conv_bwd(n2, za, dyb, grads, True, dx_halo=1, in_bwd=(ya, sa, ACT_RELU, None))
             dya = ActBuf(ya.n, ya.h, ya.w, ya.c, zero=False)
-            ops.instnorm_bwd(dza, ya, sa, ACT_RELU, dya)
-            dz = self._conv_bwd(n1, xi, dya, grads, True, dx_halo=1)
-            dz2 = skip
+            if red_a is not None:
+                ops.instnorm_bwd_apply(dza, ya, sa, red_a, ACT_RELU, dya)
+            else:
+                ops.instnorm_bwd(dza, ya, sa, ACT_RELU, dya)
+            # x_i = act(IN(y_prev)) + (residual input of block i-1): block i-1's second norm, or conv3's for block 0
+            y_prev, s_prev, act_prev = (t[f"b{i - 1}"][3], t[f"b{i - 1}"][4], ACT_NONE) if i > 0 else \
+                (t["y3"], t["s3"], ACT_RELU)
+            dz, red = self._conv_bwd(n1, xi, dya, grads, True, dx_halo=1, in_bwd=(y_prev, s_prev, act_prev, skip))
+            dz2 = None if red is not None else skip
         dy3 = ActBuf(t["y3"].n, t["y3"].h, t["y3"].w, t["y3"].c, zero=False)
-        ops.instnorm_bwd(dz, t["y3"], t["s3"], ACT_RELU, dy3, dz2=dz2)
+        if red is not None:
+            ops.instnorm_bwd_apply(dz, t["y3"], t["s3"], red, ACT_RELU, dy3)
+        else:
+            ops.instnorm_bwd(dz, t["y3"], t["s3"], ACT_RELU, dy3, dz2=dz2)
         dz2_ = self._conv_bwd(c3, t["z2"], dy3, grads, True)
         dy2 = ActBuf(t["y2"].n, t["y2"].h, t["y2"].w, t["y2"].c, zero=False)
         ops.instnorm_bwd(dz2_, t["y2"], t["s2"], ACT_RELU, dy2)

@@ -315,6 +315,50 @@ def instnorm_bwd(dz, y, stats, act, dy, dz2=None, dres=None):
          _stream())
 
 
+# Opt-in (FPG_INBWD_EPILOGUE=1): parity-green but slower today -- the epilogue's loads of y / the skip gradient queue
+# behind the TMA traffic of the main loop (150 us instead of 69 us per residual dgrad).
+INBWD_EPILOGUE = os.environ.get("FPG_INBWD_EPILOGUE", "0") == "1"
+
+
+def conv_dgrad_inbwd(dy, spec, dx, y, stats, act, add=None, force=False):
+    """dx (incl. halo) = conv_backward_data(dy, w) [+ add on the interior] where dx is the gradient w.r.t.
+    z = act(IN(y)); the reduction pass of that InstanceNorm's backward runs in the conv epilogue. Returns
+    red [n, c, 2] = {mean g', mean g' * zhat} for instnorm_bwd_apply, or None when this layer has no such epilogue
+    (nothing was launched: the caller runs conv_dgrad + instnorm_bwd)."""
+    lib = L.load()
+    if not (INBWD_EPILOGUE or force) or spec.g.stride != 1:
+        return None
+    rows = lib.fpg_conv_stats_rows(dy.ref(), spec.gref(), dx.ref(), 1)
+    if rows <= 0:
+        return None
+    ws = _stat_workspace(int(1.02 * dx.n * rows * dx.c * 2) + 4096, dx.t.device)
+    rows_out = C.c_int32(0)
+    ev = None
+    if PROFILE is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
+    rc = lib.fpg_conv2d_dgrad_inbwd(dy.ref(), _ptr(spec.w_dgrad), spec.gref(), dx.ref(), y.ref(), _ptr(stats), act,
+                                    add.ref() if add is not None else None, _ptr(ws), C.byref(rows_out), _stream())
+    if rc == 1:
+        return None
+    L.check(rc, "fpg_conv2d_dgrad_inbwd")
+    if ev is not None:
+        ev[1].record()
+        PROFILE.setdefault(_conv_key("dgrad", dx.n, dx.h, dx.w, spec), []).append(ev)
+    global LAUNCHES
+    LAUNCHES += 1
+    red = torch.empty(dx.n, dx.c, 2, dtype=torch.float32, device=dx.t.device)
+    _run("instnorm_bwd", 1, "fpg_instnorm_bwd_sums_finalize", _ptr(ws), rows_out.value, dx.n, dx.c, y.h * y.w,
+         _ptr(red), _stream())
+    return red
+
+
+def instnorm_bwd_apply(dz, y, stats, red, act, dy):
+    """the apply half of instnorm_bwd with the plane means `red` given (conv_dgrad_inbwd); dz is consumed (folded)"""
+    _run("instnorm_bwd", 2, "fpg_instnorm_bwd_apply", dz.ref(), y.ref(), _ptr(stats), _ptr(red), act, dy.ref(),
+         _stream())
+
+
 def batch_stats(y, stats, eps=1e-5):
     """Per-channel {mean, rstd} over the whole batch: InstanceNorm statistics of the batch viewed as one image."""
     flat = ActBuf(1, y.n * y.h, y.w, y.c, tensor=y.t, c0=y.c0, c_stride=y.c_stride)

@@ -103,6 +103,18 @@ typedef struct {
    * fpg_conv_stats_rows() gives the rows one launch contributes per image. */
   float* stat_partial;
   int32_t stat_rows_per_img, stat_row0;
+  /* Optional InstanceNorm-BACKWARD statistics (inbwd_y != NULL, needs stat_partial): the launch produces dz, the
+   * gradient w.r.t. a (reflect-haloed) activation z = act(IN(y)). Instead of {sum, sum of squares} the epilogue
+   * accumulates per column {sum g', sum g' * zhat}, g' = stored value * act'(zhat), zhat = (y[m] - mean) * rstd with m
+   * the interior pixel that output pixel mirrors (itself for interior pixels): the sums are linear in dz, so the halo
+   * needs no fold first. inbwd_add (optional) is added to the INTERIOR outputs before they are stored (the
+   * skip-connection gradient; it is read at its own interior when inbwd_add_halo > 0).
+   *   inbwd_y: bf16 [n][inbwd_h][inbwd_w][c], no halo; inbwd_stats: fp32 [n][c][2] = {mean, rstd};
+   *   inbwd_halo: halo of the output tensor (tile coordinates are padded coordinates). */
+  const void* inbwd_y;
+  const float* inbwd_stats;
+  const void* inbwd_add;
+  int32_t inbwd_h, inbwd_w, inbwd_c, inbwd_halo, inbwd_add_halo, inbwd_act;
 } fpg_igemm_fprop_desc;
 
 /* D_item[m, n] = sum_{pixel} X[pixel + xtap, xc + m] * Y[pixel + ytap, yc + n], split over pixel ranges,
@@ -233,6 +245,20 @@ int fpg_conv2d_dgrad_stats(const fpg_act* dy, const void* w_packed_t, const floa
 int fpg_instnorm_stats_finalize(const float* stat_partial, int32_t rows_per_img, int32_t n, int32_t c,
                                 int64_t count_per_img, float eps, float* stats, void* stream);
 
+/* Data gradient of a stride-1 convolution whose input was z = act(IN(y)) (+ reflect halo), fused with the reduction
+ * pass of that InstanceNorm's backward: dx (incl. halo) = conv_backward_data(dy, w) [+ add on the interior], and
+ * stat_partial receives the per-warp partials of {sum g', sum g' * zhat} (see fpg_igemm_fprop_desc.inbwd_*; sized
+ * as for fpg_conv2d_dgrad_stats). fpg_instnorm_bwd_sums_finalize turns them into red[(n*c + ch)*2] = {mean g',
+ * mean g' * zhat} over the h*w plane; fpg_instnorm_bwd_apply then folds dx's halo in place and applies
+ * dy = rstd * (g' - mean g' - zhat * mean g' zhat): together they equal fpg_instnorm_bwd(dz = dx, dz2 = add, ...)
+ * without its streamed reduction pass (the dominant elementwise cost of the residual trunk's backward).
+ * Returns FPG_ENOTSUP-style code 1 when the layer does not plan as one tiled launch (caller falls back). */
+int fpg_conv2d_dgrad_inbwd(const fpg_act* dy, const void* w_packed_t, const fpg_conv_geom* g, const fpg_act* dx,
+                           const fpg_act* y, const float* stats, int act, const fpg_act* add, float* stat_partial,
+                           int32_t* rows_per_img, void* stream);
+int fpg_instnorm_bwd_sums_finalize(const float* stat_partial, int32_t rows_per_img, int32_t n, int32_t c,
+                                   int64_t count_per_img, float* red, void* stream);
+
 /* dw = conv_backward_weight(x, dy): fp32 gradient written (not accumulated) in the reference parameter layout.
  *   dw[ko*dw_stride_k + ci*dw_stride_c + (r*S+s)] for ko < k_valid, ci < c_valid.
  * nn.Conv2d weight [K][C][R][S]: dw_stride_k = C*R*S, dw_stride_c = R*S;
@@ -308,6 +334,10 @@ int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_
  * be updated in place with the folded halo contributions. */
 int fpg_instnorm_bwd(const fpg_act* dz, const fpg_act* dz2, const fpg_act* y, const float* stats, int act,
                      const fpg_act* dy, const fpg_act* dres, float* scratch, int32_t* counters, void* stream);
+/* The apply half of fpg_instnorm_bwd with the reductions given: red[(n*c + ch)*2] = {mean g', mean g' * zhat}
+ * (fpg_instnorm_bwd_sums_finalize). dz (with any second branch already merged) is CONSUMED: its halo is folded in place. */
+int fpg_instnorm_bwd_apply(const fpg_act* dz, const fpg_act* y, const float* stats, const float* red, int act,
+                           const fpg_act* dy, void* stream);
 /* dx = fold(dz) * act'(z) for an activation without normalisation (PatchGAN model.0 LeakyReLU): z is the saved
  * activation output */
 int fpg_act_bwd(const fpg_act* dz, const fpg_act* z, int act, const fpg_act* dx, void* stream);

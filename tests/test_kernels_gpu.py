@@ -201,6 +201,53 @@ def test_instnorm_fwd_bwd(shape, halo, act):
     close_rms(out.to_nchw(), dres_ref, 0.02, 0.003, "halo_fold op")
 
 
+@pytest.mark.parametrize("act,with_add", [(1, False), (0, True), (1, True)])
+def test_dgrad_with_instnorm_backward_statistics(act, with_add):
+    """conv_dgrad_inbwd + instnorm_bwd_apply == autograd of conv(reflect_pad(act(IN(y)) [+ skip])) w.r.t. y and the
+    skip input: the reduction pass of the InstanceNorm backward runs in the data-gradient kernel's epilogue (halo
+    positions weighted with the statistics of the pixel they mirror, skip gradient merged on the interior)."""
+    from fpgan import ops
+    n, c, k, h = 2, 256, 256, 64
+    g = torch.Generator(device="cuda").manual_seed(11)
+    y = bf16r(torch.randn(n, c, h, h, device="cuda", generator=g) * 2 + 0.3).requires_grad_(True)
+    skip_in = bf16r(torch.randn(n, c, h, h, device="cuda", generator=g)).requires_grad_(True)
+    wt = bf16r(torch.randn(k, c, 3, 3, device="cuda", generator=g) / 48)
+    fn = {0: lambda t: t, 1: F.relu}[act]
+    x = fn(F.instance_norm(y, eps=1e-5)) + skip_in          # block input = act(IN(y)) + residual
+    out = F.conv2d(F.pad(x, (1,) * 4, "reflect"), wt)
+    dout = bf16r(torch.randn_like(out) * 0.1)
+    dskip_up = bf16r(torch.randn(n, c, h, h, device="cuda", generator=g) * 0.1)  # gradient arriving on the skip path
+    ups = [dout, dskip_up] if with_add else [dout]
+    outs = [out, x] if with_add else [out]
+    dy_ref, dskip_ref = torch.autograd.grad(outs, (y, skip_in), ups)
+
+    spec = ops.ConvSpec(3, 3, 1, 0, c, k)
+    spec.pack(wt.contiguous())
+    yb = ops.ActBuf.from_nchw(y.detach())
+    stats = torch.empty(n * c * 2, device="cuda")
+    ops.instnorm_stats(yb, stats)
+    dyb = ops.ActBuf.from_nchw(dout)
+    dx = ops.ActBuf(n, h, h, c, halo=1, zero=False)
+    add = None
+    if with_add:  # the skip gradient lives in the interior of a haloed buffer, as in the trunk backward
+        add = ops.ActBuf(n, h, h, c, halo=1)
+        add.t[:, 1:-1, 1:-1, :] = dskip_up.permute(0, 2, 3, 1)
+    red = ops.conv_dgrad_inbwd(dyb, spec, dx, yb, stats, act, add, force=True)  # opt-in path, tested regardless
+    assert red is not None, "the residual conv must plan the statistics epilogue"
+    dy = ops.ActBuf(n, h, h, c, zero=False)
+    ops.instnorm_bwd_apply(dx, yb, stats, red, act, dy)
+    close_rms(dy.to_nchw(), dy_ref, 0.03, 0.004, "fused instnorm bwd")
+    # dx's interior now holds the total gradient w.r.t. the block input = gradient w.r.t. the skip input
+    close_rms(dx.t[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2).float(), dskip_ref, 0.02, 0.003, "merged skip gradient")
+    # and the unfused path agrees
+    dx2 = ops.ActBuf(n, h, h, c, halo=1, zero=False)
+    ops.conv_dgrad(dyb, spec, dx2)
+    dy2 = ops.ActBuf(n, h, h, c, zero=False)
+    ops.instnorm_bwd(dx2, yb, stats, act, dy2, dz2=ops.ActBuf.from_nchw(dskip_up) if with_add else None)
+    # (one bf16 rounding of dz + skip here, two there)
+    close_rms(dy.to_nchw(), dy2.to_nchw(), 0.03, 0.004, "fused vs two-pass")
+
+
 def _blend_ref(content_pre, logits, image):
     """model_architectures.py:353-399 restated with torch ops"""
     content = torch.tanh(content_pre)
