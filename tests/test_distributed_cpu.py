@@ -55,6 +55,16 @@ def _worker(rank, world, port, results):
         red.finish()
         want = torch.arange(fp.flat.numel(), dtype=torch.float32) * sum(r + 1 for r in range(world))
         assert torch.equal(fp.grads.flat, want), "bucketed all-reduce must equal the sum over ranks"
+        # the default: one bucket = one all-reduce once every layer is done (FPG_DDP_BUCKET_MB=0)
+        one = _BucketReducer(fp)
+        assert one.bounds == [(0, fp.flat.numel())]
+        fp.grads.flat.copy_(torch.arange(fp.flat.numel(), dtype=torch.float32) * (rank + 1))
+        one.start()
+        for name, _ in reversed(fp.named):
+            one.ready(name)
+        assert len(one.works) == 1
+        one.finish()
+        assert torch.equal(fp.grads.flat, want)
         # a parameter whose gradient is never signalled (bias before an InstanceNorm) is still reduced by finish()
         fp.grads.flat.fill_(float(rank + 1))
         red.start()
