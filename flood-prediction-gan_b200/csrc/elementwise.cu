@@ -1442,14 +1442,15 @@ __global__ void blend_bwd_kernel(const float* __restrict__ dout_nchw, View dout_
 // single CTA: PatchGAN logits are a few thousand elements. logits fp32 NHWC, channel 0 valid.
 __global__ void mse_const_kernel(View logits, float target, float weight, float grad_scale, float* __restrict__ loss,
                                  View dlogits) {
-  const int64_t count = static_cast<int64_t>(logits.n) * logits.h * logits.w;
+  const int count = logits.n * logits.h * logits.w;  // a few thousand: 32-bit index math (64-bit divisions dominated)
   const float gcoef = dlogits.p != nullptr ? grad_scale * weight * 2.f / static_cast<float>(count) : 0.f;
   float acc = 0.f;
-  for (int64_t p = threadIdx.x; p < count; p += blockDim.x) {
-    const int px = static_cast<int>(p % logits.w);
-    const int64_t r = p / logits.w;
-    const int py = static_cast<int>(r % logits.h);
-    const int i = static_cast<int>(r / logits.h);
+#pragma unroll 4
+  for (int p = threadIdx.x; p < count; p += blockDim.x) {
+    const int px = p % logits.w;
+    const int r = p / logits.w;
+    const int py = r % logits.h;
+    const int i = r / logits.h;
     const float d = static_cast<const float*>(logits.p)[logits.at(i, py, px)] - target;
     acc += d * d;
     if (dlogits.p != nullptr) {
@@ -1999,6 +2000,7 @@ int fpg_blend_bwd(const float* dout_nchw, const fpg_act* dout_nhwc, int32_t dout
 int fpg_mse_const_loss(const fpg_act* logits, float target, float weight, float grad_scale, float* loss,
                        const fpg_act* dlogits, void* stream) {
   FPG_REQUIRE(logits && logits->fp32, "logits must be fp32");
+  FPG_REQUIRE(static_cast<int64_t>(logits->n) * logits->h * logits->w < (1ll << 30), "too many logits for one CTA");
   View gv;
   if (dlogits) {
     gv = view_of(dlogits);
