@@ -200,7 +200,10 @@ def conv_with_stats(x, spec, y, stats, transposed=False, eps=1e-5, batch=False):
         _run(_conv_key("fprop", y.n, y.h, y.w, spec), 1, "fpg_conv2d_fprop_stats", x.ref(), _ptr(spec.w_fprop), None,
              ACT_NONE, spec.gref(), y.ref(), _ptr(ws), _stream())
     n, per = (1, y.n * rows) if batch else (y.n, rows)
-    _run("instnorm_stats", 1, "fpg_instnorm_stats_finalize", _ptr(ws), per, n, y.c,
+    folds, left = 0, per  # row lists longer than 512 are first folded 256:1 (one launch per round)
+    while left > 512:
+        left, folds = (left + 255) // 256, folds + 1
+    _run("instnorm_stats", 1 + folds, "fpg_instnorm_stats_finalize", _ptr(ws), per, n, y.c,
          (y.n if batch else 1) * y.h * y.w, eps, _ptr(stats), _stream())
     return True
 
@@ -310,7 +313,7 @@ def instnorm_apply(y, stats, act, z, residual=None):
 
 
 def instnorm_bwd(dz, y, stats, act, dy, dz2=None, dres=None):
-    _run("instnorm_bwd", 2, "fpg_instnorm_bwd", dz.ref(), dz2.ref() if dz2 is not None else None, y.ref(), _ptr(stats),
+    _run("instnorm_bwd", 3 if dz.halo else 2, "fpg_instnorm_bwd", dz.ref(), dz2.ref() if dz2 is not None else None, y.ref(), _ptr(stats),
          act, dy.ref(), dres.ref() if dres is not None else None, _ptr(_scratch_for(y)), _ptr(_counters(y.t.device)),
          _stream())
 
@@ -355,7 +358,7 @@ def conv_dgrad_inbwd(dy, spec, dx, y, stats, act, add=None, force=False):
 
 def instnorm_bwd_apply(dz, y, stats, red, act, dy):
     """the apply half of instnorm_bwd with the plane means `red` given (conv_dgrad_inbwd); dz is consumed (folded)"""
-    _run("instnorm_bwd", 2, "fpg_instnorm_bwd_apply", dz.ref(), y.ref(), _ptr(stats), _ptr(red), act, dy.ref(),
+    _run("instnorm_bwd", 2 if dz.halo else 1, "fpg_instnorm_bwd_apply", dz.ref(), y.ref(), _ptr(stats), _ptr(red), act, dy.ref(),
          _stream())
 
 

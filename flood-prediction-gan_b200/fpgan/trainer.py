@@ -138,7 +138,7 @@ class PairedTrainer:
         self.loss_buf = torch.zeros(4, dtype=torch.float32, device=dev)
         self.g_reducer = _BucketReducer(self.gp, group=group) if world_size > 1 else None
         self.launches = 0
-        # CUDA-graph replay of the whole step (320 launches, the NCCL gradient reductions included): removes host
+        # CUDA-graph replay of the whole step (341 launches, the NCCL gradient reductions included): removes host
         # launch overhead and inter-kernel gaps (measured 5-6 % of the step). Captured NCCL work must be released before
         # the process group is destroyed (destroy_process_group() hangs otherwise): release_graphs(), also at exit.
         self.use_graph = os.environ.get("FPG_CUDA_GRAPH", "1") != "0" and (
