@@ -889,18 +889,19 @@ pack_batched_kernel(const fpg_pack_job* __restrict__ jobs, const int32_t* __rest
 }
 
 // stats[(i*c + ch)*2] = {mean, rstd} of image i from the epilogue partials [i][rows][c][2] (fixed summation order).
-// block = 64 channels x 4 row groups
-__global__ void __launch_bounds__(256)
+// block = 64 channels x 16 row groups (a launch has only n * c / 64 blocks: short per-thread row loops matter)
+constexpr int kFinalizeParts = 16;
+__global__ void __launch_bounds__(64 * kFinalizeParts)
 stats_finalize_kernel(const float* __restrict__ partial, int rows, int c, float inv_count, float eps, int sums_only,
                       float* __restrict__ stats) {
   const int i = blockIdx.x;
   const int ch = blockIdx.y * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
-  __shared__ float2 red[4][64];
+  __shared__ float2 red[kFinalizeParts][64];
   float a = 0.f, b = 0.f;
   if (ch < c) {
     const float2* p = reinterpret_cast<const float2*>(partial) + static_cast<int64_t>(i) * rows * c + ch;
 #pragma unroll 8
-    for (int r = part; r < rows; r += 4) {
+    for (int r = part; r < rows; r += kFinalizeParts) {
       const float2 v = __ldcg(p + static_cast<int64_t>(r) * c);
       a += v.x;
       b += v.y;
@@ -909,7 +910,7 @@ stats_finalize_kernel(const float* __restrict__ partial, int rows, int c, float 
   red[part][threadIdx.x & 63] = make_float2(a, b);
   __syncthreads();
   if (part == 0 && ch < c) {
-    for (int q = 1; q < 4; ++q) {
+    for (int q = 1; q < kFinalizeParts; ++q) {
       a += red[q][threadIdx.x].x;
       b += red[q][threadIdx.x].y;
     }
@@ -1119,8 +1120,8 @@ static int reduce_stat_rows(const float* stat_partial, int32_t rows_per_img, int
     spare += static_cast<int64_t>(n) * out_rows * c * 2;
     rows = out_rows;
   }
-  stats_finalize_kernel<<<dim3(n, (c + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(cur, rows, c, inv_count,
-                                                                                               eps, sums_only, out);
+  stats_finalize_kernel<<<dim3(n, (c + 63) / 64), 64 * kFinalizeParts, 0, static_cast<cudaStream_t>(stream)>>>(
+      cur, rows, c, inv_count, eps, sums_only, out);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

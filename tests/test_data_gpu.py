@@ -150,3 +150,24 @@ def test_loader_without_crop_or_resize():
                                           None, None, None, 0, version == "flipped")
         assert np.abs(x[k].cpu().numpy() - wx).max() <= TOL and np.abs(y[k].cpu().numpy() - wy).max() <= TOL
         assert names[k] == fname[:-8]
+
+
+def test_model_trains_from_the_device_loader():
+    """the loaders plug into Model.train_paired (reference model.py:598-658) as the reference's DataLoaders do: one epoch
+    over a small split, one loss entry per epoch, every batch consumed in DataLoader order"""
+    from models import data
+    from models import model as M
+    dec = _Decoder(128)
+    train, _, _ = data.create_flood_dataset("midwest-flooding", "best", "/data", "all", 128, 4, batch_size=4, decoder=dec,
+                                            metadata_csv=FIXTURE)
+    assert len(train) >= 3
+    m = M.Model(model="PairedAttention", topography="all", num_epochs=1, seed=47, resize=128, crop=4)
+    m.train_loader = train
+    m.train_paired()
+    for key, values in m.all_losses.items():
+        assert len(values) == 1 and np.isfinite(values[0]), (key, values)
+    # every (file, version) of the split was decoded exactly once per tensor, whatever the number of crops drawn
+    # (training images exist as an original and a flipped version: at most two decodes per file)
+    keys = {(f, v) for f, v, _ in train.dataset.data_files}
+    assert set(train.dataset.store.images) == keys
+    assert sum(dec.calls.values()) == 2 * len(keys) and max(dec.calls.values()) <= 2
