@@ -94,7 +94,11 @@ resize_rows_kernel(const float* __restrict__ src, float* __restrict__ tmp, const
   // flipped: logical pixel p is source pixel in_w - 1 - p, so the span is the mirrored contiguous range, read backwards
   const int s_lo = a.flip_w ? a.in_w - p_hi : p_lo;
   const float* row = src + (static_cast<int64_t>(y) * a.in_w + s_lo) * a.in_c;
-  for (int i = threadIdx.x; i < n_px * a.in_c; i += blockDim.x) span[i] = __ldg(row + i);
+  // 4-byte asynchronous copies (the span starts at a multiple of 36 bytes, not of 16): every thread's ~19 words are in
+  // flight together instead of one global-load latency per word
+  for (int i = threadIdx.x; i < n_px * a.in_c; i += blockDim.x)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(span + i)), "l"(row + i) : "memory");
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   float acc[NC];
   const int x = x_first + threadIdx.x;
@@ -136,12 +140,12 @@ __global__ void resize_cols_kernel(const float* __restrict__ tmp, float* __restr
   const int64_t pitch = static_cast<int64_t>(a.out_w) * a.channels;
   float acc = 0.f;
   int j = 0;
-  for (; j + 4 <= n; j += 4) {  // loads batched four at a time, summation order unchanged
-    float v[4];
+  for (; j + 8 <= n; j += 8) {  // loads batched eight at a time (one latency per batch), summation order unchanged
+    float v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = __ldg(col + (lo + j + u) * pitch);
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(col + (lo + j + u) * pitch);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const float t = __fmul_rn(v[u], w[j + u]);
       acc = (j + u) == 0 ? t : __fadd_rn(acc, t);
     }
