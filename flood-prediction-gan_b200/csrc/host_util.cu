@@ -1,3 +1,5 @@
+#include <stdlib.h>
+
 #include "host_util.h"
 
 #include <string.h>
@@ -89,6 +91,11 @@ int sm_count_cached() {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
     (void)cudaGetLastError();
     return -1;
+  }
+  // FPG_SM_BUDGET=<n>: size every grid for n SMs (experiments with several concurrent streams, tools/exp_sm_split.py)
+  if (const char* budget = getenv("FPG_SM_BUDGET")) {
+    const int b = atoi(budget);
+    if (b > 0 && b < n) n = b;
   }
   cached = n;
   return n;
