@@ -1769,8 +1769,9 @@ int fpg_instnorm_stats(const fpg_act* y, float eps, float* stats, float* scratch
       attr_set = true;
     }
     const int splits = stat_splits(y, 2 * sms);
-    in_stats_ring_kernel<<<dim3(splits, y->n), kRingThreads, smem, FPG_ST(stream)>>>(
-        view_of(y), scratch, stats, counters, 1.f / static_cast<float>(y->h * y->w), eps);
+    FPG_CUDA_CHECK(launch_persistent(in_stats_ring_kernel, dim3(splits, y->n), dim3(kRingThreads), smem,
+                                     FPG_ST(stream),
+                                     view_of(y), scratch, stats, counters, 1.f / static_cast<float>(y->h * y->w), eps));
     FPG_CUDA_CHECK(cudaGetLastError());
     return 0;
   }
@@ -1800,9 +1801,10 @@ int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_
       attr_set = true;
     }
     const RingGeom gm = ring_geom(y, stages, 2 * sms);
-    in_apply_ring_kernel<<<dim3(gm.ctas_per_img, y->n), kRingThreads, smem, FPG_ST(stream)>>>(
-        view_of(y), stats, act, residual != nullptr, view_of(z), ring_tensor(y),
-        residual ? ring_tensor(residual) : ring_tensor(y), gm);
+    FPG_CUDA_CHECK(launch_persistent(in_apply_ring_kernel, dim3(gm.ctas_per_img, y->n), dim3(kRingThreads), smem,
+                                     FPG_ST(stream),
+                                     view_of(y), stats, act, residual != nullptr, view_of(z), ring_tensor(y),
+                                     residual ? ring_tensor(residual) : ring_tensor(y), gm));
     FPG_CUDA_CHECK(cudaGetLastError());
     return 0;
   }
@@ -1881,12 +1883,14 @@ int fpg_instnorm_bwd(const fpg_act* dz, const fpg_act* dz2, const fpg_act* y, co
       const int64_t total = static_cast<int64_t>(dz->n) * band_px * (dz->c / 8);
       halo_fold_inplace_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(dz), band_px);
     }
-    in_bwd_reduce_ring_kernel<<<dim3(gm.ctas_per_img, y->n), kRingThreads, smem, FPG_ST(stream)>>>(
-        view_of(dz), v2, dz2 != nullptr, view_of(y), stats, act, vr, dres != nullptr, scratch, red, counters, inv_hw,
-        t_dz, t_y, t_dz2, gm, 1);
-    in_bwd_apply_ring_kernel<<<dim3(gm.ctas_per_img, y->n), kRingThreads, smem, FPG_ST(stream)>>>(
-        view_of(dz), v2, dz2 != nullptr, dres != nullptr, view_of(y), stats, red, act, view_of(dy),
-        dres ? ring_tensor(dres) : t_dz, t_y, t_dz2, gm, 1);
+    FPG_CUDA_CHECK(launch_persistent(in_bwd_reduce_ring_kernel, dim3(gm.ctas_per_img, y->n), dim3(kRingThreads), smem,
+                                     FPG_ST(stream),
+                                     view_of(dz), v2, dz2 != nullptr, view_of(y), stats, act, vr, dres != nullptr, scratch, red, counters, inv_hw,
+                                     t_dz, t_y, t_dz2, gm, 1));
+    FPG_CUDA_CHECK(launch_persistent(in_bwd_apply_ring_kernel, dim3(gm.ctas_per_img, y->n), dim3(kRingThreads), smem,
+                                     FPG_ST(stream),
+                                     view_of(dz), v2, dz2 != nullptr, dres != nullptr, view_of(y), stats, red, act, view_of(dy),
+                                     dres ? ring_tensor(dres) : t_dz, t_y, t_dz2, gm, 1));
     FPG_CUDA_CHECK(cudaGetLastError());
     return 0;
   }
@@ -1924,8 +1928,9 @@ int fpg_instnorm_bwd_apply(const fpg_act* dz, const fpg_act* y, const float* sta
     const int64_t total = static_cast<int64_t>(dz->n) * band_px * (dz->c / 8);
     halo_fold_inplace_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(dz), band_px);
   }
-  in_bwd_apply_ring_kernel<<<dim3(gm.ctas_per_img, y->n), kRingThreads, smem, FPG_ST(stream)>>>(
-      view_of(dz), view_of(dz), 0, 0, view_of(y), stats, red, act, view_of(dy), t_dz, t_y, t_y, gm, 1);
+  FPG_CUDA_CHECK(launch_persistent(in_bwd_apply_ring_kernel, dim3(gm.ctas_per_img, y->n), dim3(kRingThreads), smem,
+                                   FPG_ST(stream),
+                                   view_of(dz), view_of(dz), 0, 0, view_of(y), stats, red, act, view_of(dy), t_dz, t_y, t_y, gm, 1));
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

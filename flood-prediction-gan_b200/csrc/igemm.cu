@@ -1235,7 +1235,8 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
   do {                                                                                                           \
     FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_fprop_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                         static_cast<int>(smem)));                                                \
-    igemm_fprop_kernel<CB><<<grid, kThreads, smem, st>>>(amap, bmap, amap1, args);                                      \
+    FPG_CUDA_CHECK(launch_persistent(igemm_fprop_kernel<CB>, dim3(grid), dim3(kThreads), smem, st, amap, bmap, amap1, \
+                                     args));                                                                     \
   } while (0)
   if (d->cblk == 64) {
     FPG_LAUNCH_FPROP(64);
@@ -1353,7 +1354,7 @@ extern "C" int fpg_igemm_wgrad_launch(const fpg_igemm_wgrad_desc* d, void* strea
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
-  igemm_wgrad_kernel<<<grid, kThreads, smem, st>>>(xmap, ymap, args);
+  FPG_CUDA_CHECK(launch_persistent(igemm_wgrad_kernel, dim3(grid), dim3(kThreads), smem, st, xmap, ymap, args));
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

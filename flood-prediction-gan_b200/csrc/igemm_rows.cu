@@ -341,7 +341,8 @@ extern "C" int fpg_igemm_rows_launch(const fpg_igemm_rows_desc* d, void* stream)
   do {                                                                                                         \
     FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_rows_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                         static_cast<int>(smem)));                                              \
-    igemm_rows_kernel<CB><<<grid, kRowsThreads, smem, st>>>(amap, bmap, args);                                 \
+    FPG_CUDA_CHECK(launch_persistent(igemm_rows_kernel<CB>, dim3(grid), dim3(kRowsThreads), smem, st, amap, bmap, \
+                                     args));                                                                   \
   } while (0)
   if (d->cblk == 64) {
     FPG_LAUNCH_ROWS(64);

@@ -34,6 +34,10 @@ def one_round():
 for _ in range(5):  # eager calls, graph capture, first replays
     one_round()
     torch.cuda.synchronize()
+offset = int(os.environ.get("FPG_EXP_OFFSET_CYCLES", "0"))  # phase offset of the second stream (lockstep breaker)
+if offset and N > 1:
+    with torch.cuda.stream(streams[1]):
+        torch.cuda._sleep(offset)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
 for _ in range(steps):
