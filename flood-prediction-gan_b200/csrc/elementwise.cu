@@ -1800,7 +1800,10 @@ int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_
                                           static_cast<int>(smem)));
       attr_set = true;
     }
-    const RingGeom gm = ring_geom(y, stages, 2 * sms);
+    // two CTAs per SM; with an SM budget (experiments) one CTA per budgeted SM so that the grid does not spread over
+    // the SMs of another stream
+    static const bool budgeted = getenv("FPG_SM_BUDGET") != nullptr;
+    const RingGeom gm = ring_geom(y, stages, budgeted ? sms : 2 * sms);
     FPG_CUDA_CHECK(launch_persistent(in_apply_ring_kernel, dim3(gm.ctas_per_img, y->n), dim3(kRingThreads), smem,
                                      FPG_ST(stream),
                                      view_of(y), stats, act, residual != nullptr, view_of(z), ring_tensor(y),
