@@ -1,5 +1,7 @@
 """GPU parity tests of the individual sm_100a kernels, called through the C ABI (fpgan.ops -> libfpg_b200.so),
 against plain fp32 PyTorch on the same (bf16-rounded) inputs."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -233,6 +235,8 @@ def test_dgrad_with_instnorm_backward_statistics(act, with_add):
         add = ops.ActBuf(n, h, h, c, halo=1)
         add.t[:, 1:-1, 1:-1, :] = dskip_up.permute(0, 2, 3, 1)
     red = ops.conv_dgrad_inbwd(dyb, spec, dx, yb, stats, act, add, force=True)  # opt-in path, tested regardless
+    if red is None and os.environ.get("FPG_DISABLE_TILE_REGIONS"):
+        pytest.skip("the single-tile-shape plan of the haloed gradient has no statistics epilogue (caller falls back)")
     assert red is not None, "the residual conv must plan the statistics epilogue"
     dy = ops.ActBuf(n, h, h, c, zero=False)
     ops.instnorm_bwd_apply(dx, yb, stats, red, act, dy)
