@@ -1,45 +1,34 @@
-"""Evaluation entry point with the reference's flag surface (reference: evaluate.py:6-64). The generator forward and
-the flood-mask thresholding run on the native kernels; plotting and torchmetrics-based image-quality metrics are out
-of scope of this repository and raise NotImplementedError when requested."""
-import argparse
+"""Evaluation entry point with the reference's flag surface (reference: evaluate.py:6-64). --calculate_metrics runs
+generator inference, the segmentation U-Net, the bit-exact flood masks / confusion metrics and PSNR / SSIM / MS-SSIM on
+the native kernels (LPIPS is NaN: it needs downloaded AlexNet weights); the plotting flags are accepted but plotting is
+out of scope of this repository and raises NotImplementedError."""
 import os
 
 from models import model
+from train import REQUIRED, build_parser
 
-if __name__ == "__main__":
-    ap = argparse.ArgumentParser(description="Evaluate a trained model (B200-native implementation)")
-    ap.add_argument("--model", required=True)
-    ap.add_argument("--dataset_subset", default="all")
-    ap.add_argument("--dataset_dem", required=True)
-    ap.add_argument("--use_test_data", action="store_true", default=False)
-    ap.add_argument("--data_path", required=True)
-    ap.add_argument("--resize", type=int, default=None)
-    ap.add_argument("--crop", type=int, default=None)
-    ap.add_argument("--crop_index", type=int, default=0)
-    ap.add_argument("--topography", default=None)
-    ap.add_argument("--pretrained_model_path", required=True)
-    ap.add_argument("--plot_losses", action="store_true", default=False)
-    ap.add_argument("--plot_sample_images", action="store_true", default=False)
-    ap.add_argument("--num_images", type=int, default=5)
-    ap.add_argument("--seed", type=int, default=47)
-    ap.add_argument("--image_name", default=None)
-    ap.add_argument("--plot_single_image", default=None)
-    ap.add_argument("--plot_image_set", action="store_true", default=False)
-    ap.add_argument("--calculate_metrics", action="store_true", default=False)
-    ap.add_argument("--segmentation_model_path", default=None)
-    args = ap.parse_args()
-    args.model = args.model.lower()
+FLAGS = (("model", str, REQUIRED), ("dataset_subset", str, "all"), ("dataset_dem", str, REQUIRED),
+         ("use_test_data", None, False), ("data_path", str, REQUIRED), ("resize", int, None), ("crop", int, None),
+         ("crop_index", int, 0), ("topography", str, None), ("pretrained_model_path", str, REQUIRED),
+         ("plot_losses", None, False), ("plot_sample_images", None, False), ("num_images", int, 5), ("seed", int, 47),
+         ("image_name", str, None), ("plot_single_image", str, None), ("plot_image_set", None, False),
+         ("calculate_metrics", None, False), ("segmentation_model_path", str, None))
+
+
+def main():
+    args = build_parser("B200-native evaluation of a trained model", FLAGS).parse_args()
     if not os.path.isfile(args.pretrained_model_path):
         raise FileNotFoundError("Saved model not found. Check the path to the model.")
-    evaluate_model = model.Model(model=args.model, dataset_subset=args.dataset_subset, dataset_dem=args.dataset_dem,
-                                 data_path=args.data_path, resize=args.resize, crop=args.crop,
-                                 load_pretrained_model=True, pretrained_model_path=args.pretrained_model_path,
-                                 training_model=False, seed=args.seed, topography=args.topography, verbose=True)
+    net = model.Model(model=args.model.lower(), dataset_subset=args.dataset_subset, dataset_dem=args.dataset_dem,
+                      data_path=args.data_path, resize=args.resize, crop=args.crop, load_pretrained_model=True,
+                      pretrained_model_path=args.pretrained_model_path, training_model=False, seed=args.seed,
+                      topography=args.topography, verbose=True)
     if args.plot_losses or args.plot_sample_images or args.plot_single_image or args.plot_image_set:
         raise NotImplementedError("plotting is outside the accelerated hot path (DESIGN.md section 8)")
     if args.calculate_metrics:
-        # flood metrics natively (U-Net inference, bit-exact masks, confusion counts); the torchmetrics image-quality
-        # columns are NaN (un-vendored dependency)
-        evaluate_model.calculate_metrics(use_test_data=args.use_test_data, seg_model_path=args.segmentation_model_path)
-    print(f"loaded {evaluate_model.prettify_model_name()} (epoch {evaluate_model.current_epoch - 1}); "
-          f"generator on {evaluate_model.device}")
+        net.calculate_metrics(use_test_data=args.use_test_data, seg_model_path=args.segmentation_model_path)
+    print(f"loaded {net.prettify_model_name()} (epoch {net.current_epoch - 1}); generator on {net.device}")
+
+
+if __name__ == "__main__":
+    main()
