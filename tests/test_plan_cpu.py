@@ -195,7 +195,8 @@ WGRAD_CASES = [
 
 
 @pytest.mark.parametrize("case", [(2, 16, 16, 256, 256, 256, 256, 3, 1, 0, 1),  # residual conv of the 256x256 step
-                                  (1, 8, 8, 256, 256, 256, 256, 2, 1, 0, 0)])    # even tap count
+                                  (1, 8, 8, 256, 256, 256, 256, 2, 1, 0, 0),     # even tap count
+                                  (1, 11, 11, 256, 256, 256, 256, 4, 1, 1, 0)])  # 16 taps, zero pad, ragged k tiles
 def test_wgrad_pair_plan_matches_autograd(fpglib, case, monkeypatch):
     """256 x 256-channel layers plan the CTA-pair kernel (an item = two taps, D[256, 2 x 256])."""
     monkeypatch.delenv("FPG_WGRAD_SHIFT_WIDE", raising=False)
