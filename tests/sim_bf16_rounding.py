@@ -1,6 +1,6 @@
 """CPU simulation of where bf16 rounding enters the generator forward (weights, conv inputs, conv outputs,
 residual stream) using the oracle's graph. Shows that the measured 2.25e-2 output deviation of the kernels is the
-bf16 floor, and what each rounding site contributes. Not part of the product."""
+bf16 floor, and what each rounding site contributes. Not part of the product (it lives under tests/ because it executes the oracle)."""
 import os
 import sys
 

@@ -6,7 +6,7 @@ Tolerances (bf16 bound of north_star; measured values are printed with `-s`):
   * forward tensors (generator output, attention mask, PatchGAN logits): RMS error relative to the RMS of the oracle
     tensor < OUT_TOL = 3e-2; measured 2.25e-2. An element-wise rtol is meaningless for values near zero. A CPU
     simulation that rounds weights, conv inputs, conv outputs and the residual stream to bf16 inside the oracle gives
-    2.27e-2 (tools/sim_bf16_rounding.py), i.e. the kernels sit exactly at the bf16 floor; the reference itself is
+    2.27e-2 (tests/sim_bf16_rounding.py), i.e. the kernels sit exactly at the bf16 floor; the reference itself is
     2.4e-2 away from its fp32 result under torch.autocast(bf16).
   * parameter / input gradients: RMS-relative error < GRAD_TOL = 0.3. A forward deviation eps flips the ReLU /
     LeakyReLU mask of a fraction ~0.8*eps of the elements (those whose pre-activation lies within the noise of zero);
