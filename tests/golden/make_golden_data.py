@@ -113,6 +113,20 @@ def split_cases(ref_data, fixture):
     return out
 
 
+def history_buffer_case():
+    """get_buffer_image (models/model.py:275-294) over 160 generated images, Python RNG seeded with 5: which image each
+    call returns and what the 50-entry buffer holds at the end (images are tagged with their index)"""
+    import random
+    import make_golden
+    ref_model = make_golden.import_reference()
+    buf, returned = [], []
+    random.seed(5)
+    for i in range(160):
+        out = ref_model.Model.get_buffer_image(None, torch.full((1, 1, 2, 2), float(i)), buf)
+        returned.append(int(out.flatten()[0].item()))
+    return {"py_seed": 5, "n": 160, "returned": returned, "final_buffer": [int(b.flatten()[0].item()) for b in buf]}
+
+
 def main():
     fixture = os.path.join(HERE, "dataset_split_fixture.csv")
     write_fixture_csv(fixture)
@@ -120,6 +134,7 @@ def main():
     import torchvision
     vectors = {"torch": torch.__version__, "torchvision": torchvision.__version__,
                "transforms": transform_cases(ref_utils), "splits": split_cases(ref_data, fixture)}
+    vectors["history_buffer"] = history_buffer_case()  # last: importing the reference's model module changes the cwd
     with open(os.path.join(HERE, "data_vectors.json"), "w") as f:
         json.dump(vectors, f)
     print("wrote", len(vectors["transforms"]), "transform cases,", len(vectors["splits"]), "split cases")

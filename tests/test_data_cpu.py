@@ -119,3 +119,28 @@ def test_sharded_loader_partitions_the_global_batch():
 
 def test_create_flood_dataset_without_data_returns_empty_loaders():
     assert data.create_flood_dataset("all", "best", None, "all", 256, None) == ([], [], [])
+
+
+def test_history_buffer_matches_reference():
+    """get_buffer_image (reference model.py:275-294) beyond the 50-entry fill phase: the product's method (global Python
+    RNG, as the reference) and the oracle's restatement return the reference's images and end with its buffer"""
+    import random
+
+    from oracle import gan_oracle as GO
+    from models import model as M
+    gold = VECTORS["history_buffer"]
+
+    def run(fn):
+        buf, out = [], []
+        for i in range(gold["n"]):
+            out.append(int(fn(torch.full((1, 1, 2, 2), float(i)), buf).flatten()[0].item()))
+        return out, [int(b.flatten()[0].item()) for b in buf]
+
+    random.seed(gold["py_seed"])
+    got, final = run(lambda img, buf: M.Model.get_buffer_image(None, img, buf))
+    assert got == gold["returned"] and final == gold["final_buffer"]
+    tr = GO.CycleTrainer.__new__(GO.CycleTrainer)
+    tr.rng = random.Random(gold["py_seed"])
+    got, final = run(tr._buffer)
+    assert got == gold["returned"] and final == gold["final_buffer"]
+    assert any(r != i for i, r in enumerate(gold["returned"]))  # the replacement branch was exercised
