@@ -127,6 +127,53 @@ def history_buffer_case():
     return {"py_seed": 5, "n": 160, "returned": returned, "final_buffer": [int(b.flatten()[0].item()) for b in buf]}
 
 
+def bare_model(model_cls, **attrs):
+    """an object with the given attributes on which the (unbound) helper methods of a Model class can be called without
+    constructing networks"""
+    class Bare:
+        pass
+    obj = Bare()
+    for k, v in attrs.items():
+        setattr(obj, k, v)
+    obj.prettify_model_name = types.MethodType(model_cls.prettify_model_name, obj)
+    return obj
+
+
+PATH_CASES = [dict(model="pairedattention", model_is_cycle=False, add_identity_loss=False, data_path="/d", current_epoch=7,
+                   training_model=True, topography="all", dataset_subset="usa", dataset_dem="best", resize=512, crop=4,
+                   save_type="model", info=""),
+              dict(model="cyclegan", model_is_cycle=True, add_identity_loss=True, data_path="C:/data", current_epoch=3,
+                   training_model=False, topography=None, dataset_subset="all", dataset_dem="same", resize=None, crop=None,
+                   save_type="metric", info="val"),
+              dict(model="pix2pix", model_is_cycle=False, add_identity_loss=False, data_path="rel", current_epoch=1,
+                   training_model=True, topography="dem", dataset_subset="india", dataset_dem="best", resize=256, crop=None,
+                   save_type="image", info="sample_3")]
+
+
+def mask_date(path):
+    import re
+    return re.sub(r"date\d{4}-\d{2}-\d{2}-\d{2}-\d{2}-\d{2}", "date<T>", path)
+
+
+def model_helper_cases():
+    """lambda_rule, initialise_loss_storage, create_path (date masked) of the reference's Model (model.py:175-260)"""
+    import make_golden
+    cls = make_golden.import_reference().Model
+    out = {"lambda_rule": {}, "loss_keys": [], "paths": []}
+    for n in (1, 2, 7, 200):
+        out["lambda_rule"][str(n)] = [cls.lambda_rule(bare_model(cls, num_epochs=n), e) for e in range(n + 2)]
+    for cycle in (False, True):
+        for identity in (False, True):
+            for overall in (False, True):
+                keys = list(cls.initialise_loss_storage(bare_model(cls, model_is_cycle=cycle, add_identity_loss=identity),
+                                                        overall).keys())
+                out["loss_keys"].append({"cycle": cycle, "identity": identity, "overall": overall, "keys": keys})
+    for case in PATH_CASES:
+        attrs = {k: v for k, v in case.items() if k not in ("save_type", "info")}
+        out["paths"].append(mask_date(cls.create_path(bare_model(cls, **attrs), case["save_type"], case["info"])))
+    return out
+
+
 def main():
     fixture = os.path.join(HERE, "dataset_split_fixture.csv")
     write_fixture_csv(fixture)
@@ -135,6 +182,7 @@ def main():
     vectors = {"torch": torch.__version__, "torchvision": torchvision.__version__,
                "transforms": transform_cases(ref_utils), "splits": split_cases(ref_data, fixture)}
     vectors["history_buffer"] = history_buffer_case()  # last: importing the reference's model module changes the cwd
+    vectors["model_helpers"] = model_helper_cases()
     with open(os.path.join(HERE, "data_vectors.json"), "w") as f:
         json.dump(vectors, f)
     print("wrote", len(vectors["transforms"]), "transform cases,", len(vectors["splits"]), "split cases")

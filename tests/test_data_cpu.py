@@ -144,3 +144,23 @@ def test_history_buffer_matches_reference():
     got, final = run(tr._buffer)
     assert got == gold["returned"] and final == gold["final_buffer"]
     assert any(r != i for i, r in enumerate(gold["returned"]))  # the replacement branch was exercised
+
+
+def test_model_helpers_match_reference():
+    """lambda_rule (learning-rate schedule), initialise_loss_storage (loss-dictionary keys and order) and create_path
+    (artefact naming, date masked) of Model against the reference's own methods (model.py:175-260); the oracle's
+    lambda_rule too"""
+    from oracle import gan_oracle as GO
+    from models import model as M
+    gold = VECTORS["model_helpers"]
+    for n, want in gold["lambda_rule"].items():
+        got = [M.Model.lambda_rule(G.bare_model(M.Model, num_epochs=int(n)), e) for e in range(int(n) + 2)]
+        assert got == want
+        assert [GO.lambda_rule(e, int(n)) for e in range(int(n) + 2)] == want
+    for rec in gold["loss_keys"]:
+        bare = G.bare_model(M.Model, model_is_cycle=rec["cycle"], add_identity_loss=rec["identity"])
+        assert list(M.Model.initialise_loss_storage(bare, rec["overall"]).keys()) == rec["keys"]
+    for case, want in zip(G.PATH_CASES, gold["paths"]):
+        attrs = {k: v for k, v in case.items() if k not in ("save_type", "info")}
+        got = M.Model.create_path(G.bare_model(M.Model, **attrs), case["save_type"], case["info"])
+        assert G.mask_date(got) == want
