@@ -259,6 +259,13 @@ class Model:
                 "F1_No_Flood": div(2 * tn, 2 * tn + fn + fp), "Precision_No_Flood": div(tn, tn + fn),
                 "Recall_No_Flood": div(tn, tn + fp)}
 
+    @staticmethod
+    def metrics_csv_text(results):
+        """the text the reference's `metrics_df.to_csv()` writes (model.py:419-421): unnamed index column, one row
+        labelled 1, NaN as an empty field"""
+        cells = ["" if v != v else str(v) for v in results.values()]
+        return "," + ",".join(results.keys()) + "\n1," + ",".join(cells) + "\n"
+
     def load_segmentation_model(self, seg_model_path=None):
         """SegmentationModel(train=False).model (segmentation_model.py:55-61): U-Net initialised like the reference
         and, if a checkpoint is given, loaded from its "model" entry. Never switched to eval mode (the reference
@@ -317,7 +324,7 @@ class Model:
             path = self.create_path("metric")
             os.makedirs(os.path.dirname(path), exist_ok=True)
             with open(path, "w") as f:
-                f.write(",".join(results.keys()) + "\n" + ",".join(str(v) for v in results.values()) + "\n")
+                f.write(self.metrics_csv_text(results))
         return results
 
     # ------------------------------------------------------------------------------------------ training

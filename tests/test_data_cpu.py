@@ -164,3 +164,17 @@ def test_model_helpers_match_reference():
         attrs = {k: v for k, v in case.items() if k not in ("save_type", "info")}
         got = M.Model.create_path(G.bare_model(M.Model, **attrs), case["save_type"], case["info"])
         assert G.mask_date(got) == want
+
+
+def test_metrics_csv_is_the_reference_dataframe_csv():
+    """calculate_metrics writes what the reference's pandas code writes (model.py:419-421)"""
+    import io
+
+    import pandas as pd
+    from models import model as M
+    results = {"PSNR": 20.476618475778388, "SSIM": 0.9455338178579847, "MS-SSIM": float("nan"), "LPIPS": float("nan"),
+               "MSE": 0.25, "Accuracy": 0.75, "F1_Flood": 1 / 3, "Inference": 0.012345678901234}
+    frame = pd.DataFrame([(k, np.mean([v])) for k, v in results.items()]).set_index(0).transpose()
+    buf = io.StringIO()
+    frame.to_csv(buf)
+    assert M.Model.metrics_csv_text(results) == buf.getvalue()
