@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -264,6 +265,29 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+}
+// fp16 pairs (FPG_DT_FP16 tensors: pre-normalisation conv outputs, the residual skip stream). Stores saturate to the
+// largest finite fp16 instead of producing inf.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+  __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  __half2 v = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(v);
+}
+// element-type dispatch on a kernel-uniform flag (dt = FPG_DT_BF16 or FPG_DT_FP16; both are 2 bytes per element)
+__device__ __forceinline__ uint32_t pack_2x16(float lo, float hi, int dt) {
+  return dt == 2 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack_2x16(uint32_t u, int dt) {
+  return dt == 2 ? unpack_f16x2(u) : unpack_bf16x2(u);
+}
+__device__ __forceinline__ float round_16(float v, int dt) {
+  return dt == 2 ? __half2float(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)))
+                 : __bfloat162float(__float2bfloat16(v));
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

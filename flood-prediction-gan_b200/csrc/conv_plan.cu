@@ -78,7 +78,7 @@ static fpg_tap fwd_tap(int r, int s, int stride, int pad, int cs) {
 static void out_view_of(const fpg_act* y, int with_halo, fpg_out_view* o) {
   const int64_t wp = y->w + 2 * y->halo, hp = y->h + 2 * y->halo, cs = y->c_stride;
   const int64_t org = with_halo ? 0 : (static_cast<int64_t>(y->halo) * wp + y->halo) * cs;
-  o->base = y->fp32 ? static_cast<void*>(static_cast<float*>(y->data) + org)
+  o->base = y->fp32 == FPG_DT_FP32 ? static_cast<void*>(static_cast<float*>(y->data) + org)
                     : static_cast<void*>(static_cast<__nv_bfloat16*>(y->data) + org);
   o->stride_n = hp * wp * cs;
   o->stride_y = wp * cs;
@@ -192,6 +192,7 @@ static int padded_taps(int ntaps, int c, int cblk) {
 static int plan_fprop(const fpg_act* x, const void* w, const float* bias, int act, const fpg_conv_geom* g,
                       const fpg_act* y, int sms, fpg_igemm_fprop_desc* d) {
   FPG_REQUIRE(x && g && y && d, "null argument");
+  FPG_REQUIRE(x->fp32 == FPG_DT_BF16, "conv input must be bf16 (the tensor-core operand type)");
   FPG_REQUIRE(g->stride == 1 || g->stride == 2, "stride %d", g->stride);
   FPG_REQUIRE(x->halo == 0 || g->pad == 0, "input halo %d with zero pad %d", x->halo, g->pad);
   FPG_REQUIRE(x->c == g->c_in && y->c == g->c_out, "channels x %d/%d y %d/%d", x->c, g->c_in, y->c, g->c_out);
@@ -254,6 +255,7 @@ static void dgrad_class_layout(const fpg_conv_geom* g, int64_t* k_of, int64_t* o
 static int plan_dgrad(const fpg_act* dy, const void* wt, const float* bias, int act, const fpg_conv_geom* g,
                       const fpg_act* dx, int sms, fpg_igemm_fprop_desc* descs, int* n_descs) {
   FPG_REQUIRE(dy && g && dx && descs && n_descs, "null argument");
+  FPG_REQUIRE(dy->fp32 == FPG_DT_BF16, "dgrad input must be bf16 (the tensor-core operand type)");
   FPG_REQUIRE(g->stride == 1 || g->stride == 2, "stride %d", g->stride);
   FPG_REQUIRE(dy->halo == 0, "dy must not have a halo");
   FPG_REQUIRE(dx->halo == 0 || g->pad == 0, "dx halo %d with zero pad %d", dx->halo, g->pad);
@@ -346,6 +348,7 @@ static int plan_dgrad(const fpg_act* dy, const void* wt, const float* bias, int 
 static int plan_rows(const fpg_act* a, const void* w, const float* bias, int act, const fpg_conv_geom* g,
                      const fpg_act* out, int dgrad, int sms, fpg_igemm_rows_desc* d) {
   FPG_REQUIRE(a && g && out && d, "null argument");
+  FPG_REQUIRE(a->fp32 == FPG_DT_BF16, "conv input must be bf16 (the tensor-core operand type)");
   if (getenv("FPG_DISABLE_ROWS") != nullptr) return 1;
   if (g->stride != 1 || g->r * g->s <= 1 || g->r * g->s > FPG_MAX_TAPS) return 1;
   const int ca = dgrad ? g->c_out : g->c_in;     // channels of the gathered operand
@@ -441,6 +444,7 @@ static bool rows_of_64_ok(int w) { return 10 * w >= 7 * 64 * ceil_div(w, 64); } 
 
 static int plan_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g, int sms, fpg_igemm_wgrad_desc* d) {
   FPG_REQUIRE(x && dy && g && d, "null argument");
+  FPG_REQUIRE(x->fp32 == FPG_DT_BF16 && dy->fp32 == FPG_DT_BF16, "wgrad operands must be bf16");
   FPG_REQUIRE(g->stride == 1 || g->stride == 2, "stride %d", g->stride);
   FPG_REQUIRE(dy->halo == 0, "dy must not have a halo");
   FPG_REQUIRE(x->halo == 0 || g->pad == 0, "input halo %d with zero pad %d", x->halo, g->pad);
@@ -1073,7 +1077,7 @@ int fpg_conv2d_dgrad_inbwd(const fpg_act* dy, const void* w_packed_t, const fpg_
                            const fpg_act* y, const float* stats, int act, const fpg_act* add, float* stat_partial,
                            int32_t* rows_per_img, void* stream) {
   FPG_REQUIRE(dy && w_packed_t && g && dx && y && stats && stat_partial && rows_per_img, "null argument");
-  FPG_REQUIRE(!y->fp32 && y->halo == 0 && y->c == y->c_stride && y->h == dx->h && y->w == dx->w && y->c == dx->c &&
+  FPG_REQUIRE(y->fp32 != FPG_DT_FP32 && y->halo == 0 && y->c == y->c_stride && y->h == dx->h && y->w == dx->w && y->c == dx->c &&
                   y->n == dx->n && y->c % 16 == 0,
               "y must be the halo-free bf16 pre-norm tensor of the activation whose gradient is produced");
   if (add != nullptr)
@@ -1102,6 +1106,7 @@ int fpg_conv2d_dgrad_inbwd(const fpg_act* dy, const void* w_packed_t, const fpg_
   d[0].inbwd_halo = dx->halo;
   d[0].inbwd_add_halo = add ? add->halo : 0;
   d[0].inbwd_act = act;
+  d[0].inbwd_y_dt = y->fp32;
   *rows_per_img = d[0].stat_rows_per_img;
   return fpg_igemm_fprop_launch(&d[0], stream);
 }

@@ -11,6 +11,7 @@ namespace fpg {
 struct View {
   void* p;
   int32_t n, h, w, c, cs, halo;
+  int32_t dt;  // FPG_DT_*: element type (bf16 / fp32 / fp16)
   __device__ __forceinline__ int hp() const { return h + 2 * halo; }
   __device__ __forceinline__ int wp() const { return w + 2 * halo; }
   // element offset of interior pixel (y, x) of image i, channel 0
@@ -55,6 +56,7 @@ static View view_of(const fpg_act* a) {
   v.c = a->c;
   v.cs = a->c_stride;
   v.halo = a->halo;
+  v.dt = a->fp32;
   return v;
 }
 
@@ -75,6 +77,18 @@ __device__ __forceinline__ void cvt8(const uint4& u, float (&f)[8]) {
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 __device__ __forceinline__ uint4 ld16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+// the same for a tensor whose 2-byte element type is a kernel-uniform flag (bf16 or fp16)
+__device__ __forceinline__ void cvt8t(const uint4& u, float (&f)[8], int dt) {
+  float2 a = unpack_2x16(u.x, dt), b = unpack_2x16(u.y, dt), c = unpack_2x16(u.z, dt), d = unpack_2x16(u.w, dt);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void load8t(const __nv_bfloat16* p, float (&f)[8], int dt) {
+  cvt8t(*reinterpret_cast<const uint4*>(p), f, dt);
+}
+__device__ __forceinline__ void store8t(__nv_bfloat16* p, const float (&f)[8], int dt) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_2x16(f[0], f[1], dt), pack_2x16(f[2], f[3], dt),
+                                            pack_2x16(f[4], f[5], dt), pack_2x16(f[6], f[7], dt));
+}
 
 // ------------------------------------------------------------------------------------------------ IN statistics
 // grid (splits, n); block 256. thread t owns channel group (t % G), pixel lane (t / G); G = c / 8.
@@ -135,7 +149,7 @@ in_stats_kernel(View y, float* __restrict__ partial, float* __restrict__ stats, 
     for (; p + 3 * lanes < p_end; p += 4 * lanes, ptr += 4 * stride) {  // four independent 16-byte loads in flight
       float f[4][8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) load8(ptr + u * stride, f[u]);
+      for (int u = 0; u < 4; ++u) load8t(ptr + u * stride, f[u], y.dt);
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -146,7 +160,7 @@ in_stats_kernel(View y, float* __restrict__ partial, float* __restrict__ stats, 
     }
     for (; p < p_end; p += lanes, ptr += stride) {
       float f[8];
-      load8(ptr, f);
+      load8t(ptr, f, y.dt);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         s[k] += f[k];
@@ -158,7 +172,7 @@ in_stats_kernel(View y, float* __restrict__ partial, float* __restrict__ stats, 
     it.init(p_begin + pl, y.w);
     for (int p = p_begin + pl; p < p_end; p += lanes, it.advance(lanes, y.w)) {
       float f[8];
-      load8(base + y.at32(i, it.y, it.x), f);
+      load8t(base + y.at32(i, it.y, it.x), f, y.dt);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         s[k] += f[k];
@@ -252,7 +266,7 @@ in_stats_ring_kernel(View y, float* __restrict__ partial, float* __restrict__ st
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float f[8];
-        cvt8(v[u], f);
+        cvt8t(v[u], f, y.dt);
 #pragma unroll
         for (int k2 = 0; k2 < 8; ++k2) {
           s[k2] += f[k2];
@@ -310,7 +324,8 @@ __device__ __forceinline__ float act_grad(float pre, int act) {
 // The grid is sized to ONE wave of resident CTAs (a 1.15-wave grid costs two waves): ppl pixels per pixel lane.
 
 __global__ void __launch_bounds__(256, 4)
-in_apply_kernel(View y, const float* __restrict__ stats, int act, View res, int has_res, View z, int ppl) {
+in_apply_kernel(View y, const float* __restrict__ stats, int act, View res, int has_res, View z, View zs, int has_zs,
+                int ppl) {
   const int G = y.c / 8;
   const int lanes = 256 / G;
   const int g = threadIdx.x % G, pl = threadIdx.x / G;
@@ -337,16 +352,18 @@ in_apply_kernel(View y, const float* __restrict__ stats, int act, View res, int 
   for (int p = blockIdx.x * chunk + pl; p < p_end; p += lanes, it.advance(lanes, wp)) {
     const int sy = reflect_idx(it.y - z.halo, z.h), sx = reflect_idx(it.x - z.halo, z.w);
     float f[8], o[8];
-    load8(yb + y.at32(i, sy, sx), f);
+    load8t(yb + y.at32(i, sy, sx), f, y.dt);
 #pragma unroll
     for (int k = 0; k < 8; ++k) o[k] = act_fwd((f[k] - mean[k]) * rstd[k], act);
     if (has_res) {
       float rr[8];
-      load8(rb + res.at32(i, sy, sx), rr);
+      load8t(rb + res.at32(i, sy, sx), rr, res.dt);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] += rr[k];
     }
     store8(zb + z.at_padded32(i, it.y, it.x), o);
+    if (has_zs && it.y - z.halo == sy && it.x - z.halo == sx)  // interior position: the skip-stream copy
+      store8t(static_cast<__nv_bfloat16*>(zs.p) + g * 8 + zs.at32(i, sy, sx), o, zs.dt);
   }
 }
 
@@ -409,7 +426,7 @@ in_bwd_reduce_kernel(View dz, View dz2, int has_dz2, View y, const float* __rest
     const int py = it.y, px = it.x;
     float gr[8], yy[8];
     folded_grad(dz, i, py, px, g, gr);
-    load8(static_cast<const __nv_bfloat16*>(y.p) + y.at32(i, py, px) + g * 8, yy);
+    load8t(static_cast<const __nv_bfloat16*>(y.p) + y.at32(i, py, px) + g * 8, yy, y.dt);
     if (has_dz2) {
       float e[8];
       load8(static_cast<const __nv_bfloat16*>(dz2.p) + dz2.at32(i, py, px) + g * 8, e);
@@ -483,7 +500,7 @@ in_bwd_apply_kernel(View dz, View dz2, int has_dz2, View gsrc, int has_gsrc, Vie
         for (int k = 0; k < 8; ++k) gr[k] += e[k];
       }
     }
-    load8(static_cast<const __nv_bfloat16*>(y.p) + y.at32(i, py, px) + g * 8, yy);
+    load8t(static_cast<const __nv_bfloat16*>(y.p) + y.at32(i, py, px) + g * 8, yy, y.dt);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float zh = (yy[k] - mean[k]) * rstd[k];
@@ -1004,7 +1021,7 @@ in_bwd_reduce_ring_kernel(View dz, View dz2, int has_dz2, View y, const float* _
                     const int off = px * gm.pix_bytes + g * 16;
                     float gr[8], yy[8];
                     cvt8(*reinterpret_cast<const uint4*>(ptrs[0] + off), gr);
-                    cvt8(*reinterpret_cast<const uint4*>(ptrs[1] + off), yy);
+                    cvt8t(*reinterpret_cast<const uint4*>(ptrs[1] + off), yy, y.dt);
                     if (!folded) fold_extra(dz, i, row, x0 + px, g, gr);
                     if (has_dz2) {
                       float e[8];
@@ -1097,7 +1114,7 @@ in_bwd_apply_ring_kernel(View dz, View dz2, int has_dz2, int has_gsrc, View y, c
                     const int off = px * gm.pix_bytes + g * 16;
                     float gr[8], yy[8], o[8];
                     cvt8(*reinterpret_cast<const uint4*>(ptrs[0] + off), gr);
-                    cvt8(*reinterpret_cast<const uint4*>(ptrs[1] + off), yy);
+                    cvt8t(*reinterpret_cast<const uint4*>(ptrs[1] + off), yy, y.dt);
                     if (!has_gsrc) {
                       if (!folded) fold_extra(dz, i, row, x0 + px, g, gr);
                       if (use_dz2) {
@@ -1123,8 +1140,8 @@ in_bwd_apply_ring_kernel(View dz, View dz2, int has_dz2, int has_gsrc, View y, c
 // forward apply: operands {y, residual}; z = act((y - mean) * rstd) (+ residual), scattered to every padded position
 // of z that mirrors the pixel (reflect halo)
 __global__ void __launch_bounds__(kRingThreads, 2)
-in_apply_ring_kernel(View y, const float* __restrict__ stats, int act, int has_res, View z, const RingTensor t_y,
-                     const RingTensor t_res, const RingGeom gm) {
+in_apply_ring_kernel(View y, const float* __restrict__ stats, int act, int has_res, int res_dt, View z, View zs,
+                     int has_zs, const RingTensor t_y, const RingTensor t_res, const RingGeom gm) {
   extern __shared__ uint8_t ring_raw[];
   uint8_t* ring;
   uint64_t *full, *empty;
@@ -1160,16 +1177,17 @@ in_apply_ring_kernel(View y, const float* __restrict__ stats, int act, int has_r
                     const int off = px * gm.pix_bytes + g * 16;
                     const int x = x0 + px;
                     float f[8], o[8];
-                    cvt8(*reinterpret_cast<const uint4*>(ptrs[0] + off), f);
+                    cvt8t(*reinterpret_cast<const uint4*>(ptrs[0] + off), f, y.dt);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) o[k] = act_fwd((f[k] - mean[k]) * rstd[k], act);
                     if (has_res) {
                       float rr[8];
-                      cvt8(*reinterpret_cast<const uint4*>(ptrs[1] + off), rr);
+                      cvt8t(*reinterpret_cast<const uint4*>(ptrs[1] + off), rr, res_dt);
 #pragma unroll
                       for (int k = 0; k < 8; ++k) o[k] += rr[k];
                     }
                     store8(zb + z.at32(i, row, x), o);
+                    if (has_zs) store8t(static_cast<__nv_bfloat16*>(zs.p) + g * 8 + zs.at32(i, row, x), o, zs.dt);
                     if (hl > 0 && !(row > hl && row < z.h - 1 - hl && x > hl && x < z.w - 1 - hl)) {
                       int rows[3], cols[3], nr = 0, nc = 0;  // padded positions mirroring onto (row, x)
                       rows[nr++] = row + hl;
@@ -1475,11 +1493,15 @@ __global__ void mse_const_kernel(View logits, float target, float weight, float 
 
 constexpr int kL1Blocks = 296;
 __global__ void l1_partial_kernel(const float* __restrict__ pred, const float* __restrict__ target, int64_t count,
-                                  float gcoef, float* __restrict__ dpred, int accumulate, float* __restrict__ partial) {
+                                  int64_t per_image, int64_t target_image_stride, float gcoef,
+                                  float* __restrict__ dpred, int accumulate, float* __restrict__ partial) {
   float acc = 0.f;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
-    const float d = pred[i] - target[i];
+    // the target may be the leading channels of a wider NCHW tensor (cycle / identity losses compare with
+    // real_image[:, :3], model.py:703-711): per_image contiguous elements every target_image_stride
+    const int64_t ti = per_image > 0 ? (i / per_image) * target_image_stride + i % per_image : i;
+    const float d = pred[i] - target[ti];
     acc += fabsf(d);
     if (dpred != nullptr) {
       const float gsign = d > 0.f ? gcoef : (d < 0.f ? -gcoef : 0.f);
@@ -1510,7 +1532,8 @@ __global__ void l1_finalize_kernel(const float* __restrict__ partial, int nparts
 
 // ------------------------------------------------------------------------------------------------ packing
 // fp32 NCHW -> bf16 NHWC (channels [c0, c0+c_src)), reflect halo; one thread per padded destination pixel
-__global__ void pack_nchw_kernel(const float* __restrict__ src, int c_src, View dst, int c0, int zero_rest) {
+__global__ void pack_nchw_kernel(const float* __restrict__ src, int c_src, int c_img, View dst, int c0,
+                                 int zero_rest) {
   const int64_t total = static_cast<int64_t>(dst.n) * dst.hp() * dst.wp();
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -1521,7 +1544,7 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int c_src, View 
   const int sy = reflect_idx(py - dst.halo, dst.h), sx = reflect_idx(px - dst.halo, dst.w);
   __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(dst.p) + dst.at_padded(i, py, px);
   const int64_t hw = static_cast<int64_t>(dst.h) * dst.w;
-  const float* sp = src + static_cast<int64_t>(i) * c_src * hw + static_cast<int64_t>(sy) * dst.w + sx;
+  const float* sp = src + static_cast<int64_t>(i) * c_img * hw + static_cast<int64_t>(sy) * dst.w + sx;
   if (zero_rest && dst.c == 16) {
     // the whole 16-channel pixel is assembled in registers and written with two 128-bit stores
     float f[16];
@@ -1589,6 +1612,40 @@ __global__ void tanh_bwd_pack_kernel(const float* __restrict__ dout, View out, i
       }
     }
     store8(dp + c8, f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ cycle-step helpers
+// dst += src over fp32 vectors (count a multiple of 4 handled by float4, tail scalar): gradient accumulation of a
+// network that is applied several times in one step (train_cycle: each generator runs 2-3 times, model.py:683-704)
+__global__ void add_f32_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t count) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t n4 = count >> 2;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 a = reinterpret_cast<float4*>(dst)[i];
+    const float4 b = reinterpret_cast<const float4*>(src)[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(dst)[i] = a;
+  }
+  for (int64_t i = (n4 << 2) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride)
+    dst[i] += src[i];
+}
+
+// History buffer of generated images (get_buffer_image, model.py:275-294) with the pool resident on the device:
+// ctrl = {use_slot, store_slot} (device int32[2], written by the host before the launch / graph replay; -1 = none).
+//   out = use_slot >= 0 ? pool[use_slot] : cur;   if store_slot >= 0: pool[store_slot] = cur
+// use_slot == store_slot is the reference's "return the old image and replace it" case: every element is read before
+// it is overwritten by the same thread. 16-byte elements.
+__global__ void history_exchange_kernel(const uint4* __restrict__ cur, uint4* __restrict__ pool,
+                                        const int32_t* __restrict__ ctrl, uint4* __restrict__ out, int64_t n16) {
+  const int use = ctrl[0], store = ctrl[1];
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n16; i += stride) {
+    const uint4 c = cur[i];
+    uint4 o = c;
+    if (use >= 0) o = pool[static_cast<int64_t>(use) * n16 + i];
+    if (store >= 0) pool[static_cast<int64_t>(store) * n16 + i] = c;
+    out[i] = o;
   }
 }
 
@@ -1718,7 +1775,7 @@ static int stat_splits(const fpg_act* y, int slots) {
 // ring-path eligibility of an operand set: dense channels, 16 KB chunks hold whole pixels, 32-bit offsets
 static bool ring_ok(const fpg_act* a) {
   return a->c == a->c_stride && a->c % 8 == 0 && kStatThreads % (a->c / 8) == 0 &&
-         kRingStageBytes % (a->c_stride * 2) == 0 && !a->fp32 &&
+         kRingStageBytes % (a->c_stride * 2) == 0 && a->fp32 != FPG_DT_FP32 &&
          static_cast<int64_t>(a->n) * (a->h + 2 * a->halo) * (a->w + 2 * a->halo) * a->c_stride < (1ll << 31);
 }
 
@@ -1757,6 +1814,7 @@ int64_t fpg_instnorm_scratch_floats(const fpg_act* y) {
 int fpg_instnorm_stats(const fpg_act* y, float eps, float* stats, float* scratch, int32_t* counters, void* stream) {
   FPG_REQUIRE(y && stats && scratch && counters, "null argument");
   FPG_REQUIRE(y->c % 8 == 0 && kStatThreads % (y->c / 8) == 0, "instnorm channels %d", y->c);
+  FPG_REQUIRE(y->fp32 != FPG_DT_FP32, "instnorm_stats: y must be bf16 or fp16");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
   static const bool no_ring = getenv("FPG_NO_RING") != nullptr;
@@ -1783,9 +1841,15 @@ int fpg_instnorm_stats(const fpg_act* y, float eps, float* stats, float* scratch
 }
 
 int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_act* residual, const fpg_act* z,
-                       void* stream) {
+                       const fpg_act* skip_out, void* stream) {
   FPG_REQUIRE(y && stats && z, "null argument");
   FPG_REQUIRE(y->n == z->n && y->h == z->h && y->w == z->w && y->c == z->c && y->c % 8 == 0, "geometry mismatch");
+  FPG_REQUIRE(y->fp32 != FPG_DT_FP32 && z->fp32 == FPG_DT_BF16 && (!residual || residual->fp32 != FPG_DT_FP32),
+              "instnorm_apply: y / residual must be bf16 or fp16, z bf16");
+  FPG_REQUIRE(!skip_out || (skip_out->fp32 != FPG_DT_FP32 && skip_out->halo == 0 && skip_out->n == y->n &&
+                            skip_out->h == y->h && skip_out->w == y->w && skip_out->c == y->c),
+              "instnorm_apply: skip_out must be a halo-free 2-byte tensor of y's geometry");
+  View sv = skip_out ? view_of(skip_out) : view_of(z);
   FPG_REQUIRE(z->halo < z->h && z->halo < z->w, "halo too large");
   View rv = residual ? view_of(residual) : view_of(y);
   FPG_REQUIRE(256 % (y->c / 8) == 0, "instnorm channels %d", y->c);
@@ -1806,8 +1870,9 @@ int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_
     const RingGeom gm = ring_geom(y, stages, budgeted ? sms : 2 * sms);
     FPG_CUDA_CHECK(launch_persistent(in_apply_ring_kernel, dim3(gm.ctas_per_img, y->n), dim3(kRingThreads), smem,
                                      FPG_ST(stream),
-                                     view_of(y), stats, act, residual != nullptr, view_of(z), ring_tensor(y),
-                                     residual ? ring_tensor(residual) : ring_tensor(y), gm));
+                                     view_of(y), stats, act, residual != nullptr,
+                                     residual ? residual->fp32 : 0, view_of(z), sv, skip_out != nullptr,
+                                     ring_tensor(y), residual ? ring_tensor(residual) : ring_tensor(y), gm));
     FPG_CUDA_CHECK(cudaGetLastError());
     return 0;
   }
@@ -1815,7 +1880,7 @@ int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_
   const int lanes = 256 / (y->c / 8);
   const int ppl = pixels_per_lane(npix, lanes, y->n, resident_ctas(in_apply_kernel, 256));
   in_apply_kernel<<<dim3(grid_for(npix, lanes * ppl), y->n), 256, 0, FPG_ST(stream)>>>(
-      view_of(y), stats, act, rv, residual != nullptr, view_of(z), ppl);
+      view_of(y), stats, act, rv, residual != nullptr, view_of(z), sv, skip_out != nullptr, ppl);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -1838,7 +1903,9 @@ int fpg_instnorm_bwd(const fpg_act* dz, const fpg_act* dz2, const fpg_act* y, co
                     (!dz2 || (dz2->halo == 0 && dz2->c_stride == y->c_stride)) &&
                     (!dres || (dres->halo == 0 && dres->c_stride == y->c_stride)) &&
                     static_cast<int64_t>(y->n) * y->h * y->w * y->c_stride < (1ll << 31);
-  if (!split_launch && flat) {
+  FPG_REQUIRE(y->fp32 != FPG_DT_FP32 && dz->fp32 == FPG_DT_BF16 && dy->fp32 == FPG_DT_BF16,
+              "instnorm_bwd: y must be bf16 or fp16, gradients bf16");
+  if (!split_launch && flat && y->fp32 == FPG_DT_BF16) {
     // one cooperative launch: rounds of imgs_per_round images whose working set (~64 MB) stays in L2
     const int slots = resident_ctas(in_bwd_fused_kernel, kStatThreads) < 1024
                           ? resident_ctas(in_bwd_fused_kernel, kStatThreads) : 1024;
@@ -1914,6 +1981,7 @@ int fpg_instnorm_bwd_apply(const fpg_act* dz, const fpg_act* y, const float* sta
   FPG_REQUIRE(dz && y && stats && red && dy, "null argument");
   FPG_REQUIRE(dz->h == y->h && dz->w == y->w && dz->c == y->c && dy->h == y->h && dy->c == y->c, "geometry mismatch");
   FPG_REQUIRE(ring_ok(y) && ring_ok(dz) && ring_ok(dy), "tensors must suit the bulk-copy ring (see fpg_instnorm_bwd)");
+  FPG_REQUIRE(dz->fp32 == FPG_DT_BF16 && dy->fp32 == FPG_DT_BF16, "instnorm_bwd_apply: gradients must be bf16");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
   const int stages = 4;
@@ -1969,7 +2037,7 @@ int fpg_bias_grad(const fpg_act* dy, float* db, int32_t k_valid, float* scratch,
 int fpg_blend_fwd(const fpg_act* content, const fpg_act* logits, const fpg_act* input, const fpg_act* out,
                   int32_t out_c0, float* out_nchw, float* mask_nhw, void* stream) {
   FPG_REQUIRE(content && logits && input, "null argument");
-  FPG_REQUIRE(content->c_stride >= 28 && logits->c_stride >= 12 && content->fp32 && logits->fp32,
+  FPG_REQUIRE(content->c_stride >= 28 && logits->c_stride >= 12 && content->fp32 == FPG_DT_FP32 && logits->fp32 == FPG_DT_FP32,
               "blend expects fp32 content (>=28 ch) and logits (>=12 ch)");
   View ov;
   if (out) {
@@ -2007,7 +2075,7 @@ int fpg_blend_bwd(const float* dout_nchw, const fpg_act* dout_nhwc, int32_t dout
 
 int fpg_mse_const_loss(const fpg_act* logits, float target, float weight, float grad_scale, float* loss,
                        const fpg_act* dlogits, void* stream) {
-  FPG_REQUIRE(logits && logits->fp32, "logits must be fp32");
+  FPG_REQUIRE(logits && logits->fp32 == FPG_DT_FP32, "logits must be fp32");
   FPG_REQUIRE(static_cast<int64_t>(logits->n) * logits->h * logits->w < (1ll << 30), "too many logits for one CTA");
   View gv;
   if (dlogits) {
@@ -2021,20 +2089,27 @@ int fpg_mse_const_loss(const fpg_act* logits, float target, float weight, float 
   return 0;
 }
 
-int fpg_l1_loss(const float* pred, const float* target, int64_t count, float weight, float grad_scale, float* loss,
-                float* dpred, int accumulate, float* scratch, void* stream) {
-  FPG_REQUIRE(pred && target && loss && scratch && count > 0, "bad argument");
+int fpg_l1_loss(const float* pred, const float* target, int64_t count, int64_t per_image, int64_t target_image_stride,
+                float weight, float grad_scale, float* loss, float* dpred, int accumulate, float* scratch,
+                void* stream) {
+  FPG_REQUIRE(pred && target && loss && scratch && count > 0 && per_image >= 0 &&
+                  (per_image == 0 || (count % per_image == 0 && target_image_stride >= per_image)),
+              "bad argument");
   const float gcoef = grad_scale * weight / static_cast<float>(count);
-  l1_partial_kernel<<<kL1Blocks, 256, 0, FPG_ST(stream)>>>(pred, target, count, gcoef, dpred, accumulate, scratch);
+  l1_partial_kernel<<<kL1Blocks, 256, 0, FPG_ST(stream)>>>(pred, target, count, per_image, target_image_stride, gcoef,
+                                                           dpred, accumulate, scratch);
   l1_finalize_kernel<<<1, 512, 0, FPG_ST(stream)>>>(scratch, kL1Blocks, weight / static_cast<float>(count), loss);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
-int fpg_pack_nchw(const float* src, int32_t c_src, const fpg_act* dst, int32_t c0, int zero_rest, void* stream) {
-  FPG_REQUIRE(src && dst && c0 + c_src <= dst->c_stride, "bad argument");
+int fpg_pack_nchw(const float* src, int32_t c_src, int32_t c_img, const fpg_act* dst, int32_t c0, int zero_rest,
+                  void* stream) {
+  FPG_REQUIRE(src && dst && c0 + c_src <= dst->c_stride && dst->fp32 == FPG_DT_BF16 && (c_img == 0 || c_img >= c_src),
+              "bad argument");
   const int64_t total = static_cast<int64_t>(dst->n) * (dst->h + 2 * dst->halo) * (dst->w + 2 * dst->halo);
-  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(src, c_src, view_of(dst), c0, zero_rest);
+  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(src, c_src, c_img ? c_img : c_src, view_of(dst),
+                                                                     c0, zero_rest);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -2042,14 +2117,14 @@ int fpg_pack_nchw(const float* src, int32_t c_src, const fpg_act* dst, int32_t c
 int fpg_unpack_nchw(const fpg_act* src, int32_t c0, float* dst, int32_t c_dst, int accumulate, void* stream) {
   FPG_REQUIRE(src && dst && c0 + c_dst <= src->c_stride, "bad argument");
   const int64_t total = static_cast<int64_t>(src->n) * src->h * src->w;
-  unpack_nchw_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(src), src->fp32, c0, dst, c_dst,
+  unpack_nchw_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(src), src->fp32 == FPG_DT_FP32, c0, dst, c_dst,
                                                                        accumulate);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
 int fpg_tanh_bwd_pack(const float* dout_nchw, const fpg_act* out, int32_t c_valid, const fpg_act* dpre, void* stream) {
-  FPG_REQUIRE(dout_nchw && out && dpre && out->fp32 && dpre->c % 8 == 0 && c_valid <= out->c_stride, "bad argument");
+  FPG_REQUIRE(dout_nchw && out && dpre && out->fp32 == FPG_DT_FP32 && dpre->c % 8 == 0 && c_valid <= out->c_stride, "bad argument");
   const int64_t total = static_cast<int64_t>(out->n) * out->h * out->w;
   tanh_bwd_pack_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(dout_nchw, view_of(out), c_valid,
                                                                          view_of(dpre));
@@ -2081,6 +2156,26 @@ int fpg_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t coun
   if (blocks > 2368) blocks = 2368;
   adam_dev_kernel<<<static_cast<unsigned>(blocks), 256, 0, FPG_ST(stream)>>>(p, g, m, v, count, beta1, beta2, eps, state,
                                                                              grad_scale);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_add_f32(float* dst, const float* src, int64_t count, void* stream) {
+  FPG_REQUIRE(dst && src && count > 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(src) & 15) == 0,
+              "bad argument");
+  const int sms = sm_count_cached();
+  add_f32_kernel<<<(sms > 0 ? sms : 148) * 4, 256, 0, FPG_ST(stream)>>>(dst, src, count);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_history_exchange(const void* cur, void* pool, const int32_t* ctrl, void* out, int64_t entry_bytes,
+                         void* stream) {
+  FPG_REQUIRE(cur && pool && ctrl && out && entry_bytes > 0 && entry_bytes % 16 == 0, "bad argument");
+  const int sms = sm_count_cached();
+  history_exchange_kernel<<<(sms > 0 ? sms : 148) * 4, 256, 0, FPG_ST(stream)>>>(
+      static_cast<const uint4*>(cur), static_cast<uint4*>(pool), ctrl, static_cast<uint4*>(out), entry_bytes / 16);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -52,6 +52,7 @@ struct InBwdStat {
   const float* stats;        // [n][c][2] mean, rstd
   const __nv_bfloat16* add;  // optional [n][h + 2 add_halo][w + 2 add_halo][c]: added to the interior outputs
   int32_t h, w, c, halo, add_halo, act;
+  int32_t y_dt;              // element type of y: FPG_DT_BF16 or FPG_DT_FP16
 };
 
 struct FpropArgs {
@@ -94,11 +95,11 @@ __device__ __forceinline__ float warp_colsum16(float (&a)[16], int lane) {
 }
 
 __device__ __forceinline__ void stat_accumulate(const StatOut& so, const float (&f)[16], bool valid, int lane,
-                                                int64_t prow, int col0) {
+                                                int64_t prow, int col0, int dt) {
   float a[16], b[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const float r = valid ? __bfloat162float(__float2bfloat16(f[i])) : 0.f;
+    const float r = valid ? round_16(f[i], dt) : 0.f;  // statistics of the values as stored (bf16 or fp16)
     a[i] = r;
     b[i] = r * r;
   }
@@ -118,17 +119,35 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
     f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
   }
 }
+__device__ __forceinline__ void unpack_16x8(const uint4& u, float* f, int dt) {
+  if (dt != 2) return unpack_bf16x8(u, f);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 v = unpack_f16x2(w[i]);
+    f[2 * i] = v.x;
+    f[2 * i + 1] = v.y;
+  }
+}
+// 16 fp32 values -> 32 bytes of bf16 or fp16 at dst
+__device__ __forceinline__ void store_16x16(void* dst_, const float (&f)[16], int dt) {
+  uint4* dst = reinterpret_cast<uint4*>(dst_);
+  dst[0] = make_uint4(pack_2x16(f[0], f[1], dt), pack_2x16(f[2], f[3], dt), pack_2x16(f[4], f[5], dt),
+                      pack_2x16(f[6], f[7], dt));
+  dst[1] = make_uint4(pack_2x16(f[8], f[9], dt), pack_2x16(f[10], f[11], dt), pack_2x16(f[12], f[13], dt),
+                      pack_2x16(f[14], f[15], dt));
+}
 
 // InstanceNorm-backward variant of stat_accumulate: f = the 16 values about to be stored for this thread's pixel,
 // yreg = the forward pre-norm output (16 bf16) at the interior pixel it mirrors, st = {mean, rstd} of the channels.
 // Column sums over the warp's 32 rows of g' = round_bf16(f) * act'(zhat) and g' * zhat.
 __device__ __forceinline__ void inbwd_accumulate(const StatOut& so, const float (&f)[16], const uint4 (&yreg)[2],
                                                  const float* st, int act, bool valid, int lane, int64_t prow,
-                                                 int col0) {
+                                                 int col0, int y_dt) {
   float a[16], b[16];
   float yv[16];
-  unpack_bf16x8(yreg[0], yv);
-  unpack_bf16x8(yreg[1], yv + 8);
+  unpack_16x8(yreg[0], yv, y_dt);
+  unpack_16x8(yreg[1], yv + 8, y_dt);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float4 ms = __ldg(reinterpret_cast<const float4*>(st) + i);  // {mean, rstd} of channels 2i, 2i + 1
@@ -386,21 +405,18 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
           }
           if (args.stat.partial != nullptr) {
             if (st_img != nullptr)
-              inbwd_accumulate(args.stat, f, yreg, st_img + 2 * c, args.inbwd.act, valid, lane, prow, nb * BN + c);
+              inbwd_accumulate(args.stat, f, yreg, st_img + 2 * c, args.inbwd.act, valid, lane, prow, nb * BN + c,
+                               args.inbwd.y_dt);
             else
-              stat_accumulate(args.stat, f, valid, lane, prow, nb * BN + c);
+              stat_accumulate(args.stat, f, valid, lane, prow, nb * BN + c, args.out.fp32);
           }
           if (valid) {
-            if (args.out.fp32) {
+            if (args.out.fp32 == FPG_DT_FP32) {
               float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out.base) + off + c);
 #pragma unroll
               for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
             } else {
-              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out.base) + off + c);
-              dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                                  pack_bf16x2(f[6], f[7]));
-              dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                                  pack_bf16x2(f[14], f[15]));
+              store_16x16(static_cast<__nv_bfloat16*>(args.out.base) + off + c, f, args.out.fp32);
             }
           }
         };
@@ -634,18 +650,15 @@ igemm_fprop2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], args.act);
         }
-        if (args.stat.partial != nullptr) stat_accumulate(args.stat, f, valid, lane, prow, nb * BN + c);
+        if (args.stat.partial != nullptr)
+          stat_accumulate(args.stat, f, valid, lane, prow, nb * BN + c, args.out.fp32);
         if (valid) {
-          if (args.out.fp32) {
+          if (args.out.fp32 == FPG_DT_FP32) {
             float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out.base) + off + c);
 #pragma unroll
             for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
           } else {
-            uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out.base) + off + c);
-            dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                                pack_bf16x2(f[6], f[7]));
-            dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                                pack_bf16x2(f[14], f[15]));
+            store_16x16(static_cast<__nv_bfloat16*>(args.out.base) + off + c, f, args.out.fp32);
           }
         }
       }
@@ -1197,8 +1210,9 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
   args.inbwd.halo = d->inbwd_halo;
   args.inbwd.add_halo = d->inbwd_add_halo;
   args.inbwd.act = d->inbwd_act;
+  args.inbwd.y_dt = d->inbwd_y_dt;
   if (d->inbwd_y != nullptr)
-    FPG_REQUIRE(!d->cta_pair && d->stat_partial != nullptr && d->inbwd_stats != nullptr && !d->out.fp32 &&
+    FPG_REQUIRE(!d->cta_pair && d->stat_partial != nullptr && d->inbwd_stats != nullptr && d->out.fp32 == FPG_DT_BF16 &&
                     d->inbwd_c == d->block_n * d->n_blocks && d->out.mul_y == 1 && d->out.mul_x == 1,
                 "InstanceNorm-backward statistics: 1-CTA stride-1 bf16 launch with the statistics buffer");
   args.stat.c_total = d->block_n * d->n_blocks;

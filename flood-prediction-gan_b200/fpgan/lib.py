@@ -11,6 +11,8 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "libfpg_b200.so")
 
 FPG_MAX_TAPS = 64
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
+DT_BF16, DT_FP32, DT_FP16 = 0, 1, 2  # fpg_act.fp32 / fpg_out_view.fp32 element types (FPG_DT_*)
+ABI_VERSION = 2
 
 
 class Tap(C.Structure):
@@ -38,7 +40,7 @@ class FpropDesc(C.Structure):
                 ("stat_rows_per_img", C.c_int32), ("stat_row0", C.c_int32), ("inbwd_y", C.c_void_p),
                 ("inbwd_stats", C.c_void_p), ("inbwd_add", C.c_void_p), ("inbwd_h", C.c_int32), ("inbwd_w", C.c_int32),
                 ("inbwd_c", C.c_int32), ("inbwd_halo", C.c_int32), ("inbwd_add_halo", C.c_int32),
-                ("inbwd_act", C.c_int32)]
+                ("inbwd_act", C.c_int32), ("inbwd_y_dt", C.c_int32)]
 
 
 class RowsDesc(C.Structure):
@@ -116,7 +118,7 @@ SIGNATURES = {
     "fpg_bias_grad": (C.c_int, [_P(Act), _vp, _i32, _vp, _vp]),
     "fpg_instnorm_scratch_floats": (_i64, [_P(Act)]),
     "fpg_instnorm_stats": (C.c_int, [_P(Act), _f32, _vp, _vp, _vp, _vp]),
-    "fpg_instnorm_apply": (C.c_int, [_P(Act), _vp, C.c_int, _P(Act), _P(Act), _vp]),
+    "fpg_instnorm_apply": (C.c_int, [_P(Act), _vp, C.c_int, _P(Act), _P(Act), _P(Act), _vp]),
     "fpg_conv2d_dgrad_inbwd": (C.c_int, [_P(Act), _vp, _P(ConvGeom), _P(Act), _P(Act), _vp, C.c_int, _P(Act), _vp,
                                          _P(_i32), _vp]),
     "fpg_instnorm_bwd_sums_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _vp, _vp]),
@@ -142,8 +144,10 @@ SIGNATURES = {
     "fpg_blend_fwd": (C.c_int, [_P(Act), _P(Act), _P(Act), _P(Act), _i32, _vp, _vp, _vp]),
     "fpg_blend_bwd": (C.c_int, [_vp, _P(Act), _i32, _P(Act), _P(Act), _P(Act), _P(Act), _P(Act), _vp, _vp]),
     "fpg_mse_const_loss": (C.c_int, [_P(Act), _f32, _f32, _f32, _vp, _P(Act), _vp]),
-    "fpg_l1_loss": (C.c_int, [_vp, _vp, _i64, _f32, _f32, _vp, _vp, C.c_int, _vp, _vp]),
-    "fpg_pack_nchw": (C.c_int, [_vp, _i32, _P(Act), _i32, C.c_int, _vp]),
+    "fpg_l1_loss": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, C.c_int, _vp, _vp]),
+    "fpg_pack_nchw": (C.c_int, [_vp, _i32, _i32, _P(Act), _i32, C.c_int, _vp]),
+    "fpg_add_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "fpg_history_exchange": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "fpg_unpack_nchw": (C.c_int, [_P(Act), _i32, _vp, _i32, C.c_int, _vp]),
     "fpg_tanh_bwd_pack": (C.c_int, [_vp, _P(Act), _i32, _P(Act), _vp]),
     "fpg_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
@@ -173,7 +177,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.fpg_abi_version() != 1:
+    if lib.fpg_abi_version() != ABI_VERSION:
         raise FpgError("libfpg_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -50,11 +50,15 @@ class ActBuf:
 
     `c` channels starting at channel offset `c0` of the underlying storage are visible to the kernels."""
 
-    def __init__(self, n, h, w, c, halo=0, fp32=False, device="cuda", tensor=None, c0=0, c_stride=None, zero=True):
-        self.n, self.h, self.w, self.c, self.halo, self.fp32 = n, h, w, c, halo, fp32
+    def __init__(self, n, h, w, c, halo=0, fp32=False, device="cuda", tensor=None, c0=0, c_stride=None, zero=True,
+                 f16=False):
+        """fp32: network heads; f16: tensors that only elementwise kernels read (pre-normalisation conv outputs, the
+        residual skip stream) -- fp16 keeps 3 more mantissa bits than bf16 at the same size; default bf16."""
+        assert not (fp32 and f16)
+        self.n, self.h, self.w, self.c, self.halo, self.fp32, self.f16 = n, h, w, c, halo, fp32, f16
         self.c_stride = c_stride or c
         self.c0 = c0
-        dtype = torch.float32 if fp32 else torch.bfloat16
+        dtype = torch.float32 if fp32 else (torch.float16 if f16 else torch.bfloat16)
         if tensor is None:
             shape = (n, h + 2 * halo, w + 2 * halo, self.c_stride)
             tensor = torch.zeros(shape, dtype=dtype, device=device) if zero else torch.empty(shape, dtype=dtype,
@@ -65,7 +69,7 @@ class ActBuf:
         self.desc.n, self.desc.h, self.desc.w, self.desc.c = n, h, w, c
         self.desc.c_stride = self.c_stride
         self.desc.halo = halo
-        self.desc.fp32 = 1 if fp32 else 0
+        self.desc.fp32 = L.DT_FP32 if fp32 else (L.DT_FP16 if f16 else L.DT_BF16)
 
     def ref(self):
         return C.byref(self.desc)
@@ -73,12 +77,12 @@ class ActBuf:
     def channels(self, c0, c):
         """A view of `c` channels starting at c0 (shares storage)."""
         return ActBuf(self.n, self.h, self.w, c, self.halo, self.fp32, tensor=self.t, c0=self.c0 + c0,
-                      c_stride=self.c_stride)
+                      c_stride=self.c_stride, f16=self.f16)
 
     def batch_slice(self, start, n):
         """A view of images [start, start+n) (shares storage)."""
         return ActBuf(n, self.h, self.w, self.c, self.halo, self.fp32, tensor=self.t[start:start + n], c0=self.c0,
-                      c_stride=self.c_stride)
+                      c_stride=self.c_stride, f16=self.f16)
 
     def interior(self):
         """torch view [n, h, w, c] of the interior."""
@@ -90,11 +94,11 @@ class ActBuf:
         return self.interior()[..., :c].permute(0, 3, 1, 2).float().contiguous()
 
     @staticmethod
-    def from_nchw(x, c_pad=None, halo=0, mode="reflect", fp32=False):
+    def from_nchw(x, c_pad=None, halo=0, mode="reflect", fp32=False, f16=False):
         """Test helper: NCHW float tensor -> ActBuf (torch ops; the product path uses pack_nchw)."""
         n, c, h, w = x.shape
         cp = c_pad or pad16(c)
-        buf = ActBuf(n, h, w, cp, halo=halo, fp32=fp32, device=x.device)
+        buf = ActBuf(n, h, w, cp, halo=halo, fp32=fp32, device=x.device, f16=f16)
         xp = torch.nn.functional.pad(x, (halo,) * 4, mode) if halo else x
         buf.t[..., :c] = xp.permute(0, 2, 3, 1).to(buf.t.dtype)
         return buf
@@ -307,9 +311,11 @@ def instnorm_stats(y, stats, eps=1e-5):
          _ptr(_counters(y.t.device)), _stream())
 
 
-def instnorm_apply(y, stats, act, z, residual=None):
+def instnorm_apply(y, stats, act, z, residual=None, skip_out=None):
+    """z = act(IN(y)) (+ residual) with its reflect halo; skip_out (halo-free fp16 / bf16) also receives the values
+    before they are rounded to z's bf16 (the trunk's skip stream)"""
     _run("instnorm_apply", 1, "fpg_instnorm_apply", y.ref(), _ptr(stats), act, residual.ref() if residual is not None else None,
-           z.ref(), _stream())
+           z.ref(), skip_out.ref() if skip_out is not None else None, _stream())
 
 
 def instnorm_bwd(dz, y, stats, act, dy, dz2=None, dres=None):
@@ -364,7 +370,7 @@ def instnorm_bwd_apply(dz, y, stats, red, act, dy):
 
 def batch_stats(y, stats, eps=1e-5):
     """Per-channel {mean, rstd} over the whole batch: InstanceNorm statistics of the batch viewed as one image."""
-    flat = ActBuf(1, y.n * y.h, y.w, y.c, tensor=y.t, c0=y.c0, c_stride=y.c_stride)
+    flat = ActBuf(1, y.n * y.h, y.w, y.c, tensor=y.t, c0=y.c0, c_stride=y.c_stride, f16=y.f16)
     instnorm_stats(flat, stats, eps)
 
 
@@ -420,14 +426,40 @@ def mse_const_loss(logits, target, weight, grad_scale, loss, dlogits=None):
 
 
 def l1_loss(pred, target, weight, grad_scale, loss, dpred=None, accumulate=False):
+    """loss = weight * mean|pred - target| (+ its gradient). pred: contiguous fp32 [B, c, H, W]; target: contiguous, or
+    the leading c channels of a wider contiguous NCHW tensor (real_image[:, :3])."""
     ws = workspace(4096, pred.device)
-    _run("l1_loss", 2, "fpg_l1_loss", _ptr(pred), _ptr(target), pred.numel(), float(weight), float(grad_scale), _ptr(loss),
-           _ptr(dpred), 1 if accumulate else 0, _ptr(ws), _stream())
+    per_image, t_stride = 0, 0
+    assert pred.is_contiguous() and pred.dtype == torch.float32 and target.dtype == torch.float32
+    if not target.is_contiguous():
+        per_image, t_stride = pred[0].numel(), target.stride(0)
+        assert target.shape == pred.shape and target[0].is_contiguous(), "target must be a leading-channel slice"
+    _run("l1_loss", 2, "fpg_l1_loss", _ptr(pred), _ptr(target), pred.numel(), per_image, t_stride, float(weight),
+         float(grad_scale), _ptr(loss), _ptr(dpred), 1 if accumulate else 0, _ptr(ws), _stream())
 
 
 def pack_nchw(src, dst, c0=0, zero_rest=False):
-    assert src.dtype == torch.float32 and src.is_contiguous()
-    _run("pack_nchw", 1, "fpg_pack_nchw", _ptr(src), src.shape[1], dst.ref(), c0, 1 if zero_rest else 0, _stream())
+    """src: fp32 [B, c, H, W], contiguous or a channel slice x[:, a:b] of a contiguous NCHW tensor"""
+    assert src.dtype == torch.float32
+    c_img = 0
+    if not src.is_contiguous():
+        assert src[0].is_contiguous() and src.stride(0) % (src.shape[2] * src.shape[3]) == 0, "not a channel slice"
+        c_img = src.stride(0) // (src.shape[2] * src.shape[3])
+    _run("pack_nchw", 1, "fpg_pack_nchw", _ptr(src), src.shape[1], c_img, dst.ref(), c0, 1 if zero_rest else 0,
+         _stream())
+
+
+def add_f32(dst, src):
+    """dst += src (flat fp32 gradient buffers)"""
+    assert dst.dtype == src.dtype == torch.float32 and dst.numel() == src.numel()
+    _run("add_f32", 1, "fpg_add_f32", _ptr(dst), _ptr(src), dst.numel(), _stream())
+
+
+def history_exchange(cur, pool, ctrl, out):
+    """device-resident get_buffer_image: see fpg_history_exchange. cur/out: same-size tensors, pool: [50, ...]"""
+    nbytes = cur.numel() * cur.element_size()
+    assert out.numel() * out.element_size() == nbytes and pool[0].numel() * pool.element_size() == nbytes
+    _run("history_exchange", 1, "fpg_history_exchange", _ptr(cur), _ptr(pool), _ptr(ctrl), _ptr(out), nbytes, _stream())
 
 
 def unpack_nchw(src, dst, c0=0, accumulate=False):

@@ -213,7 +213,10 @@ class DeviceLoader:
     """DataLoader(dataset, batch_size, shuffle=True) semantics (data.py:28-43) without worker processes or host copies:
     a new permutation per epoch drawn exactly like torch's RandomSampler (a seed taken from the global torch RNG, after
     the one DataLoader's iterator takes for its workers), last batch kept. With world_size > 1 every rank draws the same
-    permutation and takes rows [rank*B, (rank+1)*B) of each global batch of world_size*B samples."""
+    permutation and takes rows [rank*B, (rank+1)*B) of each global batch of world_size*B samples; a ragged tail is
+    completed by wrapping around to the start of the permutation (torch's DistributedSampler does the same), so that
+    every rank takes the same number of equally sized batches -- the fused step issues NCCL all-reduces (captured in
+    a CUDA graph keyed by the batch shape) that every rank must join, with equal weight 1/world_size."""
 
     def __init__(self, dataset, batch_size=1, shuffle=True, rank=0, world_size=1):
         self.dataset, self.batch_size, self.shuffle = dataset, batch_size, shuffle
@@ -232,13 +235,18 @@ class DeviceLoader:
         g.manual_seed(seed)
         return torch.randperm(n, generator=g).tolist()
 
-    def __iter__(self):
-        order = self.order()
+    def rank_batches(self, order):
+        """index lists of this rank's batches for one epoch"""
         gb = self.batch_size * self.world_size
-        for start in range(0, len(order), gb):
-            chunk = order[start:start + gb][self.rank * self.batch_size:(self.rank + 1) * self.batch_size]
-            if chunk:
-                yield self.dataset.gather(chunk)
+        if self.world_size > 1 and order and len(order) % gb:
+            pad = gb - len(order) % gb
+            order = order + (order * (pad // len(order) + 1))[:pad]
+        lo, hi = self.rank * self.batch_size, (self.rank + 1) * self.batch_size
+        return [order[start:start + gb][lo:hi] for start in range(0, len(order), gb)]
+
+    def __iter__(self):
+        for chunk in self.rank_batches(self.order()):
+            yield self.dataset.gather(chunk)
 
 
 def create_flood_dataset(dataset_subset="all", dataset_dem="best", data_path=None, topography="all", resize=None,

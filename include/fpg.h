@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define FPG_ABI_VERSION 1
+#define FPG_ABI_VERSION 2
 #define FPG_MAX_TAPS 64
 
 #define FPG_EINVAL (-22)
@@ -69,7 +69,7 @@ typedef struct {
   int64_t stride_n, stride_y, stride_x; /* in elements */
   int32_t mul_y, off_y, mul_x, off_x;
   int32_t valid_h, valid_w; /* tile pixels with y >= valid_h or x >= valid_w are not stored */
-  int32_t fp32;             /* 0: bf16 output, 1: fp32 output */
+  int32_t fp32;             /* element type of the output: FPG_DT_BF16 / FPG_DT_FP32 / FPG_DT_FP16 */
 } fpg_out_view;
 
 /* D[pixel, k] = sum_{tap, c} A[pixel + tap, c] * B[k, tap*C + c]  (+bias, activation) */
@@ -109,12 +109,13 @@ typedef struct {
    * the interior pixel that output pixel mirrors (itself for interior pixels): the sums are linear in dz, so the halo
    * needs no fold first. inbwd_add (optional) is added to the INTERIOR outputs before they are stored (the
    * skip-connection gradient; it is read at its own interior when inbwd_add_halo > 0).
-   *   inbwd_y: bf16 [n][inbwd_h][inbwd_w][c], no halo; inbwd_stats: fp32 [n][c][2] = {mean, rstd};
+   *   inbwd_y: bf16 or fp16 [n][inbwd_h][inbwd_w][c], no halo; inbwd_stats: fp32 [n][c][2] = {mean, rstd};
    *   inbwd_halo: halo of the output tensor (tile coordinates are padded coordinates). */
   const void* inbwd_y;
   const float* inbwd_stats;
   const void* inbwd_add;
   int32_t inbwd_h, inbwd_w, inbwd_c, inbwd_halo, inbwd_add_halo, inbwd_act;
+  int32_t inbwd_y_dt; /* element type of inbwd_y: FPG_DT_BF16 or FPG_DT_FP16 */
 } fpg_igemm_fprop_desc;
 
 /* D_item[m, n] = sum_{pixel} X[pixel + xtap, xc + m] * Y[pixel + ytap, yc + n], split over pixel ranges,
@@ -184,7 +185,11 @@ int fpg_igemm_rows_launch(const fpg_igemm_rows_desc* d, void* stream);
  * model_architectures.py:312-334 (generator), :407-416 (residual blocks), :424-437 (PatchGAN)).
  * ---------------------------------------------------------------------------------------------------------- */
 
-/* An NHWC bf16 activation buffer. `halo` pixels of materialised border surround the h x w interior
+#define FPG_DT_BF16 0
+#define FPG_DT_FP32 1
+#define FPG_DT_FP16 2
+
+/* An NHWC activation buffer (bf16 unless `fp32` says otherwise). `halo` pixels of materialised border surround the h x w interior
  * (reflect halo written by the producer); c_stride >= c is the per-pixel element stride, `data` points at
  * channel 0 of the first halo pixel. */
 typedef struct {
@@ -192,7 +197,9 @@ typedef struct {
   int32_t n, h, w, c;
   int32_t c_stride;
   int32_t halo;
-  int32_t fp32; /* only meaningful for outputs */
+  int32_t fp32; /* element type FPG_DT_*: 0 = bf16 (tensor-core operands, gradients), 1 = fp32 (network heads),
+                   2 = fp16 (pre-normalisation conv outputs and the residual skip stream: tensors that only elementwise
+                   kernels read keep 3 more mantissa bits at the same 2 bytes/element; stores saturate) */
 } fpg_act;
 
 typedef struct {
@@ -324,9 +331,12 @@ int64_t fpg_instnorm_scratch_floats(const fpg_act* y);
  * and release flags of the per-image rendezvous; shared by all instnorm calls of one stream; n <= 2048). */
 int fpg_instnorm_stats(const fpg_act* y, float eps, float* stats, float* scratch, int32_t* counters, void* stream);
 /* z = act((y - mean) * rstd) [+ residual]; written to z's interior and, if z->halo > 0, mirrored into its halo.
- * residual may be NULL; it is read at interior coordinates (its own halo is skipped). */
+ * residual may be NULL; it is read at interior coordinates (its own halo is skipped). y and residual may be bf16 or
+ * fp16 (FPG_DT_*). skip_out (may be NULL; halo-free, same geometry, bf16 or fp16) receives the same values before
+ * they are rounded to z's bf16: the residual stream of the ResNet trunk (model_architectures.py:412-418) is carried
+ * in fp16 beside the bf16 tensor-core operand, so that nine skip additions do not re-round it to 8 mantissa bits. */
 int fpg_instnorm_apply(const fpg_act* y, const float* stats, int act, const fpg_act* residual, const fpg_act* z,
-                       void* stream);
+                       const fpg_act* skip_out, void* stream);
 /* Backward of z = act(IN(y)). Upstream gradient g = fold(dz) + dz2, where dz is the gradient w.r.t. z INCLUDING
  * its halo when dz->halo > 0 (folded back onto the interior: backward of F.pad(reflect)) and dz2 (may be NULL,
  * halo ignored) is a second gradient branch (residual skip). Writes dy; if dres != NULL also writes g there
@@ -437,16 +447,22 @@ int fpg_blend_bwd(const float* dout_nchw, const fpg_act* dout_nhwc, int32_t dout
 int fpg_mse_const_loss(const fpg_act* logits, float target, float weight, float grad_scale, float* loss,
                        const fpg_act* dlogits, void* stream);
 /* pred/target: fp32 NCHW [count]; dpred (fp32, may be NULL) = grad_scale * weight * sign(pred-target) / count,
- * accumulated (+=) if accumulate != 0 */
-int fpg_l1_loss(const float* pred, const float* target, int64_t count, float weight, float grad_scale, float* loss,
+ * accumulated (+=) if accumulate != 0. per_image > 0: the target is the leading per_image elements of every
+ * target_image_stride elements (real_image[:, :3] of a wider NCHW tensor: the cycle / identity losses,
+ * model.py:703-711); per_image == 0: target is flat like pred. */
+int fpg_l1_loss(const float* pred, const float* target, int64_t count, int64_t per_image,
+                int64_t target_image_stride, float weight, float grad_scale, float* loss,
                 float* dpred, int accumulate, float* scratch /* >= 512 floats */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Layout / packing helpers around the network boundary (model.py:613-617: .to(device), torch.cat).
  * ---------------------------------------------------------------------------------------------------------- */
 /* src fp32 NCHW [n][c_src][h][w] -> dst bf16 NHWC channels [c0, c0+c_src) of dst interior, reflect halo filled if
- * dst->halo > 0. Channels of dst outside the copied range are left untouched unless zero_rest != 0. */
-int fpg_pack_nchw(const float* src, int32_t c_src, const fpg_act* dst, int32_t c0, int zero_rest, void* stream);
+ * dst->halo > 0. Channels of dst outside the copied range are left untouched unless zero_rest != 0.
+ * c_img (0 = c_src): channels per image of the tensor `src` points into, when the c_src channels are a slice of a wider
+ * NCHW tensor (the topography conditions input_stack[:, 3:] re-attached to every synthetic image, model.py:683-689). */
+int fpg_pack_nchw(const float* src, int32_t c_src, int32_t c_img, const fpg_act* dst, int32_t c0, int zero_rest,
+                  void* stream);
 /* Backward through a fused tanh head (CycleGAN generator, model_architectures.py:115-116): dpre (bf16 NHWC) =
  * dout (fp32 NCHW [n][c_valid][h][w]) * (1 - out^2), out = the fp32 NHWC tanh output; channels >= c_valid are 0. */
 int fpg_tanh_bwd_pack(const float* dout_nchw, const fpg_act* out, int32_t c_valid, const fpg_act* dpre, void* stream);
@@ -466,6 +482,16 @@ int fpg_adam_step(float* p, const float* g, float* m, float* v, int64_t count, f
  *   state: int32[4] = {step (incremented by this call), lr as float bits, scratch, scratch}. */
 int fpg_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t count, float beta1, float beta2, float eps,
                       int32_t* state, float grad_scale, void* stream);
+
+/* dst += src (fp32, 16-byte aligned): accumulates the parameter gradients of a network that runs several times in one
+ * training step (train_cycle applies each generator 2-3 times, model.py:683-704). */
+int fpg_add_f32(float* dst, const float* src, int64_t count, void* stream);
+
+/* Device-resident history buffer of generated images (get_buffer_image, model.py:275-294): pool holds 50 entries of
+ * entry_bytes; ctrl = device int32[2] {use_slot, store_slot}, -1 = none, decided by the host's random draws.
+ * out = use_slot >= 0 ? pool[use_slot] : cur; then pool[store_slot] = cur if store_slot >= 0 (same slot = exchange). */
+int fpg_history_exchange(const void* cur, void* pool, const int32_t* ctrl, void* out, int64_t entry_bytes,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Flood-mask thresholding -- (sigmoid(logit) > 0.5).float(), model.py:399-400, segmentation_model.py:244-248.

@@ -112,9 +112,32 @@ def test_sharded_loader_partitions_the_global_batch():
         per_rank.append(list(data.DeviceLoader(Rec(n), batch, rank=rank, world_size=world)))
     torch.manual_seed(5)
     single = list(data.DeviceLoader(Rec(n), batch * world))
-    merged = [a + (b if i < len(per_rank[1]) else []) for i, (a, b) in
-              enumerate(zip(per_rank[0], per_rank[1] + [[]] * len(per_rank[0])))]
-    assert merged == single
+    # every rank takes the same number of equally sized batches (the fused step's NCCL all-reduces need every rank):
+    # 23 samples over 2 ranks x 3 -> 4 global batches, the ragged last one completed by wrapping around
+    assert len(per_rank[0]) == len(per_rank[1]) == len(data.DeviceLoader(Rec(n), batch, world_size=world)) == 4
+    assert all(len(b) == batch for r in per_rank for b in r)
+    merged = [a + b for a, b in zip(per_rank[0], per_rank[1])]
+    assert merged[:-1] == single[:-1]
+    torch.manual_seed(5)
+    order = data.DeviceLoader(Rec(n), batch * world).order()
+    assert merged[-1] == single[-1] + order[:1]
+
+
+@pytest.mark.parametrize("n,batch,world", [(5, 4, 2), (7, 2, 4), (8, 2, 2), (1, 2, 2)])
+def test_sharded_loader_equal_step_counts(n, batch, world):
+    """dataset lengths that do not divide world * batch (and one shorter than a single global batch)"""
+    class Rec(_Indices):
+        def gather(self, idx):
+            return list(idx)
+
+    shards = []
+    for rank in range(world):
+        torch.manual_seed(9)
+        shards.append(list(data.DeviceLoader(Rec(n), batch, rank=rank, world_size=world)))
+    assert len({len(s) for s in shards}) == 1 and len(shards[0]) == -(-n // (batch * world))
+    assert all(len(b) == batch for s in shards for b in s)
+    seen = {i for s in shards for b in s for i in b}
+    assert seen == set(range(n))  # nothing is dropped
 
 
 def test_create_flood_dataset_without_data_returns_empty_loaders():

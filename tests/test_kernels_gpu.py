@@ -148,15 +148,18 @@ def test_conv_transpose_roundtrip():
     close_rms(dw, dw_ref, 5e-3, 5e-4, "convT weight grad")
 
 
+@pytest.mark.parametrize("f16", [False, True])
 @pytest.mark.parametrize("shape,halo,act", [((3, 64, 64, 256), 1, 1), ((2, 128, 128, 64), 3, 1),
                                             ((2, 31, 31, 512), 0, 2), ((2, 32, 32, 128), 0, 0),
                                             ((2, 16, 16, 16), 0, 1)])
-def test_instnorm_fwd_bwd(shape, halo, act):
+def test_instnorm_fwd_bwd(shape, halo, act, f16):
+    """f16: the pre-norm tensor y and the residual are fp16 buffers (FPG_DT_FP16), as in the generator trunk"""
     from fpgan import ops
     n, h, w, c = shape
     g = torch.Generator(device="cuda").manual_seed(7)
-    y = bf16r(torch.randn(n, c, h, w, device="cuda", generator=g) * 3 + 0.5).requires_grad_(True)
-    res = bf16r(torch.randn(n, c, h, w, device="cuda", generator=g))
+    rnd = (lambda t: t.half().float()) if f16 else bf16r
+    y = rnd(torch.randn(n, c, h, w, device="cuda", generator=g) * 3 + 0.5).requires_grad_(True)
+    res = rnd(torch.randn(n, c, h, w, device="cuda", generator=g))
     fn = {0: lambda t: t, 1: F.relu, 2: lambda t: F.leaky_relu(t, 0.2)}[act]
     zi = fn(F.instance_norm(y, eps=1e-5)) + res
     z = F.pad(zi, (halo,) * 4, "reflect") if halo else zi
@@ -164,12 +167,15 @@ def test_instnorm_fwd_bwd(shape, halo, act):
     dz2 = bf16r(torch.randn_like(zi))
     (dy_ref,) = torch.autograd.grad([z, zi], y, [dz, dz2])
 
-    yb = ops.ActBuf.from_nchw(y.detach())
-    rb = ops.ActBuf.from_nchw(res)
+    yb = ops.ActBuf.from_nchw(y.detach(), f16=f16)
+    rb = ops.ActBuf.from_nchw(res, f16=f16)
     zb = ops.ActBuf(n, h, w, c, halo=halo)
+    skip = ops.ActBuf(n, h, w, c, f16=True, zero=False)
     stats = torch.empty(n * c * 2, device="cuda")
     ops.instnorm_stats(yb, stats)
-    ops.instnorm_apply(yb, stats, act, zb, residual=rb)
+    ops.instnorm_apply(yb, stats, act, zb, residual=rb, skip_out=skip)
+    # the skip-stream copy: same values, rounded to fp16 instead of bf16 (8x finer)
+    close_rms(skip.to_nchw(), zi.detach(), 0.003, 0.0005, "instnorm apply: fp16 skip stream")
     st = stats.view(n, c, 2)
     torch.testing.assert_close(st[..., 0], y.detach().mean((2, 3)), rtol=1e-3, atol=2e-3)
     torch.testing.assert_close(st[..., 1], (y.detach().var((2, 3), unbiased=False) + 1e-5).rsqrt(), rtol=1e-3,
@@ -203,8 +209,9 @@ def test_instnorm_fwd_bwd(shape, halo, act):
     close_rms(out.to_nchw(), dres_ref, 0.02, 0.003, "halo_fold op")
 
 
+@pytest.mark.parametrize("f16", [False, True])
 @pytest.mark.parametrize("act,with_add", [(1, False), (0, True), (1, True)])
-def test_dgrad_with_instnorm_backward_statistics(act, with_add):
+def test_dgrad_with_instnorm_backward_statistics(act, with_add, f16):
     """conv_dgrad_inbwd + instnorm_bwd_apply == autograd of conv(reflect_pad(act(IN(y)) [+ skip])) w.r.t. y and the
     skip input: the reduction pass of the InstanceNorm backward runs in the data-gradient kernel's epilogue (halo
     positions weighted with the statistics of the pixel they mirror, skip gradient merged on the interior)."""
@@ -225,7 +232,7 @@ def test_dgrad_with_instnorm_backward_statistics(act, with_add):
 
     spec = ops.ConvSpec(3, 3, 1, 0, c, k)
     spec.pack(wt.contiguous())
-    yb = ops.ActBuf.from_nchw(y.detach())
+    yb = ops.ActBuf.from_nchw(y.detach(), f16=f16)
     stats = torch.empty(n * c * 2, device="cuda")
     ops.instnorm_stats(yb, stats)
     dyb = ops.ActBuf.from_nchw(dout)
@@ -457,9 +464,11 @@ def test_dropout_mask_is_reproducible_and_fair():
     (3, 31, 31, 256, 512, 4, 1, 1, 0, False),    # PatchGAN model.8: ragged tiles, two n-blocks
     (2, 32, 32, 256, 128, 3, 2, 1, 0, True),     # transposed conv: four parity-class launches share the partials
 ])
-def test_conv_with_epilogue_statistics(case):
+@pytest.mark.parametrize("f16", [False, True])
+def test_conv_with_epilogue_statistics(case, f16):
     """{mean, rstd} per (image, channel) from the conv epilogue (no separate pass) vs torch on the stored output;
-    also in batch mode (BatchNorm statistics)."""
+    also in batch mode (BatchNorm statistics). f16: the output is an fp16 buffer (pre-norm tensors of the InstanceNorm
+    networks) -- the stored values must be the fp16 rounding of what the bf16 launch rounds to bf16."""
     from fpgan import ops
     n, h, w, c, k, r, stride, pad, halo, transposed = case
     g = torch.Generator(device="cuda").manual_seed(21)
@@ -469,7 +478,7 @@ def test_conv_with_epilogue_statistics(case):
         spec = ops.ConvSpec(r, r, stride, pad, ops.pad16(k), ops.pad16(c), c_in_valid=k, c_out_valid=c)
         spec.pack(wt.contiguous())
         xb = ops.ActBuf.from_nchw(x)
-        yb = ops.ActBuf(n, 2 * h, 2 * w, ops.pad16(k))
+        yb = ops.ActBuf(n, 2 * h, 2 * w, ops.pad16(k), f16=f16)
     else:
         x = bf16r(torch.randn(n, c, h, w, device="cuda", generator=g) + 0.2)
         wt = bf16r(torch.randn(k, c, r, r, device="cuda", generator=g) / (c * r * r) ** 0.5)
@@ -477,7 +486,7 @@ def test_conv_with_epilogue_statistics(case):
         spec.pack(wt.contiguous())
         xb = ops.ActBuf.from_nchw(x, halo=halo)
         hp, wp = h + 2 * halo, w + 2 * halo
-        yb = ops.ActBuf(n, (hp + 2 * pad - r) // stride + 1, (wp + 2 * pad - r) // stride + 1, ops.pad16(k))
+        yb = ops.ActBuf(n, (hp + 2 * pad - r) // stride + 1, (wp + 2 * pad - r) // stride + 1, ops.pad16(k), f16=f16)
     for batch in (False, True):
         stats = torch.zeros((1 if batch else n) * yb.c * 2, device="cuda")
         assert ops.conv_with_stats(xb, spec, yb, stats, transposed=transposed, batch=batch)
@@ -487,9 +496,12 @@ def test_conv_with_epilogue_statistics(case):
         st = stats.view(-1, yb.c, 2)
         torch.testing.assert_close(st[..., 0].reshape(mean.shape), mean, rtol=1e-3, atol=2e-4)
         torch.testing.assert_close(st[..., 1].reshape(var.shape), (var + 1e-5).rsqrt(), rtol=1e-3, atol=1e-3)
-    ref = ops.ActBuf(yb.n, yb.h, yb.w, yb.c)
+    ref = ops.ActBuf(yb.n, yb.h, yb.w, yb.c, fp32=f16)
     if transposed:
         ops.conv_dgrad(xb, spec, ref)
     else:
         ops.conv_fprop(xb, spec, ref)
-    assert torch.equal(ref.t, yb.t), "the statistics epilogue must not change the convolution output"
+    if f16:  # the fp32 launch shows the accumulators: the fp16 store is their round-to-nearest
+        assert torch.equal(ref.t.half(), yb.t), "fp16 output != fp16 rounding of the fp32 accumulators"
+    else:
+        assert torch.equal(ref.t, yb.t), "the statistics epilogue must not change the convolution output"

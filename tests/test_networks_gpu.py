@@ -4,10 +4,11 @@ fp32 restatement pinned to the reference by tests/test_oracle_cpu.py), on identi
 Tolerances (bf16 bound of north_star; measured values are printed with `-s`):
   * per-step losses: rtol 2e-2 (LOSS_RTOL); measured 1e-3 .. 2e-3.
   * forward tensors (generator output, attention mask, PatchGAN logits): RMS error relative to the RMS of the oracle
-    tensor < OUT_TOL = 3e-2; measured 2.25e-2. An element-wise rtol is meaningless for values near zero. A CPU
-    simulation that rounds weights, conv inputs, conv outputs and the residual stream to bf16 inside the oracle gives
-    2.27e-2 (tests/sim_bf16_rounding.py), i.e. the kernels sit exactly at the bf16 floor; the reference itself is
-    2.4e-2 away from its fp32 result under torch.autocast(bf16).
+    tensor < OUT_TOL = 2e-2 (north_star's bf16 bound). An element-wise rtol is meaningless for values near zero.
+    Round 1 stored every tensor as bf16 and measured 2.25e-2 = what a CPU simulation of the four rounding sites
+    (weights, conv inputs, conv outputs, residual stream) predicts (tests/sim_bf16_rounding.py: 2.27e-2). The two
+    sites no tensor-core instruction reads -- pre-norm conv outputs and the residual skip stream -- are now stored as
+    fp16 (same bytes, 3 more mantissa bits): simulated 1.75e-2, bf16 operand rounding alone being 1.74e-2.
   * parameter / input gradients: RMS-relative error < GRAD_TOL = 0.3. A forward deviation eps flips the ReLU /
     LeakyReLU mask of a fraction ~0.8*eps of the elements (those whose pre-activation lies within the noise of zero);
     each flip is a 100% element error, so one activation stage alone contributes sqrt(0.8*eps) ~ 13% for eps = 2%.
@@ -25,7 +26,7 @@ sys.path.insert(0, ROOT)
 pytestmark = pytest.mark.gpu
 
 LOSS_RTOL = 2e-2
-OUT_TOL = 3e-2
+OUT_TOL = 2e-2
 GRAD_TOL = 0.3
 
 
@@ -172,6 +173,57 @@ def test_fused_paired_step_matches_oracle_and_reference_golden(size, batch, step
     sd = G.state_dict()
     e = rel_rms(sd["resnet_blocks.4.conv1.weight"], otr.G["resnet_blocks.4.conv1.weight"])
     assert e < 0.1, f"weights drifted: {e}"
+
+
+def test_fused_paired_step_at_the_benchmarked_configuration():
+    """ONE fused train_paired step at BASELINE configs[1] -- batch 16, 256x256, 9 channels -- against the oracle's
+    fp32 CPU step on the same inputs: losses rtol 2e-2, generated images < OUT_TOL. At this batch the planner picks
+    kernels the small cases never launch (2-CTA fprop, row-stationary 7x7 heads at full width, CTA-pair wgrad); the
+    kernel names recorded by CUPTI during the step are checked so that the parity claim covers them."""
+    from fpgan.trainer import PairedTrainer
+    O, nets, G, D = make_pair()
+    batch, size = 16, 256
+    x, y = O.synthetic_batch(0, batch, 9, size)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref = O.PairedTrainer(nets).step(x, y)
+    tr = PairedTrainer(G, D)
+    names = set()
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            synth = tr.step(x.cuda(), y.cuda())
+            torch.cuda.synchronize()
+        names = {e.name for e in prof.events() if "fpg::" in e.name}
+    except Exception as exc:  # CUPTI not usable on this box: the plan flags below still pin the kernel choice
+        print(f"[parity] kernel-name capture unavailable ({exc})")
+        synth = tr.step(x.cuda(), y.cuda())
+    got = tr.losses()
+    e_out = rel_rms(synth, ref["synthetic"])
+    print(f"\n[parity] B=16 256x256 step: output rel-rms err {e_out:.4f}; losses " +
+          ", ".join(f"{got[k]:.5f}/{ref[k]:.5f}" for k in PairedTrainer.LOSS_KEYS))
+    assert e_out < OUT_TOL, e_out
+    for k in PairedTrainer.LOSS_KEYS:
+        assert abs(got[k] - ref[k]) <= LOSS_RTOL * abs(ref[k]) + 1e-4, f"{k}: {got[k]} vs oracle {ref[k]}"
+    if names:
+        for want in ("igemm_fprop2_kernel", "igemm_rows_kernel", "igemm_wgrad2_kernel", "igemm_fprop_kernel",
+                     "in_apply_ring_kernel", "blend_fwd_kernel", "adam"):
+            assert any(want in n for n in names), f"{want} was not launched at the benchmarked configuration: {sorted(names)}"
+    # the same facts from the planners (pure host code): residual conv -> CTA pair, 7x7 head -> row-stationary
+    import ctypes as C
+    from fpgan import lib as L, ops
+    spec = tr.G.layers["resnet_blocks.0.conv1"].spec
+    xb = ops.ActBuf(batch, 64, 64, 256, halo=1, zero=False)
+    yb = ops.ActBuf(batch, 64, 64, 256, zero=False)
+    d = L.FpropDesc()
+    L.call("fpg_conv2d_fprop_plan", xb.ref(), ops._ptr(spec.w_fprop), None, 0, spec.gref(), yb.ref(),
+           L.load().fpg_sm_count(), C.byref(d))
+    assert d.cta_pair == 1
+    head = tr.G.layers["deconv3_content"].spec
+    vb = ops.ActBuf(batch, 256, 256, 64, halo=3, zero=False)
+    cb = ops.ActBuf(batch, 256, 256, 32, fp32=True, zero=False)
+    rd = L.RowsDesc()
+    assert L.load().fpg_conv2d_rows_plan(vb.ref(), ops._ptr(head.w_fprop), None, 0, head.gref(), cb.ref(), 0,
+                                         L.load().fpg_sm_count(), C.byref(rd)) == 0
 
 
 def test_model_train_paired_api_and_checkpoint_roundtrip(tmp_path):
