@@ -4,7 +4,9 @@ synthetic 256x256 tiles (resize=512, crop=4, topography=all -> 9 input channels)
 compute with fp32 accumulation.
 
     python bench.py --gpus N --steps K --warmup W            # this implementation (N>1: launched by torchrun)
-    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the UNMODIFIED reference on the host CPU (oracle/_ref)
+    python bench.py --model cyclegan|attentiongan [--identity]   # BASELINE configs[3]: the fused train_cycle step
+    torchrun ... bench.py --gpus N --check [--model ...]     # data-parallel parity: N ranks x B/N vs one rank x B
 
 Prints ONE JSON line (rank 0). See DESIGN.md section "Measurement" for the definition of every field.
 """
@@ -26,8 +28,23 @@ _RESULT_OUT = sys.stdout
 TILE = 256
 CHANNELS = 9
 BATCH_PER_GPU = 16
-GFLOP_PER_TILE = 397.31           # algorithmic FLOPs of one paired step per tile
+# algorithmic GFLOP of one training step per tile, by (model, identity loss)
+GFLOP_PER_TILE = {("pairedattention", False): 397.31, ("cyclegan", False): 1314.1, ("cyclegan", True): 1916.2,
+                  ("attentiongan", False): 1491.5, ("attentiongan", True): 2182.2}
 RES_CONV_GFLOP_PER_TILE = 4.8318  # one residual 3x3 conv, 256->256 @ 64x64: 2 * 4096 * 256 * 2304
+PRETTY = {"pairedattention": "PairedAttention", "cyclegan": "CycleGAN", "attentiongan": "AttentionGAN"}
+
+
+def workload_config(model, identity, batch, world):
+    """`config` of the JSON line: identical keys and values on the native and the reference arm"""
+    if model == "pairedattention":
+        what = "PairedAttention train_paired step"
+    else:
+        what = f"{PRETTY[model]} train_cycle step" + (" with identity loss" if identity else "")
+    return {"workload": f"{what}, 256x256 tiles (resize=512 crop=4), 9 input channels (topography=all), batch "
+                        f"{batch} per GPU", "batch_per_gpu": batch, "global_batch": batch * world,
+            "parallelism": f"dp{world}",
+            "l2": "per-step working set (>5 GB of activations) far exceeds the 126 MB L2"}
 
 
 def ncu_traffic_bytes(report="r01_res_fprop.ncu-rep"):
@@ -111,13 +128,37 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-def cpu_reference_tiles_per_s(steps, warmup, batch=1):
-    """The reference algorithm on the host CPU: oracle port of Model.train_paired, fp32, all host threads."""
-    from oracle import gan_oracle as O
+def _synthetic_host_batches(first, steps, batch):
+    out = []
+    for step in range(first, first + steps):
+        g = torch.Generator().manual_seed(1000 + step)
+        x = torch.rand(batch, CHANNELS, TILE, TILE, generator=g) * 2 - 1
+        y = torch.rand(batch, 3, TILE, TILE, generator=g) * 2 - 1
+        out.append((x, y, ("synthetic",) * batch))
+    return out
+
+
+def cpu_reference_tiles_per_s(steps, warmup, batch, model="pairedattention", identity=False):
+    """The reference on the host CPU, fp32, all host threads: the UNMODIFIED reference staged in oracle/_ref
+    (oracle/build_ref.py) driven through its own Model.train_paired() / train_cycle() -- kind "reference" -- or, when it
+    has not been staged, the oracle's restatement of the same loop -- kind "port". Returns (tiles/s, seconds, cores,
+    kind)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    nets = O.init_model("pairedattention", "all", seed=47)
-    tr = O.PairedTrainer(nets)
+    cycle = model != "pairedattention"
+    from oracle import ref_runner
+    if ref_runner.available():
+        m = ref_runner.make_model(model, add_identity_loss=identity)
+        if warmup:
+            ref_runner.run_epoch(m, _synthetic_host_batches(0, warmup, batch), cycle)
+        data = _synthetic_host_batches(warmup, steps, batch)
+        t0 = time.perf_counter()
+        ref_runner.run_epoch(m, data, cycle)
+        dt = time.perf_counter() - t0
+        return batch * steps / dt, dt, cores, "reference"
+    from oracle import gan_oracle as O
+    nets = O.init_model(model, "all", seed=47)
+    tr = O.CycleTrainer(nets, model, add_identity_loss=identity) if cycle else O.PairedTrainer(nets)
     for s in range(warmup):
         tr.step(*O.synthetic_batch(s, batch, CHANNELS, TILE))
     data = [O.synthetic_batch(warmup + s, batch, CHANNELS, TILE) for s in range(steps)]
@@ -125,23 +166,33 @@ def cpu_reference_tiles_per_s(steps, warmup, batch=1):
     for x, y in data:
         tr.step(x, y)
     dt = time.perf_counter() - t0
-    return batch * steps / dt, dt, cores
+    return batch * steps / dt, dt, cores, "port"
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the step on this box's host cores, same `config`,
+    metric and unit as the native arm. A step is a bounded sample of the batch-16 workload: the per-step batch is the
+    largest of 16 / 8 / 4 / 2 / 1 tiles for which warm-up + timed steps fit in about three minutes (probed with one
+    batch-1 step); throughput is tiles/s either way."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warmup = args.steps, args.warmup
-    tps, dt, cores = cpu_reference_tiles_per_s(steps, warmup, batch=1)
-    sample = (f"oracle port of train_paired (oracle/gan_oracle.py), fp32, batch 1 of the batch-16 workload per step, "
+    probe, _, _, _ = cpu_reference_tiles_per_s(1, 1, 1, args.model, args.identity)
+    batch = BATCH_PER_GPU
+    while batch > 1 and (steps + warmup) * batch / probe > 180.0:
+        batch //= 2
+    tps, dt, cores, kind = cpu_reference_tiles_per_s(steps, warmup, batch, args.model, args.identity)
+    source = ("the unmodified reference (oracle/_ref, staged by oracle/build_ref.py) through its own Model."
+              f"{'train_cycle' if args.model != 'pairedattention' else 'train_paired'}()" if kind == "reference" else
+              "oracle port (oracle/gan_oracle.py) of the reference's training loop")
+    sample = (f"{source}, fp32, {cores} host threads, {batch} of the {BATCH_PER_GPU} tiles of a batch per step, "
               f"{steps} timed steps after {warmup} warm-up")
-    line = {"impl": "reference", "metric": "PairedAttention train tiles/s", "value": tps, "unit": "tiles/s",
+    line = {"impl": "reference", "metric": f"{PRETTY[args.model]} train tiles/s", "value": tps, "unit": "tiles/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1000 * dt / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "PairedAttention train_paired step, 256x256 tiles (resize=512 crop=4), 9 input "
-                                   "channels (topography=all), batch 16 per GPU"},
-            "cpu_baseline": {"value": tps, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(args.model, args.identity, BATCH_PER_GPU, args.gpus),
+            "cpu_baseline": {"value": tps, "unit": "tiles/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": tps, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
@@ -161,7 +212,8 @@ def run_native(args):
         raise SystemExit("bench.py: no CUDA device (this implementation has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("FPG_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # an NCCL_DEBUG set by the caller is honoured (stdout is already diverted to stderr, see main())
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     B, steps, warmup = args.batch, args.steps, args.warmup
@@ -178,9 +230,12 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    model = M.Model(model="PairedAttention", topography="all", num_epochs=1, resize=512, crop=4, seed=47,
-                    log_interval=1)
-    tr = model._ensure_native_paired()
+    cycle = args.model != "pairedattention"
+    model = M.Model(model=PRETTY[args.model], topography="all", num_epochs=1, resize=512, crop=4, seed=47,
+                    log_interval=1, add_identity_loss=args.identity)
+    tr = model._ensure_native_cycle() if cycle else model._ensure_native_paired()
+    train_api = model.train_cycle if cycle else model.train_paired
+    gflop_per_tile = GFLOP_PER_TILE[(args.model, args.identity)]
 
     # ---- (1) device-resident inputs: `value`
     loader = SyntheticLoader(steps=4, batch=B, channels=CHANNELS, size=TILE, rank=rank, world_size=world, pin=False)
@@ -206,13 +261,13 @@ def run_native(args):
     host = list(SyntheticLoader(steps=steps, batch=B, channels=CHANNELS, size=TILE, rank=rank, world_size=world))
     model.train_loader = host[:min(3, steps)]
     model.num_epochs = model.starting_epoch = 1
-    model.train_paired()  # warm-up epoch of the API path
+    train_api()  # warm-up epoch of the API path
     model.train_loader = host
     model.starting_epoch = model.num_epochs = 2
     barrier()
     e0.record()
     t0 = time.perf_counter()
-    model.train_paired()
+    train_api()
     e1.record()
     barrier()
     wall_ms = 1000 * (time.perf_counter() - t0)
@@ -238,25 +293,29 @@ def run_native(args):
         achieved = RES_CONV_GFLOP_PER_TILE * B / avg  # GFLOP / ms == TFLOP/s
         roofline = {"bound": "tensor", "kernel": "igemm_fprop2_kernel<64> (2-CTA tcgen05, residual 3x3 conv 256->256 @64x64)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "traffic": ncu_traffic_bytes(), "peak_source": peak_src + ", sustained bf16", "launches_timed": len(res_ms),
+                    "traffic": ncu_traffic_bytes(),
+                    "traffic_source": "committed ncu --set full capture of this kernel on this shape "
+                                      "(profiles/r01_ncu_kernels_v9.csv), not measured in this run",
+                    "peak_source": peak_src + ", sustained bf16", "launches_timed": len(res_ms),
                     "avg_ms": avg}
     conv_ms = sum(sum(v) for k, v in prof.items() if k.split()[0] in ("fprop", "dgrad", "wgrad")) / 2
     all_ms = sum(sum(v) for v in prof.values()) / 2
-    step_tflops = GFLOP_PER_TILE * B * world / (ms / steps)
+    step_tflops = gflop_per_tile * B * world / (ms / steps)
 
     if rank == 0:
-        cpu_tps, cpu_dt, cores = cpu_reference_tiles_per_s(steps=8, warmup=1, batch=1) if world == 1 else (None, 0, 0)
-        line = {"metric": "PairedAttention train tiles/s", "value": value, "unit": "tiles/s", "n_gpus": world,
+        cpu_tps = None
+        if world == 1:  # bounded sample: one warm-up + two timed batch-16 steps (paired: ~10-20 s of host work)
+            cpu_b = BATCH_PER_GPU if not cycle else 4
+            cpu_tps, cpu_dt, cores, cpu_kind = cpu_reference_tiles_per_s(2, 1, cpu_b, args.model, args.identity)
+        line = {"metric": f"{PRETTY[args.model]} train tiles/s", "value": value, "unit": "tiles/s", "n_gpus": world,
                 "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "PairedAttention train_paired step, 256x256 tiles (resize=512 crop=4), 9 input "
-                                       "channels (topography=all), batch 16 per GPU", "batch_per_gpu": B,
-                           "global_batch": B * world, "parallelism": f"dp{world}",
-                           "l2": "per-step working set (>5 GB of activations) far exceeds the 126 MB L2"},
+                "config": workload_config(args.model, args.identity, B, world),
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e, "unit": "tiles/s", "h2d_bytes_per_step": B * (CHANNELS + 3) * TILE * TILE * 4,
-                        "d2h_bytes_per_step": 16, "ms_per_step": e2e_ms / steps,
-                        "api": "models.model.Model.train_paired() with pinned host batches, log_interval=1"},
+                        "d2h_bytes_per_step": 4 * len(last_losses), "ms_per_step": e2e_ms / steps,
+                        "api": f"models.model.Model.{'train_cycle' if cycle else 'train_paired'}() with pinned host "
+                               "batches, log_interval=1"},
                 "gpu_launches": launches,
                 "roofline": roofline,
                 "step_tflops": step_tflops, "step_frac_of_peak": step_tflops / (peak_tf * world),
@@ -264,15 +323,79 @@ def run_native(args):
                 "kernel_ms_per_step": {k: sum(v) / 2 for k, v in sorted(prof.items(), key=lambda kv: -sum(kv[1]))[:12]},
                 "losses_last_step": last_losses}
         if cpu_tps is not None:
-            line["cpu_baseline"] = {"value": cpu_tps, "unit": "tiles/s", "cores": cores, "kind": "port",
-                                    "sample": "oracle port of train_paired, fp32, 8 timed batch-1 steps (256x256) "
-                                              "after 1 warm-up"}
+            line["cpu_baseline"] = {"value": cpu_tps, "unit": "tiles/s", "cores": cores, "kind": cpu_kind,
+                                    "sample": ("the unmodified reference (oracle/_ref) through its own Model training "
+                                               "loop" if cpu_kind == "reference" else "oracle port of the training "
+                                               "loop") + f", fp32, 2 timed batch-{cpu_b} steps (256x256) after 1 "
+                                              "warm-up"}
         print(json.dumps(line), file=_RESULT_OUT, flush=True)
+    model.close()  # captured NCCL work must be gone before the communicator is torn down
     if world > 1:
-        tr.release_graphs()  # captured NCCL work must be gone before the communicator is torn down
-        torch.cuda.synchronize()
+        dist.destroy_process_group()
+
+
+def run_dp_check(args):
+    """Data-parallel parity on hardware: W ranks x B/W tiles against ONE process x B tiles, same
+    seeds, three steps (two eager, one captured + replayed). Every rank computes the single-process run itself (no
+    collective), then the ranks run the sharded steps together. Reported: per-step max relative difference of the
+    (rank-averaged) losses and the relative RMS difference of all generator / discriminator weights at the end."""
+    import torch.distributed as dist
+    from fpgan import trainer as T
+    from models import model as M
+    from models.data import SyntheticLoader
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    assert B % world == 0, "--batch must divide by the number of ranks"
+    cycle = args.model != "pairedattention"
+    size = args.check_size
+
+    def build(world_size):
+        m = M.Model(model=PRETTY[args.model], topography="all", num_epochs=1, resize=512, crop=4, seed=47,
+                    add_identity_loss=args.identity)
+        if cycle:
+            return m, T.CycleTrainer(m.pre_to_post_generator, m.post_to_pre_generator, m.pre_discriminator,
+                                     m.post_discriminator, add_identity_loss=args.identity, world_size=world_size)
+        return m, T.PairedTrainer(m.generator, m.discriminator, world_size=world_size)
+
+    def run(tr, batch, r, w):
+        hist = []
+        for x, y, _ in SyntheticLoader(steps=3, batch=batch, channels=CHANNELS, size=size, rank=r, world_size=w,
+                                       pin=False):
+            tr.step(x.to(dev), y.to(dev))
+            hist.append(tr.losses())
+        return hist
+
+    m1, t1 = build(1)
+    single = run(t1, B, 0, 1)
+    w_single = torch.cat([t1.gp.flat, t1.dp.flat]).clone()
+    del t1
+    mw, tw = build(world)
+    sharded = run(tw, B // world, rank, world)
+    w_sharded = torch.cat([tw.gp.flat, tw.dp.flat])
+    diffs = [max(abs(a[k] - b[k]) / (abs(a[k]) + 1e-12) for k in a) for a, b in zip(single, sharded)]
+    w_err = ((w_sharded - w_single).norm() / w_single.norm()).item()
+    ok = diffs[0] <= 1e-5 and max(diffs) <= args.check_tol and w_err <= args.check_tol
+    if rank == 0:
+        print(json.dumps({"check": "data-parallel parity", "model": args.model, "world": world, "global_batch": B,
+                          "tile": size, "steps": 3, "loss_max_rel_diff_per_step": diffs,
+                          "weights_rel_rms_diff": w_err, "tolerance": {"step0": 1e-5, "later_and_weights": args.check_tol},
+                          "ok": bool(ok), "losses_single": single[-1], "losses_sharded": sharded[-1]}),
+              file=_RESULT_OUT, flush=True)
+    tw.release_graphs()
+    torch.cuda.synchronize()
+    if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not ok:
+        raise SystemExit(3)
 
 
 def main():
@@ -287,9 +410,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--model", default="pairedattention", choices=sorted(PRETTY),
+                    help="pairedattention (BASELINE configs[1]/[2], default) or the cycle models of configs[3]")
+    ap.add_argument("--identity", action="store_true", help="cycle models: add the identity loss (model.py:700-702)")
+    ap.add_argument("--check", action="store_true", help="data-parallel parity check instead of a benchmark")
+    ap.add_argument("--check_size", type=int, default=TILE)
+    ap.add_argument("--check_tol", type=float, default=2e-3)
     args = ap.parse_args()
+    args.model = args.model.lower()
     args.warmup = max(args.warmup, 3) if args.impl == "native" else args.warmup
-    if args.impl == "reference":
+    if args.check:
+        run_dp_check(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_native(args)

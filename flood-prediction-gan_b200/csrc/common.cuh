@@ -269,10 +269,9 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 // fp16 pairs (FPG_DT_FP16 tensors: pre-normalisation conv outputs, the residual skip stream). Stores saturate to the
 // largest finite fp16 instead of producing inf.
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  lo = fminf(fmaxf(lo, -65504.f), 65504.f);
-  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
-  __half2 v = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t u;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(hi), "f"(lo));  // one instruction, saturating
+  return u;
 }
 __device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
   __half2 v = *reinterpret_cast<__half2*>(&u);
@@ -285,9 +284,13 @@ __device__ __forceinline__ uint32_t pack_2x16(float lo, float hi, int dt) {
 __device__ __forceinline__ float2 unpack_2x16(uint32_t u, int dt) {
   return dt == 2 ? unpack_f16x2(u) : unpack_bf16x2(u);
 }
+__device__ __forceinline__ float round_f16(float v) {
+  uint16_t h;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+  return __half2float(__ushort_as_half(h));
+}
 __device__ __forceinline__ float round_16(float v, int dt) {
-  return dt == 2 ? __half2float(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)))
-                 : __bfloat162float(__float2bfloat16(v));
+  return dt == 2 ? round_f16(v) : __bfloat162float(__float2bfloat16(v));
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -79,15 +79,17 @@ __device__ __forceinline__ void cvt8(const uint4& u, float (&f)[8]) {
 __device__ __forceinline__ uint4 ld16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
 // the same for a tensor whose 2-byte element type is a kernel-uniform flag (bf16 or fp16)
 __device__ __forceinline__ void cvt8t(const uint4& u, float (&f)[8], int dt) {
-  float2 a = unpack_2x16(u.x, dt), b = unpack_2x16(u.y, dt), c = unpack_2x16(u.z, dt), d = unpack_2x16(u.w, dt);
+  if (dt != 2) return cvt8(u, f);
+  float2 a = unpack_f16x2(u.x), b = unpack_f16x2(u.y), c = unpack_f16x2(u.z), d = unpack_f16x2(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
 __device__ __forceinline__ void load8t(const __nv_bfloat16* p, float (&f)[8], int dt) {
   cvt8t(*reinterpret_cast<const uint4*>(p), f, dt);
 }
 __device__ __forceinline__ void store8t(__nv_bfloat16* p, const float (&f)[8], int dt) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(pack_2x16(f[0], f[1], dt), pack_2x16(f[2], f[3], dt),
-                                            pack_2x16(f[4], f[5], dt), pack_2x16(f[6], f[7], dt));
+  if (dt != 2) return store8(p, f);
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]),
+                                            pack_f16x2(f[6], f[7]));
 }
 
 // ------------------------------------------------------------------------------------------------ IN statistics

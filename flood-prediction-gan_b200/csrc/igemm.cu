@@ -97,12 +97,16 @@ __device__ __forceinline__ float warp_colsum16(float (&a)[16], int lane) {
 __device__ __forceinline__ void stat_accumulate(const StatOut& so, const float (&f)[16], bool valid, int lane,
                                                 int64_t prow, int col0, int dt) {
   float a[16], b[16];
+  // statistics of the values as stored (bf16 or fp16); the element type is kernel-uniform: one branch, not 16 selects
+  if (dt == 2) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float r = valid ? round_16(f[i], dt) : 0.f;  // statistics of the values as stored (bf16 or fp16)
-    a[i] = r;
-    b[i] = r * r;
+    for (int i = 0; i < 16; ++i) a[i] = valid ? round_f16(f[i]) : 0.f;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = valid ? __bfloat162float(__float2bfloat16(f[i])) : 0.f;
   }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) b[i] = a[i] * a[i];
   const float sa = warp_colsum16(a, lane);
   const float sb = warp_colsum16(b, lane);
   if ((lane & 1) == 0) {
@@ -132,10 +136,16 @@ __device__ __forceinline__ void unpack_16x8(const uint4& u, float* f, int dt) {
 // 16 fp32 values -> 32 bytes of bf16 or fp16 at dst
 __device__ __forceinline__ void store_16x16(void* dst_, const float (&f)[16], int dt) {
   uint4* dst = reinterpret_cast<uint4*>(dst_);
-  dst[0] = make_uint4(pack_2x16(f[0], f[1], dt), pack_2x16(f[2], f[3], dt), pack_2x16(f[4], f[5], dt),
-                      pack_2x16(f[6], f[7], dt));
-  dst[1] = make_uint4(pack_2x16(f[8], f[9], dt), pack_2x16(f[10], f[11], dt), pack_2x16(f[12], f[13], dt),
-                      pack_2x16(f[14], f[15], dt));
+  if (dt == 2) {
+    dst[0] = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+    dst[1] = make_uint4(pack_f16x2(f[8], f[9]), pack_f16x2(f[10], f[11]), pack_f16x2(f[12], f[13]),
+                        pack_f16x2(f[14], f[15]));
+  } else {
+    dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                        pack_bf16x2(f[6], f[7]));
+    dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                        pack_bf16x2(f[14], f[15]));
+  }
 }
 
 // InstanceNorm-backward variant of stat_accumulate: f = the 16 values about to be stored for this thread's pixel,

@@ -262,11 +262,15 @@ class _ResnetGeneratorNet(_NetBase):
     def _block_names(self, i):
         raise NotImplementedError
 
-    def _trunk_forward(self, x, t):
-        B, C, H, W = x.shape
+    def _trunk_forward(self, x, t, xin=None):
+        """x: fp32 NCHW input, or xin: the input already packed (bf16 NHWC, 16 channels, reflect halo 3)"""
         c1, c2, c3 = self.STEM
-        t["xin"] = ActBuf(B, H, W, 16, halo=3, zero=False)
-        ops.pack_nchw(x, t["xin"], 0, zero_rest=True)
+        if xin is None:
+            B, C, H, W = x.shape
+            xin = ActBuf(B, H, W, 16, halo=3, zero=False)
+            ops.pack_nchw(x, xin, 0, zero_rest=True)
+        assert xin.halo == 3 and xin.c == 16
+        t["xin"] = xin
         t["y1"], t["s1"], t["z1"] = self._conv_in(t["xin"], c1, ACT_RELU, 0)
         t["y2"], t["s2"], t["z2"] = self._conv_in(t["z1"], c2, ACT_RELU, 0)
         # the residual stream x_i is carried twice: bf16 with its reflect halo (the tensor-core operand of the next
@@ -352,10 +356,20 @@ class _ResnetGeneratorNet(_NetBase):
         ops.instnorm_bwd(dz1, t["y1"], t["s1"], ACT_RELU, dy1)
         return self._conv_bwd(c1, t["xin"], dy1, grads, need_dx, dx_halo=3)
 
-    def _input_grad_nchw(self, t, dxin, extra_rgb=None):
+    def _input_grad_nchw(self, t, dxin, extra_rgb=None, rgb_only=False):
+        """fp32 NCHW gradient w.r.t. the network input from the haloed NHWC gradient of the stem (+ extra_rgb, the
+        gradient the blend sends to the pre-flood RGB directly). rgb_only: only the three image channels
+        [B, 3, H, W] (what train_cycle's second generator pass sends back to the first), native kernels only."""
         xin = t["xin"]
         folded = ActBuf(xin.n, xin.h, xin.w, 16, zero=False)
         ops.halo_fold(dxin, None, folded)
+        if rgb_only:
+            if extra_rgb is not None:
+                ops.unpack_nchw(folded, extra_rgb, 0, accumulate=True)
+                return extra_rgb
+            dx = torch.empty(xin.n, 3, xin.h, xin.w, dtype=torch.float32, device=xin.t.device)
+            ops.unpack_nchw(folded, dx, 0)
+            return dx
         c_in = self.layers[self.STEM[0]].c_valid
         dx = torch.zeros(xin.n, c_in, xin.h, xin.w, dtype=torch.float32, device=xin.t.device)
         ops.unpack_nchw(folded, dx, 0)
@@ -386,26 +400,28 @@ class AttentionGeneratorNet(_ResnetGeneratorNet):
     def _block_names(self, i):
         return f"resnet_blocks.{i}.conv1", f"resnet_blocks.{i}.conv2"
 
-    def forward(self, x, d_input=None, d_c0=0, want_nchw=True):
-        """x: fp32 NCHW [B, C<=16, H, W]. Returns (out_nchw, tape). If d_input (ActBuf [B,H,W,16]) is given the
-        generated image is also written as bf16 into its channels [d_c0, d_c0+3)."""
+    def forward(self, x, d_input=None, d_c0=0, want_nchw=True, xin=None):
+        """x: fp32 NCHW [B, C<=16, H, W] (or xin: the packed input, see _trunk_forward). Returns (out_nchw, tape). If
+        d_input (ActBuf [B,H,W,16]) is given the generated image is also written as bf16 into its channels
+        [d_c0, d_c0+3)."""
         self.repack()
-        B, C, H, W = x.shape
         t = {}
-        xtop = self._trunk_forward(x, t)
+        xtop = self._trunk_forward(x, t, xin)
+        B, H, W = t["xin"].n, t["xin"].h, t["xin"].w
+        dev = t["xin"].t.device
         t["content"] = self._decoder_forward(xtop, "deconv1_content", "deconv2_content", 3)
         t["attention"] = self._decoder_forward(xtop, "deconv1_attention", "deconv2_attention", 0)
         t["c"] = self._conv(t["content"][5], "deconv3_content", fp32=True, act=ACT_TANH)
         t["l"] = self._conv(t["attention"][5], "deconv3_attention", fp32=True)
-        out = torch.empty(B, 3, H, W, dtype=torch.float32, device=x.device) if want_nchw else None
-        mask = torch.empty(B, H, W, dtype=torch.float32, device=x.device)
+        out = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev) if want_nchw else None
+        mask = torch.empty(B, H, W, dtype=torch.float32, device=dev)
         ops.blend_fwd(t["c"], t["l"], t["xin"], out=d_input, out_c0=d_c0, out_nchw=out, mask=mask)
         t["mask"] = mask
         return out, t
 
-    def backward(self, t, grads, dout_nchw=None, dout_nhwc=None, dout_c0=0, need_dx=False):
+    def backward(self, t, grads, dout_nchw=None, dout_nhwc=None, dout_c0=0, need_dx=False, rgb_only=False):
         """Writes every parameter gradient of this call into `grads` (overwrite, no accumulation).
-        Returns the fp32 NCHW input gradient if need_dx."""
+        Returns the fp32 NCHW input gradient if need_dx (rgb_only: its three image channels only)."""
         xin = t["xin"]
         B, H, W = xin.n, xin.h, xin.w
         dc = ActBuf(B, H, W, 32, zero=False)
@@ -420,7 +436,7 @@ class AttentionGeneratorNet(_ResnetGeneratorNet):
             dv2 = self._conv_bwd(head, v2, dhead, grads, True, dx_halo=v2.halo)
             gx.append(self._decoder_backward(t[br], xtop, dv2, f"deconv1_{br}", f"deconv2_{br}", grads))
         dxin = self._trunk_backward(t, gx[0], gx[1], grads, need_dx)  # x_n gradient = sum of both decoder branches
-        return self._input_grad_nchw(t, dxin, dimg) if need_dx else None
+        return self._input_grad_nchw(t, dxin, dimg, rgb_only) if need_dx else None
 
 
 class CycleGANGeneratorNet(_ResnetGeneratorNet):
@@ -446,18 +462,21 @@ class CycleGANGeneratorNet(_ResnetGeneratorNet):
     def _block_names(self, i):
         return f"model.{10 + i}.conv_block.1", f"model.{10 + i}.conv_block.5"
 
-    def forward(self, x):
+    def forward(self, x, d_input=None, d_c0=0, xin=None):
+        """as AttentionGeneratorNet.forward"""
         self.repack()
-        B, C, H, W = x.shape
         t = {}
-        xtop = self._trunk_forward(x, t)
+        xtop = self._trunk_forward(x, t, xin)
+        B, H, W = t["xin"].n, t["xin"].h, t["xin"].w
         t["dec"] = self._decoder_forward(xtop, "model.19", "model.22", 3)
         t["o"] = self._conv(t["dec"][5], "model.26", fp32=True, act=ACT_TANH)  # fp32 NHWC, 3 of 16 channels valid
-        out = torch.empty(B, 3, H, W, dtype=torch.float32, device=x.device)
+        out = torch.empty(B, 3, H, W, dtype=torch.float32, device=t["xin"].t.device)
         ops.unpack_nchw(t["o"], out, 0)
+        if d_input is not None:
+            ops.pack_nchw(out, d_input, d_c0)
         return out, t
 
-    def backward(self, t, grads, dout_nchw, need_dx=False):
+    def backward(self, t, grads, dout_nchw, need_dx=False, rgb_only=False):
         o = t["o"]
         dpre = ActBuf(o.n, o.h, o.w, 16, zero=False)
         ops.tanh_bwd_pack(dout_nchw, o, dpre)
@@ -465,7 +484,7 @@ class CycleGANGeneratorNet(_ResnetGeneratorNet):
         dv2 = self._conv_bwd("model.26", v2, dpre, grads, True, dx_halo=3)
         gtop = self._decoder_backward(t["dec"], t[f"x{self.n_blocks}"], dv2, "model.19", "model.22", grads)
         dxin = self._trunk_backward(t, gtop, None, grads, need_dx)
-        return self._input_grad_nchw(t, dxin) if need_dx else None
+        return self._input_grad_nchw(t, dxin, rgb_only=rgb_only) if need_dx else None
 
 
 class PatchGANNet(_NetBase):

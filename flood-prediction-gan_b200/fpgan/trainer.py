@@ -8,6 +8,7 @@ Data parallelism: one process per GPU, each rank steps on its shard of the globa
 with NCCL over NVLink (bucketed, overlapped with the generator backward) and scaled by 1/world_size inside Adam.
 """
 import os
+import random
 
 import torch
 import torch.distributed as dist
@@ -17,12 +18,19 @@ from .ops import ActBuf
 
 
 class FlatParams:
-    """Re-homes a module's parameters into one flat fp32 buffer (each Parameter becomes a view), plus matching
-    flat gradient and Adam-moment buffers. state_dict() / load_state_dict() keep working on the views."""
+    """Re-homes the parameters of one module -- or of several modules that share an optimiser (train_cycle chains both
+    generators / both discriminators into one Adam, model.py:112-122) -- into one flat fp32 buffer (each Parameter
+    becomes a view), plus matching flat gradient and Adam-moment buffers: one Adam launch and one all-reduce per
+    optimiser. state_dict() / load_state_dict() keep working on the views. With several modules the names in
+    `named` / `offsets` are prefixed "<module index>."; `grads_of[i]` addresses module i's gradients by its own names."""
 
-    def __init__(self, module):
-        self.module = module
-        self.named = list(module.named_parameters())
+    def __init__(self, *modules):
+        self.modules = modules
+        self.module = modules[0]
+        if len(modules) == 1:
+            self.named = list(modules[0].named_parameters())
+        else:
+            self.named = [(f"{i}.{n}", p) for i, m in enumerate(modules) for n, p in m.named_parameters()]
         total = sum(p.numel() for _, p in self.named)
         dev = self.named[0][1].device
         self.flat = torch.empty(total, dtype=torch.float32, device=dev)
@@ -35,6 +43,7 @@ class FlatParams:
             self.offsets[n] = (off, k)
             off += k
         self.grads = networks.Grads(self.named)
+        self.grads_of = self._per_module(self.grads.flat)
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
         # {step, lr (float bits), step_size, sqrt(bias correction 2)}: the step count and learning rate live on the
@@ -42,6 +51,21 @@ class FlatParams:
         self.state = torch.zeros(4, dtype=torch.int32, device=dev)
         self._steps = 0
         self._lr = None
+
+    def _per_module(self, flat):
+        out, off = [], 0
+        for m in self.modules:
+            named = list(m.named_parameters())
+            size = sum(p.numel() for _, p in named)
+            out.append(networks.Grads(named, flat=flat[off:off + size]))
+            off += size
+        return out
+
+    def extra_grads(self):
+        """a second flat gradient buffer (+ per-module views) for a network that runs more than once per step; the
+        caller sums it into `grads.flat` (ops.add_f32) before the all-reduce / Adam"""
+        flat = torch.zeros_like(self.grads.flat)
+        return flat, self._per_module(flat)
 
     @property
     def steps(self):
@@ -244,3 +268,236 @@ class PairedTrainer:
             buf /= self.world_size
         vals = buf.tolist()
         return dict(zip(self.LOSS_KEYS, vals))
+
+
+class _History:
+    """Host side of the history buffer of generated images (get_buffer_image, model.py:275-294): the reference's
+    decisions, drawn from Python's global `random` in the reference's order, as {use_slot, store_slot} for the
+    device-resident pool (ops.history_exchange). The first 50 images are stored and returned as they are; afterwards
+    with probability 0.5 a random stored image is returned and replaced by the new one."""
+
+    SIZE = 50
+
+    def __init__(self):
+        self.count = 0
+
+    def decide(self):
+        if self.count < self.SIZE:
+            self.count += 1
+            return -1, self.count - 1
+        if random.uniform(0, 1) > 0.5:
+            idx = random.randint(0, self.SIZE - 1)
+            return idx, idx
+        return -1, -1
+
+
+class CycleTrainer:
+    """One `train_cycle` iteration (model.py:678-739) for CycleGAN / AttentionGAN, fused like PairedTrainer: no autograd
+    graph, native loss kernels, flat-buffer Adam over the chained generators / discriminators, device-resident history
+    buffers, one gradient all-reduce per optimiser phase, the whole step replayed as a CUDA graph.
+
+    Schedule of the reference: four generator passes (synthetic post / pre from the real images, recreated post / pre
+    from the synthetic ones with the topography conditions re-attached, :680-689), optional identity passes (:701-702),
+    generator update from the LSGAN terms through the frozen discriminators + 10 x cycle L1 (+ 5 x identity L1)
+    (:703-713), then the discriminator update on the real images and on images drawn from the history buffers
+    (:722-735). Each generator runs 2-3 times per step: every run writes its parameter gradients into its own flat
+    buffer, summed before Adam."""
+
+    def __init__(self, pre_to_post, post_to_pre, pre_discriminator, post_discriminator, add_identity_loss=False,
+                 world_size=1, group=None):
+        self.identity = add_identity_loss
+        # optimiser parameter order of the reference: generators (pre_to_post, post_to_pre), discriminators (post, pre)
+        self.gp = FlatParams(pre_to_post, post_to_pre)
+        self.dp = FlatParams(post_discriminator, pre_discriminator)
+        self.Gpp, self.Gpr = pre_to_post._executor(), post_to_pre._executor()
+        self.Dpost, self.Dpre = post_discriminator._executor(), pre_discriminator._executor()
+        self.g_extra = [self.gp.extra_grads() for _ in range(2 if add_identity_loss else 1)]
+        self.world_size, self.group = world_size, group
+        self.loss_keys = self.LOSS_KEYS + (self.IDENTITY_KEYS if add_identity_loss else ())
+        dev = self.gp.flat.device
+        self.loss_buf = torch.zeros(len(self.loss_keys), dtype=torch.float32, device=dev)
+        self.hist_pre, self.hist_post = _History(), _History()
+        self.hist_ctrl = torch.full((4,), -1, dtype=torch.int32, device=dev)  # {pre use, pre store, post use, post store}
+        self._pools = {}
+        self.use_graph = os.environ.get("FPG_CUDA_GRAPH", "1") != "0" and (
+            world_size == 1 or os.environ.get("FPG_CUDA_GRAPH_DDP", "1") == "1")
+        self._graphs, self._eager_calls = {}, {}
+        if world_size > 1:
+            import atexit
+            import weakref
+            ref = weakref.ref(self)
+            atexit.register(lambda: ref() is not None and ref().release_graphs())
+
+    LOSS_KEYS = ("losses_generator_post", "losses_generator_pre", "losses_pre_to_post_cycle",
+                 "losses_post_to_pre_cycle", "losses_discriminator_pre_real", "losses_discriminator_post_real",
+                 "losses_discriminator_pre_synthetic", "losses_discriminator_post_synthetic")
+    IDENTITY_KEYS = ("losses_identity_post", "losses_identity_pre")
+
+    def release_graphs(self):
+        self._graphs.clear()
+        self._eager_calls.clear()
+
+    def _pool(self, which, like):
+        """device pool of 50 packed discriminator inputs [50][B][H][W][16] bf16 for this batch shape"""
+        key = (which, tuple(like.t.shape))
+        if key not in self._pools:
+            self._pools[key] = torch.empty((_History.SIZE,) + tuple(like.t.shape), dtype=torch.bfloat16,
+                                           device=like.t.device)
+        return self._pools[key]
+
+    def step(self, input_stack, output_image, lr_g=0.0002, lr_d=0.0002):
+        """input_stack [B,C,H,W] (pre-flood RGB + topography conditions), output_image [B,3,H,W]: fp32 CUDA tensors.
+        Returns (synthetic_post, synthetic_pre) [B,3,H,W]; the losses are left in self.loss_buf in loss_keys order."""
+        self.gp.set_lr(lr_g)
+        self.dp.set_lr(lr_d)
+        # the reference draws the pre buffer's decision first, then the post buffer's (model.py:719-720)
+        ctrl = list(self.hist_pre.decide()) + list(self.hist_post.decide())
+        self.hist_ctrl.copy_(torch.tensor(ctrl, dtype=torch.int32))
+        out = None
+        if self.use_graph and ops.PROFILE is None:
+            key = (tuple(input_stack.shape), tuple(output_image.shape))
+            entry = self._graphs.get(key)
+            if entry is None and self._eager_calls.get(key, 0) >= 2:
+                entry = self._graphs[key] = self._capture(input_stack, output_image)
+            if entry is not None:
+                sx, sy, graph, out, launches = entry
+                sx.copy_(input_stack, non_blocking=True)
+                sy.copy_(output_image, non_blocking=True)
+                graph.replay()
+                ops.LAUNCHES += launches
+            else:
+                self._eager_calls[key] = self._eager_calls.get(key, 0) + 1
+        if out is None:
+            out = self._step_impl(input_stack, output_image)
+        self.gp.note_step()
+        self.dp.note_step()
+        return out
+
+    def _capture(self, input_stack, output_image):
+        sx, sy = input_stack.clone(), output_image.clone()
+        self._pool("pre", ActBuf(sx.shape[0], sx.shape[2], sx.shape[3], 16, zero=False))  # allocate outside the capture
+        self._pool("post", ActBuf(sx.shape[0], sx.shape[2], sx.shape[3], 16, zero=False))
+        before = ops.LAUNCHES
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self._step_impl(sx, sy)
+        launches = ops.LAUNCHES - before
+        ops.LAUNCHES = before
+        return sx, sy, graph, out, launches
+
+    def _step_impl(self, x_pre, y_post):
+        Gpp, Gpr, Dpost, Dpre = self.Gpp, self.Gpr, self.Dpost, self.Dpre
+        B, C, H, W = x_pre.shape
+        n_cond = C - 3
+        inv_w = 1.0 / self.world_size
+        lb = self.loss_buf
+        gpp0, gpr0 = self.gp.grads_of
+        (gflat1, (gpp1, gpr1)) = self.g_extra[0]
+        dpost_g, dpre_g = self.dp.grads_of
+
+        def cond_into(buf):
+            """channels 3.. = the topography conditions input_stack[:, 3:] (model.py:681-689); other channels zero"""
+            if n_cond:
+                ops.pack_nchw(x_pre[:, 3:], buf, 3, zero_rest=True)
+
+        def packed_input(rgb):
+            """generator input [rgb | conditions] as a packed, reflect-haloed operand"""
+            buf = ActBuf(B, H, W, 16, halo=3, zero=False)
+            if n_cond:
+                cond_into(buf)
+                ops.pack_nchw(rgb, buf, 0)
+            else:
+                ops.pack_nchw(rgb, buf, 0, zero_rest=True)
+            return buf
+
+        # discriminator inputs: [real | history] halves, and the current synthetic images for the generator phase
+        din_pre = ActBuf(2 * B, H, W, 16, zero=False)
+        din_post = ActBuf(2 * B, H, W, 16, zero=False)
+        ops.pack_nchw(x_pre, din_pre.batch_slice(0, B), 0, zero_rest=True)              # real pre = the input stack
+        real_post = din_post.batch_slice(0, B)
+        if n_cond:
+            cond_into(real_post)
+            ops.pack_nchw(y_post, real_post, 0)
+        else:
+            ops.pack_nchw(y_post, real_post, 0, zero_rest=True)
+        fake_post = ActBuf(B, H, W, 16, zero=False)
+        fake_pre = ActBuf(B, H, W, 16, zero=False)
+        if n_cond:
+            cond_into(fake_post)
+            cond_into(fake_pre)
+        else:
+            fake_post.t.zero_()
+            fake_pre.t.zero_()
+
+        # ---- generator passes (:682-689)
+        synth_post, tA = Gpp.forward(x_pre, d_input=fake_post, d_c0=0)
+        synth_pre, tB = Gpr.forward(None, d_input=fake_pre, d_c0=0, xin=packed_input(y_post))
+        rec_post, tC = Gpp.forward(None, xin=packed_input(synth_pre))
+        rec_pre, tD = Gpr.forward(None, xin=packed_input(synth_post))
+
+        # ---- generator update (:692-713)
+        if self.identity:                                                                 # :700-702
+            (gflat2, (gpp2, gpr2)) = self.g_extra[1]
+            idt_post, tE = Gpp.forward(None, xin=packed_input(y_post))
+            d_idt = torch.empty_like(idt_post)
+            ops.l1_loss(idt_post, y_post, 5.0, 1.0, lb[8:9], dpred=d_idt)
+            Gpp.backward(tE, gpp2, dout_nchw=d_idt)
+            del tE
+            idt_pre, tF = Gpr.forward(x_pre)
+            d_idt2 = torch.empty_like(idt_pre)
+            ops.l1_loss(idt_pre, x_pre[:, :3], 5.0, 1.0, lb[9:10], dpred=d_idt2)
+            Gpr.backward(tF, gpr2, dout_nchw=d_idt2)
+            del tF
+        # cycle terms (:710-711) through the second passes, back to the synthetic images
+        d_rec_post = torch.empty_like(rec_post)
+        ops.l1_loss(rec_post, y_post, 10.0, 1.0, lb[3:4], dpred=d_rec_post)
+        g_synth_pre = Gpp.backward(tC, gpp1, dout_nchw=d_rec_post, need_dx=True, rgb_only=True)
+        del tC
+        d_rec_pre = torch.empty_like(rec_pre)
+        ops.l1_loss(rec_pre, x_pre[:, :3], 10.0, 1.0, lb[2:3], dpred=d_rec_pre)
+        g_synth_post = Gpr.backward(tD, gpr1, dout_nchw=d_rec_pre, need_dx=True, rgb_only=True)
+        del tD
+        # adversarial terms (:704-709) through the frozen discriminators: only the input gradient
+        for D, fake, slot, g_synth in ((Dpost, fake_post, 0, g_synth_post), (Dpre, fake_pre, 1, g_synth_pre)):
+            logits, tape = D.forward_buf(fake)
+            dlog = ActBuf(B, logits.h, logits.w, 16, zero=False)
+            ops.mse_const_loss(logits, 1.0, 1.0, 1.0, lb[slot:slot + 1], dlog)
+            d_din = D.backward(tape, dlog, None, need_dx=True)
+            ops.unpack_nchw(d_din, g_synth, 0, accumulate=True)  # + the image channels of the discriminator's input gradient
+        Gpp.backward(tA, gpp0, dout_nchw=g_synth_post)
+        del tA
+        Gpr.backward(tB, gpr0, dout_nchw=g_synth_pre)
+        del tB
+        ops.add_f32(self.gp.grads.flat, gflat1)
+        if self.identity:
+            ops.add_f32(self.gp.grads.flat, gflat2)
+        if self.world_size > 1:
+            dist.all_reduce(self.gp.grads.flat, group=self.group)
+        self.gp.adam(grad_scale=inv_w)
+        Gpp.repack(force=True)
+        Gpr.repack(force=True)
+
+        # ---- discriminator update (:716-735): real images vs images from the history buffers
+        ops.history_exchange(fake_pre.t, self._pool("pre", fake_pre), self.hist_ctrl[0:2], din_pre.t[B:])
+        ops.history_exchange(fake_post.t, self._pool("post", fake_post), self.hist_ctrl[2:4], din_post.t[B:])
+        for D, din, grads, k_real, k_syn in ((Dpre, din_pre, dpre_g, 4, 6), (Dpost, din_post, dpost_g, 5, 7)):
+            logits, tape = D.forward_buf(din)
+            dlog = ActBuf(2 * B, logits.h, logits.w, 16, zero=False)
+            ops.mse_const_loss(logits.batch_slice(0, B), 1.0, 1.0, 0.5, lb[k_real:k_real + 1], dlog.batch_slice(0, B))
+            ops.mse_const_loss(logits.batch_slice(B, B), 0.0, 1.0, 0.5, lb[k_syn:k_syn + 1], dlog.batch_slice(B, B))
+            D.backward(tape, dlog, grads, need_dx=False)
+        if self.world_size > 1:
+            dist.all_reduce(self.dp.grads.flat, group=self.group)
+        self.dp.adam(grad_scale=inv_w)
+        Dpre.repack(force=True)
+        Dpost.repack(force=True)
+        return synth_post, synth_pre
+
+    def losses(self):
+        """Host copy of the last step's losses (one device->host sync), averaged over ranks."""
+        buf = self.loss_buf.clone()
+        if self.world_size > 1:
+            dist.all_reduce(buf, group=self.group)
+            buf /= self.world_size
+        return dict(zip(self.loss_keys, buf.tolist()))

@@ -226,7 +226,8 @@ class Model:
         if self.verbose:
             print(f"Epoch {epoch} ({time.time() - epoch_start_time:.2f} seconds) ", end="")
             self.print_losses()
-        if self.save_model_interval != 0 and epoch % self.save_model_interval == 0:
+        if self.save_model_interval != 0 and epoch % self.save_model_interval == 0 and self._rank() == 0:
+            # data-parallel replicas hold identical weights and optimiser state: rank 0 writes the checkpoint
             self._sync_optimizer_state_for_save()
             saved = {"model": self.model, "starting_epoch": epoch + 1, "num_epochs": self.num_epochs,
                      "topography": self.topography,
@@ -333,20 +334,59 @@ class Model:
             return dist.get_world_size()
         return 1
 
+    def _rank(self):
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank()
+        return 0
+
+    def _adopt_optimizer_state(self):
+        """resume: adopt Adam moments stored in the torch optimisers (reference checkpoint layout)"""
+        for fp, opt in ((self._native.gp, self.optimizer_generator), (self._native.dp, self.optimizer_discriminator)):
+            for name, p in fp.named:
+                st = opt.state.get(p)
+                if st:
+                    off, k = fp.offsets[name]
+                    fp.m[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                    fp.v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                    fp.steps = int(st["step"])
+
     def _ensure_native_paired(self):
         if self._native is None:
             self._native = native_trainer.PairedTrainer(self.generator, self.discriminator, world_size=self._world())
-            # resume: adopt Adam moments stored in the torch optimisers (reference checkpoint layout)
-            for fp, opt in ((self._native.gp, self.optimizer_generator),
-                            (self._native.dp, self.optimizer_discriminator)):
-                for name, p in fp.named:
-                    st = opt.state.get(p)
-                    if st:
-                        off, k = fp.offsets[name]
-                        fp.m[off:off + k].copy_(st["exp_avg"].reshape(-1))
-                        fp.v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
-                        fp.steps = int(st["step"])
+            self._adopt_optimizer_state()
         return self._native
+
+    def _ensure_native_cycle(self):
+        if self._native is None:
+            self._native = native_trainer.CycleTrainer(
+                self.pre_to_post_generator, self.post_to_pre_generator, self.pre_discriminator,
+                self.post_discriminator, add_identity_loss=self.add_identity_loss, world_size=self._world())
+            self._adopt_optimizer_state()
+        return self._native
+
+    def close(self):
+        """Release the captured CUDA graphs of the fused steps. With data parallelism they hold NCCL work: call this
+        (then synchronise and barrier) before torch.distributed.destroy_process_group(), which hangs otherwise."""
+        if self._native is not None:
+            self._native.release_graphs()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        if self._world() > 1:
+            dist.barrier()
+
+    def _allreduce_module_grads(self, params):
+        """data parallelism of the module (autograd) path: sum the parameter gradients over ranks, average"""
+        world = self._world()
+        if world == 1:
+            return
+        grads = [p.grad for p in params if p.grad is not None]
+        flat = torch.cat([g.reshape(-1) for g in grads])
+        dist.all_reduce(flat)
+        flat /= world
+        off = 0
+        for g in grads:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
 
     def train_paired(self):
         """Paired training (reference :598-658). PairedAttention runs the fused native step; Pix2Pix (BatchNorm with
@@ -434,6 +474,7 @@ class Model:
                 d_syn = lsgan(D(concat_synth.detach()), 0.0)
                 d_real = lsgan(D(concat_real), 1.0)
                 ((d_syn + d_real) * 0.5).backward()
+                self._allreduce_module_grads(list(D.parameters()))
                 self.optimizer_discriminator.step()
                 for p in D.parameters():
                     p.requires_grad = False
@@ -441,15 +482,20 @@ class Model:
                 g_adv = lsgan(D(concat_synth), 1.0)
                 g_l1 = self.l1_loss(synthetic, y) * 100
                 (g_adv + g_l1).backward()
+                self._allreduce_module_grads(list(G.parameters()))
                 self.optimizer_generator.step()
-                vals = torch.stack([d_real.detach(), d_syn.detach(), g_adv.detach(), g_l1.detach()]).tolist()
+                vals = torch.stack([d_real.detach(), d_syn.detach(), g_adv.detach(), g_l1.detach()])
+                if self._world() > 1:
+                    dist.all_reduce(vals)
+                    vals /= self._world()
+                vals = vals.tolist()
                 for k, v in zip(native_trainer.PairedTrainer.LOSS_KEYS, vals):
                     losses[k].append(v)
             self.scheduler_discriminator.step()
             self.scheduler_generator.step()
             self.save_results(epoch=epoch, losses=losses, epoch_start_time=t0)
 
-    def _flush_losses(self, pending, losses, keep_last=0):
+    def _flush_losses(self, pending, losses, keep_last=0, keys=native_trainer.PairedTrainer.LOSS_KEYS):
         ready = pending[:len(pending) - keep_last]
         if not ready:
             return
@@ -460,11 +506,41 @@ class Model:
             vals /= self._world()
         vals = vals.tolist()  # one device->host sync for the whole interval
         for row in vals:
-            for k, v in zip(native_trainer.PairedTrainer.LOSS_KEYS, row):
+            for k, v in zip(keys, row):
                 losses[k].append(v)
 
     def train_cycle(self):
-        """Cycle training (reference :660-758) through the drop-in modules' autograd path."""
+        """Cycle training (reference :660-758): the fused native step (fpgan.trainer.CycleTrainer -- no autograd graph,
+        device-resident history buffers, gradient all-reduce per optimiser phase, CUDA-graph replay). FPG_CYCLE_MODULES=1
+        selects the reference loop over the drop-in modules' autograd path instead (single process only)."""
+        if os.environ.get("FPG_CYCLE_MODULES", "0") == "1":
+            return self._train_cycle_modules()
+        tr = self._ensure_native_cycle()
+        for epoch in range(self.starting_epoch, self.num_epochs + 1):
+            t0 = time.time()
+            losses = self.initialise_loss_storage(overall=False)
+            for net in (self.pre_to_post_generator, self.post_to_pre_generator, self.pre_discriminator,
+                        self.post_discriminator):
+                net.train()
+            torch.manual_seed(epoch)
+            lr_g = self.optimizer_generator.param_groups[0]["lr"]
+            lr_d = self.optimizer_discriminator.param_groups[0]["lr"]
+            pending = []
+            for x, y in self._prefetch_to_device(self.train_loader):
+                tr.step(x, y, lr_g=lr_g, lr_d=lr_d)
+                pending.append(tr.loss_buf.clone())
+                if len(pending) > self.log_interval:
+                    self._flush_losses(pending, losses, keep_last=1, keys=tr.loss_keys)
+            self._flush_losses(pending, losses, keys=tr.loss_keys)
+            self.scheduler_generator.step()
+            self.scheduler_discriminator.step()
+            self.save_results(epoch=epoch, losses=losses, epoch_start_time=t0)
+
+    def _train_cycle_modules(self):
+        """The reference loop (model.py:660-758) over the drop-in modules' autograd path (kept for cross-checks)."""
+        if self._world() > 1:
+            raise NotImplementedError("the module-path cycle loop is single-process; unset FPG_CYCLE_MODULES for the "
+                                      "data-parallel fused step")
         dev = self.device
         pre_buf, post_buf = [], []
         G_pp, G_pr = self.pre_to_post_generator, self.post_to_pre_generator

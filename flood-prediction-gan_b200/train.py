@@ -50,9 +50,14 @@ def main():
         size = (args.resize or 1024) // (2 if args.crop == 4 else 1)
         net.train_loader = SyntheticLoader(args.synthetic_steps, args.batch_size,
                                            model.TOPOGRAPHY_CHANNELS[net.topography], size, rank, world)
-    (net.train_cycle if net.model_is_cycle else net.train_paired)()
-    if world > 1:
-        dist.destroy_process_group()
+    if args.save_images_interval and rank == 0:
+        print("note: --save_images_interval is accepted for flag compatibility; plotting is outside this build")
+    try:
+        (net.train_cycle if net.model_is_cycle else net.train_paired)()
+    finally:
+        net.close()  # captured NCCL work must be released before the process group goes away
+        if world > 1:
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

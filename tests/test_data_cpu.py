@@ -167,6 +167,17 @@ def test_history_buffer_matches_reference():
     got, final = run(tr._buffer)
     assert got == gold["returned"] and final == gold["final_buffer"]
     assert any(r != i for i, r in enumerate(gold["returned"]))  # the replacement branch was exercised
+    # the fused cycle step keeps the pool on the device and takes only the DECISIONS on the host
+    # (fpgan.trainer._History -> {use_slot, store_slot} for fpg_history_exchange): replay them on a host pool
+    from fpgan.trainer import _History
+    random.seed(gold["py_seed"])
+    hist, pool, got = _History(), [None] * _History.SIZE, []
+    for i in range(gold["n"]):
+        use, store = hist.decide()
+        got.append(pool[use] if use >= 0 else i)
+        if store >= 0:
+            pool[store] = i
+    assert got == gold["returned"] and pool == gold["final_buffer"]
 
 
 def test_model_helpers_match_reference():

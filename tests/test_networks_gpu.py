@@ -251,6 +251,131 @@ def test_model_train_paired_api_and_checkpoint_roundtrip(tmp_path):
         assert torch.equal(v, m2.generator.state_dict()[k])
 
 
+def test_cyclegan_generator_forward_backward_matches_oracle():
+    """CycleGANGenerator (model_architectures.py:91-134) at the tensor level: output, parameter gradients and input
+    gradient of the drop-in module against the oracle's fp32 graph."""
+    from oracle import gan_oracle as O
+    from models import model_architectures as A
+    nets = O.init_model("cyclegan", "all", seed=47)
+    G = A.CycleGANGenerator(9)
+    G.load_state_dict(nets["pre_to_post_generator"])
+    G = G.cuda()
+    x, _ = O.synthetic_batch(0, 2, 9, 64)
+    wgt = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(1))
+    p = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in nets["pre_to_post_generator"].items()}
+    xr = x.clone().requires_grad_(True)
+    out_ref = O.cyclegan_generator_forward(p, xr)
+    names = list(p)
+    grads_ref = torch.autograd.grad((out_ref * wgt).sum(), [p[k] for k in names] + [xr])
+    xg = x.cuda().requires_grad_(True)
+    out = G(xg)
+    e_out = rel_rms(out, out_ref.detach())
+    assert e_out < OUT_TOL, e_out
+    (out * wgt.cuda()).sum().backward()
+    gp = dict(G.named_parameters())
+    worst = 0.0
+    for k, gref in zip(names, grads_ref[:-1]):
+        if k.endswith(".bias") and k != "model.26.bias":  # bias before an InstanceNorm: exactly zero gradient here
+            assert gp[k].grad.abs().max().item() == 0.0
+            continue
+        e = rel_rms(gp[k].grad, gref)
+        worst = max(worst, e)
+        assert e < GRAD_TOL, f"grad {k}: rel rms err {e}"
+    e_dx = rel_rms(xg.grad, grads_ref[-1])
+    assert e_dx < GRAD_TOL, e_dx
+    print(f"\n[parity] CycleGAN generator 64x64 B=2: output rel-rms err {e_out:.4f}, worst parameter-gradient "
+          f"rel-rms err {worst:.4f}, input-gradient err {e_dx:.4f}")
+
+
+def _cycle_pair(model, identity, seed=47):
+    from oracle import gan_oracle as O
+    from models import model_architectures as A
+    nets = O.init_model(model, "all", seed=seed)
+    gen = {"cyclegan": A.CycleGANGenerator, "attentiongan": A.AttentionGANGenerator}[model]
+    dis = {"cyclegan": A.CycleGANDiscriminator, "attentiongan": A.AttentionGANDiscriminator}[model]
+    mods = {}
+    for key, cls in (("pre_to_post_generator", gen), ("post_to_pre_generator", gen), ("pre_discriminator", dis),
+                     ("post_discriminator", dis)):
+        m = cls(9)
+        m.load_state_dict(nets[key])
+        mods[key] = m.cuda()
+    return O, nets, mods
+
+
+@pytest.mark.parametrize("model,identity", [("cyclegan", False), ("attentiongan", True)])
+def test_fused_cycle_step_matches_oracle_teacher_forced(model, identity):
+    """CycleTrainer (fused train_cycle, model.py:678-739) against the oracle's fp32 step, TEACHER-FORCED: before every
+    step the native trainer adopts the oracle's weights and Adam moments, so each step -- eager steps 0-1, the captured
+    step 2 and graph replays afterwards -- is an independent check of one full iteration: every loss within rtol 2e-2,
+    both synthetic images within OUT_TOL."""
+    from fpgan.trainer import CycleTrainer
+    O, nets, mods = _cycle_pair(model, identity)
+    otr = O.CycleTrainer(nets, model, add_identity_loss=identity, py_seed=3)
+    tr = CycleTrainer(mods["pre_to_post_generator"], mods["post_to_pre_generator"], mods["pre_discriminator"],
+                      mods["post_discriminator"], add_identity_loss=identity)
+
+    def adopt(fp, dicts, adam):
+        plist = [v for d in dicts for v in d.values() if v.is_floating_point() and v.dim() > 0]
+        assert len(plist) == len(fp.named)
+        for (name, p), src, m, v in zip(fp.named, plist, adam.m, adam.v):
+            off, k = fp.offsets[name]
+            assert p.shape == src.shape, name
+            fp.flat[off:off + k].copy_(src.reshape(-1))
+            fp.m[off:off + k].copy_(m.reshape(-1))
+            fp.v[off:off + k].copy_(v.reshape(-1))
+        fp.steps = adam.t
+
+    worst = 0.0
+    for step in range(5):
+        adopt(tr.gp, (otr.G_pp, otr.G_pr), otr.opt_g)
+        adopt(tr.dp, (otr.D_post, otr.D_pre), otr.opt_d)
+        for net in (tr.Gpp, tr.Gpr, tr.Dpost, tr.Dpre):
+            net.repack(force=True)
+        x, y = O.synthetic_batch(step, 1, 9, 64)
+        with torch.no_grad():
+            sp_ref = O.GENERATOR_FORWARD[model](otr.G_pp, x)
+            sr_ref = O.GENERATOR_FORWARD[model](otr.G_pr, torch.cat((y, x[:, 3:]), 1))
+        ref = otr.step(x, y)
+        sp, sr = tr.step(x.cuda(), y.cuda())
+        got = tr.losses()
+        e1, e2 = rel_rms(sp, sp_ref), rel_rms(sr, sr_ref)
+        print(f"\n[parity] {model} cycle step {step}: synthetic post/pre rel-rms err {e1:.4f}/{e2:.4f}; losses " +
+              ", ".join(f"{got[k]:.5f}/{ref[k]:.5f}" for k in tr.loss_keys))
+        assert e1 < OUT_TOL and e2 < OUT_TOL, (e1, e2)
+        for k in tr.loss_keys:
+            err = abs(got[k] - ref[k]) / (abs(ref[k]) + 1e-6)
+            worst = max(worst, err)
+            assert abs(got[k] - ref[k]) <= LOSS_RTOL * abs(ref[k]) + 1e-4, f"step {step} {k}: {got[k]} vs {ref[k]}"
+    assert tr._graphs, "the step was never captured"
+    print(f"[parity] {model} cycle: worst loss rel err over 5 teacher-forced steps {worst:.5f}")
+
+
+def test_history_exchange_kernel_follows_the_reference_buffer():
+    """fpg_history_exchange + _History == get_buffer_image (model.py:275-294) over 140 steps, past the fill phase"""
+    import random
+    from fpgan import ops
+    from fpgan.trainer import _History
+    from models import model as M
+    shape = (2, 4, 4, 16)
+    pool = torch.zeros((50,) + shape, dtype=torch.bfloat16, device="cuda")
+    ctrl = torch.zeros(2, dtype=torch.int32, device="cuda")
+    out = torch.empty(shape, dtype=torch.bfloat16, device="cuda")
+    random.seed(11)
+    hist, got = _History(), []
+    for i in range(140):
+        ctrl.copy_(torch.tensor(hist.decide(), dtype=torch.int32))
+        cur = torch.full(shape, float(i), dtype=torch.bfloat16, device="cuda")
+        ops.history_exchange(cur, pool, ctrl, out)
+        assert (out == out.flatten()[0]).all()
+        got.append(int(out.flatten()[0].item()))
+    random.seed(11)
+    buf, want = [], []
+    for i in range(140):
+        want.append(int(M.Model.get_buffer_image(None, torch.full((1,), float(i)), buf).item()))
+    assert got == want and [int(p.flatten()[0].item()) for p in pool] == [int(b.item()) for b in buf]
+    assert any(w != i for i, w in enumerate(want))
+
+
 @pytest.mark.parametrize("key,name", [("cyclegan_64", "CycleGAN"), ("attentiongan_64_identity", "AttentionGAN")])
 def test_train_cycle_matches_reference_golden(key, name):
     """Model.train_cycle (model.py:660-758) through the drop-in modules: initial weights identical to the reference,
