@@ -759,6 +759,7 @@ struct ReduceArgs {
   int32_t x_ca, x_atoms, x_groups, x_taps_mode, x_ntaps;
   int32_t y_ca, y_atoms, y_groups, y_taps_mode, y_ntaps;
   int32_t splits, x_is_dy, y_shifts, y_sets, taps_total, pair, last_splits;
+  int32_t parts;  // threads that share one output float4, each summing every parts-th split (power of two <= 16)
   int64_t stride_k, stride_c;
   int32_t k_valid, c_valid;
   int16_t x_tap_rs[FPG_MAX_TAPS];
@@ -767,16 +768,30 @@ struct ReduceArgs {
 
 // One thread per 4 consecutive workspace floats (same item, row, tap; 4 consecutive channels of the Y operand): sums the
 // split partials with 16-byte loads in a fixed order and scatters into the parameter-layout gradient.
+// Small gradients (a few thousand float4 against ~148 splits: PatchGAN model.0, the 1x1 / 7x7 heads, the stem) used to
+// run a handful of CTAs with ~148 dependent-latency loop trips each (38-42 us for 64 KB of output): `parts` threads now
+// share an output, each summing every parts-th split, combined in shared memory in a fixed order.
+template <bool MULTI>  // MULTI: a.parts > 1 (the single-part instantiation keeps the plain loop of the large layers)
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, const ReduceArgs a) {
+  __shared__ float4 part_sum[MULTI ? 256 : 1];
+  const int parts = MULTI ? a.parts : 1;
   const int M = a.x_atoms * a.x_ca, N = a.y_atoms * a.y_ca;
   const int NT = a.y_shifts * a.y_sets * N;
   const int NX = a.x_taps_mode ? a.x_groups : a.x_groups * a.x_ntaps;
   const int NY = a.pair ? (a.y_ntaps + 1) / 2
                         : (a.y_taps_mode ? (a.y_groups + a.y_sets - 1) / a.y_sets : a.y_groups * a.y_ntaps);
   const int per_split4 = NX * NY * M * (NT >> 2);  // float4 per split (a few million at most)
-  const int idx4 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx4 >= per_split4) return;
+  const int outs = blockDim.x / parts;              // outputs per block
+  const int part = MULTI ? threadIdx.x / outs : 0;
+  const int idx4 = blockIdx.x * outs + (MULTI ? threadIdx.x % outs : threadIdx.x);
+  bool live = idx4 < per_split4;
+  if (!MULTI && !live) return;
+  if (!live) {
+    part_sum[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    return;
+  }
   // accumulator-native workspace order of an item: [row block of RB rows][16-column chunk][4][RB][4] floats
   const int item4 = M * (NT >> 2);
   const int item = idx4 / item4;
@@ -812,21 +827,38 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, const 
       ych = ((yi % a.y_groups) * a.y_atoms + atom) * a.y_ca + within;
     }
   }
-  if (xtap >= a.x_ntaps || ytap >= a.y_ntaps) return;  // dummy atoms of a ragged last group
-  const int tap = a.x_tap_rs[xtap] + a.y_tap_rs[ytap] + shift;
-  if (tap < 0 || tap >= a.taps_total) return;
+  int tap = -1;
   const int x_valid = a.x_is_dy ? a.k_valid : a.c_valid, y_valid = a.x_is_dy ? a.c_valid : a.k_valid;
-  if (xch >= x_valid || ych >= y_valid) return;
+  if (xtap < a.x_ntaps && ytap < a.y_ntaps) {  // (else: dummy atoms of a ragged last group)
+    tap = a.x_tap_rs[xtap] + a.y_tap_rs[ytap] + shift;
+    if (tap >= a.taps_total || xch >= x_valid || ych >= y_valid) tap = -1;
+  }
+  live = tap >= 0;
+  if (!MULTI && !live) return;
   const float4* p = reinterpret_cast<const float4*>(ws) + idx4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const int splits = (a.pair && (a.y_ntaps & 1) && yi == NY - 1) ? a.last_splits : a.splits;
+  if (live) {
 #pragma unroll 8
-  for (int s = 0; s < splits; ++s) {  // loads batched by the unroll, summation order fixed
-    const float4 v = __ldcg(p + static_cast<int64_t>(s) * per_split4);
-    acc.x += v.x;
-    acc.y += v.y;
-    acc.z += v.z;
-    acc.w += v.w;
+    for (int s = part; s < splits; s += parts) {  // loads batched by the unroll, summation order fixed
+      const float4 v = __ldcg(p + static_cast<int64_t>(s) * per_split4);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+  }
+  if (MULTI) {
+    part_sum[threadIdx.x] = acc;
+    __syncthreads();
+    if (part != 0 || !live) return;
+    for (int q = 1; q < parts; ++q) {
+      const float4 v = part_sum[q * outs + threadIdx.x];
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
   }
   const int64_t x_stride = a.x_is_dy ? a.stride_k : a.stride_c, y_stride = a.x_is_dy ? a.stride_c : a.stride_k;
   float* out = dw + xch * x_stride + ych * y_stride + tap;
@@ -893,36 +925,47 @@ pack_batched_kernel(const fpg_pack_job* __restrict__ jobs, const int32_t* __rest
 }
 
 // stats[(i*c + ch)*2] = {mean, rstd} of image i from the epilogue partials [i][rows][c][2] (fixed summation order).
-// block = 64 channels x 16 row groups (a launch has only n * c / 64 blocks: short per-thread row loops matter)
-constexpr int kFinalizeParts = 16;
-__global__ void __launch_bounds__(64 * kFinalizeParts)
+// The kernel is latency bound (1 MB per image): block = 32 channels (16 lanes x 2 channels per 16-byte load) x 64 row
+// parts, so that the <= 512 rows of an image are 8 independent loads per thread and a launch has n * c / 32 blocks
+// (it was 64 channels x 16 parts: 8.3-9 us per launch, 30 launches per step).
+constexpr int kFinalizeParts = 64;
+constexpr int kFinalizeLanes = 16;
+__global__ void __launch_bounds__(kFinalizeLanes * kFinalizeParts)
 stats_finalize_kernel(const float* __restrict__ partial, int rows, int c, float inv_count, float eps, int sums_only,
                       float* __restrict__ stats) {
   const int i = blockIdx.x;
-  const int ch = blockIdx.y * 64 + (threadIdx.x & 63), part = threadIdx.x >> 6;
-  __shared__ float2 red[kFinalizeParts][64];
-  float a = 0.f, b = 0.f;
+  const int lane = threadIdx.x % kFinalizeLanes, part = threadIdx.x / kFinalizeLanes;
+  const int ch = blockIdx.y * (2 * kFinalizeLanes) + 2 * lane;  // c is a multiple of 16: ch and ch + 1 are both valid
+  __shared__ float4 red[kFinalizeParts][kFinalizeLanes];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // {sum, sumsq} of ch, {sum, sumsq} of ch + 1
   if (ch < c) {
-    const float2* p = reinterpret_cast<const float2*>(partial) + static_cast<int64_t>(i) * rows * c + ch;
+    const float4* p = reinterpret_cast<const float4*>(partial + (static_cast<int64_t>(i) * rows * c + ch) * 2);
+    const int64_t row4 = c / 2;  // float4 per partial row
 #pragma unroll 8
     for (int r = part; r < rows; r += kFinalizeParts) {
-      const float2 v = __ldcg(p + static_cast<int64_t>(r) * c);
-      a += v.x;
-      b += v.y;
+      const float4 v = __ldcg(p + static_cast<int64_t>(r) * row4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
   }
-  red[part][threadIdx.x & 63] = make_float2(a, b);
+  red[part][lane] = acc;
   __syncthreads();
   if (part == 0 && ch < c) {
     for (int q = 1; q < kFinalizeParts; ++q) {
-      a += red[q][threadIdx.x].x;
-      b += red[q][threadIdx.x].y;
+      const float4 v = red[q][lane];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    const float mean = a * inv_count;
-    const float var = fmaxf(b * inv_count - mean * mean, 0.f);
-    stats[(static_cast<int64_t>(i) * c + ch) * 2] = mean;
-    // sums_only: the two plane means themselves (InstanceNorm backward: mean g', mean g' * zhat)
-    stats[(static_cast<int64_t>(i) * c + ch) * 2 + 1] = sums_only ? b * inv_count : rsqrtf(var + eps);
+    const float s[2] = {acc.x, acc.z}, ss[2] = {acc.y, acc.w};
+    float4 out;
+    float* o = reinterpret_cast<float*>(&out);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float mean = s[k] * inv_count;
+      const float var = fmaxf(ss[k] * inv_count - mean * mean, 0.f);
+      o[2 * k] = mean;
+      // sums_only: the two plane means themselves (InstanceNorm backward: mean g', mean g' * zhat)
+      o[2 * k + 1] = sums_only ? ss[k] * inv_count : rsqrtf(var + eps);
+    }
+    *reinterpret_cast<float4*>(stats + (static_cast<int64_t>(i) * c + ch) * 2) = out;
   }
 }
 
@@ -1125,7 +1168,10 @@ static int reduce_stat_rows(const float* stat_partial, int32_t rows_per_img, int
     spare += static_cast<int64_t>(n) * out_rows * c * 2;
     rows = out_rows;
   }
-  stats_finalize_kernel<<<dim3(n, (c + 63) / 64), 64 * kFinalizeParts, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (c % 2 != 0 || (reinterpret_cast<uintptr_t>(cur) & 15) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0)
+    return fail(FPG_EINVAL, "statistics finalize: channels must be even and the buffers 16-byte aligned");
+  stats_finalize_kernel<<<dim3(n, (c + 2 * kFinalizeLanes - 1) / (2 * kFinalizeLanes)),
+                          kFinalizeLanes * kFinalizeParts, 0, static_cast<cudaStream_t>(stream)>>>(
       cur, rows, c, inv_count, eps, sums_only, out);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -1192,8 +1238,15 @@ int fpg_conv2d_wgrad(const fpg_act* x, const fpg_act* dy, const fpg_conv_geom* g
   }
   const int64_t per_split4 = wgrad_ws_floats(&d) / d.splits / 4;
   const int threads = 256;
-  const int64_t blocks = (per_split4 + threads - 1) / threads;
-  wgrad_reduce_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(ws, dw, a);
+  // fewer outputs than ~2 CTAs per SM: share every output among `parts` threads (see the kernel)
+  int parts = 1;
+  while (parts < 16 && parts * 2 <= d.splits && (per_split4 * parts + threads - 1) / threads < 2 * sms) parts *= 2;
+  a.parts = parts;
+  const int64_t blocks = (per_split4 * parts + threads - 1) / threads;
+  if (parts > 1)
+    wgrad_reduce_kernel<true><<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(ws, dw, a);
+  else
+    wgrad_reduce_kernel<false><<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(ws, dw, a);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -11,6 +11,12 @@
 namespace fpg {
 
 constexpr int kThreads = 192;
+// fprop-type kernels: 8 epilogue warps, two per TMEM lane quarter (a warp may only read lanes 32 * (warp % 4) ...), each
+// taking half of the tile's 16-column chunks. With 4 warps every SM scheduler held ONE epilogue warp, so the latencies of
+// tcgen05.ld, the statistics shuffles and the stores were all exposed (~1.2 k clk per chunk): layers with a short K loop
+// (transposed convs, PatchGAN, parity classes of the stride-2 data gradients) ran at the speed of their epilogue.
+constexpr int kEpiWarps = 8;
+constexpr int kFpropThreads = 64 + 32 * kEpiWarps;
 constexpr int kTmemCols = 512;
 
 // Phase stamps of the wgrad kernels (diagnostic build: make EXTRA=-DFPG_WGRAD_TRACE): cycles from kernel entry to the
@@ -191,7 +197,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 template <int CBLK>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFpropThreads, 1)
 igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
                    const __grid_constant__ CUtensorMap amap1, const __grid_constant__ FpropArgs args) {
   constexpr int SUB = 64 / CBLK;                   // TMA sub-loads per 64-wide K stage
@@ -230,7 +236,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 32 * kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -332,8 +338,12 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // column chunks [c_begin, c_end) of this warp: first or second half of the tile's 16-column chunks
+    const int n_chunks16 = BN / 16, chunk_split = (n_chunks16 + 1) / 2;
+    const int c_begin = (warp - 2) < 4 ? 0 : chunk_split * 16;
+    const int c_end = (warp - 2) < 4 ? chunk_split * 16 : BN;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const uint32_t as = it % ACC_STAGES, aph = (it / ACC_STAGES) & 1;
@@ -433,7 +443,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
         const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
         if (st_img == nullptr) {
           const uint4 none[2] = {zero4, zero4};
-          for (int c = 0; c < BN; c += 16) chunk(c, none, none);
+          for (int c = c_begin; c < c_end; c += 16) chunk(c, none, none);
         } else {
           // the y (and skip-gradient) reads are global loads with ~1 us latency: two register buffers, each reloaded
           // for the chunk after next as soon as it has been consumed
@@ -448,14 +458,14 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
               areg[1] = __ldg(reinterpret_cast<const uint4*>(add_px + c) + 1);
             }
           };
-          fetch(0, y0, a0);
-          if (BN > 16) fetch(16, y1, a1);
-          for (int c = 0; c < BN; c += 32) {
+          if (c_begin < c_end) fetch(c_begin, y0, a0);
+          if (c_begin + 16 < c_end) fetch(c_begin + 16, y1, a1);
+          for (int c = c_begin; c < c_end; c += 32) {
             chunk(c, y0, a0);
-            if (c + 32 < BN) fetch(c + 32, y0, a0);
-            if (c + 16 < BN) {
+            if (c + 32 < c_end) fetch(c + 32, y0, a0);
+            if (c + 16 < c_end) {
               chunk(c + 16, y1, a1);
-              if (c + 48 < BN) fetch(c + 48, y1, a1);
+              if (c + 48 < c_end) fetch(c + 48, y1, a1);
             }
           }
         }
@@ -479,7 +489,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
 // issues the MMAs and multicasts the commit to both CTAs' empty / tmem-full barriers; both epilogues drain their own
 // TMEM lanes and arrive on the leader's tmem-empty barrier.
 template <int CBLK>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
 igemm_fprop2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
                     const __grid_constant__ FpropArgs args) {
   constexpr int SUB = 64 / CBLK;
@@ -517,7 +527,7 @@ igemm_fprop2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 256);  // leader's copy is used: 128 epilogue threads of each CTA
+      mbar_init(&tempty[i], 2 * 32 * kEpiWarps);  // leader's copy is used: the epilogue threads of both CTAs
     }
     fence_barrier_init();
   }
@@ -615,6 +625,9 @@ igemm_fprop2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
     }
   } else {
     const int q = warp & 3;
+    const int n_chunks16 = BN / 16, chunk_split = (n_chunks16 + 1) / 2;  // two warps per lane quarter, see kEpiWarps
+    const int c_begin = (warp - 2) < 4 ? 0 : chunk_split * 16;
+    const int c_end = (warp - 2) < 4 ? chunk_split * 16 : BN;
     const int row = q * 32 + lane;
     const int ry = row >> args.tile_w_log2;
     const int rx = row & (args.tile_w - 1);
@@ -638,7 +651,7 @@ igemm_fprop2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256;
       const int64_t prow = static_cast<int64_t>(n) * args.stat.rows_per_img + args.stat.row0 +
                            ((ty * 2 + static_cast<int>(rank)) * args.tiles_x + tx) * 4 + q;
-      for (int c = 0; c < BN; c += 16) {
+      for (int c = c_begin; c < c_end; c += 16) {
         uint32_t v[16];
         tmem_ld16(t_addr + c, v);
         tmem_ld_wait();
@@ -1242,11 +1255,11 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
     if (d->cblk == 64) {
       FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_fprop2_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(smem2)));
-      igemm_fprop2_kernel<64><<<2 * clusters, kThreads, smem2, st>>>(amap, bmap, args);
+      igemm_fprop2_kernel<64><<<2 * clusters, kFpropThreads, smem2, st>>>(amap, bmap, args);
     } else {
       FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_fprop2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           static_cast<int>(smem2)));
-      igemm_fprop2_kernel<32><<<2 * clusters, kThreads, smem2, st>>>(amap, bmap, args);
+      igemm_fprop2_kernel<32><<<2 * clusters, kFpropThreads, smem2, st>>>(amap, bmap, args);
     }
     FPG_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -1259,7 +1272,7 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
   do {                                                                                                           \
     FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_fprop_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                         static_cast<int>(smem)));                                                \
-    FPG_CUDA_CHECK(launch_persistent(igemm_fprop_kernel<CB>, dim3(grid), dim3(kThreads), smem, st, amap, bmap, amap1, \
+    FPG_CUDA_CHECK(launch_persistent(igemm_fprop_kernel<CB>, dim3(grid), dim3(kFpropThreads), smem, st, amap, bmap, amap1, \
                                      args));                                                                     \
   } while (0)
   if (d->cblk == 64) {

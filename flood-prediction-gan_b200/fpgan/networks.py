@@ -598,7 +598,8 @@ class Pix2PixGeneratorNet(_NetBase, _BatchNormMixin):
             if "sub" in idx:
                 prefix += str(idx["sub"]) + ".model."
                 blk = seq[idx["sub"]]
-        self.dropout_seed = 0
+        import torch.distributed as dist
+        self.dropout_rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         self.dropout_masks = None  # test hook: list of three uint8 masks [pixels][c] in execution order
 
     def forward(self, x):
@@ -643,8 +644,12 @@ class Pix2PixGeneratorNet(_NetBase, _BatchNormMixin):
                     mask = self.dropout_masks[len(masks)]
                 else:
                     mask = torch.empty(u.n * u.h * u.w * u.c, dtype=torch.uint8, device=x.device)
-                    self.dropout_seed += 1
-                    ops.dropout_mask(mask, torch.initial_seed() * 1000003 + self.dropout_seed)
+                    # one draw from torch's global generator per mask: torch.manual_seed(47) before a forward (what the
+                    # reference does before every evaluation-time generator call, model.py:393,497,579) reproduces the
+                    # masks whatever ran before; under data parallelism every rank is seeded alike, so the rank is
+                    # mixed in to give each shard its own masks
+                    seed = int(torch.empty((), dtype=torch.int64).random_().item())
+                    ops.dropout_mask(mask, seed * 1000003 + self.dropout_rank)
                 masks.append(mask)
             c = lv["outer"]
             t[f"us{k}"] = self._bn_forward(u, lv["upnorm_m"], ACT_RELU, cats[k - 1].channels(c, c), mask=mask)

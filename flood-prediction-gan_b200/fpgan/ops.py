@@ -302,7 +302,7 @@ def _counters(device):
     """zero-initialised int32 ticket counters (kernels leave them zero)"""
     key = str(device)
     if key not in _counter_cache:
-        _counter_cache[key] = torch.zeros(4096, dtype=torch.int32, device=device)
+        _counter_cache[key] = torch.zeros(4096 + 64, dtype=torch.int32, device=device)
     return _counter_cache[key]
 
 
@@ -421,8 +421,10 @@ def blend_bwd(content, logits, inp, dcontent, dlogits, dout_nchw=None, dout_nhwc
 
 
 def mse_const_loss(logits, target, weight, grad_scale, loss, dlogits=None):
+    ws = workspace(4096 * 4, logits.t.device)
+    # int32 #4096 of the shared counter block is this kernel's ticket (the InstanceNorm kernels use the first 4096)
     _run("mse_const_loss", 1, "fpg_mse_const_loss", logits.ref(), float(target), float(weight), float(grad_scale), _ptr(loss),
-           dlogits.ref() if dlogits is not None else None, _stream())
+           dlogits.ref() if dlogits is not None else None, _ptr(ws), _ptr(_counters(logits.t.device)[4096:]), _stream())
 
 
 def l1_loss(pred, target, weight, grad_scale, loss, dpred=None, accumulate=False):

@@ -443,9 +443,11 @@ int fpg_blend_bwd(const float* dout_nchw, const fpg_act* dout_nhwc, int32_t dout
  * Losses -- nn.MSELoss against torch.full(target) (model.py:626-631,641-642) and nn.L1Loss * weight (model.py:643).
  * Each writes the scalar loss (mean reduction, times `weight`) to *loss and the gradient of (grad_scale * loss).
  * ---------------------------------------------------------------------------------------------------------- */
-/* logits: fp32 NHWC buffer with 1 valid channel (PatchGAN output). dlogits: bf16, same geometry (other channels 0) */
+/* logits: fp32 NHWC buffer with 1 valid channel (PatchGAN output). dlogits: bf16, same geometry (other channels 0).
+ * scratch: >= logits->n floats; counter: one int32 that is zero on entry and left zero (ticket of the per-image CTAs:
+ * the last one sums the per-image partials in image order). */
 int fpg_mse_const_loss(const fpg_act* logits, float target, float weight, float grad_scale, float* loss,
-                       const fpg_act* dlogits, void* stream);
+                       const fpg_act* dlogits, float* scratch, int32_t* counter, void* stream);
 /* pred/target: fp32 NCHW [count]; dpred (fp32, may be NULL) = grad_scale * weight * sign(pred-target) / count,
  * accumulated (+=) if accumulate != 0. per_image > 0: the target is the leading per_image elements of every
  * target_image_stride elements (real_image[:, :3] of a wider NCHW tensor: the cycle / identity losses,

