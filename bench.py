@@ -271,8 +271,22 @@ def run_native(args):
     e1.record()
     barrier()
     wall_ms = 1000 * (time.perf_counter() - t0)
-    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), wall_ms))
+    e2e_event_ms = e0.elapsed_time(e1)
+    e2e_ms = max_over_ranks(max(e2e_event_ms, wall_ms))
     e2e = B * world * steps / (e2e_ms / 1000.0)
+    # diagnostic: pinned host->device bandwidth of this box for one batch (the e2e path hides the copy of batch i+1
+    # behind step i; that only works while a batch copies faster than a step runs)
+    hx, hy = host[0][0], host[0][1]
+    torch.cuda.synchronize()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for _ in range(3):
+        hx.to(dev, non_blocking=True)
+        hy.to(dev, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_ms_per_batch = c0.elapsed_time(c1) / 3
+    h2d_gbs = (hx.numel() + hy.numel()) * 4 / (h2d_ms_per_batch * 1e6)
 
     # ---- (3) roofline of the dominant kernel: igemm_fprop_kernel<64> on the residual 3x3 conv (18 launches per
     # generator forward, 75% of the generator FLOPs), timed with CUDA events around each launch of extra steps
@@ -317,6 +331,9 @@ def run_native(args):
                 "clocks": clocks.summary(),
                 "e2e": {"value": e2e, "unit": "tiles/s", "h2d_bytes_per_step": B * (CHANNELS + 3) * TILE * TILE * 4,
                         "d2h_bytes_per_step": 4 * len(last_losses), "ms_per_step": e2e_ms / steps,
+                        "ms_per_step_device_events": e2e_event_ms / steps, "ms_per_step_host_wall": wall_ms / steps,
+                        "h2d_pinned_ms_per_batch": h2d_ms_per_batch, "h2d_pinned_GBps": h2d_gbs,
+                        "host_batches_pinned": bool(hx.is_pinned()),
                         "api": f"models.model.Model.{'train_cycle' if cycle else 'train_paired'}() with pinned host "
                                "batches, log_interval=1"},
                 "gpu_launches": launches,

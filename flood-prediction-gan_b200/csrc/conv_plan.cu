@@ -1117,15 +1117,17 @@ int fpg_conv2d_dgrad_stats(const fpg_act* dy, const void* w_packed_t, const floa
 }
 
 int fpg_conv2d_dgrad_inbwd(const fpg_act* dy, const void* w_packed_t, const fpg_conv_geom* g, const fpg_act* dx,
-                           const fpg_act* y, const float* stats, int act, const fpg_act* add, float* stat_partial,
+                           const fpg_act* z, const fpg_act* zprev, const fpg_act* add, float* stat_partial,
                            int32_t* rows_per_img, void* stream) {
-  FPG_REQUIRE(dy && w_packed_t && g && dx && y && stats && stat_partial && rows_per_img, "null argument");
-  FPG_REQUIRE(y->fp32 != FPG_DT_FP32 && y->halo == 0 && y->c == y->c_stride && y->h == dx->h && y->w == dx->w && y->c == dx->c &&
-                  y->n == dx->n && y->c % 16 == 0,
-              "y must be the halo-free bf16 pre-norm tensor of the activation whose gradient is produced");
+  FPG_REQUIRE(dy && w_packed_t && g && dx && z && stat_partial && rows_per_img, "null argument");
+  const fpg_act* same[2] = {z, zprev};
+  for (const fpg_act* t : same)
+    if (t != nullptr)
+      FPG_REQUIRE(t->fp32 == FPG_DT_BF16 && t->halo == dx->halo && t->h == dx->h && t->w == dx->w && t->c == dx->c &&
+                      t->n == dx->n && t->c % 64 == 0,
+                  "z / zprev must be bf16 tensors of dx's geometry (the convolution's saved input and the block input)");
   if (add != nullptr)
-    FPG_REQUIRE(!add->fp32 && add->c == add->c_stride && add->h == dx->h && add->w == dx->w && add->c == dx->c &&
-                    add->n == dx->n,
+    FPG_REQUIRE(add->fp32 == FPG_DT_BF16 && add->h == dx->h && add->w == dx->w && add->c == dx->c && add->n == dx->n,
                 "add must match the interior of dx");
   const int sms = sm_count_cached();
   if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
@@ -1136,20 +1138,33 @@ int fpg_conv2d_dgrad_inbwd(const fpg_act* dy, const void* w_packed_t, const fpg_
   int n = 0;
   int rc = plan_dgrad(dy, w_packed_t, nullptr, FPG_ACT_NONE, g, dx, sms, d, &n);
   if (rc) return rc;
-  if (n != 1 || d[0].cta_pair || d[0].block_n * d[0].n_blocks != y->c) return 1;
+  if (n != 1 || d[0].cta_pair || d[0].cblk != 64 || d[0].block_n % 64 != 0) return 1;
+  // the operand ring needs 3 stages x 8 KB per staged tensor of shared memory: fewer stages for the main loop when
+  // it does not fit beside them
+  const int n_tensors = 1 + (zprev ? 1 : 0) + (add ? 1 : 0);
+  while (d[0].stages > 2 && static_cast<size_t>(d[0].stages) * (16384 + d[0].block_n * 128) +
+                                    3 * n_tensors * 8192 + 2048 > 227 * 1024)
+    --d[0].stages;
   d[0].stat_partial = stat_partial;
   d[0].stat_rows_per_img = stats_rows_of(&d[0]);
   d[0].stat_row0 = 0;
-  d[0].inbwd_y = y->data;
-  d[0].inbwd_stats = stats;
-  d[0].inbwd_add = add ? add->data : nullptr;
-  d[0].inbwd_h = y->h;
-  d[0].inbwd_w = y->w;
-  d[0].inbwd_c = y->c;
+  d[0].inbwd_mode = zprev ? 2 : 1;
+  d[0].inbwd_has_add = add ? 1 : 0;
+  d[0].inbwd_h = dx->h;
+  d[0].inbwd_w = dx->w;
   d[0].inbwd_halo = dx->halo;
   d[0].inbwd_add_halo = add ? add->halo : 0;
-  d[0].inbwd_act = act;
-  d[0].inbwd_y_dt = y->fp32;
+  const bool two = d[0].tiles_x1 > 0 && d[0].tiles_y1 > 0;
+  make_act_view(z, 1, 32, d[0].tile_w, d[0].tile_h, &d[0].inbwd_z);
+  if (two) make_act_view(z, 1, 32, d[0].tile_w1, d[0].tile_h1, &d[0].inbwd_z1);
+  if (zprev) {
+    make_act_view(zprev, 1, 32, d[0].tile_w, d[0].tile_h, &d[0].inbwd_prev);
+    if (two) make_act_view(zprev, 1, 32, d[0].tile_w1, d[0].tile_h1, &d[0].inbwd_prev1);
+  }
+  if (add) {
+    make_act_view(add, 1, 32, d[0].tile_w, d[0].tile_h, &d[0].inbwd_add);
+    if (two) make_act_view(add, 1, 32, d[0].tile_w1, d[0].tile_h1, &d[0].inbwd_add1);
+  }
   *rows_per_img = d[0].stat_rows_per_img;
   return fpg_igemm_fprop_launch(&d[0], stream);
 }

@@ -17,6 +17,7 @@ constexpr int kThreads = 192;
 // (transposed convs, PatchGAN, parity classes of the stride-2 data gradients) ran at the speed of their epilogue.
 constexpr int kEpiWarps = 8;
 constexpr int kFpropThreads = 64 + 32 * kEpiWarps;
+constexpr int kFpropThreadsInBwd = kFpropThreads + 32;  // + the producer warp of the epilogue-operand ring
 constexpr int kTmemCols = 512;
 
 // Phase stamps of the wgrad kernels (diagnostic build: make EXTRA=-DFPG_WGRAD_TRACE): cycles from kernel entry to the
@@ -52,14 +53,24 @@ struct StatOut {
   int32_t c_total;
 };
 
-// InstanceNorm-backward statistics from a dgrad epilogue (fpg_igemm_fprop_desc.inbwd_*): y == nullptr = off
+// InstanceNorm-backward reductions from a dgrad epilogue (fpg_igemm_fprop_desc.inbwd_*). The launch produces dz, the
+// gradient w.r.t. the (reflect-haloed) input z of the forward convolution; z itself -- saved for the weight gradient,
+// same geometry as dz -- supplies everything the reductions need, without the pre-norm tensor or its statistics:
+//   mode 1, z = relu(zhat):            {sum f [z > 0], sum f z}        = {sum g', sum g' zhat}
+//   mode 2, z = zprev + zhat (block):  {sum f, sum f (z - zprev)}      = {sum g,  sum g zhat}
+// (f = the stored value; both sums are linear in dz and z's halo mirrors its interior, so the halo needs no fold
+// first). The operand tiles are staged by a dedicated producer warp (TMA, 32-channel slices) in a shared-memory ring.
 struct InBwdStat {
-  const __nv_bfloat16* y;    // [n][h][w][c] forward pre-norm output
-  const float* stats;        // [n][c][2] mean, rstd
-  const __nv_bfloat16* add;  // optional [n][h + 2 add_halo][w + 2 add_halo][c]: added to the interior outputs
-  int32_t h, w, c, halo, add_halo, act;
-  int32_t y_dt;              // element type of y: FPG_DT_BF16 or FPG_DT_FP16
+  int32_t mode;       // 0 = off
+  int32_t has_add;    // add the skip-connection gradient to the INTERIOR outputs before they are stored / reduced
+  int32_t halo;       // halo of the output tensor (tile coordinates are padded coordinates)
+  int32_t h, w;       // interior extent
+  int32_t add_shift;  // (halo of the skip-gradient buffer) - halo: coordinate shift of its view
+  int32_t debug;      // timing experiments (FPG_INBWD_DEBUG): bit 0 = no reductions, bit 1 = no operand loads
+  int32_t n_tensors;  // staged tensors per slice: z [, zprev] [, add] in this order
 };
+constexpr int kEStages = 3;                 // ring stages; a stage holds one 32-channel slice of each staged tensor
+constexpr int kESliceBytes = 128 * 32 * 2;  // 128 pixel rows x 32 channels bf16, 64-byte swizzle
 
 struct FpropArgs {
   int32_t chunks_per_tap;
@@ -154,29 +165,22 @@ __device__ __forceinline__ void store_16x16(void* dst_, const float (&f)[16], in
   }
 }
 
-// InstanceNorm-backward variant of stat_accumulate: f = the 16 values about to be stored for this thread's pixel,
-// yreg = the forward pre-norm output (16 bf16) at the interior pixel it mirrors, st = {mean, rstd} of the channels.
-// Column sums over the warp's 32 rows of g' = round_bf16(f) * act'(zhat) and g' * zhat.
-__device__ __forceinline__ void inbwd_accumulate(const StatOut& so, const float (&f)[16], const uint4 (&yreg)[2],
-                                                 const float* st, int act, bool valid, int lane, int64_t prow,
-                                                 int col0, int y_dt) {
+// InstanceNorm-backward variant of stat_accumulate (see InBwdStat): fr = the 16 values as stored (bf16-rounded, 0 for
+// masked rows), z / zp = the forward input and, mode 2, the previous block's input at the same pixel and channels.
+__device__ __forceinline__ void inbwd_accumulate(const StatOut& so, const float (&fr)[16], const float (&z)[16],
+                                                 const float (&zp)[16], int mode, int lane, int64_t prow, int col0) {
   float a[16], b[16];
-  float yv[16];
-  unpack_16x8(yreg[0], yv, y_dt);
-  unpack_16x8(yreg[1], yv + 8, y_dt);
+  if (mode == 1) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 ms = __ldg(reinterpret_cast<const float4*>(st) + i);  // {mean, rstd} of channels 2i, 2i + 1
+    for (int k = 0; k < 16; ++k) {
+      a[k] = z[k] > 0.f ? fr[k] : 0.f;
+      b[k] = fr[k] * z[k];
+    }
+  } else {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int k = 2 * i + h;
-      const float mean = h ? ms.z : ms.x, rstd = h ? ms.w : ms.y;
-      const float zh = valid ? (yv[k] - mean) * rstd : 0.f;
-      const float r = valid ? __bfloat162float(__float2bfloat16(f[k])) : 0.f;
-      const float slope = act == FPG_ACT_RELU ? (zh > 0.f ? 1.f : 0.f)
-                                              : (act == FPG_ACT_LEAKY ? (zh > 0.f ? 1.f : 0.2f) : 1.f);
-      a[k] = r * slope;
-      b[k] = a[k] * zh;
+    for (int k = 0; k < 16; ++k) {
+      a[k] = fr[k];
+      b[k] = fr[k] * (z[k] - zp[k]);
     }
   }
   const float sa = warp_colsum16(a, lane);
@@ -196,10 +200,15 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-template <int CBLK>
-__global__ void __launch_bounds__(kFpropThreads, 1)
+// INBWD: the InstanceNorm-backward reductions of InBwdStat run in the epilogue; zmap / pmap / gmap (+ the region-1
+// variants) are the views of z, zprev and the skip gradient with 32-channel boxes of the tile shapes.
+template <int CBLK, bool INBWD>
+__global__ void __launch_bounds__(INBWD ? kFpropThreadsInBwd : kFpropThreads, 1)
 igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
-                   const __grid_constant__ CUtensorMap amap1, const __grid_constant__ FpropArgs args) {
+                   const __grid_constant__ CUtensorMap amap1, const __grid_constant__ CUtensorMap zmap,
+                   const __grid_constant__ CUtensorMap zmap1, const __grid_constant__ CUtensorMap pmap,
+                   const __grid_constant__ CUtensorMap pmap1, const __grid_constant__ CUtensorMap gmap,
+                   const __grid_constant__ CUtensorMap gmap1, const __grid_constant__ FpropArgs args) {
   constexpr int SUB = 64 / CBLK;                   // TMA sub-loads per 64-wide K stage
   constexpr uint32_t LAYOUT = swizzle_layout_type(CBLK * 2);
   constexpr uint32_t SBO = 8u * CBLK * 2u;  // 8 rows of one swizzle atom
@@ -220,11 +229,16 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
 
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_STAGE_BYTES);
+  uint8_t* ering = smem_b + STAGES * B_STAGE_BYTES;  // INBWD: kEStages x estage_bytes (1 KB aligned: stage sizes are)
+  const int estage_bytes = INBWD ? args.inbwd.n_tensors * kESliceBytes : 0;
+  const int add_slot = (args.inbwd.mode == 2 ? 2 : 1) * kESliceBytes;  // byte offset of the skip gradient in a stage
+  uint64_t* full = reinterpret_cast<uint64_t*>(ering + kEStages * estage_bytes);
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* efull = tempty + 2;
+  uint64_t* eempty = efull + kEStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(eempty + kEStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -237,6 +251,10 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 32 * kEpiWarps);
+    }
+    for (int i = 0; i < kEStages; ++i) {
+      mbar_init(&efull[i], 1);
+      mbar_init(&eempty[i], kEpiWarps / 2);  // a slice is consumed by the four warps of one column half
     }
     fence_barrier_init();
   }
@@ -337,6 +355,44 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
         umma_commit(&tfull[as]);  // accumulator complete
       }
     }
+  } else if (INBWD && warp == 2 + kEpiWarps) {
+    // ------------------------------------------------------------ producer of the epilogue-operand ring (INBWD)
+    if (elect_one()) {
+      if (args.inbwd.debug & 2) return;
+      const uint32_t bytes = static_cast<uint32_t>(estage_bytes);
+      const int slices = BN >> 6;  // 32-channel slices per column half
+      const int shift = args.inbwd.add_shift;
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const bool r1 = tile >= args.r0_tiles;
+        const int t = r1 ? tile - args.r0_tiles : tile;
+        const int ntx = r1 ? args.tiles_x1 : args.tiles_x, nty = r1 ? args.tiles_y1 : args.tiles_y;
+        int nb = t % args.n_blocks;
+        int r = t / args.n_blocks;
+        int tx = r % ntx;
+        r /= ntx;
+        int ty = r % nty;
+        int n = r / nty;
+        const int x0 = r1 ? args.x_org1 + tx * args.tile_w1 : tx * args.tile_w;
+        const int y0 = ty * (r1 ? args.tile_h1 : args.tile_h);
+        const CUtensorMap* zm = r1 ? &zmap1 : &zmap;
+        const CUtensorMap* pm = r1 ? &pmap1 : &pmap;
+        const CUtensorMap* gm = r1 ? &gmap1 : &gmap;
+        for (int sl = 0; sl < slices; ++sl) {
+          for (int half = 0; half < 2; ++half, ++g) {
+            const uint32_t est = g % kEStages, eph = (g / kEStages) & 1;
+            mbar_wait(&eempty[est], eph ^ 1);
+            mbar_arrive_expect_tx(&efull[est], bytes);
+            uint8_t* dst = ering + est * estage_bytes;
+            const int c0 = nb * BN + half * (BN >> 1) + sl * 32;
+            tma_load_5d(zm, &efull[est], dst, c0, x0, 0, y0, n);
+            if (args.inbwd.mode == 2) tma_load_5d(pm, &efull[est], dst + kESliceBytes, c0, x0, 0, y0, n);
+            if (args.inbwd.has_add)
+              tma_load_5d(gm, &efull[est], dst + add_slot, c0, x0 + shift, 0, y0 + shift, n);
+          }
+        }
+      }
+    }
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
@@ -374,39 +430,38 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
         // statistics row of this warp: image-major, then (region, tile row, tile column, warp quarter)
         const int64_t prow = static_cast<int64_t>(n) * args.stat.rows_per_img + args.stat.row0 +
                              ((r1 ? args.tiles_y * args.tiles_x : 0) + ty * ntx + tx) * 4 + q;
-        // InstanceNorm-backward statistics: the interior pixel this (padded) output pixel mirrors, and the pixel of
-        // the skip-connection gradient added to interior outputs
-        const __nv_bfloat16* y_px = nullptr;
-        const __nv_bfloat16* add_px = nullptr;
-        const float* st_img = nullptr;
-        if (args.inbwd.y != nullptr) {
-          const InBwdStat& ib = args.inbwd;
-          int iy = py - ib.halo, ix = px - ib.halo;
-          const bool interior = iy >= 0 && iy < ib.h && ix >= 0 && ix < ib.w;
-          iy = iy < 0 ? -iy : (iy >= ib.h ? 2 * (ib.h - 1) - iy : iy);
-          ix = ix < 0 ? -ix : (ix >= ib.w ? 2 * (ib.w - 1) - ix : ix);
-          if (valid) {
-            y_px = ib.y + ((static_cast<int64_t>(n) * ib.h + iy) * ib.w + ix) * ib.c + nb * BN;
-            if (ib.add != nullptr && interior)
-              add_px = ib.add + ((static_cast<int64_t>(n) * (ib.h + 2 * ib.add_halo) + iy + ib.add_halo) *
-                                     (ib.w + 2 * ib.add_halo) + ix + ib.add_halo) * ib.c + nb * BN;
-          }
-          st_img = ib.stats + (static_cast<int64_t>(n) * ib.c + nb * BN) * 2;
+        // skip-connection gradient: added to interior outputs only (INBWD)
+        bool interior = false;
+        if constexpr (INBWD) {
+          const int iy = py - args.inbwd.halo, ix = px - args.inbwd.halo;
+          interior = valid && iy >= 0 && iy < args.inbwd.h && ix >= 0 && ix < args.inbwd.w;
         }
-        // one 16-column chunk: accumulator -> (+ skip gradient) -> bias / activation -> statistics -> store
-        auto chunk = [&](int c, const uint4 (&yreg)[2], const uint4 (&areg)[2]) {
+        // one 16-column chunk: accumulator -> (+ skip gradient) -> bias / activation -> statistics -> store.
+        // erow: this thread's row of the staged operand slice (INBWD), sub = which half of its 32 channels
+        auto chunk = [&](int c, const uint8_t* erow, int sub, int swz) {
           uint32_t v[16];
           tmem_ld16(t_addr + c, v);
           tmem_ld_wait();
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          if (add_px != nullptr) {
-            float e[16];
-            unpack_bf16x8(areg[0], e);
-            unpack_bf16x8(areg[1], e + 8);
+          float zv[16], zp[16];
+          if constexpr (INBWD) {
+            // 64-byte swizzle: the 16-byte chunk index is XORed with bits [1, 3) of the row
+            const int k0 = ((2 * sub) ^ swz) << 4, k1 = ((2 * sub + 1) ^ swz) << 4;
+            unpack_bf16x8(*reinterpret_cast<const uint4*>(erow + k0), zv);
+            unpack_bf16x8(*reinterpret_cast<const uint4*>(erow + k1), zv + 8);
+            if (args.inbwd.mode == 2) {
+              unpack_bf16x8(*reinterpret_cast<const uint4*>(erow + kESliceBytes + k0), zp);
+              unpack_bf16x8(*reinterpret_cast<const uint4*>(erow + kESliceBytes + k1), zp + 8);
+            }
+            if (args.inbwd.has_add && interior) {
+              float e[16];
+              unpack_bf16x8(*reinterpret_cast<const uint4*>(erow + add_slot + k0), e);
+              unpack_bf16x8(*reinterpret_cast<const uint4*>(erow + add_slot + k1), e + 8);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] += e[i];
+              for (int i = 0; i < 16; ++i) f[i] += e[i];
+            }
           }
           if (args.bias != nullptr) {
             const float4* bp = reinterpret_cast<const float4*>(args.bias + nb * BN + c);
@@ -424,11 +479,15 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
             for (int i = 0; i < 16; ++i) f[i] = apply_act(f[i], args.act);
           }
           if (args.stat.partial != nullptr) {
-            if (st_img != nullptr)
-              inbwd_accumulate(args.stat, f, yreg, st_img + 2 * c, args.inbwd.act, valid, lane, prow, nb * BN + c,
-                               args.inbwd.y_dt);
-            else
+            if constexpr (INBWD) {
+              float fr[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) fr[i] = valid ? __bfloat162float(__float2bfloat16(f[i])) : 0.f;
+              if (!(args.inbwd.debug & 1))
+                inbwd_accumulate(args.stat, fr, zv, zp, args.inbwd.mode, lane, prow, nb * BN + c);
+            } else {
               stat_accumulate(args.stat, f, valid, lane, prow, nb * BN + c, args.out.fp32);
+            }
           }
           if (valid) {
             if (args.out.fp32 == FPG_DT_FP32) {
@@ -440,33 +499,22 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
             }
           }
         };
-        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-        if (st_img == nullptr) {
-          const uint4 none[2] = {zero4, zero4};
-          for (int c = c_begin; c < c_end; c += 16) chunk(c, none, none);
+        if constexpr (!INBWD) {
+          for (int c = c_begin; c < c_end; c += 16) chunk(c, nullptr, 0, 0);
         } else {
-          // the y (and skip-gradient) reads are global loads with ~1 us latency: two register buffers, each reloaded
-          // for the chunk after next as soon as it has been consumed
-          uint4 y0[2] = {zero4, zero4}, y1[2] = {zero4, zero4}, a0[2] = {zero4, zero4}, a1[2] = {zero4, zero4};
-          auto fetch = [&](int c, uint4 (&yreg)[2], uint4 (&areg)[2]) {
-            if (y_px != nullptr) {
-              yreg[0] = __ldg(reinterpret_cast<const uint4*>(y_px + c));
-              yreg[1] = __ldg(reinterpret_cast<const uint4*>(y_px + c) + 1);
-            }
-            if (add_px != nullptr) {
-              areg[0] = __ldg(reinterpret_cast<const uint4*>(add_px + c));
-              areg[1] = __ldg(reinterpret_cast<const uint4*>(add_px + c) + 1);
-            }
-          };
-          if (c_begin < c_end) fetch(c_begin, y0, a0);
-          if (c_begin + 16 < c_end) fetch(c_begin + 16, y1, a1);
-          for (int c = c_begin; c < c_end; c += 32) {
-            chunk(c, y0, a0);
-            if (c + 32 < c_end) fetch(c + 32, y0, a0);
-            if (c + 16 < c_end) {
-              chunk(c + 16, y1, a1);
-              if (c + 48 < c_end) fetch(c + 48, y1, a1);
-            }
+          // operand slices arrive in the order (slice 0, half 0), (slice 0, half 1), (slice 1, half 0), ...
+          const int half = (warp - 2) >> 2;
+          const int slices = (c_end - c_begin) >> 5;  // 32-channel slices of this half (launcher: block_n % 64 == 0)
+          for (int sl = 0; sl < slices; ++sl) {
+            const uint32_t g = (it * static_cast<uint32_t>(slices) + sl) * 2 + half;
+            const uint32_t est = g % kEStages, eph = (g / kEStages) & 1;
+            if (!(args.inbwd.debug & 2)) mbar_wait(&efull[est], eph);
+            const uint8_t* erow = ering + est * estage_bytes + row * 64;
+            const int swz = (row >> 1) & 3;
+            chunk(c_begin + sl * 32, erow, 0, swz);
+            chunk(c_begin + sl * 32 + 16, erow, 1, swz);
+            __syncwarp();
+            if (lane == 0 && !(args.inbwd.debug & 2)) mbar_arrive(&eempty[est]);
           }
         }
       }
@@ -1224,20 +1272,40 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
   args.stat.partial = d->stat_partial;
   args.stat.rows_per_img = d->stat_rows_per_img;
   args.stat.row0 = d->stat_row0;
-  args.inbwd.y = static_cast<const __nv_bfloat16*>(d->inbwd_y);
-  args.inbwd.stats = d->inbwd_stats;
-  args.inbwd.add = static_cast<const __nv_bfloat16*>(d->inbwd_add);
+  args.inbwd.mode = d->inbwd_mode;
+  args.inbwd.has_add = d->inbwd_has_add;
   args.inbwd.h = d->inbwd_h;
   args.inbwd.w = d->inbwd_w;
-  args.inbwd.c = d->inbwd_c;
   args.inbwd.halo = d->inbwd_halo;
-  args.inbwd.add_halo = d->inbwd_add_halo;
-  args.inbwd.act = d->inbwd_act;
-  args.inbwd.y_dt = d->inbwd_y_dt;
-  if (d->inbwd_y != nullptr)
-    FPG_REQUIRE(!d->cta_pair && d->stat_partial != nullptr && d->inbwd_stats != nullptr && d->out.fp32 == FPG_DT_BF16 &&
-                    d->inbwd_c == d->block_n * d->n_blocks && d->out.mul_y == 1 && d->out.mul_x == 1,
-                "InstanceNorm-backward statistics: 1-CTA stride-1 bf16 launch with the statistics buffer");
+  args.inbwd.add_shift = d->inbwd_add_halo - d->inbwd_halo;
+  args.inbwd.n_tensors = 1 + (d->inbwd_mode == 2 ? 1 : 0) + (d->inbwd_has_add ? 1 : 0);
+  {
+    const char* dbg = getenv("FPG_INBWD_DEBUG");
+    args.inbwd.debug = dbg ? atoi(dbg) : 0;
+  }
+  const bool inbwd = d->inbwd_mode != 0;
+  CUtensorMap emap[6];  // z, z1, zprev, zprev1, add, add1 (copies of the activation map when unused)
+  for (int i = 0; i < 6; ++i) emap[i] = amap;
+  if (inbwd) {
+    FPG_REQUIRE((d->inbwd_mode == 1 || d->inbwd_mode == 2) && !d->cta_pair && d->stat_partial != nullptr &&
+                    d->out.fp32 == FPG_DT_BF16 && d->out.mul_y == 1 && d->out.mul_x == 1 && d->cblk == 64 &&
+                    d->block_n % 64 == 0 && d->bias == nullptr && d->act == FPG_ACT_NONE,
+                "InstanceNorm-backward reductions: 1-CTA stride-1 bf16 launch, block_n a multiple of 64, with the "
+                "statistics buffer");
+    const fpg_tmap* src[6] = {&d->inbwd_z,    &d->inbwd_z1,   &d->inbwd_prev,
+                              &d->inbwd_prev1, &d->inbwd_add, &d->inbwd_add1};
+    for (int i = 0; i < 6; ++i) {
+      const bool region1 = (i & 1) != 0;
+      const bool used = (i < 2) || (i < 4 && d->inbwd_mode == 2) || (i >= 4 && d->inbwd_has_add);
+      if (!used || (region1 && !two_regions)) continue;
+      FPG_REQUIRE(src[i]->box[0] == 32 && src[i]->swizzle_bytes == 64 &&
+                      src[i]->box[1] == static_cast<uint32_t>(region1 ? d->tile_w1 : d->tile_w) &&
+                      src[i]->box[3] == static_cast<uint32_t>(region1 ? d->tile_h1 : d->tile_h),
+                  "InstanceNorm-backward operand view %d: box {32, tile_w, 1, tile_h, 1}, 64-byte swizzle", i);
+      rc = encode_tmap(src[i], &emap[i]);
+      if (rc) return rc;
+    }
+  }
   args.stat.c_total = d->block_n * d->n_blocks;
   for (int i = 0; i < FPG_MAX_TAPS; ++i) args.taps[i] = d->taps[i];
 
@@ -1265,22 +1333,29 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
     return 0;
   }
   const int grid = total_tiles < sms ? total_tiles : sms;
-  const size_t smem =
-      static_cast<size_t>(d->stages) * (16384 * m_sub + d->block_n * 128) + (2 * d->stages + 4) * 8 + 16 + 1024;
+  if (const char* cap = getenv("FPG_FPROP_STAGES_CAP")) {  // experiment: effect of the ring depth
+    const int c = atoi(cap);
+    if (c >= 2 && c < args.stages) args.stages = c;
+  }
+  const size_t smem = static_cast<size_t>(d->stages) * (16384 * m_sub + d->block_n * 128) +
+                      (inbwd ? kEStages * args.inbwd.n_tensors * kESliceBytes : 0) +
+                      (2 * d->stages + 4 + 2 * kEStages) * 8 + 16 + 1024;
   FPG_REQUIRE(smem <= 227 * 1024, "shared memory %zu", smem);
-#define FPG_LAUNCH_FPROP(CB)                                                                                     \
-  do {                                                                                                           \
-    FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_fprop_kernel<CB>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                        static_cast<int>(smem)));                                                \
-    FPG_CUDA_CHECK(launch_persistent(igemm_fprop_kernel<CB>, dim3(grid), dim3(kFpropThreads), smem, st, amap, bmap, amap1, \
-                                     args));                                                                     \
+#define FPG_LAUNCH_FPROP(CB, IB, THREADS)                                                                          \
+  do {                                                                                                             \
+    FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_fprop_kernel<CB, IB>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                        static_cast<int>(smem)));                                                  \
+    FPG_CUDA_CHECK(launch_persistent(igemm_fprop_kernel<CB, IB>, dim3(grid), dim3(THREADS), smem, st, amap, bmap,  \
+                                     amap1, emap[0], emap[1], emap[2], emap[3], emap[4], emap[5], args));          \
   } while (0)
-  if (d->cblk == 64) {
-    FPG_LAUNCH_FPROP(64);
+  if (inbwd) {
+    FPG_LAUNCH_FPROP(64, true, kFpropThreadsInBwd);
+  } else if (d->cblk == 64) {
+    FPG_LAUNCH_FPROP(64, false, kFpropThreads);
   } else if (d->cblk == 32) {
-    FPG_LAUNCH_FPROP(32);
+    FPG_LAUNCH_FPROP(32, false, kFpropThreads);
   } else {
-    FPG_LAUNCH_FPROP(16);
+    FPG_LAUNCH_FPROP(16, false, kFpropThreads);
   }
 #undef FPG_LAUNCH_FPROP
   FPG_CUDA_CHECK(cudaGetLastError());

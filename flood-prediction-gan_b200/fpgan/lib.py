@@ -37,10 +37,10 @@ class FpropDesc(C.Structure):
                 ("act", C.c_int32), ("stages", C.c_int32), ("cta_pair", C.c_int32), ("bias", C.c_void_p), ("out", OutView),
                 ("taps", Tap * FPG_MAX_TAPS), ("a1", TMap), ("tiles_y1", C.c_int32), ("tiles_x1", C.c_int32),
                 ("tile_h1", C.c_int32), ("tile_w1", C.c_int32), ("x_org1", C.c_int32), ("stat_partial", C.c_void_p),
-                ("stat_rows_per_img", C.c_int32), ("stat_row0", C.c_int32), ("inbwd_y", C.c_void_p),
-                ("inbwd_stats", C.c_void_p), ("inbwd_add", C.c_void_p), ("inbwd_h", C.c_int32), ("inbwd_w", C.c_int32),
-                ("inbwd_c", C.c_int32), ("inbwd_halo", C.c_int32), ("inbwd_add_halo", C.c_int32),
-                ("inbwd_act", C.c_int32), ("inbwd_y_dt", C.c_int32)]
+                ("stat_rows_per_img", C.c_int32), ("stat_row0", C.c_int32), ("inbwd_mode", C.c_int32),
+                ("inbwd_has_add", C.c_int32), ("inbwd_h", C.c_int32), ("inbwd_w", C.c_int32),
+                ("inbwd_halo", C.c_int32), ("inbwd_add_halo", C.c_int32), ("inbwd_z", TMap), ("inbwd_z1", TMap),
+                ("inbwd_prev", TMap), ("inbwd_prev1", TMap), ("inbwd_add", TMap), ("inbwd_add1", TMap)]
 
 
 class RowsDesc(C.Structure):
@@ -119,7 +119,7 @@ SIGNATURES = {
     "fpg_instnorm_scratch_floats": (_i64, [_P(Act)]),
     "fpg_instnorm_stats": (C.c_int, [_P(Act), _f32, _vp, _vp, _vp, _vp]),
     "fpg_instnorm_apply": (C.c_int, [_P(Act), _vp, C.c_int, _P(Act), _P(Act), _P(Act), _vp]),
-    "fpg_conv2d_dgrad_inbwd": (C.c_int, [_P(Act), _vp, _P(ConvGeom), _P(Act), _P(Act), _vp, C.c_int, _P(Act), _vp,
+    "fpg_conv2d_dgrad_inbwd": (C.c_int, [_P(Act), _vp, _P(ConvGeom), _P(Act), _P(Act), _P(Act), _P(Act), _vp,
                                          _P(_i32), _vp]),
     "fpg_instnorm_bwd_sums_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _vp, _vp]),
     "fpg_instnorm_bwd_apply": (C.c_int, [_P(Act), _P(Act), _vp, _vp, C.c_int, _P(Act), _vp]),

@@ -216,9 +216,10 @@ class _NetBase:
     def _conv_bwd(self, name, x, dy, grads, need_dx, dx_halo=0, in_bwd=None):
         """Backward of layer `name`: x = saved layer input, dy = gradient of its raw output.
         Writes the weight (and used bias) gradient into `grads`; returns dx (incl. halo when dx_halo > 0).
-        in_bwd = (y, stats, act, add): x is act(IN(y)) -- the data-gradient kernel then also produces the plane means
-        of that InstanceNorm's backward (and merges the skip gradient `add` into dx's interior); returns (dx, red),
-        red = None when the layer has no such epilogue (dx is then the plain gradient, `add` NOT merged)."""
+        in_bwd = (xprev, add): x is the output of an InstanceNorm block -- relu(IN(y)) when xprev is None, else
+        xprev + IN(y) -- and the data-gradient kernel also produces the plane means of that InstanceNorm's backward
+        from x (and xprev), merging the skip gradient `add` into dx's interior; returns (dx, red), red = None when the
+        layer has no such epilogue (dx is then the plain gradient, `add` NOT merged)."""
         L = self.layers[name]
         g = L.spec.g
         if grads is not None:
@@ -242,8 +243,8 @@ class _NetBase:
         else:
             dx = ActBuf(x.n, x.h, x.w, g.c_in, halo=dx_halo, zero=False)
             if in_bwd is not None:  # fuse the reduction pass of the producing InstanceNorm's backward (ops.py)
-                y_prev, stats_prev, act_prev, add = in_bwd
-                red = ops.conv_dgrad_inbwd(dy, L.spec, dx, y_prev, stats_prev, act_prev, add)
+                xprev, add = in_bwd
+                red = ops.conv_dgrad_inbwd(dy, L.spec, dx, x, xprev, add)
                 if red is not None:
                     return dx, red
             ops.conv_dgrad(dy, L.spec, dx)
@@ -332,7 +333,7 @@ class _ResnetGeneratorNet(_NetBase):
                     gres = ActBuf(yb.n, yb.h, yb.w, yb.c, zero=False)  # total gradient w.r.t. x_{i+1} (skip branch)
                 ops.instnorm_bwd(dz, yb, sb, ACT_NONE, dyb, dz2=dz2, dres=gres)
                 skip = gres if gres is not None else dz
-            dza, red_a = self._conv_bwd(n2, za, dyb, grads, True, dx_halo=1, in_bwd=(ya, sa, ACT_RELU, None))
+            dza, red_a = self._conv_bwd(n2, za, dyb, grads, True, dx_halo=1, in_bwd=(None, None))  # za = relu(IN(ya))
             dya = ActBuf(ya.n, ya.h, ya.w, ya.c, zero=False)
             if red_a is not None:
                 ops.instnorm_bwd_apply(dza, ya, sa, red_a, ACT_RELU, dya)
@@ -341,7 +342,9 @@ class _ResnetGeneratorNet(_NetBase):
             # x_i = act(IN(y_prev)) + (residual input of block i-1): block i-1's second norm, or conv3's for block 0
             y_prev, s_prev, act_prev = (t[f"b{i - 1}"][3], t[f"b{i - 1}"][4], ACT_NONE) if i > 0 else \
                 (t["y3"], t["s3"], ACT_RELU)
-            dz, red = self._conv_bwd(n1, xi, dya, grads, True, dx_halo=1, in_bwd=(y_prev, s_prev, act_prev, skip))
+            # x_i = x_{i-1} + IN(yb of block i-1) for i > 0, relu(IN(y3)) for the trunk input
+            dz, red = self._conv_bwd(n1, xi, dya, grads, True, dx_halo=1,
+                                     in_bwd=(t[f"x{i - 1}"] if i > 0 else None, skip))
             dz2 = None if red is not None else skip
         dy3 = ActBuf(t["y3"].n, t["y3"].h, t["y3"].w, t["y3"].c, zero=False)
         if red is not None:

@@ -324,18 +324,22 @@ def instnorm_bwd(dz, y, stats, act, dy, dz2=None, dres=None):
          _stream())
 
 
-# Opt-in (FPG_INBWD_EPILOGUE=1): parity-green but slower today -- the epilogue's loads of y / the skip gradient queue
-# behind the TMA traffic of the main loop (150 us instead of 69 us per residual dgrad).
-INBWD_EPILOGUE = os.environ.get("FPG_INBWD_EPILOGUE", "0") == "1"
+# The reduction pass of the InstanceNorm backward runs in the epilogue of the data-gradient kernel that produces its
+# upstream gradient (FPG_INBWD_EPILOGUE=0 restores the separate streamed pass for A/B measurements).
+# Values: "0" off, "relu" only where the staged operand is the convolution's own input (relu-type norms: one tensor),
+# "1" everywhere in the residual trunk (residual-type norms stage three tensors).
+INBWD_EPILOGUE = os.environ.get("FPG_INBWD_EPILOGUE", "relu")
 
 
-def conv_dgrad_inbwd(dy, spec, dx, y, stats, act, add=None, force=False):
-    """dx (incl. halo) = conv_backward_data(dy, w) [+ add on the interior] where dx is the gradient w.r.t.
-    z = act(IN(y)); the reduction pass of that InstanceNorm's backward runs in the conv epilogue. Returns
+def conv_dgrad_inbwd(dy, spec, dx, z, zprev=None, add=None, force=False):
+    """dx (incl. halo) = conv_backward_data(dy, w) [+ add on the interior], the gradient w.r.t. the convolution's
+    saved input z = relu(IN(y)) (zprev None) or z = zprev + IN(y) (residual block output); the reduction pass of that
+    InstanceNorm's backward runs in the conv epilogue, fed by z (and zprev) staged through shared memory. Returns
     red [n, c, 2] = {mean g', mean g' * zhat} for instnorm_bwd_apply, or None when this layer has no such epilogue
     (nothing was launched: the caller runs conv_dgrad + instnorm_bwd)."""
     lib = L.load()
-    if not (INBWD_EPILOGUE or force) or spec.g.stride != 1:
+    enabled = force or INBWD_EPILOGUE == "1" or (INBWD_EPILOGUE == "relu" and zprev is None and add is None)
+    if not enabled or spec.g.stride != 1 or z.halo != dx.halo or dx.c % 64:
         return None
     rows = lib.fpg_conv_stats_rows(dy.ref(), spec.gref(), dx.ref(), 1)
     if rows <= 0:
@@ -346,7 +350,8 @@ def conv_dgrad_inbwd(dy, spec, dx, y, stats, act, add=None, force=False):
     if PROFILE is not None:
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-    rc = lib.fpg_conv2d_dgrad_inbwd(dy.ref(), _ptr(spec.w_dgrad), spec.gref(), dx.ref(), y.ref(), _ptr(stats), act,
+    rc = lib.fpg_conv2d_dgrad_inbwd(dy.ref(), _ptr(spec.w_dgrad), spec.gref(), dx.ref(), z.ref(),
+                                    zprev.ref() if zprev is not None else None,
                                     add.ref() if add is not None else None, _ptr(ws), C.byref(rows_out), _stream())
     if rc == 1:
         return None
@@ -357,7 +362,7 @@ def conv_dgrad_inbwd(dy, spec, dx, y, stats, act, add=None, force=False):
     global LAUNCHES
     LAUNCHES += 1
     red = torch.empty(dx.n, dx.c, 2, dtype=torch.float32, device=dx.t.device)
-    _run("instnorm_bwd", 1, "fpg_instnorm_bwd_sums_finalize", _ptr(ws), rows_out.value, dx.n, dx.c, y.h * y.w,
+    _run("instnorm_bwd", 1, "fpg_instnorm_bwd_sums_finalize", _ptr(ws), rows_out.value, dx.n, dx.c, dx.h * dx.w,
          _ptr(red), _stream())
     return red
 

@@ -103,19 +103,19 @@ typedef struct {
    * fpg_conv_stats_rows() gives the rows one launch contributes per image. */
   float* stat_partial;
   int32_t stat_rows_per_img, stat_row0;
-  /* Optional InstanceNorm-BACKWARD statistics (inbwd_y != NULL, needs stat_partial): the launch produces dz, the
-   * gradient w.r.t. a (reflect-haloed) activation z = act(IN(y)). Instead of {sum, sum of squares} the epilogue
-   * accumulates per column {sum g', sum g' * zhat}, g' = stored value * act'(zhat), zhat = (y[m] - mean) * rstd with m
-   * the interior pixel that output pixel mirrors (itself for interior pixels): the sums are linear in dz, so the halo
-   * needs no fold first. inbwd_add (optional) is added to the INTERIOR outputs before they are stored (the
-   * skip-connection gradient; it is read at its own interior when inbwd_add_halo > 0).
-   *   inbwd_y: bf16 or fp16 [n][inbwd_h][inbwd_w][c], no halo; inbwd_stats: fp32 [n][c][2] = {mean, rstd};
-   *   inbwd_halo: halo of the output tensor (tile coordinates are padded coordinates). */
-  const void* inbwd_y;
-  const float* inbwd_stats;
-  const void* inbwd_add;
-  int32_t inbwd_h, inbwd_w, inbwd_c, inbwd_halo, inbwd_add_halo, inbwd_act;
-  int32_t inbwd_y_dt; /* element type of inbwd_y: FPG_DT_BF16 or FPG_DT_FP16 */
+  /* Optional InstanceNorm-BACKWARD reductions (inbwd_mode != 0, needs stat_partial): the launch produces dz, the
+   * gradient w.r.t. the (reflect-haloed) input z of a stride-1 convolution whose input is the output of an
+   * InstanceNorm block. Instead of {sum, sum of squares} the epilogue accumulates per column what that norm's backward
+   * needs, from z itself (the tensor saved for the weight gradient; same geometry as dz):
+   *   inbwd_mode 1, z = relu(zhat):                  {sum f [z > 0], sum f z}    = {sum g', sum g' zhat}
+   *   inbwd_mode 2, z = zprev + zhat (residual add): {sum f, sum f (z - zprev)}  = {sum g,  sum g zhat}
+   * f = the stored value. The sums are linear in dz and z's halo mirrors its interior, so the halo needs no fold first.
+   * inbwd_has_add: the skip-connection gradient (view inbwd_add) is added to the INTERIOR outputs before they are
+   * stored and reduced; it is read at coordinates shifted by inbwd_add_halo - inbwd_halo.
+   * The views are 5-D like `a` with boxes {32, tile_w, 1, tile_h, 1} (…1: tile shape of the second region). */
+  int32_t inbwd_mode, inbwd_has_add;
+  int32_t inbwd_h, inbwd_w, inbwd_halo, inbwd_add_halo;
+  fpg_tmap inbwd_z, inbwd_z1, inbwd_prev, inbwd_prev1, inbwd_add, inbwd_add1;
 } fpg_igemm_fprop_desc;
 
 /* D_item[m, n] = sum_{pixel} X[pixel + xtap, xc + m] * Y[pixel + ytap, yc + n], split over pixel ranges,
@@ -252,16 +252,19 @@ int fpg_conv2d_dgrad_stats(const fpg_act* dy, const void* w_packed_t, const floa
 int fpg_instnorm_stats_finalize(const float* stat_partial, int32_t rows_per_img, int32_t n, int32_t c,
                                 int64_t count_per_img, float eps, float* stats, void* stream);
 
-/* Data gradient of a stride-1 convolution whose input was z = act(IN(y)) (+ reflect halo), fused with the reduction
- * pass of that InstanceNorm's backward: dx (incl. halo) = conv_backward_data(dy, w) [+ add on the interior], and
- * stat_partial receives the per-warp partials of {sum g', sum g' * zhat} (see fpg_igemm_fprop_desc.inbwd_*; sized
- * as for fpg_conv2d_dgrad_stats). fpg_instnorm_bwd_sums_finalize turns them into red[(n*c + ch)*2] = {mean g',
- * mean g' * zhat} over the h*w plane; fpg_instnorm_bwd_apply then folds dx's halo in place and applies
- * dy = rstd * (g' - mean g' - zhat * mean g' zhat): together they equal fpg_instnorm_bwd(dz = dx, dz2 = add, ...)
- * without its streamed reduction pass (the dominant elementwise cost of the residual trunk's backward).
- * Returns FPG_ENOTSUP-style code 1 when the layer does not plan as one tiled launch (caller falls back). */
+/* Data gradient of a stride-1 convolution whose input z (with its reflect halo; the tensor saved for the weight
+ * gradient) is the output of an InstanceNorm block, fused with the reduction pass of that norm's backward:
+ * dx (incl. halo) = conv_backward_data(dy, w) [+ add on the interior], and stat_partial receives the per-warp partials
+ * of the two plane sums (see fpg_igemm_fprop_desc.inbwd_*; sized as for fpg_conv2d_dgrad_stats):
+ *   zprev == NULL: z = relu(IN(y))           (first convolution's output inside a residual block; the trunk input)
+ *   zprev != NULL: z = zprev + IN(y)         (block output; zprev = the block's input, same geometry as z)
+ * fpg_instnorm_bwd_sums_finalize turns them into red[(n*c + ch)*2] = {mean g', mean g' * zhat} over the h*w plane;
+ * fpg_instnorm_bwd_apply then folds dx's halo in place and applies dy = rstd * (g' - mean g' - zhat * mean g' zhat):
+ * together they equal fpg_instnorm_bwd(dz = dx, dz2 = add, ...) without its streamed reduction pass (the dominant
+ * elementwise cost of the residual trunk's backward: model_architectures.py:408-418 under autograd).
+ * Returns 1 when the layer does not plan as one tiled 1-CTA launch with block_n % 64 == 0 (caller falls back). */
 int fpg_conv2d_dgrad_inbwd(const fpg_act* dy, const void* w_packed_t, const fpg_conv_geom* g, const fpg_act* dx,
-                           const fpg_act* y, const float* stats, int act, const fpg_act* add, float* stat_partial,
+                           const fpg_act* z, const fpg_act* zprev, const fpg_act* add, float* stat_partial,
                            int32_t* rows_per_img, void* stream);
 int fpg_instnorm_bwd_sums_finalize(const float* stat_partial, int32_t rows_per_img, int32_t n, int32_t c,
                                    int64_t count_per_img, float* red, void* stream);

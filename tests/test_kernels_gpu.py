@@ -210,46 +210,52 @@ def test_instnorm_fwd_bwd(shape, halo, act, f16):
 
 
 @pytest.mark.parametrize("f16", [False, True])
-@pytest.mark.parametrize("act,with_add", [(1, False), (0, True), (1, True)])
-def test_dgrad_with_instnorm_backward_statistics(act, with_add, f16):
-    """conv_dgrad_inbwd + instnorm_bwd_apply == autograd of conv(reflect_pad(act(IN(y)) [+ skip])) w.r.t. y and the
-    skip input: the reduction pass of the InstanceNorm backward runs in the data-gradient kernel's epilogue (halo
-    positions weighted with the statistics of the pixel they mirror, skip gradient merged on the interior)."""
+@pytest.mark.parametrize("act,with_add,batch", [(1, False, 2), (0, True, 2), (1, True, 2), (0, True, 16), (1, False, 16)])
+def test_dgrad_with_instnorm_backward_statistics(act, with_add, batch, f16):
+    """conv_dgrad_inbwd + instnorm_bwd_apply == autograd of conv(reflect_pad(z)) w.r.t. y (and the block input), where
+    z = relu(IN(y)) (act 1) or z = zprev + IN(y) (act 0: residual block output): the reduction pass of the InstanceNorm
+    backward runs in the data-gradient kernel's epilogue, fed by the saved conv input z (and zprev) staged through a
+    shared-memory ring; the skip gradient is merged on the interior. batch 16 = the benchmarked shape (two tile regions,
+    block_n 256); f16: the pre-norm tensor read by the apply pass is an fp16 buffer."""
     from fpgan import ops
-    n, c, k, h = 2, 256, 256, 64
+    n, c, k, h = batch, 256, 256, 64
     g = torch.Generator(device="cuda").manual_seed(11)
-    y = bf16r(torch.randn(n, c, h, h, device="cuda", generator=g) * 2 + 0.3).requires_grad_(True)
-    skip_in = bf16r(torch.randn(n, c, h, h, device="cuda", generator=g)).requires_grad_(True)
+    y = (torch.randn(n, c, h, h, device="cuda", generator=g) * 2 + 0.3)
+    y = (y.half().float() if f16 else bf16r(y)).requires_grad_(True)
+    zprev = bf16r(torch.randn(n, c, h, h, device="cuda", generator=g)).requires_grad_(True)
     wt = bf16r(torch.randn(k, c, 3, 3, device="cuda", generator=g) / 48)
-    fn = {0: lambda t: t, 1: F.relu}[act]
-    x = fn(F.instance_norm(y, eps=1e-5)) + skip_in          # block input = act(IN(y)) + residual
-    out = F.conv2d(F.pad(x, (1,) * 4, "reflect"), wt)
+    zhat = F.instance_norm(y, eps=1e-5)
+    z = F.relu(zhat) if act == 1 else zprev + zhat
+    out = F.conv2d(F.pad(z, (1,) * 4, "reflect"), wt)
     dout = bf16r(torch.randn_like(out) * 0.1)
-    dskip_up = bf16r(torch.randn(n, c, h, h, device="cuda", generator=g) * 0.1)  # gradient arriving on the skip path
+    dskip_up = bf16r(torch.randn(n, c, h, h, device="cuda", generator=g) * 0.1)  # gradient arriving on z directly
     ups = [dout, dskip_up] if with_add else [dout]
-    outs = [out, x] if with_add else [out]
-    dy_ref, dskip_ref = torch.autograd.grad(outs, (y, skip_in), ups)
+    outs = [out, z] if with_add else [out]
+    dy_ref, dprev_ref = torch.autograd.grad(outs, (y, zprev), ups, allow_unused=True)
 
     spec = ops.ConvSpec(3, 3, 1, 0, c, k)
     spec.pack(wt.contiguous())
     yb = ops.ActBuf.from_nchw(y.detach(), f16=f16)
     stats = torch.empty(n * c * 2, device="cuda")
     ops.instnorm_stats(yb, stats)
+    zb = ops.ActBuf.from_nchw(z.detach(), halo=1)          # the convolution's saved input (bf16, reflect halo)
+    pb = ops.ActBuf.from_nchw(zprev.detach(), halo=1) if act == 0 else None
     dyb = ops.ActBuf.from_nchw(dout)
     dx = ops.ActBuf(n, h, h, c, halo=1, zero=False)
     add = None
     if with_add:  # the skip gradient lives in the interior of a haloed buffer, as in the trunk backward
         add = ops.ActBuf(n, h, h, c, halo=1)
+        add.t.normal_()  # the halo of that buffer holds stale values: they must not be read as gradient
         add.t[:, 1:-1, 1:-1, :] = dskip_up.permute(0, 2, 3, 1)
-    red = ops.conv_dgrad_inbwd(dyb, spec, dx, yb, stats, act, add, force=True)  # opt-in path, tested regardless
+    red = ops.conv_dgrad_inbwd(dyb, spec, dx, zb, pb, add, force=True)
     if red is None and os.environ.get("FPG_DISABLE_TILE_REGIONS"):
         pytest.skip("the single-tile-shape plan of the haloed gradient has no statistics epilogue (caller falls back)")
     assert red is not None, "the residual conv must plan the statistics epilogue"
     dy = ops.ActBuf(n, h, h, c, zero=False)
     ops.instnorm_bwd_apply(dx, yb, stats, red, act, dy)
     close_rms(dy.to_nchw(), dy_ref, 0.03, 0.004, "fused instnorm bwd")
-    # dx's interior now holds the total gradient w.r.t. the block input = gradient w.r.t. the skip input
-    close_rms(dx.t[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2).float(), dskip_ref, 0.02, 0.003, "merged skip gradient")
+    if act == 0:  # dx's interior now holds the total gradient w.r.t. z = gradient w.r.t. the block input zprev
+        close_rms(dx.t[:, 1:-1, 1:-1, :].permute(0, 3, 1, 2).float(), dprev_ref, 0.02, 0.003, "merged skip gradient")
     # and the unfused path agrees
     dx2 = ops.ActBuf(n, h, h, c, halo=1, zero=False)
     ops.conv_dgrad(dyb, spec, dx2)

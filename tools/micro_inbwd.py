@@ -1,5 +1,7 @@
-"""Micro-benchmark of the data-gradient kernel with the InstanceNorm-backward statistics epilogue on the residual
-layer shape (n16 64x64 c256): plain dgrad, fused without / with the skip-gradient merge. Usage: python tools/micro_inbwd.py"""
+"""Micro-benchmark of the data-gradient kernel with the InstanceNorm-backward reductions in its epilogue on the residual
+layer shape (n16 64x64 c256): plain dgrad, fused relu-type (one staged operand), fused residual-type with the
+skip-gradient merge (three staged operands), and the separate streamed passes they replace.
+Usage: python tools/micro_inbwd.py"""
 import os
 import sys
 
@@ -14,13 +16,21 @@ spec = ops.ConvSpec(3, 3, 1, 0, c, c)
 spec.pack((torch.randn(c, c, 3, 3, device="cuda") * 0.05).contiguous())
 dy = ops.ActBuf(n, h, h, c)
 dy.t.normal_()
-y = ops.ActBuf(n, h, h, c)
+y = ops.ActBuf(n, h, h, c, f16=True)
 y.t.normal_()
 stats = torch.empty(n * c * 2, device="cuda")
 ops.instnorm_stats(y, stats)
+z = ops.ActBuf(n, h, h, c, halo=1)
+z.t.normal_()
+zprev = ops.ActBuf(n, h, h, c, halo=1)
+zprev.t.normal_()
 add = ops.ActBuf(n, h, h, c, halo=1)
 add.t.normal_()
 dx = ops.ActBuf(n, h, h, c, halo=1, zero=False)
+dyo = ops.ActBuf(n, h, h, c, zero=False)
+gres = ops.ActBuf(n, h, h, c, zero=False)
+dz2 = ops.ActBuf(n, h, h, c)
+dz2.t.normal_()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
 
@@ -38,6 +48,13 @@ def timed(fn, reps=7):
     return ts[len(ts) // 2]
 
 
-print("plain dgrad        %.1f us" % (1e3 * timed(lambda: ops.conv_dgrad(dy, spec, dx))))
-print("fused (relu)       %.1f us" % (1e3 * timed(lambda: ops.conv_dgrad_inbwd(dy, spec, dx, y, stats, ops.ACT_RELU, force=True))))
-print("fused (none + add) %.1f us" % (1e3 * timed(lambda: ops.conv_dgrad_inbwd(dy, spec, dx, y, stats, ops.ACT_NONE, add, force=True))))
+tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("FPG_"))
+print(f"[{tag}]")
+print("plain dgrad                 %.1f us" % (1e3 * timed(lambda: ops.conv_dgrad(dy, spec, dx))))
+print("fused relu-type             %.1f us" % (1e3 * timed(lambda: ops.conv_dgrad_inbwd(dy, spec, dx, z, force=True))))
+print("fused residual-type         %.1f us" % (1e3 * timed(lambda: ops.conv_dgrad_inbwd(dy, spec, dx, z, zprev, force=True))))
+print("fused residual-type + add   %.1f us" % (1e3 * timed(lambda: ops.conv_dgrad_inbwd(dy, spec, dx, z, zprev, add, force=True))))
+red = torch.zeros(n, c, 2, device="cuda")
+print("apply pass only             %.1f us" % (1e3 * timed(lambda: ops.instnorm_bwd_apply(dx, y, stats, red, ops.ACT_NONE, dyo))))
+print("two-pass IN bwd (relu)      %.1f us" % (1e3 * timed(lambda: ops.instnorm_bwd(dx, y, stats, ops.ACT_RELU, dyo))))
+print("two-pass IN bwd (res + add) %.1f us" % (1e3 * timed(lambda: ops.instnorm_bwd(dx, y, stats, ops.ACT_NONE, dyo, dz2=dz2, dres=gres))))
