@@ -1299,7 +1299,7 @@ __global__ void bias_grad_finalize_kernel(const float* __restrict__ partial, flo
 
 // ------------------------------------------------------------------------------------------------ blend
 // one thread per pixel. content: fp32 NHWC 32 ch (27 valid, tanh applied); logits: fp32 NHWC 16 ch (10 valid)
-__global__ void blend_fwd_kernel(View content, View logits, View input, View out, int out_c0,
+__global__ void blend_fwd_kernel(View content, View logits, View input, int input_lo, View out, int out_c0,
                                  float* __restrict__ out_nchw, float* __restrict__ mask) {
   const int64_t total = static_cast<int64_t>(content.n) * content.h * content.w;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -1340,7 +1340,9 @@ __global__ void blend_fwd_kernel(View content, View logits, View input, View out
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc += c[3 * k + j] * a[k];
-    acc += __bfloat162float(ip[j]) * a[9];
+    // input_lo > 0 (fp32 parity mode): the image is carried as hi + lo bf16 halves, lo block input_lo channels on
+    const float rgb = __bfloat162float(ip[j]) + (input_lo > 0 ? __bfloat162float(ip[input_lo + j]) : 0.f);
+    acc += rgb * a[9];
     o[j] = acc;
   }
   if (out.p != nullptr) {
@@ -1702,6 +1704,15 @@ __global__ void adam_prepare_kernel(int32_t* __restrict__ state, float beta1, fl
   f[2] = static_cast<float>(static_cast<double>(f[1]) / bc1);
   f[3] = static_cast<float>(sqrt(bc2));
 }
+__device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float w1, float beta2, float eps,
+                                            float step_size, float bc2_sqrt, float grad_scale) {
+  const float gr = g * grad_scale;
+  m = (w1 < 0.5f) ? m + w1 * (gr - m) : gr - (gr - m) * (1.f - w1);  // torch.lerp(m, g, w1)
+  v = v * beta2 + (1.f - beta2) * gr * gr;
+  const float denom = sqrtf(v) / bc2_sqrt + eps;
+  p = p - step_size * (m / denom);
+}
+// 16-byte accesses (the four flat buffers are 16-byte aligned torch allocations): 28 B/parameter of traffic
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, int64_t count, float beta1, float beta2, float eps,
                                 const int32_t* __restrict__ state, float grad_scale) {
@@ -1709,16 +1720,21 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
   const float bc2_sqrt = reinterpret_cast<const float*>(state)[3];
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const float w1 = 1.f - beta1;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
-    const float gr = g[i] * grad_scale;
-    float mi = m[i], vi = v[i];
-    mi = (w1 < 0.5f) ? mi + w1 * (gr - mi) : gr - (gr - mi) * (1.f - w1);
-    vi = vi * beta2 + (1.f - beta2) * gr * gr;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] - step_size * (mi / denom);
-    m[i] = mi;
-    v[i] = vi;
+  const int64_t n4 = count >> 2;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i];
+    float4 v4 = reinterpret_cast<float4*>(v)[i];
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    adam_update(p4.x, g4.x, m4.x, v4.x, w1, beta2, eps, step_size, bc2_sqrt, grad_scale);
+    adam_update(p4.y, g4.y, m4.y, v4.y, w1, beta2, eps, step_size, bc2_sqrt, grad_scale);
+    adam_update(p4.z, g4.z, m4.z, v4.z, w1, beta2, eps, step_size, bc2_sqrt, grad_scale);
+    adam_update(p4.w, g4.w, m4.w, v4.w, w1, beta2, eps, step_size, bc2_sqrt, grad_scale);
+    reinterpret_cast<float4*>(p)[i] = p4;
+    reinterpret_cast<float4*>(m)[i] = m4;
+    reinterpret_cast<float4*>(v)[i] = v4;
   }
+  for (int64_t i = (n4 << 2) + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride)
+    adam_update(p[i], g[i], m[i], v[i], w1, beta2, eps, step_size, bc2_sqrt, grad_scale);
 }
 
 // ------------------------------------------------------------------------------------------------ flood mask
@@ -2057,8 +2073,8 @@ int fpg_bias_grad(const fpg_act* dy, float* db, int32_t k_valid, float* scratch,
   return 0;
 }
 
-int fpg_blend_fwd(const fpg_act* content, const fpg_act* logits, const fpg_act* input, const fpg_act* out,
-                  int32_t out_c0, float* out_nchw, float* mask_nhw, void* stream) {
+int fpg_blend_fwd(const fpg_act* content, const fpg_act* logits, const fpg_act* input, int32_t input_lo_offset,
+                  const fpg_act* out, int32_t out_c0, float* out_nchw, float* mask_nhw, void* stream) {
   FPG_REQUIRE(content && logits && input, "null argument");
   FPG_REQUIRE(content->c_stride >= 28 && logits->c_stride >= 12 && content->fp32 == FPG_DT_FP32 && logits->fp32 == FPG_DT_FP32,
               "blend expects fp32 content (>=28 ch) and logits (>=12 ch)");
@@ -2071,7 +2087,8 @@ int fpg_blend_fwd(const fpg_act* content, const fpg_act* logits, const fpg_act* 
   }
   const int64_t total = static_cast<int64_t>(content->n) * content->h * content->w;
   blend_fwd_kernel<<<grid_for(total, 128), 128, 0, FPG_ST(stream)>>>(view_of(content), view_of(logits),
-                                                                     view_of(input), ov, out_c0, out_nchw, mask_nhw);
+                                                                     view_of(input), input_lo_offset, ov, out_c0,
+                                                                     out_nchw, mask_nhw);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -2178,8 +2195,11 @@ int fpg_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t coun
                       int32_t* state, float grad_scale, void* stream) {
   FPG_REQUIRE(p && g && m && v && state && count > 0, "bad argument");
   adam_prepare_kernel<<<1, 32, 0, FPG_ST(stream)>>>(state, beta1, beta2);
-  int64_t blocks = (count + 255) / 256;
+  FPG_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                reinterpret_cast<uintptr_t>(v)) & 15) == 0, "Adam buffers must be 16-byte aligned");
+  int64_t blocks = (count / 4 + 255) / 256;
   if (blocks > 2368) blocks = 2368;
+  if (blocks < 1) blocks = 1;
   adam_dev_kernel<<<static_cast<unsigned>(blocks), 256, 0, FPG_ST(stream)>>>(p, g, m, v, count, beta1, beta2, eps, state,
                                                                              grad_scale);
   FPG_CUDA_CHECK(cudaGetLastError());

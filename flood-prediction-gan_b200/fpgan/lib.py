@@ -141,7 +141,9 @@ SIGNATURES = {
     "fpg_tile_gather": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _i32, _f32, _f32, _vp, _vp]),
     "fpg_act_bwd": (C.c_int, [_P(Act), _P(Act), C.c_int, _P(Act), _vp]),
     "fpg_halo_fold": (C.c_int, [_P(Act), _P(Act), _P(Act), _vp]),
-    "fpg_blend_fwd": (C.c_int, [_P(Act), _P(Act), _P(Act), _P(Act), _i32, _vp, _vp, _vp]),
+    "fpg_blend_fwd": (C.c_int, [_P(Act), _P(Act), _P(Act), _i32, _P(Act), _i32, _vp, _vp, _vp]),
+    "fpg_norm_split_f32": (C.c_int, [_P(Act), C.c_int, _f32, C.c_int, _vp, _vp, _P(Act), _vp]),
+    "fpg_pack_nchw_split": (C.c_int, [_vp, _i32, _P(Act), _vp]),
     "fpg_blend_bwd": (C.c_int, [_vp, _P(Act), _i32, _P(Act), _P(Act), _P(Act), _P(Act), _P(Act), _vp, _vp]),
     "fpg_mse_const_loss": (C.c_int, [_P(Act), _f32, _f32, _f32, _vp, _P(Act), _vp, _vp, _vp]),
     "fpg_l1_loss": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, C.c_int, _vp, _vp]),

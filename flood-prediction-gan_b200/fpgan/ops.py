@@ -415,9 +415,20 @@ def halo_fold(a, b, c):
     _run("halo_fold", 1, "fpg_halo_fold", a.ref(), b.ref() if b is not None else None, c.ref(), _stream())
 
 
-def blend_fwd(content, logits, inp, out=None, out_c0=0, out_nchw=None, mask=None):
-    _run("blend_fwd", 1, "fpg_blend_fwd", content.ref(), logits.ref(), inp.ref(), out.ref() if out is not None else None, out_c0,
-           _ptr(out_nchw), _ptr(mask), _stream())
+def blend_fwd(content, logits, inp, out=None, out_c0=0, out_nchw=None, mask=None, input_lo_offset=0):
+    _run("blend_fwd", 1, "fpg_blend_fwd", content.ref(), logits.ref(), inp.ref(), input_lo_offset,
+         out.ref() if out is not None else None, out_c0, _ptr(out_nchw), _ptr(mask), _stream())
+
+
+def norm_split_f32(y, out, norm=True, act=ACT_NONE, residual=None, skip_out=None, eps=1e-5):
+    """fp32 parity mode: out [hi | lo | hi] = act(IN(y) or y) (+ residual), fp32 throughout (see fpg_norm_split_f32)"""
+    _run("norm_split_f32", 1, "fpg_norm_split_f32", y.ref(), 1 if norm else 0, float(eps), act, _ptr(residual),
+         _ptr(skip_out), out.ref(), _stream())
+
+
+def pack_nchw_split(src, dst):
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    _run("pack_nchw_split", 1, "fpg_pack_nchw_split", _ptr(src), src.shape[1], dst.ref(), _stream())
 
 
 def blend_bwd(content, logits, inp, dcontent, dlogits, dout_nchw=None, dout_nhwc=None, dout_c0=0, dimage_nchw=None):

@@ -429,12 +429,13 @@ int fpg_sq_err_sum(const float* a, const float* b, int64_t count, float clamp_lo
  * Attention / content blend -- model_architectures.py:353-399.
  *   content: fp32, tanh already applied, 27 valid channels (9 RGB triplets) in a 32-channel buffer
  *   logits:  fp32, 10 valid channels in a 16-channel buffer (pre-softmax)
- *   image:   pre-flood RGB = channels 0..2 of `input` (interior of a possibly haloed buffer)
+ *   image:   pre-flood RGB = channels 0..2 of `input` (interior of a possibly haloed buffer); input_lo_offset > 0
+ *            (fp32 parity mode): plus channels input_lo_offset + 0..2, the low bf16 halves of the image
  *   out = sum_k content_k * a_k + image * a_10, written as bf16 into `out` channels [out_c0, out_c0+3)
  *   and as fp32 NCHW into out_nchw (may be NULL); mask_nhw (fp32 [n][h][w], may be NULL) gets a_10.
  * ---------------------------------------------------------------------------------------------------------- */
-int fpg_blend_fwd(const fpg_act* content, const fpg_act* logits, const fpg_act* input, const fpg_act* out,
-                  int32_t out_c0, float* out_nchw, float* mask_nhw, void* stream);
+int fpg_blend_fwd(const fpg_act* content, const fpg_act* logits, const fpg_act* input, int32_t input_lo_offset,
+                  const fpg_act* out, int32_t out_c0, float* out_nchw, float* mask_nhw, void* stream);
 /* upstream gradient = dout_nchw (fp32 [n][3][h][w], may be NULL) + dout_nhwc channels [dout_c0, dout_c0+3)
  * (bf16, may be NULL) -> dcontent (pre-tanh gradient, bf16 32 ch), dlogits (bf16 16 ch) and, if not NULL,
  * dimage_nchw = gradient w.r.t. the pre-flood RGB (fp32 [n][3][h][w]; needed by the cycle models). */
@@ -458,6 +459,21 @@ int fpg_mse_const_loss(const fpg_act* logits, float target, float weight, float 
 int fpg_l1_loss(const float* pred, const float* target, int64_t count, int64_t per_image,
                 int64_t target_image_stride, float weight, float grad_scale, float* loss,
                 float* dpred, int accumulate, float* scratch /* >= 512 floats */, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * fp32 parity mode (north_star: "fp32 rtol 1e-4"): every tensor-core operand is a pair of bf16 tensors hi + lo and a
+ * convolution is hi_x*hi_w + lo_x*hi_w + hi_x*lo_w in ONE launch of the ordinary conv kernels -- activations hold the
+ * channel blocks [hi | lo | hi] (3 * C channels), packed weights [hi_w | hi_w | lo_w] along the contraction dimension,
+ * outputs stay fp32 (fpg_act.fp32 = FPG_DT_FP32). The two helpers below are the elementwise glue of that mode.
+ * ---------------------------------------------------------------------------------------------------------- */
+/* v = act(norm ? InstanceNorm(y) : y) [+ residual]; y: halo-free fp32 [n][h][w][c]; residual / skip_out (may be NULL):
+ * dense fp32 [n][h][w][c]; out: bf16, 3 * c channels = [hi(v) | lo(v) | hi(v)], reflect halo out->halo mirrored.
+ * (nn.InstanceNorm2d + relu / LeakyReLU / F.pad(reflect) / residual add of model_architectures.py:313-333,408-418.) */
+int fpg_norm_split_f32(const fpg_act* y, int norm, float eps, int act, const float* residual, float* skip_out,
+                       const fpg_act* out, void* stream);
+/* src fp32 NCHW [n][c_src][h][w] -> dst bf16 [n][h+2halo][w+2halo][3 * cpad] = [hi | lo | hi], reflect halo, channels
+ * >= c_src zero */
+int fpg_pack_nchw_split(const float* src, int32_t c_src, const fpg_act* dst, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Layout / packing helpers around the network boundary (model.py:613-617: .to(device), torch.cat).

@@ -19,6 +19,7 @@ import sys
 
 import pytest
 import torch
+import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -249,6 +250,36 @@ def test_model_train_paired_api_and_checkpoint_roundtrip(tmp_path):
     assert m2.starting_epoch == 2
     for k, v in m.generator.state_dict().items():
         assert torch.equal(v, m2.generator.state_dict()[k])
+
+
+@pytest.mark.parametrize("size,batch", [(64, 2), (256, 1)])
+def test_fp32_parity_mode_matches_reference_to_1e4(size, batch):
+    """north_star: "fp32 rtol 1e-4". The 3 x bf16-split mode (fpgan/fp32mode.py: every conv = hi*hi + lo*hi + hi*lo on
+    the tcgen05 kernels, everything else fp32) against the oracle's fp32 CPU graph on identical inputs and weights:
+    generator output, attention mask, PatchGAN logits and the four losses of the step."""
+    from fpgan import fp32mode
+    O, nets, G, D = make_pair()
+    x, y = O.synthetic_batch(0, batch, 9, size)
+    with torch.no_grad():
+        out_ref, mask_ref = O.attention_generator_forward(nets["generator"], x, return_mask=True)
+        lg_syn = O.patchgan_forward(nets["discriminator"], torch.cat((x, out_ref), 1))
+        lg_real = O.patchgan_forward(nets["discriminator"], torch.cat((x, y), 1))
+        ref = {"losses_discriminator_real": F.mse_loss(lg_real, torch.ones_like(lg_real)).item(),
+               "losses_discriminator_synthetic": F.mse_loss(lg_syn, torch.zeros_like(lg_syn)).item(),
+               "losses_generator_synthetic": F.mse_loss(lg_syn, torch.ones_like(lg_syn)).item(),
+               "l1_losses_generator_synthetic": 100 * F.l1_loss(out_ref, y).item()}
+    sg = fp32mode.SplitAttentionGenerator(G)
+    out, mask = sg.forward(x.cuda())
+    e_out, e_mask = rel_rms(out, out_ref), rel_rms(mask, mask_ref)
+    worst = ((out.cpu() - out_ref).abs() / (out_ref.abs() + out_ref.abs().mean())).max().item()
+    synth, got, logits = fp32mode.paired_forward_losses(G, D, x.cuda(), y.cuda())
+    e_log = rel_rms(logits.to_nchw(1), lg_syn)
+    print(f"\n[parity fp32 mode] {size}x{size} B={batch}: output rel-rms {e_out:.2e} (worst element {worst:.2e}), "
+          f"mask {e_mask:.2e}, logits {e_log:.2e}; losses " + ", ".join(f"{got[k]:.6f}/{ref[k]:.6f}" for k in ref))
+    assert e_out < 1e-4 and e_mask < 1e-4 and e_log < 1e-4, (e_out, e_mask, e_log)
+    assert worst < 1e-3
+    for k in ref:
+        assert abs(got[k] - ref[k]) <= 1e-4 * abs(ref[k]), f"{k}: {got[k]} vs {ref[k]}"
 
 
 def test_cyclegan_generator_forward_backward_matches_oracle():
