@@ -219,10 +219,11 @@ class PairedTrainer:
         ops.LAUNCHES = before  # capturing records the launches, it does not run them
         return sx, sy, graph, out, launches
 
-    def _step_impl(self, input_stack, output_image):
+    def _phase_d(self, input_stack, output_image):
+        """generator forward + discriminator forward / backward on [synthetic | real] (:615-632): leaves the
+        discriminator gradients of this batch in self.dp.grads and returns what the generator phase needs"""
         G, D = self.G, self.D
         B, C, H, W = input_stack.shape
-        inv_w = 1.0 / self.world_size
         # D input for [synthetic | real] halves: channels 0..C-1 = input stack, C..C+2 = image (model.py:616-617)
         din = ActBuf(2 * B, H, W, 16, zero=False)
         fake, real = din.batch_slice(0, B), din.batch_slice(B, B)
@@ -237,28 +238,71 @@ class PairedTrainer:
         ops.mse_const_loss(logits.batch_slice(0, B), 0.0, 1.0, 0.5, self.loss_buf[1:2], dlog.batch_slice(0, B))
         ops.mse_const_loss(logits.batch_slice(B, B), 1.0, 1.0, 0.5, self.loss_buf[0:1], dlog.batch_slice(B, B))
         D.backward(dtape, dlog, self.dp.grads, need_dx=False)
-        if self.world_size > 1:
-            dist.all_reduce(self.dp.grads.flat, group=self.group)
-        self.dp.adam(grad_scale=inv_w)
-        self._force_repack(D)
+        return synthetic, gtape, fake, output_image, C
 
-        # ---- generator update (:636-646): adversarial term through the UPDATED discriminator
+    def _phase_g(self, state, reducer=None):
+        """generator update terms (:636-645) through the UPDATED discriminator: leaves the generator gradients of
+        this batch in self.gp.grads"""
+        G, D = self.G, self.D
+        synthetic, gtape, fake, output_image, C = state
+        B = synthetic.shape[0]
         logits_g, dtape_g = D.forward_buf(fake)
         dlog_g = ActBuf(B, logits_g.h, logits_g.w, 16, zero=False)
         ops.mse_const_loss(logits_g, 1.0, 1.0, 1.0, self.loss_buf[2:3], dlog_g)
         d_din = D.backward(dtape_g, dlog_g, None, need_dx=True)
         dl1 = torch.empty_like(synthetic)
         ops.l1_loss(synthetic, output_image, self.l1_weight, 1.0, self.loss_buf[3:4], dpred=dl1)
-        if self.g_reducer is not None:
-            self.g_reducer.start()
-            G.grad_ready = self.g_reducer.ready
+        if reducer is not None:
+            reducer.start()
+            G.grad_ready = reducer.ready
         G.backward(gtape, self.gp.grads, dout_nchw=dl1, dout_nhwc=d_din, dout_c0=C, need_dx=False)
-        if self.g_reducer is not None:
+        if reducer is not None:
             G.grad_ready = None
-            self.g_reducer.finish()
+            reducer.finish()
+
+    def _step_impl(self, input_stack, output_image):
+        inv_w = 1.0 / self.world_size
+        state = self._phase_d(input_stack, output_image)
+        if self.world_size > 1:
+            dist.all_reduce(self.dp.grads.flat, group=self.group)
+        self.dp.adam(grad_scale=inv_w)
+        self._force_repack(self.D)
+        self._phase_g(state, self.g_reducer)
         self.gp.adam(grad_scale=inv_w)
-        self._force_repack(G)
-        return synthetic
+        self._force_repack(self.G)
+        return state[0]
+
+    def step_accumulated(self, shards, lr_g=0.0002, lr_d=0.0002):
+        """One optimiser step over several micro-batches [(input_stack, output_image), ...] with the gradients summed
+        in shard order and averaged -- what W data-parallel ranks compute together, in ONE process and with the very
+        same kernels per shard (plans depend on the per-process batch). The data-parallel parity check compares the
+        NCCL run against this; it is also plain gradient accumulation for batches that do not fit. Eager (no graph).
+        Returns the per-shard generated images; loss_buf holds the shard-averaged losses."""
+        assert self.world_size == 1, "step_accumulated emulates the ranks in a single process"
+        self.gp.set_lr(lr_g)
+        self.dp.set_lr(lr_d)
+        n = len(shards)
+        states, loss_sum = [], torch.zeros_like(self.loss_buf)
+        dsum = torch.zeros_like(self.dp.grads.flat)
+        for x, y in shards:
+            states.append(self._phase_d(x, y))
+            ops.add_f32(dsum, self.dp.grads.flat)
+            loss_sum[0:2] += self.loss_buf[0:2]
+        self.dp.grads.flat.copy_(dsum)
+        self.dp.adam(grad_scale=1.0 / n)
+        self._force_repack(self.D)
+        gsum = torch.zeros_like(self.gp.grads.flat)
+        for st in states:
+            self._phase_g(st)
+            ops.add_f32(gsum, self.gp.grads.flat)
+            loss_sum[2:4] += self.loss_buf[2:4]
+        self.gp.grads.flat.copy_(gsum)
+        self.gp.adam(grad_scale=1.0 / n)
+        self._force_repack(self.G)
+        self.loss_buf.copy_(loss_sum / n)
+        self.gp.note_step()
+        self.dp.note_step()
+        return [st[0] for st in states]
 
     def losses(self):
         """Host copy of the last step's losses (one device->host sync), averaged over ranks."""
@@ -387,10 +431,63 @@ class CycleTrainer:
         return sx, sy, graph, out, launches
 
     def _step_impl(self, x_pre, y_post):
+        inv_w = 1.0 / self.world_size
+        state = self._phase_g(x_pre, y_post)
+        if self.world_size > 1:
+            dist.all_reduce(self.gp.grads.flat, group=self.group)
+        self.gp.adam(grad_scale=inv_w)
+        self.Gpp.repack(force=True)
+        self.Gpr.repack(force=True)
+        self._phase_d(state)
+        if self.world_size > 1:
+            dist.all_reduce(self.dp.grads.flat, group=self.group)
+        self.dp.adam(grad_scale=inv_w)
+        self.Dpre.repack(force=True)
+        self.Dpost.repack(force=True)
+        return state[0], state[1]
+
+    def step_accumulated(self, shards, lr_g=0.0002, lr_d=0.0002):
+        """As PairedTrainer.step_accumulated: one optimiser step over several micro-batches, gradients summed in shard
+        order -- what W data-parallel ranks compute together, in one process with the same per-shard kernels. Meant
+        for the first 50 steps, while the history buffers return the current images (every rank has its own buffer)."""
+        assert self.world_size == 1
+        self.gp.set_lr(lr_g)
+        self.dp.set_lr(lr_d)
+        ctrl = list(self.hist_pre.decide()) + list(self.hist_post.decide())
+        assert ctrl[0] < 0 and ctrl[2] < 0, "step_accumulated: the history buffers are past their fill phase"
+        self.hist_ctrl.copy_(torch.tensor([-1, -1, -1, -1], dtype=torch.int32))  # nothing stored: one pool, many shards
+        n = len(shards)
+        states, loss_sum = [], torch.zeros_like(self.loss_buf)
+        gsum = torch.zeros_like(self.gp.grads.flat)
+        g_keys = [0, 1, 2, 3] + ([8, 9] if self.identity else [])
+        for x, y in shards:
+            states.append(self._phase_g(x, y))
+            ops.add_f32(gsum, self.gp.grads.flat)
+            loss_sum[g_keys] += self.loss_buf[g_keys]
+        self.gp.grads.flat.copy_(gsum)
+        self.gp.adam(grad_scale=1.0 / n)
+        self.Gpp.repack(force=True)
+        self.Gpr.repack(force=True)
+        dsum = torch.zeros_like(self.dp.grads.flat)
+        for st in states:
+            self._phase_d(st)
+            ops.add_f32(dsum, self.dp.grads.flat)
+            loss_sum[4:8] += self.loss_buf[4:8]
+        self.dp.grads.flat.copy_(dsum)
+        self.dp.adam(grad_scale=1.0 / n)
+        self.Dpre.repack(force=True)
+        self.Dpost.repack(force=True)
+        self.loss_buf.copy_(loss_sum / n)
+        self.gp.note_step()
+        self.dp.note_step()
+        return [(st[0], st[1]) for st in states]
+
+    def _phase_g(self, x_pre, y_post):
+        """the generator passes and the generator update terms (:680-713): leaves the summed generator gradients of
+        this batch in self.gp.grads and returns what the discriminator phase needs"""
         Gpp, Gpr, Dpost, Dpre = self.Gpp, self.Gpr, self.Dpost, self.Dpre
         B, C, H, W = x_pre.shape
         n_cond = C - 3
-        inv_w = 1.0 / self.world_size
         lb = self.loss_buf
         gpp0, gpr0 = self.gp.grads_of
         (gflat1, (gpp1, gpr1)) = self.g_extra[0]
@@ -472,13 +569,16 @@ class CycleTrainer:
         ops.add_f32(self.gp.grads.flat, gflat1)
         if self.identity:
             ops.add_f32(self.gp.grads.flat, gflat2)
-        if self.world_size > 1:
-            dist.all_reduce(self.gp.grads.flat, group=self.group)
-        self.gp.adam(grad_scale=inv_w)
-        Gpp.repack(force=True)
-        Gpr.repack(force=True)
+        return synth_post, synth_pre, fake_pre, fake_post, din_pre, din_post
 
-        # ---- discriminator update (:716-735): real images vs images from the history buffers
+    def _phase_d(self, state):
+        """discriminator update terms (:716-735): real images vs images from the history buffers; leaves the
+        discriminator gradients of this batch in self.dp.grads"""
+        Dpost, Dpre = self.Dpost, self.Dpre
+        _, _, fake_pre, fake_post, din_pre, din_post = state
+        B = fake_pre.n
+        lb = self.loss_buf
+        dpost_g, dpre_g = self.dp.grads_of
         ops.history_exchange(fake_pre.t, self._pool("pre", fake_pre), self.hist_ctrl[0:2], din_pre.t[B:])
         ops.history_exchange(fake_post.t, self._pool("post", fake_post), self.hist_ctrl[2:4], din_post.t[B:])
         for D, din, grads, k_real, k_syn in ((Dpre, din_pre, dpre_g, 4, 6), (Dpost, din_post, dpost_g, 5, 7)):
@@ -487,12 +587,6 @@ class CycleTrainer:
             ops.mse_const_loss(logits.batch_slice(0, B), 1.0, 1.0, 0.5, lb[k_real:k_real + 1], dlog.batch_slice(0, B))
             ops.mse_const_loss(logits.batch_slice(B, B), 0.0, 1.0, 0.5, lb[k_syn:k_syn + 1], dlog.batch_slice(B, B))
             D.backward(tape, dlog, grads, need_dx=False)
-        if self.world_size > 1:
-            dist.all_reduce(self.dp.grads.flat, group=self.group)
-        self.dp.adam(grad_scale=inv_w)
-        Dpre.repack(force=True)
-        Dpost.repack(force=True)
-        return synth_post, synth_pre
 
     def losses(self):
         """Host copy of the last step's losses (one device->host sync), averaged over ranks."""
