@@ -292,6 +292,49 @@ __device__ __forceinline__ float round_f16(float v) {
 __device__ __forceinline__ float round_16(float v, int dt) {
   return dt == 2 ? round_f16(v) : __bfloat162float(__float2bfloat16(v));
 }
+// 32-byte global store (STG.256, sm_100): one full sector per lane. The epilogues store one pixel row per thread, so a
+// warp's store touches 32 different lines; with 16-byte stores every sector was written in two half-filled pieces (ncu:
+// "16 of the 32 bytes per sector utilized", L1/TEX the busiest unit of the short-K kernels).
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+// 16 fp32 values -> 32 bytes of bf16 or fp16 at dst (32-byte aligned: channel offsets are multiples of 16 elements)
+__device__ __forceinline__ void store_16x16(void* dst_, const float (&f)[16], int dt) {
+  uint32_t w[8];
+  if (dt == 2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = pack_f16x2(f[2 * i], f[2 * i + 1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+  }
+  if ((reinterpret_cast<uintptr_t>(dst_) & 31) == 0) {
+    st_global_256(dst_, w);
+  } else {
+    uint4* dst = reinterpret_cast<uint4*>(dst_);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+// 16 fp32 values -> 64 bytes of fp32 at dst
+__device__ __forceinline__ void store_16x32(float* dst, const float (&f)[16]) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+    uint32_t w[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = __float_as_uint(f[8 * h + i]);
+      st_global_256(dst + 8 * h, w);
+    }
+  } else {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -1041,11 +1041,34 @@ int fpg_conv2d_dgrad(const fpg_act* dy, const void* w_packed_t, const float* bia
   if (rc != 1) return rc;
   rc = plan_dgrad(dy, w_packed_t, bias, act, g, dx, sms, d, &n);
   if (rc) return rc;
+  rc = fpg_igemm_s2cls_launch(d, n, stream);  // the four parity classes of a stride-2 layer in one launch
+  if (rc != 1) return rc;
   for (int q = 0; q < n; ++q) {
     rc = fpg_igemm_fprop_launch(&d[q], stream);
     if (rc) return rc;
   }
   return 0;
+}
+
+int32_t fpg_conv2d_dgrad_launches(const fpg_act* dy, const fpg_conv_geom* g, const fpg_act* dx) {
+  const int sms = sm_count_cached() > 0 ? sm_count_cached() : 148;
+  fpg_igemm_rows_desc rd;
+  if (plan_rows(dy, nullptr, nullptr, 0, g, dx, 1, sms, &rd) == 0) return 1;
+  fpg_igemm_fprop_desc d[4];
+  int n = 0;
+  if (plan_dgrad(dy, nullptr, nullptr, 0, g, dx, sms, d, &n)) return -1;
+  if (n == 4 && getenv("FPG_DISABLE_S2CLS") == nullptr) {
+    // the eligibility test of fpg_igemm_s2cls_launch, without launching
+    int slots = 0;
+    bool ok = true;
+    for (int q = 0; q < 4; ++q) {
+      ok = ok && d[q].cblk == 64 && !d[q].cta_pair && d[q].n_blocks == 1 && d[q].block_n <= 64 && d[q].num_taps <= 4 &&
+           d[q].tiles_x1 == 0 && d[q].tile_w == d[0].tile_w && d[q].tile_h == d[0].tile_h;
+      slots += d[q].num_taps * (d[q].c_per_tap / 64);
+    }
+    if (ok && static_cast<size_t>(slots) * d[0].block_n * 128 + 2 * 16384 + 2048 <= 227 * 1024) return 1;
+  }
+  return n;
 }
 
 int fpg_conv2d_rows_plan(const fpg_act* a, const void* w_packed, const float* bias, int act, const fpg_conv_geom* g,
@@ -1110,6 +1133,10 @@ int fpg_conv2d_dgrad_stats(const fpg_act* dy, const void* w_packed_t, const floa
     d[q].stat_rows_per_img = rows;
     d[q].stat_row0 = row0;
     row0 += stats_rows_of(&d[q]);
+  }
+  rc = fpg_igemm_s2cls_launch(d, n, stream);
+  if (rc != 1) return rc;
+  for (int q = 0; q < n; ++q) {
     rc = fpg_igemm_fprop_launch(&d[q], stream);
     if (rc) return rc;
   }

@@ -5,6 +5,8 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM owner + MMA issuer (one
 // elected lane), warps 2..5 = epilogue (TMEM -> registers -> global). One CTA per SM (TMEM: all 512 columns).
+#include <string.h>
+
 #include "common.cuh"
 #include "host_util.h"
 
@@ -150,21 +152,6 @@ __device__ __forceinline__ void unpack_16x8(const uint4& u, float* f, int dt) {
     f[2 * i + 1] = v.y;
   }
 }
-// 16 fp32 values -> 32 bytes of bf16 or fp16 at dst
-__device__ __forceinline__ void store_16x16(void* dst_, const float (&f)[16], int dt) {
-  uint4* dst = reinterpret_cast<uint4*>(dst_);
-  if (dt == 2) {
-    dst[0] = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
-    dst[1] = make_uint4(pack_f16x2(f[8], f[9]), pack_f16x2(f[10], f[11]), pack_f16x2(f[12], f[13]),
-                        pack_f16x2(f[14], f[15]));
-  } else {
-    dst[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                        pack_bf16x2(f[6], f[7]));
-    dst[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                        pack_bf16x2(f[14], f[15]));
-  }
-}
-
 // InstanceNorm-backward variant of stat_accumulate (see InBwdStat): fr = the 16 values as stored (bf16-rounded, 0 for
 // masked rows), z / zp = the forward input and, mode 2, the previous block's input at the same pixel and channels.
 __device__ __forceinline__ void inbwd_accumulate(const StatOut& so, const float (&fr)[16], const float (&z)[16],
@@ -491,9 +478,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
           }
           if (valid) {
             if (args.out.fp32 == FPG_DT_FP32) {
-              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out.base) + off + c);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+              store_16x32(static_cast<float*>(args.out.base) + off + c, f);
             } else {
               store_16x16(static_cast<__nv_bfloat16*>(args.out.base) + off + c, f, args.out.fp32);
             }
@@ -725,9 +710,7 @@ igemm_fprop2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
           stat_accumulate(args.stat, f, valid, lane, prow, nb * BN + c, args.out.fp32);
         if (valid) {
           if (args.out.fp32 == FPG_DT_FP32) {
-            float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out.base) + off + c);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            store_16x32(static_cast<float*>(args.out.base) + off + c, f);
           } else {
             store_16x16(static_cast<__nv_bfloat16*>(args.out.base) + off + c, f, args.out.fp32);
           }
@@ -741,6 +724,209 @@ igemm_fprop2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) tmem_dealloc_2cta(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------ stride-2 classes
+// All FOUR output-parity classes of a stride-2 data gradient / transposed-convolution forward in ONE launch.
+//   out[n, 2i + pi, 2j + pj, c] = sum over the taps (r, s) of class (pi, pj), over k:  dy[n, i + ty, j + tx, k] * W[k, c, r, s]
+// Launched class by class (igemm_fprop_kernel, one launch per class) these layers run at the speed of the L2 -> SM
+// path, not of the tensor cores: K = taps * c_out is short (1-4 taps), so per 128-pixel tile a class moves 24 KB of
+// operands per 64-wide K step for 128 x N x 64 MACs, the activation tile is fetched once per tap (9 times over the
+// four classes of a 3x3 filter) and the weight tile once per tile (ncu: 8 TB/s of L2 -> SM traffic, tensor pipe 19-28 %
+// active, profiles/r02). Here a CTA keeps EVERY tap's weights resident in shared memory for its lifetime and walks the
+// distinct input shifts (ty, tx) -- four for a 3x3 filter -- loading each shifted activation tile once and issuing
+// the MMAs of every class that has a tap with that shift into that class's accumulator (4 x N <= 256 TMEM columns,
+// two accumulator stages). 3.4x less operand traffic for the 3x3 layers.
+constexpr int kS2MaxShifts = 9;
+struct S2Args {
+  int32_t n_img, tiles_y, tiles_x, tile_w_log2, tile_h, tile_w;  // tiling of the class grid (= the dy pixel grid)
+  int32_t block_n;   // N = c_in <= 64
+  int32_t kchunks;   // c_out / 64
+  int32_t stages;    // activation ring
+  int32_t n_shifts;
+  int32_t cls_taps[4];      // taps of each class
+  int32_t cls_slot0[4];     // first resident weight slot of each class (slot = one tap x one 64-wide K chunk)
+  struct Shift {
+    int16_t ty, tx;
+    int16_t n_users, pad;
+    struct { int16_t cls, slot; } u[4];  // slot: resident slot of (class, tap) at K chunk 0
+  } shift[kS2MaxShifts];
+  int32_t off_y[4], off_x[4];  // output parity of each class
+  int32_t stat_row0[4];
+  fpg_out_view out;            // mul 2, offsets per class above
+  StatOut stat;
+};
+
+__global__ void __launch_bounds__(kFpropThreads, 1)
+igemm_s2cls_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap0,
+                   const __grid_constant__ CUtensorMap bmap1, const __grid_constant__ CUtensorMap bmap2,
+                   const __grid_constant__ CUtensorMap bmap3, const __grid_constant__ S2Args args) {
+  constexpr uint32_t LAYOUT = swizzle_layout_type(128);
+  constexpr uint32_t SBO = 8u * 128u;
+  constexpr uint32_t A_STAGE_BYTES = 128u * 64u * 2u;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int BN = args.block_n;
+  const uint32_t SLOT_BYTES = static_cast<uint32_t>(BN) * 128u;
+  const int STAGES = args.stages;
+  int n_slots = 0;
+  for (int q = 0; q < 4; ++q) n_slots += args.cls_taps[q] * args.kchunks;
+  uint8_t* smem_b = smem;                                   // resident weights
+  uint8_t* smem_a = smem + ((n_slots * SLOT_BYTES + 1023u) & ~1023u);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_a + STAGES * A_STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tfull = empty + STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 32 * kEpiWarps);
+    }
+    mbar_init(bfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&amap);
+    tma_prefetch_desc(&bmap0);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = args.n_img * args.tiles_y * args.tiles_x;
+  const int KC = args.kchunks;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // every tap's weights, once: slot (class q, tap t, K chunk kc) <- columns [(t * KC + kc) * 64, +64) of class q's matrix
+      mbar_arrive_expect_tx(bfull, static_cast<uint32_t>(n_slots) * SLOT_BYTES);
+      const CUtensorMap* bm[4] = {&bmap0, &bmap1, &bmap2, &bmap3};
+      for (int q = 0; q < 4; ++q)
+        for (int t = 0; t < args.cls_taps[q]; ++t)
+          for (int kc = 0; kc < KC; ++kc)
+            tma_load_2d(bm[q], bfull, smem_b + (args.cls_slot0[q] + t * KC + kc) * SLOT_BYTES, (t * KC + kc) * 64, 0);
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int tx = r % args.tiles_x;
+        r /= args.tiles_x;
+        const int ty = r % args.tiles_y;
+        const int n = r / args.tiles_y;
+        const int x0 = tx * args.tile_w, y0 = ty * args.tile_h;
+        for (int si = 0; si < args.n_shifts; ++si) {
+          const int sx = args.shift[si].tx, sy = args.shift[si].ty;
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES);
+            tma_load_5d(&amap, &full[stage], smem_a + stage * A_STAGE_BYTES, kc * 64, x0 + sx, 0, y0 + sy, n);
+            if (++stage == static_cast<uint32_t>(STAGES)) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      mbar_wait(bfull, 0);
+      tc_fence_after();
+      const uint32_t b_base = smem_u32(smem_b);
+      uint32_t stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const uint32_t as = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * 256;
+        uint32_t started = 0;  // classes whose accumulator has received its first MMA of this tile
+        for (int si = 0; si < args.n_shifts; ++si) {
+          const int nu = args.shift[si].n_users;
+          for (int kc = 0; kc < KC; ++kc) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
+            for (int u = 0; u < nu; ++u) {
+              const int cls = args.shift[si].u[u].cls;
+              const uint32_t b_addr = b_base + (args.shift[si].u[u].slot + kc) * SLOT_BYTES;
+              const uint32_t first = (kc == 0 && !((started >> cls) & 1u)) ? 1u : 0u;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t ad = make_smem_desc(a_addr + k * 32, 0, SBO, LAYOUT);
+                const uint64_t bd = make_smem_desc(b_addr + k * 32, 0, SBO, LAYOUT);
+                umma_bf16(d_tmem + cls * BN, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
+              }
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == static_cast<uint32_t>(STAGES)) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          for (int u = 0; u < nu; ++u) started |= 1u << args.shift[si].u[u].cls;
+        }
+        umma_commit(&tfull[as]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int cls0 = (warp - 2) < 4 ? 0 : 2;  // two classes per column half of the epilogue warps
+    const int row = q * 32 + lane;
+    const int ry = row >> args.tile_w_log2;
+    const int rx = row & (args.tile_w - 1);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const uint32_t as = it & 1, aph = (it >> 1) & 1;
+      int r = tile;
+      const int tx = r % args.tiles_x;
+      r /= args.tiles_x;
+      const int ty = r % args.tiles_y;
+      const int n = r / args.tiles_y;
+      const int py = ty * args.tile_h + ry, px = tx * args.tile_w + rx;
+      const bool valid = (py < args.out.valid_h) && (px < args.out.valid_w);
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      for (int cls = cls0; cls < cls0 + 2; ++cls) {
+        const int64_t off = static_cast<int64_t>(n) * args.out.stride_n +
+                            static_cast<int64_t>(py * 2 + args.off_y[cls]) * args.out.stride_y +
+                            static_cast<int64_t>(px * 2 + args.off_x[cls]) * args.out.stride_x;
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256 + cls * BN;
+        const int64_t prow = static_cast<int64_t>(n) * args.stat.rows_per_img + args.stat_row0[cls] +
+                             (ty * args.tiles_x + tx) * 4 + q;
+        for (int c = 0; c < BN; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_addr + c, v);
+          tmem_ld_wait();
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (args.stat.partial != nullptr) stat_accumulate(args.stat, f, valid, lane, prow, c, args.out.fp32);
+          if (valid) {
+            if (args.out.fp32 == FPG_DT_FP32) {
+              store_16x32(static_cast<float*>(args.out.base) + off + c, f);
+            } else {
+              store_16x16(static_cast<__nv_bfloat16*>(args.out.base) + off + c, f, args.out.fp32);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad
@@ -1358,6 +1544,99 @@ extern "C" int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* strea
     FPG_LAUNCH_FPROP(16, false, kFpropThreads);
   }
 #undef FPG_LAUNCH_FPROP
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// The four parity-class launches of a stride-2 data gradient as ONE launch of igemm_s2cls_kernel. Returns 1 when the
+// class plans do not qualify (the caller then launches them one by one): 1-CTA plans with one 64-channel chunk per K
+// step, N = c_in <= 64 in one block, the same tiling for every class, no bias / activation, and all tap weights
+// (taps x c_out x N bf16) fitting in shared memory beside at least two activation stages.
+extern "C" int fpg_igemm_s2cls_launch(const fpg_igemm_fprop_desc* d, int32_t n_cls, void* stream) {
+  FPG_REQUIRE(d != nullptr, "null descriptor");
+  static const bool disabled = getenv("FPG_DISABLE_S2CLS") != nullptr;
+  if (disabled || n_cls != 4) return 1;
+  int n_slots = 0;
+  for (int q = 0; q < 4; ++q) {
+    const fpg_igemm_fprop_desc& c = d[q];
+    if (c.cblk != 64 || c.cta_pair || c.n_blocks != 1 || c.block_n > 64 || c.block_n % 16 != 0 ||
+        c.tile_h * c.tile_w != 128 || c.tiles_x1 > 0 || c.bias != nullptr || c.act != FPG_ACT_NONE ||
+        c.inbwd_mode != 0 || c.c_per_tap % 64 != 0 || c.num_taps < 1 || c.num_taps > 4 ||
+        c.out.mul_y != 2 || c.out.mul_x != 2)
+      return 1;
+    if (c.tile_h != d[0].tile_h || c.tile_w != d[0].tile_w || c.tiles_x != d[0].tiles_x ||
+        c.tiles_y != d[0].tiles_y || c.block_n != d[0].block_n || c.c_per_tap != d[0].c_per_tap ||
+        c.n_img != d[0].n_img || c.out.base != d[0].out.base || c.a.base != d[0].a.base ||
+        c.stat_partial != d[0].stat_partial || c.out.fp32 != d[0].out.fp32)
+      return 1;
+    n_slots += c.num_taps * (c.c_per_tap / 64);
+  }
+  const int BN = d[0].block_n;
+  const size_t resident = (static_cast<size_t>(n_slots) * BN * 128 + 1023) & ~size_t(1023);
+  const size_t budget = 227 * 1024 - 1024 - 256;
+  if (resident + 2 * 16384 > budget) return 1;
+  int stages = static_cast<int>((budget - resident) / 16384);
+  if (stages > 6) stages = 6;
+
+  S2Args args;
+  memset(&args, 0, sizeof(args));
+  args.n_img = d[0].n_img;
+  args.tiles_y = d[0].tiles_y;
+  args.tiles_x = d[0].tiles_x;
+  args.tile_w_log2 = log2_exact(d[0].tile_w);
+  args.tile_h = d[0].tile_h;
+  args.tile_w = d[0].tile_w;
+  FPG_REQUIRE(args.tile_w_log2 >= 0, "tile width %d", d[0].tile_w);
+  args.block_n = BN;
+  args.kchunks = d[0].c_per_tap / 64;
+  args.stages = stages;
+  int slot = 0;
+  for (int q = 0; q < 4; ++q) {
+    args.cls_taps[q] = d[q].num_taps;
+    args.cls_slot0[q] = slot;
+    for (int t = 0; t < d[q].num_taps; ++t) {
+      const fpg_tap& tp = d[q].taps[t];
+      FPG_REQUIRE(tp.c0 == 0 && tp.plane == 0, "class taps must address the stride-1 view of dy");
+      int si = 0;
+      while (si < args.n_shifts && (args.shift[si].ty != tp.dy || args.shift[si].tx != tp.dx)) ++si;
+      if (si == args.n_shifts) {
+        if (args.n_shifts == kS2MaxShifts) return 1;
+        args.shift[si].ty = static_cast<int16_t>(tp.dy);
+        args.shift[si].tx = static_cast<int16_t>(tp.dx);
+        ++args.n_shifts;
+      }
+      auto& sh = args.shift[si];
+      if (sh.n_users == 4) return 1;
+      sh.u[sh.n_users].cls = static_cast<int16_t>(q);
+      sh.u[sh.n_users].slot = static_cast<int16_t>(slot + t * args.kchunks);
+      ++sh.n_users;
+    }
+    slot += d[q].num_taps * args.kchunks;
+    args.off_y[q] = d[q].out.off_y;
+    args.off_x[q] = d[q].out.off_x;
+    args.stat_row0[q] = d[q].stat_row0;
+  }
+  args.out = d[0].out;
+  args.stat.partial = d[0].stat_partial;
+  args.stat.rows_per_img = d[0].stat_rows_per_img;
+  args.stat.row0 = 0;
+  args.stat.c_total = BN;
+  CUtensorMap amap, bmap[4];
+  int rc = encode_tmap(&d[0].a, &amap);
+  if (rc) return rc;
+  for (int q = 0; q < 4; ++q) {
+    rc = encode_tmap(&d[q].b, &bmap[q]);
+    if (rc) return rc;
+  }
+  const int sms = sm_count_cached();
+  if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
+  const int total_tiles = args.n_img * args.tiles_y * args.tiles_x;
+  const int grid = total_tiles < sms ? total_tiles : sms;
+  const size_t smem = resident + static_cast<size_t>(stages) * 16384 + (2 * stages + 5) * 8 + 16 + 1024;
+  FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_s2cls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+  FPG_CUDA_CHECK(launch_persistent(igemm_s2cls_kernel, dim3(grid), dim3(kFpropThreads), smem,
+                                   static_cast<cudaStream_t>(stream), amap, bmap[0], bmap[1], bmap[2], bmap[3], args));
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -264,16 +264,9 @@ igemm_rows_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constan
           }
           if (valid) {
             if (args.out.fp32 == FPG_DT_FP32) {
-              float4* dst = reinterpret_cast<float4*>(static_cast<float*>(args.out.base) + off + c);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) dst[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+              store_16x32(static_cast<float*>(args.out.base) + off + c, f);
             } else {
-              uint4* dst = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(args.out.base) + off + c);
-              const int dt = args.out.fp32;
-              dst[0] = make_uint4(pack_2x16(f[0], f[1], dt), pack_2x16(f[2], f[3], dt), pack_2x16(f[4], f[5], dt),
-                                  pack_2x16(f[6], f[7], dt));
-              dst[1] = make_uint4(pack_2x16(f[8], f[9], dt), pack_2x16(f[10], f[11], dt),
-                                  pack_2x16(f[12], f[13], dt), pack_2x16(f[14], f[15], dt));
+              store_16x16(static_cast<__nv_bfloat16*>(args.out.base) + off + c, f, args.out.fp32);
             }
           }
         }

@@ -100,6 +100,8 @@ SIGNATURES = {
     "fpg_conv2d_dgrad_plan": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), C.c_int, _P(FpropDesc),
                                         _P(C.c_int)]),
     "fpg_conv_stats_rows": (_i32, [_P(Act), _P(ConvGeom), _P(Act), C.c_int]),
+    "fpg_igemm_s2cls_launch": (C.c_int, [_P(FpropDesc), _i32, _vp]),
+    "fpg_conv2d_dgrad_launches": (_i32, [_P(Act), _P(ConvGeom), _P(Act)]),
     "fpg_conv2d_fprop_stats": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), _vp, _vp]),
     "fpg_conv2d_dgrad_stats": (C.c_int, [_P(Act), _vp, _vp, C.c_int, _P(ConvGeom), _P(Act), _vp, _vp]),
     "fpg_instnorm_stats_finalize": (C.c_int, [_vp, _i32, _i32, _i32, _i64, _f32, _vp, _vp]),

@@ -170,8 +170,22 @@ def conv_fprop(x, spec, y, bias=None, act=ACT_NONE):
          spec.gref(), y.ref(), _stream())
 
 
+_dgrad_launches = {}
+
+
+def dgrad_launches(dy, spec, dx):
+    """kernels one conv_dgrad launches for this geometry (the parity classes of a stride-2 layer run as one launch
+    where their plans qualify)"""
+    g = spec.g
+    key = (dy.n, dy.h, dy.w, dx.h, dx.w, dx.halo, g.r, g.s, g.stride, g.pad, g.c_in, g.c_out)
+    if key not in _dgrad_launches:
+        n = L.load().fpg_conv2d_dgrad_launches(dy.ref(), spec.gref(), dx.ref()) if g.stride == 2 else 1
+        _dgrad_launches[key] = max(1, n)
+    return _dgrad_launches[key]
+
+
 def conv_dgrad(dy, spec, dx, bias=None, act=ACT_NONE):
-    _run(_conv_key("dgrad", dx.n, dx.h, dx.w, spec), 4 if spec.g.stride == 2 else 1, "fpg_conv2d_dgrad", dy.ref(),
+    _run(_conv_key("dgrad", dx.n, dx.h, dx.w, spec), dgrad_launches(dy, spec, dx), "fpg_conv2d_dgrad", dy.ref(),
          _ptr(spec.w_dgrad), _ptr(bias), act, spec.gref(), dx.ref(), _stream())
 
 
@@ -198,7 +212,7 @@ def conv_with_stats(x, spec, y, stats, transposed=False, eps=1e-5, batch=False):
         return False
     ws = _stat_workspace(int(1.02 * y.n * rows * y.c * 2) + 4096, y.t.device)
     if transposed:
-        _run(_conv_key("dgrad", y.n, y.h, y.w, spec), 4 if spec.g.stride == 2 else 1, "fpg_conv2d_dgrad_stats", x.ref(),
+        _run(_conv_key("dgrad", y.n, y.h, y.w, spec), dgrad_launches(x, spec, y), "fpg_conv2d_dgrad_stats", x.ref(),
              _ptr(spec.w_dgrad), None, ACT_NONE, spec.gref(), y.ref(), _ptr(ws), _stream())
     else:
         _run(_conv_key("fprop", y.n, y.h, y.w, spec), 1, "fpg_conv2d_fprop_stats", x.ref(), _ptr(spec.w_fprop), None,

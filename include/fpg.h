@@ -179,6 +179,10 @@ typedef struct {
 int fpg_igemm_fprop_launch(const fpg_igemm_fprop_desc* d, void* stream);
 int fpg_igemm_wgrad_launch(const fpg_igemm_wgrad_desc* d, void* stream);
 int fpg_igemm_rows_launch(const fpg_igemm_rows_desc* d, void* stream);
+/* The n_cls == 4 output-parity class plans of a stride-2 data gradient / transposed-convolution forward
+ * (fpg_conv2d_dgrad_plan) as ONE launch: every tap's weights resident in shared memory, each shifted activation tile
+ * loaded once for all classes. Returns 0 (launched), 1 (plans do not qualify: launch them one by one) or an error. */
+int fpg_igemm_s2cls_launch(const fpg_igemm_fprop_desc* descs, int32_t n_cls, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Convolution family (replaces nn.Conv2d / nn.ConvTranspose2d forward and aten::convolution_backward;
@@ -229,6 +233,8 @@ int fpg_conv2d_dgrad(const fpg_act* dy, const void* w_packed_t, const float* bia
 int fpg_conv2d_dgrad_plan(const fpg_act* dy, const void* w_packed_t, const float* bias, int act,
                           const fpg_conv_geom* g, const fpg_act* dx, int sm_count, fpg_igemm_fprop_desc* out_descs,
                           int* n_descs);
+/* kernels fpg_conv2d_dgrad launches for this layer (1, or 4 when the parity classes run one by one) */
+int32_t fpg_conv2d_dgrad_launches(const fpg_act* dy, const fpg_conv_geom* g, const fpg_act* dx);
 
 /* Row-stationary plan of the same operation as fpg_conv2d_fprop (dgrad == 0: a = x, out = y) or fpg_conv2d_dgrad
  * (dgrad != 0: a = dy, out = dx, w_packed = the dgrad packing). Returns 0 and fills *out_desc when that path applies
