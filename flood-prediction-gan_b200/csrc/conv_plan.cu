@@ -890,36 +890,123 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, __nv_bfloat16
   }
 }
 
-// One launch for every packed operand of a network: block b works on elements [2048 * block_first[b], +2048) of job
-// block_job[b]. Jobs with dst_fp32 != 0 copy an fp32 vector (bias) into a zero-padded fp32 buffer.
+// One launch for every packed operand of a network. Block b works on tile block_first[b] of job block_job[b].
+// A weight job gathers dst[row][tap][col] (bf16) = src[row * stride_row + col * stride_col + src_tap[tap]] from the fp32
+// parameter [K][C][R*S]: one of (row, col) walks the parameter with stride R*S, the other with stride C*R*S, so per
+// element the old kernel fetched a 4-byte value out of a 36-byte neighbourhood that other threads of other blocks wanted
+// (116 us for the generator's 24 M packed values). Here a block takes a tile of kPackRows(rs) x 64 (row, col) pairs with
+// ALL their taps: it reads the tile as contiguous runs of the parameter into shared memory (the run direction is
+// whichever index has stride R*S) and writes every (row, tap) as a contiguous 128-byte run of the destination.
+// Jobs with dst_fp32 != 0 copy an fp32 vector (bias) into a zero-padded fp32 buffer, 2048 elements per block.
 constexpr int kPackChunk = 2048;
+constexpr int kPackCols = 64;
+constexpr int kPackUnroll = 8;
+constexpr int kPackSmemFloats = 11 * 1024;  // 44 KB (static shared memory: 48 KB with the job copy)
+__host__ __device__ inline int pack_rs(const fpg_pack_job& j) {
+  return static_cast<int>(j.src_stride_row < j.src_stride_col ? j.src_stride_row : j.src_stride_col);
+}
+__host__ __device__ inline int pack_tile_rows(int rs) {  // rows per tile such that rows|1 x 64 x (rs|1) floats fit
+  int r = kPackSmemFloats / (kPackCols * (rs | 1));
+  r = r > 33 ? 32 : r - 1;  // the shared-memory row pitch is (rows | 1)
+  return r < 1 ? 1 : r;
+}
+
 __global__ void __launch_bounds__(256)
 pack_batched_kernel(const fpg_pack_job* __restrict__ jobs, const int32_t* __restrict__ block_job,
                     const int32_t* __restrict__ block_first) {
   __shared__ fpg_pack_job job;
+  __shared__ float tile[kPackSmemFloats];
   {
     const int32_t* src = reinterpret_cast<const int32_t*>(jobs + block_job[blockIdx.x]);
     int32_t* dst = reinterpret_cast<int32_t*>(&job);
     for (int i = threadIdx.x; i < static_cast<int>(sizeof(fpg_pack_job) / 4); i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  const int64_t total = static_cast<int64_t>(job.rows) * job.taps * job.cols;
-  const int64_t begin = static_cast<int64_t>(block_first[blockIdx.x]) * kPackChunk;
+  if (job.dst_fp32) {
+    const int64_t total = static_cast<int64_t>(job.rows) * job.taps * job.cols;
+    const int64_t begin = static_cast<int64_t>(block_first[blockIdx.x]) * kPackChunk;
 #pragma unroll
-  for (int u = 0; u < kPackChunk / 256; ++u) {
-    const int64_t i = begin + u * 256 + threadIdx.x;
-    if (i >= total) break;
-    const int col = static_cast<int>(i % job.cols);
-    const int t = static_cast<int>((i / job.cols) % job.taps);
-    const int row = static_cast<int>(i / (static_cast<int64_t>(job.cols) * job.taps));
-    float v = 0.f;
-    const int st = job.src_tap[t];
-    if (st >= 0 && row < job.rows_valid && col < job.cols_valid)
-      v = job.src[row * job.src_stride_row + col * job.src_stride_col + st];
-    if (job.dst_fp32) {
+    for (int u = 0; u < kPackChunk / 256; ++u) {
+      const int64_t i = begin + u * 256 + threadIdx.x;
+      if (i >= total) break;
+      const int col = static_cast<int>(i % job.cols);
+      const int t = static_cast<int>((i / job.cols) % job.taps);
+      const int row = static_cast<int>(i / (static_cast<int64_t>(job.cols) * job.taps));
+      float v = 0.f;
+      const int st = job.src_tap[t];
+      if (st >= 0 && row < job.rows_valid && col < job.cols_valid)
+        v = job.src[row * job.src_stride_row + col * job.src_stride_col + st];
       static_cast<float*>(job.dst)[i] = v;
+    }
+    return;
+  }
+  const int rs = pack_rs(job), rsp = rs | 1;
+  const int TR = pack_tile_rows(rs), trp = TR | 1;
+  const int col_tiles = (job.cols + kPackCols - 1) / kPackCols;
+  const int tile_idx = block_first[blockIdx.x];
+  const int row0 = (tile_idx / col_tiles) * TR, col0 = (tile_idx % col_tiles) * kPackCols;
+  const int nr = min(TR, job.rows_valid - row0), nc = min(kPackCols, job.cols_valid - col0);  // valid part (may be <= 0)
+  const bool col_runs = job.src_stride_col < job.src_stride_row;  // consecutive cols are rs floats apart (fprop layout)
+  // ---- load: contiguous runs of the parameter (warp per run, lanes along it; e / rs by reciprocal: e < 64 * 49)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float inv_rs = 1.f / static_cast<float>(rs);
+  if (nr > 0 && nc > 0) {
+    if (col_runs) {
+      const int run = nc * rs;  // per tile row
+      for (int r = warp; r < nr; r += 8) {
+        const float* sp = job.src + (row0 + r) * job.src_stride_row + static_cast<int64_t>(col0) * rs;
+        for (int e0 = lane; e0 < run; e0 += 32 * kPackUnroll) {  // batches of independent loads (latency bound)
+          float v[kPackUnroll];
+#pragma unroll
+          for (int u = 0; u < kPackUnroll; ++u) v[u] = e0 + 32 * u < run ? __ldg(sp + e0 + 32 * u) : 0.f;
+#pragma unroll
+          for (int u = 0; u < kPackUnroll; ++u) {
+            const int e = e0 + 32 * u;
+            if (e < run) {
+              const int c = __float2int_rz((static_cast<float>(e) + 0.5f) * inv_rs), st = e - c * rs;
+              tile[(c * trp + r) * rsp + st] = v[u];
+            }
+          }
+        }
+      }
     } else {
-      static_cast<__nv_bfloat16*>(job.dst)[i] = __float2bfloat16(v);
+      const int run = nr * rs;  // per tile column
+      for (int c = warp; c < nc; c += 8) {
+        const float* sp = job.src + (col0 + c) * job.src_stride_col + static_cast<int64_t>(row0) * rs;
+        for (int e0 = lane; e0 < run; e0 += 32 * kPackUnroll) {
+          float v[kPackUnroll];
+#pragma unroll
+          for (int u = 0; u < kPackUnroll; ++u) v[u] = e0 + 32 * u < run ? __ldg(sp + e0 + 32 * u) : 0.f;
+#pragma unroll
+          for (int u = 0; u < kPackUnroll; ++u) {
+            const int e = e0 + 32 * u;
+            if (e < run) {
+              const int r = __float2int_rz((static_cast<float>(e) + 0.5f) * inv_rs), st = e - r * rs;
+              tile[(c * trp + r) * rsp + st] = v[u];
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- store: dst[row][tap][col], two columns (4 bytes) per thread, 32 lanes = one 128-byte run per (row, tap)
+  const int rows_here = min(TR, job.rows - row0), cols_here = min(kPackCols, job.cols - col0);  // cols are even
+  const int pairs = cols_here >> 1;
+  __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(job.dst);
+  for (int rt = warp; rt < rows_here * job.taps; rt += 8) {
+    const int r = rt / job.taps, t = rt - r * job.taps;
+    const int st = job.src_tap[t];
+    const bool live = st >= 0 && r < nr;
+    __nv_bfloat16* drow = dst + (static_cast<int64_t>(row0 + r) * job.taps + t) * job.cols + col0;
+    for (int cp = lane; cp < pairs; cp += 32) {
+      const int c = 2 * cp;
+      float v0 = 0.f, v1 = 0.f;
+      if (live) {
+        if (c < nc) v0 = tile[(c * trp + r) * rsp + st];
+        if (c + 1 < nc) v1 = tile[((c + 1) * trp + r) * rsp + st];
+      }
+      *reinterpret_cast<uint32_t*>(drow + c) = pack_bf16x2(v0, v1);
     }
   }
 }
@@ -1445,8 +1532,12 @@ int fpg_pack_job_copy_f32(const float* src, int32_t count_valid, float* dst, int
 }
 
 int32_t fpg_pack_job_blocks(const fpg_pack_job* job) {
-  const int64_t total = static_cast<int64_t>(job->rows) * job->taps * job->cols;
-  return static_cast<int32_t>((total + kPackChunk - 1) / kPackChunk);
+  if (job->dst_fp32) {
+    const int64_t total = static_cast<int64_t>(job->rows) * job->taps * job->cols;
+    return static_cast<int32_t>((total + kPackChunk - 1) / kPackChunk);
+  }
+  const int tr = pack_tile_rows(pack_rs(*job));
+  return ((job->rows + tr - 1) / tr) * ((job->cols + kPackCols - 1) / kPackCols);
 }
 
 int fpg_pack_weights_batched(const fpg_pack_job* jobs_dev, const int32_t* block_job_dev, const int32_t* block_first_dev,

@@ -738,6 +738,7 @@ igemm_fprop2_kernel(const __grid_constant__ CUtensorMap amap, const __grid_const
 // the MMAs of every class that has a tap with that shift into that class's accumulator (4 x N <= 256 TMEM columns,
 // two accumulator stages). 3.4x less operand traffic for the 3x3 layers.
 constexpr int kS2MaxShifts = 9;
+constexpr int kS2MaxOps = 4 * 4 * 8;  // (taps over the four classes) x K chunks: 16 taps x 8 chunks of 64 channels
 struct S2Args {
   int32_t n_img, tiles_y, tiles_x, tile_w_log2, tile_h, tile_w;  // tiling of the class grid (= the dy pixel grid)
   int32_t block_n;   // N = c_in <= 64
@@ -778,7 +779,9 @@ igemm_s2cls_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
   uint64_t* tfull = empty + STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* bfull = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  uint64_t* op_bdesc = bfull + 1;  // tabulated MMA groups: kS2MaxOps weight descriptors + info words
+  uint32_t* op_info = reinterpret_cast<uint32_t*>(op_bdesc + kS2MaxOps);
+  uint32_t* tmem_slot = op_info + kS2MaxOps;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -843,37 +846,55 @@ igemm_s2cls_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
       mbar_wait(bfull, 0);
       tc_fence_after();
       const uint32_t b_base = smem_u32(smem_b);
+      // The sequence of MMA groups is the same for every tile: it is tabulated once in shared memory (the single
+      // issuing thread is on the critical path; walking the shift / user tables in the kernel parameters per MMA cost
+      // more than the MMAs). Entry: weight descriptor, accumulator column, flags {first of its class, last of its stage}.
+      uint32_t n_ops = 0;
+      {
+        uint32_t started = 0;
+        for (int si = 0; si < args.n_shifts; ++si) {
+          const int nu = args.shift[si].n_users;
+          for (int kc = 0; kc < KC; ++kc)
+            for (int u = 0; u < nu; ++u, ++n_ops) {
+              const int cls = args.shift[si].u[u].cls;
+              op_bdesc[n_ops] = make_smem_desc(b_base + (args.shift[si].u[u].slot + kc) * SLOT_BYTES, 0, SBO, LAYOUT);
+              op_info[n_ops] = static_cast<uint32_t>(cls * BN) | ((kc == 0 && !((started >> cls) & 1u)) ? 1u << 16 : 0u) |
+                               (u == nu - 1 ? 1u << 17 : 0u);
+            }
+          for (int u = 0; u < nu; ++u) started |= 1u << args.shift[si].u[u].cls;
+        }
+      }
+      const uint64_t a_hi = make_smem_desc(0, 0, SBO, LAYOUT);  // descriptor without the start address
       uint32_t stage = 0, phase = 0, it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const uint32_t as = it & 1, aph = (it >> 1) & 1;
         mbar_wait(&tempty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * 256;
-        uint32_t started = 0;  // classes whose accumulator has received its first MMA of this tile
-        for (int si = 0; si < args.n_shifts; ++si) {
-          const int nu = args.shift[si].n_users;
-          for (int kc = 0; kc < KC; ++kc) {
+        bool need_stage = true;
+        uint64_t ad = 0;
+        for (uint32_t j = 0; j < n_ops; ++j) {
+          if (need_stage) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
-            for (int u = 0; u < nu; ++u) {
-              const int cls = args.shift[si].u[u].cls;
-              const uint32_t b_addr = b_base + (args.shift[si].u[u].slot + kc) * SLOT_BYTES;
-              const uint32_t first = (kc == 0 && !((started >> cls) & 1u)) ? 1u : 0u;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t ad = make_smem_desc(a_addr + k * 32, 0, SBO, LAYOUT);
-                const uint64_t bd = make_smem_desc(b_addr + k * 32, 0, SBO, LAYOUT);
-                umma_bf16(d_tmem + cls * BN, ad, bd, idesc, (first && k == 0) ? 0u : 1u);
-              }
-            }
+            ad = a_hi | static_cast<uint64_t>((smem_u32(smem_a + stage * A_STAGE_BYTES) >> 4) & 0x3FFFu);
+            need_stage = false;
+          }
+          const uint64_t bd = op_bdesc[j];
+          const uint32_t info = op_info[j];
+          const uint32_t d_col = d_tmem + (info & 0xFFFFu);
+          umma_bf16(d_col, ad, bd, idesc, (info >> 16) & 1u ? 0u : 1u);
+          umma_bf16(d_col, ad + 2, bd + 2, idesc, 1u);  // + 32 bytes = + 2 in the 16-byte address field
+          umma_bf16(d_col, ad + 4, bd + 4, idesc, 1u);
+          umma_bf16(d_col, ad + 6, bd + 6, idesc, 1u);
+          if ((info >> 17) & 1u) {
             umma_commit(&empty[stage]);
             if (++stage == static_cast<uint32_t>(STAGES)) {
               stage = 0;
               phase ^= 1;
             }
+            need_stage = true;
           }
-          for (int u = 0; u < nu; ++u) started |= 1u << args.shift[si].u[u].cls;
         }
         umma_commit(&tfull[as]);
       }
@@ -1573,7 +1594,7 @@ extern "C" int fpg_igemm_s2cls_launch(const fpg_igemm_fprop_desc* d, int32_t n_c
   }
   const int BN = d[0].block_n;
   const size_t resident = (static_cast<size_t>(n_slots) * BN * 128 + 1023) & ~size_t(1023);
-  const size_t budget = 227 * 1024 - 1024 - 256;
+  const size_t budget = 227 * 1024 - 1024 - 256 - kS2MaxOps * 12;
   if (resident + 2 * 16384 > budget) return 1;
   int stages = static_cast<int>((budget - resident) / 16384);
   if (stages > 6) stages = 6;
@@ -1632,7 +1653,8 @@ extern "C" int fpg_igemm_s2cls_launch(const fpg_igemm_fprop_desc* d, int32_t n_c
   if (sms <= 0) return fail(FPG_ENOTSUP, "no CUDA device");
   const int total_tiles = args.n_img * args.tiles_y * args.tiles_x;
   const int grid = total_tiles < sms ? total_tiles : sms;
-  const size_t smem = resident + static_cast<size_t>(stages) * 16384 + (2 * stages + 5) * 8 + 16 + 1024;
+  if (n_slots > kS2MaxOps) return 1;
+  const size_t smem = resident + static_cast<size_t>(stages) * 16384 + (2 * stages + 5) * 8 + kS2MaxOps * 12 + 16 + 1024;
   FPG_CUDA_CHECK(cudaFuncSetAttribute(igemm_s2cls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(smem)));
   FPG_CUDA_CHECK(launch_persistent(igemm_s2cls_kernel, dim3(grid), dim3(kFpropThreads), smem,
