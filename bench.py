@@ -47,10 +47,10 @@ def workload_config(model, identity, batch, world):
             "l2": "per-step working set (>5 GB of activations) far exceeds the 126 MB L2"}
 
 
-def ncu_traffic_bytes(report="r01_res_fprop.ncu-rep"):
+def ncu_traffic_bytes(report="r02_res_fprop.ncu-rep"):
     """DRAM bytes (read + write) per launch of the dominant kernel from the committed ncu --set full summary
-    (profiles/r01_ncu_kernels_v9.csv, produced by tools/profile_kernels.sh + tools/summarize_ncu.py); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_kernels_v9.csv")
+    (profiles/r02/ncu_kernels.csv, produced by tools/profile_kernels.sh + tools/summarize_ncu.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r02", "ncu_kernels.csv")
     if not os.path.exists(path):
         return None
     import csv
@@ -309,7 +309,7 @@ def run_native(args):
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "traffic": ncu_traffic_bytes(),
                     "traffic_source": "committed ncu --set full capture of this kernel on this shape "
-                                      "(profiles/r01_ncu_kernels_v9.csv), not measured in this run",
+                                      "(profiles/r02/ncu_kernels.csv), not measured in this run",
                     "peak_source": peak_src + ", sustained bf16", "launches_timed": len(res_ms),
                     "avg_ms": avg}
     conv_ms = sum(sum(v) for k, v in prof.items() if k.split()[0] in ("fprop", "dgrad", "wgrad")) / 2
