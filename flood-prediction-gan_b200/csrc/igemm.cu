@@ -745,6 +745,7 @@ struct S2Args {
   int32_t kchunks;   // c_out / 64
   int32_t stages;    // activation ring
   int32_t n_shifts;
+  int32_t line_store;       // BN == 64: lanes of a group of four write one pixel's 128-byte line together
   int32_t cls_taps[4];      // taps of each class
   int32_t cls_slot0[4];     // first resident weight slot of each class (slot = one tap x one 64-wide K chunk)
   struct Shift {
@@ -924,6 +925,70 @@ igemm_s2cls_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 256 + cls * BN;
         const int64_t prow = static_cast<int64_t>(n) * args.stat.rows_per_img + args.stat_row0[cls] +
                              (ty * args.tiles_x + tx) * 4 + q;
+        if (BN == 64 && args.line_store && args.out.fp32 != FPG_DT_FP32) {
+          // 64 produced channels = 128 bytes per pixel = four 32-byte chunks. Row-per-thread stores touch 32 different
+          // lines per instruction (ncu: the epilogue warps spent a quarter of their time on store back-pressure): the
+          // four chunks of four neighbouring pixels are transposed among groups of four lanes (two shuffle butterflies),
+          // so that lanes 4g .. 4g+3 then write ONE pixel's 128-byte line together: 8 full lines per store instruction.
+          uint32_t w[4][8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t v[16];
+            tmem_ld16(t_addr + 16 * j, v);
+            tmem_ld_wait();
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            if (args.stat.partial != nullptr) stat_accumulate(args.stat, f, valid, lane, prow, 16 * j, args.out.fp32);
+            if (args.out.fp32 == 2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) w[j][i] = pack_f16x2(f[2 * i], f[2 * i + 1]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) w[j][i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+            }
+          }
+          // 4 x 4 transpose of 32-byte blocks within lane groups of four: afterwards w[i] = chunk (lane & 3) of the
+          // pixel of lane (lane & ~3) + i
+#pragma unroll
+          for (int bit = 1; bit <= 2; bit <<= 1) {
+            const bool hi = (lane & bit) != 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j & bit) continue;  // pairs (j, j + bit)
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t send = hi ? w[j][i] : w[j + bit][i];
+                const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, bit);
+                if (hi) {
+                  w[j][i] = recv;
+                } else {
+                  w[j + bit][i] = recv;
+                }
+              }
+            }
+          }
+          const int k = lane & 3;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int prow_i = q * 32 + (lane & ~3) + i;  // tile row of the pixel this store belongs to
+            const int py_i = ty * args.tile_h + (prow_i >> args.tile_w_log2);
+            const int px_i = tx * args.tile_w + (prow_i & (args.tile_w - 1));
+            if (py_i < args.out.valid_h && px_i < args.out.valid_w) {
+              const int64_t off_i = static_cast<int64_t>(n) * args.out.stride_n +
+                                    static_cast<int64_t>(py_i * 2 + args.off_y[cls]) * args.out.stride_y +
+                                    static_cast<int64_t>(px_i * 2 + args.off_x[cls]) * args.out.stride_x + 16 * k;
+              __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(args.out.base) + off_i;
+              if ((reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+                st_global_256(dst, w[i]);
+              } else {
+                reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
+                reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[i][4], w[i][5], w[i][6], w[i][7]);
+              }
+            }
+          }
+          continue;
+        }
         for (int c = 0; c < BN; c += 16) {
           uint32_t v[16];
           tmem_ld16(t_addr + c, v);
@@ -1611,6 +1676,8 @@ extern "C" int fpg_igemm_s2cls_launch(const fpg_igemm_fprop_desc* d, int32_t n_c
   args.block_n = BN;
   args.kchunks = d[0].c_per_tap / 64;
   args.stages = stages;
+  static const bool row_store = getenv("FPG_S2CLS_ROWSTORE") != nullptr;  // A/B switch: row-per-thread stores
+  args.line_store = row_store ? 0 : 1;
   int slot = 0;
   for (int q = 0; q < 4; ++q) {
     args.cls_taps[q] = d[q].num_taps;

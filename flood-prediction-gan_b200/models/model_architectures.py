@@ -190,7 +190,8 @@ class _InstanceNormPatchGAN(_NativeModule):
         self.model = nn.Sequential(*seq)
 
     def _run_backward(self, net, tape, dout, grads, need_dx):
-        dl = ops.ActBuf.from_nchw(dout, c_pad=16)
+        dl = ops.ActBuf(dout.shape[0], dout.shape[2], dout.shape[3], 16, zero=False)
+        ops.pack_nchw(dout.contiguous(), dl, 0, zero_rest=True)  # fp32 NCHW logit gradient -> bf16 NHWC, native kernel
         dd = net.backward(tape, dl, grads, need_dx)
         if not need_dx:
             return None
@@ -285,7 +286,8 @@ class Pix2PixDiscriminator(_NativeModule):
         self.model = nn.Sequential(*seq)
 
     def _run_backward(self, net, tape, dout, grads, need_dx):
-        dl = ops.ActBuf.from_nchw(dout, c_pad=16)
+        dl = ops.ActBuf(dout.shape[0], dout.shape[2], dout.shape[3], 16, zero=False)
+        ops.pack_nchw(dout.contiguous(), dl, 0, zero_rest=True)  # fp32 NCHW logit gradient -> bf16 NHWC, native kernel
         dd = net.backward(tape, dl, grads, need_dx)
         if not need_dx:
             return None
