@@ -244,6 +244,8 @@ def run_native(args):
         tr.step(*resident[s % len(resident)])
     barrier()
     ops.LAUNCHES = 0
+    peer_reds = [r for r in (getattr(tr, "g_reducer", None), getattr(tr, "d_reducer", None)) if hasattr(r, "waited_ms")]
+    waited0 = sum(r.waited_ms() for r in peer_reds)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         e0.record()
@@ -252,6 +254,7 @@ def run_native(args):
         e1.record()
         barrier()
     launches = ops.LAUNCHES
+    waited_ms_per_step = (sum(r.waited_ms() for r in peer_reds) - waited0) / steps if peer_reds else None
     ms = max_over_ranks(e0.elapsed_time(e1))
     value = B * world * steps / (ms / 1000.0)
     last_losses = tr.losses()
@@ -342,6 +345,19 @@ def run_native(args):
                 "conv_share_of_step": conv_ms / all_ms if all_ms else None,
                 "kernel_ms_per_step": {k: sum(v) / 2 for k, v in sorted(prof.items(), key=lambda kv: -sum(kv[1]))[:12]},
                 "losses_last_step": last_losses, "extra": extra}
+        red = getattr(getattr(model, "_native", None), "g_reducer", None)
+        if red is not None:  # how the gradients of the ranks are summed (fpgan/peer.py or NCCL)
+            peer = type(red).__name__ == "PeerReducer"
+            line["gradient_exchange"] = {
+                "kind": "copy-engine all-gather over peer memory + rank-ordered sum inside Adam" if peer
+                        else "NCCL all-reduce",
+                "buckets": len(red.bounds), "bytes_pushed_per_rank_per_step":
+                    sum(4 * r.count * (world - 1) for r in (model._native.g_reducer, model._native.d_reducer))
+                    if peer else None,
+                # rank 0's stream time inside the flag waits of the timed (replayed) steps, device clock: the part of
+                # the exchange the backward pass did not hide + the skew between the ranks
+                "wait_ms_per_step_rank0": waited_ms_per_step,
+                "adam_ms_per_step_eager": sum(prof.get("adam_step", [])) / 2}
         if cpu_tps is not None:
             line["cpu_baseline"] = {"value": cpu_tps, "unit": "tiles/s", "cores": cores, "kind": cpu_kind,
                                     "sample": ("the unmodified reference (oracle/_ref) through its own Model training "
@@ -482,6 +498,7 @@ def run_dp_check(args):
     single, single_first = run(t1, B, 0, 1)
     w_single = torch.cat([t1.gp.flat, t1.dp.flat]).clone()
     del t1, m1
+    os.environ["FPG_PEER_KEEP_SUM"] = "1"  # leave the rank-ordered gradient SUM in grads.flat (compared below)
     mw, tw = build(world)
     sharded, sh_first = run(tw, b, rank, world)
     w_sharded = torch.cat([tw.gp.flat, tw.dp.flat])
@@ -504,7 +521,7 @@ def run_dp_check(args):
                           "world": world, "global_batch": B, "tile": size, "steps": 3, **rec, "tolerance": tol,
                           "ok": bool(ok), "losses_single": single[-1], "losses_sharded": sharded[-1]}),
               file=_RESULT_OUT, flush=True)
-    tw.release_graphs()
+    tw.close()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

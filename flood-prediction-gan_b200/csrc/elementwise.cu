@@ -2191,6 +2191,13 @@ int fpg_adam_step(float* p, const float* g, float* m, float* v, int64_t count, f
   return 0;
 }
 
+int fpg_adam_prepare_dev(int32_t* state, float beta1, float beta2, void* stream) {
+  FPG_REQUIRE(state != nullptr, "bad argument");
+  adam_prepare_kernel<<<1, 32, 0, FPG_ST(stream)>>>(state, beta1, beta2);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int fpg_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t count, float beta1, float beta2, float eps,
                       int32_t* state, float grad_scale, void* stream) {
   FPG_REQUIRE(p && g && m && v && state && count > 0, "bad argument");

@@ -156,6 +156,17 @@ SIGNATURES = {
     "fpg_tanh_bwd_pack": (C.c_int, [_vp, _P(Act), _i32, _P(Act), _vp]),
     "fpg_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
     "fpg_adam_step_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp, _f32, _vp]),
+    "fpg_adam_prepare_dev": (C.c_int, [_vp, _f32, _f32, _vp]),
+    "fpg_peer_alloc": (C.c_int, [_P(_vp), _i64]),
+    "fpg_peer_free": (C.c_int, [_vp]),
+    "fpg_peer_export": (C.c_int, [_vp, _vp]),
+    "fpg_peer_open": (C.c_int, [_vp, _P(_vp)]),
+    "fpg_peer_close": (C.c_int, [_vp]),
+    "fpg_peer_copy": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "fpg_peer_signal": (C.c_int, [_P(_vp), _i32, _vp, C.c_uint32, C.c_uint32, _vp]),
+    "fpg_peer_wait": (C.c_int, [_vp, _i32, _i32, _vp, C.c_uint32, _vp, _f32, _vp]),
+    "fpg_peer_push": (C.c_int, [_vp, _P(_vp), _i32, _i64, _vp]),
+    "fpg_adam_step_dev_multi": (C.c_int, [_vp, _P(_vp), _i32, _vp, _vp, _i64, _f32, _f32, _f32, _vp, _f32, _vp, _vp]),
     "fpg_flood_mask": (C.c_int, [_vp, _vp, _i64, _vp]),
     "fpg_confusion_counts": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
 }

@@ -13,7 +13,7 @@ import random
 import torch
 import torch.distributed as dist
 
-from . import networks, ops
+from . import networks, ops, peer
 from .ops import ActBuf
 
 
@@ -144,6 +144,28 @@ class _BucketReducer:
             w.wait()
         self.works = []
 
+    def adam(self, grad_scale, betas=(0.5, 0.999), eps=1e-8):
+        self.fp.adam(grad_scale=grad_scale, betas=betas, eps=eps)
+
+    def close(self):
+        pass
+
+
+def make_reducers(world_size, group, *flat_params, overlappable=True):
+    """One gradient reducer per optimiser for data-parallel training, None each for a single process. Where the
+    backward pass can hide the transfers (`overlappable`): the copy-engine exchange over peer memory (peer.PeerReducer)
+    when every rank can map the others' memory (one NVSwitch / NVLink box); FPG_DDP=nccl or no peer access -> NCCL
+    all-reduces (_BucketReducer). Where nothing can be hidden (train_cycle: every network runs 2-3 times per step and
+    its gradient is complete only after the last run) an all-reduce is the right collective -- it moves 2(W-1)/W of
+    the buffer per rank, the all-gather W-1 times -- so those steps use NCCL (NVLS in-switch reduction) unless
+    FPG_DDP=peer asks otherwise."""
+    if world_size <= 1:
+        return [None] * len(flat_params)
+    want_peer = overlappable or os.environ.get("FPG_DDP", "") == "peer"
+    if want_peer and peer.supported(group):
+        return [peer.PeerReducer(fp, group=group) for fp in flat_params]
+    return [_BucketReducer(fp, group=group) for fp in flat_params]
+
 
 class PairedTrainer:
     """One `train_paired` iteration (model.py:611-651) for the InstanceNorm paired model (PairedAttention)."""
@@ -160,7 +182,7 @@ class PairedTrainer:
         self.l1_weight = l1_weight
         dev = self.gp.flat.device
         self.loss_buf = torch.zeros(4, dtype=torch.float32, device=dev)
-        self.g_reducer = _BucketReducer(self.gp, group=group) if world_size > 1 else None
+        self.g_reducer, self.d_reducer = make_reducers(world_size, group, self.gp, self.dp)
         self.launches = 0
         # CUDA-graph replay of the whole step (341 launches, the NCCL gradient reductions included): removes host
         # launch overhead and inter-kernel gaps (measured 5-6 % of the step). Captured NCCL work must be released before
@@ -208,6 +230,14 @@ class PairedTrainer:
         self._graphs.clear()
         self._eager_calls.clear()
 
+    def close(self):
+        """collective teardown of the data-parallel state: captured steps, then the peer-memory mappings"""
+        self.release_graphs()
+        for r in (self.g_reducer, self.d_reducer):
+            if r is not None:
+                r.close()
+        self.g_reducer = self.d_reducer = None
+
     def _capture(self, input_stack, output_image):
         sx, sy = input_stack.clone(), output_image.clone()
         before = ops.LAUNCHES
@@ -219,7 +249,21 @@ class PairedTrainer:
         ops.LAUNCHES = before  # capturing records the launches, it does not run them
         return sx, sy, graph, out, launches
 
-    def _phase_d(self, input_stack, output_image):
+    def _backward_reduced(self, net, reducer, run):
+        """run() = a backward pass of executor `net`; with a reducer its gradient buckets are sent to the other ranks
+        as they complete and the call returns once the exchange is in flight / has landed (reducer.finish)"""
+        if reducer is None:
+            return run()
+        reducer.start()
+        net.grad_ready = reducer.ready
+        try:
+            out = run()
+        finally:
+            net.grad_ready = None
+        reducer.finish()
+        return out
+
+    def _phase_d(self, input_stack, output_image, reducer=None):
         """generator forward + discriminator forward / backward on [synthetic | real] (:615-632): leaves the
         discriminator gradients of this batch in self.dp.grads and returns what the generator phase needs"""
         G, D = self.G, self.D
@@ -237,7 +281,7 @@ class PairedTrainer:
         dlog = ActBuf(2 * B, logits.h, logits.w, 16, zero=False)
         ops.mse_const_loss(logits.batch_slice(0, B), 0.0, 1.0, 0.5, self.loss_buf[1:2], dlog.batch_slice(0, B))
         ops.mse_const_loss(logits.batch_slice(B, B), 1.0, 1.0, 0.5, self.loss_buf[0:1], dlog.batch_slice(B, B))
-        D.backward(dtape, dlog, self.dp.grads, need_dx=False)
+        self._backward_reduced(D, reducer, lambda: D.backward(dtape, dlog, self.dp.grads, need_dx=False))
         return synthetic, gtape, fake, output_image, C
 
     def _phase_g(self, state, reducer=None):
@@ -252,23 +296,16 @@ class PairedTrainer:
         d_din = D.backward(dtape_g, dlog_g, None, need_dx=True)
         dl1 = torch.empty_like(synthetic)
         ops.l1_loss(synthetic, output_image, self.l1_weight, 1.0, self.loss_buf[3:4], dpred=dl1)
-        if reducer is not None:
-            reducer.start()
-            G.grad_ready = reducer.ready
-        G.backward(gtape, self.gp.grads, dout_nchw=dl1, dout_nhwc=d_din, dout_c0=C, need_dx=False)
-        if reducer is not None:
-            G.grad_ready = None
-            reducer.finish()
+        self._backward_reduced(G, reducer, lambda: G.backward(gtape, self.gp.grads, dout_nchw=dl1, dout_nhwc=d_din,
+                                                              dout_c0=C, need_dx=False))
 
     def _step_impl(self, input_stack, output_image):
         inv_w = 1.0 / self.world_size
-        state = self._phase_d(input_stack, output_image)
-        if self.world_size > 1:
-            dist.all_reduce(self.dp.grads.flat, group=self.group)
-        self.dp.adam(grad_scale=inv_w)
+        state = self._phase_d(input_stack, output_image, self.d_reducer)
+        (self.d_reducer or self.dp).adam(grad_scale=inv_w)
         self._force_repack(self.D)
         self._phase_g(state, self.g_reducer)
-        self.gp.adam(grad_scale=inv_w)
+        (self.g_reducer or self.gp).adam(grad_scale=inv_w)
         self._force_repack(self.G)
         return state[0]
 
@@ -357,6 +394,7 @@ class CycleTrainer:
         self.Dpost, self.Dpre = post_discriminator._executor(), pre_discriminator._executor()
         self.g_extra = [self.gp.extra_grads() for _ in range(2 if add_identity_loss else 1)]
         self.world_size, self.group = world_size, group
+        self.g_reducer, self.d_reducer = make_reducers(world_size, group, self.gp, self.dp, overlappable=False)
         self.loss_keys = self.LOSS_KEYS + (self.IDENTITY_KEYS if add_identity_loss else ())
         dev = self.gp.flat.device
         self.loss_buf = torch.zeros(len(self.loss_keys), dtype=torch.float32, device=dev)
@@ -380,6 +418,14 @@ class CycleTrainer:
     def release_graphs(self):
         self._graphs.clear()
         self._eager_calls.clear()
+
+    def close(self):
+        """collective teardown of the data-parallel state: captured steps, then the peer-memory mappings"""
+        self.release_graphs()
+        for r in (self.g_reducer, self.d_reducer):
+            if r is not None:
+                r.close()
+        self.g_reducer = self.d_reducer = None
 
     def _pool(self, which, like):
         """device pool of 50 packed discriminator inputs [50][B][H][W][16] bf16 for this batch shape"""
@@ -433,15 +479,19 @@ class CycleTrainer:
     def _step_impl(self, x_pre, y_post):
         inv_w = 1.0 / self.world_size
         state = self._phase_g(x_pre, y_post)
-        if self.world_size > 1:
-            dist.all_reduce(self.gp.grads.flat, group=self.group)
-        self.gp.adam(grad_scale=inv_w)
+        # every network runs 2-3 times per step and its gradient is complete only after the last sum: one exchange
+        # per optimiser phase (the step is 3.3 x longer per exchanged byte than the paired one)
+        if self.g_reducer is not None:
+            self.g_reducer.start()
+            self.g_reducer.finish()
+        (self.g_reducer or self.gp).adam(grad_scale=inv_w)
         self.Gpp.repack(force=True)
         self.Gpr.repack(force=True)
         self._phase_d(state)
-        if self.world_size > 1:
-            dist.all_reduce(self.dp.grads.flat, group=self.group)
-        self.dp.adam(grad_scale=inv_w)
+        if self.d_reducer is not None:
+            self.d_reducer.start()
+            self.d_reducer.finish()
+        (self.d_reducer or self.dp).adam(grad_scale=inv_w)
         self.Dpre.repack(force=True)
         self.Dpost.repack(force=True)
         return state[0], state[1]

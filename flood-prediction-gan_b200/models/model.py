@@ -368,7 +368,7 @@ class Model:
         """Release the captured CUDA graphs of the fused steps. With data parallelism they hold NCCL work: call this
         (then synchronise and barrier) before torch.distributed.destroy_process_group(), which hangs otherwise."""
         if self._native is not None:
-            self._native.release_graphs()
+            self._native.close()  # captured steps, then the peer-memory mappings of the gradient exchange (collective)
         if torch.cuda.is_available():
             torch.cuda.synchronize()
         if self._world() > 1:

@@ -510,6 +510,44 @@ int fpg_adam_step(float* p, const float* g, float* m, float* v, int64_t count, f
 int fpg_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t count, float beta1, float beta2, float eps,
                       int32_t* state, float grad_scale, void* stream);
 
+/* The first half of fpg_adam_step_dev alone: advance state[0] and refresh the bias-correction scalars. */
+int fpg_adam_prepare_dev(int32_t* state, float beta1, float beta2, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Peer exchange -- data-parallel gradient sum over NVLink / NVSwitch peer memory, no reference counterpart (the
+ * reference is one process; this is what stands between loss.backward() and optimizer.step(), model.py:632-633 and
+ * :645-646, when the batch is sharded over W GPUs). Copy engines push each rank's gradient buckets into a staging slot
+ * on every peer (no SM involved, overlaps the backward pass); Adam sums the W sources in rank order (bit-identical
+ * replicas, equal to one process accumulating the shards in order). See csrc/peer.cu.
+ *   fpg_peer_alloc / free      a zero-filled device block of its own cudaMalloc (IPC handles address whole blocks);
+ *   fpg_peer_export            handle_host <- the FPG_PEER_HANDLE_BYTES-byte IPC handle of such a block;
+ *   fpg_peer_open / close      map / unmap another process's block (peer access enabled on first use);
+ *   fpg_peer_copy              asynchronous device-to-device copy on `stream` (copy engine; capturable);
+ *   fpg_peer_signal            *flags_host[i] = *ctr + add for i < n (system-scope release stores into peer memory,
+ *                              ordered after everything earlier on the stream), then *ctr += bump;
+ *   fpg_peer_wait              block the stream until local_flags[i] >= *ctr + add for every i < n except i == skip
+ *                              (words the peers write); status = device int64[2]: after timeout_s seconds status[0] =
+ *                              i + 1 and the kernel traps; status[1] accumulates the nanoseconds spent waiting;
+ *   fpg_peer_push              src[0, bytes) -> every dst_host[i] (i < n_dst <= 16, peer memory) by ONE kernel (16-byte
+ *                              accesses): for the tail of an exchange, where nothing is left to overlap with;
+ *   fpg_adam_step_dev_multi    fpg_adam_step_dev on g = ((grads_host[0] + grads_host[1]) + ...) (n_src <= 16 fp32
+ *                              device buffers, summed in that order); gsum_out (optional, may alias a source) <- g.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define FPG_PEER_HANDLE_BYTES 64
+int fpg_peer_alloc(void** ptr, int64_t bytes);
+int fpg_peer_free(void* ptr);
+int fpg_peer_export(void* ptr, void* handle_host);
+int fpg_peer_open(const void* handle_host, void** ptr);
+int fpg_peer_close(void* ptr);
+int fpg_peer_copy(void* dst, const void* src, int64_t bytes, void* stream);
+int fpg_peer_signal(void* const* flags_host, int32_t n, uint32_t* ctr, uint32_t add, uint32_t bump, void* stream);
+int fpg_peer_wait(const uint32_t* local_flags, int32_t n, int32_t skip, const uint32_t* ctr, uint32_t add,
+                  int64_t* status, float timeout_s, void* stream);
+int fpg_peer_push(const void* src, void* const* dst_host, int32_t n_dst, int64_t bytes, void* stream);
+int fpg_adam_step_dev_multi(float* p, const void* const* grads_host, int32_t n_src, float* m, float* v, int64_t count,
+                            float beta1, float beta2, float eps, int32_t* state, float grad_scale, float* gsum_out,
+                            void* stream);
+
 /* dst += src (fp32, 16-byte aligned): accumulates the parameter gradients of a network that runs several times in one
  * training step (train_cycle applies each generator 2-3 times, model.py:683-704). */
 int fpg_add_f32(float* dst, const float* src, int64_t count, void* stream);

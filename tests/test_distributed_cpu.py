@@ -110,3 +110,34 @@ def test_binary_metrics_from_counts_match_definitions():
     assert abs(m["Precision_No_Flood"] - int((inv_p & inv_t).sum()) / int(inv_p.sum())) < 1e-12
     assert abs(m["Recall_No_Flood"] - int((inv_p & inv_t).sum()) / int(inv_t.sum())) < 1e-12
     assert M.Model.binary_metrics_from_counts(0, 0, 10, 0)["Precision_Flood"] == 0.0  # safe division
+
+
+def test_peer_exchange_bucket_plan():
+    """fpgan/peer.py::plan_buckets: buckets are contiguous, cover the flat buffer exactly once, every name maps to the
+    bucket that holds it, the tail is the small prefix (first layers = last gradients), the others reach the target"""
+    from fpgan import peer
+    sizes, off = [], 0
+    layers = [("stem", 28224, 64), ("c2", 73728, 128), ("c3", 294912, 256)]
+    layers += [(f"b{i}.c{j}", 589824, 256) for i in range(9) for j in (1, 2)]
+    layers += [("d1", 294912, 128), ("d2", 73728, 64), ("head", 84672, 27)]
+    for n, w, b in layers:
+        sizes.append((n + ".weight", off, w))
+        off += w
+        sizes.append((n + ".bias", off, b))
+        off += b
+    for bucket_mb, tail_mb in ((4, 2), (8, 2), (1, 0.05), (64, 64), (0.001, 0.001)):
+        bounds, of, tail = peer.plan_buckets(sizes, int(bucket_mb * 2 ** 20), int(tail_mb * 2 ** 20))
+        assert bounds[0][0] == 0 and bounds[-1][1] == off
+        assert all(a[1] == b[0] for a, b in zip(bounds, bounds[1:])) and all(e > s for s, e in bounds)
+        for n, o, k in sizes:
+            s, e = bounds[of[n]]
+            assert s <= o and o + k <= e
+        assert tail == 0
+        if len(bounds) > 1:
+            if sizes[0][2] * 4 <= tail_mb * 2 ** 20:  # else no prefix fits and the first bucket in flat order is the tail
+                assert (bounds[0][1] - bounds[0][0]) * 4 <= tail_mb * 2 ** 20
+            for s, e in bounds[2:]:  # every bucket but the tail and its neighbour reaches the target
+                assert (e - s) * 4 >= min(bucket_mb * 2 ** 20, max(k for _, _, k in sizes) * 4) * 0.5
+    bounds, of, tail = peer.plan_buckets(sizes, 4 << 20, 2 << 20)
+    assert of["stem.weight"] == of["c3.bias"] == 0 and of["b0.c1.weight"] != 0
+    assert (bounds[0][1] - bounds[0][0]) == sum(w + b for n, w, b in layers[:3])
