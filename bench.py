@@ -30,15 +30,17 @@ CHANNELS = 9
 BATCH_PER_GPU = 16
 # algorithmic GFLOP of one training step per tile, by (model, identity loss)
 GFLOP_PER_TILE = {("pairedattention", False): 397.31, ("cyclegan", False): 1314.1, ("cyclegan", True): 1916.2,
-                  ("attentiongan", False): 1491.5, ("attentiongan", True): 2182.2}
+                  ("attentiongan", False): 1491.5, ("attentiongan", True): 2182.2, ("pix2pix", False): 88.55}
+CYCLE_MODELS = ("cyclegan", "attentiongan")
 RES_CONV_GFLOP_PER_TILE = 4.8318  # one residual 3x3 conv, 256->256 @ 64x64: 2 * 4096 * 256 * 2304
-PRETTY = {"pairedattention": "PairedAttention", "cyclegan": "CycleGAN", "attentiongan": "AttentionGAN"}
+PRETTY = {"pairedattention": "PairedAttention", "cyclegan": "CycleGAN", "attentiongan": "AttentionGAN",
+          "pix2pix": "Pix2Pix"}
 
 
 def workload_config(model, identity, batch, world):
     """`config` of the JSON line: identical keys and values on the native and the reference arm"""
-    if model == "pairedattention":
-        what = "PairedAttention train_paired step"
+    if model in ("pairedattention", "pix2pix"):
+        what = f"{PRETTY[model]} train_paired step"
     else:
         what = f"{PRETTY[model]} train_cycle step" + (" with identity loss" if identity else "")
     return {"workload": f"{what}, 256x256 tiles (resize=512 crop=4), 9 input channels (topography=all), batch "
@@ -145,7 +147,7 @@ def cpu_reference_tiles_per_s(steps, warmup, batch, model="pairedattention", ide
     kind)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    cycle = model != "pairedattention"
+    cycle = model in CYCLE_MODELS
     from oracle import ref_runner
     if ref_runner.available():
         m = ref_runner.make_model(model, add_identity_loss=identity)
@@ -158,7 +160,7 @@ def cpu_reference_tiles_per_s(steps, warmup, batch, model="pairedattention", ide
         return batch * steps / dt, dt, cores, "reference"
     from oracle import gan_oracle as O
     nets = O.init_model(model, "all", seed=47)
-    tr = O.CycleTrainer(nets, model, add_identity_loss=identity) if cycle else O.PairedTrainer(nets)
+    tr = O.CycleTrainer(nets, model, add_identity_loss=identity) if cycle else O.PairedTrainer(nets, model)
     for s in range(warmup):
         tr.step(*O.synthetic_batch(s, batch, CHANNELS, TILE))
     data = [O.synthetic_batch(warmup + s, batch, CHANNELS, TILE) for s in range(steps)]
@@ -184,7 +186,7 @@ def run_reference(args):
         batch //= 2
     tps, dt, cores, kind = cpu_reference_tiles_per_s(steps, warmup, batch, args.model, args.identity)
     source = ("the unmodified reference (oracle/_ref, staged by oracle/build_ref.py) through its own Model."
-              f"{'train_cycle' if args.model != 'pairedattention' else 'train_paired'}()" if kind == "reference" else
+              f"{'train_cycle' if args.model in CYCLE_MODELS else 'train_paired'}()" if kind == "reference" else
               "oracle port (oracle/gan_oracle.py) of the reference's training loop")
     sample = (f"{source}, fp32, {cores} host threads, {batch} of the {BATCH_PER_GPU} tiles of a batch per step, "
               f"{steps} timed steps after {warmup} warm-up")
@@ -230,7 +232,7 @@ def run_native(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
-    cycle = args.model != "pairedattention"
+    cycle = args.model in CYCLE_MODELS
     model = M.Model(model=PRETTY[args.model], topography="all", num_epochs=1, resize=512, crop=4, seed=47,
                     log_interval=1, add_identity_loss=args.identity)
     tr = model._ensure_native_cycle() if cycle else model._ensure_native_paired()
@@ -320,7 +322,7 @@ def run_native(args):
     step_tflops = gflop_per_tile * B * world / (ms / steps)
 
     extra = {}
-    if rank == 0 and world == 1 and not cycle and not args.no_unet:
+    if rank == 0 and world == 1 and args.model == "pairedattention" and not args.no_unet:
         extra["unet"] = unet_block(dev)
     if rank == 0:
         cpu_tps = None
@@ -431,7 +433,7 @@ def run_dp_check(args):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     assert B % world == 0, "--batch must divide by the number of ranks"
-    cycle = args.model != "pairedattention"
+    cycle = args.model in CYCLE_MODELS
     size = args.check_size
 
     def build(world_size):
@@ -543,7 +545,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--model", default="pairedattention", choices=sorted(PRETTY),
-                    help="pairedattention (BASELINE configs[1]/[2], default) or the cycle models of configs[3]")
+                    help="pairedattention (BASELINE configs[1]/[2], default), the cycle models of configs[3], or pix2pix "
+                         "(the model of configs[0], fused step)")
     ap.add_argument("--identity", action="store_true", help="cycle models: add the identity loss (model.py:700-702)")
     ap.add_argument("--check", action="store_true", help="data-parallel parity check instead of a benchmark")
     ap.add_argument("--no_unet", action="store_true", help="skip the extra.unet block (configs[4]) of the 1-GPU line")

@@ -210,7 +210,11 @@ __global__ void bn_running_kernel(const float* __restrict__ stats, float eps, fl
 }
 
 // Bernoulli(keep) byte mask from a counter-based hash (splitmix64 of seed + element index): reproducible per call
-__global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t count, uint64_t seed, float keep) {
+// seed_dev != nullptr: the seed is read from device memory and `seed` is added to it (a captured step draws fresh
+// masks on every replay: the host writes the next seeds before it launches the graph)
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ mask, int64_t count, uint64_t seed,
+                                    const uint64_t* __restrict__ seed_dev, float keep) {
+  if (seed_dev != nullptr) seed += *seed_dev;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += stride) {
     uint64_t z = seed + 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(i + 1);
@@ -337,7 +341,17 @@ int fpg_dropout_mask(uint8_t* mask, int64_t count, uint64_t seed, float keep, vo
   FPG_REQUIRE(mask && count > 0 && keep > 0.f && keep <= 1.f, "bad argument");
   int64_t blocks = (count + 255) / 256;
   if (blocks > 1184) blocks = 1184;
-  dropout_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, FPG_ST(stream)>>>(mask, count, seed, keep);
+  dropout_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, FPG_ST(stream)>>>(mask, count, seed, nullptr, keep);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_dropout_mask_dev(uint8_t* mask, int64_t count, const uint64_t* seed_dev, uint64_t seed_add, float keep,
+                         void* stream) {
+  FPG_REQUIRE(mask && seed_dev && count > 0 && keep > 0.f && keep <= 1.f, "bad argument");
+  int64_t blocks = (count + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  dropout_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, FPG_ST(stream)>>>(mask, count, seed_add, seed_dev, keep);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

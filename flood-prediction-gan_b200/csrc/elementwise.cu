@@ -1592,6 +1592,49 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int c_src, int c
   }
 }
 
+// The three packed copies of a paired training batch in ONE pass over the fp32 NCHW inputs (train_paired,
+// model.py:615-617: the generator input and the two discriminator inputs torch.cat((stack, synthetic), 1) /
+// torch.cat((stack, real), 1)): one thread per PADDED pixel of the generator input (reflect halo) assembles the 16-channel
+// bf16 pixel [x_0 .. x_{cx-1}, 0 ...] once; interior threads also write it to `fake` (whose channels [cx, cx+3) the
+// generator fills later) and, with the target image in channels [cx, cx+cy), to `real`.
+__global__ void pack_paired_inputs_kernel(const float* __restrict__ x, int cx, const float* __restrict__ y, int cy,
+                                          View gin, View fake, View real) {
+  const int64_t total = static_cast<int64_t>(gin.n) * gin.hp() * gin.wp();
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int px = static_cast<int>(idx % gin.wp());
+  const int64_t r = idx / gin.wp();
+  const int py = static_cast<int>(r % gin.hp());
+  const int i = static_cast<int>(r / gin.hp());
+  const int uy = py - gin.halo, ux = px - gin.halo;
+  const int sy = reflect_idx(uy, gin.h), sx = reflect_idx(ux, gin.w);
+  const int64_t hw = static_cast<int64_t>(gin.h) * gin.w;
+  const float* xp = x + static_cast<int64_t>(i) * cx * hw + static_cast<int64_t>(sy) * gin.w + sx;
+  float f[16];
+#pragma unroll
+  for (int ch = 0; ch < 16; ++ch) f[ch] = ch < cx ? __ldg(xp + ch * hw) : 0.f;
+  uint4 lo = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  uint4 hi = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                        pack_bf16x2(f[14], f[15]));
+  uint4* g4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(gin.p) + gin.at_padded(i, py, px));
+  g4[0] = lo;
+  g4[1] = hi;
+  if (uy < 0 || uy >= gin.h || ux < 0 || ux >= gin.w) return;
+  uint4* f4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(fake.p) + fake.at(i, sy, sx));
+  f4[0] = lo;
+  f4[1] = hi;
+  const float* yp = y + static_cast<int64_t>(i) * cy * hw + static_cast<int64_t>(sy) * gin.w + sx;
+#pragma unroll
+  for (int ch = 0; ch < 16; ++ch) {
+    const int sc = ch - cx;
+    if (sc >= 0 && sc < cy) f[ch] = __ldg(yp + sc * hw);
+  }
+  uint4* r4 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(real.p) + real.at(i, sy, sx));
+  r4[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+  r4[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                     pack_bf16x2(f[14], f[15]));
+}
+
 // bf16 NHWC (interior, channels [c0, c0+c_dst)) -> fp32 NCHW; one thread per pixel
 __global__ void unpack_nchw_kernel(View src, int src_fp32, int c0, float* __restrict__ dst, int c_dst, int accumulate) {
   const int64_t total = static_cast<int64_t>(src.n) * src.h * src.w;
@@ -2153,6 +2196,21 @@ int fpg_pack_nchw(const float* src, int32_t c_src, int32_t c_img, const fpg_act*
   const int64_t total = static_cast<int64_t>(dst->n) * (dst->h + 2 * dst->halo) * (dst->w + 2 * dst->halo);
   pack_nchw_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(src, c_src, c_img ? c_img : c_src, view_of(dst),
                                                                      c0, zero_rest);
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_pack_paired_inputs(const float* x, int32_t c_x, const float* y, int32_t c_y, const fpg_act* gin,
+                           const fpg_act* fake, const fpg_act* real, void* stream) {
+  FPG_REQUIRE(x && y && gin && fake && real && c_x >= 1 && c_y >= 1 && c_x + c_y <= 16, "bad argument");
+  for (const fpg_act* a : {gin, fake, real})
+    FPG_REQUIRE(a->c == 16 && a->c_stride == 16 && a->fp32 == FPG_DT_BF16 && a->n == gin->n && a->h == gin->h &&
+                    a->w == gin->w && (reinterpret_cast<uintptr_t>(a->data) & 15) == 0,
+                "the three destinations are 16-channel bf16 buffers of one geometry");
+  FPG_REQUIRE(fake->halo == 0 && real->halo == 0, "the discriminator inputs have no halo");
+  const int64_t total = static_cast<int64_t>(gin->n) * (gin->h + 2 * gin->halo) * (gin->w + 2 * gin->halo);
+  pack_paired_inputs_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(x, c_x, y, c_y, view_of(gin), view_of(fake),
+                                                                              view_of(real));
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -133,6 +133,7 @@ SIGNATURES = {
     "fpg_batchnorm_running_update": (C.c_int, [_vp, _i32, _i64, _f32, _f32, _vp, _vp, _vp]),
     "fpg_maxpool2": (C.c_int, [_P(Act), _P(Act), _vp]),
     "fpg_dropout_mask": (C.c_int, [_vp, _i64, C.c_uint64, _f32, _vp]),
+    "fpg_dropout_mask_dev": (C.c_int, [_vp, _i64, _vp, C.c_uint64, _f32, _vp]),
     "fpg_ssim_scratch_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "fpg_ssim_stats": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
     "fpg_avgpool2_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
@@ -150,6 +151,7 @@ SIGNATURES = {
     "fpg_mse_const_loss": (C.c_int, [_P(Act), _f32, _f32, _f32, _vp, _P(Act), _vp, _vp, _vp]),
     "fpg_l1_loss": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, C.c_int, _vp, _vp]),
     "fpg_pack_nchw": (C.c_int, [_vp, _i32, _i32, _P(Act), _i32, C.c_int, _vp]),
+    "fpg_pack_paired_inputs": (C.c_int, [_vp, _i32, _vp, _i32, _P(Act), _P(Act), _P(Act), _vp]),
     "fpg_add_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
     "fpg_history_exchange": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "fpg_unpack_nchw": (C.c_int, [_P(Act), _i32, _vp, _i32, C.c_int, _vp]),

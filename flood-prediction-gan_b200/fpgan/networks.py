@@ -604,6 +604,7 @@ class Pix2PixGeneratorNet(_NetBase, _BatchNormMixin):
         import torch.distributed as dist
         self.dropout_rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         self.dropout_masks = None  # test hook: list of three uint8 masks [pixels][c] in execution order
+        self.dropout_seeds_dev = None  # int64[3] on the device: per-step seeds of the three masks (Pix2PixTrainer)
 
     def forward(self, x):
         self.repack()
@@ -645,6 +646,11 @@ class Pix2PixGeneratorNet(_NetBase, _BatchNormMixin):
             if lv["kind"] == "dropout":
                 if self.dropout_masks is not None:
                     mask = self.dropout_masks[len(masks)]
+                elif self.dropout_seeds_dev is not None:
+                    # fused trainer: the step's seeds live on the device (written by the host before every step /
+                    # graph replay from the same draws as below)
+                    mask = torch.empty(u.n * u.h * u.w * u.c, dtype=torch.uint8, device=x.device)
+                    ops.dropout_mask_dev(mask, self.dropout_seeds_dev[len(masks):len(masks) + 1], self.dropout_rank)
                 else:
                     mask = torch.empty(u.n * u.h * u.w * u.c, dtype=torch.uint8, device=x.device)
                     # one draw from torch's global generator per mask: torch.manual_seed(47) before a forward (what the
@@ -715,11 +721,9 @@ class PatchGANBatchNormNet(_NetBase, _BatchNormMixin):
         self._add("model.11", seq[11], 4, 1, 1, use_bias=True)
         self.norms = {"model.3": seq[3], "model.6": seq[6], "model.9": seq[9]}
 
-    def forward(self, x):
+    def forward_buf(self, din):
+        """din: ActBuf [B, H, W, 16] (channels beyond the real ones zero). Returns (logits ActBuf fp32, tape)."""
         self.repack()
-        B, C, H, W = x.shape
-        din = ActBuf(B, H, W, 16, zero=False)
-        ops.pack_nchw(x, din, 0, zero_rest=True)
         t = {"din": din}
         t["a1"] = self._conv(din, "model.0", act=ACT_LEAKY)
         cur = t["a1"]
@@ -730,7 +734,14 @@ class PatchGANBatchNormNet(_NetBase, _BatchNormMixin):
             t[f"y{i}"], t[f"a{i}"] = y, a
             cur = a
         t["logits"] = self._conv(cur, "model.11", fp32=True)
-        return t["logits"].to_nchw(1), t
+        return t["logits"], t
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        din = ActBuf(B, H, W, 16, zero=False)
+        ops.pack_nchw(x, din, 0, zero_rest=True)
+        logits, t = self.forward_buf(din)
+        return logits.to_nchw(1), t
 
     def backward(self, t, dlogits, grads, need_dx):
         d = self._conv_bwd("model.11", t["a4"], dlogits, grads, True)

@@ -421,6 +421,13 @@ def dropout_mask(mask, seed, keep=0.5):
          float(keep), _stream())
 
 
+def dropout_mask_dev(mask, seed_dev, seed_add=0, keep=0.5):
+    """seed_dev: one int64 element on the device (the step's seed); seed_add is added to it"""
+    assert seed_dev.dtype == torch.int64 and seed_dev.numel() == 1
+    _run("dropout_mask", 1, "fpg_dropout_mask_dev", _ptr(mask), mask.numel(), _ptr(seed_dev),
+         C.c_uint64(int(seed_add) & (2 ** 64 - 1)), float(keep), _stream())
+
+
 def act_bwd(dz, z, act, dx):
     _run("act_bwd", 1, "fpg_act_bwd", dz.ref(), z.ref(), act, dx.ref(), _stream())
 
@@ -479,6 +486,14 @@ def pack_nchw(src, dst, c0=0, zero_rest=False):
         c_img = src.stride(0) // (src.shape[2] * src.shape[3])
     _run("pack_nchw", 1, "fpg_pack_nchw", _ptr(src), src.shape[1], c_img, dst.ref(), c0, 1 if zero_rest else 0,
          _stream())
+
+
+def pack_paired_inputs(x, y, gin, fake, real):
+    """x [B, cx, H, W], y [B, cy, H, W] contiguous fp32 -> the generator input (reflect halo) and both discriminator
+    inputs, one pass (fpg_pack_paired_inputs)"""
+    assert x.dtype == y.dtype == torch.float32 and x.is_contiguous() and y.is_contiguous()
+    _run("pack_nchw", 1, "fpg_pack_paired_inputs", _ptr(x), x.shape[1], _ptr(y), y.shape[1], gin.ref(), fake.ref(),
+         real.ref(), _stream())
 
 
 def add_f32(dst, src):

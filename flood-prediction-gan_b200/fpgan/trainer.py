@@ -271,10 +271,15 @@ class PairedTrainer:
         # D input for [synthetic | real] halves: channels 0..C-1 = input stack, C..C+2 = image (model.py:616-617)
         din = ActBuf(2 * B, H, W, 16, zero=False)
         fake, real = din.batch_slice(0, B), din.batch_slice(B, B)
-        ops.pack_nchw(input_stack, fake, 0, zero_rest=True)
-        ops.pack_nchw(input_stack, real, 0, zero_rest=True)
-        ops.pack_nchw(output_image, real, C)
-        synthetic, gtape = G.forward(input_stack, d_input=fake, d_c0=C)                         # :615
+        if input_stack.is_contiguous() and output_image.is_contiguous():
+            gin = ActBuf(B, H, W, 16, halo=3, zero=False)
+            ops.pack_paired_inputs(input_stack, output_image, gin, fake, real)  # one pass over the fp32 batch
+        else:
+            gin = None
+            ops.pack_nchw(input_stack, fake, 0, zero_rest=True)
+            ops.pack_nchw(input_stack, real, 0, zero_rest=True)
+            ops.pack_nchw(output_image, real, C)
+        synthetic, gtape = G.forward(input_stack, d_input=fake, d_c0=C, xin=gin)                # :615
 
         # ---- discriminator update (:620-633): both halves in one pass (InstanceNorm is per sample)
         logits, dtape = D.forward_buf(din)
@@ -349,6 +354,82 @@ class PairedTrainer:
             buf /= self.world_size
         vals = buf.tolist()
         return dict(zip(self.LOSS_KEYS, vals))
+
+
+class Pix2PixTrainer(PairedTrainer):
+    """One `train_paired` iteration (model.py:611-651) for Pix2Pix (BatchNorm U-Net generator with dropout + BatchNorm
+    PatchGAN, model_architectures.py:9-85), fused like PairedTrainer: no autograd graph, native loss kernels, flat-buffer
+    Adam, CUDA-graph replay, gradient exchange per optimiser under data parallelism. Differences from the InstanceNorm
+    pair, all the reference's: BatchNorm uses BATCH statistics, so the discriminator's synthetic and real passes are two
+    separate calls (two running-statistics updates, in the reference's order: synthetic first) whose parameter gradients
+    are summed, and a third call in the generator phase; the dropout masks of the generator change every step (seeds
+    drawn on the host from torch's global generator -- one per mask, exactly as the module path draws them -- and
+    written to the device before the step / replay); BatchNorm statistics and dropout masks are per rank (what
+    torch DDP does without SyncBatchNorm; parity with the single-process reference is defined per replica)."""
+
+    def __init__(self, generator, discriminator, world_size=1, group=None, l1_weight=100.0):
+        super().__init__(generator, discriminator, world_size=world_size, group=group, l1_weight=l1_weight)
+        self.d_extra_flat, d_extra = self.dp.extra_grads()
+        self.d_extra = d_extra[0]
+        dev = self.gp.flat.device
+        self.seeds = torch.zeros(3, dtype=torch.int64, device=dev)
+        self.inject_masks = None  # test hook: three uint8 keep-masks in execution order instead of drawn ones
+
+    def _draw_seeds(self):
+        vals = []
+        for _ in range(3):  # the draws Pix2PixGeneratorNet.forward makes, in its order
+            v = (int(torch.empty((), dtype=torch.int64).random_().item()) * 1000003) & (2 ** 64 - 1)
+            vals.append(v - 2 ** 64 if v >= 2 ** 63 else v)
+        self.seeds.copy_(torch.tensor(vals, dtype=torch.int64))
+
+    def step(self, input_stack, output_image, lr_g=0.0002, lr_d=0.0002):
+        self.G.dropout_masks = self.inject_masks
+        self.G.dropout_seeds_dev = self.seeds
+        if self.inject_masks is None:
+            self._draw_seeds()
+        try:
+            return super().step(input_stack, output_image, lr_g=lr_g, lr_d=lr_d)
+        finally:
+            self.G.dropout_seeds_dev = None  # module-path calls (evaluation) keep drawing on the host
+
+    def _phase_d(self, input_stack, output_image, reducer=None):
+        G, D = self.G, self.D
+        B, C, H, W = input_stack.shape
+        synthetic, gtape = G.forward(input_stack)                                               # :615
+        fake = ActBuf(B, H, W, 16, zero=False)
+        real = ActBuf(B, H, W, 16, zero=False)
+        ops.pack_nchw(input_stack, fake, 0, zero_rest=True)                                     # torch.cat, :616-617
+        ops.pack_nchw(synthetic, fake, C)
+        ops.pack_nchw(input_stack, real, 0, zero_rest=True)
+        ops.pack_nchw(output_image, real, C)
+        # ---- discriminator update (:620-633): synthetic pass, then real pass (BatchNorm statistics per call)
+        lf, tf = D.forward_buf(fake)
+        lr_, tr_ = D.forward_buf(real)
+        dlf = ActBuf(B, lf.h, lf.w, 16, zero=False)
+        dlr = ActBuf(B, lr_.h, lr_.w, 16, zero=False)
+        ops.mse_const_loss(lf, 0.0, 1.0, 0.5, self.loss_buf[1:2], dlf)
+        ops.mse_const_loss(lr_, 1.0, 1.0, 0.5, self.loss_buf[0:1], dlr)
+        D.backward(tf, dlf, self.d_extra, need_dx=False)
+
+        D.backward(tr_, dlr, self.dp.grads, need_dx=False)
+        ops.add_f32(self.dp.grads.flat, self.d_extra_flat)
+        if reducer is not None:  # complete only after the sum of the two passes: one exchange, nothing to overlap with
+            reducer.start()
+            reducer.finish()
+        return synthetic, gtape, fake, output_image, C
+
+    def _phase_g(self, state, reducer=None):
+        G, D = self.G, self.D
+        synthetic, gtape, fake, output_image, C = state
+        B = synthetic.shape[0]
+        lg, tg = D.forward_buf(fake)                                                            # :637, updated D
+        dlg = ActBuf(B, lg.h, lg.w, 16, zero=False)
+        ops.mse_const_loss(lg, 1.0, 1.0, 1.0, self.loss_buf[2:3], dlg)
+        d_din = D.backward(tg, dlg, None, need_dx=True)
+        dout = torch.empty_like(synthetic)
+        ops.l1_loss(synthetic, output_image, self.l1_weight, 1.0, self.loss_buf[3:4], dpred=dout)
+        ops.unpack_nchw(d_din, dout, c0=C, accumulate=True)  # + the adversarial gradient w.r.t. the synthetic image
+        self._backward_reduced(G, reducer, lambda: G.backward(gtape, self.gp.grads, dout, need_dx=False))
 
 
 class _History:

@@ -352,7 +352,8 @@ class Model:
 
     def _ensure_native_paired(self):
         if self._native is None:
-            self._native = native_trainer.PairedTrainer(self.generator, self.discriminator, world_size=self._world())
+            cls = native_trainer.Pix2PixTrainer if self.model == "pix2pix" else native_trainer.PairedTrainer
+            self._native = cls(self.generator, self.discriminator, world_size=self._world())
             self._adopt_optimizer_state()
         return self._native
 
@@ -389,9 +390,10 @@ class Model:
             off += g.numel()
 
     def train_paired(self):
-        """Paired training (reference :598-658). PairedAttention runs the fused native step; Pix2Pix (BatchNorm with
-        batch statistics, dropout) steps through the drop-in modules' autograd path."""
-        if self.model != "pairedattention":
+        """Paired training (reference :598-658): the fused native step (fpgan.trainer.PairedTrainer for PairedAttention,
+        Pix2PixTrainer for Pix2Pix -- BatchNorm with batch statistics, dropout). FPG_PAIRED_MODULES=1 selects the
+        reference loop over the drop-in modules' autograd path instead (cross-check)."""
+        if os.environ.get("FPG_PAIRED_MODULES", "0") == "1":
             return self._train_paired_modules()
         tr = self._ensure_native_paired()
         for epoch in range(self.starting_epoch, self.num_epochs + 1):

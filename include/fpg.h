@@ -391,6 +391,10 @@ int fpg_batchnorm_running_update(const float* stats, int32_t c, int64_t count, f
 int fpg_maxpool2(const fpg_act* x, const fpg_act* y, void* stream);
 /* mask[i] = 1 with probability keep (counter-based hash of seed and i: reproducible), else 0 */
 int fpg_dropout_mask(uint8_t* mask, int64_t count, uint64_t seed, float keep, void* stream);
+/* the same with seed = *seed_dev + seed_add read on the device (constant launch arguments: a captured training step
+ * draws fresh masks on every replay) */
+int fpg_dropout_mask_dev(uint8_t* mask, int64_t count, const uint64_t* seed_dev, uint64_t seed_add, float keep,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Input pipeline -- models/utils.py:19-67 (apply_transformations), models/data.py:57-78 (FloodDataset.__getitem__).
@@ -490,6 +494,12 @@ int fpg_pack_nchw_split(const float* src, int32_t c_src, const fpg_act* dst, voi
  * NCHW tensor (the topography conditions input_stack[:, 3:] re-attached to every synthetic image, model.py:683-689). */
 int fpg_pack_nchw(const float* src, int32_t c_src, int32_t c_img, const fpg_act* dst, int32_t c0, int zero_rest,
                   void* stream);
+/* The three packed copies of a paired training batch in one pass (train_paired, model.py:615-617): x fp32 NCHW
+ * [n][c_x][h][w], y fp32 NCHW [n][c_y][h][w]  ->  gin (16-channel bf16, reflect halo: the generator input), fake and real
+ * (16-channel bf16, no halo: the discriminator inputs torch.cat((x, .), 1); fake gets channels [0, c_x), its image
+ * channels are written by fpg_blend_fwd; real gets x and y). Channels beyond the valid ones are 0. */
+int fpg_pack_paired_inputs(const float* x, int32_t c_x, const float* y, int32_t c_y, const fpg_act* gin,
+                           const fpg_act* fake, const fpg_act* real, void* stream);
 /* Backward through a fused tanh head (CycleGAN generator, model_architectures.py:115-116): dpre (bf16 NHWC) =
  * dout (fp32 NCHW [n][c_valid][h][w]) * (1 - out^2), out = the fp32 NHWC tanh output; channels >= c_valid are 0. */
 int fpg_tanh_bwd_pack(const float* dout_nchw, const fpg_act* out, int32_t c_valid, const fpg_act* dpre, void* stream);

@@ -377,6 +377,30 @@ def test_pack_unpack_bias_grad():
     torch.testing.assert_close(db, dy.to_nchw(27).sum((0, 2, 3)), rtol=1e-4, atol=1e-3)
 
 
+def test_pack_paired_inputs_matches_the_separate_packs():
+    """the one-pass packer of a paired batch (generator input with reflect halo + both discriminator inputs) against
+    torch and against the three pack_nchw calls it replaces (bit-exact)"""
+    from fpgan import ops
+    g = torch.Generator(device="cuda").manual_seed(23)
+    x = torch.rand(3, 9, 24, 40, device="cuda", generator=g) * 2 - 1
+    y = torch.rand(3, 3, 24, 40, device="cuda", generator=g) * 2 - 1
+    gin = ops.ActBuf(3, 24, 40, 16, halo=3, zero=False)
+    din = ops.ActBuf(6, 24, 40, 16, zero=False)
+    for b in (gin, din):
+        b.t.fill_(7.0)
+    fake, real = din.batch_slice(0, 3), din.batch_slice(3, 3)
+    ops.pack_paired_inputs(x, y, gin, fake, real)
+    ref = F.pad(x, (3,) * 4, "reflect")
+    assert torch.equal(gin.t[..., :9].permute(0, 3, 1, 2).float(), bf16r(ref)) and (gin.t[..., 9:] == 0).all()
+    assert torch.equal(fake.t[..., :9].permute(0, 3, 1, 2).float(), bf16r(x)) and (fake.t[..., 9:] == 0).all()
+    assert torch.equal(real.t[..., :12].permute(0, 3, 1, 2).float(), bf16r(torch.cat([x, y], 1)))
+    assert (real.t[..., 12:] == 0).all()
+    old = ops.ActBuf(3, 24, 40, 16, zero=False)
+    ops.pack_nchw(x, old, 0, zero_rest=True)
+    ops.pack_nchw(y, old, 9)
+    assert torch.equal(old.t, real.t)
+
+
 def test_flood_mask_bit_exact_and_confusion():
     """(sigmoid(x) > 0.5).float() -- model.py:399-400 -- bit-exact against the fp32 CPU expression, including the
     interval 0 < x < ~9e-8 where the fp32 sigmoid rounds to exactly 0.5."""

@@ -599,6 +599,81 @@ def test_pix2pix_forward_and_step_match_oracle():
     assert sum(agree) / len(agree) > 0.8
 
 
+def test_fused_pix2pix_step_matches_oracle_teacher_forced():
+    """Pix2PixTrainer (fused train_paired for the BatchNorm / dropout model, model.py:611-651) against the oracle's
+    fp32 step with identical dropout masks, TEACHER-FORCED: before every step the native trainer adopts the oracle's
+    weights, Adam moments and BatchNorm running statistics, so each of the five steps -- eager 0-1, the captured step 2,
+    graph replays afterwards -- checks one full iteration: the four losses (rtol 3e-2: BatchNorm over 4-64 values per
+    channel at the bottleneck with B=1 amplifies bf16 noise), the generated image, and the
+    BatchNorm running statistics after the step (three discriminator calls, one generator call)."""
+    from fpgan.trainer import Pix2PixTrainer
+    O, nets, G, D = _pix2pix_pair()
+    otr = O.PairedTrainer(nets, "pix2pix")
+    tr = Pix2PixTrainer(G, D)
+
+    def adopt(fp, module, params, adam):
+        plist = [v for k_, v in params.items() if v.is_floating_point() and v.dim() > 0 and "running_" not in k_]
+        assert len(plist) == len(fp.named)
+        for (name, p), src, m, v in zip(fp.named, plist, adam.m, adam.v):
+            off, k = fp.offsets[name]
+            assert p.shape == src.shape, name
+            fp.flat[off:off + k].copy_(src.detach().reshape(-1))
+            fp.m[off:off + k].copy_(m.reshape(-1))
+            fp.v[off:off + k].copy_(v.reshape(-1))
+        fp.steps = adam.t
+        sd = module.state_dict()
+        for k_, v_ in params.items():
+            if "running_" in k_ or "num_batches" in k_:
+                sd[k_].copy_(v_)
+
+    worst = 0.0
+    for step in range(5):
+        adopt(tr.gp, G, otr.G, otr.opt_g)
+        adopt(tr.dp, D, otr.D, otr.opt_d)
+        tr.G.repack(force=True)
+        tr.D.repack(force=True)
+        x, y = O.synthetic_batch(step, 1, 9, 256)
+        om, nm = _dropout_masks(1, 5)  # the same masks every step: under graph replay the injected buffers are baked in
+        if tr.inject_masks is None:
+            tr.inject_masks = nm
+        otr.g_forward = lambda p, inp: O.pix2pix_generator_forward(p, inp, masks=om)
+        ref = otr.step(x, y)
+        out = tr.step(x.cuda(), y.cuda())
+        got = tr.losses()
+        e = rel_rms(out, ref["synthetic"])
+        print(f"\n[parity] pix2pix fused step {step}: synthetic rel-rms err {e:.4f}; losses " +
+              ", ".join(f"{got[k]:.5f}/{ref[k]:.5f}" for k in tr.LOSS_KEYS))
+        assert e < 6e-2, e
+        for k in tr.LOSS_KEYS:
+            worst = max(worst, abs(got[k] - ref[k]) / (abs(ref[k]) + 1e-6))
+            assert abs(got[k] - ref[k]) <= 3e-2 * abs(ref[k]) + 1e-3, f"step {step} {k}: {got[k]} vs {ref[k]}"
+        for module, params in ((G, otr.G), (D, otr.D)):
+            sd = module.state_dict()
+            for k_, v_ in params.items():
+                if "running_" in k_:
+                    assert rel_rms(sd[k_], v_) < 2e-2, (step, k_)
+                if "num_batches" in k_:
+                    assert int(sd[k_]) == int(v_), (step, k_)
+    assert tr._graphs, "the step was never captured"
+    print(f"[parity] pix2pix fused: worst loss rel err over 5 teacher-forced steps {worst:.5f}")
+
+
+def test_fused_pix2pix_draws_new_dropout_masks_on_every_replay():
+    """the captured step reads its dropout seeds from device memory: two replays on the same batch from the same
+    weights give different images (fresh masks), the same torch seed gives the same image"""
+    from fpgan.trainer import Pix2PixTrainer
+    O, nets, G, D = _pix2pix_pair()
+    tr = Pix2PixTrainer(G, D)
+    x, y = (t.cuda() for t in O.synthetic_batch(0, 1, 9, 256))
+    outs = []
+    for step in range(5):
+        torch.manual_seed(100 + (step if step < 4 else 3))  # steps 3 and 4 share their seed
+        outs.append(tr.step(x, y, lr_g=0.0, lr_d=0.0).clone())  # lr 0: the weights stay what they are
+    assert tr._graphs
+    assert not torch.equal(outs[2], outs[3])
+    assert torch.equal(outs[3], outs[4])
+
+
 def test_model_api_pix2pix_train_paired_and_checkpoint(tmp_path):
     """`--model=Pix2Pix` through the public API: Model(...).train_paired() on synthetic 256x256 batches, losses stay
     in the reference's range (golden first-step losses of the unmodified reference; dropout masks differ: the
