@@ -341,4 +341,19 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// One Adam update (torch.optim.Adam without weight decay / amsgrad, model.py:119-122) in torch's operation order:
+// g * grad_scale; m.lerp_(g, 1 - beta1); v.mul_(beta2).addcmul_(g, g, value = 1 - beta2); denom = sqrt(v) / sqrt(bc2) +
+// eps; p -= step_size * m / denom. Written with explicitly rounded operations so that every kernel that contains it
+// (the flat Adam, the multi-source Adam of the peer exchange, the fused Adam + repack) produces bit-identical values
+// whatever multiply-add contraction the compiler would otherwise choose in each of them.
+__device__ __forceinline__ void adam_update_rn(float& p, float g, float& m, float& v, float w1, float beta2, float eps,
+                                               float step_size, float bc2_sqrt, float grad_scale) {
+  const float gr = __fmul_rn(g, grad_scale);
+  const float d = __fsub_rn(gr, m);
+  m = (w1 < 0.5f) ? __fadd_rn(m, __fmul_rn(w1, d)) : __fsub_rn(gr, __fmul_rn(d, __fsub_rn(1.f, w1)));
+  v = __fadd_rn(__fmul_rn(v, beta2), __fmul_rn(__fmul_rn(__fsub_rn(1.f, beta2), gr), gr));
+  const float denom = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), eps);
+  p = __fsub_rn(p, __fmul_rn(step_size, __fdiv_rn(m, denom)));
+}
+
 }  // namespace fpg

@@ -1635,6 +1635,34 @@ __global__ void pack_paired_inputs_kernel(const float* __restrict__ x, int cx, c
                      pack_bf16x2(f[14], f[15]));
 }
 
+// Space-to-depth copy of a 16-channel bf16 NHWC tensor for a 4x4 stride-2 pad-1 convolution (the PatchGAN stem,
+// model_architectures.py:424 / :68): block (by, bx) of the [n][h/2+1][w/2+1][64] destination holds the four pixels
+// (2by - 1 + i, 2bx - 1 + j), i, j in {0, 1}, as channels (2i + j) * 16 + c; pixels outside the image are the zero
+// padding. On that tensor the convolution is a 2x2 stride-1 one over 64 channels: 128-byte TMA rows and 4 taps instead
+// of 32-byte rows and 16 taps (the tiled kernel on the 16-channel tensor ran at the TMA row rate, 9 % tensor-active).
+// One thread per (block, sub-pixel): a 32-byte copy; consecutive threads write consecutive 32-byte pieces.
+__global__ void space_to_depth16_kernel(View src, __nv_bfloat16* __restrict__ dst, int hb, int wb) {
+  const int64_t total = static_cast<int64_t>(src.n) * hb * wb * 4;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int sub = static_cast<int>(idx & 3);
+  int64_t r = idx >> 2;
+  const int bx = static_cast<int>(r % wb);
+  r /= wb;
+  const int by = static_cast<int>(r % hb);
+  const int i = static_cast<int>(r / hb);
+  const int y = 2 * by - 1 + (sub >> 1), x = 2 * bx - 1 + (sub & 1);
+  uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+  if (y >= 0 && y < src.h && x >= 0 && x < src.w) {
+    const uint4* sp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(src.p) + src.at(i, y, x));
+    lo = sp[0];
+    hi = sp[1];
+  }
+  uint4* dp = reinterpret_cast<uint4*>(dst + idx * 16);
+  dp[0] = lo;
+  dp[1] = hi;
+}
+
 // bf16 NHWC (interior, channels [c0, c0+c_dst)) -> fp32 NCHW; one thread per pixel
 __global__ void unpack_nchw_kernel(View src, int src_fp32, int c0, float* __restrict__ dst, int c_dst, int accumulate) {
   const int64_t total = static_cast<int64_t>(src.n) * src.h * src.w;
@@ -1749,11 +1777,7 @@ __global__ void adam_prepare_kernel(int32_t* __restrict__ state, float beta1, fl
 }
 __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float w1, float beta2, float eps,
                                             float step_size, float bc2_sqrt, float grad_scale) {
-  const float gr = g * grad_scale;
-  m = (w1 < 0.5f) ? m + w1 * (gr - m) : gr - (gr - m) * (1.f - w1);  // torch.lerp(m, g, w1)
-  v = v * beta2 + (1.f - beta2) * gr * gr;
-  const float denom = sqrtf(v) / bc2_sqrt + eps;
-  p = p - step_size * (m / denom);
+  adam_update_rn(p, g, m, v, w1, beta2, eps, step_size, bc2_sqrt, grad_scale);  // common.cuh
 }
 // 16-byte accesses (the four flat buffers are 16-byte aligned torch allocations): 28 B/parameter of traffic
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -2211,6 +2235,22 @@ int fpg_pack_paired_inputs(const float* x, int32_t c_x, const float* y, int32_t 
   const int64_t total = static_cast<int64_t>(gin->n) * (gin->h + 2 * gin->halo) * (gin->w + 2 * gin->halo);
   pack_paired_inputs_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(x, c_x, y, c_y, view_of(gin), view_of(fake),
                                                                               view_of(real));
+  FPG_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int fpg_space_to_depth16(const fpg_act* src, const fpg_act* dst, void* stream) {
+  FPG_REQUIRE(src && dst && src->c == 16 && src->c_stride == 16 && src->fp32 == FPG_DT_BF16 && src->h % 2 == 0 &&
+                  src->w % 2 == 0 && (reinterpret_cast<uintptr_t>(src->data) & 15) == 0,
+              "source: a 16-channel bf16 tensor of even extent");
+  FPG_REQUIRE(dst->n == src->n && dst->h == src->h / 2 + 1 && dst->w == src->w / 2 + 1 && dst->c == 64 &&
+                  dst->c_stride == 64 && dst->halo == 0 && dst->fp32 == FPG_DT_BF16 &&
+                  (reinterpret_cast<uintptr_t>(dst->data) & 15) == 0,
+              "destination: [n][h/2+1][w/2+1][64] bf16");
+  const int64_t total = static_cast<int64_t>(dst->n) * dst->h * dst->w * 4;
+  space_to_depth16_kernel<<<grid_for(total, 256), 256, 0, FPG_ST(stream)>>>(view_of(src),
+                                                                            static_cast<__nv_bfloat16*>(dst->data), dst->h,
+                                                                            dst->w);
   FPG_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

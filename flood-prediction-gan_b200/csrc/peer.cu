@@ -12,6 +12,7 @@
 // words per rank (written by the peers with system-scope release stores, polled locally): "data of step s has landed"
 // and "I have consumed step s" (the staging slot may be overwritten). Flag values are step counters read from device
 // memory, so every launch has constant arguments and the whole step replays as a CUDA graph.
+#include "common.cuh"
 #include "host_util.h"
 
 using namespace fpg;
@@ -93,11 +94,7 @@ __global__ void __launch_bounds__(256) peer_push_kernel(const uint4* __restrict_
 
 __device__ __forceinline__ void adam_update(float& p, float g, float& m, float& v, float w1, float beta2, float eps,
                                             float step_size, float bc2_sqrt, float grad_scale) {
-  const float gr = g * grad_scale;
-  m = (w1 < 0.5f) ? m + w1 * (gr - m) : gr - (gr - m) * (1.f - w1);  // torch.lerp(m, g, w1)
-  v = v * beta2 + (1.f - beta2) * gr * gr;
-  const float denom = sqrtf(v) / bc2_sqrt + eps;
-  p = p - step_size * (m / denom);
+  adam_update_rn(p, g, m, v, w1, beta2, eps, step_size, bc2_sqrt, grad_scale);  // common.cuh
 }
 
 // streaming (evict-first) coherent load: gsum_out may alias the local source

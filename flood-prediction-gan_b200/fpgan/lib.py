@@ -70,6 +70,15 @@ class WgradDesc(C.Structure):
                 ("x_tap_rs", C.c_int16 * FPG_MAX_TAPS), ("y_tap_rs", C.c_int16 * FPG_MAX_TAPS)]
 
 
+class AdamPackLayer(C.Structure):
+    _fields_ = [("p_off", C.c_int64), ("k", C.c_int32), ("c", C.c_int32), ("rs", C.c_int32), ("tk", C.c_int32),
+                ("tc", C.c_int32), ("n_jobs", C.c_int32), ("job", C.c_int32 * 8)]
+
+
+class AdamPackChunk(C.Structure):
+    _fields_ = [("off", C.c_int64), ("copy_dst", C.c_void_p), ("count", C.c_int32), ("pad_", C.c_int32)]
+
+
 class Act(C.Structure):
     """fpg_act: NHWC activation buffer descriptor."""
     _fields_ = [("data", C.c_void_p), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
@@ -152,12 +161,16 @@ SIGNATURES = {
     "fpg_l1_loss": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _f32, _f32, _vp, _vp, C.c_int, _vp, _vp]),
     "fpg_pack_nchw": (C.c_int, [_vp, _i32, _i32, _P(Act), _i32, C.c_int, _vp]),
     "fpg_pack_paired_inputs": (C.c_int, [_vp, _i32, _vp, _i32, _P(Act), _P(Act), _P(Act), _vp]),
+    "fpg_space_to_depth16": (C.c_int, [_P(Act), _P(Act), _vp]),
     "fpg_add_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
     "fpg_history_exchange": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "fpg_unpack_nchw": (C.c_int, [_P(Act), _i32, _vp, _i32, C.c_int, _vp]),
     "fpg_tanh_bwd_pack": (C.c_int, [_vp, _P(Act), _i32, _P(Act), _vp]),
     "fpg_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _f32, _vp]),
     "fpg_adam_step_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp, _f32, _vp]),
+    "fpg_adam_pack_tile": (C.c_int, [_i32, _P(_i32), _P(_i32)]),
+    "fpg_adam_pack_step": (C.c_int, [_vp, _P(_vp), _i32, _vp, _vp, _f32, _f32, _f32, _vp, _f32, _vp, _vp, _vp, _vp, _vp,
+                                     _vp, _i32, _vp]),
     "fpg_adam_prepare_dev": (C.c_int, [_vp, _f32, _f32, _vp]),
     "fpg_peer_alloc": (C.c_int, [_P(_vp), _i64]),
     "fpg_peer_free": (C.c_int, [_vp]),

@@ -38,10 +38,27 @@ class ConvLayer:
         self.k_valid, self.c_valid = k, c
         self.spec = ConvSpec(r, r, stride, pad, pad16(c), pad16(k), c_in_valid=c, c_out_valid=k)
         self.bias_pad = None
+        self.s2d_spec = None  # _NetBase._add_s2d_stem: the same layer as a 2x2 stride-1 conv over a space-to-depth input
 
     def version(self):
         return (self.weight._version, self.weight.data_ptr(),
                 self.bias._version if self.use_bias else 0, self.bias.data_ptr() if self.use_bias else 0)
+
+
+def _s2d_job(layer, fprop_job):
+    """pack job of the space-to-depth operand of a 4x4 stride-2 stem: [k][(ty, tx)][(i, j, c16)] bf16 -- the ordinary
+    fprop operand [k][r * 4 + s][c16] with its taps permuted (r = 2 ty + i, s = 2 tx + j)"""
+    sp = layer.s2d_spec
+    if sp.w_fprop is None:
+        nbytes = L.load().fpg_packed_weight_bytes(sp.gref())
+        assert nbytes == 2 * fprop_job.rows * fprop_job.taps * fprop_job.cols and fprop_job.taps == 16
+        sp.w_fprop = torch.zeros(nbytes // 2, dtype=torch.bfloat16, device=layer.weight.device)
+    job = _copy_job(fprop_job)
+    job.dst = sp.w_fprop.data_ptr()
+    for t in range(16):
+        ty, tx, i, j = t >> 3, (t >> 2) & 1, (t >> 1) & 1, t & 1
+        job.src_tap[t] = (2 * ty + i) * 4 + 2 * tx + j
+    return job
 
 
 class _PackTable:
@@ -62,6 +79,8 @@ class _PackTable:
             L.call("fpg_pack_jobs", C.c_void_p(w.data_ptr()), sp.c_in_valid * rs, rs, sp.c_out_valid, sp.c_in_valid,
                    sp.gref(), C.c_void_p(sp.w_fprop.data_ptr()), C.c_void_p(sp.w_dgrad.data_ptr()), buf, C.byref(n))
             jobs.extend(_copy_job(buf[i]) for i in range(n.value))
+            if layer.s2d_spec is not None:
+                jobs.append(_s2d_job(layer, buf[0]))
             if layer.use_bias:
                 npad = sp.g.c_in if layer.transposed else sp.g.c_out
                 if layer.bias_pad is None:
@@ -85,6 +104,109 @@ class _PackTable:
 
     def run(self):
         ops.pack_weights_batched(self.jobs, self.block_job, self.block_first, self.n_blocks)
+
+
+class AdamPack:
+    """Adam + the repack of every bf16 GEMM operand of the networks of one optimiser in ONE launch
+    (fpg_adam_pack_step, csrc/adam_pack.cu): convolution weights are updated tile by tile and written straight into their
+    fprop / data-gradient operand layouts from shared memory; every other parameter (and the zero-padded bias vectors the
+    epilogues read) by chunk blocks of the same launch. `fp` is a trainer.FlatParams over the modules that `executors`
+    run; the operands are packed once here the old way so that their padding is in place."""
+
+    CHUNK = 4096
+
+    def __init__(self, fp, executors):
+        lib = L.load()
+        self.fp = fp
+        for ex in executors:
+            ex.repack(force=True)
+        base, total = fp.flat.data_ptr(), fp.flat.numel()
+        dev = fp.flat.device
+        jobs, layers, covered, biases = [], [], [], []
+        for ex in executors:
+            for layer in ex.layers.values():
+                w = layer.weight
+                off = (w.data_ptr() - base) // 4
+                assert 0 <= off and off + w.numel() <= total, "the executor's parameters do not live in this flat buffer"
+                sp = layer.spec
+                rs = sp.g.r * sp.g.s
+                assert w.numel() == sp.c_out_valid * sp.c_in_valid * rs
+                buf = (L.PackJob * 5)()
+                n = C.c_int32()
+                L.call("fpg_pack_jobs", C.c_void_p(w.data_ptr()), sp.c_in_valid * rs, rs, sp.c_out_valid, sp.c_in_valid,
+                       sp.gref(), C.c_void_p(sp.w_fprop.data_ptr()), C.c_void_p(sp.w_dgrad.data_ptr()), buf, C.byref(n))
+                tk, tc = C.c_int32(), C.c_int32()
+                L.call("fpg_adam_pack_tile", rs, C.byref(tk), C.byref(tc))
+                lay = L.AdamPackLayer()
+                lay.p_off, lay.k, lay.c, lay.rs = off, sp.c_out_valid, sp.c_in_valid, rs
+                lay.tk, lay.tc, lay.n_jobs = tk.value, tc.value, n.value
+                for i in range(n.value):
+                    lay.job[i] = len(jobs)
+                    jobs.append(_copy_job(buf[i]))
+                if layer.s2d_spec is not None:
+                    lay.job[lay.n_jobs] = len(jobs)
+                    lay.n_jobs += 1
+                    jobs.append(_s2d_job(layer, buf[0]))
+                layers.append(lay)
+                covered.append((off, off + w.numel()))
+                if layer.use_bias:
+                    boff = (layer.bias.data_ptr() - base) // 4
+                    assert 0 <= boff and boff + layer.bias.numel() <= total and layer.bias_pad is not None
+                    biases.append((boff, boff + layer.bias.numel(), layer.bias_pad.data_ptr()))
+        chunks = []
+        for a, b in self._gaps(sorted(covered), total):
+            cuts = sorted({a, b} | {x for lo, hi, _ in biases for x in (lo, hi) if a < x < b})
+            for x, y in zip(cuts, cuts[1:]):
+                dst = next((ptr + 4 * (x - lo) for lo, hi, ptr in biases if lo <= x and y <= hi), None)
+                for o in range(x, y, self.CHUNK):
+                    ch = L.AdamPackChunk()
+                    ch.off, ch.count = o, min(self.CHUNK, y - o)
+                    ch.copy_dst = dst + 4 * (o - x) if dst is not None else None
+                    chunks.append(ch)
+        item, first = [], []
+        for i, lay in enumerate(layers):
+            nt = -(-lay.k // lay.tk) * -(-lay.c // lay.tc)
+            item.extend([i] * nt)
+            first.extend(range(nt))
+        for i in range(len(chunks)):
+            item.append(-1 - i)
+            first.append(0)
+        self.n_params_tiled = sum(b - a for a, b in covered)
+
+        def to_dev(arr_type, items):
+            if not items:
+                return torch.zeros(8, dtype=torch.uint8, device=dev)
+            arr = (arr_type * len(items))(*items)
+            return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+
+        self.layers = to_dev(L.AdamPackLayer, layers)
+        self.jobs = to_dev(L.PackJob, jobs)
+        self.chunks = to_dev(L.AdamPackChunk, chunks)
+        self.block_item = torch.tensor(item, dtype=torch.int32, device=dev)
+        self.block_first = torch.tensor(first, dtype=torch.int32, device=dev)
+        self.n_blocks = len(item)
+        self._own = (C.c_void_p * 1)(fp.grads.flat.data_ptr())
+
+    @staticmethod
+    def _gaps(covered, total):
+        pos = 0
+        for a, b in covered:
+            assert a >= pos, "overlapping parameters"
+            if a > pos:
+                yield pos, a
+            pos = b
+        if pos < total:
+            yield pos, total
+
+    def run(self, grad_scale=1.0, sources=None, n_src=1, gsum=None, betas=(0.5, 0.999), eps=1e-8):
+        """one optimiser step on the gradient fp.grads.flat (or the rank-ordered sum of `sources`, a ctypes array of
+        n_src device pointers), operands repacked"""
+        fp = self.fp
+        ops._run("adam_step", 2, "fpg_adam_pack_step", ops._ptr(fp.flat), sources if sources is not None else self._own,
+                 n_src, ops._ptr(fp.m), ops._ptr(fp.v), float(betas[0]), float(betas[1]), float(eps), ops._ptr(fp.state),
+                 float(grad_scale), ops._ptr(gsum) if gsum is not None else None, ops._ptr(self.layers),
+                 ops._ptr(self.jobs), ops._ptr(self.chunks), ops._ptr(self.block_item), ops._ptr(self.block_first),
+                 self.n_blocks, ops._stream())
 
 
 def _copy_job(job):
@@ -146,6 +268,34 @@ class _NetBase:
         layer = ConvLayer(name, conv_module.weight, conv_module.bias, r, stride, pad, transposed, use_bias)
         self.layers[name] = layer
         return layer
+
+    def _add_s2d_stem(self, name):
+        """EXPERIMENT (FPG_S2D_STEM=1, off by default): the 4x4 stride-2 pad-1 layer `name` over a 16-channel input (the
+        PatchGAN stem) ALSO as a 2x2 stride-1 convolution over the space-to-depth copy of its input
+        (ops.space_to_depth16): 128-byte TMA rows and 4 taps instead of 32-byte rows and 16 taps. Forward only; the
+        gradients keep the ordinary formulation. Parity-green, but measured NOT faster (tools/micro_s2d.py, B=32:
+        strided 102 us; copy 27 us + 2x2 kernel 98 us tiled / 145 us row-stationary): the layer is bound by the
+        L2 -> SM path (402 MB through the crossbar for a 67 MB input: every tile re-fetches the 32 KB of weights and
+        every input pixel is fetched by 4 taps, ncu r02_m0_fprop), not by the TMA row rate, and the space-to-depth form
+        moves the same bytes."""
+        layer = self.layers[name]
+        g = layer.spec.g
+        assert (g.r, g.s, g.stride, g.pad, g.c_in) == (4, 4, 2, 1, 16) and not layer.transposed
+        if os.environ.get("FPG_S2D_STEM", "0") == "1":
+            layer.s2d_spec = ConvSpec(2, 2, 1, 0, 64, g.c_out, c_in_valid=64, c_out_valid=layer.spec.c_out_valid)
+
+    def _stem_conv(self, din, name, act, xs=None):
+        """forward of a stem registered with _add_s2d_stem -> (output, space-to-depth copy of din or None); `xs`: that
+        copy when the caller already has it (the same discriminator input is used twice per training step)"""
+        layer = self.layers[name]
+        if layer.s2d_spec is None or din.h % 2 or din.w % 2 or din.halo or din.c_stride != 16:
+            return self._conv(din, name, act=act), None
+        if xs is None:
+            xs = ActBuf(din.n, din.h // 2 + 1, din.w // 2 + 1, 64, zero=False)
+            ops.space_to_depth16(din, xs)
+        y = ActBuf(din.n, din.h // 2, din.w // 2, layer.spec.g.c_out, zero=False)
+        ops.conv_fprop(xs, layer.s2d_spec, y, bias=layer.bias_pad if layer.use_bias else None, act=act)
+        return y, xs
 
     def repack(self, force=False):
         """Rebuild the bf16 GEMM operands if any fp32 parameter changed since the last call (one launch)."""
@@ -501,12 +651,14 @@ class PatchGANNet(_NetBase):
         self._add("model.5", seq[5], 4, 2, 1)
         self._add("model.8", seq[8], 4, 1, 1)
         self._add("model.11", seq[11], 4, 1, 1, use_bias=True)
+        self._add_s2d_stem("model.0")
 
-    def forward_buf(self, din):
-        """din: ActBuf [B, H, W, 16] (D input, channels beyond the real ones zero). Returns (logits ActBuf fp32, tape)."""
+    def forward_buf(self, din, xs=None):
+        """din: ActBuf [B, H, W, 16] (D input, channels beyond the real ones zero); xs: its space-to-depth copy if the
+        caller kept it from an earlier pass (tape["din_s2d"]). Returns (logits ActBuf fp32, tape)."""
         self.repack()
         t = {"din": din}
-        t["a1"] = self._conv(din, "model.0", act=ACT_LEAKY)
+        t["a1"], t["din_s2d"] = self._stem_conv(din, "model.0", ACT_LEAKY, xs)
         t["y2"], t["s2"], t["a2"] = self._conv_in(t["a1"], "model.2", ACT_LEAKY, 0)
         t["y3"], t["s3"], t["a3"] = self._conv_in(t["a2"], "model.5", ACT_LEAKY, 0)
         t["y4"], t["s4"], t["a4"] = self._conv_in(t["a3"], "model.8", ACT_LEAKY, 0)
@@ -720,12 +872,14 @@ class PatchGANBatchNormNet(_NetBase, _BatchNormMixin):
         self._add("model.8", seq[8], 4, 1, 1)
         self._add("model.11", seq[11], 4, 1, 1, use_bias=True)
         self.norms = {"model.3": seq[3], "model.6": seq[6], "model.9": seq[9]}
+        self._add_s2d_stem("model.0")
 
-    def forward_buf(self, din):
-        """din: ActBuf [B, H, W, 16] (channels beyond the real ones zero). Returns (logits ActBuf fp32, tape)."""
+    def forward_buf(self, din, xs=None):
+        """din: ActBuf [B, H, W, 16] (channels beyond the real ones zero); xs: its space-to-depth copy if the caller
+        kept it (tape["din_s2d"]). Returns (logits ActBuf fp32, tape)."""
         self.repack()
         t = {"din": din}
-        t["a1"] = self._conv(din, "model.0", act=ACT_LEAKY)
+        t["a1"], t["din_s2d"] = self._stem_conv(din, "model.0", ACT_LEAKY, xs)
         cur = t["a1"]
         for i, (conv, norm) in enumerate((("model.2", "model.3"), ("model.5", "model.6"), ("model.8", "model.9")), 2):
             y = self._conv(cur, conv)

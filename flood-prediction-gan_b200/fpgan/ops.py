@@ -496,6 +496,11 @@ def pack_paired_inputs(x, y, gin, fake, real):
          real.ref(), _stream())
 
 
+def space_to_depth16(src, dst):
+    """16-channel bf16 [n, h, w, 16] -> [n, h/2+1, w/2+1, 64] (fpg_space_to_depth16): the PatchGAN stem's input"""
+    _run("space_to_depth", 1, "fpg_space_to_depth16", src.ref(), dst.ref(), _stream())
+
+
 def add_f32(dst, src):
     """dst += src (flat fp32 gradient buffers)"""
     assert dst.dtype == src.dtype == torch.float32 and dst.numel() == src.numel()

@@ -227,13 +227,17 @@ class PeerReducer:
         """milliseconds this rank's stream has spent in the flag waits so far (device-side clock; one host sync)"""
         return self.status[1].item() / 1e6
 
-    def adam(self, grad_scale, betas=(0.5, 0.999), eps=1e-8):
-        """Adam on the rank-ordered sum of the W gradient sources, then release the staging slots to the peers"""
+    def adam(self, grad_scale, betas=(0.5, 0.999), eps=1e-8, fused=None):
+        """Adam on the rank-ordered sum of the W gradient sources (with `fused`, a networks.AdamPack: in the same launch
+        as the operand repack), then release the staging slots to the peers"""
         fp = self.fp
-        gsum = ops._ptr(fp.grads.flat) if self.keep_sum else None
-        ops._run("adam_step", 2, "fpg_adam_step_dev_multi", ops._ptr(fp.flat), self._sources, self.world, ops._ptr(fp.m),
-                 ops._ptr(fp.v), fp.flat.numel(), float(betas[0]), float(betas[1]), float(eps), ops._ptr(fp.state),
-                 float(grad_scale), gsum, ops._stream())
+        gsum = fp.grads.flat if self.keep_sum else None
+        if fused is not None:
+            fused.run(grad_scale, sources=self._sources, n_src=self.world, gsum=gsum, betas=betas, eps=eps)
+        else:
+            ops._run("adam_step", 2, "fpg_adam_step_dev_multi", ops._ptr(fp.flat), self._sources, self.world,
+                     ops._ptr(fp.m), ops._ptr(fp.v), fp.flat.numel(), float(betas[0]), float(betas[1]), float(eps),
+                     ops._ptr(fp.state), float(grad_scale), ops._ptr(gsum) if gsum is not None else None, ops._stream())
         ops._run("peer_signal", 1, "fpg_peer_signal", self._ack_ptrs, len(self.peers), ops._ptr(self.ctr), 1, 1,
                  ops._stream())
 

@@ -144,11 +144,28 @@ class _BucketReducer:
             w.wait()
         self.works = []
 
-    def adam(self, grad_scale, betas=(0.5, 0.999), eps=1e-8):
-        self.fp.adam(grad_scale=grad_scale, betas=betas, eps=eps)
+    def adam(self, grad_scale, betas=(0.5, 0.999), eps=1e-8, fused=None):
+        if fused is not None:
+            fused.run(grad_scale, betas=betas, eps=eps)
+        else:
+            self.fp.adam(grad_scale=grad_scale, betas=betas, eps=eps)
 
     def close(self):
         pass
+
+
+def optimiser_step(fp, reducer, fused, nets, grad_scale):
+    """Adam on `fp` (through the data-parallel reducer when there is one) + the bf16 operands of `nets` rebuilt: one
+    launch with `fused` (networks.AdamPack), else the update followed by the batched repack."""
+    if reducer is not None:
+        reducer.adam(grad_scale, fused=fused)
+    elif fused is not None:
+        fused.run(grad_scale)
+    else:
+        fp.adam(grad_scale=grad_scale)
+    if fused is None:
+        for net in nets:
+            net.repack(force=True)
 
 
 def make_reducers(world_size, group, *flat_params, overlappable=True):
@@ -183,6 +200,10 @@ class PairedTrainer:
         dev = self.gp.flat.device
         self.loss_buf = torch.zeros(4, dtype=torch.float32, device=dev)
         self.g_reducer, self.d_reducer = make_reducers(world_size, group, self.gp, self.dp)
+        # FPG_ADAM_PACK=0: Adam and the operand repack as two launches (cross-check of the fused kernel)
+        fuse = os.environ.get("FPG_ADAM_PACK", "1") != "0"
+        self.g_fused = networks.AdamPack(self.gp, [self.G]) if fuse else None
+        self.d_fused = networks.AdamPack(self.dp, [self.D]) if fuse else None
         self.launches = 0
         # CUDA-graph replay of the whole step (341 launches, the NCCL gradient reductions included): removes host
         # launch overhead and inter-kernel gaps (measured 5-6 % of the step). Captured NCCL work must be released before
@@ -287,15 +308,16 @@ class PairedTrainer:
         ops.mse_const_loss(logits.batch_slice(0, B), 0.0, 1.0, 0.5, self.loss_buf[1:2], dlog.batch_slice(0, B))
         ops.mse_const_loss(logits.batch_slice(B, B), 1.0, 1.0, 0.5, self.loss_buf[0:1], dlog.batch_slice(B, B))
         self._backward_reduced(D, reducer, lambda: D.backward(dtape, dlog, self.dp.grads, need_dx=False))
-        return synthetic, gtape, fake, output_image, C
+        xs = dtape.get("din_s2d")  # space-to-depth copy of [synthetic | real]: its first half serves the generator phase
+        return synthetic, gtape, fake, output_image, C, xs.batch_slice(0, B) if xs is not None else None
 
     def _phase_g(self, state, reducer=None):
         """generator update terms (:636-645) through the UPDATED discriminator: leaves the generator gradients of
         this batch in self.gp.grads"""
         G, D = self.G, self.D
-        synthetic, gtape, fake, output_image, C = state
+        synthetic, gtape, fake, output_image, C, xs_fake = state
         B = synthetic.shape[0]
-        logits_g, dtape_g = D.forward_buf(fake)
+        logits_g, dtape_g = D.forward_buf(fake, xs_fake)
         dlog_g = ActBuf(B, logits_g.h, logits_g.w, 16, zero=False)
         ops.mse_const_loss(logits_g, 1.0, 1.0, 1.0, self.loss_buf[2:3], dlog_g)
         d_din = D.backward(dtape_g, dlog_g, None, need_dx=True)
@@ -307,11 +329,9 @@ class PairedTrainer:
     def _step_impl(self, input_stack, output_image):
         inv_w = 1.0 / self.world_size
         state = self._phase_d(input_stack, output_image, self.d_reducer)
-        (self.d_reducer or self.dp).adam(grad_scale=inv_w)
-        self._force_repack(self.D)
+        optimiser_step(self.dp, self.d_reducer, self.d_fused, [self.D], inv_w)
         self._phase_g(state, self.g_reducer)
-        (self.g_reducer or self.gp).adam(grad_scale=inv_w)
-        self._force_repack(self.G)
+        optimiser_step(self.gp, self.g_reducer, self.g_fused, [self.G], inv_w)
         return state[0]
 
     def step_accumulated(self, shards, lr_g=0.0002, lr_d=0.0002):
@@ -331,16 +351,14 @@ class PairedTrainer:
             ops.add_f32(dsum, self.dp.grads.flat)
             loss_sum[0:2] += self.loss_buf[0:2]
         self.dp.grads.flat.copy_(dsum)
-        self.dp.adam(grad_scale=1.0 / n)
-        self._force_repack(self.D)
+        optimiser_step(self.dp, None, self.d_fused, [self.D], 1.0 / n)
         gsum = torch.zeros_like(self.gp.grads.flat)
         for st in states:
             self._phase_g(st)
             ops.add_f32(gsum, self.gp.grads.flat)
             loss_sum[2:4] += self.loss_buf[2:4]
         self.gp.grads.flat.copy_(gsum)
-        self.gp.adam(grad_scale=1.0 / n)
-        self._force_repack(self.G)
+        optimiser_step(self.gp, None, self.g_fused, [self.G], 1.0 / n)
         self.loss_buf.copy_(loss_sum / n)
         self.gp.note_step()
         self.dp.note_step()
@@ -416,13 +434,13 @@ class Pix2PixTrainer(PairedTrainer):
         if reducer is not None:  # complete only after the sum of the two passes: one exchange, nothing to overlap with
             reducer.start()
             reducer.finish()
-        return synthetic, gtape, fake, output_image, C
+        return synthetic, gtape, fake, output_image, C, tf.get("din_s2d")
 
     def _phase_g(self, state, reducer=None):
         G, D = self.G, self.D
-        synthetic, gtape, fake, output_image, C = state
+        synthetic, gtape, fake, output_image, C, xs_fake = state
         B = synthetic.shape[0]
-        lg, tg = D.forward_buf(fake)                                                            # :637, updated D
+        lg, tg = D.forward_buf(fake, xs_fake)                                                   # :637, updated D
         dlg = ActBuf(B, lg.h, lg.w, 16, zero=False)
         ops.mse_const_loss(lg, 1.0, 1.0, 1.0, self.loss_buf[2:3], dlg)
         d_din = D.backward(tg, dlg, None, need_dx=True)
@@ -476,6 +494,9 @@ class CycleTrainer:
         self.g_extra = [self.gp.extra_grads() for _ in range(2 if add_identity_loss else 1)]
         self.world_size, self.group = world_size, group
         self.g_reducer, self.d_reducer = make_reducers(world_size, group, self.gp, self.dp, overlappable=False)
+        fuse = os.environ.get("FPG_ADAM_PACK", "1") != "0"
+        self.g_fused = networks.AdamPack(self.gp, [self.Gpp, self.Gpr]) if fuse else None
+        self.d_fused = networks.AdamPack(self.dp, [self.Dpost, self.Dpre]) if fuse else None
         self.loss_keys = self.LOSS_KEYS + (self.IDENTITY_KEYS if add_identity_loss else ())
         dev = self.gp.flat.device
         self.loss_buf = torch.zeros(len(self.loss_keys), dtype=torch.float32, device=dev)
@@ -565,16 +586,12 @@ class CycleTrainer:
         if self.g_reducer is not None:
             self.g_reducer.start()
             self.g_reducer.finish()
-        (self.g_reducer or self.gp).adam(grad_scale=inv_w)
-        self.Gpp.repack(force=True)
-        self.Gpr.repack(force=True)
+        optimiser_step(self.gp, self.g_reducer, self.g_fused, [self.Gpp, self.Gpr], inv_w)
         self._phase_d(state)
         if self.d_reducer is not None:
             self.d_reducer.start()
             self.d_reducer.finish()
-        (self.d_reducer or self.dp).adam(grad_scale=inv_w)
-        self.Dpre.repack(force=True)
-        self.Dpost.repack(force=True)
+        optimiser_step(self.dp, self.d_reducer, self.d_fused, [self.Dpre, self.Dpost], inv_w)
         return state[0], state[1]
 
     def step_accumulated(self, shards, lr_g=0.0002, lr_d=0.0002):
@@ -596,18 +613,14 @@ class CycleTrainer:
             ops.add_f32(gsum, self.gp.grads.flat)
             loss_sum[g_keys] += self.loss_buf[g_keys]
         self.gp.grads.flat.copy_(gsum)
-        self.gp.adam(grad_scale=1.0 / n)
-        self.Gpp.repack(force=True)
-        self.Gpr.repack(force=True)
+        optimiser_step(self.gp, None, self.g_fused, [self.Gpp, self.Gpr], 1.0 / n)
         dsum = torch.zeros_like(self.dp.grads.flat)
         for st in states:
             self._phase_d(st)
             ops.add_f32(dsum, self.dp.grads.flat)
             loss_sum[4:8] += self.loss_buf[4:8]
         self.dp.grads.flat.copy_(dsum)
-        self.dp.adam(grad_scale=1.0 / n)
-        self.Dpre.repack(force=True)
-        self.Dpost.repack(force=True)
+        optimiser_step(self.dp, None, self.d_fused, [self.Dpre, self.Dpost], 1.0 / n)
         self.loss_buf.copy_(loss_sum / n)
         self.gp.note_step()
         self.dp.note_step()

@@ -500,6 +500,11 @@ int fpg_pack_nchw(const float* src, int32_t c_src, int32_t c_img, const fpg_act*
  * channels are written by fpg_blend_fwd; real gets x and y). Channels beyond the valid ones are 0. */
 int fpg_pack_paired_inputs(const float* x, int32_t c_x, const float* y, int32_t c_y, const fpg_act* gin,
                            const fpg_act* fake, const fpg_act* real, void* stream);
+/* Space-to-depth copy for a 4x4 stride-2 pad-1 convolution over a 16-channel tensor (PatchGAN model.0,
+ * model_architectures.py:424): dst [n][h/2+1][w/2+1][64] bf16, block (by, bx) = pixels (2by-1+i, 2bx-1+j) of src as
+ * channels (2i+j)*16 + c, zeros outside the image. The convolution then is 2x2 stride-1 pad-0 over 64 channels with
+ * weights W2[k][ty][tx][(2i+j)*16 + c] = W[k][c][2ty+i][2tx+j] (a tap permutation of the ordinary fprop operand). */
+int fpg_space_to_depth16(const fpg_act* src, const fpg_act* dst, void* stream);
 /* Backward through a fused tanh head (CycleGAN generator, model_architectures.py:115-116): dpre (bf16 NHWC) =
  * dout (fp32 NCHW [n][c_valid][h][w]) * (1 - out^2), out = the fp32 NHWC tanh output; channels >= c_valid are 0. */
 int fpg_tanh_bwd_pack(const float* dout_nchw, const fpg_act* out, int32_t c_valid, const fpg_act* dpre, void* stream);
@@ -519,6 +524,38 @@ int fpg_adam_step(float* p, const float* g, float* m, float* v, int64_t count, f
  *   state: int32[4] = {step (incremented by this call), lr as float bits, scratch, scratch}. */
 int fpg_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t count, float beta1, float beta2, float eps,
                       int32_t* state, float grad_scale, void* stream);
+
+/* Adam AND the repack of the bf16 GEMM operands in one launch (csrc/adam_pack.cu): replaces fpg_adam_step_dev followed
+ * by fpg_pack_weights_batched after every optimiser step (model.py:633,646). The flat buffers p / m / v / gradient
+ * source(s) hold every parameter of one optimiser; tables in device memory describe them:
+ *   layers[i]  a convolution weight [k][c][rs] at element offset p_off of the flat buffers, cut into tiles of tk x tc
+ *              (k, c) pairs (fpg_adam_pack_tile gives the tile for a tap count); job[0..n_jobs <= 8) index `jobs`: the
+ *              fpg_pack_job descriptors of its operands as built by fpg_pack_jobs (their `src` is not used). Padding
+ *              rows / taps / columns of the operands are NOT rewritten: pack once with fpg_pack_weights_batched first;
+ *   chunks[i]  count <= 4096 other parameters at element offset off; copy_dst (optional) receives the new values
+ *              (the zero-padded fp32 bias vector of a layer whose epilogue adds a bias);
+ *   block b    works on tile block_first[b] of layer block_item[b] (>= 0), or on chunk -1 - block_item[b].
+ * grads_host: n_src <= 16 device pointers, summed in that order (data-parallel peer exchange); gsum_out (optional,
+ * may alias a source) receives the sum. state as in fpg_adam_step_dev. */
+typedef struct {
+  int64_t p_off;
+  int32_t k, c, rs;
+  int32_t tk, tc;
+  int32_t n_jobs;
+  int32_t job[8];
+} fpg_adam_pack_layer;
+typedef struct {
+  int64_t off;
+  float* copy_dst;
+  int32_t count;
+  int32_t pad_;
+} fpg_adam_pack_chunk;
+int fpg_adam_pack_tile(int32_t rs, int32_t* tk, int32_t* tc);
+int fpg_adam_pack_step(float* p, const void* const* grads_host, int32_t n_src, float* m, float* v, float beta1,
+                       float beta2, float eps, int32_t* state, float grad_scale, float* gsum_out,
+                       const fpg_adam_pack_layer* layers_dev, const fpg_pack_job* jobs_dev,
+                       const fpg_adam_pack_chunk* chunks_dev, const int32_t* block_item_dev,
+                       const int32_t* block_first_dev, int32_t n_blocks, void* stream);
 
 /* The first half of fpg_adam_step_dev alone: advance state[0] and refresh the bias-correction scalars. */
 int fpg_adam_prepare_dev(int32_t* state, float beta1, float beta2, void* stream);

@@ -356,6 +356,94 @@ def test_adam_matches_torch():
         torch.testing.assert_close(p, ref_p.detach(), rtol=1e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("family", ["pairedattention", "pix2pix"])
+def test_fused_adam_and_repack_equals_the_two_launches(family):
+    """fpg_adam_pack_step (Adam + every bf16 operand layout + padded bias vectors in one launch) against
+    fpg_adam_step_dev followed by fpg_pack_weights_batched: parameters, both moments and every packed operand
+    bit-identical over three steps, also with the gradient given as three sources summed in order."""
+    from fpgan import networks, ops
+    from fpgan.trainer import FlatParams
+    from models import model_architectures as A
+    import ctypes as C
+
+    def build():
+        torch.manual_seed(5)
+        if family == "pix2pix":
+            mods = [A.Pix2PixGenerator(9).cuda(), A.Pix2PixDiscriminator(9).cuda()]
+        else:
+            mods = [A.PairedAttentionGenerator(9).cuda(), A.PairedAttentionDiscriminator(9).cuda()]
+        fp = FlatParams(*mods)
+        return fp, [m._executor() for m in mods]
+
+    fa, ea = build()
+    fb, eb = build()
+    assert torch.equal(fa.flat, fb.flat)
+    fused = networks.AdamPack(fb, eb)
+    for ex in ea:
+        ex.repack(force=True)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for step in range(3):
+        parts = [torch.randn(fa.flat.shape, device="cuda", generator=g) * 10.0 ** (step - 2) for _ in range(3)]
+        total = (parts[0] + parts[1]) + parts[2]
+        fa.set_lr(2e-4)
+        fb.set_lr(2e-4)
+        fa.grads.flat.copy_(total)
+        fa.adam(grad_scale=0.5)
+        for ex in ea:
+            ex.repack(force=True)
+        if step == 1:
+            srcs = (C.c_void_p * 3)(*[t.data_ptr() for t in parts])
+            gsum = torch.empty_like(total)
+            fused.run(0.5, sources=srcs, n_src=3, gsum=gsum)
+            assert torch.equal(gsum, total)
+        else:
+            fb.grads.flat.copy_(total)
+            fused.run(0.5)
+        torch.cuda.synchronize()
+        assert torch.equal(fa.flat, fb.flat) and torch.equal(fa.m, fb.m) and torch.equal(fa.v, fb.v), step
+        assert torch.equal(fa.state, fb.state)
+        for xa, xb in zip(ea, eb):
+            for name, la in xa.layers.items():
+                lb = xb.layers[name]
+                assert torch.equal(la.spec.w_fprop, lb.spec.w_fprop), (step, name, "fprop operand")
+                assert torch.equal(la.spec.w_dgrad, lb.spec.w_dgrad), (step, name, "dgrad operand")
+                if la.use_bias:
+                    assert torch.equal(la.bias_pad, lb.bias_pad), (step, name, "bias")
+
+
+@pytest.mark.parametrize("shape", [(3, 64, 96), (2, 256, 256)])
+def test_space_to_depth_stem_matches_the_strided_convolution(shape, monkeypatch):
+    """(opt-in experiment, FPG_S2D_STEM=1) The PatchGAN stem (4x4 stride 2 pad 1 over 16 channels) as a 2x2 stride-1 convolution over the space-to-depth
+    copy of its input: the copy is exact, the operand is a tap permutation of the ordinary one, and the outputs of both
+    formulations agree with each other (fp32 accumulation order differs: a few bf16 roundings) and with torch."""
+    from fpgan import ops
+    from models import model_architectures as A
+    n, h, w = shape
+    monkeypatch.setenv("FPG_S2D_STEM", "1")
+    torch.manual_seed(3)
+    D = A.PairedAttentionDiscriminator(9).cuda()
+    ex = D._executor()
+    ex.repack()
+    layer = ex.layers["model.0"]
+    assert layer.s2d_spec is not None
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = bf16r(torch.randn(n, 12, h, w, device="cuda", generator=g))
+    din = ops.ActBuf(n, h, w, 16, zero=False)
+    ops.pack_nchw(x, din, 0, zero_rest=True)
+    y_s2d, xs = ex._stem_conv(din, "model.0", ops.ACT_LEAKY)
+    assert xs is not None and tuple(xs.t.shape) == (n, h // 2 + 1, w // 2 + 1, 64)
+    padded = F.pad(din.t, (0, 0, 1, 1, 1, 1))  # zero ring: pixel (y, x) sits at (y + 1, x + 1)
+    blocks = padded.reshape(n, h // 2 + 1, 2, w // 2 + 1, 2, 16).permute(0, 1, 3, 2, 4, 5).reshape(xs.t.shape)
+    assert torch.equal(xs.t, blocks)
+    wf = layer.spec.w_fprop.view(64, 4, 4, 16)            # [k][r][s][c]
+    w2 = layer.s2d_spec.w_fprop.view(64, 2, 2, 2, 2, 16)  # [k][ty][tx][i][j][c]
+    assert torch.equal(w2, wf.view(64, 2, 2, 2, 2, 16).permute(0, 1, 3, 2, 4, 5))  # r = 2 ty + i, s = 2 tx + j
+    y_ref = ex._conv(din, "model.0", act=ops.ACT_LEAKY)
+    close_rms(y_s2d.t, y_ref.t, 2e-2, 1e-3, "space-to-depth vs strided kernel")
+    ref = F.leaky_relu(F.conv2d(x, bf16r(D.model[0].weight.detach()), D.model[0].bias.detach(), stride=2, padding=1), 0.2)
+    close_rms(y_s2d.to_nchw(64), ref, 2e-2, 2e-3, "space-to-depth stem vs torch")
+
+
 def test_pack_unpack_bias_grad():
     from fpgan import ops
     g = torch.Generator(device="cuda").manual_seed(19)
