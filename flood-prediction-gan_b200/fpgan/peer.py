@@ -33,8 +33,7 @@ def supported(group=None):
     world = dist.get_world_size(group)
     if world < 2 or world > MAX_WORLD or not torch.cuda.is_available():
         return False
-    mode = os.environ.get("FPG_DDP", "peer")
-    ok = mode != "nccl" and torch.cuda.device_count() >= world
+    ok = os.environ.get("FPG_DDP", "auto") != "nccl" and torch.cuda.device_count() >= world
     dev = torch.cuda.current_device()
     if ok:
         # one process per GPU of ONE node (torchrun --nnodes=1): the ranks own devices 0..W-1 of this node

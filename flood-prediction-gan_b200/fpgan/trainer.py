@@ -169,16 +169,19 @@ def optimiser_step(fp, reducer, fused, nets, grad_scale):
 
 
 def make_reducers(world_size, group, *flat_params, overlappable=True):
-    """One gradient reducer per optimiser for data-parallel training, None each for a single process. Where the
-    backward pass can hide the transfers (`overlappable`): the copy-engine exchange over peer memory (peer.PeerReducer)
-    when every rank can map the others' memory (one NVSwitch / NVLink box); FPG_DDP=nccl or no peer access -> NCCL
-    all-reduces (_BucketReducer). Where nothing can be hidden (train_cycle: every network runs 2-3 times per step and
-    its gradient is complete only after the last run) an all-reduce is the right collective -- it moves 2(W-1)/W of
-    the buffer per rank, the all-gather W-1 times -- so those steps use NCCL (NVLS in-switch reduction) unless
-    FPG_DDP=peer asks otherwise."""
+    """One gradient reducer per optimiser for data-parallel training, None each for a single process.
+    FPG_DDP=peer: the copy-engine exchange over peer memory (peer.PeerReducer; needs every rank to map the others'
+    memory: one NVSwitch / NVLink box); FPG_DDP=nccl: NCCL all-reduces (_BucketReducer). Default (auto): the peer
+    exchange where the backward pass can hide its transfers (`overlappable`: the paired steps) AND the world is small
+    (<= 4 ranks) -- its cost grows with the world size (W - 1 pushes per bucket, W gradient sources read by Adam:
+    measured on 8 x B200 10.01 ms per step against 9.96 ms with NCCL's in-switch reduction, on 2 x B200 9.66-9.77 ms
+    against 9.79-9.86 ms), while an NVLS all-reduce costs about the same at any size. Where nothing can be hidden
+    (train_cycle: every network runs 2-3 times per step and its gradient is complete only after the last run) an
+    all-reduce is the right collective -- it moves 2(W-1)/W of the buffer per rank, the all-gather W-1 times it."""
     if world_size <= 1:
         return [None] * len(flat_params)
-    want_peer = overlappable or os.environ.get("FPG_DDP", "") == "peer"
+    mode = os.environ.get("FPG_DDP", "auto")
+    want_peer = mode == "peer" or (mode == "auto" and overlappable and world_size <= 4)
     if want_peer and peer.supported(group):
         return [peer.PeerReducer(fp, group=group) for fp in flat_params]
     return [_BucketReducer(fp, group=group) for fp in flat_params]
