@@ -113,6 +113,40 @@ def test_oracle_forward_matches_live_reference_modules():
         torch.testing.assert_close(O.patchgan_forward(p, xd), d(xd), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference sources not present")
+def test_pix2pix_oracle_matches_live_reference_modules_at_batch_2():
+    """BatchNorm over a batch of TWO (the goldens step at batch 1) and dropout from the same seeded RNG: the oracle's
+    Pix2Pix U-Net and BatchNorm PatchGAN against the live reference modules in training mode, running statistics
+    included."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_model_architectures",
+                                                  "/root/reference/models/model_architectures.py")
+    ref_arch = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_arch)
+    torch.manual_seed(5)
+    g, d = ref_arch.Pix2PixGenerator(9), ref_arch.Pix2PixDiscriminator(9)
+    g.train()
+    d.train()
+    pg = {k: v.detach().clone() for k, v in g.state_dict().items()}
+    pd = {k: v.detach().clone() for k, v in d.state_dict().items()}
+    x = torch.rand(2, 9, 256, 256) * 2 - 1
+    xd = torch.rand(2, 12, 256, 256) * 2 - 1
+    with torch.no_grad():
+        torch.manual_seed(11)
+        want = g(x)
+        torch.manual_seed(11)
+        got = O.pix2pix_generator_forward(pg, x)
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(O.patchgan_bn_forward(pd, xd), d(xd), rtol=1e-4, atol=1e-5)
+    for params, module in ((pg, g), (pd, d)):
+        sd = module.state_dict()
+        for k, v in params.items():
+            if "running_" in k:
+                torch.testing.assert_close(v, sd[k], rtol=1e-4, atol=1e-6, msg=k)
+            if "num_batches" in k:
+                assert int(v) == int(sd[k]) == 1, k
+
+
 def test_pix2pix_oracle_matches_reference_golden():
     """Pix2Pix (BASELINE.json configs[0]): 8-level U-Net with BatchNorm in training mode, in-place activations feeding
     the skip connections and dropout from the torch RNG seeded per epoch (model.py:609)."""
